@@ -1,0 +1,93 @@
+"""Pins the CPU restatement (oracle/mcac_oracle.cpp) against the UNMODIFIED reference.
+
+The golden fixtures are traces of oracle/_ref/MCAC_tap (the reference's own sources compiled from
+/root/reference with link-time taps; tests/golden/make_golden.py).  Bar: BIT-EXACT on every field — same
+machine, same glibc / libstdc++, no FMA contraction — for all five BASELINE configs plus caps / scaled variants.
+"""
+import numpy as np
+import pytest
+
+import ref_trace as rt
+from golden_lib import SEARCH_KEYS, Golden, digest_from_oracle_records
+from oracle_lib import Oracle
+
+FIXTURES = ["pytest_seed42", "monodisperse_seed42", "polydisperse_seed42", "brownian_seed42", "surface_growth_seed42",
+            "caps_seed7", "classic_seed1000", "c2_small_seed42", "c3_small_seed42"]
+
+
+def assert_state_equal(got: dict, ref: dict, tag: str):
+    for k in rt.SPHERE_FIELDS:
+        np.testing.assert_array_equal(got["spheres"][k], ref["spheres"][k], err_msg=f"{tag}: sphere {k}")
+    for k in rt.AGG_FIELDS:
+        if k == "electric_charge_field":  # storage column the reference never writes (aggregat_storage.cpp:25-46)
+            continue
+        np.testing.assert_array_equal(got["aggregates"][k], ref["aggregates"][k], err_msg=f"{tag}: aggregate {k}")
+    for k in ["sphere_label", "sphere_charge", "agg_n_spheres", "agg_charge", "members", "offsets", "agg_cell",
+              "member_volumes", "member_surfaces", "member_distances_center"]:
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{tag}: {k}")
+    for k in rt.SCALARS:
+        assert got[k] == ref[k], f"{tag}: scalar {k}: {got[k]!r} != {ref[k]!r}"
+
+
+def run_like_reference(g: Golden, n_steps: int, partial_last: bool) -> tuple[Oracle, np.ndarray]:
+    o = Oracle(g.base, g.overrides)
+    if partial_last:
+        recs = o.run(n_steps - 1)
+        recs = np.concatenate([recs, o.run_partial_step()])
+    else:
+        recs = o.run(n_steps)
+    return o, recs
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_full_trace(name):
+    g = Golden(name)
+    total = g.meta["total_steps"]
+    o = Oracle(g.base, g.overrides)
+    assert_state_equal(o.state(), g.state("state_init"), "initial state (a23 placement, enforce_volume_fraction)")
+    if g.meta["bounded"]:
+        recs = np.concatenate([o.run(total - 1), o.run_partial_step()])
+    else:
+        recs = o.run(total + 10)
+        assert o.finished
+    assert len(recs) == total
+    with_coll = len(g.searches) > 0
+    k = len(g.steps)
+    if with_coll:
+        for f in SEARCH_KEYS:
+            a, b = recs[f][:k], g.searches[f]
+            np.testing.assert_array_equal(a, b, err_msg=f"search tap field {f}")
+    for f, src in [("label", "source"), ("dt", "dt"), ("proper_time", "proper_time"), ("pos", "pos"), ("lpm", "full_distance")]:
+        np.testing.assert_array_equal(recs[src][:k], g.steps[f], err_msg=f"step tap field {f}")
+    # every record of the whole run, through the digest
+    assert digest_from_oracle_records(recs, with_coll) == g.meta["digest"]
+    merged_steps = np.nonzero(recs["merged"])[0]
+    np.testing.assert_array_equal(merged_steps, g.merges["step"][g.merges["ok"] == 1])
+    assert_state_equal(o.state(), g.state("state_final"), "final state")
+    c, s = o.counters(), g.meta["summary"]
+    assert c["rand_calls"] == s["rand_calls"]
+    if not g.meta["bounded"]:
+        assert c["pair_sphere"] == s["pair_tests_sphere"] and c["pair_bounding"] == s["pair_tests_bounding"]
+
+
+@pytest.mark.parametrize("name", ["pytest_seed42", "monodisperse_seed42", "surface_growth_seed42", "classic_seed1000",
+                                  "c3_small_seed42"])
+def test_mid_run_snapshots(name):
+    g = Golden(name)
+    for s in g.meta["state_steps"]:
+        if s > 60000 or s >= g.meta["total_steps"]:
+            continue
+        o, _ = run_like_reference(g, s + 1, partial_last=True)  # tap dumps inside time_forward of step s
+        assert_state_equal(o.state(), g.state(f"state_{s}"), f"snapshot after the move of step {s}")
+
+
+@pytest.mark.parametrize("name", ["monodisperse_seed42", "polydisperse_seed42", "c3_small_seed42"])
+def test_pick_table_matches_std_sort_of_reference(name):
+    """index_sorted_time_steps / cumulative_time_steps after the first sort_time_steps call (H3: tie order)."""
+    g = Golden(name)
+    srt = g.sort(0)
+    o = Oracle(g.base, g.overrides)
+    o.run(1)
+    idx, cum = o.pick_table()
+    np.testing.assert_array_equal(idx, srt["idx"])
+    np.testing.assert_array_equal(cum, srt["cum"])
