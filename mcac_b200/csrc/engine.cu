@@ -1,0 +1,1077 @@
+// mcac_b200 — engine: device memory of one realization, launch orchestration, and the C ABI (include/mcac_b200.h).
+//
+// Host code here only sequences kernels and moves state across the PCIe boundary; all per-step arithmetic of the
+// hot path runs in the kernels of mcac_kernels.cuh.  There is no CPU fallback: every entry point fails with
+// UNKNOWN_ERROR when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/mcac_b200.h"
+#include "mcac_kernels.cuh"
+
+using namespace mcacb;
+
+namespace {
+constexpr int kRngBuf = 31 * 33826;  // ~1.05 M draws, multiple of 31
+enum { E_OK = 0, E_UNKNOWN = 1, E_IO = 2, E_VERLET = 3, E_INPUT = 4, E_MERGE = 9 };
+
+struct Buf {  // raw device allocation
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+// Host-side image of a realization in the reference's own layout (label / creation order); used at the
+// upload / download boundary and by the (rare, host-orchestrated) domain duplication.
+struct HostState {
+    long long n_sph = 0, n_agg = 0;
+    std::vector<double> sph;        // 9 x n_sph field-major
+    std::vector<long long> sph_label, sph_charge;
+    std::vector<double> agg;        // 21 x n_agg field-major
+    std::vector<long long> agg_n, agg_charge, agg_cells, offsets, members;
+    std::vector<double> per_member;  // 3 x n_sph
+    double scalars[20] = {0};
+};
+}  // namespace
+
+struct mcac_gpu {
+    mcac_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    DevState d{};
+    DevState alt{};  // alternate sphere buffers for pool compaction (only s_* pointers used)
+    std::vector<void *> owned;       // size-dependent allocations (re-made by upload / duplication)
+    std::vector<void *> persistent;  // RNG stream, scalars, batch scratch: live as long as the handle
+    Scalars *h_sc = nullptr;  // pinned mirror
+    Scalars sc_host{};
+    // scratch
+    int *q_slot = nullptr;
+    double *q_dir = nullptr, *q_dist = nullptr;
+    long long *q_label = nullptr;
+    SearchResult *q_res = nullptr;
+    int *scan_tmp = nullptr, *scan_out = nullptr, *block_sums = nullptr, *sorted_label = nullptr, *merged_flag = nullptr;
+    double *partials = nullptr, *stats_dev = nullptr;
+    mcac_step_record *rec_dev = nullptr;
+    long long rec_cap = 0;
+    long long rng_generated = 0;  // stream position after the last generated draw
+    long long dup_threshold = 0;
+    bool labels_valid = false, pick_valid = false, cells_valid = false, uploaded = false;
+    long long launches = 0;
+    int n_sm = 148;
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return E_UNKNOWN;                                                                     \
+        }                                                                                         \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ != E_OK) return r_; \
+    } while (0)
+
+namespace {
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+int dev_alloc(mcac_gpu *h, T **p, size_t n) {
+    void *q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    h->owned.push_back(q);
+    *p = (T *)q;
+    return E_OK;
+}
+template <class T>
+int dev_alloc_persistent(mcac_gpu *h, T **p, size_t n) {
+    void *q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    h->persistent.push_back(q);
+    *p = (T *)q;
+    return E_OK;
+}
+void free_all(mcac_gpu *h) {
+    for (void *p : h->owned) cudaFree(p);
+    h->owned.clear();
+}
+int alloc_persistent(mcac_gpu *h) {
+    DevState &d = h->d;
+    TRY(dev_alloc_persistent(h, &d.rng, 1));
+    TRY(dev_alloc_persistent(h, &d.rng_buf, kRngBuf + 64));
+    TRY(dev_alloc_persistent(h, &d.sc, 1));
+    TRY(dev_alloc_persistent(h, &h->q_slot, kMaxBatch));
+    TRY(dev_alloc_persistent(h, &h->q_dir, 3 * kMaxBatch));
+    TRY(dev_alloc_persistent(h, &h->q_dist, kMaxBatch));
+    TRY(dev_alloc_persistent(h, &h->q_label, kMaxBatch));
+    TRY(dev_alloc_persistent(h, &h->q_res, kMaxBatch));
+    TRY(dev_alloc_persistent(h, &h->partials, 3 * 1024));
+    TRY(dev_alloc_persistent(h, &h->merged_flag, 4));
+    TRY(dev_alloc_persistent(h, &h->stats_dev, 4096));
+    h->alt.sc = d.sc;
+    return E_OK;
+}
+
+int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
+    DevState &d = h->d;
+    d.agg_cap = (int)agg_cap;
+    d.sph_cap = (int)sph_cap;
+    for (DevState *t : {&h->d, &h->alt}) {
+        TRY(dev_alloc(h, &t->s_posr, sph_cap));
+        TRY(dev_alloc(h, &t->s_relv, sph_cap));
+        TRY(dev_alloc(h, &t->s_surf, sph_cap));
+        TRY(dev_alloc(h, &t->s_veff, sph_cap));
+        TRY(dev_alloc(h, &t->s_seff, sph_cap));
+        TRY(dev_alloc(h, &t->s_dcen, sph_cap));
+        TRY(dev_alloc(h, &t->s_id, sph_cap));
+        TRY(dev_alloc(h, &t->s_charge, sph_cap));
+    }
+    TRY(dev_alloc(h, &d.slot_of_id, sph_cap));
+    TRY(dev_alloc(h, &d.a_posr, agg_cap));
+    for (double **p : {&d.a_rg, &d.a_fagg, &d.a_lpm, &d.a_ts, &d.a_vol, &d.a_surf, &d.a_rx, &d.a_ry, &d.a_rz, &d.a_ptime, &d.a_dp,
+                       &d.a_dgdp, &d.a_ovl, &d.a_cn, &d.a_dm, &d.a_ch, &d.a_bulk, &d.a_alpha, &d.cum, &d.keys})
+        TRY(dev_alloc(h, p, agg_cap));
+    for (int **p : {&d.a_n, &d.a_off, &d.a_cx, &d.a_cy, &d.a_cz, &d.a_charge, &d.a_alive, &d.label_of_slot, &d.slot_of_label,
+                    &d.sorted_slot, &d.cell_items, &h->sorted_label})
+        TRY(dev_alloc(h, p, agg_cap));
+    TRY(dev_alloc(h, &d.cell_start, (size_t)d.n_cells + 1));
+    TRY(dev_alloc(h, &d.cell_fill, (size_t)d.n_cells + 1));
+    const size_t scan_n = (size_t)std::max<long long>(agg_cap, d.n_cells) + 2;
+    TRY(dev_alloc(h, &h->scan_tmp, scan_n));
+    TRY(dev_alloc(h, &h->scan_out, scan_n));
+    TRY(dev_alloc(h, &h->block_sums, scan_n / (kScanBlock * kScanItems) + 8));
+    return E_OK;
+}
+
+// deterministic exclusive scan of n ints (in -> out[0..n], out[n] = total)
+int scan_ints(mcac_gpu *h, const int *in, int n, int *out) {
+    const int per = kScanBlock * kScanItems;
+    const int nb = std::max(1, div_up(n, per));
+    k_scan_partials<<<nb, kScanBlock, 0, h->stream>>>(in, n, h->block_sums);
+    k_scan_block_sums<<<1, 1024, 0, h->stream>>>(h->block_sums, nb);
+    k_scan_apply<<<nb, kScanBlock, 0, h->stream>>>(in, n, h->block_sums, nb, out);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return E_OK;
+}
+
+int pull_scalars(mcac_gpu *h) {
+    CK(cudaMemcpyAsync(h->h_sc, h->d.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->sc_host = *h->h_sc;
+    return E_OK;
+}
+int push_scalars(mcac_gpu *h) {
+    *h->h_sc = h->sc_host;
+    CK(cudaMemcpyAsync(h->d.sc, h->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return E_OK;
+}
+
+int refresh_labels(mcac_gpu *h) {
+    if (h->labels_valid) return E_OK;
+    const int n = h->sc_host.n_agg_slots;
+    TRY(scan_ints(h, h->d.a_alive, n, h->scan_out));
+    k_alive_to_labels<<<div_up(n, 256), 256, 0, h->stream>>>(h->d, h->scan_out);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->labels_valid = true;
+    return E_OK;
+}
+
+// K2: counting sort of live aggregates into their stored Verlet cells
+int build_cells(mcac_gpu *h) {
+    if (h->cells_valid) return E_OK;
+    DevState &d = h->d;
+    const int n = h->sc_host.n_agg_slots;
+    CK(cudaMemsetAsync(d.cell_fill, 0, sizeof(int) * ((size_t)d.n_cells + 1), h->stream));
+    k_cell_count<<<div_up(n, 256), 256, 0, h->stream>>>(d);
+    h->launches++;
+    TRY(scan_ints(h, d.cell_fill, d.n_cells, d.cell_start));
+    CK(cudaMemsetAsync(d.cell_fill, 0, sizeof(int) * ((size_t)d.n_cells + 1), h->stream));
+    k_cell_scatter<<<div_up(n, 256), 256, 0, h->stream>>>(d);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->cells_valid = true;
+    return E_OK;
+}
+
+int refresh_reduce(mcac_gpu *h) {
+    const int nb = std::min(1024, std::max(1, div_up(h->sc_host.n_agg_slots, kReduceThreads)));
+    k_refresh_partials<<<nb, kReduceThreads, 0, h->stream>>>(h->d, h->partials);
+    k_refresh_final<<<1, 32, 0, h->stream>>>(h->d, h->partials, nb);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return E_OK;
+}
+
+// AggregatList::sort_time_steps (aggregat_list.cpp:124-141).  The 1/dt weights are computed on the device in label
+// order.  MCAC_ORDER_LIBSTDCXX reproduces the reference's std::sort (introsort) order among EQUAL weights, which
+// decides the pick in monodisperse runs: the index sort is done by libstdc++'s std::sort itself on the
+// host (the very routine the reference calls; it runs only on events), together with the sequential prefix sum.
+int sort_time_steps(mcac_gpu *h, double factor) {
+    DevState &d = h->d;
+    TRY(refresh_labels(h));
+    const int n = h->sc_host.n_agg;
+    k_make_keys<<<div_up(n, 256), 256, 0, h->stream>>>(d, factor);
+    h->launches++;
+    std::vector<double> keys((size_t)n), cum((size_t)n);
+    CK(cudaMemcpyAsync(keys.data(), d.keys, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<int> idx((size_t)n);
+    std::iota(idx.begin(), idx.end(), 0);
+    if (h->prm.sort_order == MCAC_ORDER_LIBSTDCXX) {
+        std::vector<size_t> idx64((size_t)n);
+        std::iota(idx64.begin(), idx64.end(), 0);
+        std::sort(idx64.begin(), idx64.end(), [&keys](size_t a, size_t b) { return keys[a] < keys[b]; });
+        for (int i = 0; i < n; i++) idx[(size_t)i] = (int)idx64[(size_t)i];
+    } else {
+        std::stable_sort(idx.begin(), idx.end(), [&keys](int a, int b) { return keys[(size_t)a] < keys[(size_t)b]; });
+    }
+    cum[0] = keys[(size_t)idx[0]];
+    for (int i = 1; i < n; i++) cum[(size_t)i] = cum[(size_t)i - 1] + keys[(size_t)idx[(size_t)i]];
+    CK(cudaMemcpyAsync(h->sorted_label, idx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.cum, cum.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    k_sorted_labels_to_slots<<<div_up(n, 256), 256, 0, h->stream>>>(d, h->sorted_label, n);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->sc_host.n_pick = n;
+    h->sc_host.cum_total = cum[(size_t)n - 1];
+    h->pick_valid = true;
+    return E_OK;
+}
+
+int ensure_rng(mcac_gpu *h, long long need_until) {  // draws [rand_pos, need_until) must be in rng_buf
+    DevState &d = h->d;
+    const long long pos = h->sc_host.rand_pos;
+    if (need_until <= h->rng_generated && pos >= d.rng_buf_base) return E_OK;
+    const long long keep = std::max<long long>(0, h->rng_generated - pos);  // generated but unconsumed
+    if (keep > 0 && pos > d.rng_buf_base) {
+        std::vector<int> tmp((size_t)keep);
+        CK(cudaMemcpyAsync(tmp.data(), d.rng_buf + (pos - d.rng_buf_base), sizeof(int) * keep, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpyAsync(d.rng_buf, tmp.data(), sizeof(int) * keep, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    d.rng_buf_base = pos;
+    long long room = kRngBuf - keep;
+    room -= room % 31;
+    k_rng_fill<<<1, 32, 0, h->stream>>>(d.rng, d.rng_buf + keep, (int)room);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->rng_generated = pos + keep + room;
+    d.rng_buf_n = (int)(keep + room);
+    return E_OK;
+}
+
+int compact_pool(mcac_gpu *h) {
+    DevState &d = h->d;
+    const int n = h->sc_host.n_agg_slots;
+    k_compact_counts<<<div_up(n, 256), 256, 0, h->stream>>>(d, h->scan_tmp);
+    TRY(scan_ints(h, h->scan_tmp, n, h->scan_out));
+    k_compact_move<<<div_up(n, 8), 256, 0, h->stream>>>(d, h->alt, h->scan_out);
+    k_compact_finish<<<1, 32, 0, h->stream>>>(d, h->scan_out);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    std::swap(d.s_posr, h->alt.s_posr);
+    std::swap(d.s_relv, h->alt.s_relv);
+    std::swap(d.s_surf, h->alt.s_surf);
+    std::swap(d.s_veff, h->alt.s_veff);
+    std::swap(d.s_seff, h->alt.s_seff);
+    std::swap(d.s_dcen, h->alt.s_dcen);
+    std::swap(d.s_id, h->alt.s_id);
+    std::swap(d.s_charge, h->alt.s_charge);
+    TRY(pull_scalars(h));
+    return E_OK;
+}
+
+int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_step, bool keep_scalars);
+int download(mcac_gpu *h, HostState &s);
+
+// AggregatList::duplication (aggregat_list.cpp:142-190): box x2, 7 translated copies of every aggregate appended in
+// (i,j,k) order, Verlet rebuilt.  Rare (once per 8x drop of N_agg) and purely a re-layout, so it is orchestrated
+// through the download/upload boundary; the copies' positions are produced by the same K3 translate kernel.
+int duplicate(mcac_gpu *h) {
+    HostState s;
+    TRY(download(h, s));
+    const long long n0 = s.n_agg, m0 = s.n_sph;
+    const double old_l = s.scalars[1];
+    HostState t;
+    t.n_agg = 8 * n0;
+    t.n_sph = 8 * m0;
+    t.sph.assign((size_t)(9 * t.n_sph), 0.);
+    t.sph_label.assign((size_t)t.n_sph, 0);
+    t.sph_charge.assign((size_t)t.n_sph, 0);
+    t.agg.assign((size_t)(21 * t.n_agg), 0.);
+    t.agg_n.assign((size_t)t.n_agg, 0);
+    t.agg_charge.assign((size_t)t.n_agg, 0);
+    t.agg_cells.assign((size_t)(3 * t.n_agg), 0);
+    t.offsets.assign((size_t)t.n_agg + 1, 0);
+    t.members.assign((size_t)t.n_sph, 0);
+    t.per_member.assign((size_t)(3 * t.n_sph), 0.);
+    // originals keep label / sphere index; copy c of aggregate a gets label n0 + 7a + c and fresh sphere ids in member order
+    std::vector<long long> src_of((size_t)t.n_agg);
+    std::vector<int> shift((size_t)t.n_agg, 0);
+    for (long long a = 0; a < n0; a++) src_of[(size_t)a] = a;
+    {
+        long long l = n0;
+        for (long long a = 0; a < n0; a++)
+            for (int c = 1; c < 8; c++) { src_of[(size_t)l] = a; shift[(size_t)l] = c; l++; }
+    }
+    for (long long i = 0; i < m0; i++) {
+        for (int f = 0; f < 9; f++) t.sph[(size_t)(f * t.n_sph + i)] = s.sph[(size_t)(f * m0 + i)];
+        t.sph_charge[(size_t)i] = s.sph_charge[(size_t)i];
+    }
+    long long next_id = m0, off = 0;
+    for (long long l = 0; l < t.n_agg; l++) {
+        const long long a = src_of[(size_t)l];
+        for (int f = 0; f < 21; f++) t.agg[(size_t)(f * t.n_agg + l)] = s.agg[(size_t)(f * n0 + a)];
+        t.agg_n[(size_t)l] = s.agg_n[(size_t)a];
+        t.agg_charge[(size_t)l] = (l < n0) ? s.agg_charge[(size_t)a] : 0;  // copy ctor resets the charge (aggregat_storage.cpp:138)
+        t.offsets[(size_t)l] = off;
+        for (long long k = 0; k < s.agg_n[(size_t)a]; k++) {
+            const long long sid = s.members[(size_t)(s.offsets[(size_t)a] + k)];
+            long long nid = sid;
+            if (l >= n0) {
+                nid = next_id++;
+                for (int f = 0; f < 9; f++) t.sph[(size_t)(f * t.n_sph + nid)] = s.sph[(size_t)(f * m0 + sid)];
+                t.sph_charge[(size_t)nid] = 0;
+            }
+            t.members[(size_t)(off + k)] = nid;
+            for (int f = 0; f < 3; f++) t.per_member[(size_t)(f * t.n_sph + off + k)] = s.per_member[(size_t)(f * m0 + s.offsets[(size_t)a] + k)];
+        }
+        off += s.agg_n[(size_t)a];
+    }
+    t.offsets[(size_t)t.n_agg] = off;
+    std::memcpy(t.scalars, s.scalars, sizeof(t.scalars));
+    // new box (aggregat_list.cpp:145-148)
+    h->prm.box_length = old_l * 2;
+    h->prm.n_monomeres *= 8;
+    h->prm.box_volume = std::pow(h->prm.box_length, 3);
+    t.scalars[1] = h->prm.box_length;
+    t.scalars[15] = h->prm.box_volume;
+    t.scalars[17] = (double)h->prm.n_monomeres;
+    Scalars keep = h->sc_host;
+    free_all(h);
+    h->uploaded = false;
+    TRY(upload(h, t, t.scalars[2], t.scalars[3], false));
+    // restore run-time scalars that upload() resets
+    h->sc_host.time = keep.time;
+    h->sc_host.n_iter_without_event = keep.n_iter_without_event;
+    h->sc_host.total_events = keep.total_events;
+    h->sc_host.steps_done = keep.steps_done;
+    h->sc_host.rand_pos = keep.rand_pos;
+    h->sc_host.pair_sphere = keep.pair_sphere;
+    h->sc_host.pair_bounding = keep.pair_bounding;
+    h->sc_host.searches = keep.searches;
+    h->sc_host.conflicts = keep.conflicts;
+    h->sc_host.event = keep.event;
+    h->sc_host.avg_npp = keep.avg_npp;
+    h->sc_host.nucleation_accum = keep.nucleation_accum;
+    TRY(push_scalars(h));
+    // translate the copies with the new box length and recompute every Verlet cell (aggregat_list.cpp:169-183)
+    k_dup_finish<<<div_up(t.n_agg, 8), 256, 0, h->stream>>>(h->d, (int)n0, old_l);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->cells_valid = false;
+    // PhysicalModel::update at the end of duplication (:186-189): totals are unchanged x8, concentrations recomputed
+    TRY(refresh_reduce(h));
+    TRY(pull_scalars(h));
+    h->sc_host.max_time_step = keep.max_time_step;  // duplication does not call refresh()
+    h->sc_host.avg_npp = keep.avg_npp;
+    TRY(push_scalars(h));
+    return E_OK;
+}
+}  // namespace
+
+namespace {
+void fill_devstate_params(mcac_gpu *h) {
+    DevState &d = h->d;
+    const mcac_params &p = h->prm;
+    d.n_div = p.n_verlet_divisions;
+    d.n_cells = p.n_verlet_divisions * p.n_verlet_divisions * p.n_verlet_divisions;
+    d.gas.mean_free_path = p.gaz_mean_free_path;
+    d.gas.viscosity = p.viscosity;
+    d.gas.temperature = p.temperature;
+    d.gas.fractal_dimension = p.fractal_dimension;
+    d.gas.density = p.density;
+    d.gas.with_maturity = p.with_maturity;
+    d.u_sg = p.u_sg;
+    d.rp_min_oxid = p.rp_min_oxid;
+    d.volsurf_method = p.volsurf_method;
+    d.pick_method = p.pick_method;
+    d.with_collisions = p.with_collisions;
+    d.n_iter_limit = p.n_iter_without_event_limit;
+    d.n_agg_limit = p.number_of_aggregates_limit;
+    d.npp_limit = p.mean_monomere_per_aggregate_limit;
+    d.time_limit = p.physical_time_limit;
+}
+
+int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_step, bool keep_scalars) {
+    (void)keep_scalars;
+    DevState &d = h->d;
+    fill_devstate_params(h);
+    const long long n_agg = s.n_agg, n_sph = s.n_sph;
+    if (n_agg <= 0 || n_sph <= 0) { h->err = "upload_state: empty state"; return E_INPUT; }
+    TRY(alloc_state(h, n_agg, 3 * n_sph + 1024));
+    std::vector<double4> posr((size_t)n_sph), relv((size_t)n_sph), aposr((size_t)n_agg);
+    std::vector<double> surf((size_t)n_sph), veff((size_t)n_sph), seff((size_t)n_sph), dcen((size_t)n_sph);
+    std::vector<int> sid((size_t)n_sph), scharge((size_t)n_sph), slot_of_id((size_t)n_sph);
+    auto S = [&](int f, long long i) { return s.sph[(size_t)(f * n_sph + i)]; };
+    auto A = [&](int f, long long a) { return s.agg[(size_t)(f * n_agg + a)]; };
+    for (long long a = 0; a < n_agg; a++) {
+        for (long long k = s.offsets[(size_t)a]; k < s.offsets[(size_t)a + 1]; k++) {
+            const long long id = s.members[(size_t)k];
+            posr[(size_t)k] = make_double4(S(0, id), S(1, id), S(2, id), S(3, id));
+            relv[(size_t)k] = make_double4(S(6, id), S(7, id), S(8, id), S(4, id));
+            surf[(size_t)k] = S(5, id);
+            veff[(size_t)k] = s.per_member[(size_t)k];
+            seff[(size_t)k] = s.per_member[(size_t)(n_sph + k)];
+            dcen[(size_t)k] = s.per_member[(size_t)(2 * n_sph + k)];
+            sid[(size_t)k] = (int)id;
+            scharge[(size_t)k] = (int)s.sph_charge[(size_t)id];
+            slot_of_id[(size_t)id] = (int)k;
+        }
+        aposr[(size_t)a] = make_double4(A(7, a), A(8, a), A(9, a), A(4, a));
+    }
+    auto up = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream); };
+    CK(up(d.s_posr, posr.data(), sizeof(double4) * n_sph));
+    CK(up(d.s_relv, relv.data(), sizeof(double4) * n_sph));
+    CK(up(d.s_surf, surf.data(), sizeof(double) * n_sph));
+    CK(up(d.s_veff, veff.data(), sizeof(double) * n_sph));
+    CK(up(d.s_seff, seff.data(), sizeof(double) * n_sph));
+    CK(up(d.s_dcen, dcen.data(), sizeof(double) * n_sph));
+    CK(up(d.s_id, sid.data(), sizeof(int) * n_sph));
+    CK(up(d.s_charge, scharge.data(), sizeof(int) * n_sph));
+    CK(up(d.slot_of_id, slot_of_id.data(), sizeof(int) * n_sph));
+    CK(up(d.a_posr, aposr.data(), sizeof(double4) * n_agg));
+    // AggregatesFields order: RG,F_AGG,LPM,TIME_STEP,RMAX,VOLUME,SURFACE,X,Y,Z,RX,RY,RZ,TIME,DP,DG_OVER_DP,OVERLAPPING,
+    // COORDINATION_NUMBER,ELECTRIC_CHARGE,D_M,CH_RATIO (include/constants.hpp:46-69)
+    struct { double *dst; int f; } cols[] = {{d.a_rg, 0}, {d.a_fagg, 1}, {d.a_lpm, 2}, {d.a_ts, 3}, {d.a_vol, 5}, {d.a_surf, 6}, {d.a_rx, 10},
+                                              {d.a_ry, 11}, {d.a_rz, 12}, {d.a_ptime, 13}, {d.a_dp, 14}, {d.a_dgdp, 15}, {d.a_ovl, 16},
+                                              {d.a_cn, 17}, {d.a_dm, 19}, {d.a_ch, 20}};
+    for (auto &c : cols) CK(up(c.dst, s.agg.data() + (size_t)c.f * n_agg, sizeof(double) * n_agg));
+    std::vector<double> bulk((size_t)n_agg, h->prm.density), alpha((size_t)n_agg);
+    std::vector<int> an((size_t)n_agg), aoff((size_t)n_agg), cx((size_t)n_agg), cy((size_t)n_agg), cz((size_t)n_agg), ach((size_t)n_agg),
+        alive((size_t)n_agg, 1), ident((size_t)n_agg);
+    for (long long a = 0; a < n_agg; a++) {
+        an[(size_t)a] = (int)s.agg_n[(size_t)a];
+        aoff[(size_t)a] = (int)s.offsets[(size_t)a];
+        alpha[(size_t)a] = 1.0 / static_cast<double>(s.agg_n[(size_t)a]);
+        cx[(size_t)a] = (int)s.agg_cells[(size_t)a];
+        cy[(size_t)a] = (int)s.agg_cells[(size_t)(n_agg + a)];
+        cz[(size_t)a] = (int)s.agg_cells[(size_t)(2 * n_agg + a)];
+        ach[(size_t)a] = (int)s.agg_charge[(size_t)a];
+        ident[(size_t)a] = (int)a;
+    }
+    CK(up(d.a_bulk, bulk.data(), sizeof(double) * n_agg));
+    CK(up(d.a_alpha, alpha.data(), sizeof(double) * n_agg));
+    CK(up(d.a_n, an.data(), sizeof(int) * n_agg));
+    CK(up(d.a_off, aoff.data(), sizeof(int) * n_agg));
+    CK(up(d.a_cx, cx.data(), sizeof(int) * n_agg));
+    CK(up(d.a_cy, cy.data(), sizeof(int) * n_agg));
+    CK(up(d.a_cz, cz.data(), sizeof(int) * n_agg));
+    CK(up(d.a_charge, ach.data(), sizeof(int) * n_agg));
+    CK(up(d.a_alive, alive.data(), sizeof(int) * n_agg));
+    CK(up(d.label_of_slot, ident.data(), sizeof(int) * n_agg));
+    CK(up(d.slot_of_label, ident.data(), sizeof(int) * n_agg));
+    CK(cudaStreamSynchronize(h->stream));
+    Scalars &sc = h->sc_host;
+    const Scalars old = sc;
+    std::memset(&sc, 0, sizeof(sc));
+    sc.time = h->prm.time;
+    sc.box_length = h->prm.box_length;
+    sc.box_volume = h->prm.box_volume;
+    sc.maxradius = maxradius;
+    sc.max_time_step = max_time_step;
+    sc.avg_npp = static_cast<double>(n_sph) / static_cast<double>(n_agg);
+    sc.nucleation_accum = h->prm.nucleation_accum;
+    sc.n_monomeres = h->prm.n_monomeres;
+    sc.n_agg = sc.n_agg_slots = (int)n_agg;
+    sc.n_sph = sc.pool_top = (int)n_sph;
+    sc.event = 1;
+    sc.rand_pos = old.rand_pos;
+    sc.aggregate_concentration = static_cast<double>(n_agg) / sc.box_volume;
+    sc.monomer_concentration = static_cast<double>(n_sph) / sc.box_volume;
+    TRY(push_scalars(h));
+    h->labels_valid = true;
+    h->pick_valid = false;
+    h->cells_valid = false;
+    h->uploaded = true;
+    return E_OK;
+}
+
+int download(mcac_gpu *h, HostState &s) {
+    DevState &d = h->d;
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    const Scalars &sc = h->sc_host;
+    const long long n_agg = sc.n_agg, n_sph = sc.n_sph, n_slots = sc.n_agg_slots, pool = sc.pool_top;
+    s.n_agg = n_agg;
+    s.n_sph = n_sph;
+    std::vector<double4> posr((size_t)pool), relv((size_t)pool), aposr((size_t)n_slots);
+    std::vector<double> surf((size_t)pool), veff((size_t)pool), seff((size_t)pool), dcen((size_t)pool);
+    std::vector<int> sid((size_t)pool), scharge((size_t)pool), an((size_t)n_slots), aoff((size_t)n_slots), cx((size_t)n_slots),
+        cy((size_t)n_slots), cz((size_t)n_slots), ach((size_t)n_slots), slot_of_label((size_t)n_slots);
+    auto dn = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream); };
+    CK(dn(posr.data(), d.s_posr, sizeof(double4) * pool));
+    CK(dn(relv.data(), d.s_relv, sizeof(double4) * pool));
+    CK(dn(surf.data(), d.s_surf, sizeof(double) * pool));
+    CK(dn(veff.data(), d.s_veff, sizeof(double) * pool));
+    CK(dn(seff.data(), d.s_seff, sizeof(double) * pool));
+    CK(dn(dcen.data(), d.s_dcen, sizeof(double) * pool));
+    CK(dn(sid.data(), d.s_id, sizeof(int) * pool));
+    CK(dn(scharge.data(), d.s_charge, sizeof(int) * pool));
+    CK(dn(aposr.data(), d.a_posr, sizeof(double4) * n_slots));
+    CK(dn(an.data(), d.a_n, sizeof(int) * n_slots));
+    CK(dn(aoff.data(), d.a_off, sizeof(int) * n_slots));
+    CK(dn(cx.data(), d.a_cx, sizeof(int) * n_slots));
+    CK(dn(cy.data(), d.a_cy, sizeof(int) * n_slots));
+    CK(dn(cz.data(), d.a_cz, sizeof(int) * n_slots));
+    CK(dn(ach.data(), d.a_charge, sizeof(int) * n_slots));
+    CK(dn(slot_of_label.data(), d.slot_of_label, sizeof(int) * n_slots));
+    std::vector<std::vector<double>> acol(21, std::vector<double>((size_t)n_slots, 0.));
+    struct { double *src; int f; } cols[] = {{d.a_rg, 0}, {d.a_fagg, 1}, {d.a_lpm, 2}, {d.a_ts, 3}, {d.a_vol, 5}, {d.a_surf, 6}, {d.a_rx, 10},
+                                              {d.a_ry, 11}, {d.a_rz, 12}, {d.a_ptime, 13}, {d.a_dp, 14}, {d.a_dgdp, 15}, {d.a_ovl, 16},
+                                              {d.a_cn, 17}, {d.a_dm, 19}, {d.a_ch, 20}};
+    for (auto &c : cols) CK(dn(acol[(size_t)c.f].data(), c.src, sizeof(double) * n_slots));
+    CK(cudaStreamSynchronize(h->stream));
+    s.sph.assign((size_t)(9 * n_sph), 0.);
+    s.sph_label.assign((size_t)n_sph, -1);
+    s.sph_charge.assign((size_t)n_sph, 0);
+    s.agg.assign((size_t)(21 * n_agg), 0.);
+    s.agg_n.assign((size_t)n_agg, 0);
+    s.agg_charge.assign((size_t)n_agg, 0);
+    s.agg_cells.assign((size_t)(3 * n_agg), 0);
+    s.offsets.assign((size_t)n_agg + 1, 0);
+    s.members.assign((size_t)n_sph, 0);
+    s.per_member.assign((size_t)(3 * n_sph), 0.);
+    long long off = 0;
+    for (long long l = 0; l < n_agg; l++) {
+        const int slot = slot_of_label[(size_t)l];
+        const int n = an[(size_t)slot], o = aoff[(size_t)slot];
+        s.offsets[(size_t)l] = off;
+        if (off + n > n_sph) { h->err = "download_state: membership exceeds the sphere count"; return E_UNKNOWN; }
+        for (int k = 0; k < n; k++) {
+            const int t = o + k;
+            const long long id = sid[(size_t)t];
+            const double v[9] = {posr[(size_t)t].x, posr[(size_t)t].y, posr[(size_t)t].z, posr[(size_t)t].w, relv[(size_t)t].w, surf[(size_t)t],
+                                 relv[(size_t)t].x, relv[(size_t)t].y, relv[(size_t)t].z};
+            for (int f = 0; f < 9; f++) s.sph[(size_t)(f * n_sph + id)] = v[f];
+            s.sph_label[(size_t)id] = l;
+            s.sph_charge[(size_t)id] = scharge[(size_t)t];
+            s.members[(size_t)(off + k)] = id;
+            s.per_member[(size_t)(off + k)] = veff[(size_t)t];
+            s.per_member[(size_t)(n_sph + off + k)] = seff[(size_t)t];
+            s.per_member[(size_t)(2 * n_sph + off + k)] = dcen[(size_t)t];
+        }
+        off += n;
+        for (int f = 0; f < 21; f++) s.agg[(size_t)(f * n_agg + l)] = acol[(size_t)f][(size_t)slot];
+        s.agg[(size_t)(4 * n_agg + l)] = aposr[(size_t)slot].w;
+        s.agg[(size_t)(7 * n_agg + l)] = aposr[(size_t)slot].x;
+        s.agg[(size_t)(8 * n_agg + l)] = aposr[(size_t)slot].y;
+        s.agg[(size_t)(9 * n_agg + l)] = aposr[(size_t)slot].z;
+        s.agg_n[(size_t)l] = n;
+        s.agg_charge[(size_t)l] = ach[(size_t)slot];
+        s.agg_cells[(size_t)l] = cx[(size_t)slot];
+        s.agg_cells[(size_t)(n_agg + l)] = cy[(size_t)slot];
+        s.agg_cells[(size_t)(2 * n_agg + l)] = cz[(size_t)slot];
+    }
+    s.offsets[(size_t)n_agg] = off;
+    const double sv[20] = {sc.time, sc.box_length, sc.maxradius, sc.max_time_step, sc.avg_npp, sc.volume_fraction, sc.aggregate_concentration,
+                           sc.monomer_concentration, sc.total_volume_concent, sc.total_surface_concent, h->prm.u_sg, h->prm.gaz_mean_free_path,
+                           0., 0., h->prm.viscosity, sc.box_volume, (double)sc.n_iter_without_event, (double)sc.n_monomeres,
+                           h->prm.temperature, sc.nucleation_accum};
+    std::memcpy(s.scalars, sv, sizeof(sv));
+    return E_OK;
+}
+
+// PhysicalModel::finished (physical_model.cpp:288-337) on the mirrored scalars; wall-clock limits are not part of the path
+bool finished(const mcac_gpu *h) {
+    const Scalars &sc = h->sc_host;
+    const mcac_params &p = h->prm;
+    if (sc.n_agg < 1) return true;
+    if (sc.n_agg <= p.number_of_aggregates_limit) return true;
+    if (p.n_iter_without_event_limit > 0 && sc.n_iter_without_event >= p.n_iter_without_event_limit) return true;
+    if (p.physical_time_limit > 0 && sc.time >= p.physical_time_limit) return true;
+    if (p.mean_monomere_per_aggregate_limit > 0 && sc.avg_npp >= (double)p.mean_monomere_per_aggregate_limit) return true;
+    return false;
+}
+
+// what calcul() does between a merge and the next pick: refresh(), PhysicalModel::update, duplication test, re-sort
+int after_event(mcac_gpu *h) {
+    h->labels_valid = false;
+    h->cells_valid = false;
+    TRY(refresh_labels(h));
+    TRY(refresh_reduce(h));
+    TRY(pull_scalars(h));
+    return E_OK;
+}
+
+int search_launch(mcac_gpu *h, int nq) {
+    TRY(build_cells(h));
+    k_search<<<nq, kSearchThreads, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
+    h->launches++;
+    CK(cudaGetLastError());
+    return E_OK;
+}
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
+    if (!params || !out) return E_INPUT;
+    mcac_gpu *h = new mcac_gpu();
+    *out = h;
+    h->prm = *params;
+    h->device = device;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= device) {
+        h->err = "mcac_b200 needs a CUDA device (sm_100a); there is no CPU fallback";
+        return E_UNKNOWN;
+    }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void **)&h->h_sc, sizeof(Scalars)));
+    fill_devstate_params(h);
+    TRY(alloc_persistent(h));
+    GlibcRandState st;
+    glibc_srand(st, params->random_seed);
+    CK(cudaMemcpy(h->d.rng, &st, sizeof(st), cudaMemcpyHostToDevice));
+    h->d.rng_buf_base = 0;
+    h->d.rng_buf_n = 0;
+    h->rng_generated = 0;
+    return E_OK;
+}
+
+int mcac_gpu_destroy(mcac_gpu *h) {
+    if (!h) return E_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_all(h);
+    for (void *p : h->persistent) cudaFree(p);
+    if (h->rec_dev) cudaFree(h->rec_dev);
+    if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return E_OK;
+}
+
+const char *mcac_gpu_last_error(const mcac_gpu *h) { return h ? h->err.c_str() : "null handle"; }
+void *mcac_gpu_stream(mcac_gpu *h) { return h ? (void *)h->stream : nullptr; }
+
+// srand(seed) followed by `consumed` draws already taken by the host-side initial placement (a23)
+int mcac_gpu_set_rng(mcac_gpu *h, uint32_t seed, int64_t consumed) {
+    CK(cudaSetDevice(h->device));
+    GlibcRandState st;
+    glibc_srand(st, seed);
+    for (int64_t i = 0; i < consumed; i++) glibc_rand_next(st);
+    GlibcRandState rot;  // rotate so that the device generator always starts a block at ring position 0
+    for (int i = 0; i < 31; i++) rot.ring[i] = st.ring[(st.pos + i) % 31];
+    rot.pos = 0;
+    CK(cudaMemcpy(h->d.rng, &rot, sizeof(rot), cudaMemcpyHostToDevice));
+    h->sc_host.rand_pos = consumed;
+    h->d.rng_buf_base = consumed;
+    h->d.rng_buf_n = 0;
+    h->rng_generated = consumed;
+    if (h->uploaded) TRY(push_scalars(h));
+    return E_OK;
+}
+
+int mcac_gpu_upload_state(mcac_gpu *h, int64_t n_sph, int64_t n_agg, const double *sphere_fields, const int64_t *sphere_charge,
+                          const double *agg_fields, const int64_t *agg_charge, const int64_t *agg_cells, const int64_t *offsets,
+                          const int64_t *members, const double *per_member, double maxradius, double max_time_step) {
+    CK(cudaSetDevice(h->device));
+    HostState s;
+    s.n_sph = n_sph;
+    s.n_agg = n_agg;
+    s.sph.assign(sphere_fields, sphere_fields + 9 * n_sph);
+    s.sph_charge.assign((size_t)n_sph, 0);
+    if (sphere_charge) s.sph_charge.assign(sphere_charge, sphere_charge + n_sph);
+    s.agg.assign(agg_fields, agg_fields + 21 * n_agg);
+    s.agg_charge.assign((size_t)n_agg, 0);
+    if (agg_charge) s.agg_charge.assign(agg_charge, agg_charge + n_agg);
+    s.agg_cells.assign(agg_cells, agg_cells + 3 * n_agg);
+    s.offsets.assign(offsets, offsets + n_agg + 1);
+    s.members.assign(members, members + n_sph);
+    s.agg_n.resize((size_t)n_agg);
+    for (int64_t a = 0; a < n_agg; a++) s.agg_n[(size_t)a] = offsets[a + 1] - offsets[a];
+    s.per_member.assign(per_member, per_member + 3 * n_sph);
+    free_all(h);
+    TRY(upload(h, s, maxradius, max_time_step, false));
+    h->dup_threshold = n_agg / 8;  // calcul.cpp:58
+    return E_OK;
+}
+
+int mcac_gpu_sizes(mcac_gpu *h, int64_t *n_sph, int64_t *n_agg) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    if (n_sph) *n_sph = h->sc_host.n_sph;
+    if (n_agg) *n_agg = h->sc_host.n_agg;
+    return E_OK;
+}
+
+int mcac_gpu_download_state(mcac_gpu *h, double *sphere_fields, int64_t *sphere_label, int64_t *sphere_charge, double *agg_fields,
+                            int64_t *agg_n_spheres, int64_t *agg_charge, int64_t *agg_cells, int64_t *offsets, int64_t *members,
+                            double *per_member, double *scalars) {
+    CK(cudaSetDevice(h->device));
+    HostState s;
+    TRY(download(h, s));
+    auto cp = [](auto *dst, const auto &v) { if (dst) std::copy(v.begin(), v.end(), dst); };
+    cp(sphere_fields, s.sph);
+    cp(sphere_label, s.sph_label);
+    cp(sphere_charge, s.sph_charge);
+    cp(agg_fields, s.agg);
+    cp(agg_n_spheres, s.agg_n);
+    cp(agg_charge, s.agg_charge);
+    cp(agg_cells, s.agg_cells);
+    cp(offsets, s.offsets);
+    cp(members, s.members);
+    cp(per_member, s.per_member);
+    if (scalars) std::memcpy(scalars, s.scalars, sizeof(s.scalars));
+    return E_OK;
+}
+
+int mcac_gpu_contact_search_batch(mcac_gpu *h, int64_t n, const int64_t *source_labels, const double *directions, const double *distances,
+                                  mcac_contact *out, int64_t *pair_tests) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    std::vector<SearchResult> res(kMaxBatch);
+    std::vector<int> sid;
+    int64_t ps = 0, pb = 0;
+    for (int64_t base = 0; base < n; base += kMaxBatch) {
+        const int nq = (int)std::min<int64_t>(kMaxBatch, n - base);
+        CK(cudaMemcpyAsync(h->q_label, source_labels + base, sizeof(int64_t) * nq, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->q_dir, directions + 3 * base, sizeof(double) * 3 * nq, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->q_dist, distances + base, sizeof(double) * nq, cudaMemcpyHostToDevice, h->stream));
+        k_labels_to_slots<<<div_up(nq, 128), 128, 0, h->stream>>>(h->d, nq, (const long long *)h->q_label, h->q_slot);
+        h->launches++;
+        TRY(search_launch(h, nq));
+        CK(cudaMemcpyAsync(res.data(), h->q_res, sizeof(SearchResult) * nq, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        // ids: sphere slots -> creation indices, aggregate slots -> labels
+        std::vector<int> want;
+        for (int j = 0; j < nq; j++) {
+            out[base + j].distance = res[(size_t)j].distance;
+            out[base + j].moving_sphere = out[base + j].other_sphere = out[base + j].moving_label = out[base + j].other_label = -1;
+            ps += res[(size_t)j].n_sphere_pairs;
+            pb += res[(size_t)j].n_bounding;
+            if (res[(size_t)j].status == 3) { h->err = "Aggregate not on the verlet list ???"; return E_VERLET; }
+            if (res[(size_t)j].status == 1) { h->err = "contact search: suspect list overflow"; return E_UNKNOWN; }
+        }
+        for (int j = 0; j < nq; j++) {
+            const SearchResult &r = res[(size_t)j];
+            if (r.other_agg < 0) continue;
+            int ids[2], lab;
+            CK(cudaMemcpyAsync(&ids[0], h->d.s_id + r.moving_slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(&ids[1], h->d.s_id + r.other_slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(&lab, h->d.label_of_slot + r.other_agg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            out[base + j].moving_sphere = ids[0];
+            out[base + j].other_sphere = ids[1];
+            out[base + j].moving_label = source_labels[base + j];
+            out[base + j].other_label = lab;
+        }
+    }
+    if (pair_tests) { pair_tests[0] = ps; pair_tests[1] = pb; }
+    return E_OK;
+}
+
+int mcac_gpu_contact_search(mcac_gpu *h, int64_t source_label, const double direction[3], double distance, mcac_contact *out) {
+    return mcac_gpu_contact_search_batch(h, 1, &source_label, direction, &distance, out, nullptr);
+}
+
+int mcac_gpu_translate(mcac_gpu *h, int64_t label, const double vector[3]) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    if (label < 0 || label >= h->sc_host.n_agg) { h->err = "translate: bad label"; return E_INPUT; }
+    int slot;
+    CK(cudaMemcpyAsync(&slot, h->d.slot_of_label + label, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    k_translate_one<<<1, 128, 0, h->stream>>>(h->d, slot, vector[0], vector[1], vector[2]);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->cells_valid = false;
+    return E_OK;
+}
+
+int mcac_gpu_merge(mcac_gpu *h, const mcac_contact *c, int *merged) {
+    CK(cudaSetDevice(h->device));
+    if (merged) *merged = 0;
+    if (!c || c->moving_sphere < 0 || c->other_sphere < 0) return E_OK;  // expired weak_ptrs: merge() returns false
+    TRY(pull_scalars(h));
+    if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph) TRY(compact_pool(h));
+    k_merge_one<<<1, kCommitThreads, 0, h->stream>>>(h->d, (int)c->moving_sphere, (int)c->other_sphere, h->merged_flag);
+    h->launches++;
+    CK(cudaGetLastError());
+    int m = 0;
+    CK(cudaMemcpyAsync(&m, h->merged_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (merged) *merged = m;
+    if (m) { h->labels_valid = false; h->cells_valid = false; h->pick_valid = false; }
+    TRY(pull_scalars(h));
+    if (h->sc_host.error) { h->err = "device error during merge"; return h->sc_host.error; }
+    return E_OK;
+}
+
+int mcac_gpu_grow(mcac_gpu *h, double dt, int64_t label) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    int slot = -1, n = h->sc_host.pool_top;
+    if (label >= 0) {
+        CK(cudaMemcpyAsync(&slot, h->d.slot_of_label + label, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        n = h->sc_host.n_sph;
+    }
+    k_grow<<<div_up(n, 256), 256, 0, h->stream>>>(h->d, dt, slot);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return E_OK;
+}
+
+int mcac_gpu_update(mcac_gpu *h, int64_t label, int full) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    int slot = -1;
+    if (label >= 0) {
+        CK(cudaMemcpyAsync(&slot, h->d.slot_of_label + label, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    const int nblk = label >= 0 ? 1 : div_up(h->sc_host.n_agg_slots, 8);
+    k_update_all<<<nblk, 256, 0, h->stream>>>(h->d, full, slot);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->cells_valid = false;
+    TRY(pull_scalars(h));
+    if (h->sc_host.error) { h->err = "device error during update (VolSurfError)"; return h->sc_host.error; }
+    return E_OK;
+}
+
+int mcac_gpu_refresh(mcac_gpu *h, double *max_time_step, double *avg_npp, double *total_volume, double *total_surface) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(refresh_reduce(h));
+    TRY(pull_scalars(h));
+    if (max_time_step) *max_time_step = h->sc_host.max_time_step;
+    if (avg_npp) *avg_npp = h->sc_host.avg_npp;
+    if (total_volume) *total_volume = h->sc_host.total_volume;
+    if (total_surface) *total_surface = h->sc_host.total_surface;
+    return E_OK;
+}
+
+int mcac_gpu_sort_time_steps(mcac_gpu *h, double factor) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(sort_time_steps(h, factor));
+    return E_OK;
+}
+
+int mcac_gpu_get_pick_table(mcac_gpu *h, int64_t *index_sorted, double *cumulative, int64_t *n_out) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    const int n = h->sc_host.n_pick;
+    if (n_out) *n_out = n;
+    std::vector<int> lab((size_t)n);
+    CK(cudaMemcpyAsync(lab.data(), h->sorted_label, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (cumulative) CK(cudaMemcpyAsync(cumulative, h->d.cum, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (index_sorted) for (int i = 0; i < n; i++) index_sorted[i] = lab[(size_t)i];
+    return E_OK;
+}
+
+int mcac_gpu_pick_random(mcac_gpu *h, double u, int64_t *label, double *deltatemps) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    if (!h->pick_valid) { h->err = "pick_random before sort_time_steps"; return E_INPUT; }
+    const int n = h->sc_host.n_pick;
+    std::vector<double> cum((size_t)n);
+    std::vector<int> lab((size_t)n);
+    CK(cudaMemcpyAsync(cum.data(), h->d.cum, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lab.data(), h->sorted_label, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double val = u * cum[(size_t)n - 1];
+    const long k = std::lower_bound(cum.begin(), cum.end(), val) - cum.begin();
+    if (label) *label = lab[(size_t)k];
+    if (deltatemps) *deltatemps = h->sc_host.max_time_step / cum[(size_t)n - 1];
+    return E_OK;
+}
+
+int mcac_gpu_pick_last(mcac_gpu *h, int64_t *label) {
+    CK(cudaSetDevice(h->device));
+    HostState s;
+    TRY(download(h, s));
+    int64_t latest = 0;
+    double t = s.agg[(size_t)(13 * s.n_agg)];
+    for (int64_t l = 0; l < s.n_agg; l++)
+        if (s.agg[(size_t)(13 * s.n_agg + l)] < t) { t = s.agg[(size_t)(13 * s.n_agg + l)]; latest = l; }
+    if (label) *label = latest;
+    return E_OK;
+}
+
+int mcac_gpu_duplicate(mcac_gpu *h) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(duplicate(h));
+    return E_OK;
+}
+
+int mcac_gpu_rand(mcac_gpu *h, int64_t n, int32_t *out) {
+    CK(cudaSetDevice(h->device));
+    if (h->uploaded) TRY(pull_scalars(h));
+    for (int64_t done = 0; done < n;) {
+        const int64_t chunk = std::min<int64_t>(n - done, kRngBuf / 2);
+        TRY(ensure_rng(h, h->sc_host.rand_pos + chunk));
+        CK(cudaMemcpyAsync(out + done, h->d.rng_buf + (h->sc_host.rand_pos - h->d.rng_buf_base), sizeof(int) * chunk,
+                           cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->sc_host.rand_pos += chunk;
+        done += chunk;
+    }
+    if (h->uploaded) TRY(push_scalars(h));
+    return E_OK;
+}
+
+int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record *records, int64_t n_records, mcac_run_report *report) {
+    CK(cudaSetDevice(h->device));
+    if (!h->uploaded) { h->err = "run before upload_state"; return E_INPUT; }
+    if (h->prm.pick_method != MCAC_PICK_RANDOM || !h->prm.with_collisions || h->prm.with_surface_reactions || h->prm.with_potentials ||
+        h->prm.with_nucleation) {
+        h->err = "mcac_gpu_run: this configuration is not on the device-resident loop yet (use the per-call entry points)";
+        return E_INPUT;
+    }
+    const int B = batch > 0 ? std::min<int>(batch, kMaxBatch) : 256;
+    TRY(pull_scalars(h));
+    const Scalars at_start = h->sc_host;
+    const long long launches0 = h->launches;
+    if (records && n_records > 0) {
+        if (h->rec_cap < n_records) {
+            if (h->rec_dev) cudaFree(h->rec_dev);
+            CK(cudaMalloc((void **)&h->rec_dev, sizeof(mcac_step_record) * (size_t)n_records));
+            h->rec_cap = n_records;
+        }
+    }
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, h->stream));
+    int64_t steps = 0, batches = 0, sorts = 0, dups = 0;
+    int rc = E_OK;
+    bool fin = false;
+    while (steps < max_steps) {
+        if (finished(h)) { fin = true; break; }
+        if (h->sc_host.event || !h->pick_valid) {
+            // top of the loop after an event (calcul.cpp:72-101): duplication test, then sort_time_steps(max)
+            if (h->sc_host.event && h->prm.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(h->prm.u_sg < 0.0)) {
+                if ((rc = duplicate(h)) != E_OK) break;
+                dups++;
+            }
+            if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
+            sorts++;
+        }
+        if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph)
+            if ((rc = compact_pool(h)) != E_OK) break;
+        const int nq = (int)std::min<int64_t>(B, max_steps - steps);
+        if ((rc = ensure_rng(h, h->sc_host.rand_pos + 3LL * nq)) != E_OK) break;
+        k_prepare_queries<<<div_up(nq, 128), 128, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist);
+        h->launches++;
+        if ((rc = search_launch(h, nq)) != E_OK) break;
+        BatchArgs ba;
+        ba.nq = nq;
+        ba.q_slot = h->q_slot;
+        ba.q_dir = h->q_dir;
+        ba.q_dist = h->q_dist;
+        ba.res = h->q_res;
+        ba.rec = (records && n_records > 0) ? h->rec_dev : nullptr;
+        ba.rec_cap = n_records;
+        ba.rec_base = steps;
+        ba.max_steps = max_steps - steps;
+        k_commit<<<1, kCommitThreads, 0, h->stream>>>(h->d, ba);
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) { h->err = "k_commit launch failed"; rc = E_UNKNOWN; break; }
+        if ((rc = pull_scalars(h)) != E_OK) break;
+        batches++;
+        h->cells_valid = false;
+        if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
+        steps += h->sc_host.b_committed;
+        if (h->sc_host.b_merged) {
+            h->pick_valid = false;
+            if ((rc = after_event(h)) != E_OK) break;
+        }
+        if (h->sc_host.b_stop_reason == STOP_FINISHED) { fin = true; break; }
+        if (h->sc_host.b_committed == 0) { h->err = "batch made no progress"; rc = E_UNKNOWN; break; }
+    }
+    CK(cudaEventRecord(ev1, h->stream));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (rc != E_OK) return rc;
+    if (records && n_records > 0 && steps > 0)
+        CK(cudaMemcpy(records, h->rec_dev, sizeof(mcac_step_record) * (size_t)std::min<int64_t>(steps, n_records), cudaMemcpyDeviceToHost));
+    if (report) {
+        const Scalars &sc = h->sc_host;
+        std::memset(report, 0, sizeof(*report));
+        report->steps = steps;
+        report->events = sc.total_events - at_start.total_events;
+        report->searches = sc.searches - at_start.searches;
+        report->pair_tests_sphere = sc.pair_sphere - at_start.pair_sphere;
+        report->pair_tests_bounding = sc.pair_bounding - at_start.pair_bounding;
+        report->batches = batches;
+        report->conflicts = sc.conflicts - at_start.conflicts;
+        report->duplications = dups;
+        report->sorts = sorts;
+        report->kernel_launches = h->launches - launches0;
+        report->n_aggregates = sc.n_agg;
+        report->n_spheres = sc.n_sph;
+        report->finished = (fin || finished(h)) ? 1 : 0;
+        report->time = sc.time;
+        report->box_length = sc.box_length;
+        report->avg_npp = sc.avg_npp;
+        report->max_time_step = sc.max_time_step;
+        report->volume_fraction = sc.volume_fraction;
+        report->device_ms = ms;
+    }
+    return E_OK;
+}
+
+int mcac_gpu_morphology_stats(mcac_gpu *h, int32_t n_bins, double rg_max, double *out) {
+    CK(cudaSetDevice(h->device));
+    HostState s;
+    TRY(download(h, s));
+    (void)rg_max;
+    (void)n_bins;
+    (void)out;
+    h->err = "morphology stats: not built yet";
+    return E_UNKNOWN;
+}
+int mcac_gpu_morphology_stats_device(mcac_gpu *h, int32_t n_bins, double rg_max, void *device_out) {
+    (void)n_bins; (void)rg_max; (void)device_out;
+    h->err = "morphology stats: not built yet";
+    return E_UNKNOWN;
+}
+
+}  // extern "C"

@@ -1,0 +1,984 @@
+// mcac_b200 — hand-written sm_100a kernels of the Monte-Carlo aggregation step.
+// K1 contact search, K2 cell list (counting sort), K3 translate/commit, K4 merge, K5-K7 aggregate update,
+// K8 surface growth, K9 pick table helpers, K10 RNG stream.  No tensor cores: nothing here is a dense
+// contraction (FP64 scalar pipes + HBM/L2 streams).  Compiled with --fmad=false (see mcac_math.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/mcac_b200.h"
+#include "mcac_device.cuh"
+
+namespace mcacb {
+
+constexpr int kSearchThreads = 128;
+constexpr int kCandCap = 512;   // eligible aggregates per search kept in shared memory
+constexpr int kCommitThreads = 512;
+constexpr int kMaxBatch = 1024;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// small cooperative helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+// exclusive scan of one int per thread over the whole block (blockDim multiple of 32, <= 1024); returns prefix, total via *total
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *warp_sums /* >= 32 ints of smem */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int inc = warp_inclusive_scan(v, lane);
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+        s = warp_inclusive_scan(s, lane);
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int base = w ? warp_sums[w - 1] : 0;
+    *total = warp_sums[nw - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+// lexicographic (distance, index) min across a warp: strict `<` on the distance keeps the FIRST minimum in visiting
+// order, which is what the reference's nested loops do (sphere_contact.cpp:131-137, aggregat_distance.cpp:30-41).
+__device__ __forceinline__ void warp_argmin(double &d, long long &idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(kFull, d, o);
+        const long long oi = __shfl_xor_sync(kFull, idx, o);
+        if (od < d || (od == d && oi < idx)) {
+            d = od;
+            idx = oi;
+        }
+    }
+}
+__device__ __forceinline__ void atomic_max_positive_double(double *addr, double v) {
+    atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));  // valid for non-negative doubles
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10 — glibc rand() stream: one thread advances the 31-word ring kept in registers/local memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rng_fill(GlibcRandState *st, int *out, int n) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    GlibcRandState s = *st;
+    for (int i = 0; i < n; i++) out[i] = glibc_rand_next(s);
+    *st = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 — pick: one thread per speculative step j reads its three draws (pick, theta, phi), does
+// pick_random (lower_bound on the cumulative table, aggregat_list.cpp:59-66) and random_direction.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir, double *q_dist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    const Scalars &sc = *d.sc;
+    const long long p = sc.rand_pos + 3LL * j - d.rng_buf_base;
+    const double u_pick = uniform_from_rand(d.rng_buf[p]);
+    const double u_theta = uniform_from_rand(d.rng_buf[p + 1]);
+    const double u_phi = uniform_from_rand(d.rng_buf[p + 2]);
+    const int n = sc.n_pick;
+    const double val = u_pick * d.cum[n - 1];
+    int lo = 0, hi = n;  // std::lower_bound: first index with cum[i] >= val
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (d.cum[mid] < val) lo = mid + 1; else hi = mid;
+    }
+    const int slot = d.sorted_slot[lo];
+    const Vec3 dir = direction_from_draws(u_theta, u_phi);
+    q_slot[j] = slot;
+    q_dir[3 * j] = dir.x;
+    q_dir[3 * j + 1] = dir.y;
+    q_dir[3 * j + 2] = dir.z;
+    q_dist[j] = d.a_lpm[slot];
+}
+// explicit queries given by label (the per-call C ABI)
+__global__ void k_labels_to_slots(DevState d, int nq, const long long *labels, int *q_slot) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    const long long l = labels[j];
+    q_slot[j] = (l >= 0 && l < d.sc->n_agg) ? d.slot_of_label[l] : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 — swept-sphere contact search, one CTA per query.
+// Replaces AggregatList::distance_to_next_contact + get_neighborhood + filter_neighborhood +
+// distance_to_contact x3 (aggregat_list.cpp:447-532, aggregat_distance.cpp:24-44, sphere_contact.cpp:47-139).
+//  phase 1: every aggregate of the Verlet cells along the displacement (verlet.cpp:52-98) gets the
+//           bounding-sphere sweep test; the eligible ones (d_b < distance, strict) are kept with the
+//           reference's visiting key = (cell scan rank, label).
+//  phase 2: one warp per eligible aggregate sweeps moving spheres x other spheres with the exact FP64 pair
+//           test and a warp-shuffle argmin whose tie-break is the (i, j) visiting order.
+//  phase 3: the suspects are ranked by (d_b, key) — the multimap order — and scanned with the reference's
+//           two early breaks, so zero-distance / stale-rmax corner cases resolve exactly as on the CPU.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSearchThreads) k_search(DevState d, int nq, const int *__restrict__ q_slot,
+                                                           const double *__restrict__ q_dir, const double *__restrict__ q_dist,
+                                                           SearchResult *__restrict__ out) {
+    __shared__ int seg_beg[kSearchThreads];
+    __shared__ int seg_pre[kSearchThreads + 1];
+    __shared__ int warp_sums[32];
+    __shared__ int c_slot[kCandCap];
+    __shared__ double c_db[kCandCap];
+    __shared__ unsigned long long c_key[kCandCap];
+    __shared__ double c_d[kCandCap];
+    __shared__ long long c_pair[kCandCap];
+    __shared__ int c_order[kCandCap];
+    __shared__ int s_count, s_nb;
+
+    const int q = blockIdx.x;
+    if (q >= nq) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSearchThreads >> 5;
+    const int slot = q_slot[q];
+    SearchResult res;
+    res.distance = INFINITY;
+    res.moving_slot = res.other_slot = res.other_agg = -1;
+    res.n_bounding = 0;
+    res.n_sphere_pairs = 0;
+    res.status = 0;
+    res.pad = 0;
+    if (slot < 0) {
+        if (tid == 0) { res.status = 3; out[q] = res; }  // VerletError
+        return;
+    }
+    const Scalars &sc = *d.sc;
+    const double box = sc.box_length;
+    const int n_div = d.n_div;
+    const double4 me = d.a_posr[slot];
+    const double dist = q_dist[q];
+    const double dx = q_dir[3 * q], dy = q_dir[3 * q + 1], dz = q_dir[3 * q + 2];
+    const CellRange rg = verlet_range(me.x, me.y, me.z, dist * dx, dist * dy, dist * dz, me.w + sc.maxradius, n_div, box);
+    const int ni = rg.hi[0] - rg.lo[0] + 1, nj = rg.hi[1] - rg.lo[1] + 1, nk = rg.hi[2] - rg.lo[2] + 1;
+    if (tid == 0) { s_count = 0; s_nb = 0; }
+    __syncthreads();
+
+    // ---- phase 1: rows (i, j) of the cell range; along k the CSR entries are contiguous (<= 2 segments with wrap)
+    const int ks = wrap_cell(rg.lo[2], n_div);
+    const bool wraps = ks + nk > n_div;
+    const int nseg = ni * nj * (wraps ? 2 : 1);
+    for (int seg0 = 0; seg0 < nseg; seg0 += kSearchThreads) {
+        int len = 0, beg = 0;
+        const int s = seg0 + tid;
+        if (s < nseg) {
+            const int row = wraps ? (s >> 1) : s;
+            const int part = wraps ? (s & 1) : 0;
+            const int ii = wrap_cell(rg.lo[0] + row / nj, n_div), jj = wrap_cell(rg.lo[1] + row % nj, n_div);
+            const int base = (ii * n_div + jj) * n_div;
+            int ka, kb;  // inclusive wrapped k span of this segment
+            if (!wraps) { ka = ks; kb = ks + nk - 1; }
+            else if (part == 0) { ka = ks; kb = n_div - 1; }
+            else { ka = 0; kb = nk - (n_div - ks) - 1; }
+            beg = d.cell_start[base + ka];
+            len = d.cell_start[base + kb + 1] - beg;
+        }
+        int total;
+        const int pre = block_exclusive_scan(len, &total, warp_sums);
+        seg_beg[tid] = beg;
+        seg_pre[tid] = pre;
+        if (tid == 0) seg_pre[kSearchThreads] = total;
+        __syncthreads();
+        for (int f = tid; f < total; f += kSearchThreads) {
+            int lo = 0, hi = kSearchThreads;  // last segment whose prefix <= f
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (seg_pre[mid] <= f) lo = mid; else hi = mid;
+            }
+            const int o = d.cell_items[seg_beg[lo] + (f - seg_pre[lo])];
+            if (o == slot) continue;
+            const double4 oa = d.a_posr[o];
+            const double db = pair_contact_distance(me.x, me.y, me.z, me.w, oa.x, oa.y, oa.z, oa.w, dx, dy, dz, dist, box);
+            atomicAdd(&s_nb, 1);
+            if (db < dist) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < kCandCap) {
+                    const int r0 = range_rank(d.a_cx[o], rg.lo[0], rg.hi[0], n_div);
+                    const int r1 = range_rank(d.a_cy[o], rg.lo[1], rg.hi[1], n_div);
+                    const int r2 = range_rank(d.a_cz[o], rg.lo[2], rg.hi[2], n_div);
+                    const unsigned long long cell_rank = (unsigned long long)((r0 * nj + r1) * (long long)nk + r2);
+                    c_slot[pos] = o;
+                    c_db[pos] = db;
+                    c_key[pos] = (cell_rank << 32) | (unsigned)o;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int m_all = s_count;
+    const int m = m_all < kCandCap ? m_all : kCandCap;
+    if (m_all > kCandCap) res.status = 1;  // more eligible suspects than the shared-memory list holds
+
+    // ---- phase 2: exact sphere-sphere sweep, one warp per eligible aggregate
+    const int n_src = d.a_n[slot], off_src = d.a_off[slot];
+    for (int k = warp; k < m; k += nwarps) {
+        const int o = c_slot[k];
+        const int n_o = d.a_n[o], off_o = d.a_off[o];
+        const long long npairs = (long long)n_src * n_o;
+        double best = INFINITY;
+        long long best_p = npairs;
+        for (long long p = lane; p < npairs; p += 32) {
+            const int i = (int)(p / n_o), j = (int)(p - (long long)i * n_o);
+            const double4 a = d.s_posr[off_src + i];
+            const double4 b = d.s_posr[off_o + j];
+            const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+            if (c < best) { best = c; best_p = p; }
+        }
+        warp_argmin(best, best_p);
+        if (lane == 0) { c_d[k] = best; c_pair[k] = best_p; }
+    }
+    __syncthreads();
+
+    // ---- phase 3: multimap order + the reference's scan with its two breaks (aggregat_list.cpp:459-482)
+    for (int t = tid; t < m; t += kSearchThreads) {
+        const double db = c_db[t];
+        const unsigned long long key = c_key[t];
+        int rank = 0;
+        for (int u = 0; u < m; u++) {
+            const double du = c_db[u];
+            rank += (du < db || (du == db && c_key[u] < key)) ? 1 : 0;
+        }
+        c_order[rank] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double closest = INFINITY;
+        int who = -1;
+        long long examined = 0;
+        for (int r = 0; r < m; r++) {
+            const int t = c_order[r];
+            if (closest <= 0.) break;
+            if (closest < c_db[t]) break;
+            examined += (long long)n_src * d.a_n[c_slot[t]];
+            if (c_d[t] < closest) { closest = c_d[t]; who = t; }
+        }
+        res.n_bounding = s_nb;
+        res.n_sphere_pairs = examined;
+        if (who >= 0) {
+            const int o = c_slot[who];
+            const int n_o = d.a_n[o];
+            const long long p = c_pair[who];
+            res.distance = closest;
+            res.moving_slot = off_src + (int)(p / n_o);
+            res.other_slot = d.a_off[o] + (int)(p % n_o);
+            res.other_agg = o;
+        }
+        out[q] = res;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 — Verlet cell list by counting sort (replaces Verlet ctor/add/remove, verlet.cpp:26-51, and
+// Aggregate::update_verlet bookkeeping): histogram of the stored cell of each live aggregate ->
+// exclusive scan -> scatter.  The in-cell order is irrelevant: K1 re-derives the reference's visiting key.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cell_count(DevState d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.sc->n_agg_slots || !d.a_alive[s]) return;
+    const int c = (d.a_cx[s] * d.n_div + d.a_cy[s]) * d.n_div + d.a_cz[s];
+    atomicAdd(&d.cell_fill[c], 1);
+}
+__global__ void k_cell_scatter(DevState d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.sc->n_agg_slots || !d.a_alive[s]) return;
+    const int c = (d.a_cx[s] * d.n_div + d.a_cy[s]) * d.n_div + d.a_cz[s];
+    const int pos = atomicAdd(&d.cell_fill[c], 1);
+    d.cell_items[d.cell_start[c] + pos] = s;
+}
+// generic 3-phase exclusive scan of ints (deterministic): in[0..n) -> out[0..n], out[n] = total
+constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;
+__global__ void k_scan_partials(const int *in, int n, int *block_sums) {
+    __shared__ int ws[32];
+    const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) v += (base + k < n) ? in[base + k] : 0;
+    int total;
+    block_exclusive_scan(v, &total, ws);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void k_scan_block_sums(int *block_sums, int nb) {  // single block; nb <= few thousand
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nb ? block_sums[i] : 0;
+        int total;
+        const int pre = block_exclusive_scan(v, &total, ws);
+        if (i < nb) block_sums[i] = carry + pre;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+__global__ void k_scan_apply(const int *in, int n, const int *block_sums, int nb, int *out) {
+    __shared__ int ws[32];
+    const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    int x[kScanItems];
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { x[k] = (base + k < n) ? in[base + k] : 0; v += x[k]; }
+    int total;
+    int pre = block_exclusive_scan(v, &total, ws) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = pre;
+        pre += x[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[nb];
+}
+
+// label <-> slot maps (label = rank of the slot among live slots): flags -> scan -> scatter
+__global__ void k_alive_to_labels(DevState d, const int *scan /* exclusive scan of a_alive */) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.sc->n_agg_slots) return;
+    if (d.a_alive[s]) {
+        d.label_of_slot[s] = scan[s];
+        d.slot_of_label[scan[s]] = s;
+    } else {
+        d.label_of_slot[s] = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Aggregate-level device functions used by commit / merge / growth kernels
+// ------------------------------------------------------------------------------------------------
+// Aggregate::set_position (aggregat.cpp:109-118): periodic wrap of the centre + stored Verlet cell
+__device__ __forceinline__ void agg_store_position(const DevState &d, int slot, double x, double y, double z, double box) {
+    const double nx = periodic_position(x, box), ny = periodic_position(y, box), nz = periodic_position(z, box);
+    double4 a = d.a_posr[slot];
+    a.x = nx; a.y = ny; a.z = nz;
+    d.a_posr[slot] = a;
+    d.a_cx[slot] = cell_of(nx, d.n_div, box);
+    d.a_cy[slot] = cell_of(ny, d.n_div, box);
+    d.a_cz[slot] = cell_of(nz, d.n_div, box);
+}
+template <bool kBlock>
+__device__ __forceinline__ void group_sync() {
+    if (kBlock) __syncthreads(); else __syncwarp();
+}
+// K3 — Aggregate::translate (aggregat.cpp:148-161), cooperative over the `nth` threads of a warp or of the CTA.
+// Every thread recomputes the new centre (cheap); the centre itself is rewritten after a group barrier.
+template <bool kBlock>
+__device__ __forceinline__ void agg_translate(const DevState &d, int slot, double vx, double vy, double vz, double box, int tid, int nth) {
+    const double4 a = d.a_posr[slot];
+    const double nx = periodic_position(a.x + vx, box), ny = periodic_position(a.y + vy, box), nz = periodic_position(a.z + vz, box);
+    const double refx = nx - d.a_rx[slot], refy = ny - d.a_ry[slot], refz = nz - d.a_rz[slot];
+    const int off = d.a_off[slot], n = d.a_n[slot];
+    for (int i = tid; i < n; i += nth) {
+        const double4 rel = d.s_relv[off + i];
+        double4 p = d.s_posr[off + i];
+        p.x = refx + rel.x; p.y = refy + rel.y; p.z = refz + rel.z;  // root sphere: rel == 0 -> refpos
+        d.s_posr[off + i] = p;
+    }
+    group_sync<kBlock>();
+    if (tid == 0) agg_store_position(d, slot, a.x + vx, a.y + vy, a.z + vz, box);
+    group_sync<kBlock>();
+}
+
+// K5-K7 — Aggregate::update() / update_partial() (aggregat.cpp:247-288, 321-483, 719-764) for one aggregate,
+// cooperative over the threads [0,nth) of a warp (kBlock = false) or of the whole CTA (kBlock = true).
+// All 1-D sums (volume, surface, centre of mass, gyration sums, mean diameter) are accumulated by ONE lane in
+// `myspheres` order, exactly like the reference's loops, so they come out bit-identical; the O(n^2) contact
+// pass gives one sphere per lane (ascending partner index) and its overlap statistics are combined in a fixed
+// tree (deterministic, <= 1e-15 relative from the reference's hash-map order).
+// scratch: kUpdateScratch doubles of shared memory private to the group.
+constexpr int kUpdateScratch = 192;  // [0,8) results, [8,40) per-warp maxima, [40,40+7*16) per-warp partial sums
+template <bool kBlock>
+__device__ void agg_update(const DevState &d, int slot, bool full, int tid, int nth, double *scratch, double box) {
+    const int off = d.a_off[slot], n = d.a_n[slot];
+    const int method = d.volsurf_method;
+    const int w = tid >> 5, nw = (nth + 31) >> 5;
+    if (full) {
+        // ---- contact pass (update_distances_and_overlapping + the contact-graph loops of compute_volume_surface)
+        double vals[7] = {0., 0., 0., 0., 0., 0., 0.};  // intersections, sum c_ij, c_s10, c_v20, c_v30, vp_sum, sp_sum
+        for (int i = tid; i < n; i += nth) {
+            const double4 ri = d.s_relv[off + i];
+            const double r_i = d.s_posr[off + i].w;
+            const double s_i = d.s_surf[off + i];
+            double veff = ri.w, seff = s_i;
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                const double4 rj = d.s_relv[off + j];
+                const double r_j = d.s_posr[off + j].w;
+                const double ex = ri.x - rj.x, ey = ri.y - rj.y, ez = ri.z - rj.z;
+                const double dist = sqrt(ex * ex + ey * ey + ez * ez);
+                const double rs = r_i + r_j;
+                if (dist <= (1. + kCoordinationEpsilon) * rs) {
+                    const double c_ij = (rs - dist) / rs;
+                    vals[0] += 1.;
+                    vals[1] += c_ij;
+                    if (method == MCAC_VS_ALPHAS) {
+                        const double vp = pow(r_i, 3.) + pow(r_j, 3.);
+                        const double sp = r_i * r_i + r_j * r_j;
+                        vals[5] += vp;
+                        vals[6] += sp;
+                        vals[2] += c_ij * sp;
+                        vals[3] += (c_ij * c_ij) * vp;
+                        vals[4] += pow(c_ij, 3.) * vp;
+                    } else if (method == MCAC_VS_CAPS) {
+                        double caps[4];
+                        if (i < j) {
+                            lens_caps(r_i, ri.w, s_i, r_j, rj.w, d.s_surf[off + j], dist, caps);
+                            veff = veff - caps[0];
+                            seff = seff - caps[2];
+                        } else {
+                            lens_caps(r_j, rj.w, d.s_surf[off + j], r_i, ri.w, s_i, dist, caps);
+                            veff = veff - caps[1];
+                            seff = seff - caps[3];
+                        }
+                    }
+                }
+            }
+            if (method == MCAC_VS_CAPS) {
+                veff = (veff < 0.0) ? 0.0 : veff;
+                seff = (seff < 0.0) ? 0.0 : seff;
+            }
+            d.s_veff[off + i] = veff;
+            d.s_seff[off + i] = seff;
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(kFull, vals[k], o);
+        }
+        if (kBlock) {
+            if ((tid & 31) == 0)
+                for (int k = 0; k < 7; k++) scratch[40 + w * 7 + k] = vals[k];
+            __syncthreads();
+            for (int k = 0; k < 7; k++) {
+                double acc = 0.;
+                for (int ww = 0; ww < nw; ww++) acc += scratch[40 + ww * 7 + k];
+                vals[k] = acc;
+            }
+        }
+        group_sync<kBlock>();  // s_veff / s_seff visible
+        if (tid == 0) {
+            double V = 0., S = 0.;
+            for (int i = 0; i < n; i++) {
+                V = V + d.s_veff[off + i];
+                S = S + d.s_seff[off + i];
+            }
+            double ovl = 0., cn = 0.;
+            const double intersections = vals[0];
+            if (intersections > 0.) {
+                ovl = vals[1] / intersections;
+                cn = intersections / static_cast<double>(n);
+                if (method == MCAC_VS_ALPHAS) {
+                    const double c_s10 = vals[2] / vals[6], c_v20 = vals[3] / vals[5], c_v30 = vals[4] / vals[5];
+                    const double min_cn = 2 * (1.0 - 1.0 / static_cast<double>(n));
+                    const double extreme = d.a_alpha[slot];
+                    V *= volume_alpha_correction(cn, c_v20, c_v30, min_cn, extreme);
+                    S *= surface_alpha_correction(cn, c_s10, min_cn, extreme);
+                }
+            }
+            d.a_ovl[slot] = ovl;
+            d.a_cn[slot] = cn;
+            d.a_vol[slot] = V;
+            d.a_surf[slot] = S;
+            if (V <= 0 || S <= 0) d.sc->error = 8;  // VolSurfError, aggregat.cpp:427-429
+        }
+        group_sync<kBlock>();
+    }
+    // ---- update_partial: centre of mass (lanes 0..2), mean diameter / mean sphere volume (lanes 3, 4)
+    const double V = d.a_vol[slot];
+    if (tid < 3) {
+        double acc = 0.;
+        for (int i = 0; i < n; i++) {
+            const double4 rel = d.s_relv[off + i];
+            const double c = (tid == 0) ? rel.x : (tid == 1) ? rel.y : rel.z;
+            acc += c * d.s_veff[off + i];
+        }
+        scratch[tid] = acc / V;
+    } else if (tid == 3) {
+        double acc = 0.;
+        for (int i = 0; i < n; i++) acc += d.s_posr[off + i].w;
+        scratch[3] = 2 * acc / static_cast<double>(n);  // dp
+    } else if (tid == 4) {
+        double acc = 0.;
+        for (int i = 0; i < n; i++) acc += d.s_relv[off + i].w;
+        scratch[4] = acc / static_cast<double>(n);  // vol_pp
+    }
+    group_sync<kBlock>();
+    const double cx = scratch[0], cy = scratch[1], cz = scratch[2];
+    double rmax = 0.;
+    for (int i = tid; i < n; i += nth) {
+        const double4 rel = d.s_relv[off + i];
+        const double ex = rel.x - cx, ey = rel.y - cy, ez = rel.z - cz;
+        const double dc = sqrt(ex * ex + ey * ey + ez * ez);
+        d.s_dcen[off + i] = dc;
+        const double e = d.s_posr[off + i].w + dc;
+        rmax = (rmax < e) ? e : rmax;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(kFull, rmax, o);
+        rmax = (rmax < other) ? other : rmax;
+    }
+    if (kBlock) {
+        if ((tid & 31) == 0) scratch[8 + w] = rmax;
+        __syncthreads();
+        for (int ww = 0; ww < nw; ww++) rmax = (rmax < scratch[8 + ww]) ? scratch[8 + ww] : rmax;
+    }
+    group_sync<kBlock>();  // s_dcen visible
+    if (tid < 2) {  // gyration sums, aggregat.cpp:465-483
+        double acc = 0.;
+        for (int i = 0; i < n; i++) {
+            const double wgt = d.s_veff[off + i];
+            const double q = (tid == 0) ? d.s_dcen[off + i] : d.s_posr[off + i].w;
+            acc = acc + wgt * (q * q);
+        }
+        scratch[5 + tid] = acc;
+    }
+    group_sync<kBlock>();
+    if (tid == 0) {
+        const double4 root = d.s_posr[off];
+        agg_store_position(d, slot, root.x + cx, root.y + cy, root.z + cz, box);
+        double4 a = d.a_posr[slot];
+        a.w = rmax;
+        d.a_posr[slot] = a;
+        d.a_rx[slot] = cx; d.a_ry[slot] = cy; d.a_rz[slot] = cz;
+        const double rg = sqrt(fabs((scratch[5] + 3. / 5. * scratch[6]) / V));
+        d.a_rg[slot] = rg;
+        const double dp = scratch[3], vol_pp = scratch[4];
+        d.a_dp[slot] = dp;
+        double ch = d.a_ch[slot];
+        const Mobility mob = mobility_epilogue(d.gas, V, vol_pp, dp, &ch);
+        d.a_ch[slot] = ch;
+        d.a_bulk[slot] = mob.bulk_density;
+        d.a_fagg[slot] = mob.f_agg;
+        d.a_dm[slot] = mob.d_m;
+        d.a_ts[slot] = mob.time_step;
+        d.a_lpm[slot] = mob.lpm;
+        d.a_dgdp[slot] = 2 * rg / dp;
+        atomic_max_positive_double(&d.sc->maxradius, rmax);
+    }
+    group_sync<kBlock>();
+}
+
+// K4 — AggregatList::merge + Aggregate::merge + ListStorage::merge/remove (aggregat_list.cpp:367-410,
+// aggregat.cpp:486-544): CTA-cooperative.  Returns (to every thread, uniformly) 1 when the aggregates were united.
+__device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int other_agg, double *scratch, double box) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const double4 pm = d.s_posr[ms], po = d.s_posr[os];
+    if (!spheres_in_contact(pm.x, pm.y, pm.z, pm.w, po.x, po.y, po.z, po.w, box)) return 0;  // aggregat_list.cpp:375
+    const int kept = moving_agg < other_agg ? moving_agg : other_agg;  // min(label) == min(slot)
+    const int removed = moving_agg < other_agg ? other_agg : moving_agg;
+    const int my = (kept == moving_agg) ? ms : os, oth = (kept == moving_agg) ? os : ms;
+    const int n_k = d.a_n[kept], n_r = d.a_n[removed], off_k = d.a_off[kept], off_r = d.a_off[removed];
+    const double newtime = d.a_ptime[kept] + d.a_ptime[removed] - d.sc->time;  // :387
+    const int total_charge = d.a_charge[kept] + d.a_charge[removed];
+    const double4 root = d.s_posr[off_k];
+    const double4 pmy = d.s_posr[my], poth = d.s_posr[oth];
+    const double4 rmy = d.s_relv[my], roth = d.s_relv[oth];
+    const double dcx = periodic_distance(poth.x - pmy.x, box), dcy = periodic_distance(poth.y - pmy.y, box),
+                 dcz = periodic_distance(poth.z - pmy.z, box);
+    const double fx = rmy.x + dcx - roth.x, fy = rmy.y + dcy - roth.y, fz = rmy.z + dcz - roth.z;  // aggregat.cpp:516-521
+    const int dst = d.sc->pool_top;
+    __syncthreads();  // everybody has read pool_top / the contact spheres before anything is rewritten
+    if (dst + n_k + n_r > d.sph_cap) {
+        if (tid == 0) d.sc->error = 1;
+        return 0;
+    }
+    for (int i = tid; i < n_k + n_r; i += nth) {
+        const bool from_removed = i >= n_k;
+        const int src = from_removed ? off_r + (i - n_k) : off_k + i;
+        double4 p = d.s_posr[src];
+        double4 rel = d.s_relv[src];
+        if (from_removed) {
+            rel.x += fx; rel.y += fy; rel.z += fz;                              // Sphere::relative_translate(diffpos)
+            p.x = rel.x + root.x; p.y = rel.y + root.y; p.z = rel.z + root.z;  // newpos = rel; newpos += refpos
+        }
+        const int t = dst + i;
+        d.s_posr[t] = p;
+        d.s_relv[t] = rel;
+        d.s_surf[t] = d.s_surf[src];
+        d.s_veff[t] = d.s_veff[src];
+        d.s_seff[t] = d.s_seff[src];
+        d.s_dcen[t] = d.s_dcen[src];
+        const int id = d.s_id[src];
+        d.s_id[t] = id;
+        d.s_charge[t] = d.s_charge[src];
+        d.slot_of_id[id] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        d.sc->pool_top = dst + n_k + n_r;
+        d.a_off[kept] = dst;
+        d.a_n[kept] = n_k + n_r;
+        d.a_alpha[kept] = 1.0 / static_cast<double>(n_k + n_r);
+        d.a_alive[removed] = 0;
+        d.a_n[removed] = 0;
+        d.sc->n_agg -= 1;
+    }
+    __syncthreads();
+    agg_update<true>(d, kept, true, tid, nth, scratch, box);
+    if (tid == 0) {
+        d.a_ptime[kept] = newtime;
+        d.a_charge[kept] = total_charge;
+    }
+    __syncthreads();
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 + orchestration — in-order commit of a speculative batch (single CTA).
+// Steps 0..B-1 were searched in parallel against the state at the start of the batch.  A step is valid iff no
+// EARLIER step of the batch moved the same aggregate or an aggregate that is, before or after its move, an
+// eligible suspect of this step (bounding-sphere sweep test of aggregat_list.cpp:510-532): then the sequential
+// algorithm would have computed exactly the same result.  The first contact ends the batch (its merge
+// re-sorts the pick table); the first conflict makes the next batch restart at that step.
+// ------------------------------------------------------------------------------------------------
+struct BatchArgs {
+    int nq;
+    const int *q_slot;
+    const double *q_dir;
+    const double *q_dist;
+    const SearchResult *res;
+    mcac_step_record *rec;  // device buffer or nullptr
+    long long rec_cap, rec_base;
+    long long max_steps;    // steps still allowed in this run call
+};
+__global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs b) {
+    __shared__ int sh_slot[kMaxBatch];
+    __shared__ unsigned char sh_contact[kMaxBatch];
+    __shared__ double sh_time[kMaxBatch + 1];
+    __shared__ double scratch[kUpdateScratch];
+    __shared__ double cap[8];  // contact step: dt, proper time, position right after the move
+    __shared__ int s_conf, s_contact, s_limit, s_finished;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    Scalars &sc = *d.sc;
+    const double box = sc.box_length;
+    const int nq = b.nq;
+    const int n_agg_before = sc.n_agg;
+    const long long steps_before = sc.steps_done, rand_before = sc.rand_pos, iter_before = sc.n_iter_without_event;
+    const double dt_base = sc.max_time_step / sc.cum_total;  // AggregatList::get_time_step(max), aggregat_list.cpp:54-58
+    if (tid == 0) { s_conf = nq; s_contact = nq; s_limit = nq; s_finished = 0; }
+    for (int j = tid; j < nq; j += nth) {
+        sh_slot[j] = b.q_slot[j];
+        sh_contact[j] = (b.res[j].distance <= b.q_dist[j]) ? 1 : 0;  // `next_contact <= full_distance`, calcul.cpp:128
+    }
+    __syncthreads();
+    // ---- stop conditions evaluated at the top of every step (PhysicalModel::finished, physical_model.cpp:288-337)
+    if (tid == 0) {
+        double t = sc.time;
+        int lim = nq;
+        if ((long long)lim > b.max_steps) lim = (int)b.max_steps;
+        for (int j = 0; j < nq; j++) {
+            sh_time[j] = t;
+            const bool fin = (d.time_limit > 0 && t >= d.time_limit) || (d.n_iter_limit > 0 && iter_before + j >= d.n_iter_limit);
+            if (fin && j < lim) { lim = j; s_finished = 1; }
+            t = t + dt_base;  // free flight: dt * (lpm/lpm + 0) == dt
+        }
+        sh_time[nq] = t;
+        s_limit = lim;
+    }
+    for (int j = tid; j < nq; j += nth)
+        if (sh_contact[j]) atomicMin(&s_contact, j);
+    // ---- conflicts with earlier movers of the batch
+    for (int j = tid; j < nq; j += nth) {
+        const int sj = sh_slot[j];
+        const double4 aj = d.a_posr[sj];
+        const double dj = b.q_dist[j];
+        const double djx = b.q_dir[3 * j], djy = b.q_dir[3 * j + 1], djz = b.q_dir[3 * j + 2];
+        bool conflict = false;
+        for (int i = 0; i < j && !conflict; i++) {
+            const int si = sh_slot[i];
+            if (si == sj) { conflict = true; break; }
+            const double4 ai = d.a_posr[si];
+            const double di = b.q_dist[i];
+            const double guard = (dj + di + aj.w + ai.w) * (1. + 1e-9) + 1e-9 * box;
+            const double ex = fabs(periodic_distance(aj.x - ai.x, box)), ey = fabs(periodic_distance(aj.y - ai.y, box)),
+                         ez = fabs(periodic_distance(aj.z - ai.z, box));
+            if (ex > guard || ey > guard || ez > guard) continue;
+            const double before = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, ai.x, ai.y, ai.z, ai.w, djx, djy, djz, dj, box);
+            const double nx = periodic_position(ai.x + b.q_dir[3 * i] * di, box), ny = periodic_position(ai.y + b.q_dir[3 * i + 1] * di, box),
+                         nz = periodic_position(ai.z + b.q_dir[3 * i + 2] * di, box);
+            const double after = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, nx, ny, nz, ai.w, djx, djy, djz, dj, box);
+            if (before < dj || after < dj) conflict = true;
+        }
+        if (conflict) atomicMin(&s_conf, j);
+    }
+    __syncthreads();
+    int stop = s_limit;
+    int reason = s_finished ? STOP_FINISHED : STOP_BATCH_END;
+    if (s_conf < stop) { stop = s_conf; reason = STOP_CONFLICT; }
+    const bool do_contact = s_contact < stop;  // the contact step is valid (no conflict before it) and allowed
+    if (do_contact) { stop = s_contact; reason = STOP_CONTACT; }
+    // ---- commit the free-flight steps [0, stop): distinct aggregates, one warp per step
+    for (int j = warp; j < stop; j += nwarps) {
+        const int sj = sh_slot[j];
+        const double dj = b.q_dist[j];
+        agg_translate<false>(d, sj, b.q_dir[3 * j] * dj, b.q_dir[3 * j + 1] * dj, b.q_dir[3 * j + 2] * dj, box, lane, 32);
+        if (lane == 0) d.a_ptime[sj] += dt_base * (dj / dj + 0.0);  // calcul.cpp:147-149 with move == full, n_try == 1
+    }
+    __syncthreads();
+    int merged = 0;
+    if (do_contact) {
+        const int j = stop;
+        const int sj = sh_slot[j];
+        const SearchResult r = b.res[j];
+        const double full = b.q_dist[j], move = r.distance;
+        agg_translate<true>(d, sj, b.q_dir[3 * j] * move, b.q_dir[3 * j + 1] * move, b.q_dir[3 * j + 2] * move, box, tid, nth);
+        if (tid == 0) {
+            const double dt = dt_base * (move / full + 0.0);
+            d.a_ptime[sj] += dt;
+            sc.time = sh_time[j] + dt;
+            const double4 a = d.a_posr[sj];
+            cap[0] = dt; cap[1] = d.a_ptime[sj]; cap[2] = a.x; cap[3] = a.y; cap[4] = a.z;
+        }
+        __syncthreads();
+        merged = agg_merge(d, r.moving_slot, r.other_slot, sj, r.other_agg, scratch, box);
+    } else if (tid == 0) {
+        sc.time = sh_time[stop];
+    }
+    __syncthreads();
+    // ---- trace records (tests / replay), one per committed step.  Old sphere slots stay readable after a merge.
+    const int done = stop + (do_contact ? 1 : 0);
+    if (b.rec) {
+        for (int j = tid; j < done; j += nth) {
+            const long long at = b.rec_base + j;
+            if (at >= b.rec_cap) continue;
+            const SearchResult r = b.res[j];
+            const bool is_contact = do_contact && j == stop;
+            const bool has = r.other_agg >= 0;
+            mcac_step_record o;
+            o.step = steps_before + j;
+            o.rand_calls = rand_before + 3LL * (j + 1);
+            o.source = d.label_of_slot[sh_slot[j]];
+            o.dir[0] = b.q_dir[3 * j]; o.dir[1] = b.q_dir[3 * j + 1]; o.dir[2] = b.q_dir[3 * j + 2];
+            o.full_distance = b.q_dist[j];
+            o.distance = r.distance;
+            o.moving_sphere = has ? (long long)d.s_id[r.moving_slot] : -1;
+            o.other_sphere = has ? (long long)d.s_id[r.other_slot] : -1;
+            o.moving_label = has ? (long long)d.label_of_slot[sh_slot[j]] : -1;
+            o.other_label = has ? (long long)d.label_of_slot[r.other_agg] : -1;
+            o.n_agg_before = n_agg_before;
+            o.time_before = sh_time[j];
+            if (is_contact) {
+                o.dt = cap[0]; o.proper_time_after = cap[1];
+                o.pos_after[0] = cap[2]; o.pos_after[1] = cap[3]; o.pos_after[2] = cap[4];
+            } else {
+                const double4 a = d.a_posr[sh_slot[j]];
+                o.dt = dt_base * (b.q_dist[j] / b.q_dist[j] + 0.0);
+                o.proper_time_after = d.a_ptime[sh_slot[j]];
+                o.pos_after[0] = a.x; o.pos_after[1] = a.y; o.pos_after[2] = a.z;
+            }
+            o.merged = is_contact ? merged : 0;
+            o.n_try = 1;
+            b.rec[at] = o;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sc.steps_done = steps_before + done;
+        sc.rand_pos = rand_before + 3LL * done;
+        sc.searches += done;
+        long long ps = 0, pb = 0;
+        for (int j = 0; j < done; j++) { ps += b.res[j].n_sphere_pairs; pb += b.res[j].n_bounding; }
+        sc.pair_sphere += ps;
+        sc.pair_bounding += pb;
+        if (reason == STOP_CONFLICT) sc.conflicts += 1;
+        if (merged) {
+            sc.n_iter_without_event = 0;
+            sc.total_events += 1;
+            sc.event = 1;
+        } else if (done > 0) {
+            sc.n_iter_without_event = iter_before + done;
+            sc.event = 0;
+        }
+        sc.b_committed = done;
+        sc.b_stop_reason = reason;
+        sc.b_contact = do_contact ? 1 : 0;
+        sc.b_merged = merged;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Event pipeline: AggregatList::refresh + get_total_volume/surface (aggregat_list.cpp:100-108, 28-45) as a
+// deterministic two-phase reduction, and the 1/dt weights of sort_time_steps (:124-131) in label order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kReduceThreads = 256;
+__global__ void __launch_bounds__(kReduceThreads) k_refresh_partials(DevState d, double *partials /* 3 x gridDim */) {
+    __shared__ double sm[3][kReduceThreads / 32];
+    const int n = d.sc->n_agg_slots;
+    double mx = 0., sv = 0., ss = 0.;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        if (!d.a_alive[s]) continue;
+        const double ts = d.a_ts[s];
+        mx = (mx < ts) ? ts : mx;
+        sv += d.a_vol[s];
+        ss += d.a_surf[s];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omx = __shfl_xor_sync(kFull, mx, o);
+        mx = (mx < omx) ? omx : mx;
+        sv += __shfl_xor_sync(kFull, sv, o);
+        ss += __shfl_xor_sync(kFull, ss, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sm[0][w] = mx; sm[1][w] = sv; sm[2][w] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int ww = 1; ww < kReduceThreads / 32; ww++) {
+            mx = (mx < sm[0][ww]) ? sm[0][ww] : mx;
+            sv += sm[1][ww];
+            ss += sm[2][ww];
+        }
+        partials[blockIdx.x] = mx;
+        partials[gridDim.x + blockIdx.x] = sv;
+        partials[2 * gridDim.x + blockIdx.x] = ss;
+    }
+}
+__global__ void k_refresh_final(DevState d, const double *partials, int nb) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mx = 0., sv = 0., ss = 0.;
+    for (int b = 0; b < nb; b++) {
+        mx = (mx < partials[b]) ? partials[b] : mx;
+        sv += partials[nb + b];
+        ss += partials[2 * nb + b];
+    }
+    Scalars &sc = *d.sc;
+    sc.max_time_step = mx;
+    sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg);
+    sc.total_volume = sv;
+    sc.total_surface = ss;
+    // PhysicalModel::update, physical_model.cpp:489-498
+    sc.total_volume_concent = sv / sc.box_volume;
+    sc.total_surface_concent = ss / sc.box_volume;
+    sc.aggregate_concentration = static_cast<double>(sc.n_agg) / sc.box_volume;
+    sc.monomer_concentration = static_cast<double>(sc.n_sph) / sc.box_volume;
+    sc.volume_fraction = sv / sc.box_volume;
+}
+__global__ void k_make_keys(DevState d, double factor) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= d.sc->n_agg) return;
+    d.keys[l] = factor / d.a_ts[d.slot_of_label[l]];
+}
+// sorted labels -> slots, cumulative table already uploaded / scanned
+__global__ void k_sorted_labels_to_slots(DevState d, const int *sorted_label, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d.sorted_slot[i] = d.slot_of_label[sorted_label[i]];
+    if (i == 0) { d.sc->n_pick = n; d.sc->cum_total = d.cum[n - 1]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 — surface growth of every sphere (Sphere::croissance_surface, sphere.cpp:113-120 through the chain
+// aggregat_list.cpp:549-579): elementwise over the sphere pool, 8 B in / 24 B out per sphere.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grow(DevState d, double dt, int only_slot) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = 0, hi = d.sc->pool_top;
+    if (only_slot >= 0) { lo = d.a_off[only_slot]; hi = lo + d.a_n[only_slot]; }
+    const int t = lo + s;
+    if (t >= hi) return;
+    double4 p = d.s_posr[t];
+    const double new_r = p.w + d.u_sg * dt;  // PhysicalModel::grow, physical_model.cpp:587-590
+    const double r2 = new_r * new_r;
+    const double r3 = r2 * new_r;
+    p.w = new_r;
+    d.s_posr[t] = p;
+    double4 rel = d.s_relv[t];
+    rel.w = volume_factor() * r3;
+    d.s_relv[t] = rel;
+    d.s_surf[t] = surface_factor() * r2;
+    if (new_r <= d.rp_min_oxid) d.sc->error = 1;  // sphere removal by oxidation (u_sg < 0) is outside the built path
+}
+// K5-K7 over ALL aggregates (growth mode, calcul.cpp:184-206): one warp per aggregate
+__global__ void __launch_bounds__(256) k_update_all(DevState d, int full, int only_slot) {
+    __shared__ double scratch[8][kUpdateScratch / 4];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int slot = blockIdx.x * 8 + w;
+    if (only_slot >= 0) { if (slot != 0) return; slot = only_slot; }
+    if (slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
+    agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], d.sc->box_length);
+}
+// single-aggregate entry points of the per-call C ABI
+__global__ void __launch_bounds__(kCommitThreads) k_translate_one(DevState d, int slot, double vx, double vy, double vz) {
+    agg_translate<true>(d, slot, vx, vy, vz, d.sc->box_length, threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(kCommitThreads) k_merge_one(DevState d, int ms_id, int os_id, int *merged_out) {
+    __shared__ double scratch[kUpdateScratch];
+    const int ms = d.slot_of_id[ms_id], os = d.slot_of_id[os_id];
+    // owning aggregates from the pool: search the aggregate whose block holds the slot (labels are not stored per sphere)
+    __shared__ int owner[2];
+    if (threadIdx.x == 0) { owner[0] = -1; owner[1] = -1; }
+    __syncthreads();
+    for (int s = threadIdx.x; s < d.sc->n_agg_slots; s += blockDim.x) {
+        if (!d.a_alive[s]) continue;
+        const int off = d.a_off[s], n = d.a_n[s];
+        if (ms >= off && ms < off + n) owner[0] = s;
+        if (os >= off && os < off + n) owner[1] = s;
+    }
+    __syncthreads();
+    const int merged = (owner[0] >= 0 && owner[1] >= 0 && owner[0] != owner[1])
+                           ? agg_merge(d, ms, os, owner[0], owner[1], scratch, d.sc->box_length) : 0;
+    if (threadIdx.x == 0) {
+        *merged_out = merged;
+        if (merged) { d.sc->total_events += 1; d.sc->event = 1; d.sc->n_iter_without_event = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pool compaction: live aggregates re-packed in slot (= label) order into the alternate sphere buffers.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_compact_counts(DevState d, int *counts) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.sc->n_agg_slots) return;
+    counts[s] = d.a_alive[s] ? d.a_n[s] : 0;
+}
+__global__ void __launch_bounds__(256) k_compact_move(DevState d, DevState dst, const int *new_off) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + w;
+    if (slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
+    const int off = d.a_off[slot], n = d.a_n[slot], to = new_off[slot];
+    for (int i = lane; i < n; i += 32) {
+        dst.s_posr[to + i] = d.s_posr[off + i];
+        dst.s_relv[to + i] = d.s_relv[off + i];
+        dst.s_surf[to + i] = d.s_surf[off + i];
+        dst.s_veff[to + i] = d.s_veff[off + i];
+        dst.s_seff[to + i] = d.s_seff[off + i];
+        dst.s_dcen[to + i] = d.s_dcen[off + i];
+        const int id = d.s_id[off + i];
+        dst.s_id[to + i] = id;
+        dst.s_charge[to + i] = d.s_charge[off + i];
+        d.slot_of_id[id] = to + i;
+    }
+    __syncwarp();
+    if (lane == 0) d.a_off[slot] = to;
+}
+__global__ void k_compact_finish(DevState d, const int *new_off) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) d.sc->pool_top = new_off[d.sc->n_agg_slots];
+}
+
+
+// Domain duplication (AggregatList::duplication, aggregat_list.cpp:142-190), device part: the 7 copies of every
+// aggregate (labels n0 + 7a + c-1, c = 4i+2j+k) are translated by (i,j,k)*old_box with the NEW box length, and every
+// aggregate's Verlet cell is recomputed for the doubled box.  One warp per aggregate.
+__global__ void __launch_bounds__(256) k_dup_finish(DevState d, int n0, double old_l) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + w;
+    if (slot >= d.sc->n_agg_slots) return;
+    const double box = d.sc->box_length;
+    if (slot >= n0) {
+        const int c = (slot - n0) % 7 + 1;
+        agg_translate<false>(d, slot, ((c >> 2) & 1) * old_l, ((c >> 1) & 1) * old_l, (c & 1) * old_l, box, lane, 32);
+    } else if (lane == 0) {
+        const double4 a = d.a_posr[slot];
+        d.a_cx[slot] = cell_of(a.x, d.n_div, box);
+        d.a_cy[slot] = cell_of(a.y, d.n_div, box);
+        d.a_cz[slot] = cell_of(a.z, d.n_div, box);
+    }
+}
+
+}  // namespace mcacb

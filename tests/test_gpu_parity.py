@@ -1,0 +1,151 @@
+"""Parity of the CUDA path (through the C ABI of libmcac_b200.so) against the oracle — run on the B200 with -m gpu.
+
+Bar (BASELINE.json north_star): bit-exact for integer / indexing work (picked aggregate, RNG position, chosen
+collision partner, merge order, labels, membership, cells); <= 1e-12 relative for FP64 quantities.  The pair test
+itself only uses +,-,*,/,sqrt,fmod,floor, so on identical inputs it is compared BIT-EXACTLY.
+"""
+import numpy as np
+import pytest
+
+import ref_trace as rt
+from golden_lib import Golden
+from oracle.run_ref import merged_config
+from oracle_lib import Oracle, rand_stream
+
+import mcac_b200
+from mcac_b200 import HostModel, Simulation, ini_text
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+INT_FIELDS = ["step", "rand_calls", "source", "moving_sphere", "other_sphere", "moving_label", "other_label", "n_agg", "merged", "n_try"]
+FP_FIELDS = ["dir", "full_distance", "distance", "time", "dt", "proper_time", "pos"]
+
+
+def assert_records_match(got, ref, box):
+    n = min(len(got), len(ref))
+    assert n > 0
+    for f in INT_FIELDS:
+        bad = np.nonzero(got[f][:n] != ref[f][:n])[0]
+        assert len(bad) == 0, f"{f}: first divergence at step {bad[0]}: gpu {got[f][bad[0]]} vs oracle {ref[f][bad[0]]}"
+    fin = np.isfinite(ref["distance"][:n])
+    assert np.array_equal(fin, np.isfinite(got["distance"][:n]))
+    np.testing.assert_allclose(got["distance"][:n][fin], ref["distance"][:n][fin], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(got["dir"][:n], ref["dir"][:n], rtol=0, atol=4e-16)  # unit vector: 2 ulp of CUDA sincos/acos
+    for f in ["full_distance", "time", "dt", "proper_time"]:
+        np.testing.assert_allclose(got[f][:n], ref[f][:n], rtol=RTOL, atol=0, err_msg=f)
+    np.testing.assert_allclose(got["pos"][:n], ref["pos"][:n], rtol=0, atol=RTOL * box, err_msg="pos")
+
+
+def assert_states_match(got, ref, box):
+    assert got["n_sph"] == ref["n_sph"] and got["n_agg"] == ref["n_agg"]
+    for k in ["sphere_label", "agg_n_spheres", "members", "offsets", "agg_cell"]:
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    for k in ["x", "y", "z", "rx", "ry", "rz"]:
+        np.testing.assert_allclose(got["spheres"][k], ref["spheres"][k], rtol=0, atol=RTOL * box, err_msg=f"sphere {k}")
+    for k in ["r", "volume", "surface"]:
+        np.testing.assert_allclose(got["spheres"][k], ref["spheres"][k], rtol=RTOL, atol=0, err_msg=f"sphere {k}")
+    for k in ["x", "y", "z", "rx", "ry", "rz"]:
+        np.testing.assert_allclose(got["aggregates"][k], ref["aggregates"][k], rtol=0, atol=RTOL * box, err_msg=f"aggregate {k}")
+    for k in ["rg", "f_agg", "lpm", "time_step", "rmax", "volume", "surface", "proper_time", "dp", "dg_over_dp", "overlapping",
+              "coordination_number", "d_m"]:
+        np.testing.assert_allclose(got["aggregates"][k], ref["aggregates"][k], rtol=RTOL, atol=1e-300, err_msg=f"aggregate {k}")
+    for k in ["member_volumes", "member_surfaces"]:
+        np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=0, err_msg=k)
+    np.testing.assert_allclose(got["member_distances_center"], ref["member_distances_center"], rtol=0, atol=RTOL * box)
+    for k in ["time", "box_length", "maxradius", "max_time_step", "avg_npp"]:
+        np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, err_msg=k)
+
+
+def test_device_rng_is_the_glibc_stream():
+    text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 42}, "monomers": {"number": 50}}))
+    sim = Simulation(text)
+    consumed = HostModel(text).state()["rand_consumed"]
+    n = 3_000_000  # crosses two refills of the device buffer
+    got = sim.rand(n)
+    ref = rand_stream(42, consumed + n)[consumed:]
+    np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("base,ov", [
+    ("monodisperse", {"numerics": {"random_seed": 42}}),
+    ("polydisperse", {"numerics": {"random_seed": 42, "n_verlet_divisions": 12}, "monomers": {"number": 4000}}),
+    ("brownian", {"numerics": {"random_seed": 42, "n_verlet_divisions": 16, "with_collisions": "true", "pick_method": "random"},
+                  "environment": {"volume_fraction": "1000e-6"}, "monomers": {"number": 4000}, "limits": {"physical_time": -1}}),
+])
+def test_contact_search_on_initial_state_bit_exact(base, ov):
+    """K1 vs AggregatList::distance_to_next_contact on identical state and identical directions: bit-exact."""
+    text = ini_text(merged_config(base, ov))
+    sim = Simulation(text)
+    o = Oracle(base, ov)
+    st = o.state()
+    rng = np.random.default_rng(1)
+    n_agg = st["n_agg"]
+    labels = rng.integers(0, n_agg, 600)
+    v = rng.normal(size=(600, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    # long sweeps so that a good share of the queries really hit something
+    dist = st["aggregates"]["lpm"][labels] * rng.choice([1.0, 30.0, 300.0], 600)
+    got, pairs = sim.contact_search_batch(labels, v, dist)
+    hits = 0
+    for q in range(600):
+        d, ids = o.search(int(labels[q]), v[q], float(dist[q]))
+        if np.isinf(d):
+            assert np.isinf(got["distance"][q])
+            continue
+        hits += 1
+        assert got["distance"][q] == d, (q, got["distance"][q], d)
+        assert (got["moving_sphere"][q], got["other_sphere"][q], got["moving_label"][q], got["other_label"][q]) == tuple(ids)
+    assert hits > 20
+    c = o.counters()
+    assert pairs[0] == c["pair_sphere"] and pairs[1] == c["pair_bounding"]
+
+
+@pytest.mark.parametrize("name,steps,batch", [("monodisperse_seed42", 60000, 128), ("c3_small_seed42", 40000, 256),
+                                              ("c2_small_seed42", 30000, 256), ("polydisperse_seed42", 30000, 64)])
+def test_run_replays_the_collision_sequence(name, steps, batch):
+    """The device-resident loop (speculative batches + in-order commit) against the oracle, step by step."""
+    g = Golden(name)
+    text = ini_text(merged_config(g.base, g.overrides))
+    sim = Simulation(text)
+    rep, recs = sim.run(steps, batch=batch, records=steps)
+    o = Oracle(g.base, g.overrides)
+    ref = o.run(steps)
+    box = o.scalars()["box_length"]
+    assert rep["steps"] == len(ref)
+    assert_records_match(recs, ref, box)
+    assert rep["events"] == int(ref["merged"].sum())
+    c = o.counters()
+    assert rep["pair_tests_sphere"] == c["pair_sphere"] and rep["pair_tests_bounding"] == c["pair_bounding"]
+    assert_states_match(sim.state(), o.state(), box)
+    # structural invariant pinned by the reference (pymcac/tests/test_data.py:166-205)
+    st = sim.state()
+    np.testing.assert_array_equal(np.bincount(st["sphere_label"], minlength=st["n_agg"]), st["agg_n_spheres"])
+
+
+def test_batch_width_does_not_change_the_trajectory():
+    """Speculation must be invisible: batch = 1 (pure sequential) and batch = 512 give bit-identical device results."""
+    text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 3}}))
+    a = Simulation(text); b = Simulation(text)
+    ra, reca = a.run(20000, batch=1, records=20000)
+    rb, recb = b.run(20000, batch=512, records=20000)
+    assert ra["steps"] == rb["steps"]
+    for f in INT_FIELDS + FP_FIELDS:
+        np.testing.assert_array_equal(reca[f], recb[f], err_msg=f)
+    assert rb["batches"] < ra["batches"]
+
+
+def test_monodisperse_full_run_through_two_duplications():
+    """C1 literal: 800 -> 6400 -> 51200 spheres, 1 000 452 steps, 1 688 merges — decisions via the golden digest."""
+    g = Golden("monodisperse_seed42")
+    sim = Simulation(ini_text(merged_config(g.base, g.overrides)))
+    rep, recs = sim.run(2_000_000, batch=256, records=1_100_000)
+    assert rep["finished"] == 1
+    assert rep["steps"] == g.meta["total_steps"]
+    assert rep["events"] == 1688 and rep["duplications"] == 2
+    np.testing.assert_array_equal(np.nonzero(recs["merged"])[0], g.merges["step"][g.merges["ok"] == 1])
+    fin = g.state("state_final")
+    st = sim.state()
+    np.testing.assert_array_equal(st["sphere_label"], fin["sphere_label"])
+    np.testing.assert_array_equal(st["members"], fin["members"])
+    np.testing.assert_allclose(st["aggregates"]["rg"], fin["aggregates"]["rg"], rtol=1e-9)
+    np.testing.assert_allclose(st["time"], fin["time"], rtol=1e-9)
