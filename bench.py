@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — MC steps/s and contact-pair tests/s of the per-step aggregation hot path at N = 1e6 (BASELINE.json).
+
+Workload (config.workload = "c3"): validation/params_brownian.ini scaled as SURVEY.md §8d prescribes —
+number=1e6, volume_fraction=1000e-6, n_verlet_divisions=100, with_collisions=true, pick_method=random, duplication
+off, random_seed=42(+rank): monodisperse 30 nm monomers, the reference's own placement procedure.  One bench
+"step" = `--mc-steps` consecutive MC steps of one realization (pick -> direction -> contact search -> translate ->
+merge/update).  N GPUs = N independent realizations (the path does not shard: replicas only, weak scaling),
+followed by one NCCL all-gather of the morphology statistics.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n-monomers 1000000] [--mc-steps 20000]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "mc_steps_per_sec_at_N1e6"
+UNIT = "MC steps/s"
+
+
+def workload_config(n_monomers: int, seed: int) -> tuple[str, dict]:
+    ov = {"monomers": {"number": n_monomers}, "environment": {"volume_fraction": "1000e-6"},
+          "limits": {"physical_time": -1},
+          "numerics": {"with_collisions": "true", "pick_method": "random", "n_verlet_divisions": 100 if n_monomers >= 200000 else 16,
+                       "with_domain_duplication": "false", "random_seed": seed}}
+    return "brownian", ov
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_run(n_monomers: int, seed: int, mc_steps: int, n_chunks: int) -> dict:
+    """The reference's own CPU implementation of the path (oracle/_ref/MCAC_tap = unmodified sources + counters), one thread
+    (the reference is single-threaded), bounded sample: n_chunks x mc_steps MC steps after its own initial placement."""
+    from oracle.run_ref import read_summary, run_reference
+
+    base, ov = workload_config(n_monomers, seed)
+    ov["output"] = {"write_between_event_frequency": 1000000000, "write_events_frequency": 1000000000}
+    kind = "reference"
+    exe = ROOT / "oracle" / "_ref" / "MCAC_tap"
+    if not exe.exists():
+        raise FileNotFoundError("oracle/_ref/MCAC_tap is not built")
+    t0 = time.perf_counter()
+    wd, _ = run_reference(base, ov, env={"MCAC_TAP_EXIT_STEP": mc_steps * n_chunks, "MCAC_TAP_CHUNK": mc_steps})
+    total_wall = time.perf_counter() - t0
+    s = read_summary(wd)
+    shutil.rmtree(wd, ignore_errors=True)
+    ct = [0.0] + s["chunk_times"]
+    chunk_s = [b - a for a, b in zip(ct[:-1], ct[1:])]
+    return dict(kind=kind, chunk_s=chunk_s, steps=s["steps"], pair_tests=s["pair_tests_sphere"] + s["pair_tests_bounding"],
+                calcul_wall_s=s["calcul_wall_s"], init_s=total_wall - s["calcul_wall_s"])
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mcac_b200", choices=["mcac_b200", "reference"])
+    ap.add_argument("--n-monomers", type=int, default=1_000_000)
+    ap.add_argument("--mc-steps", type=int, default=0, help="MC steps per bench step (default 20000; 400 for --impl reference)")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    K, W = a.steps, max(a.warmup, 0)
+    config = {"workload": "c3", "ini": "validation/params_brownian.ini + number, volume_fraction=1000e-6, n_verlet_divisions=100, "
+              "with_collisions=true, pick_method=random, with_domain_duplication=false", "n_monomers": a.n_monomers,
+              "volume_fraction_ppm": 1000, "random_seed": "42+rank", "parallelism": f"replicas x{a.gpus} (independent realizations)",
+              "l2": "state (>300 MB of sphere + aggregate SoA at N=1e6) exceeds the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        M = a.mc_steps or 400
+        try:
+            r = reference_run(a.n_monomers, 42, M, W + K)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+            return
+        timed = r["chunk_s"][W:W + K]
+        value = M * len(timed) / sum(timed)
+        config["mc_steps_per_step"] = M
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * sum(timed) / len(timed), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                 "sample": f"{W + K} x {M} MC steps of the same N={a.n_monomers} workload, one thread, "
+                                           f"placement ({r['init_s']:.1f} s) excluded, cpu: {cpu_model()}"},
+                "pair_tests_per_sec": r["pair_tests"] / r["calcul_wall_s"],
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import numpy as np
+    import torch
+
+    import mcac_b200
+    from oracle.run_ref import merged_config  # config dict literals only (no oracle code is executed on this arm)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mcac_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    M = a.mc_steps or 20000
+    config["mc_steps_per_step"] = M
+    config["batch"] = a.batch
+    base, ov = workload_config(a.n_monomers, 42 + rank)
+    text = mcac_b200.ini_text(merged_config(base, ov))
+    t0 = time.perf_counter()
+    sim = mcac_b200.Simulation(text, device=local)
+    init_s = time.perf_counter() - t0
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        sim.run(M, batch=a.batch)
+    sim.set_profile(True)
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    t_wall = time.perf_counter()
+    reps = [sim.run(M, batch=a.batch)[0] for _ in range(K)]
+    sync_all()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    sim.set_profile(False)
+    dev_ms = sum(r["device_ms"] for r in reps)
+    steps_done = sum(r["steps"] for r in reps)
+    pair_tests = sum(r["pair_tests_sphere"] + r["pair_tests_bounding"] for r in reps)
+    t = torch.tensor([dev_ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(steps_done), float(pair_tests), float(sum(r["kernel_launches"] for r in reps))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    max_ms = float(t[0])
+    value = float(tot[0]) / (max_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (K1 contact search), measured live with CUDA events on the handle's stream
+    searches = sum(r["searches"] for r in reps)
+    ps = sum(r["pair_tests_sphere"] for r in reps); pb = sum(r["pair_tests_bounding"] for r in reps)
+    n_launch = max(1, sum(r["search_launches"] for r in reps))
+    search_ms = sum(r["search_ms"] for r in reps)
+    commit_ms = sum(r["commit_ms"] for r in reps)
+    # algorithmic bytes per search (restated for aggregate-level candidates): 36 B per bounding test
+    # (x,y,z,rmax + slot id), 32 B per sphere of the sphere-level sweep (moving + other), 48 B of result
+    alg_bytes = 36.0 * pb + 32.0 * (ps + searches) + 48.0 * searches
+    peaks = {}
+    try:
+        peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
+    roofline = {"kernel": "k_search (K1, speculative batch inside the MC loop)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "launches": n_launch, "avg_launch_us": 1e3 * search_ms / n_launch, "algorithmic_bytes_per_launch": alg_bytes / n_launch,
+                "share_of_step": search_ms / dev_ms if dev_ms else None, "commit_share_of_step": commit_ms / dev_ms if dev_ms else None}
+    # the same kernel fed with one launch of ~3.5e5 independent searches (what an ensemble / wide speculation gives it)
+    sw = sim.search_sweep(349000, repeats=3)
+    sw_bytes = 36.0 * sw["pair_tests_bounding"] + 32.0 * (sw["pair_tests_sphere"] + sw["n_queries"]) + 48.0 * sw["n_queries"]
+    sw_gbs = sw_bytes / (sw["kernel_ms"] * 1e-3) / 1e9
+    roofline_sweep = {"kernel": "k_search, one launch of %d searches" % sw["n_queries"], "bound": "hbm", "achieved": sw_gbs, "peak": peak,
+                      "unit": "GB/s", "frac": sw_gbs / peak, "traffic": None, "kernel_ms": sw["kernel_ms"],
+                      "pair_tests_per_sec": (sw["pair_tests_bounding"] + sw["pair_tests_sphere"]) / (sw["kernel_ms"] * 1e-3),
+                      "searches_per_sec": sw["n_queries"] / (sw["kernel_ms"] * 1e-3)}
+
+    # ---- e2e: the same metric through the C ABI with HOST buffers: upload_state (H2D) + run + download_state (D2H) per step
+    e2e = None
+    if a.e2e_steps > 0:
+        st = sim.state()
+        h2d = d2h = 0
+        torch.cuda.synchronize()
+        t_e = time.perf_counter()
+        steps_e = 0
+        for _ in range(a.e2e_steps):
+            up = dict(sphere_fields=np.stack([st["spheres"][k] for k in mcac_b200.SPHERE_FIELDS]),
+                      agg_fields=np.stack([st["aggregates"][k] for k in mcac_b200.AGG_FIELDS]), sphere_charge=st["sphere_charge"],
+                      agg_charge=st["agg_charge"], agg_cell=st["agg_cell"], offsets=st["offsets"], members=st["members"],
+                      per_member=np.stack([st["member_volumes"], st["member_surfaces"], st["member_distances_center"]]),
+                      maxradius=st["maxradius"], max_time_step=st["max_time_step"])
+            sim.upload(up)
+            r, _ = sim.run(M, batch=a.batch)
+            st = sim.state()
+            steps_e += r["steps"]
+            h2d = sum(v.nbytes for v in up.values() if hasattr(v, "nbytes"))
+            d2h = h2d + st["sphere_label"].nbytes + st["agg_n_spheres"].nbytes + 160
+        torch.cuda.synchronize()
+        e_s = time.perf_counter() - t_e
+        e = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+        es = torch.tensor([float(steps_e)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(es, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(es[0]) / float(e[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "what": "mcac_gpu_upload_state(host SoA) + mcac_gpu_run + mcac_gpu_download_state(host SoA) per step, wall clock"}
+
+    # ---- the only collective of the path: all-gather of the per-realization morphology statistics (K11)
+    n_bins = 24
+    stats = torch.zeros(2 * n_bins + 8, dtype=torch.float64, device="cuda")
+    sim.morphology_stats_device(stats.data_ptr(), n_bins, 2e-6)
+    ensemble = None
+    if world > 1:
+        gathered = torch.zeros(world * (2 * n_bins + 8), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(gathered, stats)
+        g = gathered.view(world, -1).cpu().numpy()
+    else:
+        g = stats.view(1, -1).cpu().numpy()
+    if rank == 0:
+        tail = g[:, 2 * n_bins:]
+        ensemble = {"realizations": int(g.shape[0]), "n_agg": [int(x) for x in tail[:, 0]], "mean_npp": [float(x[1] / x[0]) for x in tail],
+                    "mean_rg_nm": [float(1e9 * x[7] / x[0]) for x in tail]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            Mr = 400
+            r = reference_run(a.n_monomers, 42, Mr, 8)
+            timed = r["chunk_s"][2:]
+            cpu_baseline = {"value": Mr * len(timed) / sum(timed), "unit": UNIT, "cores": 1, "kind": r["kind"],
+                            "sample": f"{len(timed)} x {Mr} MC steps of the same N={a.n_monomers} workload (seed 42) after 2 warm-up chunks, one thread "
+                                      f"(the reference is single-threaded), placement ({r['init_s']:.1f} s) excluded, cpu: {cpu_model()}",
+                            "pair_tests_per_sec": r["pair_tests"] / r["calcul_wall_s"]}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {str(e)[:160]}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "pair_tests_per_sec": float(tot[1]) / (max_ms * 1e-3), "mc_steps_timed": int(tot[0]),
+                "events_timed": sum(r["events"] for r in reps), "wall_ms_per_step": float(t[1]) / K, "init_placement_s": init_s,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[2]), "roofline": roofline, "roofline_sweep": roofline_sweep,
+                "cpu_baseline": cpu_baseline, "ensemble_stats": ensemble}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,7 +77,16 @@ typedef struct mcac_run_report {
     int64_t n_aggregates, n_spheres, finished;
     double time, box_length, avg_npp, max_time_step, volume_fraction;
     double device_ms;                      /* CUDA-event time of the whole call on the handle's stream */
+    double search_ms, commit_ms;           /* CUDA-event time spent in the K1 / commit+merge kernels (profile != 0) */
+    int64_t search_launches, commit_launches;
 } mcac_run_report;
+
+/* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction
+ * exactly as in calcul(), nothing committed, stream position restored): the batched form of the contact search. */
+typedef struct mcac_sweep_report {
+    int64_t n_queries, contacts, pair_tests_sphere, pair_tests_bounding;
+    double distance_checksum, kernel_ms;
+} mcac_sweep_report;
 
 /* --- lifetime ------------------------------------------------------------------------------- */
 /* AggregatList::AggregatList(PhysicalModel*) minus placement (src/aggregats/aggregat_list_storage.cpp:52-88) */
@@ -135,10 +144,15 @@ int mcac_gpu_rand(mcac_gpu *h, int64_t n, int32_t *out);
  * may be NULL) receives one mcac_step_record per step; `batch` = speculative batch width (0 = default). */
 int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record *records, int64_t n_records, mcac_run_report *report);
 
+int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_report *report);
+/* profile != 0: mcac_gpu_run brackets its K1 / commit launches with CUDA events (reported in mcac_run_report) */
+int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile);
+
 /* --- ensemble statistics (K11): per-realization morphology histogram staged for the NCCL all-gather ---- */
 /* out[0..n_bins) = histogram of log2(Np), out[n_bins..2n_bins) = histogram of Rg over [0,rg_max),
- * then {n_agg, sum Np, kf, Df, fit_ok} from AggregatList::get_instantaneous_fractal_law (aggregat_list_fractal_law.cpp:23-33). */
-int mcac_gpu_morphology_stats(mcac_gpu *h, int32_t n_bins, double rg_max, double *out /* 2*n_bins + 5 */);
+ * then {n_agg, sum Np, sum lx, sum lx^2, sum lx*ly, sum ly, sum ly^2, sum Rg} with lx = log(dg/dp), ly = log(Np): the sums of
+ * AggregatList::get_instantaneous_fractal_law -> linreg (aggregat_list_fractal_law.cpp:23-33, tools.cpp:126-157). */
+int mcac_gpu_morphology_stats(mcac_gpu *h, int32_t n_bins, double rg_max, double *out /* 2*n_bins + 8 */);
 /* same, written to a device buffer (for torch.distributed all_gather without a host round trip) */
 int mcac_gpu_morphology_stats_device(mcac_gpu *h, int32_t n_bins, double rg_max, void *device_out);
 /* raw CUDA stream of the handle (cudaStream_t) so callers can order their own work / events on it */

@@ -10,7 +10,8 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import AGG_FIELDS, CONTACT_DTYPE, SCALARS, SPHERE_FIELDS, STEP_DTYPE, Contact, McacError, Params, RunReport, lib, ptr
+from ._capi import (AGG_FIELDS, CONTACT_DTYPE, SCALARS, SPHERE_FIELDS, STEP_DTYPE, Contact, McacError, Params, RunReport, SweepReport,
+                    lib, ptr)
 
 __all__ = ["HostModel", "Simulation", "McacError", "ini_text", "Params"]
 
@@ -188,6 +189,22 @@ class Simulation:
         out = np.zeros(n, np.int32)
         self._ck(self.L.mcac_gpu_rand(self.h, n, ptr(out)))
         return out
+
+    def search_sweep(self, n: int, repeats: int = 1) -> dict:
+        rep = SweepReport()
+        self._ck(self.L.mcac_gpu_search_sweep(self.h, n, repeats, C.byref(rep)))
+        return rep.as_dict()
+
+    def set_profile(self, on: bool = True):
+        self._ck(self.L.mcac_gpu_set_profile(self.h, int(on)))
+
+    def morphology_stats(self, n_bins: int = 24, rg_max: float = 1e-5) -> np.ndarray:
+        out = np.zeros(2 * n_bins + 8)
+        self._ck(self.L.mcac_gpu_morphology_stats(self.h, n_bins, rg_max, ptr(out)))
+        return out
+
+    def morphology_stats_device(self, device_ptr: int, n_bins: int = 24, rg_max: float = 1e-5):
+        self._ck(self.L.mcac_gpu_morphology_stats_device(self.h, n_bins, rg_max, C.c_void_p(device_ptr)))
 
     # ---- the whole loop
     def run(self, max_steps: int, batch: int = 0, records: int = 0):

@@ -55,7 +55,17 @@ class RunReport(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ["steps", "events", "searches", "pair_tests_sphere", "pair_tests_bounding", "batches", "conflicts", "duplications",
                  "sorts", "kernel_launches", "n_aggregates", "n_spheres", "finished"]] + \
-               [(n, C.c_double) for n in ["time", "box_length", "avg_npp", "max_time_step", "volume_fraction", "device_ms"]]
+               [(n, C.c_double) for n in ["time", "box_length", "avg_npp", "max_time_step", "volume_fraction", "device_ms",
+                                          "search_ms", "commit_ms"]] + \
+               [(n, C.c_int64) for n in ["search_launches", "commit_launches"]]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SweepReport(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ["n_queries", "contacts", "pair_tests_sphere", "pair_tests_bounding"]] + \
+               [("distance_checksum", C.c_double), ("kernel_ms", C.c_double)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -73,7 +83,8 @@ EXPORTS = [
     "mcac_gpu_download_state", "mcac_gpu_contact_search", "mcac_gpu_contact_search_batch", "mcac_gpu_translate", "mcac_gpu_merge",
     "mcac_gpu_grow", "mcac_gpu_update", "mcac_gpu_refresh", "mcac_gpu_sort_time_steps", "mcac_gpu_get_pick_table",
     "mcac_gpu_pick_random", "mcac_gpu_pick_last", "mcac_gpu_duplicate", "mcac_gpu_rand", "mcac_gpu_run",
-    "mcac_gpu_morphology_stats", "mcac_gpu_morphology_stats_device", "mcac_gpu_stream",
+    "mcac_gpu_morphology_stats", "mcac_gpu_morphology_stats_device", "mcac_gpu_stream", "mcac_gpu_search_sweep",
+    "mcac_gpu_set_profile",
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_state", "mcac_sim_create",
 ]
@@ -111,6 +122,8 @@ def lib() -> C.CDLL:
         L.mcac_gpu_run.argtypes = [vp, i64, C.c_int32, vp, i64, C.POINTER(RunReport)]
         L.mcac_gpu_morphology_stats.argtypes = [vp, C.c_int32, dbl, vp]
         L.mcac_gpu_morphology_stats_device.argtypes = [vp, C.c_int32, dbl, vp]
+        L.mcac_gpu_search_sweep.argtypes = [vp, i64, C.c_int32, C.POINTER(SweepReport)]
+        L.mcac_gpu_set_profile.argtypes = [vp, C.c_int32]
         L.mcac_gpu_stream.argtypes = [vp]
         L.mcac_gpu_stream.restype = vp
         L.mcac_host_last_error.restype = C.c_char_p

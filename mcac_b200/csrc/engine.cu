@@ -65,6 +65,13 @@ struct mcac_gpu {
     bool labels_valid = false, pick_valid = false, cells_valid = false, uploaded = false;
     long long launches = 0;
     int n_sm = 148;
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;  // start/stop pairs recorded around K1 / commit launches when profile != 0
+    std::vector<int> ev_kind;
+    int *sweep_slot = nullptr;
+    double *sweep_dir = nullptr, *sweep_dist = nullptr;
+    SearchResult *sweep_res = nullptr;
+    long long sweep_cap = 0;
 };
 
 #define CK(call)                                                                                  \
@@ -618,6 +625,37 @@ int after_event(mcac_gpu *h) {
     return E_OK;
 }
 
+void prof_begin(mcac_gpu *h, int kind) {
+    if (!h->profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    h->ev_pool.push_back(a);
+    h->ev_pool.push_back(b);
+    h->ev_kind.push_back(kind);
+    cudaEventRecord(a, h->stream);
+}
+void prof_end(mcac_gpu *h) {
+    if (!h->profile) return;
+    cudaEventRecord(h->ev_pool.back(), h->stream);
+}
+void prof_collect(mcac_gpu *h, mcac_run_report *rep) {
+    double ms[2] = {0., 0.};
+    long long cnt[2] = {0, 0};
+    for (size_t i = 0; i < h->ev_kind.size(); i++) {
+        float t = 0.f;
+        cudaEventSynchronize(h->ev_pool[2 * i + 1]);
+        cudaEventElapsedTime(&t, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]);
+        ms[h->ev_kind[i]] += t;
+        cnt[h->ev_kind[i]]++;
+        cudaEventDestroy(h->ev_pool[2 * i]);
+        cudaEventDestroy(h->ev_pool[2 * i + 1]);
+    }
+    h->ev_pool.clear();
+    h->ev_kind.clear();
+    if (rep) { rep->search_ms = ms[0]; rep->commit_ms = ms[1]; rep->search_launches = cnt[0]; rep->commit_launches = cnt[1]; }
+}
+
 int search_launch(mcac_gpu *h, int nq) {
     TRY(build_cells(h));
     k_search<<<nq, kSearchThreads, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
@@ -667,6 +705,7 @@ int mcac_gpu_destroy(mcac_gpu *h) {
     free_all(h);
     for (void *p : h->persistent) cudaFree(p);
     if (h->rec_dev) cudaFree(h->rec_dev);
+    for (void *p : {(void *)h->sweep_slot, (void *)h->sweep_dir, (void *)h->sweep_dist, (void *)h->sweep_res}) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -713,9 +752,25 @@ int mcac_gpu_upload_state(mcac_gpu *h, int64_t n_sph, int64_t n_agg, const doubl
     s.agg_n.resize((size_t)n_agg);
     for (int64_t a = 0; a < n_agg; a++) s.agg_n[(size_t)a] = offsets[a + 1] - offsets[a];
     s.per_member.assign(per_member, per_member + 3 * n_sph);
+    const bool had_state = h->uploaded;
+    const Scalars keep = h->sc_host;
+    if (had_state) TRY(pull_scalars(h));
+    const Scalars live = h->sc_host;
     free_all(h);
+    h->uploaded = false;
     TRY(upload(h, s, maxradius, max_time_step, false));
-    h->dup_threshold = n_agg / 8;  // calcul.cpp:58
+    if (had_state) {  // the realization keeps running: clocks, counters and the RNG position are the handle's, not the host's
+        Scalars &sc = h->sc_host;
+        sc.time = live.time; sc.n_iter_without_event = live.n_iter_without_event; sc.total_events = live.total_events;
+        sc.steps_done = live.steps_done; sc.rand_pos = live.rand_pos; sc.pair_sphere = live.pair_sphere;
+        sc.pair_bounding = live.pair_bounding; sc.searches = live.searches; sc.conflicts = live.conflicts;
+        sc.nucleation_accum = live.nucleation_accum; sc.event = 1;
+        sc.total_volume = live.total_volume; sc.total_surface = live.total_surface; sc.volume_fraction = live.volume_fraction;
+        TRY(push_scalars(h));
+    } else {
+        h->dup_threshold = n_agg / 8;  // calcul.cpp:58
+    }
+    (void)keep;
     return E_OK;
 }
 
@@ -997,7 +1052,10 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if ((rc = ensure_rng(h, h->sc_host.rand_pos + 3LL * nq)) != E_OK) break;
         k_prepare_queries<<<div_up(nq, 128), 128, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist);
         h->launches++;
+        if ((rc = build_cells(h)) != E_OK) break;
+        prof_begin(h, 0);
         if ((rc = search_launch(h, nq)) != E_OK) break;
+        prof_end(h);
         BatchArgs ba;
         ba.nq = nq;
         ba.q_slot = h->q_slot;
@@ -1008,7 +1066,9 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         ba.rec_cap = n_records;
         ba.rec_base = steps;
         ba.max_steps = max_steps - steps;
+        prof_begin(h, 1);
         k_commit<<<1, kCommitThreads, 0, h->stream>>>(h->d, ba);
+        prof_end(h);
         h->launches++;
         if (cudaGetLastError() != cudaSuccess) { h->err = "k_commit launch failed"; rc = E_UNKNOWN; break; }
         if ((rc = pull_scalars(h)) != E_OK) break;
@@ -1055,23 +1115,77 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->volume_fraction = sc.volume_fraction;
         report->device_ms = ms;
     }
+    prof_collect(h, report);
     return E_OK;
 }
 
-int mcac_gpu_morphology_stats(mcac_gpu *h, int32_t n_bins, double rg_max, double *out) {
-    CK(cudaSetDevice(h->device));
-    HostState s;
-    TRY(download(h, s));
-    (void)rg_max;
-    (void)n_bins;
-    (void)out;
-    h->err = "morphology stats: not built yet";
-    return E_UNKNOWN;
-}
+int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile) { h->profile = profile; return E_OK; }
+
 int mcac_gpu_morphology_stats_device(mcac_gpu *h, int32_t n_bins, double rg_max, void *device_out) {
-    (void)n_bins; (void)rg_max; (void)device_out;
-    h->err = "morphology stats: not built yet";
-    return E_UNKNOWN;
+    CK(cudaSetDevice(h->device));
+    if (n_bins < 1 || !device_out) { h->err = "morphology_stats: bad arguments"; return E_INPUT; }
+    TRY(pull_scalars(h));
+    CK(cudaMemsetAsync(device_out, 0, sizeof(double) * (2 * (size_t)n_bins + 8), h->stream));
+    const int nb = std::min(1024, std::max(1, div_up(h->sc_host.n_agg_slots, 256)));
+    k_morphology_stats<<<nb, 256, 0, h->stream>>>(h->d, n_bins, rg_max, (double *)device_out);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return E_OK;
+}
+int mcac_gpu_morphology_stats(mcac_gpu *h, int32_t n_bins, double rg_max, double *out) {
+    if (2 * (size_t)n_bins + 8 > 4096) { h->err = "morphology_stats: too many bins"; return E_INPUT; }
+    TRY(mcac_gpu_morphology_stats_device(h, n_bins, rg_max, h->stats_dev));
+    CK(cudaMemcpy(out, h->stats_dev, sizeof(double) * (2 * (size_t)n_bins + 8), cudaMemcpyDeviceToHost));
+    return E_OK;
+}
+
+int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_report *report) {
+    CK(cudaSetDevice(h->device));
+    if (!h->uploaded || n < 1) { h->err = "search_sweep: no state"; return E_INPUT; }
+    if (3 * n > kRngBuf - 64) n = (kRngBuf - 64) / 3;
+    TRY(pull_scalars(h));
+    if (!h->pick_valid) TRY(sort_time_steps(h, h->sc_host.max_time_step));
+    if (h->sweep_cap < n) {
+        for (void *p : {(void *)h->sweep_slot, (void *)h->sweep_dir, (void *)h->sweep_dist, (void *)h->sweep_res}) if (p) cudaFree(p);
+        CK(cudaMalloc((void **)&h->sweep_slot, sizeof(int) * n));
+        CK(cudaMalloc((void **)&h->sweep_dir, sizeof(double) * 3 * n));
+        CK(cudaMalloc((void **)&h->sweep_dist, sizeof(double) * n));
+        CK(cudaMalloc((void **)&h->sweep_res, sizeof(SearchResult) * n));
+        h->sweep_cap = n;
+    }
+    TRY(ensure_rng(h, h->sc_host.rand_pos + 3 * n));
+    TRY(build_cells(h));
+    k_prepare_queries<<<div_up(n, 128), 128, 0, h->stream>>>(h->d, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int reps = repeats > 0 ? repeats : 1;
+    k_search<<<(int)n, kSearchThreads, 0, h->stream>>>(h->d, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist, h->sweep_res);  // warm-up
+    CK(cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps; r++)
+        k_search<<<(int)n, kSearchThreads, 0, h->stream>>>(h->d, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist, h->sweep_res);
+    CK(cudaEventRecord(e1, h->stream));
+    h->launches += reps + 2;
+    CK(cudaMemsetAsync(h->stats_dev, 0, sizeof(double) * 4, h->stream));
+    k_sweep_summary<<<std::min(1024, div_up(n, 256)), 256, 0, h->stream>>>(h->sweep_res, h->sweep_dist, (int)n, h->stats_dev);
+    double out[4];
+    CK(cudaMemcpyAsync(out, h->stats_dev, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (report) {
+        report->n_queries = n;
+        report->contacts = (int64_t)out[0];
+        report->distance_checksum = out[1];
+        report->pair_tests_sphere = (int64_t)out[2];
+        report->pair_tests_bounding = (int64_t)out[3];
+        report->kernel_ms = ms / reps;
+    }
+    return E_OK;
 }
 
 }  // extern "C"

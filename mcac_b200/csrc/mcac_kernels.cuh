@@ -981,4 +981,65 @@ __global__ void __launch_bounds__(256) k_dup_finish(DevState d, int n0, double o
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K11 — per-realization morphology statistics staged for the ensemble all-gather: histogram of log2(Np),
+// histogram of Rg on [0, rg_max), and the log-log regression sums of AggregatList::get_instantaneous_fractal_law
+// (aggregat_list_fractal_law.cpp:23-33 -> linreg, tools.cpp:126-157: x = dg_over_dp, y = Np).
+// out: [0,nb) Np histogram, [nb,2nb) Rg histogram, then n, sum_np, sumx, sumx2, sumxy, sumy, sumy2, sum_rg
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, double rg_max, double *out) {
+    __shared__ double red[8][8];
+    const int n = d.sc->n_agg_slots;
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        if (!d.a_alive[s]) continue;
+        const double np_ = static_cast<double>(d.a_n[s]);
+        const double rg = d.a_rg[s];
+        int b1 = 31 - __clz(d.a_n[s]);
+        b1 = b1 < nb ? b1 : nb - 1;
+        int b2 = static_cast<int>(rg / rg_max * nb);
+        b2 = b2 < 0 ? 0 : (b2 < nb ? b2 : nb - 1);
+        atomicAdd(&out[b1], 1.0);
+        atomicAdd(&out[nb + b2], 1.0);
+        const double lx = log(d.a_dgdp[s]), ly = log(np_);
+        acc[0] += 1.; acc[1] += np_; acc[2] += lx; acc[3] += lx * lx; acc[4] += lx * ly; acc[5] += ly; acc[6] += ly * ly; acc[7] += rg;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(kFull, acc[k], o);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 8; k++) red[w][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.;
+        for (int ww = 0; ww < 8; ww++) t += red[ww][threadIdx.x];
+        atomicAdd(&out[2 * nb + threadIdx.x], t);
+    }
+}
+// summary of a sweep of independent searches (no commit): contacts, checksum of the finite distances, pair counters
+__global__ void __launch_bounds__(256) k_sweep_summary(const SearchResult *res, const double *q_dist, int nq, double *out /* 4 */) {
+    double cnt = 0., sum = 0., ps = 0., pb = 0.;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const SearchResult r = res[q];
+        if (r.distance <= q_dist[q]) { cnt += 1.; sum += r.distance; }
+        ps += (double)r.n_sphere_pairs;
+        pb += (double)r.n_bounding;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(kFull, cnt, o);
+        sum += __shfl_xor_sync(kFull, sum, o);
+        ps += __shfl_xor_sync(kFull, ps, o);
+        pb += __shfl_xor_sync(kFull, pb, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], cnt);
+        atomicAdd(&out[1], sum);
+        atomicAdd(&out[2], ps);
+        atomicAdd(&out[3], pb);
+    }
+}
+
 }  // namespace mcacb

@@ -19,6 +19,7 @@
 //                         (inside time_forward, i.e. after translate, before growth/merge)
 //   MCAC_TAP_SORT_CALLS   comma list of sort_time_steps call numbers whose result is dumped
 //   MCAC_TAP_EXIT_STEP    call _exit(0) once this many steps were done (bounded samples)
+//   MCAC_TAP_CHUNK        record the wall clock (s since calcul started) every CHUNK steps -> summary.txt `chunk_times`
 // Outputs (raw little-endian, layouts in tests/ref_trace.py):
 //   steps.bin  searches.bin  merges.bin  sort_<k>.bin  state_<step>.bin  state_init.bin  state_final.bin  summary.txt
 #include "aggregats/aggregat_list.hpp"
@@ -63,7 +64,8 @@ std::vector<size_t> real_verlet(const Verlet *, const std::array<double, 3> &, c
 namespace {
 struct Tap {
     std::string dir = ".";
-    long long max_steps = 0, exit_step = -1;
+    long long max_steps = 0, exit_step = -1, chunk = 0;
+    std::vector<double> chunk_times;
     std::set<long long> state_steps, sort_calls;
     FILE *f_steps = nullptr, *f_search = nullptr, *f_merge = nullptr;
     long long n_rand = 0, n_steps = 0, n_search = 0, n_merge_calls = 0, n_merge_ok = 0, n_sort = 0;
@@ -76,6 +78,7 @@ struct Tap {
         if (const char *e = getenv("MCAC_TAP_DIR")) dir = e;
         if (const char *e = getenv("MCAC_TAP_MAX_STEPS")) max_steps = atoll(e);
         if (const char *e = getenv("MCAC_TAP_EXIT_STEP")) exit_step = atoll(e);
+        if (const char *e = getenv("MCAC_TAP_CHUNK")) chunk = atoll(e);
         parse(getenv("MCAC_TAP_STATE_STEPS"), state_steps);
         parse(getenv("MCAC_TAP_SORT_CALLS"), sort_calls);
     }
@@ -161,6 +164,11 @@ void Tap::summary(const char *why) {
             n_search, n_merge_calls, n_merge_ok, n_sort);
     fprintf(f, "pair_tests_sphere %lld\npair_tests_bounding %lld\naggregate_pair_calls %lld\n", n_pair_sphere, n_pair_bound, n_aggdist);
     fprintf(f, "calcul_wall_s %.6f\n", wall);
+    if (!chunk_times.empty()) {
+        fprintf(f, "chunk_times");
+        for (double t : chunk_times) fprintf(f, " %.6f", t);
+        fprintf(f, "\n");
+    }
     if (list) fprintf(f, "n_agg %zu\nn_sph %zu\n", list->size(), list->spheres.size());
     if (pm) fprintf(f, "time %.17g\nbox_length %.17g\n", pm->time, pm->box_length);
     fclose(f);
@@ -239,6 +247,8 @@ void wrap_time_forward(Aggregate *self, double dt) {
     }
     if (tap.list && tap.state_steps.count(tap.n_steps)) dump_state(*tap.list, "state_" + std::to_string(tap.n_steps) + ".bin");
     tap.n_steps++;
+    if (tap.chunk > 0 && tap.n_steps % tap.chunk == 0)
+        tap.chunk_times.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - tap.t0).count());
     if (tap.exit_step >= 0 && tap.n_steps >= tap.exit_step) {
         tap.summary("exit_step");
         if (tap.list) dump_state(*tap.list, "state_final.bin");

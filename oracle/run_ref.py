@@ -134,6 +134,9 @@ def read_summary(wd: Path) -> dict:
     out = {}
     for line in (Path(wd) / "tap" / "summary.txt").read_text().splitlines():
         k, _, v = line.partition(" ")
+        if k == "chunk_times":
+            out[k] = [float(x) for x in v.split()]
+            continue
         try:
             out[k] = int(v)
         except ValueError:

@@ -30,8 +30,12 @@ def assert_records_match(got, ref, box):
         assert len(bad) == 0, f"{f}: first divergence at step {bad[0]}: gpu {got[f][bad[0]]} vs oracle {ref[f][bad[0]]}"
     fin = np.isfinite(ref["distance"][:n])
     assert np.array_equal(fin, np.isfinite(got["distance"][:n]))
-    np.testing.assert_allclose(got["distance"][:n][fin], ref["distance"][:n][fin], rtol=RTOL, atol=0)
-    np.testing.assert_allclose(got["dir"][:n], ref["dir"][:n], rtol=0, atol=4e-16)  # unit vector: 2 ulp of CUDA sincos/acos
+    # the contact distance is a difference (proj - sqrt(R^2 - axis^2)): 1e-12 relative to the scale of its operands
+    # (the displacement length); on bit-identical inputs it is checked bit-exactly in test_contact_search_*
+    err = np.abs(got["distance"][:n][fin] - ref["distance"][:n][fin])
+    assert np.all(err <= RTOL * ref["full_distance"][:n][fin]), f"contact distance off by {err.max()}"
+    np.testing.assert_allclose(got["distance"][:n][fin], ref["distance"][:n][fin], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(got["dir"][:n], ref["dir"][:n], rtol=0, atol=1e-15)  # unit vector: a few ulp of CUDA sincos/acos vs glibc
     for f in ["full_distance", "time", "dt", "proper_time"]:
         np.testing.assert_allclose(got[f][:n], ref[f][:n], rtol=RTOL, atol=0, err_msg=f)
     np.testing.assert_allclose(got["pos"][:n], ref["pos"][:n], rtol=0, atol=RTOL * box, err_msg="pos")
