@@ -25,7 +25,7 @@ typedef struct mcac_gpu mcac_gpu; /* opaque */
 
 enum { MCAC_PICK_RANDOM = 0, MCAC_PICK_LAST = 1 };                          /* constants.hpp:91-96  */
 enum { MCAC_VS_CAPS = 0, MCAC_VS_SBL = 1, MCAC_VS_ARVO = 2, MCAC_VS_ALPHAS = 3, MCAC_VS_NONE = 4 }; /* :103-110 */
-enum { MCAC_ORDER_LIBSTDCXX = 0, MCAC_ORDER_STABLE = 1 };
+enum { MCAC_ORDER_LIBSTDCXX = 0, MCAC_ORDER_STABLE = 1, MCAC_ORDER_HOST_STDSORT = 2 /* debugging aid: libstdc++ std::sort on the host */ };
 
 /* Physics + numerics of one realization: the PhysicalModel fields the hot path reads
  * (include/physical_model/physical_model.hpp:31-77), already derived by the host-side reader. */

@@ -68,6 +68,12 @@ struct mcac_gpu {
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;  // start/stop pairs recorded around K1 / commit launches when profile != 0
     std::vector<int> ev_kind;
+    SortBufs sortb{};
+    long long *scan64_sums = nullptr;
+    double *cum_sums = nullptr;
+    int *h_flags = nullptr;  // pinned: sort `active` flags
+    long long sort_levels = 0, sort_fallbacks = 0;
+    int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
     int *sweep_slot = nullptr;
     double *sweep_dir = nullptr, *sweep_dist = nullptr;
     SearchResult *sweep_res = nullptr;
@@ -152,6 +158,19 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
         TRY(dev_alloc(h, p, agg_cap));
     TRY(dev_alloc(h, &d.cell_start, (size_t)d.n_cells + 1));
     TRY(dev_alloc(h, &d.cell_fill, (size_t)d.n_cells + 1));
+    SortBufs &sb = h->sortb;
+    TRY(dev_alloc(h, &sb.perm, agg_cap));
+    TRY(dev_alloc(h, &sb.wk, agg_cap));
+    TRY(dev_alloc(h, &sb.segf, agg_cap));
+    TRY(dev_alloc(h, &sb.segl, agg_cap));
+    TRY(dev_alloc(h, &sb.flags, agg_cap + 1));
+    TRY(dev_alloc(h, &sb.pre, agg_cap + 2));
+    TRY(dev_alloc(h, &sb.tmp_a, agg_cap + 1));
+    TRY(dev_alloc(h, &sb.tmp_b, agg_cap + 1));
+    TRY(dev_alloc(h, &sb.cut, agg_cap + 1));
+    TRY(dev_alloc(h, &sb.active, 4));
+    TRY(dev_alloc(h, &h->scan64_sums, agg_cap / (kScanBlock * kScanItems) + 8));
+    TRY(dev_alloc(h, &h->cum_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     const size_t scan_n = (size_t)std::max<long long>(agg_cap, d.n_cells) + 2;
     TRY(dev_alloc(h, &h->scan_tmp, scan_n));
     TRY(dev_alloc(h, &h->scan_out, scan_n));
@@ -225,18 +244,15 @@ int refresh_reduce(mcac_gpu *h) {
 // order.  MCAC_ORDER_LIBSTDCXX reproduces the reference's std::sort (introsort) order among EQUAL weights, which
 // decides the pick in monodisperse runs: the index sort is done by libstdc++'s std::sort itself on the
 // host (the very routine the reference calls; it runs only on events), together with the sequential prefix sum.
-int sort_time_steps(mcac_gpu *h, double factor) {
+int sort_time_steps_host(mcac_gpu *h) {
     DevState &d = h->d;
-    TRY(refresh_labels(h));
     const int n = h->sc_host.n_agg;
-    k_make_keys<<<div_up(n, 256), 256, 0, h->stream>>>(d, factor);
-    h->launches++;
     std::vector<double> keys((size_t)n), cum((size_t)n);
     CK(cudaMemcpyAsync(keys.data(), d.keys, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     std::vector<int> idx((size_t)n);
     std::iota(idx.begin(), idx.end(), 0);
-    if (h->prm.sort_order == MCAC_ORDER_LIBSTDCXX) {
+    if (h->prm.sort_order != MCAC_ORDER_STABLE) {
         std::vector<size_t> idx64((size_t)n);
         std::iota(idx64.begin(), idx64.end(), 0);
         std::sort(idx64.begin(), idx64.end(), [&keys](size_t a, size_t b) { return keys[a] < keys[b]; });
@@ -254,6 +270,70 @@ int sort_time_steps(mcac_gpu *h, double factor) {
     CK(cudaStreamSynchronize(h->stream));
     h->sc_host.n_pick = n;
     h->sc_host.cum_total = cum[(size_t)n - 1];
+    h->pick_valid = true;
+    return E_OK;
+}
+
+// Device form: weights (K9 keys) -> replayed introsort (see mcac_kernels.cuh) -> cumulative table -> slots.
+int sort_time_steps(mcac_gpu *h, double factor) {
+    DevState &d = h->d;
+    TRY(refresh_labels(h));
+    const int n = h->sc_host.n_agg;
+    const int nb = div_up(n, 256);
+    k_make_keys<<<nb, 256, 0, h->stream>>>(d, factor);
+    h->launches++;
+    if (h->prm.sort_order == 2) return sort_time_steps_host(h);  // MCAC_ORDER_HOST_STDSORT: debugging aid
+    SortBufs sb = h->sortb;
+    sb.n = n;
+    sb.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
+    k_sort_init<<<nb, 256, 0, h->stream>>>(sb, d.keys);
+    h->launches++;
+    int lg = 0;
+    while ((1LL << (lg + 1)) <= n) lg++;
+    int depth = 2 * lg;  // std::__lg(n) * 2
+    bool active = n > kSortLeaf, fail = false;
+    const int per = kScanBlock * kScanItems, snb = std::max(1, div_up(n + 1, per));
+    while (active && !fail) {
+        depth--;
+        k_sort_pivot<<<nb, 256, 0, h->stream>>>(sb);
+        k_sort_flags<<<nb, 256, 0, h->stream>>>(sb);
+        CK(cudaMemsetAsync(sb.flags + n, 0, sizeof(long long), h->stream));
+        k_scan64_partials<<<snb, kScanBlock, 0, h->stream>>>(sb.flags, n + 1, h->scan64_sums);
+        k_scan64_block_sums<<<1, 1024, 0, h->stream>>>(h->scan64_sums, snb);
+        k_scan64_apply<<<snb, kScanBlock, 0, h->stream>>>(sb.flags, n + 1, h->scan64_sums, snb, sb.pre);
+        k_sort_scatter<<<nb, 256, 0, h->stream>>>(sb);
+        k_sort_swap<<<nb, 256, 0, h->stream>>>(sb);
+        CK(cudaMemsetAsync(sb.active, 0, 2 * sizeof(int), h->stream));
+        k_sort_split<<<nb, 256, 0, h->stream>>>(sb, depth);
+        h->launches += 8;
+        CK(cudaMemcpyAsync(h->h_flags, sb.active, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        active = h->h_flags[0] != 0;
+        fail = h->h_flags[1] != 0;
+        h->sort_levels++;
+    }
+    CK(cudaGetLastError());
+    if (fail) {  // introsort's depth limit was hit (heap-sort branch): take libstdc++'s own std::sort for this (rare) call
+        h->sort_fallbacks++;
+        return sort_time_steps_host(h);
+    }
+    k_sort_leaves<<<nb, 256, 0, h->stream>>>(sb);
+    h->launches++;
+    if (n <= h->cum_sequential_max) {
+        k_cum_sequential<<<1, 32, 0, h->stream>>>(sb.wk, d.cum, n);
+        h->launches++;
+    } else {
+        const int cnb = std::max(1, div_up(n, per));
+        k_cum_partials<<<cnb, kScanBlock, 0, h->stream>>>(sb.wk, n, h->cum_sums);
+        k_cum_block_sums<<<1, 32, 0, h->stream>>>(h->cum_sums, cnb);
+        k_cum_apply<<<cnb, kScanBlock, 0, h->stream>>>(sb.wk, n, h->cum_sums, d.cum);
+        h->launches += 3;
+    }
+    CK(cudaMemcpyAsync(h->sorted_label, sb.perm, sizeof(int) * n, cudaMemcpyDeviceToDevice, h->stream));
+    k_sort_finish<<<nb, 256, 0, h->stream>>>(d, sb);
+    h->launches++;
+    CK(cudaGetLastError());
+    TRY(pull_scalars(h));
     h->pick_valid = true;
     return E_OK;
 }
@@ -687,6 +767,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     h->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaMallocHost((void **)&h->h_sc, sizeof(Scalars)));
+    CK(cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)));
     fill_devstate_params(h);
     TRY(alloc_persistent(h));
     GlibcRandState st;
@@ -707,6 +788,7 @@ int mcac_gpu_destroy(mcac_gpu *h) {
     if (h->rec_dev) cudaFree(h->rec_dev);
     for (void *p : {(void *)h->sweep_slot, (void *)h->sweep_dir, (void *)h->sweep_dist, (void *)h->sweep_res}) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return E_OK;

@@ -982,6 +982,277 @@ __global__ void __launch_bounds__(256) k_dup_finish(DevState d, int n0, double o
 }
 
 // ------------------------------------------------------------------------------------------------
+// K9 — AggregatList::sort_time_steps on the device (aggregat_list.cpp:109-141).
+// The reference sorts label indices with libstdc++'s std::sort (introsort) and the tie order among EQUAL 1/dt
+// weights decides which aggregate a draw picks (in monodisperse runs whole classes tie).  std::sort's
+// result is a deterministic function of the comparisons only, so it is replayed here in a level-synchronous form:
+//   * __introsort_loop: every segment longer than 16 does median-of-3 -> __unguarded_partition.  The Hoare
+//     partition is "k-th element from the left that is not < pivot swaps with the k-th from the right that is
+//     not > pivot, while they have not crossed", i.e. two prefix counts + one pairing pass — parallel per level;
+//   * __final_insertion_sort is a stable sort, and segments are already ordered relative to each other, so it
+//     equals a stable sort inside each leaf (<= 16 elements).
+// depth_limit exhaustion (heap-sort branch) is reported through `fail` and handled by the caller.
+// `stable` != 0 orders ties by label instead (MCAC_ORDER_STABLE).
+// ------------------------------------------------------------------------------------------------
+struct SortBufs {
+    int *perm;          // labels being sorted
+    double *wk;         // their weights, moved together with perm
+    int *segf, *segl;   // per element: its current segment [segf, segl)
+    long long *flags, *pre;  // low 32 bits: "not < pivot" ; high 32 bits: "not > pivot" ; and their exclusive scan
+    int *tmp_a, *tmp_b, *cut;
+    int *active;        // [0]: some segment still longer than 16 ; [1]: fail
+    int n, stable;
+};
+constexpr int kSortLeaf = 16;
+__device__ __forceinline__ bool w_less(double ka, int la, double kb, int lb, int stable) {
+    return ka < kb || (stable && ka == kb && la < lb);
+}
+__global__ void k_sort_init(SortBufs b, const double *keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    b.perm[i] = i;
+    b.wk[i] = keys[i];
+    b.segf[i] = 0;
+    b.segl[i] = b.n;
+    if (i == 0) { b.active[0] = b.n > kSortLeaf ? 1 : 0; b.active[1] = 0; }
+}
+// __move_median_to_first(first, first+1, mid, last-1) by the segment leader
+__global__ void k_sort_pivot(SortBufs b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n || b.segf[i] != i) return;
+    const int f = i, l = b.segl[i];
+    if (l - f <= kSortLeaf) return;
+    const int pa = f + 1, pb = f + (l - f) / 2, pc = l - 1;
+    const double ka = b.wk[pa], kb = b.wk[pb], kc = b.wk[pc];
+    const int la = b.perm[pa], lb = b.perm[pb], lc = b.perm[pc];
+    int pick;
+    if (w_less(ka, la, kb, lb, b.stable)) {
+        if (w_less(kb, lb, kc, lc, b.stable)) pick = pb;
+        else if (w_less(ka, la, kc, lc, b.stable)) pick = pc;
+        else pick = pa;
+    } else if (w_less(ka, la, kc, lc, b.stable)) pick = pa;
+    else if (w_less(kb, lb, kc, lc, b.stable)) pick = pc;
+    else pick = pb;
+    const double kf = b.wk[f];
+    const int lf = b.perm[f];
+    b.wk[f] = b.wk[pick]; b.perm[f] = b.perm[pick];
+    b.wk[pick] = kf; b.perm[pick] = lf;
+}
+__global__ void k_sort_flags(SortBufs b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const int f = b.segf[i], l = b.segl[i];
+    long long fl = 0;
+    if (l - f > kSortLeaf && i > f) {
+        const double kp = b.wk[f], kx = b.wk[i];
+        const int lp = b.perm[f], lx = b.perm[i];
+        if (!w_less(kx, lx, kp, lp, b.stable)) fl |= 1LL;
+        if (!w_less(kp, lp, kx, lx, b.stable)) fl |= (1LL << 32);
+    }
+    b.flags[i] = fl;
+}
+__global__ void k_sort_scatter(SortBufs b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const int f = b.segf[i], l = b.segl[i];
+    if (l - f <= kSortLeaf || i <= f) return;
+    const int base = f + 1;
+    const long long p0 = b.pre[base], pi_ = b.pre[i], pl = b.pre[l];
+    const long long fl = b.flags[i];
+    if (fl & 1LL) b.tmp_a[base + (int)((pi_ & 0xffffffffLL) - (p0 & 0xffffffffLL))] = i;
+    if (fl >> 32) {
+        const int n_b = (int)((pl >> 32) - (p0 >> 32));
+        b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = i;
+    }
+}
+__global__ void k_sort_swap(SortBufs b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.n) return;
+    const int f = b.segf[j], l = b.segl[j];
+    if (l - f <= kSortLeaf || j <= f) return;
+    const int base = f + 1, k = j - base;
+    const long long p0 = b.pre[base], pl = b.pre[l];
+    const int n_a = (int)((pl & 0xffffffffLL) - (p0 & 0xffffffffLL)), n_b = (int)((pl >> 32) - (p0 >> 32));
+    const int m = n_a < n_b ? n_a : n_b;
+    const bool sw = k < m && b.tmp_a[base + k] < b.tmp_b[base + k];
+    const bool next_sw = (k + 1 < m) && b.tmp_a[base + k + 1] < b.tmp_b[base + k + 1];
+    if (sw) {
+        const int pa = b.tmp_a[base + k], pb = b.tmp_b[base + k];
+        const double ka = b.wk[pa];
+        const int la = b.perm[pa];
+        b.wk[pa] = b.wk[pb]; b.perm[pa] = b.perm[pb];
+        b.wk[pb] = ka; b.perm[pb] = la;
+    }
+    int s = -1;
+    if (sw && !next_sw) s = k + 1;
+    else if (k == 0 && !sw) s = 0;
+    if (s >= 0) {  // where the two scans of __unguarded_partition stop after `s` swaps
+        const int a_s = s < n_a ? b.tmp_a[base + s] : 0x7fffffff;
+        const int b_prev = s > 0 ? b.tmp_b[base + s - 1] : l;
+        b.cut[f] = a_s < b_prev ? a_s : b_prev;
+    }
+}
+__global__ void k_sort_split(SortBufs b, int depth_left) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const int f = b.segf[i], l = b.segl[i];
+    if (l - f <= kSortLeaf) return;
+    const int c = b.cut[f];
+    int nf = f, nl = l;
+    if (i < c) nl = c; else nf = c;
+    b.segf[i] = nf;
+    b.segl[i] = nl;
+    if (i == nf && nl - nf > kSortLeaf) {
+        if (depth_left > 0) b.active[0] = 1; else b.active[1] = 1;  // would enter the heap-sort branch of introsort
+    }
+}
+// __final_insertion_sort restricted to a leaf: stable insertion sort of <= 16 elements by the leaf leader
+__global__ void k_sort_leaves(SortBufs b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n || b.segf[i] != i) return;
+    const int f = i, l = b.segl[i];
+    if (l - f > kSortLeaf) return;
+    for (int x = f + 1; x < l; x++) {
+        const double kv = b.wk[x];
+        const int lv = b.perm[x];
+        int y = x - 1;
+        while (y >= f && w_less(kv, lv, b.wk[y], b.perm[y], b.stable)) {
+            b.wk[y + 1] = b.wk[y]; b.perm[y + 1] = b.perm[y];
+            y--;
+        }
+        b.wk[y + 1] = kv; b.perm[y + 1] = lv;
+    }
+}
+// 64-bit packed exclusive scan (same 3-phase structure as the int scan)
+__device__ __forceinline__ long long warp_inclusive_scan_ll(long long v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long n = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+__device__ __forceinline__ long long block_exclusive_scan_ll(long long v, long long *total, long long *warp_sums) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long inc = warp_inclusive_scan_ll(v, lane);
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        long long s = lane < nw ? warp_sums[lane] : 0;
+        s = warp_inclusive_scan_ll(s, lane);
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const long long base = w ? warp_sums[w - 1] : 0;
+    *total = warp_sums[nw - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+__global__ void k_scan64_partials(const long long *in, int n, long long *block_sums) {
+    __shared__ long long ws[32];
+    const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    long long v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) v += (base + k < n) ? in[base + k] : 0;
+    long long total;
+    block_exclusive_scan_ll(v, &total, ws);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void k_scan64_block_sums(long long *block_sums, int nb) {
+    __shared__ long long ws[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += blockDim.x) {
+        const int i = b0 + threadIdx.x;
+        const long long v = i < nb ? block_sums[i] : 0;
+        long long total;
+        const long long pre = block_exclusive_scan_ll(v, &total, ws);
+        if (i < nb) block_sums[i] = carry + pre;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+__global__ void k_scan64_apply(const long long *in, int n, const long long *block_sums, int nb, long long *out) {
+    __shared__ long long ws[32];
+    const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    long long x[kScanItems];
+    long long v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { x[k] = (base + k < n) ? in[base + k] : 0; v += x[k]; }
+    long long total;
+    long long pre = block_exclusive_scan_ll(v, &total, ws) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = pre;
+        pre += x[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[nb];
+}
+// cumulative_time_steps (aggregat_list.cpp:133-140).  Sequential form = the reference's rounding, one thread.
+__global__ void k_cum_sequential(const double *wk, double *cum, int n) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double acc = wk[0];
+    cum[0] = acc;
+    for (int i = 1; i < n; i++) { acc = acc + wk[i]; cum[i] = acc; }
+}
+// Parallel form for large N: fixed three-phase tree (deterministic; rounds differently from the sequential sum by a few ulp)
+__global__ void k_cum_partials(const double *wk, int n, double *block_sums) {
+    __shared__ double sm[32];
+    const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    double v = 0.;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) v += (base + k < n) ? wk[base + k] : 0.;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.;
+        for (int w = 0; w < kScanBlock / 32; w++) t += sm[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+__global__ void k_cum_block_sums(double *block_sums, int nb) {  // exclusive, sequential over <= few hundred blocks
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double acc = 0.;
+    for (int b = 0; b < nb; b++) { const double t = block_sums[b]; block_sums[b] = acc; acc += t; }
+}
+__global__ void k_cum_apply(const double *wk, int n, const double *block_sums, double *cum) {
+    __shared__ double warp_tot[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    double x[kScanItems];
+    double v = 0.;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { x[k] = (base + k < n) ? wk[base + k] : 0.; v += x[k]; }
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    double wbase = 0.;
+    for (int ww = 0; ww < w; ww++) wbase += warp_tot[ww];
+    double run = block_sums[blockIdx.x] + wbase + (inc - v);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        run += x[k];
+        if (base + k < n) cum[base + k] = run;
+    }
+}
+__global__ void k_sort_finish(DevState d, SortBufs b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    d.sorted_slot[i] = d.slot_of_label[b.perm[i]];
+    if (i == 0) { d.sc->n_pick = b.n; d.sc->cum_total = d.cum[b.n - 1]; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K11 — per-realization morphology statistics staged for the ensemble all-gather: histogram of log2(Np),
 // histogram of Rg on [0, rg_max), and the log-log regression sums of AggregatList::get_instantaneous_fractal_law
 // (aggregat_list_fractal_law.cpp:23-33 -> linreg, tools.cpp:126-157: x = dg_over_dp, y = Np).

@@ -118,6 +118,7 @@ void PhysicalModel::parse(std::istream &in) {
     if (!word.empty()) {
         if (word == "libstdcxx") sort_order = MCAC_ORDER_LIBSTDCXX;
         else if (word == "stable") sort_order = MCAC_ORDER_STABLE;
+        else if (word == "host_stdsort") sort_order = MCAC_ORDER_HOST_STDSORT;
         else throw InputError("Invalid sort_order: " + word);
     }
     take(ini, "inter_potential", "with_potentials", with_potentials);

@@ -36,8 +36,10 @@ def assert_records_match(got, ref, box):
     assert np.all(err <= RTOL * ref["full_distance"][:n][fin]), f"contact distance off by {err.max()}"
     np.testing.assert_allclose(got["distance"][:n][fin], ref["distance"][:n][fin], rtol=1e-9, atol=0)
     np.testing.assert_allclose(got["dir"][:n], ref["dir"][:n], rtol=0, atol=1e-15)  # unit vector: a few ulp of CUDA sincos/acos vs glibc
-    for f in ["full_distance", "time", "dt", "proper_time"]:
+    for f in ["full_distance", "time", "proper_time"]:
         np.testing.assert_allclose(got[f][:n], ref[f][:n], rtol=RTOL, atol=0, err_msg=f)
+    # dt of a contact step = dt * (contact distance / lpm): inherits the conditioning of the contact distance
+    np.testing.assert_allclose(got["dt"][:n], ref["dt"][:n], rtol=RTOL, atol=RTOL * ref["dt"][:n].max(), err_msg="dt")
     np.testing.assert_allclose(got["pos"][:n], ref["pos"][:n], rtol=0, atol=RTOL * box, err_msg="pos")
 
 
@@ -124,6 +126,44 @@ def test_run_replays_the_collision_sequence(name, steps, batch):
     # structural invariant pinned by the reference (pymcac/tests/test_data.py:166-205)
     st = sim.state()
     np.testing.assert_array_equal(np.bincount(st["sphere_label"], minlength=st["n_agg"]), st["agg_n_spheres"])
+
+
+@pytest.mark.parametrize("name", ["monodisperse_seed42", "polydisperse_seed42", "c3_small_seed42", "c2_small_seed42"])
+def test_device_sort_replays_std_sort_tie_order(name):
+    """index_sorted_time_steps / cumulative_time_steps of the reference's first sort_time_steps call (taps: sort_0) —
+    monodisperse: every weight ties, so this is purely libstdc++'s introsort order, replayed on the device."""
+    g = Golden(name)
+    srt = g.sort(0)
+    sim = Simulation(ini_text(merged_config(g.base, g.overrides)))
+    sim.sort_time_steps(float(srt["factor"]))
+    idx, cum = sim.pick_table()
+    np.testing.assert_array_equal(idx, srt["idx"])
+    np.testing.assert_array_equal(cum, srt["cum"])  # n <= 65536: summed sequentially, the reference's rounding
+
+
+def test_device_sort_against_std_sort_on_random_weights():
+    """Same check on synthetic weight patterns (few classes, all equal, sorted, reversed, random) through the C ABI:
+    the aggregates' time steps are overwritten by uploading a doctored state."""
+    from oracle_lib import introsort_order
+    text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 5, "n_verlet_divisions": 8}, "monomers": {"number": 30000}}))
+    hm = HostModel(text).state()
+    rng = np.random.default_rng(3)
+    n = hm["n_agg"]
+    patterns = [rng.random(n) + 0.5, rng.integers(1, 4, n).astype(float), np.ones(n), np.sort(rng.integers(1, 60, n)).astype(float),
+                np.sort(rng.random(n) + 0.5)[::-1].copy()]
+    for ts in patterns:
+        st = dict(hm)
+        af = hm["agg_fields"].copy()
+        af[3] = ts  # TIME_STEP column
+        st["agg_fields"] = af
+        sim = Simulation(text)
+        sim.upload(st)
+        sim.sort_time_steps(2.0)
+        idx, cum = sim.pick_table()
+        keys = 2.0 / ts
+        ref = introsort_order(keys)
+        np.testing.assert_array_equal(idx, ref)
+        np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))  # np.cumsum is the sequential sum
 
 
 def test_batch_width_does_not_change_the_trajectory():
