@@ -11,6 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
 base, ov = workload_config(n, 42)
 sim = mcac_b200.Simulation(mcac_b200.ini_text(merged_config(base, ov)))
-rep, _ = sim.run(steps, batch=256)
-print({k: rep[k] for k in ("steps", "events", "batches", "kernel_launches", "device_ms")})
-print(sim.search_sweep(100000, repeats=1))
+if steps > 0:
+    rep, _ = sim.run(steps, batch=256)
+    print({k: rep[k] for k in ("steps", "events", "batches", "kernel_launches", "device_ms")})
+print(sim.search_sweep(int(sys.argv[3]) if len(sys.argv) > 3 else 100000, repeats=1))

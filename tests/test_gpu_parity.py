@@ -121,7 +121,11 @@ def test_run_replays_the_collision_sequence(name, steps, batch):
     assert_records_match(recs, ref, box)
     assert rep["events"] == int(ref["merged"].sum())
     c = o.counters()
-    assert rep["pair_tests_sphere"] == c["pair_sphere"] and rep["pair_tests_bounding"] == c["pair_bounding"]
+    # sphere-level tests of the examined suspects: exact.  Bounding prefilter tests: a speculative search sees the Verlet
+    # cells as they were at the start of its batch, so the SIZE of its superset neighbourhood may differ by a few entries
+    # from the sequential run although the eligible suspects (and hence every result) are identical.
+    assert rep["pair_tests_sphere"] == c["pair_sphere"]
+    assert abs(rep["pair_tests_bounding"] - c["pair_bounding"]) <= 1e-3 * c["pair_bounding"]
     assert_states_match(sim.state(), o.state(), box)
     # structural invariant pinned by the reference (pymcac/tests/test_data.py:166-205)
     st = sim.state()
