@@ -1094,12 +1094,13 @@ int mcac_gpu_rand(mcac_gpu *h, int64_t n, int32_t *out) {
 int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record *records, int64_t n_records, mcac_run_report *report) {
     CK(cudaSetDevice(h->device));
     if (!h->uploaded) { h->err = "run before upload_state"; return E_INPUT; }
-    if (h->prm.pick_method != MCAC_PICK_RANDOM || !h->prm.with_collisions || h->prm.with_surface_reactions || h->prm.with_potentials ||
-        h->prm.with_nucleation) {
-        h->err = "mcac_gpu_run: this configuration is not on the device-resident loop yet (use the per-call entry points)";
+    if (h->prm.with_potentials || h->prm.with_nucleation) {
+        h->err = "mcac_gpu_run: interaction potentials / nucleation are not on the device-resident loop yet";
         return E_INPUT;
     }
-    const int B = batch > 0 ? std::min<int>(batch, kMaxBatch) : 256;
+    // speculative batches need a pick sequence that is fixed between events: random pick, no per-step growth
+    const bool speculative = h->prm.pick_method == MCAC_PICK_RANDOM && h->prm.with_collisions && !h->prm.with_surface_reactions;
+    const int B = !speculative ? 1 : (batch > 0 ? std::min<int>(batch, kMaxBatch) : 256);
     TRY(pull_scalars(h));
     const Scalars at_start = h->sc_host;
     const long long launches0 = h->launches;
@@ -1117,7 +1118,68 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     int64_t steps = 0, batches = 0, sorts = 0, dups = 0;
     int rc = E_OK;
     bool fin = false;
-    while (steps < max_steps) {
+    while (!speculative && steps < max_steps) {  // ---- general step: one MC step per iteration, calcul() order
+        if (finished(h)) { fin = true; break; }
+        const mcac_params &p = h->prm;
+        const bool growth = p.with_surface_reactions != 0, pick_last = p.pick_method == MCAC_PICK_LAST;
+        if (h->sc_host.event && p.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(p.u_sg < 0.0)) {
+            if ((rc = duplicate(h)) != E_OK) break;
+            dups++;
+        }
+        if (!pick_last && (h->sc_host.event || growth || !h->pick_valid)) {
+            if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
+            sorts++;
+        }
+        if ((rc = refresh_labels(h)) != E_OK) break;
+        if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph)
+            if ((rc = compact_pool(h)) != E_OK) break;
+        const int draws = pick_last ? 2 : 3;
+        if ((rc = ensure_rng(h, h->sc_host.rand_pos + draws)) != E_OK) break;
+        if (pick_last) {
+            k_pick_last<<<1, 1024, 0, h->stream>>>(h->d, h->q_slot);
+            k_prepare_direction<<<1, 32, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, 0);
+            h->launches += 2;
+        } else {
+            k_prepare_queries<<<1, 128, 0, h->stream>>>(h->d, 1, h->q_slot, h->q_dir, h->q_dist);
+            h->launches++;
+        }
+        if (p.with_collisions) {
+            prof_begin(h, 0);
+            if ((rc = search_launch(h, 1)) != E_OK) break;
+            prof_end(h);
+        }
+        StepArgs sa;
+        sa.q_slot = h->q_slot; sa.q_dir = h->q_dir; sa.q_dist = h->q_dist; sa.res = h->q_res;
+        sa.rec = (records && n_records > 0) ? h->rec_dev : nullptr;
+        sa.rec_cap = n_records; sa.rec_index = steps;
+        sa.pick_last = pick_last; sa.with_collisions = p.with_collisions; sa.n_try = 1; sa.draws = draws;
+        prof_begin(h, 1);
+        k_step_move<<<1, kCommitThreads, 0, h->stream>>>(h->d, sa);
+        if (growth) k_grow_pending<<<div_up(p.individual_surf_reactions ? h->sc_host.n_sph : h->sc_host.pool_top, 256), 256, 0, h->stream>>>(h->d, p.individual_surf_reactions);
+        k_step_merge<<<1, kCommitThreads, 0, h->stream>>>(h->d, sa.rec, sa.rec_cap, sa.rec_index);
+        prof_end(h);
+        h->launches += growth ? 3 : 2;
+        if (growth) {  // calcul.cpp:184-206 — the frequency test uses the counter BEFORE this step's bookkeeping
+            const int full = (h->sc_host.n_iter_without_event % p.full_aggregate_update_frequency == 0) ? 1 : 0;
+            k_update_step<<<div_up(h->sc_host.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
+            h->launches++;
+        }
+        {   // refresh() after an event, PhysicalModel::update after an event or in growth mode (calcul.cpp:232-234, 272-277)
+            const int nb = std::min(1024, std::max(1, div_up(h->sc_host.n_agg_slots, kReduceThreads)));
+            k_refresh_partials<<<nb, kReduceThreads, 0, h->stream>>>(h->d, h->partials);
+            if (growth) k_step_totals<<<1, 32, 0, h->stream>>>(h->d, h->partials, nb);
+            else k_refresh_if_event<<<1, 32, 0, h->stream>>>(h->d, h->partials, nb);
+            h->launches += 2;
+        }
+        if (cudaGetLastError() != cudaSuccess) { h->err = "general step launch failed"; rc = E_UNKNOWN; break; }
+        if ((rc = pull_scalars(h)) != E_OK) break;
+        batches++;
+        h->cells_valid = false;
+        if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
+        steps += 1;
+        if (h->sc_host.b_merged) { h->pick_valid = false; h->labels_valid = false; }
+    }
+    while (speculative && steps < max_steps) {
         if (finished(h)) { fin = true; break; }
         if (h->sc_host.event || !h->pick_valid) {
             // top of the loop after an event (calcul.cpp:72-101): duplication test, then sort_time_steps(max)

@@ -31,6 +31,9 @@ struct Scalars {
     int error;  // sticky device-side error (ErrorCodes)
     // outcome of the last batch
     int b_committed, b_stop_reason, b_contact, b_merged, b_need;
+    // general step: contact found by the search, merged after growth (calcul.cpp:174-181)
+    int p_contact, p_ms, p_os, p_magg, p_oagg, p_slot;
+    double p_dt, p_dt_indiv;
 };
 enum StopReason { STOP_NONE = 0, STOP_CONTACT = 1, STOP_CONFLICT = 2, STOP_FINISHED = 3, STOP_BATCH_END = 4 };
 

@@ -13,7 +13,7 @@ namespace mcacb {
 constexpr int kSearchThreads = 128;
 constexpr int kCandCap = 512;   // eligible aggregates per search kept in shared memory
 constexpr int kCommitThreads = 512;
-constexpr int kMaxBatch = 1024;
+constexpr int kMaxBatch = 512;
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
@@ -64,11 +64,21 @@ __device__ __forceinline__ void atomic_max_positive_double(double *addr, double 
 // ------------------------------------------------------------------------------------------------
 // K10 — glibc rand() stream: one thread advances the 31-word ring kept in registers/local memory.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_rng_fill(GlibcRandState *st, int *out, int n) {
+__global__ void k_rng_fill(GlibcRandState *st, int *out, int n) {  // n multiple of 31, ring position 0 on entry and exit
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    GlibcRandState s = *st;
-    for (int i = 0; i < n; i++) out[i] = glibc_rand_next(s);
-    *st = s;
+    uint32_t r[31];
+#pragma unroll
+    for (int k = 0; k < 31; k++) r[k] = st->ring[(st->pos + k) % 31];
+    for (int base = 0; base + 31 <= n; base += 31) {
+#pragma unroll
+        for (int k = 0; k < 31; k++) {  // r[i] = r[i-31] + r[i-3]; compile-time ring indices keep the state in registers
+            r[k] = r[k] + r[(k + 28) % 31];
+            out[base + k] = (int)(r[k] >> 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 31; k++) st->ring[k] = r[k];
+    st->pos = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -654,6 +664,9 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     __shared__ double scratch[kUpdateScratch];
     __shared__ double cap[8];  // contact step: dt, proper time, position right after the move
     __shared__ int s_conf, s_contact, s_limit, s_finished;
+    __shared__ double4 sh_posr[kMaxBatch];  // movers of the batch staged once: the O(B^2) conflict test then runs from shared memory
+    __shared__ double sh_dist[kMaxBatch];
+    __shared__ double sh_dir[3 * kMaxBatch];
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
     Scalars &sc = *d.sc;
     const double box = sc.box_length;
@@ -665,6 +678,9 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     for (int j = tid; j < nq; j += nth) {
         sh_slot[j] = b.q_slot[j];
         sh_contact[j] = (b.res[j].distance <= b.q_dist[j]) ? 1 : 0;  // `next_contact <= full_distance`, calcul.cpp:128
+        sh_posr[j] = d.a_posr[b.q_slot[j]];
+        sh_dist[j] = b.q_dist[j];
+        sh_dir[3 * j] = b.q_dir[3 * j]; sh_dir[3 * j + 1] = b.q_dir[3 * j + 1]; sh_dir[3 * j + 2] = b.q_dir[3 * j + 2];
     }
     __syncthreads();
     // ---- stop conditions evaluated at the top of every step (PhysicalModel::finished, physical_model.cpp:288-337)
@@ -686,22 +702,22 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     // ---- conflicts with earlier movers of the batch
     for (int j = tid; j < nq; j += nth) {
         const int sj = sh_slot[j];
-        const double4 aj = d.a_posr[sj];
-        const double dj = b.q_dist[j];
-        const double djx = b.q_dir[3 * j], djy = b.q_dir[3 * j + 1], djz = b.q_dir[3 * j + 2];
+        const double4 aj = sh_posr[j];
+        const double dj = sh_dist[j];
+        const double djx = sh_dir[3 * j], djy = sh_dir[3 * j + 1], djz = sh_dir[3 * j + 2];
         bool conflict = false;
         for (int i = 0; i < j && !conflict; i++) {
             const int si = sh_slot[i];
             if (si == sj) { conflict = true; break; }
-            const double4 ai = d.a_posr[si];
-            const double di = b.q_dist[i];
+            const double4 ai = sh_posr[i];
+            const double di = sh_dist[i];
             const double guard = (dj + di + aj.w + ai.w) * (1. + 1e-9) + 1e-9 * box;
             const double ex = fabs(periodic_distance(aj.x - ai.x, box)), ey = fabs(periodic_distance(aj.y - ai.y, box)),
                          ez = fabs(periodic_distance(aj.z - ai.z, box));
             if (ex > guard || ey > guard || ez > guard) continue;
             const double before = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, ai.x, ai.y, ai.z, ai.w, djx, djy, djz, dj, box);
-            const double nx = periodic_position(ai.x + b.q_dir[3 * i] * di, box), ny = periodic_position(ai.y + b.q_dir[3 * i + 1] * di, box),
-                         nz = periodic_position(ai.z + b.q_dir[3 * i + 2] * di, box);
+            const double nx = periodic_position(ai.x + sh_dir[3 * i] * di, box), ny = periodic_position(ai.y + sh_dir[3 * i + 1] * di, box),
+                         nz = periodic_position(ai.z + sh_dir[3 * i + 2] * di, box);
             const double after = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, nx, ny, nz, ai.w, djx, djy, djz, dj, box);
             if (before < dj || after < dj) conflict = true;
         }
@@ -803,6 +819,126 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
 }
 
 // ------------------------------------------------------------------------------------------------
+// General step (growth / pick_last / no-collision configurations): one MC step per launch sequence, in the exact
+// order of calcul() (src/calcul.cpp:93-234): move + clocks here, then K8 growth, then the deferred merge, then updates.
+// ------------------------------------------------------------------------------------------------
+// AggregatList::pick_last (aggregat_list.cpp:67-81): first minimum of proper_time in label (= slot) order
+__global__ void __launch_bounds__(1024) k_pick_last(DevState d, int *q_slot) {
+    __shared__ double sv[32];
+    __shared__ int si[32];
+    const int n = d.sc->n_agg_slots;
+    double best = INFINITY;
+    int who = 0x7fffffff;
+    for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        if (!d.a_alive[s]) continue;
+        const double t = d.a_ptime[s];
+        if (t < best || (t == best && s < who)) { best = t; who = s; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(kFull, best, o);
+        const int ow = __shfl_xor_sync(kFull, who, o);
+        if (ob < best || (ob == best && ow < who)) { best = ob; who = ow; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = who; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+            if (sv[w] < best || (sv[w] == best && si[w] < who)) { best = sv[w]; who = si[w]; }
+        q_slot[0] = who;
+    }
+}
+// direction (2 draws) + lpm for an already picked aggregate (PICK_LAST, or a re-drawn orientation)
+__global__ void k_prepare_direction(DevState d, int *q_slot, double *q_dir, double *q_dist, long long draw_offset) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long p = d.sc->rand_pos + draw_offset - d.rng_buf_base;
+    const Vec3 dir = direction_from_draws(uniform_from_rand(d.rng_buf[p]), uniform_from_rand(d.rng_buf[p + 1]));
+    q_dir[0] = dir.x; q_dir[1] = dir.y; q_dir[2] = dir.z;
+    q_dist[0] = d.a_lpm[q_slot[0]];
+}
+struct StepArgs {
+    const int *q_slot;
+    const double *q_dir;
+    const double *q_dist;
+    const SearchResult *res;
+    mcac_step_record *rec;
+    long long rec_cap, rec_index;
+    int pick_last, with_collisions, n_try, draws;
+};
+__global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepArgs a) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    Scalars &sc = *d.sc;
+    const double box = sc.box_length;
+    const int slot = a.q_slot[0];
+    const double full = a.q_dist[0];
+    SearchResult r;
+    r.distance = INFINITY; r.moving_slot = r.other_slot = r.other_agg = -1; r.n_bounding = 0; r.n_sphere_pairs = 0;
+    if (a.with_collisions) r = a.res[0];
+    const bool contact = a.with_collisions && r.distance <= full;
+    const double move = contact ? r.distance : full;
+    const double time_before = sc.time;
+    const int n_agg_before = sc.n_agg;
+    double deltatemps = a.pick_last ? d.a_ts[slot] : sc.max_time_step / sc.cum_total;  // calcul.cpp:103,106
+    double deltatemps_indiv = d.a_ts[slot];                                             // :108
+    agg_translate<true>(d, slot, a.q_dir[0] * move, a.q_dir[1] * move, a.q_dir[2] * move, box, tid, nth);
+    if (tid == 0) {
+        const double factor = move / full + static_cast<double>(a.n_try - 1);           // :147-148
+        deltatemps = deltatemps * factor;
+        deltatemps_indiv = deltatemps_indiv * factor;
+        d.a_ptime[slot] += deltatemps;                                                  // :149
+        const double dt_rec = deltatemps;
+        if (a.pick_last) deltatemps = deltatemps / double(n_agg_before);                // :150-152
+        sc.time = time_before + deltatemps;
+        sc.p_contact = contact ? 1 : 0;
+        sc.p_ms = r.moving_slot; sc.p_os = r.other_slot; sc.p_magg = slot; sc.p_oagg = r.other_agg;
+        sc.p_dt = deltatemps; sc.p_dt_indiv = deltatemps_indiv; sc.p_slot = slot;
+        sc.searches += a.with_collisions ? 1 : 0;
+        sc.pair_sphere += r.n_sphere_pairs;
+        sc.pair_bounding += r.n_bounding;
+        if (a.rec && a.rec_index < a.rec_cap) {
+            mcac_step_record o;
+            const bool has = r.other_agg >= 0;
+            o.step = sc.steps_done;
+            o.rand_calls = sc.rand_pos + a.draws;
+            o.source = d.label_of_slot[slot];
+            o.dir[0] = a.q_dir[0]; o.dir[1] = a.q_dir[1]; o.dir[2] = a.q_dir[2];
+            o.full_distance = full;
+            o.distance = r.distance;
+            o.moving_sphere = has ? (long long)d.s_id[r.moving_slot] : -1;
+            o.other_sphere = has ? (long long)d.s_id[r.other_slot] : -1;
+            o.moving_label = has ? (long long)d.label_of_slot[slot] : -1;
+            o.other_label = has ? (long long)d.label_of_slot[r.other_agg] : -1;
+            o.n_agg_before = n_agg_before;
+            o.time_before = time_before;
+            o.dt = dt_rec;
+            o.proper_time_after = d.a_ptime[slot];
+            const double4 p = d.a_posr[slot];
+            o.pos_after[0] = p.x; o.pos_after[1] = p.y; o.pos_after[2] = p.z;
+            o.merged = 0;
+            o.n_try = a.n_try;
+            a.rec[a.rec_index] = o;
+        }
+        sc.steps_done += 1;
+        sc.rand_pos += a.draws;
+    }
+}
+// the deferred AggregatList::merge of the step (calcul.cpp:174-181) + event bookkeeping (:222-229)
+__global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
+    __shared__ double scratch[kUpdateScratch];
+    Scalars &sc = *d.sc;
+    int merged = 0;
+    if (sc.p_contact) merged = agg_merge(d, sc.p_ms, sc.p_os, sc.p_magg, sc.p_oagg, scratch, sc.box_length);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (merged) { sc.n_iter_without_event = 0; sc.total_events += 1; sc.event = 1; }
+        else { sc.n_iter_without_event += 1; sc.event = 0; }
+        sc.b_merged = merged;
+        sc.b_committed = 1;
+        if (rec && rec_index < rec_cap) rec[rec_index].merged = merged;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Event pipeline: AggregatList::refresh + get_total_volume/surface (aggregat_list.cpp:100-108, 28-45) as a
 // deterministic two-phase reduction, and the 1/dt weights of sort_time_steps (:124-131) in label order.
 // ------------------------------------------------------------------------------------------------
@@ -839,20 +975,107 @@ __global__ void __launch_bounds__(kReduceThreads) k_refresh_partials(DevState d,
         partials[2 * gridDim.x + blockIdx.x] = ss;
     }
 }
-__global__ void k_refresh_final(DevState d, const double *partials, int nb) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_refresh_final(DevState d, const double *partials, int nb) {  // one warp, fixed combination order
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 32) return;
     double mx = 0., sv = 0., ss = 0.;
-    for (int b = 0; b < nb; b++) {
+    for (int b = lane; b < nb; b += 32) {
         mx = (mx < partials[b]) ? partials[b] : mx;
         sv += partials[nb + b];
         ss += partials[2 * nb + b];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omx = __shfl_xor_sync(kFull, mx, o);
+        mx = (mx < omx) ? omx : mx;
+        sv += __shfl_xor_sync(kFull, sv, o);
+        ss += __shfl_xor_sync(kFull, ss, o);
+    }
+    if (lane != 0) return;
     Scalars &sc = *d.sc;
     sc.max_time_step = mx;
     sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg);
     sc.total_volume = sv;
     sc.total_surface = ss;
     // PhysicalModel::update, physical_model.cpp:489-498
+    sc.total_volume_concent = sv / sc.box_volume;
+    sc.total_surface_concent = ss / sc.box_volume;
+    sc.aggregate_concentration = static_cast<double>(sc.n_agg) / sc.box_volume;
+    sc.monomer_concentration = static_cast<double>(sc.n_sph) / sc.box_volume;
+    sc.volume_fraction = sv / sc.box_volume;
+}
+// end of a general step: refresh() only after an event (calcul.cpp:232-234), PhysicalModel::update always (:272-277)
+__global__ void k_step_totals(DevState d, const double *partials, int nb) {
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 32) return;
+    double mx = 0., sv = 0., ss = 0.;
+    for (int b = lane; b < nb; b += 32) {
+        mx = (mx < partials[b]) ? partials[b] : mx;
+        sv += partials[nb + b];
+        ss += partials[2 * nb + b];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omx = __shfl_xor_sync(kFull, mx, o);
+        mx = (mx < omx) ? omx : mx;
+        sv += __shfl_xor_sync(kFull, sv, o);
+        ss += __shfl_xor_sync(kFull, ss, o);
+    }
+    if (lane != 0) return;
+    Scalars &sc = *d.sc;
+    if (sc.event) {
+        sc.max_time_step = mx;
+        sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg);
+    }
+    sc.total_volume = sv;
+    sc.total_surface = ss;
+    sc.total_volume_concent = sv / sc.box_volume;
+    sc.total_surface_concent = ss / sc.box_volume;
+    sc.aggregate_concentration = static_cast<double>(sc.n_agg) / sc.box_volume;
+    sc.monomer_concentration = static_cast<double>(sc.n_sph) / sc.box_volume;
+    sc.volume_fraction = sv / sc.box_volume;
+}
+__global__ void k_refresh_if_event(DevState d, const double *partials, int nb) {  // no growth: everything only after an event
+    if (!d.sc->event) return;
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 32) return;
+    double mx = 0., sv = 0., ss = 0.;
+    for (int b = lane; b < nb; b += 32) {
+        mx = (mx < partials[b]) ? partials[b] : mx;
+        sv += partials[nb + b];
+        ss += partials[2 * nb + b];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omx = __shfl_xor_sync(kFull, mx, o);
+        mx = (mx < omx) ? omx : mx;
+        sv += __shfl_xor_sync(kFull, sv, o);
+        ss += __shfl_xor_sync(kFull, ss, o);
+    }
+    if (lane != 0) return;
+    Scalars &sc = *d.sc;
+    sc.max_time_step = mx;
+    sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg);
+    sc.total_volume = sv;
+    sc.total_surface = ss;
+    sc.total_volume_concent = sv / sc.box_volume;
+    sc.total_surface_concent = ss / sc.box_volume;
+    sc.aggregate_concentration = static_cast<double>(sc.n_agg) / sc.box_volume;
+    sc.monomer_concentration = static_cast<double>(sc.n_sph) / sc.box_volume;
+    sc.volume_fraction = sv / sc.box_volume;
+}
+// PhysicalModel::update only (growth mode updates the concentrations every step but max_time_step / avg_npp only on events)
+__global__ void k_totals_final(DevState d, const double *partials, int nb) {
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 32) return;
+    double sv = 0., ss = 0.;
+    for (int b = lane; b < nb; b += 32) { sv += partials[nb + b]; ss += partials[2 * nb + b]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(kFull, sv, o); ss += __shfl_xor_sync(kFull, ss, o); }
+    if (lane != 0) return;
+    Scalars &sc = *d.sc;
+    sc.total_volume = sv;
+    sc.total_surface = ss;
     sc.total_volume_concent = sv / sc.box_volume;
     sc.total_surface_concent = ss / sc.box_volume;
     sc.aggregate_concentration = static_cast<double>(sc.n_agg) / sc.box_volume;
@@ -893,6 +1116,38 @@ __global__ void k_grow(DevState d, double dt, int only_slot) {
     d.s_relv[t] = rel;
     d.s_surf[t] = surface_factor() * r2;
     if (new_r <= d.rp_min_oxid) d.sc->error = 1;  // sphere removal by oxidation (u_sg < 0) is outside the built path
+}
+// growth of the general step: dt and the picked aggregate are device scalars written by k_step_move
+__global__ void k_grow_pending(DevState d, int individual) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const Scalars &sc = *d.sc;
+    int lo = 0, hi = sc.pool_top;
+    double dt = sc.p_dt;
+    if (individual) { lo = d.a_off[sc.p_slot]; hi = lo + d.a_n[sc.p_slot]; dt = sc.p_dt_indiv; }
+    const int t = lo + s;
+    if (t >= hi) return;
+    double4 p = d.s_posr[t];
+    const double new_r = p.w + d.u_sg * dt;
+    const double r2 = new_r * new_r;
+    const double r3 = r2 * new_r;
+    p.w = new_r;
+    d.s_posr[t] = p;
+    double4 rel = d.s_relv[t];
+    rel.w = volume_factor() * r3;
+    d.s_relv[t] = rel;
+    d.s_surf[t] = surface_factor() * r2;
+    if (new_r <= d.rp_min_oxid) d.sc->error = 1;
+}
+// update block of calcul.cpp:184-206 for the general step: mode 0 = every aggregate, mode 1 = individual reactions
+// (only the picked aggregate unless a merge happened, in which case every aggregate, as the reference does)
+__global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int individual) {
+    __shared__ double scratch[8][kUpdateScratch / 4];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + w;
+    const Scalars &sc = *d.sc;
+    if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
+    if (individual && !sc.b_merged && slot != sc.p_slot) return;
+    agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], sc.box_length);
 }
 // K5-K7 over ALL aggregates (growth mode, calcul.cpp:184-206): one warp per aggregate
 __global__ void __launch_bounds__(256) k_update_all(DevState d, int full, int only_slot) {

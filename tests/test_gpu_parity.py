@@ -170,6 +170,70 @@ def test_device_sort_against_std_sort_on_random_weights():
         np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))  # np.cumsum is the sequential sum
 
 
+@pytest.mark.parametrize("name,steps", [("surface_growth_seed42", 2500), ("caps_seed7", 4000), ("pytest_seed42", 20000),
+                                        ("brownian_seed42", 4000)])
+def test_general_step_loop_growth_picklast_nocollision(name, steps):
+    """Configurations without a fixed pick sequence (surface growth: alphas / caps, all aggregates updated every step;
+    pick_last without collisions) run one MC step per launch sequence in calcul()'s order — same records as the oracle.
+    pytest_seed42 runs to its end (NPP_avg limit) through one domain duplication."""
+    g = Golden(name)
+    text = ini_text(merged_config(g.base, g.overrides))
+    sim = Simulation(text)
+    rep, recs = sim.run(steps, records=steps)
+    o = Oracle(g.base, g.overrides)
+    ref = o.run(steps)
+    box = o.scalars()["box_length"]
+    assert rep["steps"] == len(ref)
+    assert rep["finished"] == int(o.finished)
+    assert_records_match(recs, ref, box)
+    assert rep["events"] == int(ref["merged"].sum())
+    assert_states_match(sim.state(), o.state(), box)
+
+
+def test_per_call_entry_points_follow_the_reference_methods():
+    """translate / grow / update(partial, full) / merge / refresh called one by one through the C ABI (the per-call mode a
+    reference shim would use) against the oracle driven the same way."""
+    ov = {"numerics": {"random_seed": 11}, "monomers": {"number": 300}, "surface_growth": {"volsurf_method": "caps"}}
+    text = ini_text(merged_config("pytest", ov))
+    sim = Simulation(text)
+    o = Oracle("pytest", ov)
+    st0 = o.state()
+    rng = np.random.default_rng(0)
+    box = st0["box_length"]
+    # find a pair that collides: sweep label 0..n with long moves until the search reports a contact
+    contact = None
+    for lab in range(st0["n_agg"]):
+        v = rng.normal(size=3); v /= np.linalg.norm(v)
+        c = sim.contact_search(lab, v, box)
+        d, ids = o.search(lab, v, box)
+        assert c.distance == d
+        if np.isfinite(d):
+            contact = (lab, v, c)
+            break
+    assert contact is not None
+    lab, v, c = contact
+    sim.translate(lab, v * c.distance)
+    assert sim.merge(c)
+    st = sim.state()
+    assert st["n_agg"] == st0["n_agg"] - 1
+    kept = min(c.moving_label, c.other_label)
+    assert st["agg_n_spheres"][kept] == 2
+    np.testing.assert_array_equal(np.bincount(st["sphere_label"], minlength=st["n_agg"]), st["agg_n_spheres"])
+    # growth of every sphere then a full update of every aggregate: volumes follow r^3, caps keep V below the sum
+    r_before = st["spheres"]["r"].copy()
+    sim.grow(1e-3)
+    sim.update(-1, full=True)
+    st2 = sim.state()
+    u_sg = st2["u_sg"]
+    np.testing.assert_allclose(st2["spheres"]["r"], r_before + u_sg * 1e-3, rtol=1e-15)
+    np.testing.assert_allclose(st2["spheres"]["volume"], 4 * np.pi / 3 * st2["spheres"]["r"] ** 3, rtol=1e-14)
+    members = st2["members"][st2["offsets"][kept]:st2["offsets"][kept + 1]]
+    assert st2["aggregates"]["volume"][kept] < st2["spheres"]["volume"][members].sum()  # lens caps removed
+    ref = sim.refresh()
+    np.testing.assert_allclose(ref["total_volume"], st2["aggregates"]["volume"].sum(), rtol=1e-13)
+    assert ref["max_time_step"] == st2["aggregates"]["time_step"].max()
+
+
 def test_batch_width_does_not_change_the_trajectory():
     """Speculation must be invisible: batch = 1 (pure sequential) and batch = 512 give bit-identical device results."""
     text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 3}}))
