@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -73,6 +74,9 @@ struct mcac_gpu {
     double *cum_sums = nullptr;
     int *h_flags = nullptr;  // pinned: sort `active` flags
     long long sort_levels = 0, sort_fallbacks = 0;
+    int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
+    long long *part_ll = nullptr;
+    double *part_d = nullptr;
     int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
     int *sweep_slot = nullptr;
     double *sweep_dir = nullptr, *sweep_dist = nullptr;
@@ -335,6 +339,45 @@ int sort_time_steps(mcac_gpu *h, double factor) {
     CK(cudaGetLastError());
     TRY(pull_scalars(h));
     h->pick_valid = true;
+    return E_OK;
+}
+
+// The per-event pipeline as ONE cooperative launch (k_event): labels, refresh / PhysicalModel::update, weights, replayed
+// introsort, cumulative table.  Falls back to the multi-launch form when cooperative launch is unavailable or when
+// introsort's depth limit is hit.
+int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort) {
+    if (h->coop_blocks <= 0) {
+        if (do_refresh || do_totals) { h->labels_valid = false; TRY(refresh_labels(h)); TRY(refresh_reduce(h)); TRY(pull_scalars(h)); }
+        if (do_sort) TRY(sort_time_steps(h, h->sc_host.max_time_step));
+        return E_OK;
+    }
+    EventArgs a{};
+    a.sb = h->sortb;
+    a.part_ll = h->part_ll;
+    a.part_d = h->part_d;
+    a.scan_tmp = h->scan_tmp;
+    a.do_labels = h->labels_valid ? 0 : 1;
+    a.do_refresh = do_refresh ? 1 : 0;
+    a.do_totals = do_totals ? 1 : 0;
+    a.do_sort = do_sort ? 1 : 0;
+    a.cum_sequential_max = h->cum_sequential_max;
+    a.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
+    if (h->prm.sort_order == MCAC_ORDER_HOST_STDSORT) a.do_sort = 0;
+    DevState dcopy = h->d;
+    void *args[] = {&dcopy, &a};
+    CK(cudaLaunchCooperativeKernel((void *)k_event, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream));
+    h->launches++;
+    TRY(pull_scalars(h));
+    h->labels_valid = true;
+    if (do_sort) {
+        if (a.do_sort == 0 || h->sc_host.b_need == 99) {  // host std::sort requested, or introsort depth limit hit
+            h->sc_host.b_need = 0;
+            TRY(push_scalars(h));
+            h->sort_fallbacks++;
+            TRY(sort_time_steps(h, h->sc_host.max_time_step));
+        }
+        h->pick_valid = true;
+    }
     return E_OK;
 }
 
@@ -770,6 +813,15 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     CK(cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)));
     fill_devstate_params(h);
     TRY(alloc_persistent(h));
+    {
+        int occ = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event, kEventThreads, 0) == cudaSuccess && occ > 0)
+            h->coop_blocks = h->n_sm * std::min(occ, 2);
+        if (getenv("MCAC_B200_NO_COOP")) h->coop_blocks = 0;
+        TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
+        TRY(dev_alloc_persistent(h, &h->part_d, 4 * 4096));
+    }
     GlibcRandState st;
     glibc_srand(st, params->random_seed);
     CK(cudaMemcpy(h->d.rng, &st, sizeof(st), cudaMemcpyHostToDevice));
@@ -1117,7 +1169,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     CK(cudaEventRecord(ev0, h->stream));
     int64_t steps = 0, batches = 0, sorts = 0, dups = 0;
     int rc = E_OK;
-    bool fin = false;
+    bool fin = false, need_refresh = false;
     while (!speculative && steps < max_steps) {  // ---- general step: one MC step per iteration, calcul() order
         if (finished(h)) { fin = true; break; }
         const mcac_params &p = h->prm;
@@ -1127,7 +1179,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             dups++;
         }
         if (!pick_last && (h->sc_host.event || growth || !h->pick_valid)) {
-            if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
+            if ((rc = event_pipeline(h, false, false, true)) != E_OK) break;
             sorts++;
         }
         if ((rc = refresh_labels(h)) != E_OK) break;
@@ -1187,7 +1239,8 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                 if ((rc = duplicate(h)) != E_OK) break;
                 dups++;
             }
-            if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
+            if ((rc = event_pipeline(h, need_refresh, need_refresh, true)) != E_OK) break;
+            need_refresh = false;
             sorts++;
         }
         if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph)
@@ -1220,12 +1273,18 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         h->cells_valid = false;
         if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
         steps += h->sc_host.b_committed;
-        if (h->sc_host.b_merged) {
+        if (h->sc_host.b_merged) {  // refresh() + PhysicalModel::update + re-sort happen in the event pipeline at the loop top
             h->pick_valid = false;
-            if ((rc = after_event(h)) != E_OK) break;
+            h->labels_valid = false;
+            need_refresh = true;
+            h->sc_host.avg_npp = static_cast<double>(h->sc_host.n_sph) / static_cast<double>(h->sc_host.n_agg);  // for finished()
         }
         if (h->sc_host.b_stop_reason == STOP_FINISHED) { fin = true; break; }
         if (h->sc_host.b_committed == 0) { h->err = "batch made no progress"; rc = E_UNKNOWN; break; }
+    }
+    if (rc == E_OK && need_refresh) {  // the call ended on a merge: refresh() / PhysicalModel::update belong to that step
+        rc = event_pipeline(h, true, true, false);
+        need_refresh = false;
     }
     CK(cudaEventRecord(ev1, h->stream));
     CK(cudaEventSynchronize(ev1));

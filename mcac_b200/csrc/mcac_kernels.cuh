@@ -3,6 +3,7 @@
 // K8 surface growth, K9 pick table helpers, K10 RNG stream.  No tensor cores: nothing here is a dense
 // contraction (FP64 scalar pipes + HBM/L2 streams).  Compiled with --fmad=false (see mcac_math.cuh).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "../../include/mcac_b200.h"
@@ -1505,6 +1506,357 @@ __global__ void k_sort_finish(DevState d, SortBufs b) {
     if (i >= b.n) return;
     d.sorted_slot[i] = d.slot_of_label[b.perm[i]];
     if (i == 0) { d.sc->n_pick = b.n; d.sc->cum_total = d.cum[b.n - 1]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole per-event pipeline in ONE cooperative launch (grid barriers instead of ~180 launches + host polls):
+// labels (rank of live slots) -> refresh()/PhysicalModel::update -> 1/dt weights -> replayed introsort ->
+// cumulative table -> pick table in slots.  Same arithmetic and same visiting orders as the stand-alone kernels
+// above; every scan is a chunk-contiguous two-phase scan (block b owns elements [b*chunk, (b+1)*chunk)).
+// ------------------------------------------------------------------------------------------------
+constexpr int kEventThreads = 512;
+struct EventArgs {
+    SortBufs sb;
+    long long *part_ll;   // >= gridDim + 1
+    double *part_d;       // >= 4 * (gridDim + 1)
+    int *scan_tmp;        // >= n_agg_slots + 1 (exclusive scan of a_alive)
+    int do_labels, do_refresh /* 1: max_time_step + avg_npp */, do_totals /* PhysicalModel::update */, do_sort;
+    int cum_sequential_max, stable;
+};
+namespace cgx = cooperative_groups;
+
+__device__ __forceinline__ double block_sum_fixed(double v, double *sm /* >= 32 */) {  // fixed tree: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sm[w];
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ double block_max_fixed(double v, double *sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(kFull, v, o); v = (v < t) ? t : v; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t = (t < sm[w]) ? sm[w] : t;
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ long long block_sum_ll(long long v, long long *sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sm[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a) {
+    cgx::grid_group grid = cgx::this_grid();
+    __shared__ long long sm_ll[32];
+    __shared__ double sm_d[32];
+    __shared__ long long sh_carry;
+    const int tid = threadIdx.x, nthr = blockDim.x, nblk = gridDim.x, blk = blockIdx.x;
+    const long long gtid = (long long)blk * nthr + tid, gsize = (long long)nblk * nthr;
+    Scalars &sc = *d.sc;
+    const int n_slots = sc.n_agg_slots;
+
+    // ---------------- phase A: live-slot count per chunk + refresh partials
+    const int chunk_s = ((n_slots + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
+    {
+        long long cnt = 0;
+        double mx = 0., sv = 0., ss = 0.;
+        const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
+        for (int s = lo + tid; s < hi; s += nthr) {
+            if (!d.a_alive[s]) continue;
+            cnt += 1;
+            const double ts = d.a_ts[s];
+            mx = (mx < ts) ? ts : mx;
+            sv += d.a_vol[s];
+            ss += d.a_surf[s];
+        }
+        const long long c = block_sum_ll(cnt, sm_ll);
+        const double bmx = block_max_fixed(mx, sm_d), bsv = block_sum_fixed(sv, sm_d), bss = block_sum_fixed(ss, sm_d);
+        if (tid == 0) {
+            a.part_ll[blk] = c;
+            a.part_d[blk] = bmx;
+            a.part_d[nblk + blk] = bsv;
+            a.part_d[2 * nblk + blk] = bss;
+        }
+    }
+    grid.sync();
+    // ---------------- phase B: labels; every block derives n_agg / max / totals in the same fixed order
+    int n_agg = 0;
+    double factor = sc.max_time_step;
+    {
+        long long base = 0, total = 0;
+        double mx = 0., sv = 0., ss = 0.;
+        for (int b = 0; b < nblk; b++) {  // sequential, same in every thread: deterministic
+            const long long c = a.part_ll[b];
+            if (b < blk) base += c;
+            total += c;
+            const double t = a.part_d[b];
+            mx = (mx < t) ? t : mx;
+            sv += a.part_d[nblk + b];
+            ss += a.part_d[2 * nblk + b];
+        }
+        n_agg = (int)total;
+        if (a.do_refresh) factor = mx;
+        if (a.do_labels) {
+            const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
+            if (tid == 0) sh_carry = base;
+            __syncthreads();
+            for (int t0 = lo; t0 < hi; t0 += nthr) {
+                const int s = t0 + tid;
+                const int alive = (s < hi) ? d.a_alive[s] : 0;
+                int tot;
+                __shared__ int ws[32];
+                const int pre = block_exclusive_scan(alive, &tot, ws);
+                if (s < hi) {
+                    const int lab = (int)sh_carry + pre;
+                    if (alive) { d.label_of_slot[s] = lab; d.slot_of_label[lab] = s; }
+                    else d.label_of_slot[s] = -1;
+                }
+                __syncthreads();
+                if (tid == 0) sh_carry += tot;
+                __syncthreads();
+            }
+        }
+        if (gtid == 0) {
+            if (a.do_refresh) {
+                sc.max_time_step = mx;
+                sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(n_agg);
+            }
+            if (a.do_totals) {
+                sc.total_volume = sv;
+                sc.total_surface = ss;
+                sc.total_volume_concent = sv / sc.box_volume;
+                sc.total_surface_concent = ss / sc.box_volume;
+                sc.aggregate_concentration = static_cast<double>(n_agg) / sc.box_volume;
+                sc.monomer_concentration = static_cast<double>(sc.n_sph) / sc.box_volume;
+                sc.volume_fraction = sv / sc.box_volume;
+            }
+        }
+    }
+    if (!a.do_sort) return;
+    grid.sync();
+    // ---------------- phase C: weights in label order + sort state
+    SortBufs b = a.sb;
+    const int n = n_agg;
+    b.n = n;
+    b.stable = a.stable;
+    for (long long i = gtid; i < n; i += gsize) {
+        b.perm[i] = (int)i;
+        b.wk[i] = factor / d.a_ts[d.slot_of_label[i]];
+        b.segf[i] = 0;
+        b.segl[i] = n;
+    }
+    if (gtid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
+    grid.sync();
+    const int chunk = ((n + 1 + nblk - 1) / nblk + nthr - 1) / nthr * nthr;  // over n+1 entries so that pre[n] exists
+    int lg = 0;
+    while ((1LL << (lg + 1)) <= n) lg++;
+    int depth = 2 * lg;
+    bool active = n > kSortLeaf;
+    auto pivot_of = [&](int f, int l) {  // __move_median_to_first(first, first+1, mid, last-1)
+        const int pa = f + 1, pb = f + (l - f) / 2, pc = l - 1;
+        const double ka = b.wk[pa], kb = b.wk[pb], kc = b.wk[pc];
+        const int la = b.perm[pa], lb = b.perm[pb], lc = b.perm[pc];
+        int pick;
+        if (w_less(ka, la, kb, lb, b.stable)) {
+            if (w_less(kb, lb, kc, lc, b.stable)) pick = pb;
+            else if (w_less(ka, la, kc, lc, b.stable)) pick = pc;
+            else pick = pa;
+        } else if (w_less(ka, la, kc, lc, b.stable)) pick = pa;
+        else if (w_less(kb, lb, kc, lc, b.stable)) pick = pc;
+        else pick = pb;
+        const double kf = b.wk[f];
+        const int lf = b.perm[f];
+        b.wk[f] = b.wk[pick]; b.perm[f] = b.perm[pick];
+        b.wk[pick] = kf; b.perm[pick] = lf;
+    };
+    if (active && gtid == 0) pivot_of(0, n);
+    int level = 0;
+    bool fail = false;
+    while (active) {
+        depth--;
+        grid.sync();  // pivots of this level are in place
+        // ---- flags + chunk sums
+        {
+            const int lo = blk * chunk, hi = min(n + 1, lo + chunk);
+            long long acc = 0;
+            for (int i = lo + tid; i < hi; i += nthr) {
+                long long fl = 0;
+                if (i < n) {
+                    const int f = b.segf[i], l = b.segl[i];
+                    if (l - f > kSortLeaf && i > f) {
+                        const double kp = b.wk[f], kx = b.wk[i];
+                        const int lp = b.perm[f], lx = b.perm[i];
+                        if (!w_less(kx, lx, kp, lp, b.stable)) fl |= 1LL;
+                        if (!w_less(kp, lp, kx, lx, b.stable)) fl |= (1LL << 32);
+                    }
+                }
+                b.flags[i] = fl;
+                acc += fl;
+            }
+            const long long t = block_sum_ll(acc, sm_ll);
+            if (tid == 0) a.part_ll[blk] = t;
+        }
+        grid.sync();
+        // ---- exclusive scan of the packed flags
+        {
+            long long base = 0;
+            for (int bb = tid; bb < blk; bb += nthr) base += a.part_ll[bb];
+            base = block_sum_ll(base, sm_ll);
+            const int lo = blk * chunk, hi = min(n + 1, lo + chunk);
+            if (tid == 0) sh_carry = base;
+            __syncthreads();
+            for (int t0 = lo; t0 < hi; t0 += nthr) {
+                const int i = t0 + tid;
+                const long long v = (i < hi) ? b.flags[i] : 0;
+                long long tot;
+                const long long pre = block_exclusive_scan_ll(v, &tot, sm_ll);
+                if (i < hi) b.pre[i] = sh_carry + pre;
+                __syncthreads();
+                if (tid == 0) sh_carry += tot;
+                __syncthreads();
+            }
+        }
+        grid.sync();
+        // ---- scatter the "not < pivot" (ascending) and "not > pivot" (descending) positions
+        for (long long i = gtid; i < n; i += gsize) {
+            const int f = b.segf[i], l = b.segl[i];
+            if (l - f <= kSortLeaf || i <= f) continue;
+            const int base = f + 1;
+            const long long p0 = b.pre[base], pi_ = b.pre[i], pl = b.pre[l];
+            const long long fl = b.flags[i];
+            if (fl & 1LL) b.tmp_a[base + (int)((pi_ & 0xffffffffLL) - (p0 & 0xffffffffLL))] = (int)i;
+            if (fl >> 32) {
+                const int n_b = (int)((pl >> 32) - (p0 >> 32));
+                b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = (int)i;
+            }
+        }
+        grid.sync();
+        // ---- pairwise swaps + where the two scans stop
+        for (long long j = gtid; j < n; j += gsize) {
+            const int f = b.segf[j], l = b.segl[j];
+            if (l - f <= kSortLeaf || j <= f) continue;
+            const int base = f + 1, k = (int)j - base;
+            const long long p0 = b.pre[base], pl = b.pre[l];
+            const int n_a = (int)((pl & 0xffffffffLL) - (p0 & 0xffffffffLL)), n_b = (int)((pl >> 32) - (p0 >> 32));
+            const int m = n_a < n_b ? n_a : n_b;
+            const bool sw = k < m && b.tmp_a[base + k] < b.tmp_b[base + k];
+            const bool next_sw = (k + 1 < m) && b.tmp_a[base + k + 1] < b.tmp_b[base + k + 1];
+            if (sw) {
+                const int pa = b.tmp_a[base + k], pb = b.tmp_b[base + k];
+                const double ka = b.wk[pa];
+                const int la = b.perm[pa];
+                b.wk[pa] = b.wk[pb]; b.perm[pa] = b.perm[pb];
+                b.wk[pb] = ka; b.perm[pb] = la;
+            }
+            int s_ = -1;
+            if (sw && !next_sw) s_ = k + 1;
+            else if (k == 0 && !sw) s_ = 0;
+            if (s_ >= 0) {
+                const int a_s = s_ < n_a ? b.tmp_a[base + s_] : 0x7fffffff;
+                const int b_prev = s_ > 0 ? b.tmp_b[base + s_ - 1] : l;
+                b.cut[f] = a_s < b_prev ? a_s : b_prev;
+            }
+        }
+        if (gtid == 0) b.active[(level + 1) & 1] = 0;
+        grid.sync();
+        // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
+        for (long long i = gtid; i < n; i += gsize) {
+            const int f = b.segf[i], l = b.segl[i];
+            if (l - f <= kSortLeaf) continue;
+            const int c = b.cut[f];
+            int nf = f, nl = l;
+            if (i < c) nl = c; else nf = c;
+            b.segf[i] = nf;
+            b.segl[i] = nl;
+            if (i == nf && nl - nf > kSortLeaf) {
+                if (depth > 0) { b.active[level & 1] = 1; pivot_of(nf, nl); }
+                else b.active[2] = 1;  // would enter introsort's heap-sort branch
+            }
+        }
+        grid.sync();
+        active = b.active[level & 1] != 0;
+        fail = b.active[2] != 0;
+        if (fail) break;
+        level++;
+    }
+    if (fail) {  // the host falls back to libstdc++'s std::sort for this call
+        if (gtid == 0) sc.b_need = 99;
+        return;
+    }
+    // ---- __final_insertion_sort per leaf
+    for (long long i = gtid; i < n; i += gsize) {
+        if (b.segf[i] != i) continue;
+        const int f = (int)i, l = b.segl[i];
+        for (int x = f + 1; x < l; x++) {
+            const double kv = b.wk[x];
+            const int lv = b.perm[x];
+            int y = x - 1;
+            while (y >= f && w_less(kv, lv, b.wk[y], b.perm[y], b.stable)) {
+                b.wk[y + 1] = b.wk[y]; b.perm[y + 1] = b.perm[y];
+                y--;
+            }
+            b.wk[y + 1] = kv; b.perm[y + 1] = lv;
+        }
+    }
+    grid.sync();
+    // ---- cumulative_time_steps
+    if (n <= a.cum_sequential_max) {
+        if (gtid == 0) {
+            double acc = b.wk[0];
+            d.cum[0] = acc;
+            for (int i = 1; i < n; i++) { acc = acc + b.wk[i]; d.cum[i] = acc; }
+        }
+    } else {
+        const int chunk_c = ((n + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
+        const int lo = blk * chunk_c, hi = min(n, lo + chunk_c);
+        double acc = 0.;
+        for (int i = lo + tid; i < hi; i += nthr) acc += b.wk[i];
+        const double t = block_sum_fixed(acc, sm_d);
+        if (tid == 0) a.part_d[3 * nblk + blk] = t;
+        grid.sync();
+        double base = 0.;
+        for (int bb = 0; bb < blk; bb++) base += a.part_d[3 * nblk + bb];  // sequential: deterministic
+        __shared__ double carry_d;
+        __shared__ double wtot[32];
+        if (tid == 0) carry_d = base;
+        __syncthreads();
+        for (int t0 = lo; t0 < hi; t0 += nthr) {
+            const int i = t0 + tid;
+            const double v = (i < hi) ? b.wk[i] : 0.;
+            double inc = v;
+            const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double tt = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += tt;
+            }
+            if (lane == 31) wtot[w] = inc;
+            __syncthreads();
+            double wbase = 0.;
+            for (int ww = 0; ww < w; ww++) wbase += wtot[ww];
+            if (i < hi) d.cum[i] = carry_d + wbase + inc;
+            __syncthreads();
+            if (tid == nthr - 1) carry_d = carry_d + wbase + inc;
+            __syncthreads();
+        }
+    }
+    grid.sync();
+    for (long long i = gtid; i < n; i += gsize) d.sorted_slot[i] = d.slot_of_label[b.perm[i]];
+    if (gtid == 0) { sc.n_pick = n; sc.cum_total = d.cum[n - 1]; }
 }
 
 // ------------------------------------------------------------------------------------------------
