@@ -172,6 +172,8 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     TRY(dev_alloc(h, &sb.tmp_a, agg_cap + 1));
     TRY(dev_alloc(h, &sb.tmp_b, agg_cap + 1));
     TRY(dev_alloc(h, &sb.cut, agg_cap + 1));
+    TRY(dev_alloc(h, &sb.fin_perm, agg_cap + 1));
+    TRY(dev_alloc(h, &sb.fin_wk, agg_cap + 1));
     TRY(dev_alloc(h, &sb.active, 4));
     TRY(dev_alloc(h, &h->scan64_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     TRY(dev_alloc(h, &h->cum_sums, agg_cap / (kScanBlock * kScanItems) + 8));
@@ -345,24 +347,26 @@ int sort_time_steps(mcac_gpu *h, double factor) {
 // The per-event pipeline as ONE cooperative launch (k_event): labels, refresh / PhysicalModel::update, weights, replayed
 // introsort, cumulative table.  Falls back to the multi-launch form when cooperative launch is unavailable or when
 // introsort's depth limit is hit.
-int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort) {
-    if (h->coop_blocks <= 0) {
+int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, const double *factor = nullptr) {
+    if (h->coop_blocks <= 0 || h->prm.sort_order == MCAC_ORDER_HOST_STDSORT) {
         if (do_refresh || do_totals) { h->labels_valid = false; TRY(refresh_labels(h)); TRY(refresh_reduce(h)); TRY(pull_scalars(h)); }
-        if (do_sort) TRY(sort_time_steps(h, h->sc_host.max_time_step));
+        if (do_sort) TRY(sort_time_steps(h, factor ? *factor : h->sc_host.max_time_step));
         return E_OK;
     }
     EventArgs a{};
+    a.use_factor = factor ? 1 : 0;
+    a.factor = factor ? *factor : 0.;
     a.sb = h->sortb;
     a.part_ll = h->part_ll;
     a.part_d = h->part_d;
     a.scan_tmp = h->scan_tmp;
+    a.sorted_label = h->sorted_label;
     a.do_labels = h->labels_valid ? 0 : 1;
     a.do_refresh = do_refresh ? 1 : 0;
     a.do_totals = do_totals ? 1 : 0;
     a.do_sort = do_sort ? 1 : 0;
     a.cum_sequential_max = h->cum_sequential_max;
     a.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
-    if (h->prm.sort_order == MCAC_ORDER_HOST_STDSORT) a.do_sort = 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
     CK(cudaLaunchCooperativeKernel((void *)k_event, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream));
@@ -370,11 +374,11 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort) {
     TRY(pull_scalars(h));
     h->labels_valid = true;
     if (do_sort) {
-        if (a.do_sort == 0 || h->sc_host.b_need == 99) {  // host std::sort requested, or introsort depth limit hit
+        if (h->sc_host.b_need == 99) {  // introsort's depth limit was hit: multi-launch path, which ends in libstdc++'s std::sort
             h->sc_host.b_need = 0;
             TRY(push_scalars(h));
             h->sort_fallbacks++;
-            TRY(sort_time_steps(h, h->sc_host.max_time_step));
+            TRY(sort_time_steps(h, factor ? *factor : h->sc_host.max_time_step));
         }
         h->pick_valid = true;
     }
@@ -1074,7 +1078,7 @@ int mcac_gpu_refresh(mcac_gpu *h, double *max_time_step, double *avg_npp, double
 int mcac_gpu_sort_time_steps(mcac_gpu *h, double factor) {
     CK(cudaSetDevice(h->device));
     TRY(pull_scalars(h));
-    TRY(sort_time_steps(h, factor));
+    TRY(event_pipeline(h, false, false, true, &factor));
     return E_OK;
 }
 

@@ -1256,6 +1256,8 @@ struct SortBufs {
     int *segf, *segl;   // per element: its current segment [segf, segl)
     long long *flags, *pre;  // low 32 bits: "not < pivot" ; high 32 bits: "not > pivot" ; and their exclusive scan
     int *tmp_a, *tmp_b, *cut;
+    int *fin_perm;      // final order (cooperative kernel: all-equal segments are finished analytically, out of place)
+    double *fin_wk;
     int *active;        // [0]: some segment still longer than 16 ; [1]: fail
     int n, stable;
 };
@@ -1520,8 +1522,11 @@ struct EventArgs {
     long long *part_ll;   // >= gridDim + 1
     double *part_d;       // >= 4 * (gridDim + 1)
     int *scan_tmp;        // >= n_agg_slots + 1 (exclusive scan of a_alive)
+    int *sorted_label;    // the reference's index_sorted_time_steps (labels), for mcac_gpu_get_pick_table
     int do_labels, do_refresh /* 1: max_time_step + avg_npp */, do_totals /* PhysicalModel::update */, do_sort;
     int cum_sequential_max, stable;
+    int use_factor;       // sort_time_steps(factor) called with an explicit factor (per-call C ABI)
+    double factor;
 };
 namespace cgx = cooperative_groups;
 
@@ -1610,6 +1615,7 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
         }
         n_agg = (int)total;
         if (a.do_refresh) factor = mx;
+        if (a.use_factor) factor = a.factor;
         if (a.do_labels) {
             const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
             if (tid == 0) sh_carry = base;
@@ -1731,18 +1737,47 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
             }
         }
         grid.sync();
-        // ---- scatter the "not < pivot" (ascending) and "not > pivot" (descending) positions
+        // ---- scatter the "not < pivot" (ascending) and "not > pivot" (descending) positions.
+        // A segment whose elements ALL equal the pivot (whole tie classes: every monomer of a monodisperse run) needs no
+        // more memory passes: introsort's moves on equal keys do not depend on the data (median-of-3 picks `mid`, the
+        // Hoare partition mirrors [f+1, l-1], the cut falls at f+1+(m-1)/2, leaves do not move), so every element
+        // computes its final position in registers and leaves the level loop.
         for (long long i = gtid; i < n; i += gsize) {
             const int f = b.segf[i], l = b.segl[i];
-            if (l - f <= kSortLeaf || i <= f) continue;
+            if (l - f <= kSortLeaf) continue;
             const int base = f + 1;
-            const long long p0 = b.pre[base], pi_ = b.pre[i], pl = b.pre[l];
+            const long long p0 = b.pre[base], pl = b.pre[l];
+            const int n_a = (int)((pl & 0xffffffffLL) - (p0 & 0xffffffffLL)), n_b = (int)((pl >> 32) - (p0 >> 32));
+            if (n_a == l - f - 1 && n_b == l - f - 1) {
+                int cf = f, cl = l, pos = (int)i, dep = depth;
+                bool first = true, bad = false;
+                while (cl - cf > kSortLeaf) {
+                    const int m = cl - cf;
+                    if (!first) {  // the pivot move of the current level has already been applied to the arrays
+                        const int mid = cf + m / 2;
+                        if (pos == cf) pos = mid; else if (pos == mid) pos = cf;
+                    }
+                    first = false;
+                    if (pos > cf) pos = cf + cl - pos;
+                    const int cutp = cf + 1 + (m - 1) / 2;
+                    if (pos < cutp) cl = cutp; else cf = cutp;
+                    if (cl - cf > kSortLeaf) {
+                        if (dep == 0) { bad = true; break; }
+                        dep--;
+                    }
+                }
+                if (bad) { b.active[2] = 1; continue; }
+                b.fin_perm[pos] = b.perm[i];
+                b.fin_wk[pos] = b.wk[i];
+                b.segf[i] = 0x7fffffff;  // done: inactive in every later phase
+                b.segl[i] = 0;
+                continue;
+            }
+            if (i <= f) continue;
+            const long long pi_ = b.pre[i];
             const long long fl = b.flags[i];
             if (fl & 1LL) b.tmp_a[base + (int)((pi_ & 0xffffffffLL) - (p0 & 0xffffffffLL))] = (int)i;
-            if (fl >> 32) {
-                const int n_b = (int)((pl >> 32) - (p0 >> 32));
-                b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = (int)i;
-            }
+            if (fl >> 32) b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = (int)i;
         }
         grid.sync();
         // ---- pairwise swaps + where the two scans stop
@@ -1811,20 +1846,23 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
             }
             b.wk[y + 1] = kv; b.perm[y + 1] = lv;
         }
+        b.fin_perm[i] = b.perm[i];  // whole leaf, written by its leader after sorting it
+        b.fin_wk[i] = b.wk[i];
+        for (int x = f + 1; x < l; x++) { b.fin_perm[x] = b.perm[x]; b.fin_wk[x] = b.wk[x]; }
     }
     grid.sync();
     // ---- cumulative_time_steps
     if (n <= a.cum_sequential_max) {
         if (gtid == 0) {
-            double acc = b.wk[0];
+            double acc = b.fin_wk[0];
             d.cum[0] = acc;
-            for (int i = 1; i < n; i++) { acc = acc + b.wk[i]; d.cum[i] = acc; }
+            for (int i = 1; i < n; i++) { acc = acc + b.fin_wk[i]; d.cum[i] = acc; }
         }
     } else {
         const int chunk_c = ((n + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
         const int lo = blk * chunk_c, hi = min(n, lo + chunk_c);
         double acc = 0.;
-        for (int i = lo + tid; i < hi; i += nthr) acc += b.wk[i];
+        for (int i = lo + tid; i < hi; i += nthr) acc += b.fin_wk[i];
         const double t = block_sum_fixed(acc, sm_d);
         if (tid == 0) a.part_d[3 * nblk + blk] = t;
         grid.sync();
@@ -1836,7 +1874,7 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
         __syncthreads();
         for (int t0 = lo; t0 < hi; t0 += nthr) {
             const int i = t0 + tid;
-            const double v = (i < hi) ? b.wk[i] : 0.;
+            const double v = (i < hi) ? b.fin_wk[i] : 0.;
             double inc = v;
             const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -1855,7 +1893,11 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
         }
     }
     grid.sync();
-    for (long long i = gtid; i < n; i += gsize) d.sorted_slot[i] = d.slot_of_label[b.perm[i]];
+    for (long long i = gtid; i < n; i += gsize) {
+        const int lab = b.fin_perm[i];
+        d.sorted_slot[i] = d.slot_of_label[lab];
+        a.sorted_label[i] = lab;
+    }
     if (gtid == 0) { sc.n_pick = n; sc.cum_total = d.cum[n - 1]; }
 }
 
