@@ -221,7 +221,12 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "launches": n_launch, "avg_launch_us": 1e3 * search_ms / n_launch, "algorithmic_bytes_per_launch": alg_bytes / n_launch,
-                "share_of_step": search_ms / dev_ms if dev_ms else None, "commit_share_of_step": commit_ms / dev_ms if dev_ms else None}
+                "share_of_step": search_ms / dev_ms if dev_ms else None, "commit_share_of_step": commit_ms / dev_ms if dev_ms else None,
+                "event_pipeline_share_of_step": sum(r["event_ms"] for r in reps) / dev_ms if dev_ms else None,
+                "cells_share_of_step": sum(r["cells_ms"] for r in reps) / dev_ms if dev_ms else None,
+                "avg_event_pipeline_us": 1e3 * sum(r["event_ms"] for r in reps) / max(1, sum(r["event_launches"] for r in reps)),
+                "avg_commit_us": 1e3 * commit_ms / max(1, sum(r["commit_launches"] for r in reps)),
+                "avg_cells_us": 1e3 * sum(r["cells_ms"] for r in reps) / max(1, sum(r["cells_launches"] for r in reps))}
     # the same kernel fed with one launch of ~3.5e5 independent searches (what an ensemble / wide speculation gives it)
     sw = sim.search_sweep(349000, repeats=3)
     sw_bytes = 36.0 * sw["pair_tests_bounding"] + 32.0 * (sw["pair_tests_sphere"] + sw["n_queries"]) + 48.0 * sw["n_queries"]

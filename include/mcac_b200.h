@@ -79,6 +79,8 @@ typedef struct mcac_run_report {
     double device_ms;                      /* CUDA-event time of the whole call on the handle's stream */
     double search_ms, commit_ms;           /* CUDA-event time spent in the K1 / commit+merge kernels (profile != 0) */
     int64_t search_launches, commit_launches;
+    double event_ms, cells_ms;             /* per-event pipeline (k_event) / Verlet cell rebuild (K2) */
+    int64_t event_launches, cells_launches;
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction

@@ -57,7 +57,9 @@ class RunReport(C.Structure):
                  "sorts", "kernel_launches", "n_aggregates", "n_spheres", "finished"]] + \
                [(n, C.c_double) for n in ["time", "box_length", "avg_npp", "max_time_step", "volume_fraction", "device_ms",
                                           "search_ms", "commit_ms"]] + \
-               [(n, C.c_int64) for n in ["search_launches", "commit_launches"]]
+               [(n, C.c_int64) for n in ["search_launches", "commit_launches"]] + \
+               [(n, C.c_double) for n in ["event_ms", "cells_ms"]] + \
+               [(n, C.c_int64) for n in ["event_launches", "cells_launches"]]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -174,7 +174,7 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     TRY(dev_alloc(h, &sb.cut, agg_cap + 1));
     TRY(dev_alloc(h, &sb.fin_perm, agg_cap + 1));
     TRY(dev_alloc(h, &sb.fin_wk, agg_cap + 1));
-    TRY(dev_alloc(h, &sb.active, 4));
+    TRY(dev_alloc(h, &sb.active, 16));
     TRY(dev_alloc(h, &h->scan64_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     TRY(dev_alloc(h, &h->cum_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     const size_t scan_n = (size_t)std::max<long long>(agg_cap, d.n_cells) + 2;
@@ -767,8 +767,8 @@ void prof_end(mcac_gpu *h) {
     cudaEventRecord(h->ev_pool.back(), h->stream);
 }
 void prof_collect(mcac_gpu *h, mcac_run_report *rep) {
-    double ms[2] = {0., 0.};
-    long long cnt[2] = {0, 0};
+    double ms[4] = {0., 0., 0., 0.};
+    long long cnt[4] = {0, 0, 0, 0};
     for (size_t i = 0; i < h->ev_kind.size(); i++) {
         float t = 0.f;
         cudaEventSynchronize(h->ev_pool[2 * i + 1]);
@@ -780,7 +780,10 @@ void prof_collect(mcac_gpu *h, mcac_run_report *rep) {
     }
     h->ev_pool.clear();
     h->ev_kind.clear();
-    if (rep) { rep->search_ms = ms[0]; rep->commit_ms = ms[1]; rep->search_launches = cnt[0]; rep->commit_launches = cnt[1]; }
+    if (rep) {
+        rep->search_ms = ms[0]; rep->commit_ms = ms[1]; rep->search_launches = cnt[0]; rep->commit_launches = cnt[1];
+        rep->event_ms = ms[2]; rep->cells_ms = ms[3]; rep->event_launches = cnt[2]; rep->cells_launches = cnt[3];
+    }
 }
 
 int search_launch(mcac_gpu *h, int nq) {
@@ -1243,7 +1246,9 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                 if ((rc = duplicate(h)) != E_OK) break;
                 dups++;
             }
+            prof_begin(h, 2);
             if ((rc = event_pipeline(h, need_refresh, need_refresh, true)) != E_OK) break;
+            prof_end(h);
             need_refresh = false;
             sorts++;
         }
@@ -1253,7 +1258,9 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if ((rc = ensure_rng(h, h->sc_host.rand_pos + 3LL * nq)) != E_OK) break;
         k_prepare_queries<<<div_up(nq, 128), 128, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist);
         h->launches++;
+        prof_begin(h, 3);
         if ((rc = build_cells(h)) != E_OK) break;
+        prof_end(h);
         prof_begin(h, 0);
         if ((rc = search_launch(h, nq)) != E_OK) break;
         prof_end(h);

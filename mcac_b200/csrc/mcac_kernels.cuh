@@ -795,14 +795,18 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         }
     }
     __syncthreads();
+    {   // pair-test counters of the committed steps (block reduction)
+        long long ps = 0, pb = 0;
+        for (int j = tid; j < done; j += nth) { ps += b.res[j].n_sphere_pairs; pb += b.res[j].n_bounding; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(kFull, ps, o); pb += __shfl_xor_sync(kFull, pb, o); }
+        if (lane == 0) { atomicAdd((unsigned long long *)&sc.pair_sphere, (unsigned long long)ps); atomicAdd((unsigned long long *)&sc.pair_bounding, (unsigned long long)pb); }
+    }
+    __syncthreads();
     if (tid == 0) {
         sc.steps_done = steps_before + done;
         sc.rand_pos = rand_before + 3LL * done;
         sc.searches += done;
-        long long ps = 0, pb = 0;
-        for (int j = 0; j < done; j++) { ps += b.res[j].n_sphere_pairs; pb += b.res[j].n_bounding; }
-        sc.pair_sphere += ps;
-        sc.pair_bounding += pb;
         if (reason == STOP_CONFLICT) sc.conflicts += 1;
         if (merged) {
             sc.n_iter_without_event = 0;
@@ -1667,7 +1671,6 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
     }
     if (gtid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
     grid.sync();
-    const int chunk = ((n + 1 + nblk - 1) / nblk + nthr - 1) / nthr * nthr;  // over n+1 entries so that pre[n] exists
     int lg = 0;
     while ((1LL << (lg + 1)) <= n) lg++;
     int depth = 2 * lg;
@@ -1689,15 +1692,34 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
         b.wk[f] = b.wk[pick]; b.perm[f] = b.perm[pick];
         b.wk[pick] = kf; b.perm[pick] = lf;
     };
-    if (active && gtid == 0) pivot_of(0, n);
+    // b.active: [0],[1] ping-pong "some segment still > 16", [2] fail, [4..7] ping-pong (min, max) of the span of active segments
+    if (gtid == 0) {
+        if (active) pivot_of(0, n);
+        b.active[4] = 0; b.active[5] = n; b.active[6] = 0x7fffffff; b.active[7] = 0;
+    }
     int level = 0;
-    bool fail = false;
+    bool fail = false, local = false;
+    // Work is restricted to the span [amin, amax) of the still-active segments (all-equal segments leave the loop
+    // analytically, so in tie-dominated tables the span halves every level).  Once the span fits kSortLocal elements,
+    // block 0 finishes the remaining levels alone with __syncthreads() instead of grid barriers.
+    constexpr int kSortLocal = 8192;
+    int eblk = blk, enblk = nblk;
+    long long etid = gtid, esize = gsize;
+    auto barrier = [&]() { if (local) __syncthreads(); else grid.sync(); };
+    grid.sync();  // first pivot + span in place
     while (active) {
         depth--;
-        grid.sync();  // pivots of this level are in place
+        const int amin = b.active[4 + 2 * (level & 1)], amax = b.active[5 + 2 * (level & 1)];
+        if (!local && amax - amin <= kSortLocal) {
+            local = true;
+            if (blk != 0) break;  // the other blocks wait at the barrier behind the loop
+            eblk = 0; enblk = 1; etid = tid; esize = nthr;
+        }
+        const int span = amax - amin + 1;  // + 1 so that pre[amax] exists
+        const int chunk = ((span + enblk - 1) / enblk + nthr - 1) / nthr * nthr;
         // ---- flags + chunk sums
         {
-            const int lo = blk * chunk, hi = min(n + 1, lo + chunk);
+            const int lo = amin + eblk * chunk, hi = min(amax + 1, lo + chunk);
             long long acc = 0;
             for (int i = lo + tid; i < hi; i += nthr) {
                 long long fl = 0;
@@ -1714,15 +1736,15 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
                 acc += fl;
             }
             const long long t = block_sum_ll(acc, sm_ll);
-            if (tid == 0) a.part_ll[blk] = t;
+            if (tid == 0) a.part_ll[eblk] = t;
         }
-        grid.sync();
-        // ---- exclusive scan of the packed flags
+        barrier();
+        // ---- exclusive scan of the packed flags over the span
         {
             long long base = 0;
-            for (int bb = tid; bb < blk; bb += nthr) base += a.part_ll[bb];
+            for (int bb = tid; bb < eblk; bb += nthr) base += a.part_ll[bb];
             base = block_sum_ll(base, sm_ll);
-            const int lo = blk * chunk, hi = min(n + 1, lo + chunk);
+            const int lo = amin + eblk * chunk, hi = min(amax + 1, lo + chunk);
             if (tid == 0) sh_carry = base;
             __syncthreads();
             for (int t0 = lo; t0 < hi; t0 += nthr) {
@@ -1736,13 +1758,13 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
                 __syncthreads();
             }
         }
-        grid.sync();
+        barrier();
         // ---- scatter the "not < pivot" (ascending) and "not > pivot" (descending) positions.
         // A segment whose elements ALL equal the pivot (whole tie classes: every monomer of a monodisperse run) needs no
         // more memory passes: introsort's moves on equal keys do not depend on the data (median-of-3 picks `mid`, the
         // Hoare partition mirrors [f+1, l-1], the cut falls at f+1+(m-1)/2, leaves do not move), so every element
         // computes its final position in registers and leaves the level loop.
-        for (long long i = gtid; i < n; i += gsize) {
+        for (long long i = amin + etid; i < amax; i += esize) {
             const int f = b.segf[i], l = b.segl[i];
             if (l - f <= kSortLeaf) continue;
             const int base = f + 1;
@@ -1779,9 +1801,9 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
             if (fl & 1LL) b.tmp_a[base + (int)((pi_ & 0xffffffffLL) - (p0 & 0xffffffffLL))] = (int)i;
             if (fl >> 32) b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = (int)i;
         }
-        grid.sync();
+        barrier();
         // ---- pairwise swaps + where the two scans stop
-        for (long long j = gtid; j < n; j += gsize) {
+        for (long long j = amin + etid; j < amax; j += esize) {
             const int f = b.segf[j], l = b.segl[j];
             if (l - f <= kSortLeaf || j <= f) continue;
             const int base = f + 1, k = (int)j - base;
@@ -1806,10 +1828,14 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
                 b.cut[f] = a_s < b_prev ? a_s : b_prev;
             }
         }
-        if (gtid == 0) b.active[(level + 1) & 1] = 0;
-        grid.sync();
+        if (etid == 0) {
+            b.active[(level + 1) & 1] = 0;
+            b.active[4 + 2 * ((level + 1) & 1)] = 0x7fffffff;
+            b.active[5 + 2 * ((level + 1) & 1)] = 0;
+        }
+        barrier();
         // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
-        for (long long i = gtid; i < n; i += gsize) {
+        for (long long i = amin + etid; i < amax; i += esize) {
             const int f = b.segf[i], l = b.segl[i];
             if (l - f <= kSortLeaf) continue;
             const int c = b.cut[f];
@@ -1818,16 +1844,22 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
             b.segf[i] = nf;
             b.segl[i] = nl;
             if (i == nf && nl - nf > kSortLeaf) {
-                if (depth > 0) { b.active[level & 1] = 1; pivot_of(nf, nl); }
-                else b.active[2] = 1;  // would enter introsort's heap-sort branch
+                if (depth > 0) {
+                    b.active[level & 1] = 1;
+                    atomicMin(&b.active[4 + 2 * ((level + 1) & 1)], nf);
+                    atomicMax(&b.active[5 + 2 * ((level + 1) & 1)], nl);
+                    pivot_of(nf, nl);
+                } else b.active[2] = 1;  // would enter introsort's heap-sort branch
             }
         }
-        grid.sync();
+        barrier();
         active = b.active[level & 1] != 0;
         fail = b.active[2] != 0;
         if (fail) break;
         level++;
     }
+    grid.sync();  // blocks that left the loop early wait here for block 0's local levels
+    fail = b.active[2] != 0;
     if (fail) {  // the host falls back to libstdc++'s std::sort for this call
         if (gtid == 0) sc.b_need = 99;
         return;
