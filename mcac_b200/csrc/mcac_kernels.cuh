@@ -700,27 +700,28 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     }
     for (int j = tid; j < nq; j += nth)
         if (sh_contact[j]) atomicMin(&s_contact, j);
-    // ---- conflicts with earlier movers of the batch
-    for (int j = tid; j < nq; j += nth) {
-        const int sj = sh_slot[j];
-        const double4 aj = sh_posr[j];
-        const double dj = sh_dist[j];
-        const double djx = sh_dir[3 * j], djy = sh_dir[3 * j + 1], djz = sh_dir[3 * j + 2];
-        bool conflict = false;
-        for (int i = 0; i < j && !conflict; i++) {
-            const int si = sh_slot[i];
-            if (si == sj) { conflict = true; break; }
-            const double4 ai = sh_posr[i];
-            const double di = sh_dist[i];
+    // ---- conflicts with earlier movers of the batch: all (j, i<j) pairs, flattened over the block
+    for (int p = tid; p < nq * nq; p += nth) {
+        const int j = p / nq, i = p - j * nq;
+        if (i >= j || j >= s_conf) continue;  // benign race on s_conf: only ever shrinks the work
+        const int sj = sh_slot[j], si = sh_slot[i];
+        bool conflict = (si == sj);
+        if (!conflict) {
+            const double4 aj = sh_posr[j], ai = sh_posr[i];
+            const double dj = sh_dist[j], di = sh_dist[i];
             const double guard = (dj + di + aj.w + ai.w) * (1. + 1e-9) + 1e-9 * box;
-            const double ex = fabs(periodic_distance(aj.x - ai.x, box)), ey = fabs(periodic_distance(aj.y - ai.y, box)),
-                         ez = fabs(periodic_distance(aj.z - ai.z, box));
-            if (ex > guard || ey > guard || ez > guard) continue;
-            const double before = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, ai.x, ai.y, ai.z, ai.w, djx, djy, djz, dj, box);
-            const double nx = periodic_position(ai.x + sh_dir[3 * i] * di, box), ny = periodic_position(ai.y + sh_dir[3 * i + 1] * di, box),
-                         nz = periodic_position(ai.z + sh_dir[3 * i + 2] * di, box);
-            const double after = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, nx, ny, nz, ai.w, djx, djy, djz, dj, box);
-            if (before < dj || after < dj) conflict = true;
+            // centres are wrapped into [0, box): minimum-image separation per axis, branch-free
+            double ex = fabs(aj.x - ai.x), ey = fabs(aj.y - ai.y), ez = fabs(aj.z - ai.z);
+            ex = fmin(ex, box - ex); ey = fmin(ey, box - ey); ez = fmin(ez, box - ez);
+            if (ex <= guard && ey <= guard && ez <= guard) {
+                // exact: was / will `i` be an eligible suspect of j (bounding-sphere sweep, strict <)?
+                const double djx = sh_dir[3 * j], djy = sh_dir[3 * j + 1], djz = sh_dir[3 * j + 2];
+                const double before = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, ai.x, ai.y, ai.z, ai.w, djx, djy, djz, dj, box);
+                const double nx = periodic_position(ai.x + sh_dir[3 * i] * di, box), ny = periodic_position(ai.y + sh_dir[3 * i + 1] * di, box),
+                             nz = periodic_position(ai.z + sh_dir[3 * i + 2] * di, box);
+                const double after = pair_contact_distance(aj.x, aj.y, aj.z, aj.w, nx, ny, nz, ai.w, djx, djy, djz, dj, box);
+                conflict = before < dj || after < dj;
+            }
         }
         if (conflict) atomicMin(&s_conf, j);
     }
