@@ -39,6 +39,7 @@ typedef struct mcac_params {
     double u_sg;                    /* surface growth velocity dr/dt                                */
     double rp_min_oxid;
     double flux_nucleation, nucleation_accum, box_volume;
+    double mean_diameter_nucleation, dispersion_diameter_nucleation; /* law of the nucleated monomers [nm] */
     double physical_time_limit;     /* limits (PhysicalModel::finished, physical_model.cpp:288-337) */
     int64_t number_of_aggregates_limit;
     int64_t n_iter_without_event_limit;
@@ -49,6 +50,7 @@ typedef struct mcac_params {
     int32_t pick_method, volsurf_method;
     int32_t with_collisions, with_surface_reactions, individual_surf_reactions, with_domain_duplication;
     int32_t with_maturity, with_potentials, with_external_potentials, with_nucleation, with_dynamic_random_charges;
+    int32_t normal_initialisation;  /* monomeres_initialisation_type == NORMAL_INITIALISATION */
     int32_t sort_order;             /* MCAC_ORDER_LIBSTDCXX replays std::sort's tie order */
     uint32_t random_seed;           /* srand() argument (src/tools/tools.cpp:41-50)                 */
 } mcac_params;
@@ -99,6 +101,11 @@ const char *mcac_gpu_last_error(const mcac_gpu *h);      /* BaseException::what(
 /* init_random(seed) (src/tools/tools.cpp:41-50) followed by `consumed` draws already taken by the host-side
  * initial placement, so the device stream continues exactly where the reference's would */
 int mcac_gpu_set_rng(mcac_gpu *h, uint32_t seed, int64_t consumed);
+
+/* Interpotential(file) (src/physical_model/physical_model_interpotential.cpp:46-121): energy-barrier / well tables indexed
+ * [charge1][charge2][dp1][dp2], already parsed by the host layer */
+int mcac_gpu_set_interpotential(mcac_gpu *h, int32_t n_dp1, int32_t n_dp2, int32_t n_charge, const int32_t *val_charge,
+                                const double *val_dp1, const double *val_dp2, const double *e_barr, const double *e_well);
 
 /* --- state (host SoA <-> HBM) ---------------------------------------------------------------- */
 /* Sphere fields in SpheresFields order, field-major: X,Y,Z,R,VOLUME,SURFACE,RX,RY,RZ (constants.hpp:34-45);

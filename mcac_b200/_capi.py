@@ -26,14 +26,16 @@ ERROR_NAMES = ["NO_ERROR", "UNKNOWN_ERROR", "IO_ERROR", "VERLET_ERROR", "INPUT_E
 class Params(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ["box_length", "time", "temperature", "pressure", "viscosity", "gaz_mean_free_path", "density", "fractal_dimension",
-                 "u_sg", "rp_min_oxid", "flux_nucleation", "nucleation_accum", "box_volume", "physical_time_limit"]] + \
+                 "u_sg", "rp_min_oxid", "flux_nucleation", "nucleation_accum", "box_volume", "mean_diameter_nucleation",
+                 "dispersion_diameter_nucleation", "physical_time_limit"]] + \
                [(n, C.c_int64) for n in
                 ["number_of_aggregates_limit", "n_iter_without_event_limit", "mean_monomere_per_aggregate_limit", "n_monomeres",
                  "full_aggregate_update_frequency"]] + \
                [(n, C.c_int32) for n in
                 ["n_verlet_divisions", "pick_method", "volsurf_method", "with_collisions", "with_surface_reactions",
                  "individual_surf_reactions", "with_domain_duplication", "with_maturity", "with_potentials",
-                 "with_external_potentials", "with_nucleation", "with_dynamic_random_charges", "sort_order"]] + \
+                 "with_external_potentials", "with_nucleation", "with_dynamic_random_charges", "normal_initialisation",
+                 "sort_order"]] + \
                [("random_seed", C.c_uint32)]
 
 
@@ -86,7 +88,7 @@ EXPORTS = [
     "mcac_gpu_grow", "mcac_gpu_update", "mcac_gpu_refresh", "mcac_gpu_sort_time_steps", "mcac_gpu_get_pick_table",
     "mcac_gpu_pick_random", "mcac_gpu_pick_last", "mcac_gpu_duplicate", "mcac_gpu_rand", "mcac_gpu_run",
     "mcac_gpu_morphology_stats", "mcac_gpu_morphology_stats_device", "mcac_gpu_stream", "mcac_gpu_search_sweep",
-    "mcac_gpu_set_profile",
+    "mcac_gpu_set_profile", "mcac_gpu_set_interpotential",
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_state", "mcac_sim_create",
 ]
@@ -126,6 +128,7 @@ def lib() -> C.CDLL:
         L.mcac_gpu_morphology_stats_device.argtypes = [vp, C.c_int32, dbl, vp]
         L.mcac_gpu_search_sweep.argtypes = [vp, i64, C.c_int32, C.POINTER(SweepReport)]
         L.mcac_gpu_set_profile.argtypes = [vp, C.c_int32]
+        L.mcac_gpu_set_interpotential.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L.mcac_gpu_stream.argtypes = [vp]
         L.mcac_gpu_stream.restype = vp
         L.mcac_host_last_error.restype = C.c_char_p

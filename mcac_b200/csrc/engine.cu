@@ -549,6 +549,11 @@ void fill_devstate_params(mcac_gpu *h) {
     d.n_agg_limit = p.number_of_aggregates_limit;
     d.npp_limit = p.mean_monomere_per_aggregate_limit;
     d.time_limit = p.physical_time_limit;
+    d.with_external_potentials = p.with_external_potentials;
+    d.nucl_mean_diameter = p.mean_diameter_nucleation;
+    d.nucl_dispersion_diameter = p.dispersion_diameter_nucleation;
+    d.flux_nucleation = p.flux_nucleation;
+    d.init_mode_normal = p.normal_initialisation;
 }
 
 int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_step, bool keep_scalars) {
@@ -557,7 +562,8 @@ int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_st
     fill_devstate_params(h);
     const long long n_agg = s.n_agg, n_sph = s.n_sph;
     if (n_agg <= 0 || n_sph <= 0) { h->err = "upload_state: empty state"; return E_INPUT; }
-    TRY(alloc_state(h, n_agg, 3 * n_sph + 1024));
+    const long long headroom = h->prm.with_nucleation ? std::max<long long>(n_agg, 4096) : 0;  // slots for nucleated monomers
+    TRY(alloc_state(h, n_agg + headroom, 3 * (n_sph + headroom) + 1024));
     std::vector<double4> posr((size_t)n_sph), relv((size_t)n_sph), aposr((size_t)n_agg);
     std::vector<double> surf((size_t)n_sph), veff((size_t)n_sph), seff((size_t)n_sph), dcen((size_t)n_sph);
     std::vector<int> sid((size_t)n_sph), scharge((size_t)n_sph), slot_of_id((size_t)n_sph);
@@ -874,6 +880,27 @@ int mcac_gpu_set_rng(mcac_gpu *h, uint32_t seed, int64_t consumed) {
     return E_OK;
 }
 
+int mcac_gpu_set_interpotential(mcac_gpu *h, int32_t n1, int32_t n2, int32_t nq, const int32_t *val_charge, const double *val_dp1,
+                                const double *val_dp2, const double *e_barr, const double *e_well) {
+    CK(cudaSetDevice(h->device));
+    DevState &d = h->d;
+    const size_t nt = (size_t)nq * nq * n1 * n2;
+    int *c; double *a, *b, *eb, *ew;
+    TRY(dev_alloc_persistent(h, &c, (size_t)nq));
+    TRY(dev_alloc_persistent(h, &a, (size_t)n1));
+    TRY(dev_alloc_persistent(h, &b, (size_t)n2));
+    TRY(dev_alloc_persistent(h, &eb, nt));
+    TRY(dev_alloc_persistent(h, &ew, nt));
+    CK(cudaMemcpy(c, val_charge, sizeof(int) * nq, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(a, val_dp1, sizeof(double) * n1, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b, val_dp2, sizeof(double) * n2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(eb, e_barr, sizeof(double) * nt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ew, e_well, sizeof(double) * nt, cudaMemcpyHostToDevice));
+    d.ip_n1 = n1; d.ip_n2 = n2; d.ip_nq = nq;
+    d.ip_charge = c; d.ip_dp1 = a; d.ip_dp2 = b; d.ip_ebar = eb; d.ip_ewell = ew;
+    return E_OK;
+}
+
 int mcac_gpu_upload_state(mcac_gpu *h, int64_t n_sph, int64_t n_agg, const double *sphere_fields, const int64_t *sphere_charge,
                           const double *agg_fields, const int64_t *agg_charge, const int64_t *agg_cells, const int64_t *offsets,
                           const int64_t *members, const double *per_member, double maxradius, double max_time_step) {
@@ -1153,12 +1180,13 @@ int mcac_gpu_rand(mcac_gpu *h, int64_t n, int32_t *out) {
 int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record *records, int64_t n_records, mcac_run_report *report) {
     CK(cudaSetDevice(h->device));
     if (!h->uploaded) { h->err = "run before upload_state"; return E_INPUT; }
-    if (h->prm.with_potentials || h->prm.with_nucleation) {
-        h->err = "mcac_gpu_run: interaction potentials / nucleation are not on the device-resident loop yet";
+    if (h->prm.with_external_potentials && h->prm.with_potentials && !h->d.ip_ebar) {
+        h->err = "mcac_gpu_run: with_external_potentials needs mcac_gpu_set_interpotential first";
         return E_INPUT;
     }
-    // speculative batches need a pick sequence that is fixed between events: random pick, no per-step growth
-    const bool speculative = h->prm.pick_method == MCAC_PICK_RANDOM && h->prm.with_collisions && !h->prm.with_surface_reactions;
+    // speculative batches need a pick sequence that is fixed between events: random pick, no per-step growth / redraws / nucleation
+    const bool speculative = h->prm.pick_method == MCAC_PICK_RANDOM && h->prm.with_collisions && !h->prm.with_surface_reactions &&
+                             !h->prm.with_potentials && !h->prm.with_nucleation;
     const int B = !speculative ? 1 : (batch > 0 ? std::min<int>(batch, kMaxBatch) : 256);
     TRY(pull_scalars(h));
     const Scalars at_start = h->sc_host;
@@ -1192,8 +1220,22 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if ((rc = refresh_labels(h)) != E_OK) break;
         if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph)
             if ((rc = compact_pool(h)) != E_OK) break;
-        const int draws = pick_last ? 2 : 3;
-        if ((rc = ensure_rng(h, h->sc_host.rand_pos + draws)) != E_OK) break;
+        // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up
+        if (p.with_nucleation && (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64)) {
+            HostState hs;
+            if ((rc = download(h, hs)) != E_OK) break;
+            const Scalars keep = h->sc_host;
+            free_all(h);
+            h->uploaded = false;
+            if ((rc = upload(h, hs, keep.maxradius, keep.max_time_step, false)) != E_OK) break;
+            Scalars &sc = h->sc_host;
+            const int n_slots = sc.n_agg_slots, pool = sc.pool_top;
+            sc = keep;
+            sc.n_agg_slots = n_slots; sc.pool_top = pool;
+            if ((rc = push_scalars(h)) != E_OK) break;
+        }
+        if ((rc = ensure_rng(h, h->sc_host.rand_pos + 8192)) != E_OK) break;
+        int draws = pick_last ? 2 : 3, n_try = 1;
         if (pick_last) {
             k_pick_last<<<1, 1024, 0, h->stream>>>(h->d, h->q_slot);
             k_prepare_direction<<<1, 32, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, 0);
@@ -1206,12 +1248,29 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             prof_begin(h, 0);
             if ((rc = search_launch(h, 1)) != E_OK) break;
             prof_end(h);
+            // orientation loop of calcul.cpp:119-141: a non-sticking contact redraws the direction (n_try++)
+            while (p.with_potentials) {
+                k_check_regime<<<1, 32, 0, h->stream>>>(h->d, h->q_res, h->q_dist, draws);
+                h->launches++;
+                if ((rc = pull_scalars(h)) != E_OK) break;
+                if (h->sc_host.error) break;
+                draws += h->sc_host.p_regime_draws;
+                if (h->sc_host.p_regime == 0) break;
+                n_try++;
+                if (draws + 8 > 8192) { h->err = "orientation loop: too many redraws"; rc = E_UNKNOWN; break; }
+                k_prepare_direction<<<1, 32, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, draws);
+                draws += 2;
+                h->launches++;
+                if ((rc = search_launch(h, 1)) != E_OK) break;
+            }
+            if (rc != E_OK) break;
+            if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
         }
         StepArgs sa;
         sa.q_slot = h->q_slot; sa.q_dir = h->q_dir; sa.q_dist = h->q_dist; sa.res = h->q_res;
         sa.rec = (records && n_records > 0) ? h->rec_dev : nullptr;
         sa.rec_cap = n_records; sa.rec_index = steps;
-        sa.pick_last = pick_last; sa.with_collisions = p.with_collisions; sa.n_try = 1; sa.draws = draws;
+        sa.pick_last = pick_last; sa.with_collisions = p.with_collisions; sa.n_try = n_try; sa.draws = draws;
         prof_begin(h, 1);
         k_step_move<<<1, kCommitThreads, 0, h->stream>>>(h->d, sa);
         if (growth) k_grow_pending<<<div_up(p.individual_surf_reactions ? h->sc_host.n_sph : h->sc_host.pool_top, 256), 256, 0, h->stream>>>(h->d, p.individual_surf_reactions);
@@ -1223,6 +1282,14 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             k_update_step<<<div_up(h->sc_host.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
             h->launches++;
         }
+        if (p.with_nucleation) {  // calcul.cpp:208-220
+            k_nucleate<<<1, kCommitThreads, 0, h->stream>>>(h->d, 0., 1);
+            h->launches++;
+        } else {
+            CK(cudaMemsetAsync(&h->d.sc->n_nucleated, 0, sizeof(int), h->stream));
+        }
+        k_step_event<<<1, 32, 0, h->stream>>>(h->d);
+        h->launches++;
         {   // refresh() after an event, PhysicalModel::update after an event or in growth mode (calcul.cpp:232-234, 272-277)
             const int nb = std::min(1024, std::max(1, div_up(h->sc_host.n_agg_slots, kReduceThreads)));
             k_refresh_partials<<<nb, kReduceThreads, 0, h->stream>>>(h->d, h->partials);
@@ -1237,6 +1304,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
         steps += 1;
         if (h->sc_host.b_merged) { h->pick_valid = false; h->labels_valid = false; }
+        if (h->sc_host.n_nucleated > 0) h->pick_valid = false;
     }
     while (speculative && steps < max_steps) {
         if (finished(h)) { fin = true; break; }

@@ -34,6 +34,8 @@ struct Scalars {
     // general step: contact found by the search, merged after growth (calcul.cpp:174-181)
     int p_contact, p_ms, p_os, p_magg, p_oagg, p_slot;
     double p_dt, p_dt_indiv;
+    int p_regime, p_regime_draws;  // check_InterPotentialRegime outcome of the last try (0 sticking) and draws it consumed
+    int n_nucleated, pad_n;
 };
 enum StopReason { STOP_NONE = 0, STOP_CONTACT = 1, STOP_CONFLICT = 2, STOP_FINISHED = 3, STOP_BATCH_END = 4 };
 
@@ -79,6 +81,13 @@ struct DevState {
     int volsurf_method, pick_method, with_collisions;
     long long n_iter_limit, n_agg_limit, npp_limit;
     double time_limit;
+    // interaction potentials (src/physical_model/physical_model_interpotential.cpp): table [q1][q2][dp1][dp2]
+    int with_external_potentials, ip_n1, ip_n2, ip_nq;
+    const int *ip_charge;
+    const double *ip_dp1, *ip_dp2, *ip_ebar, *ip_ewell;
+    // nucleation (physical_model.cpp:499-502, 557-578): diameter law of new monomers
+    double nucl_mean_diameter, nucl_dispersion_diameter, flux_nucleation;
+    int init_mode_normal, pad_i;
 };
 
 }  // namespace mcacb

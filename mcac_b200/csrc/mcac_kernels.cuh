@@ -928,6 +928,149 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepAr
         sc.rand_pos += a.draws;
     }
 }
+// AggregatList::check_InterPotentialRegime (aggregat_list.cpp:313-366) for the contact found by the last search:
+// sticking / repulsion / bouncing decided with <= 2 draws taken at stream offset `draw_offset` of this step.
+__global__ void k_check_regime(DevState d, const SearchResult *res, const double *q_dist, long long draw_offset) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Scalars &sc = *d.sc;
+    sc.p_regime = 0;
+    sc.p_regime_draws = 0;
+    const SearchResult r = res[0];
+    if (!(r.distance <= q_dist[0])) return;  // no contact: the move is effective
+    const double d_moving = 2.0 * d.s_posr[r.moving_slot].w, d_other = 2.0 * d.s_posr[r.other_slot].w;
+    double p_stick = 1.0, p_coll = 1.0;
+    if (d.with_external_potentials) {
+        // Interpotential::get_Ebar_Ewell (physical_model_interpotential.cpp:144-197)
+        const int q1 = 0, q2 = 0;  // aggregate charges: electric charges are not built (with_electric_charges = false)
+        int i1 = 0, j1 = 0, k = -1, l = -1;
+        while (i1 < d.ip_n1 && !(d_moving < d.ip_dp1[i1])) i1++;  // std::upper_bound
+        while (j1 < d.ip_n2 && !(d_other < d.ip_dp2[j1])) j1++;
+        for (int c = 0; c < d.ip_nq; c++) { if (d.ip_charge[c] == q1 && k < 0) k = c; if (d.ip_charge[c] == q2 && l < 0) l = c; }
+        if (i1 == 0 || i1 == d.ip_n1 || j1 == 0 || j1 == d.ip_n2 || k < 0 || l < 0) { sc.error = 11; return; }  // InterPotentialError
+        const int i0 = i1 - 1, j0 = j1 - 1;
+        const double a = (d_moving - d.ip_dp1[i0]) / (d.ip_dp1[i1] - d.ip_dp1[i0]);
+        const double b = (d_other - d.ip_dp2[j0]) / (d.ip_dp2[j1] - d.ip_dp2[j0]);
+        auto at = [&](int ii, int jj) { return (((size_t)k * d.ip_nq + l) * d.ip_n1 + ii) * d.ip_n2 + jj; };
+        const double e_bar = interpolate_2d(d.ip_ebar[at(i0, j0)], d.ip_ebar[at(i0, j1)], d.ip_ebar[at(i1, j0)], d.ip_ebar[at(i1, j1)], a, b);
+        const double e_well = interpolate_2d(d.ip_ewell[at(i0, j0)], d.ip_ewell[at(i0, j1)], d.ip_ewell[at(i1, j0)], d.ip_ewell[at(i1, j1)], a, b);
+        const double e_stick = fabs(e_well) + fabs(e_bar);
+        p_stick = erf(sqrt(e_stick)) - sqrt(e_stick) * exp(-e_stick);
+        p_coll = 1.0 - erf(sqrt(e_bar)) + sqrt(e_bar) * exp(-e_bar);
+    } else {  // Hou et al., J. Aerosol Sci. (2020) 105478
+        const double kbt = kBoltzmann * d.gas.temperature;
+        double dd = d_moving * d_other / (d_moving + d_other);
+        dd = dd * (1e+09);
+        const double e_well = (-6.6891e-23) * pow(dd, 3.) + (1.1244e-21) * (dd * dd) + (1.1394e-20) * dd - 5.5373e-21;
+        p_stick = 1.0 - (1.0 + fabs(e_well) / kbt) * exp(-fabs(e_well) / kbt);
+    }
+    const long long p = sc.rand_pos + draw_offset - d.rng_buf_base;
+    sc.p_regime_draws = 1;
+    if (uniform_from_rand(d.rng_buf[p]) > p_coll) { sc.p_regime = 1; return; }  // REPULSION
+    sc.p_regime_draws = 2;
+    if (uniform_from_rand(d.rng_buf[p + 1]) > p_stick) { sc.p_regime = 2; return; }  // BOUNCING
+}
+
+// AggregatList::add(n) for nucleation (aggregat_list.cpp:82-99 -> Aggregate::init(nucleation = true), aggregat.cpp:162-229):
+// each new monomer draws its diameter (1 draw) then positions (3 draws per try) until it overlaps no existing aggregate
+// (bounding sphere first, then member spheres: aggregat_distance.cpp:45-58), becomes the last aggregate / last sphere and gets
+// Aggregate::update().  Single CTA; the free-space test of a try is spread over the threads.
+__global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double deltatemps_unused, int use_pending_dt) {
+    __shared__ double scratch[kUpdateScratch];
+    __shared__ double cand[4];
+    __shared__ int s_hit, s_stop, s_count;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    Scalars &sc = *d.sc;
+    const double box = sc.box_length;
+    if (tid == 0) {
+        // PhysicalModel::nucleation(dt) (physical_model.cpp:499-502) + the accumulator test of calcul.cpp:211-216
+        const double dt = use_pending_dt ? sc.p_dt : deltatemps_unused;
+        sc.nucleation_accum += d.flux_nucleation * sc.box_volume * dt;
+        int n_new = 0;
+        if (sc.nucleation_accum > 1.0) {
+            n_new = static_cast<int>(floor(sc.nucleation_accum));
+            sc.nucleation_accum -= static_cast<double>(n_new);
+        }
+        s_count = n_new;
+        sc.n_nucleated = n_new;
+        s_stop = 0;
+    }
+    __syncthreads();
+    const int n_new = s_count;
+    for (int m = 0; m < n_new; m++) {
+        if (tid == 0) {
+            const long long p = sc.rand_pos - d.rng_buf_base;
+            if (p + 1 >= d.rng_buf_n) { sc.error = 1; s_stop = 1; }
+            else {
+                const double diameter = diameter_from_draw(uniform_from_rand(d.rng_buf[p]), d.nucl_mean_diameter, d.nucl_dispersion_diameter, d.init_mode_normal);
+                cand[3] = diameter * 0.5;
+                sc.rand_pos += 1;
+            }
+        }
+        __syncthreads();
+        if (s_stop) return;
+        const int max_tries = sc.n_sph - m + n_new;  // `n_try < external_storage->spheres.size()`: the list already holds the n new spheres
+        bool placed = false;
+        for (int attempt = 0; attempt < max_tries && !placed; attempt++) {
+            if (tid == 0) {
+                const long long p = sc.rand_pos - d.rng_buf_base;
+                if (p + 3 >= d.rng_buf_n) { sc.error = 1; s_stop = 1; }
+                else {
+                    cand[0] = uniform_from_rand(d.rng_buf[p]) * box;
+                    cand[1] = uniform_from_rand(d.rng_buf[p + 1]) * box;
+                    cand[2] = uniform_from_rand(d.rng_buf[p + 2]) * box;
+                    sc.rand_pos += 3;
+                }
+                s_hit = 0;
+            }
+            __syncthreads();
+            if (s_stop) return;
+            const double px = cand[0], py = cand[1], pz = cand[2], pr = cand[3];
+            for (int s = tid; s < sc.n_agg_slots; s += nth) {
+                if (!d.a_alive[s]) continue;
+                const double4 a = d.a_posr[s];
+                if (!spheres_in_contact(px, py, pz, pr, a.x, a.y, a.z, a.w, box)) continue;
+                const int off = d.a_off[s], n = d.a_n[s];
+                for (int k = 0; k < n; k++) {
+                    const double4 q = d.s_posr[off + k];
+                    if (spheres_in_contact(px, py, pz, pr, q.x, q.y, q.z, q.w, box)) { s_hit = 1; break; }
+                }
+            }
+            __syncthreads();
+            placed = (s_hit == 0);
+            __syncthreads();
+        }
+        if (!placed) { if (tid == 0) sc.error = 6; return; }  // TooDenseError
+        const int slot = sc.n_agg_slots, sp = sc.pool_top, id = sc.n_sph;
+        if (slot >= d.agg_cap || sp >= d.sph_cap || id >= d.sph_cap) { if (tid == 0) sc.error = 1; return; }
+        if (tid == 0) {
+            const double r = cand[3];
+            d.s_posr[sp] = make_double4(cand[0], cand[1], cand[2], r);
+            d.s_relv[sp] = make_double4(0., 0., 0., volume_factor() * pow(r, 3.));
+            d.s_surf[sp] = surface_factor() * (r * r);
+            d.s_id[sp] = id;
+            d.s_charge[sp] = 0;
+            d.slot_of_id[id] = sp;
+            d.a_n[slot] = 1;
+            d.a_off[slot] = sp;
+            d.a_alpha[slot] = 1.0;
+            d.a_alive[slot] = 1;
+            d.a_charge[slot] = 0;
+            d.a_ptime[slot] = sc.time;
+            d.a_ch[slot] = 0.;
+            d.a_posr[slot] = make_double4(cand[0], cand[1], cand[2], 0.);
+            d.label_of_slot[slot] = sc.n_agg;
+            d.slot_of_label[sc.n_agg] = slot;
+            sc.n_agg_slots = slot + 1;
+            sc.pool_top = sp + 1;
+            sc.n_sph = id + 1;
+            sc.n_agg += 1;
+        }
+        __syncthreads();
+        agg_update<true>(d, slot, true, tid, nth, scratch, box);
+        __syncthreads();
+    }
+}
+
 // the deferred AggregatList::merge of the step (calcul.cpp:174-181) + event bookkeeping (:222-229)
 __global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
     __shared__ double scratch[kUpdateScratch];
@@ -936,12 +1079,18 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_
     if (sc.p_contact) merged = agg_merge(d, sc.p_ms, sc.p_os, sc.p_magg, sc.p_oagg, scratch, sc.box_length);
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (merged) { sc.n_iter_without_event = 0; sc.total_events += 1; sc.event = 1; }
-        else { sc.n_iter_without_event += 1; sc.event = 0; }
         sc.b_merged = merged;
         sc.b_committed = 1;
         if (rec && rec_index < rec_cap) rec[rec_index].merged = merged;
     }
+}
+// event bookkeeping at the end of a general step (calcul.cpp:222-229): event = merge || nucleation
+__global__ void k_step_event(DevState d) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Scalars &sc = *d.sc;
+    const bool ev = sc.b_merged || sc.n_nucleated > 0;
+    if (ev) { sc.n_iter_without_event = 0; sc.total_events += 1; sc.event = 1; }
+    else { sc.n_iter_without_event += 1; sc.event = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -264,6 +264,33 @@ MCAC_HD double surface_alpha_correction(double cn, double c10, double min_cn, do
     return (alpha < extreme) ? extreme : alpha;
 }
 
+// inverfc / inverf of src/tools/tools.cpp:56-77 (rational start + two Halley steps), used by random_diameter
+MCAC_HD double inverse_erfc(double p) {
+    if (p >= 2.) return -100.;
+    if (p <= 0.0) return 100.;
+    const double pp = (p < 1.0) ? p : 2. - p;
+    const double t = sqrt(-2. * log(pp / 2.));
+    double x = -0.70711 * ((2.30753 + t * 0.27061) / (1. + t * (0.99229 + t * 0.04481)) - t);
+    for (int it = 0; it < 2; it++) {
+        const double err = erfc(x) - pp;
+        x += err / (1.12837916709551257 * exp(-(x * x)) - x * err);
+    }
+    return (p < 1.0 ? x : -x);
+}
+// PhysicalModel::random_diameter (physical_model.cpp:557-578) on the uniform draw; metres
+MCAC_HD double diameter_from_draw(double u, double mean, double dispersion, int normal_law) {
+    double diameter;
+    if (normal_law) diameter = mean + sqrt(2.) * dispersion * inverse_erfc(1. - (2. * u - 1.0));
+    else diameter = mean * pow(dispersion, sqrt(2.) * inverse_erfc(1. - (2. * u - 1.0)));
+    if (diameter <= 0) diameter = mean;
+    return diameter * 1E-9;
+}
+// interpolate_2d, src/tools/tools.cpp:162-175
+MCAC_HD double interpolate_2d(double f11, double f12, double f21, double f22, double dx, double dy) {
+    const double df_x = f21 - f11, df_y = f12 - f11, df_xy = (f11 + f22) - (f21 + f12);
+    return df_x * dx + df_y * dy + df_xy * dx * dy + f11;
+}
+
 // --------------------------------------------------------------------------------------------------
 // glibc rand() TYPE_3 additive-feedback stream: r[i] = r[i-31] + r[i-3] (mod 2^32),
 // output r[i] >> 1.  State = the last 31 words in a ring.  Reproduced so that a trajectory can be replayed

@@ -220,6 +220,9 @@ mcac_params PhysicalModel::to_params() const {
     p.flux_nucleation = flux_nucleation;
     p.nucleation_accum = nucleation_accum;
     p.box_volume = box_volume;
+    p.mean_diameter_nucleation = mean_diameter_nucleation;
+    p.dispersion_diameter_nucleation = dispersion_diameter_nucleation;
+    p.normal_initialisation = monomeres_initialisation_type == NORMAL_INITIALISATION ? 1 : 0;
     p.physical_time_limit = physical_time_limit;
     p.number_of_aggregates_limit = static_cast<int64_t>(number_of_aggregates_limit);
     p.n_iter_without_event_limit = n_iter_without_event_limit;

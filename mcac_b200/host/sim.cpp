@@ -1,8 +1,10 @@
 // mcac_b200 host layer — C shims over the host mirror (PhysicalModel + initial placement) so that tests, bench.py
 // and foreign-language hosts can build a realization from an .ini text and hand it to the device engine.
 #include <cstring>
+#include <fstream>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #include "../../include/mcac_b200.h"
 #include "physical_model.hpp"
@@ -73,6 +75,32 @@ int mcac_host_model_state(const mcac_host_model *m, double *sphere_fields, doubl
     if (rand_consumed) *rand_consumed = s.rand_consumed;
     return 0;
 }
+// Interpotential(file) of the reference (physical_model_interpotential.cpp:46-121): 4 header values, the charge / dp1 / dp2 axes,
+// then (E_barr, E_well) pairs ordered dp1-major, dp2, charge1, charge2; handed to the device as [q1][q2][dp1][dp2] tables.
+static int load_interpotential(mcac_gpu *h, const std::string &file) {
+    std::ifstream f(file);
+    if (!f) { g_host_err = " Interpotential file does not exist: " + file; return mcac::IO_ERROR; }
+    double t, d;
+    f >> t;
+    f >> d; const int n1 = static_cast<int>(d);
+    f >> d; const int n2 = static_cast<int>(d);
+    f >> d; const int nq = static_cast<int>(d);
+    std::vector<int32_t> q((size_t)nq);
+    std::vector<double> a((size_t)n1), b((size_t)n2), eb((size_t)nq * nq * n1 * n2), ew(eb.size());
+    for (int i = 0; i < nq; i++) { f >> d; q[(size_t)i] = static_cast<int>(d); }
+    for (int i = 0; i < n1; i++) f >> a[(size_t)i];
+    for (int i = 0; i < n2; i++) f >> b[(size_t)i];
+    for (int i = 0; i < n1; i++)
+        for (int j = 0; j < n2; j++)
+            for (int k = 0; k < nq; k++)
+                for (int l = 0; l < nq; l++) {
+                    const size_t at = (((size_t)k * nq + l) * n1 + i) * n2 + j;
+                    f >> eb[at] >> ew[at];
+                }
+    if (!f) { g_host_err = "Interpotential file is truncated: " + file; return mcac::IO_ERROR; }
+    return mcac_gpu_set_interpotential(h, n1, n2, nq, q.data(), a.data(), b.data(), eb.data(), ew.data());
+}
+
 // PhysicalModel(ini) + AggregatList(&physicalmodel) of the reference's main() (src/main.cpp:26-56): placement on the host,
 // state uploaded to HBM, RNG stream continued on the device.
 int mcac_sim_create(const char *ini_text, int device, mcac_gpu **out) {
@@ -88,6 +116,10 @@ int mcac_sim_create(const char *ini_text, int device, mcac_gpu **out) {
         r = mcac_gpu_upload_state(h, m->st.n_sph, m->st.n_agg, m->st.sphere_fields.data(), m->st.sphere_charge.data(), m->st.agg_fields.data(),
                                   m->st.agg_charge.data(), m->st.agg_cells.data(), m->st.offsets.data(), m->st.members.data(),
                                   m->st.per_member.data(), m->st.maxradius, m->st.max_time_step);
+    if (r == 0 && m->pm.with_potentials && m->pm.with_external_potentials) {
+        r = load_interpotential(h, m->pm.interpotential_file);  // path relative to the CWD, like the reference (:49)
+        if (r) { mcac_host_model_destroy(m); if (h) mcac_gpu_destroy(h); return r; }
+    }
     if (r) g_host_err = h ? mcac_gpu_last_error(h) : "mcac_gpu_create failed";
     mcac_host_model_destroy(m);
     if (r) { if (h) mcac_gpu_destroy(h); return r; }

@@ -105,6 +105,13 @@ def make(name: str) -> None:
     shutil.rmtree(wd, ignore_errors=True)
 
 
+def make_interpotential_fixture() -> None:
+    """examples/Interpotential_input.dat (input table of examples/classic.ini) as a compact array; tests write it back as text."""
+    vals = np.array(open(INTERPOT).read().split(), dtype=np.float64)
+    np.savez_compressed(Path(__file__).parent / "interpotential_table.npz", values=vals)
+
+
 if __name__ == "__main__":
+    make_interpotential_fixture()
     for n in (sys.argv[1:] or list(FIXTURES)):
         make(n)

@@ -54,3 +54,13 @@ def digest_from_oracle_records(recs: np.ndarray, with_collisions: bool) -> str:
     for k in STEP_KEYS:
         h.update(np.ascontiguousarray(recs[ORC_TO_STEP[k]]).tobytes())
     return h.hexdigest()
+
+
+def write_interpotential_file(path) -> str:
+    """Re-create the text table examples/classic.ini points at from the committed fixture (one value per line is a valid layout:
+    the reference reads it with operator>>)."""
+    vals = np.load(GOLDEN / "interpotential_table.npz")["values"]
+    with open(path, "w") as f:
+        f.write("\n".join(repr(float(v)) for v in vals))
+        f.write("\n")
+    return str(path)

@@ -192,6 +192,25 @@ def test_general_step_loop_growth_picklast_nocollision(name, steps):
     assert_states_match(sim.state(), o.state(), box)
 
 
+def test_classic_potentials_nucleation_individual_growth(tmp_path):
+    """examples/classic.ini (the ensemble workload): external interaction potentials with direction redraws, nucleation,
+    individual surface reactions, normal-law diameters, three domain duplications within the first 1500 steps."""
+    from golden_lib import write_interpotential_file
+    g = Golden("classic_seed1000")
+    ov = dict(g.overrides)
+    ov["inter_potential"] = {"interpotential_file": write_interpotential_file(tmp_path / "Interpotential_input.dat")}
+    steps = 1500
+    sim = Simulation(ini_text(merged_config(g.base, ov)))
+    rep, recs = sim.run(steps, records=steps)
+    o = Oracle(g.base, ov)
+    ref = o.run(steps)
+    box = o.scalars()["box_length"]
+    assert rep["steps"] == len(ref)
+    assert_records_match(recs, ref, box)
+    assert rep["events"] == o.counters()["events"]
+    assert_states_match(sim.state(), o.state(), box)
+
+
 def test_per_call_entry_points_follow_the_reference_methods():
     """translate / grow / update(partial, full) / merge / refresh called one by one through the C ABI (the per-call mode a
     reference shim would use) against the oracle driven the same way."""
