@@ -1235,7 +1235,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             if ((rc = push_scalars(h)) != E_OK) break;
         }
         if ((rc = ensure_rng(h, h->sc_host.rand_pos + 8192)) != E_OK) break;
-        int draws = pick_last ? 2 : 3, n_try = 1;
+        int draws = pick_last ? 2 : 3, n_try = 1, draws_at_search = pick_last ? 2 : 3;
         if (pick_last) {
             k_pick_last<<<1, 1024, 0, h->stream>>>(h->d, h->q_slot);
             k_prepare_direction<<<1, 32, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, 0);
@@ -1260,6 +1260,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                 if (draws + 8 > 8192) { h->err = "orientation loop: too many redraws"; rc = E_UNKNOWN; break; }
                 k_prepare_direction<<<1, 32, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, draws);
                 draws += 2;
+                draws_at_search = draws;
                 h->launches++;
                 if ((rc = search_launch(h, 1)) != E_OK) break;
             }
@@ -1270,7 +1271,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         sa.q_slot = h->q_slot; sa.q_dir = h->q_dir; sa.q_dist = h->q_dist; sa.res = h->q_res;
         sa.rec = (records && n_records > 0) ? h->rec_dev : nullptr;
         sa.rec_cap = n_records; sa.rec_index = steps;
-        sa.pick_last = pick_last; sa.with_collisions = p.with_collisions; sa.n_try = n_try; sa.draws = draws;
+        sa.pick_last = pick_last; sa.with_collisions = p.with_collisions; sa.n_try = n_try; sa.draws = draws; sa.draws_at_search = draws_at_search;
         prof_begin(h, 1);
         k_step_move<<<1, kCommitThreads, 0, h->stream>>>(h->d, sa);
         if (growth) k_grow_pending<<<div_up(p.individual_surf_reactions ? h->sc_host.n_sph : h->sc_host.pool_top, 256), 256, 0, h->stream>>>(h->d, p.individual_surf_reactions);

@@ -870,6 +870,7 @@ struct StepArgs {
     mcac_step_record *rec;
     long long rec_cap, rec_index;
     int pick_last, with_collisions, n_try, draws;
+    int draws_at_search;  // draws consumed when the last search returned (the tap convention of the step records)
 };
 __global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepArgs a) {
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -905,7 +906,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepAr
             mcac_step_record o;
             const bool has = r.other_agg >= 0;
             o.step = sc.steps_done;
-            o.rand_calls = sc.rand_pos + a.draws;
+            o.rand_calls = sc.rand_pos + a.draws_at_search;
             o.source = d.label_of_slot[slot];
             o.dir[0] = a.q_dir[0]; o.dir[1] = a.q_dir[1]; o.dir[2] = a.q_dir[2];
             o.full_distance = full;
