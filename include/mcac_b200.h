@@ -83,6 +83,7 @@ typedef struct mcac_run_report {
     int64_t search_launches, commit_launches;
     double event_ms, cells_ms;             /* per-event pipeline (k_event) / Verlet cell rebuild (K2) */
     int64_t event_launches, cells_launches;
+    int64_t sort_span_elements, sort_levels; /* sum over sort levels of the active span (elements) / number of levels */
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction

@@ -61,7 +61,7 @@ class RunReport(C.Structure):
                                           "search_ms", "commit_ms"]] + \
                [(n, C.c_int64) for n in ["search_launches", "commit_launches"]] + \
                [(n, C.c_double) for n in ["event_ms", "cells_ms"]] + \
-               [(n, C.c_int64) for n in ["event_launches", "cells_launches"]]
+               [(n, C.c_int64) for n in ["event_launches", "cells_launches", "sort_span_elements", "sort_levels"]]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

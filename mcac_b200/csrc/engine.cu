@@ -75,6 +75,9 @@ struct mcac_gpu {
     int *h_flags = nullptr;  // pinned: sort `active` flags
     long long sort_levels = 0, sort_fallbacks = 0;
     int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
+    int coop_bps = 1, sort_local_span = 4096;
+    long long *event_work = nullptr;
+    long long event_work_seen[2] = {0, 0};
     long long *part_ll = nullptr;
     double *part_d = nullptr;
     int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
@@ -367,9 +370,12 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.do_sort = do_sort ? 1 : 0;
     a.cum_sequential_max = h->cum_sequential_max;
     a.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
+    a.local_span = h->sort_local_span;
+    a.work = h->event_work;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
-    CK(cudaLaunchCooperativeKernel((void *)k_event, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream));
+    const void *fn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream));
     h->launches++;
     TRY(pull_scalars(h));
     h->labels_valid = true;
@@ -829,9 +835,14 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event, kEventThreads, 0) == cudaSuccess && occ > 0)
-            h->coop_blocks = h->n_sm * std::min(occ, 2);
+        if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
+        if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
+        cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, 0)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, 0);
+        if (coop && oe == cudaSuccess && occ > 0) h->coop_blocks = h->n_sm * std::min(occ, h->coop_bps);
         if (getenv("MCAC_B200_NO_COOP")) h->coop_blocks = 0;
+        TRY(dev_alloc_persistent(h, &h->event_work, 4));
+        CK(cudaMemset(h->event_work, 0, 4 * sizeof(long long)));
         TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
         TRY(dev_alloc_persistent(h, &h->part_d, 4 * 4096));
     }
@@ -1397,6 +1408,11 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->max_time_step = sc.max_time_step;
         report->volume_fraction = sc.volume_fraction;
         report->device_ms = ms;
+        long long w[2] = {0, 0};
+        cudaMemcpy(w, h->event_work, sizeof(w), cudaMemcpyDeviceToHost);
+        report->sort_span_elements = w[0] - h->event_work_seen[0];
+        report->sort_levels = w[1] - h->event_work_seen[1];
+        h->event_work_seen[0] = w[0]; h->event_work_seen[1] = w[1];
     }
     prof_collect(h, report);
     return E_OK;

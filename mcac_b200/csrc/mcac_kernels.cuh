@@ -1682,6 +1682,8 @@ struct EventArgs {
     int cum_sequential_max, stable;
     int use_factor;       // sort_time_steps(factor) called with an explicit factor (per-call C ABI)
     double factor;
+    int local_span;       // span (elements) below which block 0 finishes the sort alone
+    long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
 };
 namespace cgx = cooperative_groups;
 
@@ -1719,7 +1721,8 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long *sm) {
     return t;
 }
 
-__global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d, EventArgs a) {
     cgx::grid_group grid = cgx::this_grid();
     __shared__ long long sm_ll[32];
     __shared__ double sm_d[32];
@@ -1853,7 +1856,7 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
     // Work is restricted to the span [amin, amax) of the still-active segments (all-equal segments leave the loop
     // analytically, so in tie-dominated tables the span halves every level).  Once the span fits kSortLocal elements,
     // block 0 finishes the remaining levels alone with __syncthreads() instead of grid barriers.
-    constexpr int kSortLocal = 8192;
+    const int kSortLocal = a.local_span;
     int eblk = blk, enblk = nblk;
     long long etid = gtid, esize = gsize;
     auto barrier = [&]() { if (local) __syncthreads(); else grid.sync(); };
@@ -1867,6 +1870,7 @@ __global__ void __launch_bounds__(kEventThreads) k_event(DevState d, EventArgs a
             eblk = 0; enblk = 1; etid = tid; esize = nthr;
         }
         const int span = amax - amin + 1;  // + 1 so that pre[amax] exists
+        if (etid == 0 && a.work) { a.work[0] += span; a.work[1] += 1; }
         const int chunk = ((span + enblk - 1) / enblk + nthr - 1) / nthr * nthr;
         // ---- flags + chunk sums
         {
