@@ -115,7 +115,7 @@ def main():
     ap.add_argument("--n-monomers", type=int, default=1_000_000)
     ap.add_argument("--mc-steps", type=int, default=0, help="MC steps per bench step (default 20000; 400 for --impl reference)")
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -239,32 +239,47 @@ def main():
     # ---- e2e: the same metric through the C ABI with HOST buffers: upload_state (H2D) + run + download_state (D2H) per step
     e2e = None
     if a.e2e_steps > 0:
-        st = sim.state()
+        # The host owns the state (the reference's SoA arrays, here in page-locked memory); every step uploads it, runs M MC
+        # steps and reads the new state back.  Array sizes change with the merges, so each step re-binds views of the same
+        # pinned blocks (n_agg shrinks; n_sph is constant in this workload).
+        ns0, na0 = sim.sizes()
+        pin = sim.pinned_state_buffers(ns0, na0)
+
+        def views(na):
+            v = dict(pin)
+            v["agg_fields"] = pin["agg_fields"].reshape(-1)[:21 * na].reshape(21, na)
+            v["agg_cell"] = pin["agg_cell"].reshape(-1)[:3 * na].reshape(3, na)
+            for k in ("agg_n_spheres", "agg_charge"):
+                v[k] = pin[k][:na]
+            v["offsets"] = pin["offsets"][:na + 1]
+            return v
+
+        cur = views(na0)
+        sim.download_into(cur)
         h2d = d2h = 0
         torch.cuda.synchronize()
         t_e = time.perf_counter()
         steps_e = 0
         for _ in range(a.e2e_steps):
-            up = dict(sphere_fields=np.stack([st["spheres"][k] for k in mcac_b200.SPHERE_FIELDS]),
-                      agg_fields=np.stack([st["aggregates"][k] for k in mcac_b200.AGG_FIELDS]), sphere_charge=st["sphere_charge"],
-                      agg_charge=st["agg_charge"], agg_cell=st["agg_cell"], offsets=st["offsets"], members=st["members"],
-                      per_member=np.stack([st["member_volumes"], st["member_surfaces"], st["member_distances_center"]]),
-                      maxradius=st["maxradius"], max_time_step=st["max_time_step"])
-            sim.upload(up)
+            sim.upload_from(cur)
+            h2d = sum(cur[k].nbytes for k in ("sphere_fields", "sphere_charge", "agg_fields", "agg_charge", "agg_cell", "offsets",
+                                              "members", "per_member"))
             r, _ = sim.run(M, batch=a.batch)
-            st = sim.state()
+            cur = views(r["n_aggregates"])
+            sim.download_into(cur)
             steps_e += r["steps"]
-            h2d = sum(v.nbytes for v in up.values() if hasattr(v, "nbytes"))
-            d2h = h2d + st["sphere_label"].nbytes + st["agg_n_spheres"].nbytes + 160
+            d2h = sum(v.nbytes for k, v in cur.items() if k != "_pinned")
         torch.cuda.synchronize()
         e_s = time.perf_counter() - t_e
+        sim.free_pinned(pin)
         e = torch.tensor([e_s], dtype=torch.float64, device="cuda")
         es = torch.tensor([float(steps_e)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(e, op=dist.ReduceOp.MAX)
             dist.all_reduce(es, op=dist.ReduceOp.SUM)
         e2e = {"value": float(es[0]) / float(e[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "what": "mcac_gpu_upload_state(host SoA) + mcac_gpu_run + mcac_gpu_download_state(host SoA) per step, wall clock"}
+               "what": "per step: mcac_gpu_upload_state(host SoA, pinned) + mcac_gpu_run(M MC steps) + mcac_gpu_download_state(host SoA, "
+                       "pinned); wall clock over the steps, max over ranks"}
 
     # ---- the only collective of the path: all-gather of the per-realization morphology statistics (K11)
     n_bins = 24

@@ -118,6 +118,10 @@ int mcac_gpu_upload_state(mcac_gpu *h, int64_t n_sph, int64_t n_agg, const doubl
                           const int64_t *offsets, const int64_t *members, const double *per_member, double maxradius,
                           double max_time_step);
 int mcac_gpu_sizes(mcac_gpu *h, int64_t *n_sph, int64_t *n_agg);
+/* Page-locked host memory for the arrays above (the storage behind the reference's ListStorage vectors,
+ * include/list_storage/list_storage.hpp:32-34, when the caller wants full-bandwidth async transfers); pageable memory works too. */
+int mcac_host_alloc_pinned(int64_t bytes, void **out);
+int mcac_host_free_pinned(void *p);
 int mcac_gpu_download_state(mcac_gpu *h, double *sphere_fields, int64_t *sphere_label, int64_t *sphere_charge, double *agg_fields,
                             int64_t *agg_n_spheres, int64_t *agg_charge, int64_t *agg_cells, int64_t *offsets, int64_t *members,
                             double *per_member, double *scalars /* 20, same order as the oracle's orc_get_scalars */);

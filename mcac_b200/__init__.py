@@ -133,6 +133,42 @@ class Simulation:
         out.update(dict(zip(SCALARS, (float(v) for v in sc))))
         return out
 
+    # ---- the same boundary on caller-owned page-locked arrays (no per-call allocation; full-bandwidth async copies)
+    def pinned_state_buffers(self, n_sph: int | None = None, n_agg: int | None = None) -> dict:
+        """Host arrays of the state boundary in page-locked memory, sized for (n_sph, n_agg) (default: the current state)."""
+        if n_sph is None or n_agg is None:
+            n_sph, n_agg = self.sizes()
+        spec = dict(sphere_fields=((9, n_sph), np.float64), sphere_label=((n_sph,), np.int64), sphere_charge=((n_sph,), np.int64),
+                    agg_fields=((21, n_agg), np.float64), agg_n_spheres=((n_agg,), np.int64), agg_charge=((n_agg,), np.int64),
+                    agg_cell=((3, n_agg), np.int64), offsets=((n_agg + 1,), np.int64), members=((n_sph,), np.int64),
+                    per_member=((3, n_sph), np.float64), scalars=((20,), np.float64))
+        out = {"_pinned": []}
+        for name, (shape, dt) in spec.items():
+            nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+            p = C.c_void_p()
+            if self.L.mcac_host_alloc_pinned(nbytes, C.byref(p)):
+                raise McacError(1, "cudaHostAlloc failed")
+            out["_pinned"].append(p)
+            buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+            out[name] = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        return out
+
+    def free_pinned(self, bufs: dict):
+        for p in bufs.pop("_pinned", []):
+            self.L.mcac_host_free_pinned(p)
+
+    def download_into(self, b: dict, n_sph: int | None = None, n_agg: int | None = None):
+        """mcac_gpu_download_state into arrays of matching size (see pinned_state_buffers)."""
+        self._ck(self.L.mcac_gpu_download_state(self.h, ptr(b["sphere_fields"]), ptr(b["sphere_label"]), ptr(b["sphere_charge"]),
+                                                ptr(b["agg_fields"]), ptr(b["agg_n_spheres"]), ptr(b["agg_charge"]), ptr(b["agg_cell"]),
+                                                ptr(b["offsets"]), ptr(b["members"]), ptr(b["per_member"]), ptr(b["scalars"])))
+
+    def upload_from(self, b: dict):
+        ns, na = b["sphere_fields"].shape[1], b["agg_fields"].shape[1]
+        self._ck(self.L.mcac_gpu_upload_state(self.h, ns, na, ptr(b["sphere_fields"]), ptr(b["sphere_charge"]), ptr(b["agg_fields"]),
+                                              ptr(b["agg_charge"]), ptr(b["agg_cell"]), ptr(b["offsets"]), ptr(b["members"]),
+                                              ptr(b["per_member"]), float(b["scalars"][2]), float(b["scalars"][3])))
+
     # ---- per-call mirror of the AggregatList / Aggregate methods
     def contact_search(self, label: int, direction, distance: float) -> Contact:
         d = np.ascontiguousarray(direction, np.float64)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/mcac_b200.h"
@@ -85,6 +86,12 @@ struct mcac_gpu {
     double *sweep_dir = nullptr, *sweep_dist = nullptr;
     SearchResult *sweep_res = nullptr;
     long long sweep_cap = 0;
+    int *wide_list = nullptr, *wide_count = nullptr;  // queries handed from the group search kernel to the wide one
+    long long wide_cap = 0;
+    int wide_parity = 0;
+    int search_group = 8;     // lanes per query of K1 (4, 8, 16 or 32)
+    void *stage = nullptr;  // device staging of the host-layout arrays at the upload / download boundary
+    size_t stage_bytes = 0;
 };
 
 #define CK(call)                                                                                  \
@@ -163,6 +170,7 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     for (int **p : {&d.a_n, &d.a_off, &d.a_cx, &d.a_cy, &d.a_cz, &d.a_charge, &d.a_alive, &d.label_of_slot, &d.slot_of_label,
                     &d.sorted_slot, &d.cell_items, &h->sorted_label})
         TRY(dev_alloc(h, p, agg_cap));
+    TRY(dev_alloc(h, &d.cell_posr, agg_cap));
     TRY(dev_alloc(h, &d.cell_start, (size_t)d.n_cells + 1));
     TRY(dev_alloc(h, &d.cell_fill, (size_t)d.n_cells + 1));
     SortBufs &sb = h->sortb;
@@ -435,8 +443,26 @@ int compact_pool(mcac_gpu *h) {
     return E_OK;
 }
 
+// raw host arrays in the reference's layout (what the C ABI receives / fills)
+struct HostView {
+    long long n_sph, n_agg;
+    const double *sph;
+    const long long *sph_charge;
+    const double *agg;
+    const long long *agg_charge, *agg_cells, *offsets, *members;
+    const double *per_member;
+};
+struct HostOut {
+    double *sph;
+    long long *sph_label, *sph_charge;
+    double *agg;
+    long long *agg_n, *agg_charge, *agg_cells, *offsets, *members;
+    double *per_member, *scalars;
+};
+int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_step);
 int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_step, bool keep_scalars);
 int download(mcac_gpu *h, HostState &s);
+int download_to(mcac_gpu *h, const HostOut &o);
 
 // AggregatList::duplication (aggregat_list.cpp:142-190): box x2, 7 translated copies of every aggregate appended in
 // (i,j,k) order, Verlet rebuilt.  Rare (once per 8x drop of N_agg) and purely a re-layout, so it is orchestrated
@@ -502,7 +528,6 @@ int duplicate(mcac_gpu *h) {
     t.scalars[15] = h->prm.box_volume;
     t.scalars[17] = (double)h->prm.n_monomeres;
     Scalars keep = h->sc_host;
-    free_all(h);
     h->uploaded = false;
     TRY(upload(h, t, t.scalars[2], t.scalars[3], false));
     // restore run-time scalars that upload() resets
@@ -562,76 +587,78 @@ void fill_devstate_params(mcac_gpu *h) {
     d.init_mode_normal = p.normal_initialisation;
 }
 
+// carve the staging buffer into the host-layout arrays (256-byte aligned); returns the bytes needed
+size_t carve_stage(HostLayout &L, char *base, long long n_sph, long long n_agg) {
+    size_t off = 0;
+    auto take = [&](auto **p, size_t count) {
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+        *p = reinterpret_cast<T *>(base + off);
+        off += (count * sizeof(T) + 255) / 256 * 256;
+    };
+    L.n_sph = n_sph;
+    L.n_agg = n_agg;
+    take(&L.sph, (size_t)(9 * n_sph));
+    take(&L.sph_label, (size_t)n_sph);
+    take(&L.sph_charge, (size_t)n_sph);
+    take(&L.agg, (size_t)(21 * n_agg));
+    take(&L.agg_n, (size_t)n_agg);
+    take(&L.agg_charge, (size_t)n_agg);
+    take(&L.agg_cells, (size_t)(3 * n_agg));
+    take(&L.offsets, (size_t)n_agg + 1);
+    take(&L.members, (size_t)n_sph);
+    take(&L.per_member, (size_t)(3 * n_sph));
+    return off;
+}
+int ensure_stage(mcac_gpu *h, size_t bytes) {
+    if (h->stage_bytes >= bytes) return E_OK;
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    const size_t want = bytes + bytes / 8;
+    CK(cudaMalloc(&h->stage, want));
+    h->stage_bytes = want;
+    return E_OK;
+}
+
 int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_step, bool keep_scalars) {
     (void)keep_scalars;
+    HostView v{s.n_sph, s.n_agg, s.sph.data(), s.sph_charge.data(), s.agg.data(), s.agg_charge.data(), s.agg_cells.data(),
+               s.offsets.data(), s.members.data(), s.per_member.data()};
+    return upload(h, v, maxradius, max_time_step);
+}
+
+// Host SoA -> HBM: the arrays cross PCIe as they are (one async copy each, full bandwidth from pinned memory); the
+// gather into the aggregate-major pool is K-side work (k_upload_spheres / k_upload_aggregates).
+int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_step) {
     DevState &d = h->d;
     fill_devstate_params(h);
     const long long n_agg = s.n_agg, n_sph = s.n_sph;
     if (n_agg <= 0 || n_sph <= 0) { h->err = "upload_state: empty state"; return E_INPUT; }
+    if (s.offsets[0] != 0 || s.offsets[n_agg] != n_sph) { h->err = "upload_state: membership offsets do not cover the spheres"; return E_INPUT; }
     const long long headroom = h->prm.with_nucleation ? std::max<long long>(n_agg, 4096) : 0;  // slots for nucleated monomers
-    TRY(alloc_state(h, n_agg + headroom, 3 * (n_sph + headroom) + 1024));
-    std::vector<double4> posr((size_t)n_sph), relv((size_t)n_sph), aposr((size_t)n_agg);
-    std::vector<double> surf((size_t)n_sph), veff((size_t)n_sph), seff((size_t)n_sph), dcen((size_t)n_sph);
-    std::vector<int> sid((size_t)n_sph), scharge((size_t)n_sph), slot_of_id((size_t)n_sph);
-    auto S = [&](int f, long long i) { return s.sph[(size_t)(f * n_sph + i)]; };
-    auto A = [&](int f, long long a) { return s.agg[(size_t)(f * n_agg + a)]; };
-    for (long long a = 0; a < n_agg; a++) {
-        for (long long k = s.offsets[(size_t)a]; k < s.offsets[(size_t)a + 1]; k++) {
-            const long long id = s.members[(size_t)k];
-            posr[(size_t)k] = make_double4(S(0, id), S(1, id), S(2, id), S(3, id));
-            relv[(size_t)k] = make_double4(S(6, id), S(7, id), S(8, id), S(4, id));
-            surf[(size_t)k] = S(5, id);
-            veff[(size_t)k] = s.per_member[(size_t)k];
-            seff[(size_t)k] = s.per_member[(size_t)(n_sph + k)];
-            dcen[(size_t)k] = s.per_member[(size_t)(2 * n_sph + k)];
-            sid[(size_t)k] = (int)id;
-            scharge[(size_t)k] = (int)s.sph_charge[(size_t)id];
-            slot_of_id[(size_t)id] = (int)k;
-        }
-        aposr[(size_t)a] = make_double4(A(7, a), A(8, a), A(9, a), A(4, a));
+    const long long need_agg = n_agg + headroom, need_sph = 3 * (n_sph + headroom) + 1024;
+    if (h->owned.empty() || d.agg_cap < need_agg || d.sph_cap < need_sph) {  // otherwise the resident allocation is reused
+        free_all(h);
+        TRY(alloc_state(h, need_agg, need_sph));
     }
+    HostLayout L;
+    TRY(ensure_stage(h, carve_stage(L, nullptr, n_sph, n_agg)));
+    carve_stage(L, (char *)h->stage, n_sph, n_agg);
     auto up = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream); };
-    CK(up(d.s_posr, posr.data(), sizeof(double4) * n_sph));
-    CK(up(d.s_relv, relv.data(), sizeof(double4) * n_sph));
-    CK(up(d.s_surf, surf.data(), sizeof(double) * n_sph));
-    CK(up(d.s_veff, veff.data(), sizeof(double) * n_sph));
-    CK(up(d.s_seff, seff.data(), sizeof(double) * n_sph));
-    CK(up(d.s_dcen, dcen.data(), sizeof(double) * n_sph));
-    CK(up(d.s_id, sid.data(), sizeof(int) * n_sph));
-    CK(up(d.s_charge, scharge.data(), sizeof(int) * n_sph));
-    CK(up(d.slot_of_id, slot_of_id.data(), sizeof(int) * n_sph));
-    CK(up(d.a_posr, aposr.data(), sizeof(double4) * n_agg));
-    // AggregatesFields order: RG,F_AGG,LPM,TIME_STEP,RMAX,VOLUME,SURFACE,X,Y,Z,RX,RY,RZ,TIME,DP,DG_OVER_DP,OVERLAPPING,
-    // COORDINATION_NUMBER,ELECTRIC_CHARGE,D_M,CH_RATIO (include/constants.hpp:46-69)
-    struct { double *dst; int f; } cols[] = {{d.a_rg, 0}, {d.a_fagg, 1}, {d.a_lpm, 2}, {d.a_ts, 3}, {d.a_vol, 5}, {d.a_surf, 6}, {d.a_rx, 10},
-                                              {d.a_ry, 11}, {d.a_rz, 12}, {d.a_ptime, 13}, {d.a_dp, 14}, {d.a_dgdp, 15}, {d.a_ovl, 16},
-                                              {d.a_cn, 17}, {d.a_dm, 19}, {d.a_ch, 20}};
-    for (auto &c : cols) CK(up(c.dst, s.agg.data() + (size_t)c.f * n_agg, sizeof(double) * n_agg));
-    std::vector<double> bulk((size_t)n_agg, h->prm.density), alpha((size_t)n_agg);
-    std::vector<int> an((size_t)n_agg), aoff((size_t)n_agg), cx((size_t)n_agg), cy((size_t)n_agg), cz((size_t)n_agg), ach((size_t)n_agg),
-        alive((size_t)n_agg, 1), ident((size_t)n_agg);
-    for (long long a = 0; a < n_agg; a++) {
-        an[(size_t)a] = (int)s.agg_n[(size_t)a];
-        aoff[(size_t)a] = (int)s.offsets[(size_t)a];
-        alpha[(size_t)a] = 1.0 / static_cast<double>(s.agg_n[(size_t)a]);
-        cx[(size_t)a] = (int)s.agg_cells[(size_t)a];
-        cy[(size_t)a] = (int)s.agg_cells[(size_t)(n_agg + a)];
-        cz[(size_t)a] = (int)s.agg_cells[(size_t)(2 * n_agg + a)];
-        ach[(size_t)a] = (int)s.agg_charge[(size_t)a];
-        ident[(size_t)a] = (int)a;
-    }
-    CK(up(d.a_bulk, bulk.data(), sizeof(double) * n_agg));
-    CK(up(d.a_alpha, alpha.data(), sizeof(double) * n_agg));
-    CK(up(d.a_n, an.data(), sizeof(int) * n_agg));
-    CK(up(d.a_off, aoff.data(), sizeof(int) * n_agg));
-    CK(up(d.a_cx, cx.data(), sizeof(int) * n_agg));
-    CK(up(d.a_cy, cy.data(), sizeof(int) * n_agg));
-    CK(up(d.a_cz, cz.data(), sizeof(int) * n_agg));
-    CK(up(d.a_charge, ach.data(), sizeof(int) * n_agg));
-    CK(up(d.a_alive, alive.data(), sizeof(int) * n_agg));
-    CK(up(d.label_of_slot, ident.data(), sizeof(int) * n_agg));
-    CK(up(d.slot_of_label, ident.data(), sizeof(int) * n_agg));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(up(L.sph, s.sph, sizeof(double) * 9 * n_sph));
+    if (s.sph_charge) CK(up(L.sph_charge, s.sph_charge, sizeof(long long) * n_sph));
+    else CK(cudaMemsetAsync(L.sph_charge, 0, sizeof(long long) * n_sph, h->stream));
+    CK(up(L.agg, s.agg, sizeof(double) * 21 * n_agg));
+    if (s.agg_charge) CK(up(L.agg_charge, s.agg_charge, sizeof(long long) * n_agg));
+    else CK(cudaMemsetAsync(L.agg_charge, 0, sizeof(long long) * n_agg, h->stream));
+    CK(up(L.agg_cells, s.agg_cells, sizeof(long long) * 3 * n_agg));
+    CK(up(L.offsets, s.offsets, sizeof(long long) * (n_agg + 1)));
+    CK(up(L.members, s.members, sizeof(long long) * n_sph));
+    CK(up(L.per_member, s.per_member, sizeof(double) * 3 * n_sph));
+    k_upload_spheres<<<div_up(n_sph, 256), 256, 0, h->stream>>>(d, L);
+    k_upload_aggregates<<<div_up(n_agg, 256), 256, 0, h->stream>>>(d, L, h->prm.density);
+    h->launches += 2;
+    CK(cudaGetLastError());
     Scalars &sc = h->sc_host;
     const Scalars old = sc;
     std::memset(&sc, 0, sizeof(sc));
@@ -649,7 +676,7 @@ int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_st
     sc.rand_pos = old.rand_pos;
     sc.aggregate_concentration = static_cast<double>(n_agg) / sc.box_volume;
     sc.monomer_concentration = static_cast<double>(n_sph) / sc.box_volume;
-    TRY(push_scalars(h));
+    TRY(push_scalars(h));  // synchronizes the stream: the host arrays may be reused on return
     h->labels_valid = true;
     h->pick_valid = false;
     h->cells_valid = false;
@@ -657,89 +684,66 @@ int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_st
     return E_OK;
 }
 
-int download(mcac_gpu *h, HostState &s) {
+// HBM -> host SoA in the reference's layout (label order, creation-order sphere indices); any pointer may be null
+int download_to(mcac_gpu *h, const HostOut &o) {
     DevState &d = h->d;
     TRY(pull_scalars(h));
     TRY(refresh_labels(h));
     const Scalars &sc = h->sc_host;
-    const long long n_agg = sc.n_agg, n_sph = sc.n_sph, n_slots = sc.n_agg_slots, pool = sc.pool_top;
+    const long long n_agg = sc.n_agg, n_sph = sc.n_sph;
+    HostLayout L;
+    TRY(ensure_stage(h, carve_stage(L, nullptr, n_sph, n_agg)));
+    carve_stage(L, (char *)h->stage, n_sph, n_agg);
+    k_download_counts<<<div_up(n_agg, 256), 256, 0, h->stream>>>(d, (int)n_agg, h->scan_tmp);
+    TRY(scan_ints(h, h->scan_tmp, (int)n_agg, h->scan_out));
+    int total = 0;
+    CK(cudaMemcpyAsync(&total, h->scan_out + n_agg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (total != n_sph) { h->err = "download_state: membership does not match the sphere count"; return E_UNKNOWN; }
+    k_download_state<<<div_up(n_agg * 32, 256), 256, 0, h->stream>>>(d, L, h->scan_out);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    auto dn = [&](void *dst, const void *src, size_t bytes) {
+        return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+    };
+    CK(dn(o.sph, L.sph, sizeof(double) * 9 * n_sph));
+    CK(dn(o.sph_label, L.sph_label, sizeof(long long) * n_sph));
+    CK(dn(o.sph_charge, L.sph_charge, sizeof(long long) * n_sph));
+    CK(dn(o.agg, L.agg, sizeof(double) * 21 * n_agg));
+    CK(dn(o.agg_n, L.agg_n, sizeof(long long) * n_agg));
+    CK(dn(o.agg_charge, L.agg_charge, sizeof(long long) * n_agg));
+    CK(dn(o.agg_cells, L.agg_cells, sizeof(long long) * 3 * n_agg));
+    CK(dn(o.offsets, L.offsets, sizeof(long long) * (n_agg + 1)));
+    CK(dn(o.members, L.members, sizeof(long long) * n_sph));
+    CK(dn(o.per_member, L.per_member, sizeof(double) * 3 * n_sph));
+    CK(cudaStreamSynchronize(h->stream));
+    if (o.scalars) {
+        const double sv[20] = {sc.time, sc.box_length, sc.maxradius, sc.max_time_step, sc.avg_npp, sc.volume_fraction,
+                               sc.aggregate_concentration, sc.monomer_concentration, sc.total_volume_concent, sc.total_surface_concent,
+                               h->prm.u_sg, h->prm.gaz_mean_free_path, 0., 0., h->prm.viscosity, sc.box_volume,
+                               (double)sc.n_iter_without_event, (double)sc.n_monomeres, h->prm.temperature, sc.nucleation_accum};
+        std::memcpy(o.scalars, sv, sizeof(sv));
+    }
+    return E_OK;
+}
+
+int download(mcac_gpu *h, HostState &s) {
+    TRY(pull_scalars(h));
+    const long long n_agg = h->sc_host.n_agg, n_sph = h->sc_host.n_sph;
     s.n_agg = n_agg;
     s.n_sph = n_sph;
-    std::vector<double4> posr((size_t)pool), relv((size_t)pool), aposr((size_t)n_slots);
-    std::vector<double> surf((size_t)pool), veff((size_t)pool), seff((size_t)pool), dcen((size_t)pool);
-    std::vector<int> sid((size_t)pool), scharge((size_t)pool), an((size_t)n_slots), aoff((size_t)n_slots), cx((size_t)n_slots),
-        cy((size_t)n_slots), cz((size_t)n_slots), ach((size_t)n_slots), slot_of_label((size_t)n_slots);
-    auto dn = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream); };
-    CK(dn(posr.data(), d.s_posr, sizeof(double4) * pool));
-    CK(dn(relv.data(), d.s_relv, sizeof(double4) * pool));
-    CK(dn(surf.data(), d.s_surf, sizeof(double) * pool));
-    CK(dn(veff.data(), d.s_veff, sizeof(double) * pool));
-    CK(dn(seff.data(), d.s_seff, sizeof(double) * pool));
-    CK(dn(dcen.data(), d.s_dcen, sizeof(double) * pool));
-    CK(dn(sid.data(), d.s_id, sizeof(int) * pool));
-    CK(dn(scharge.data(), d.s_charge, sizeof(int) * pool));
-    CK(dn(aposr.data(), d.a_posr, sizeof(double4) * n_slots));
-    CK(dn(an.data(), d.a_n, sizeof(int) * n_slots));
-    CK(dn(aoff.data(), d.a_off, sizeof(int) * n_slots));
-    CK(dn(cx.data(), d.a_cx, sizeof(int) * n_slots));
-    CK(dn(cy.data(), d.a_cy, sizeof(int) * n_slots));
-    CK(dn(cz.data(), d.a_cz, sizeof(int) * n_slots));
-    CK(dn(ach.data(), d.a_charge, sizeof(int) * n_slots));
-    CK(dn(slot_of_label.data(), d.slot_of_label, sizeof(int) * n_slots));
-    std::vector<std::vector<double>> acol(21, std::vector<double>((size_t)n_slots, 0.));
-    struct { double *src; int f; } cols[] = {{d.a_rg, 0}, {d.a_fagg, 1}, {d.a_lpm, 2}, {d.a_ts, 3}, {d.a_vol, 5}, {d.a_surf, 6}, {d.a_rx, 10},
-                                              {d.a_ry, 11}, {d.a_rz, 12}, {d.a_ptime, 13}, {d.a_dp, 14}, {d.a_dgdp, 15}, {d.a_ovl, 16},
-                                              {d.a_cn, 17}, {d.a_dm, 19}, {d.a_ch, 20}};
-    for (auto &c : cols) CK(dn(acol[(size_t)c.f].data(), c.src, sizeof(double) * n_slots));
-    CK(cudaStreamSynchronize(h->stream));
-    s.sph.assign((size_t)(9 * n_sph), 0.);
-    s.sph_label.assign((size_t)n_sph, -1);
-    s.sph_charge.assign((size_t)n_sph, 0);
-    s.agg.assign((size_t)(21 * n_agg), 0.);
-    s.agg_n.assign((size_t)n_agg, 0);
-    s.agg_charge.assign((size_t)n_agg, 0);
-    s.agg_cells.assign((size_t)(3 * n_agg), 0);
-    s.offsets.assign((size_t)n_agg + 1, 0);
-    s.members.assign((size_t)n_sph, 0);
-    s.per_member.assign((size_t)(3 * n_sph), 0.);
-    long long off = 0;
-    for (long long l = 0; l < n_agg; l++) {
-        const int slot = slot_of_label[(size_t)l];
-        const int n = an[(size_t)slot], o = aoff[(size_t)slot];
-        s.offsets[(size_t)l] = off;
-        if (off + n > n_sph) { h->err = "download_state: membership exceeds the sphere count"; return E_UNKNOWN; }
-        for (int k = 0; k < n; k++) {
-            const int t = o + k;
-            const long long id = sid[(size_t)t];
-            const double v[9] = {posr[(size_t)t].x, posr[(size_t)t].y, posr[(size_t)t].z, posr[(size_t)t].w, relv[(size_t)t].w, surf[(size_t)t],
-                                 relv[(size_t)t].x, relv[(size_t)t].y, relv[(size_t)t].z};
-            for (int f = 0; f < 9; f++) s.sph[(size_t)(f * n_sph + id)] = v[f];
-            s.sph_label[(size_t)id] = l;
-            s.sph_charge[(size_t)id] = scharge[(size_t)t];
-            s.members[(size_t)(off + k)] = id;
-            s.per_member[(size_t)(off + k)] = veff[(size_t)t];
-            s.per_member[(size_t)(n_sph + off + k)] = seff[(size_t)t];
-            s.per_member[(size_t)(2 * n_sph + off + k)] = dcen[(size_t)t];
-        }
-        off += n;
-        for (int f = 0; f < 21; f++) s.agg[(size_t)(f * n_agg + l)] = acol[(size_t)f][(size_t)slot];
-        s.agg[(size_t)(4 * n_agg + l)] = aposr[(size_t)slot].w;
-        s.agg[(size_t)(7 * n_agg + l)] = aposr[(size_t)slot].x;
-        s.agg[(size_t)(8 * n_agg + l)] = aposr[(size_t)slot].y;
-        s.agg[(size_t)(9 * n_agg + l)] = aposr[(size_t)slot].z;
-        s.agg_n[(size_t)l] = n;
-        s.agg_charge[(size_t)l] = ach[(size_t)slot];
-        s.agg_cells[(size_t)l] = cx[(size_t)slot];
-        s.agg_cells[(size_t)(n_agg + l)] = cy[(size_t)slot];
-        s.agg_cells[(size_t)(2 * n_agg + l)] = cz[(size_t)slot];
-    }
-    s.offsets[(size_t)n_agg] = off;
-    const double sv[20] = {sc.time, sc.box_length, sc.maxradius, sc.max_time_step, sc.avg_npp, sc.volume_fraction, sc.aggregate_concentration,
-                           sc.monomer_concentration, sc.total_volume_concent, sc.total_surface_concent, h->prm.u_sg, h->prm.gaz_mean_free_path,
-                           0., 0., h->prm.viscosity, sc.box_volume, (double)sc.n_iter_without_event, (double)sc.n_monomeres,
-                           h->prm.temperature, sc.nucleation_accum};
-    std::memcpy(s.scalars, sv, sizeof(sv));
-    return E_OK;
+    s.sph.resize((size_t)(9 * n_sph));
+    s.sph_label.resize((size_t)n_sph);
+    s.sph_charge.resize((size_t)n_sph);
+    s.agg.resize((size_t)(21 * n_agg));
+    s.agg_n.resize((size_t)n_agg);
+    s.agg_charge.resize((size_t)n_agg);
+    s.agg_cells.resize((size_t)(3 * n_agg));
+    s.offsets.resize((size_t)n_agg + 1);
+    s.members.resize((size_t)n_sph);
+    s.per_member.resize((size_t)(3 * n_sph));
+    return download_to(h, HostOut{s.sph.data(), s.sph_label.data(), s.sph_charge.data(), s.agg.data(), s.agg_n.data(), s.agg_charge.data(),
+                                  s.agg_cells.data(), s.offsets.data(), s.members.data(), s.per_member.data(), s.scalars});
 }
 
 // PhysicalModel::finished (physical_model.cpp:288-337) on the mirrored scalars; wall-clock limits are not part of the path
@@ -798,12 +802,35 @@ void prof_collect(mcac_gpu *h, mcac_run_report *rep) {
     }
 }
 
-int search_launch(mcac_gpu *h, int nq) {
-    TRY(build_cells(h));
-    k_search<<<nq, kSearchThreads, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
-    h->launches++;
+// K1: group-per-query kernel, then the wide kernel over the (usually empty) list of queries it handed over
+int search_kernels(mcac_gpu *h, int nq, const int *q_slot, const double *q_dir, const double *q_dist, SearchResult *res) {
+    if (h->wide_cap < nq) {
+        if (h->wide_list) cudaFree(h->wide_list);
+        h->wide_list = nullptr;
+        h->wide_cap = 0;
+        CK(cudaMalloc((void **)&h->wide_list, sizeof(int) * ((size_t)nq + 2)));
+        CK(cudaMemsetAsync(h->wide_list + nq, 0, 2 * sizeof(int), h->stream));
+        h->wide_cap = nq;
+    }
+    // two counters used alternately: each launch of the group kernel clears the one the NEXT search will use
+    h->wide_parity ^= 1;
+    int *count = h->wide_list + h->wide_cap + h->wide_parity, *next_count = h->wide_list + h->wide_cap + (h->wide_parity ^ 1);
+    switch (h->search_group) {
+    case 4: k_search_group<4><<<div_up(nq, kSearchThreads / 4), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
+    case 16: k_search_group<16><<<div_up(nq, kSearchThreads / 16), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
+    case 32: k_search_group<32><<<div_up(nq, kSearchThreads / 32), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
+    case 0: CK(cudaMemsetAsync(next_count, 0, sizeof(int), h->stream)); break;  // wide kernel only (comparison runs)
+    default: k_search_group<8><<<div_up(nq, kSearchThreads / 8), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
+    }
+    const int wide_grid = h->search_group == 0 ? nq : std::min(nq, 8 * h->n_sm);
+    k_search_wide<<<wide_grid, kSearchThreads, 0, h->stream>>>(h->d, nq, h->search_group == 0 ? nullptr : h->wide_list, count, q_slot, q_dir, q_dist, res);
+    h->launches += h->search_group == 0 ? 1 : 2;
     CK(cudaGetLastError());
     return E_OK;
+}
+int search_launch(mcac_gpu *h, int nq) {
+    TRY(build_cells(h));
+    return search_kernels(h, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
 }
 }  // namespace
 
@@ -835,6 +862,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
         cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, 0)
@@ -862,6 +890,8 @@ int mcac_gpu_destroy(mcac_gpu *h) {
     free_all(h);
     for (void *p : h->persistent) cudaFree(p);
     if (h->rec_dev) cudaFree(h->rec_dev);
+    if (h->stage) cudaFree(h->stage);
+    if (h->wide_list) cudaFree(h->wide_list);
     for (void *p : {(void *)h->sweep_slot, (void *)h->sweep_dir, (void *)h->sweep_dist, (void *)h->sweep_res}) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -871,6 +901,13 @@ int mcac_gpu_destroy(mcac_gpu *h) {
 }
 
 const char *mcac_gpu_last_error(const mcac_gpu *h) { return h ? h->err.c_str() : "null handle"; }
+
+int mcac_host_alloc_pinned(int64_t bytes, void **out) {
+    if (!out || bytes < 0) return E_INPUT;
+    *out = nullptr;
+    return cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? E_OK : E_UNKNOWN;
+}
+int mcac_host_free_pinned(void *p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? E_OK : E_UNKNOWN; }
 void *mcac_gpu_stream(mcac_gpu *h) { return h ? (void *)h->stream : nullptr; }
 
 // srand(seed) followed by `consumed` draws already taken by the host-side initial placement (a23)
@@ -916,28 +953,16 @@ int mcac_gpu_upload_state(mcac_gpu *h, int64_t n_sph, int64_t n_agg, const doubl
                           const double *agg_fields, const int64_t *agg_charge, const int64_t *agg_cells, const int64_t *offsets,
                           const int64_t *members, const double *per_member, double maxradius, double max_time_step) {
     CK(cudaSetDevice(h->device));
-    HostState s;
-    s.n_sph = n_sph;
-    s.n_agg = n_agg;
-    s.sph.assign(sphere_fields, sphere_fields + 9 * n_sph);
-    s.sph_charge.assign((size_t)n_sph, 0);
-    if (sphere_charge) s.sph_charge.assign(sphere_charge, sphere_charge + n_sph);
-    s.agg.assign(agg_fields, agg_fields + 21 * n_agg);
-    s.agg_charge.assign((size_t)n_agg, 0);
-    if (agg_charge) s.agg_charge.assign(agg_charge, agg_charge + n_agg);
-    s.agg_cells.assign(agg_cells, agg_cells + 3 * n_agg);
-    s.offsets.assign(offsets, offsets + n_agg + 1);
-    s.members.assign(members, members + n_sph);
-    s.agg_n.resize((size_t)n_agg);
-    for (int64_t a = 0; a < n_agg; a++) s.agg_n[(size_t)a] = offsets[a + 1] - offsets[a];
-    s.per_member.assign(per_member, per_member + 3 * n_sph);
+    if (!sphere_fields || !agg_fields || !agg_cells || !offsets || !members || !per_member) { h->err = "upload_state: null array"; return E_INPUT; }
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    const HostView s{n_sph, n_agg, sphere_fields, (const long long *)sphere_charge, agg_fields, (const long long *)agg_charge,
+                     (const long long *)agg_cells, (const long long *)offsets, (const long long *)members, per_member};
     const bool had_state = h->uploaded;
     const Scalars keep = h->sc_host;
     if (had_state) TRY(pull_scalars(h));
     const Scalars live = h->sc_host;
-    free_all(h);
     h->uploaded = false;
-    TRY(upload(h, s, maxradius, max_time_step, false));
+    TRY(upload(h, s, maxradius, max_time_step));
     if (had_state) {  // the realization keeps running: clocks, counters and the RNG position are the handle's, not the host's
         Scalars &sc = h->sc_host;
         sc.time = live.time; sc.n_iter_without_event = live.n_iter_without_event; sc.total_events = live.total_events;
@@ -965,21 +990,9 @@ int mcac_gpu_download_state(mcac_gpu *h, double *sphere_fields, int64_t *sphere_
                             int64_t *agg_n_spheres, int64_t *agg_charge, int64_t *agg_cells, int64_t *offsets, int64_t *members,
                             double *per_member, double *scalars) {
     CK(cudaSetDevice(h->device));
-    HostState s;
-    TRY(download(h, s));
-    auto cp = [](auto *dst, const auto &v) { if (dst) std::copy(v.begin(), v.end(), dst); };
-    cp(sphere_fields, s.sph);
-    cp(sphere_label, s.sph_label);
-    cp(sphere_charge, s.sph_charge);
-    cp(agg_fields, s.agg);
-    cp(agg_n_spheres, s.agg_n);
-    cp(agg_charge, s.agg_charge);
-    cp(agg_cells, s.agg_cells);
-    cp(offsets, s.offsets);
-    cp(members, s.members);
-    cp(per_member, s.per_member);
-    if (scalars) std::memcpy(scalars, s.scalars, sizeof(s.scalars));
-    return E_OK;
+    return download_to(h, HostOut{sphere_fields, (long long *)sphere_label, (long long *)sphere_charge, agg_fields, (long long *)agg_n_spheres,
+                                  (long long *)agg_charge, (long long *)agg_cells, (long long *)offsets, (long long *)members, per_member,
+                                  scalars});
 }
 
 int mcac_gpu_contact_search_batch(mcac_gpu *h, int64_t n, const int64_t *source_labels, const double *directions, const double *distances,
@@ -1236,7 +1249,6 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             HostState hs;
             if ((rc = download(h, hs)) != E_OK) break;
             const Scalars keep = h->sc_host;
-            free_all(h);
             h->uploaded = false;
             if ((rc = upload(h, hs, keep.maxradius, keep.max_time_step, false)) != E_OK) break;
             Scalars &sc = h->sc_host;
@@ -1460,12 +1472,11 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     const int reps = repeats > 0 ? repeats : 1;
-    k_search<<<(int)n, kSearchThreads, 0, h->stream>>>(h->d, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist, h->sweep_res);  // warm-up
+    TRY(search_kernels(h, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist, h->sweep_res));  // warm-up
     CK(cudaEventRecord(e0, h->stream));
-    for (int r = 0; r < reps; r++)
-        k_search<<<(int)n, kSearchThreads, 0, h->stream>>>(h->d, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist, h->sweep_res);
+    for (int r = 0; r < reps; r++) TRY(search_kernels(h, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist, h->sweep_res));
     CK(cudaEventRecord(e1, h->stream));
-    h->launches += reps + 2;
+    h->launches += 1;
     CK(cudaMemsetAsync(h->stats_dev, 0, sizeof(double) * 4, h->stream));
     k_sweep_summary<<<std::min(1024, div_up(n, 256)), 256, 0, h->stream>>>(h->sweep_res, h->sweep_dist, (int)n, h->stats_dev);
     double out[4];

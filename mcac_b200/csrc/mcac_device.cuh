@@ -65,6 +65,7 @@ struct DevState {
     int *label_of_slot, *slot_of_label;
     // ---- Verlet cells
     int *cell_start, *cell_fill, *cell_items;
+    double4 *cell_posr;  // (x, y, z, rmax) of cell_items[i], i.e. the aggregate bounding spheres in cell order (rebuilt with the cells)
     // ---- pick table (sorted 1/dt weights)
     int *sorted_slot;
     double *cum, *keys;

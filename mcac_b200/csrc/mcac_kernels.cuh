@@ -129,9 +129,9 @@ __global__ void k_labels_to_slots(DevState d, int nq, const long long *labels, i
 //  phase 3: the suspects are ranked by (d_b, key) — the multimap order — and scanned with the reference's
 //           two early breaks, so zero-distance / stale-rmax corner cases resolve exactly as on the CPU.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSearchThreads) k_search(DevState d, int nq, const int *__restrict__ q_slot,
-                                                           const double *__restrict__ q_dir, const double *__restrict__ q_dist,
-                                                           SearchResult *__restrict__ out) {
+__device__ __forceinline__ void search_wide_one(const DevState &d, int q, const int *__restrict__ q_slot,
+                                                const double *__restrict__ q_dir, const double *__restrict__ q_dist,
+                                                SearchResult *__restrict__ out) {
     __shared__ int seg_beg[kSearchThreads];
     __shared__ int seg_pre[kSearchThreads + 1];
     __shared__ int warp_sums[32];
@@ -143,8 +143,6 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevState d, int nq, c
     __shared__ int c_order[kCandCap];
     __shared__ int s_count, s_nb;
 
-    const int q = blockIdx.x;
-    if (q >= nq) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSearchThreads >> 5;
     const int slot = q_slot[q];
     SearchResult res;
@@ -281,6 +279,213 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevState d, int nq, c
         out[q] = res;
     }
 }
+// wide form: one CTA per listed query (the searches the group kernel hands over: > kGroupCap eligible suspects or
+// aggregate pairs with many sphere pairs); list == nullptr runs every query (debug / comparison)
+__global__ void __launch_bounds__(kSearchThreads) k_search_wide(DevState d, int nq, const int *__restrict__ list, const int *__restrict__ count,
+                                                                const int *__restrict__ q_slot, const double *__restrict__ q_dir,
+                                                                const double *__restrict__ q_dist, SearchResult *__restrict__ out) {
+    const int n = list ? *count : nq;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        search_wide_one(d, list ? list[e] : e, q_slot, q_dir, q_dist, out);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (main form) — one GROUP of G lanes (a quarter, half or whole warp) per query; no block-level barriers, no
+// shared-memory atomics.  Same three phases and the same visiting order as above:
+//  phase 1: the group's lanes take the (i, j) rows of the Verlet range, scan their lengths with shuffles and sweep
+//           the concatenated candidate list G at a time.  The bounding spheres are read from `cell_posr`, a copy of
+//           (x, y, z, rmax) laid out in CELL ORDER by K2, so the candidates of a row are one contiguous 32-byte-vector
+//           stream instead of a gather over the aggregate table.
+//  phase 3 before phase 2: the eligible suspects (<= kGroupCap) are ranked in the multimap order first, then the
+//           sphere-sphere sweeps run in that order with the reference's two early breaks — suspects the reference
+//           never examines are never swept.
+// Queries whose suspect list overflows or whose aggregate pairs are large are appended to `wide_list`.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGroupCap = 32;
+constexpr long long kGroupMaxPairs = 4096;
+template <int G>
+__device__ __forceinline__ void group_argmin(double &dmin, long long &idx, unsigned gmask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(gmask, dmin, o);
+        const long long oi = __shfl_xor_sync(gmask, idx, o);
+        if (od < dmin || (od == dmin && oi < idx)) { dmin = od; idx = oi; }
+    }
+}
+template <int G>
+__global__ void __launch_bounds__(kSearchThreads) k_search_group(DevState d, int nq, const int *__restrict__ q_slot,
+                                                                 const double *__restrict__ q_dir, const double *__restrict__ q_dist,
+                                                                 SearchResult *__restrict__ out, int *__restrict__ wide_list,
+                                                                 int *__restrict__ wide_count, int *__restrict__ next_count) {
+    constexpr int GPB = kSearchThreads / G;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+    __shared__ int c_slot[GPB][kGroupCap];
+    __shared__ double c_db[GPB][kGroupCap];
+    __shared__ unsigned long long c_key[GPB][kGroupCap];
+    __shared__ unsigned char c_order[GPB][kGroupCap];
+    const int g = threadIdx.x / G, gl = threadIdx.x % G;
+    const int q = blockIdx.x * GPB + g;
+    if (q >= nq) return;  // whole groups leave together
+    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+    const unsigned lane_lt = (1u << (threadIdx.x & 31)) - 1u;
+    const int slot = q_slot[q];
+    SearchResult res;
+    res.distance = INFINITY;
+    res.moving_slot = res.other_slot = res.other_agg = -1;
+    res.n_bounding = 0;
+    res.n_sphere_pairs = 0;
+    res.status = 0;
+    res.pad = 0;
+    if (slot < 0) {
+        if (gl == 0) { res.status = 3; out[q] = res; }  // VerletError
+        return;
+    }
+    const Scalars &sc = *d.sc;
+    const double box = sc.box_length;
+    const int n_div = d.n_div;
+    const double4 me = d.a_posr[slot];
+    const double dist = q_dist[q];
+    const double dx = q_dir[3 * q], dy = q_dir[3 * q + 1], dz = q_dir[3 * q + 2];
+    const CellRange rg = verlet_range(me.x, me.y, me.z, dist * dx, dist * dy, dist * dz, me.w + sc.maxradius, n_div, box);
+    const int ni = rg.hi[0] - rg.lo[0] + 1, nj = rg.hi[1] - rg.lo[1] + 1, nk = rg.hi[2] - rg.lo[2] + 1;
+
+    // ---- phase 1
+    const int ks = wrap_cell(rg.lo[2], n_div);
+    const bool wraps = ks + nk > n_div;
+    const int nseg = ni * nj * (wraps ? 2 : 1);
+    int m_all = 0, nb = 0;
+    for (int seg0 = 0; seg0 < nseg; seg0 += G) {
+        int len = 0, beg = 0;
+        const int s = seg0 + gl;
+        if (s < nseg) {
+            const int row = wraps ? (s >> 1) : s;
+            const int part = wraps ? (s & 1) : 0;
+            const int ii = wrap_cell(rg.lo[0] + row / nj, n_div), jj = wrap_cell(rg.lo[1] + row % nj, n_div);
+            const int base = (ii * n_div + jj) * n_div;
+            int ka, kb;  // inclusive wrapped k span of this segment
+            if (!wraps) { ka = ks; kb = ks + nk - 1; }
+            else if (part == 0) { ka = ks; kb = n_div - 1; }
+            else { ka = 0; kb = nk - (n_div - ks) - 1; }
+            beg = d.cell_start[base + ka];
+            len = d.cell_start[base + kb + 1] - beg;
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const int t = __shfl_up_sync(gmask, incl, o, G);
+            if (gl >= o) incl += t;
+        }
+        const int excl = incl - len;
+        const int total = __shfl_sync(gmask, incl, G - 1, G);
+        for (int f0 = 0; f0 < total; f0 += G) {
+            const int f = f0 + gl;
+            int L = 0;  // last segment whose exclusive prefix <= f
+#pragma unroll
+            for (int step = G / 2; step > 0; step >>= 1) {
+                const int t = __shfl_sync(gmask, excl, L + step, G);
+                if (t <= f) L += step;
+            }
+            const int sb = __shfl_sync(gmask, beg, L, G), se = __shfl_sync(gmask, excl, L, G);
+            bool elig = false;
+            double db = 0.;
+            int o = -1;
+            if (f < total) {
+                const int idx = sb + (f - se);
+                o = d.cell_items[idx];
+                if (o != slot) {
+                    const double4 oa = d.cell_posr[idx];
+                    db = pair_contact_distance(me.x, me.y, me.z, me.w, oa.x, oa.y, oa.z, oa.w, dx, dy, dz, dist, box);
+                    nb++;
+                    elig = db < dist;
+                }
+            }
+            const unsigned bal = __ballot_sync(gmask, elig) & gmask;
+            if (elig) {
+                const int pos = m_all + __popc(bal & lane_lt);
+                if (pos < kGroupCap) {
+                    const int r0 = range_rank(d.a_cx[o], rg.lo[0], rg.hi[0], n_div);
+                    const int r1 = range_rank(d.a_cy[o], rg.lo[1], rg.hi[1], n_div);
+                    const int r2 = range_rank(d.a_cz[o], rg.lo[2], rg.hi[2], n_div);
+                    const unsigned long long cell_rank = (unsigned long long)((r0 * nj + r1) * (long long)nk + r2);
+                    c_slot[g][pos] = o;
+                    c_db[g][pos] = db;
+                    c_key[g][pos] = (cell_rank << 32) | (unsigned)o;
+                }
+            }
+            m_all += __popc(bal);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) nb += __shfl_xor_sync(gmask, nb, o);
+    bool wide = m_all > kGroupCap;
+    const int m = wide ? 0 : m_all;
+    __syncwarp(gmask);
+
+    // ---- phase 3 first: rank in multimap order (bounding distance, then cell scan rank, then label)
+    for (int t = gl; t < m; t += G) {
+        const double db = c_db[g][t];
+        const unsigned long long key = c_key[g][t];
+        int rank = 0;
+        for (int u = 0; u < m; u++) {
+            const double du = c_db[g][u];
+            rank += (du < db || (du == db && c_key[g][u] < key)) ? 1 : 0;
+        }
+        c_order[g][rank] = (unsigned char)t;
+    }
+    __syncwarp(gmask);
+
+    // ---- phase 2 in that order, with the reference's two breaks (aggregat_list.cpp:459-482)
+    const int n_src = d.a_n[slot], off_src = d.a_off[slot];
+    double closest = INFINITY;
+    int who = -1;
+    long long who_pair = 0, examined = 0;
+    for (int r = 0; r < m; r++) {
+        const int t = c_order[g][r];
+        if (closest <= 0.) break;
+        if (closest < c_db[g][t]) break;
+        const int o = c_slot[g][t];
+        const int n_o = d.a_n[o], off_o = d.a_off[o];
+        const long long npairs = (long long)n_src * n_o;
+        if (npairs > kGroupMaxPairs) { wide = true; break; }
+        double best = INFINITY;
+        long long best_p = npairs;
+        if (npairs == 1) {  // monomer against monomer: every lane evaluates the same pair
+            const double4 a = d.s_posr[off_src];
+            const double4 b = d.s_posr[off_o];
+            best = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+            best_p = 0;
+        } else {
+            for (long long p = gl; p < npairs; p += G) {
+                const int i = (int)(p / n_o), j = (int)(p - (long long)i * n_o);
+                const double4 a = d.s_posr[off_src + i];
+                const double4 b = d.s_posr[off_o + j];
+                const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+                if (c < best) { best = c; best_p = p; }
+            }
+            group_argmin<G>(best, best_p, gmask);
+        }
+        examined += npairs;
+        if (best < closest) { closest = best; who = t; who_pair = best_p; }
+    }
+    if (gl != 0) return;
+    if (wide) {
+        wide_list[atomicAdd(wide_count, 1)] = q;
+        return;
+    }
+    res.n_bounding = nb;
+    res.n_sphere_pairs = examined;
+    if (who >= 0) {
+        const int o = c_slot[g][who];
+        const int n_o = d.a_n[o];
+        res.distance = closest;
+        res.moving_slot = off_src + (int)(who_pair / n_o);
+        res.other_slot = d.a_off[o] + (int)(who_pair % n_o);
+        res.other_agg = o;
+    }
+    out[q] = res;
+}
 
 // ------------------------------------------------------------------------------------------------
 // K2 — Verlet cell list by counting sort (replaces Verlet ctor/add/remove, verlet.cpp:26-51, and
@@ -297,8 +502,9 @@ __global__ void k_cell_scatter(DevState d) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= d.sc->n_agg_slots || !d.a_alive[s]) return;
     const int c = (d.a_cx[s] * d.n_div + d.a_cy[s]) * d.n_div + d.a_cz[s];
-    const int pos = atomicAdd(&d.cell_fill[c], 1);
-    d.cell_items[d.cell_start[c] + pos] = s;
+    const int pos = d.cell_start[c] + atomicAdd(&d.cell_fill[c], 1);
+    d.cell_items[pos] = s;
+    d.cell_posr[pos] = d.a_posr[s];  // bounding sphere in cell order: K1 streams it
 }
 // generic 3-phase exclusive scan of ints (deterministic): in[0..n) -> out[0..n], out[n] = total
 constexpr int kScanBlock = 1024;
@@ -2146,6 +2352,105 @@ __global__ void __launch_bounds__(256) k_sweep_summary(const SearchResult *res, 
         atomicAdd(&out[1], sum);
         atomicAdd(&out[2], ps);
         atomicAdd(&out[3], pb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// State boundary (mcac_gpu_upload_state / mcac_gpu_download_state): the host keeps the reference's layout
+// (field-major SoA in creation / label order, include/constants.hpp:34-69; ordered `myspheres` as CSR).  The raw
+// arrays cross PCIe once, as they are; the re-layout into the aggregate-major pool (and back) is done here, in HBM.
+// ------------------------------------------------------------------------------------------------
+struct HostLayout {  // device staging copy of the host arrays (all int64 / double, host layout)
+    long long n_sph, n_agg;
+    double *sph;                 // 9 x n_sph
+    long long *sph_label;        // n_sph (download only)
+    long long *sph_charge;       // n_sph
+    double *agg;                 // 21 x n_agg
+    long long *agg_n;            // n_agg (download only)
+    long long *agg_charge;       // n_agg
+    long long *agg_cells;        // 3 x n_agg
+    long long *offsets;          // n_agg + 1
+    long long *members;          // n_sph
+    double *per_member;          // 3 x n_sph
+};
+__global__ void __launch_bounds__(256) k_upload_spheres(DevState d, HostLayout s) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.n_sph) return;
+    const long long id = s.members[k], n = s.n_sph;
+    d.s_posr[k] = make_double4(s.sph[id], s.sph[n + id], s.sph[2 * n + id], s.sph[3 * n + id]);
+    d.s_relv[k] = make_double4(s.sph[6 * n + id], s.sph[7 * n + id], s.sph[8 * n + id], s.sph[4 * n + id]);
+    d.s_surf[k] = s.sph[5 * n + id];
+    d.s_veff[k] = s.per_member[k];
+    d.s_seff[k] = s.per_member[n + k];
+    d.s_dcen[k] = s.per_member[2 * n + k];
+    d.s_id[k] = (int)id;
+    d.s_charge[k] = (int)s.sph_charge[id];
+    d.slot_of_id[id] = (int)k;
+}
+__global__ void __launch_bounds__(256) k_upload_aggregates(DevState d, HostLayout s, double density) {
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= s.n_agg) return;
+    const long long m = s.n_agg;
+    const double *A = s.agg;
+    d.a_posr[a] = make_double4(A[7 * m + a], A[8 * m + a], A[9 * m + a], A[4 * m + a]);
+    d.a_rg[a] = A[a]; d.a_fagg[a] = A[m + a]; d.a_lpm[a] = A[2 * m + a]; d.a_ts[a] = A[3 * m + a];
+    d.a_vol[a] = A[5 * m + a]; d.a_surf[a] = A[6 * m + a];
+    d.a_rx[a] = A[10 * m + a]; d.a_ry[a] = A[11 * m + a]; d.a_rz[a] = A[12 * m + a]; d.a_ptime[a] = A[13 * m + a];
+    d.a_dp[a] = A[14 * m + a]; d.a_dgdp[a] = A[15 * m + a]; d.a_ovl[a] = A[16 * m + a]; d.a_cn[a] = A[17 * m + a];
+    d.a_dm[a] = A[19 * m + a]; d.a_ch[a] = A[20 * m + a];
+    const long long o = s.offsets[a], n = s.offsets[a + 1] - o;
+    d.a_bulk[a] = density;
+    d.a_alpha[a] = 1.0 / static_cast<double>(n);
+    d.a_n[a] = (int)n;
+    d.a_off[a] = (int)o;
+    d.a_cx[a] = (int)s.agg_cells[a]; d.a_cy[a] = (int)s.agg_cells[m + a]; d.a_cz[a] = (int)s.agg_cells[2 * m + a];
+    d.a_charge[a] = (int)s.agg_charge[a];
+    d.a_alive[a] = 1;
+    d.label_of_slot[a] = (int)a;
+    d.slot_of_label[a] = (int)a;
+}
+__global__ void __launch_bounds__(256) k_download_counts(DevState d, int n_agg, int *cnt) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n_agg) cnt[l] = d.a_n[d.slot_of_label[l]];
+}
+// one warp per label: aggregate row by lane 0, its spheres (a contiguous block of the pool) by all lanes
+__global__ void __launch_bounds__(256) k_download_state(DevState d, HostLayout s, const int *off_of_label) {
+    const long long l = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= s.n_agg) return;
+    const long long m = s.n_agg, ns = s.n_sph;
+    const int slot = d.slot_of_label[l];
+    const int n = d.a_n[slot], o = d.a_off[slot];
+    const long long off = off_of_label[l];
+    if (lane == 0) {
+        double *A = s.agg;
+        const double4 p = d.a_posr[slot];
+        A[l] = d.a_rg[slot]; A[m + l] = d.a_fagg[slot]; A[2 * m + l] = d.a_lpm[slot]; A[3 * m + l] = d.a_ts[slot];
+        A[4 * m + l] = p.w; A[5 * m + l] = d.a_vol[slot]; A[6 * m + l] = d.a_surf[slot];
+        A[7 * m + l] = p.x; A[8 * m + l] = p.y; A[9 * m + l] = p.z;
+        A[10 * m + l] = d.a_rx[slot]; A[11 * m + l] = d.a_ry[slot]; A[12 * m + l] = d.a_rz[slot]; A[13 * m + l] = d.a_ptime[slot];
+        A[14 * m + l] = d.a_dp[slot]; A[15 * m + l] = d.a_dgdp[slot]; A[16 * m + l] = d.a_ovl[slot]; A[17 * m + l] = d.a_cn[slot];
+        A[18 * m + l] = 0.; A[19 * m + l] = d.a_dm[slot]; A[20 * m + l] = d.a_ch[slot];
+        s.agg_n[l] = n;
+        s.agg_charge[l] = d.a_charge[slot];
+        s.agg_cells[l] = d.a_cx[slot]; s.agg_cells[m + l] = d.a_cy[slot]; s.agg_cells[2 * m + l] = d.a_cz[slot];
+        s.offsets[l] = off;
+        if (l == m - 1) s.offsets[m] = off + n;
+    }
+    if (off + n > ns) return;  // inconsistent membership: reported by the host from the scan total
+    for (int k = lane; k < n; k += 32) {
+        const int t = o + k;
+        const long long id = d.s_id[t];
+        const double4 p = d.s_posr[t], r = d.s_relv[t];
+        s.sph[id] = p.x; s.sph[ns + id] = p.y; s.sph[2 * ns + id] = p.z; s.sph[3 * ns + id] = p.w;
+        s.sph[4 * ns + id] = r.w; s.sph[5 * ns + id] = d.s_surf[t];
+        s.sph[6 * ns + id] = r.x; s.sph[7 * ns + id] = r.y; s.sph[8 * ns + id] = r.z;
+        s.sph_label[id] = l;
+        s.sph_charge[id] = d.s_charge[t];
+        s.members[off + k] = id;
+        s.per_member[off + k] = d.s_veff[t];
+        s.per_member[ns + off + k] = d.s_seff[t];
+        s.per_member[2 * ns + off + k] = d.s_dcen[t];
     }
 }
 

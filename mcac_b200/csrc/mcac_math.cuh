@@ -58,6 +58,18 @@ MCAC_HD bool spheres_in_contact(double ax, double ay, double az, double ra, doub
     return (d2 - rc <= kContactEpsilon);
 }
 
+// fmod(x, box) for box > 0, bit for bit: fmod is exact, so is x -/+ box on box <= |x| < 2 box (Sterbenz), and the sign of a
+// zero result follows x as in fmod.  Sphere coordinates stay within a box length of the origin, so the libm loop is rare.
+MCAC_HD double fmod_box(double x, double box) {
+    const double ax = fabs(x);
+    if (ax < box) return x;
+    if (ax < 2 * box) {
+        const double r = (x < 0) ? x + box : x - box;
+        return (r == 0.) ? ((x < 0) ? -0. : 0.) : r;
+    }
+    return fmod(x, box);
+}
+
 // --------------------------------------------------------------------------------------------------
 // THE pair test (K1 inner op): distance the sphere (p1, r1) can travel along `dir` (|dir| = 1, at most
 // `dist`) before touching sphere (p2, r2) or one of its periodic images; +inf if it never does.
@@ -83,10 +95,11 @@ MCAC_HD double pair_contact_distance(double p1x, double p1y, double p1z, double 
         const double base = lo - rsum;
         const double end = hi + rsum;
         zone[l] = end - base;
-        double w = fmod(p2[l] - base, box);
+        double w = fmod_box(p2[l] - base, box);
         if (w < 0) w += box;
         p2[l] = w + base;
-        nper[l] = static_cast<int>(floor(zone[l] / box));
+        // floor(zone / box): a quotient of 0 < zone < box rounds to at most 1 - 2^-53, so the division is only needed beyond
+        nper[l] = (zone[l] >= 0. && zone[l] < box) ? 0 : static_cast<int>(floor(zone[l] / box));
     }
     double res = INFINITY;
     const double endx = p1[0] + disp[0], endy = p1[1] + disp[1], endz = p1[2] + disp[2];
