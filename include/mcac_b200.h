@@ -159,6 +159,10 @@ int mcac_gpu_rand(mcac_gpu *h, int64_t n, int32_t *out);
 int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record *records, int64_t n_records, mcac_run_report *report);
 
 int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_report *report);
+/* Times one kernel of the path on the resident state (CUDA events on the handle's stream, `reps` launches after one warm-up):
+ * which = 0 K2 cell rebuild, 1 K8 growth (all spheres), 2 update_partial (all aggregates), 3 full update, 4 K9 event pipeline with
+ * sort, 5 without sort, 6 100 grid barriers at K9's launch shape, 7 K10 RNG fill, 8 K11 statistics.  units = items per launch. */
+int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_per_launch, int64_t *units);
 /* profile != 0: mcac_gpu_run brackets its K1 / commit launches with CUDA events (reported in mcac_run_report) */
 int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile);
 

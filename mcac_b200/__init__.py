@@ -231,6 +231,14 @@ class Simulation:
         self._ck(self.L.mcac_gpu_search_sweep(self.h, n, repeats, C.byref(rep)))
         return rep.as_dict()
 
+    KERNELS = {"cells": 0, "grow": 1, "update_partial": 2, "update_full": 3, "event_sort": 4, "event_nosort": 5, "grid_barriers_x100": 6,
+               "rng_fill": 7, "morphology_stats": 8}
+
+    def kernel_bench(self, which: str, reps: int = 5) -> dict:
+        ms, units = C.c_double(), C.c_int64()
+        self._ck(self.L.mcac_gpu_kernel_bench(self.h, self.KERNELS[which], reps, C.byref(ms), C.byref(units)))
+        return {"kernel": which, "ms": ms.value, "units": units.value}
+
     def set_profile(self, on: bool = True):
         self._ck(self.L.mcac_gpu_set_profile(self.h, int(on)))
 

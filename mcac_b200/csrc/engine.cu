@@ -89,7 +89,8 @@ struct mcac_gpu {
     int *wide_list = nullptr, *wide_count = nullptr;  // queries handed from the group search kernel to the wide one
     long long wide_cap = 0;
     int wide_parity = 0;
-    int search_group = 8;     // lanes per query of K1 (4, 8, 16 or 32)
+    int search_group = -1;    // lanes per query of K1 (4, 8, 16, 32; 0 = wide kernel only; -1 = by launch size)
+    int search_min_blocks = 8;  // occupancy target (__launch_bounds__ min blocks) of the narrow-group kernels
     void *stage = nullptr;  // device staging of the host-layout arrays at the upload / download boundary
     size_t stage_bytes = 0;
 };
@@ -815,16 +816,22 @@ int search_kernels(mcac_gpu *h, int nq, const int *q_slot, const double *q_dir, 
     // two counters used alternately: each launch of the group kernel clears the one the NEXT search will use
     h->wide_parity ^= 1;
     int *count = h->wide_list + h->wide_cap + h->wide_parity, *next_count = h->wide_list + h->wide_cap + (h->wide_parity ^ 1);
-    switch (h->search_group) {
-    case 4: k_search_group<4><<<div_up(nq, kSearchThreads / 4), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
-    case 16: k_search_group<16><<<div_up(nq, kSearchThreads / 16), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
-    case 32: k_search_group<32><<<div_up(nq, kSearchThreads / 32), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
-    case 0: CK(cudaMemsetAsync(next_count, 0, sizeof(int), h->stream)); break;  // wide kernel only (comparison runs)
-    default: k_search_group<8><<<div_up(nq, kSearchThreads / 8), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count); break;
-    }
-    const int wide_grid = h->search_group == 0 ? nq : std::min(nq, 8 * h->n_sm);
-    k_search_wide<<<wide_grid, kSearchThreads, 0, h->stream>>>(h->d, nq, h->search_group == 0 ? nullptr : h->wide_list, count, q_slot, q_dir, q_dist, res);
-    h->launches += h->search_group == 0 ? 1 : 2;
+    // group width: wide groups for small launches (latency-bound: more lanes per query), narrow ones for big launches
+    // (throughput-bound: more queries in flight); MCAC_B200_SEARCH_GROUP / _MB override (0 = wide kernel only)
+    const int G = h->search_group >= 0 ? h->search_group : (nq <= 4096 ? 32 : 8);
+#define MCAC_LAUNCH_GROUP(GG, MB) \
+    k_search_group<GG, MB><<<div_up(nq, kSearchThreads / GG), kSearchThreads, 0, h->stream>>>(h->d, nq, q_slot, q_dir, q_dist, res, h->wide_list, count, next_count)
+    const int MB = h->search_min_blocks;
+    if (G == 0) CK(cudaMemsetAsync(next_count, 0, sizeof(int), h->stream));
+    else if (G == 4) { if (MB >= 8) MCAC_LAUNCH_GROUP(4, 8); else if (MB >= 6) MCAC_LAUNCH_GROUP(4, 6); else MCAC_LAUNCH_GROUP(4, 4); }
+    else if (G == 8) { if (MB >= 8) MCAC_LAUNCH_GROUP(8, 8); else if (MB >= 6) MCAC_LAUNCH_GROUP(8, 6); else MCAC_LAUNCH_GROUP(8, 4); }
+    else if (G == 16) { if (MB >= 8) MCAC_LAUNCH_GROUP(16, 8); else MCAC_LAUNCH_GROUP(16, 4); }
+    else MCAC_LAUNCH_GROUP(32, 4);
+#undef MCAC_LAUNCH_GROUP
+    const bool wide_only = G == 0;
+    const int wide_grid = wide_only ? nq : std::min(nq, 8 * h->n_sm);
+    k_search_wide<<<wide_grid, kSearchThreads, 0, h->stream>>>(h->d, nq, wide_only ? nullptr : h->wide_list, count, q_slot, q_dir, q_dist, res);
+    h->launches += wide_only ? 1 : 2;
     CK(cudaGetLastError());
     return E_OK;
 }
@@ -863,6 +870,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
+        if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
         cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, 0)
@@ -1107,6 +1115,7 @@ int mcac_gpu_update(mcac_gpu *h, int64_t label, int full) {
         CK(cudaStreamSynchronize(h->stream));
     }
     const int nblk = label >= 0 ? 1 : div_up(h->sc_host.n_agg_slots, 8);
+    if (label < 0) { k_update_small<<<div_up(h->sc_host.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, full, 0, 1); h->launches++; }
     k_update_all<<<nblk, 256, 0, h->stream>>>(h->d, full, slot);
     h->launches++;
     CK(cudaGetLastError());
@@ -1303,8 +1312,9 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         h->launches += growth ? 3 : 2;
         if (growth) {  // calcul.cpp:184-206 — the frequency test uses the counter BEFORE this step's bookkeeping
             const int full = (h->sc_host.n_iter_without_event % p.full_aggregate_update_frequency == 0) ? 1 : 0;
+            k_update_small<<<div_up(h->sc_host.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, full, p.individual_surf_reactions, 0);
             k_update_step<<<div_up(h->sc_host.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
-            h->launches++;
+            h->launches += 2;
         }
         if (p.with_nucleation) {  // calcul.cpp:208-220
             k_nucleate<<<1, kCommitThreads, 0, h->stream>>>(h->d, 0., 1);
@@ -1496,6 +1506,72 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
         report->kernel_ms = ms / reps;
     }
     return E_OK;
+}
+
+// Per-kernel timings on the resident state (bench.py's per-kernel roofline table; profiles/).  `which`:
+//  0 K2 cell list rebuild, 1 K8 growth of every sphere (dt = 0), 2 K6/K7 update_partial of every aggregate, 3 K5-K7 full update,
+//  4 K9 event pipeline with sort, 5 event pipeline without sort (labels + refresh + totals), 6 100 grid barriers at K9's launch shape,
+//  7 K10 RNG fill (kRngBuf draws), 8 K11 morphology statistics.
+// Growth / update rewrite derived fields from the resident radii (a replayed trajectory should not continue from this state).
+int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_out, int64_t *units_out) {
+    CK(cudaSetDevice(h->device));
+    if (!h->uploaded || reps < 1 || !ms_out) { h->err = "kernel_bench: bad arguments / no state"; return E_INPUT; }
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    const Scalars sc = h->sc_host;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int64_t units = 0;
+    int rc = E_OK;
+    for (int r = -1; r < reps && rc == E_OK; r++) {  // r == -1: warm-up
+        if (r == 0) CK(cudaEventRecord(e0, h->stream));
+        switch (which) {
+        case 0: h->cells_valid = false; rc = build_cells(h); units = sc.n_agg; break;
+        case 1: k_grow<<<div_up(sc.pool_top, 256), 256, 0, h->stream>>>(h->d, 0., -1); units = sc.n_sph; break;
+        case 2:
+        case 3:
+            k_update_small<<<div_up(sc.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, which == 3, 0, 1);
+            k_update_all<<<div_up(sc.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, which == 3, -1);
+            units = sc.n_agg;
+            break;
+        case 4: h->labels_valid = false; rc = event_pipeline(h, true, true, true); units = sc.n_agg; break;
+        case 5: h->labels_valid = false; rc = event_pipeline(h, true, true, false); units = sc.n_agg; break;
+        case 6: {
+            if (h->coop_blocks <= 0) { h->err = "kernel_bench: no cooperative launch"; rc = E_INPUT; break; }
+            int n = 100;
+            int *sink = nullptr;
+            void *args[] = {&n, &sink};
+            if (cudaLaunchCooperativeKernel((const void *)k_barrier_probe, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream) != cudaSuccess) rc = E_UNKNOWN;
+            units = n;
+            break;
+        }
+        case 7: {  // draws go to the staging buffer and the stream state is put back afterwards: the realization's stream is untouched
+            if ((rc = ensure_stage(h, sizeof(int) * (size_t)kRngBuf)) != E_OK) break;
+            cudaMemcpyAsync(h->stats_dev, h->d.rng, sizeof(GlibcRandState), cudaMemcpyDeviceToDevice, h->stream);
+            k_rng_fill<<<1, 32, 0, h->stream>>>(h->d.rng, (int *)h->stage, kRngBuf);
+            cudaMemcpyAsync(h->d.rng, h->stats_dev, sizeof(GlibcRandState), cudaMemcpyDeviceToDevice, h->stream);
+            units = kRngBuf;
+            break;
+        }
+        case 8: k_morphology_stats<<<std::min(1024, std::max(1, div_up(sc.n_agg_slots, 256))), 256, 0, h->stream>>>(h->d, 24, 2e-6, h->stats_dev); units = sc.n_agg; break;
+        default: h->err = "kernel_bench: unknown kernel"; rc = E_INPUT;
+        }
+    }
+    if (rc == E_OK) {
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_out = ms / reps;
+        if (units_out) *units_out = units;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->cells_valid = false;
+    h->pick_valid = false;
+    return rc;
 }
 
 }  // extern "C"

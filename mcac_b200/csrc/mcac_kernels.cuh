@@ -314,8 +314,64 @@ __device__ __forceinline__ void group_argmin(double &dmin, long long &idx, unsig
         if (od < dmin || (od == dmin && oi < idx)) { dmin = od; idx = oi; }
     }
 }
+struct GroupHit {
+    double closest;
+    int who;
+    long long who_pair, examined;
+};
+// phases 3 + 2 of one query for its group of G lanes; returns true when the query must go to the wide kernel
 template <int G>
-__global__ void __launch_bounds__(kSearchThreads) k_search_group(DevState d, int nq, const int *__restrict__ q_slot,
+__device__ __noinline__ bool group_sweep_suspects(const int *__restrict__ a_n, const int *__restrict__ a_off,
+                                                  const double4 *__restrict__ s_posr, int slot, int m, const int *c_slot, const double *c_db,
+                                                  const unsigned long long *c_key, unsigned char *c_order, double dx, double dy, double dz,
+                                                  double dist, double box, unsigned gmask, int gl, GroupHit &hit) {
+    __syncwarp(gmask);
+    // ---- phase 3 first: rank in multimap order (bounding distance, then cell scan rank, then label)
+    for (int t = gl; t < m; t += G) {
+        const double db = c_db[t];
+        const unsigned long long key = c_key[t];
+        int rank = 0;
+        for (int u = 0; u < m; u++) {
+            const double du = c_db[u];
+            rank += (du < db || (du == db && c_key[u] < key)) ? 1 : 0;
+        }
+        c_order[rank] = (unsigned char)t;
+    }
+    __syncwarp(gmask);
+    // ---- phase 2 in that order, with the reference's two breaks (aggregat_list.cpp:459-482)
+    const int n_src = a_n[slot], off_src = a_off[slot];
+    double closest = INFINITY;
+    int who = -1;
+    long long who_pair = 0, examined = 0;
+    for (int r = 0; r < m; r++) {
+        const int t = c_order[r];
+        if (closest <= 0.) break;
+        if (closest < c_db[t]) break;
+        const int o = c_slot[t];
+        const int n_o = a_n[o], off_o = a_off[o];
+        const long long npairs = (long long)n_src * n_o;
+        if (npairs > kGroupMaxPairs) return true;
+        double best = INFINITY;
+        long long best_p = npairs;
+        for (long long p = gl; p < npairs; p += G) {
+            const int i = (int)(p / n_o), j = (int)(p - (long long)i * n_o);
+            const double4 a = s_posr[off_src + i];
+            const double4 b = s_posr[off_o + j];
+            const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+            if (c < best) { best = c; best_p = p; }
+        }
+        group_argmin<G>(best, best_p, gmask);
+        examined += npairs;
+        if (best < closest) { closest = best; who = t; who_pair = best_p; }
+    }
+    hit.closest = closest;
+    hit.who = who;
+    hit.who_pair = who_pair;
+    hit.examined = examined;
+    return false;
+}
+template <int G, int kMinBlocks>
+__global__ void __launch_bounds__(kSearchThreads, kMinBlocks) k_search_group(DevState d, int nq, const int *__restrict__ q_slot,
                                                                  const double *__restrict__ q_dir, const double *__restrict__ q_dist,
                                                                  SearchResult *__restrict__ out, int *__restrict__ wide_list,
                                                                  int *__restrict__ wide_count, int *__restrict__ next_count) {
@@ -394,8 +450,8 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_group(DevState d, int
             if (f < total) {
                 const int idx = sb + (f - se);
                 o = d.cell_items[idx];
+                const double4 oa = d.cell_posr[idx];  // issued with the id load, not behind it
                 if (o != slot) {
-                    const double4 oa = d.cell_posr[idx];
                     db = pair_contact_distance(me.x, me.y, me.z, me.w, oa.x, oa.y, oa.z, oa.w, dx, dy, dz, dist, box);
                     nb++;
                     elig = db < dist;
@@ -420,68 +476,26 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_group(DevState d, int
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) nb += __shfl_xor_sync(gmask, nb, o);
     bool wide = m_all > kGroupCap;
-    const int m = wide ? 0 : m_all;
-    __syncwarp(gmask);
-
-    // ---- phase 3 first: rank in multimap order (bounding distance, then cell scan rank, then label)
-    for (int t = gl; t < m; t += G) {
-        const double db = c_db[g][t];
-        const unsigned long long key = c_key[g][t];
-        int rank = 0;
-        for (int u = 0; u < m; u++) {
-            const double du = c_db[g][u];
-            rank += (du < db || (du == db && c_key[g][u] < key)) ? 1 : 0;
-        }
-        c_order[g][rank] = (unsigned char)t;
-    }
-    __syncwarp(gmask);
-
-    // ---- phase 2 in that order, with the reference's two breaks (aggregat_list.cpp:459-482)
-    const int n_src = d.a_n[slot], off_src = d.a_off[slot];
-    double closest = INFINITY;
-    int who = -1;
-    long long who_pair = 0, examined = 0;
-    for (int r = 0; r < m; r++) {
-        const int t = c_order[g][r];
-        if (closest <= 0.) break;
-        if (closest < c_db[g][t]) break;
-        const int o = c_slot[g][t];
-        const int n_o = d.a_n[o], off_o = d.a_off[o];
-        const long long npairs = (long long)n_src * n_o;
-        if (npairs > kGroupMaxPairs) { wide = true; break; }
-        double best = INFINITY;
-        long long best_p = npairs;
-        if (npairs == 1) {  // monomer against monomer: every lane evaluates the same pair
-            const double4 a = d.s_posr[off_src];
-            const double4 b = d.s_posr[off_o];
-            best = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
-            best_p = 0;
-        } else {
-            for (long long p = gl; p < npairs; p += G) {
-                const int i = (int)(p / n_o), j = (int)(p - (long long)i * n_o);
-                const double4 a = d.s_posr[off_src + i];
-                const double4 b = d.s_posr[off_o + j];
-                const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
-                if (c < best) { best = c; best_p = p; }
-            }
-            group_argmin<G>(best, best_p, gmask);
-        }
-        examined += npairs;
-        if (best < closest) { closest = best; who = t; who_pair = best_p; }
-    }
+    GroupHit hit;
+    hit.closest = INFINITY;
+    hit.who = -1;
+    hit.who_pair = 0;
+    hit.examined = 0;
+    if (m_all > 0 && !wide)  // rare: kept out of line so that the sweep above keeps a small register footprint
+        wide = group_sweep_suspects<G>(d.a_n, d.a_off, d.s_posr, slot, m_all, c_slot[g], c_db[g], c_key[g], c_order[g], dx, dy, dz, dist, box, gmask, gl, hit);
     if (gl != 0) return;
     if (wide) {
         wide_list[atomicAdd(wide_count, 1)] = q;
         return;
     }
     res.n_bounding = nb;
-    res.n_sphere_pairs = examined;
-    if (who >= 0) {
-        const int o = c_slot[g][who];
+    res.n_sphere_pairs = hit.examined;
+    if (hit.who >= 0) {
+        const int o = c_slot[g][hit.who];
         const int n_o = d.a_n[o];
-        res.distance = closest;
-        res.moving_slot = off_src + (int)(who_pair / n_o);
-        res.other_slot = d.a_off[o] + (int)(who_pair % n_o);
+        res.distance = hit.closest;
+        res.moving_slot = d.a_off[slot] + (int)(hit.who_pair / n_o);
+        res.other_slot = d.a_off[o] + (int)(hit.who_pair % n_o);
         res.other_agg = o;
     }
     out[q] = res;
@@ -776,9 +790,144 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
         d.a_ts[slot] = mob.time_step;
         d.a_lpm[slot] = mob.lpm;
         d.a_dgdp[slot] = 2 * rg / dp;
-        atomic_max_positive_double(&d.sc->maxradius, rmax);
+        if (d.sc->maxradius < rmax) atomic_max_positive_double(&d.sc->maxradius, rmax);  // only ever grows: the plain read filters almost all
     }
     group_sync<kBlock>();
+}
+
+// The same update for a SMALL aggregate (n <= kSingleMax) by ONE thread: a population of monomers / dimers (growth mode updates
+// every aggregate every step, calcul.cpp:184-206) then runs one aggregate per lane instead of one per warp.  Every sum is taken
+// in the same order as agg_update (sequential `myspheres` order; the overlap statistics in the butterfly order of its warp
+// reduction), so both forms give bit-identical results.
+constexpr int kSingleMax = 8;
+__device__ void agg_update_single(const DevState &d, int slot, bool full, double box) {
+    const int off = d.a_off[slot], n = d.a_n[slot];
+    const int method = d.volsurf_method;
+    if (full) {
+        double v[7][kSingleMax];
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+#pragma unroll
+            for (int i = 0; i < kSingleMax; i++) v[k][i] = 0.;
+        for (int i = 0; i < n; i++) {
+            const double4 ri = d.s_relv[off + i];
+            const double r_i = d.s_posr[off + i].w;
+            const double s_i = d.s_surf[off + i];
+            double veff = ri.w, seff = s_i;
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                const double4 rj = d.s_relv[off + j];
+                const double r_j = d.s_posr[off + j].w;
+                const double ex = ri.x - rj.x, ey = ri.y - rj.y, ez = ri.z - rj.z;
+                const double dist = sqrt(ex * ex + ey * ey + ez * ez);
+                const double rs = r_i + r_j;
+                if (dist <= (1. + kCoordinationEpsilon) * rs) {
+                    const double c_ij = (rs - dist) / rs;
+                    v[0][i] += 1.;
+                    v[1][i] += c_ij;
+                    if (method == MCAC_VS_ALPHAS) {
+                        const double vp = pow(r_i, 3.) + pow(r_j, 3.);
+                        const double sp = r_i * r_i + r_j * r_j;
+                        v[5][i] += vp;
+                        v[6][i] += sp;
+                        v[2][i] += c_ij * sp;
+                        v[3][i] += (c_ij * c_ij) * vp;
+                        v[4][i] += pow(c_ij, 3.) * vp;
+                    } else if (method == MCAC_VS_CAPS) {
+                        double caps[4];
+                        if (i < j) {
+                            lens_caps(r_i, ri.w, s_i, r_j, rj.w, d.s_surf[off + j], dist, caps);
+                            veff = veff - caps[0];
+                            seff = seff - caps[2];
+                        } else {
+                            lens_caps(r_j, rj.w, d.s_surf[off + j], r_i, ri.w, s_i, dist, caps);
+                            veff = veff - caps[1];
+                            seff = seff - caps[3];
+                        }
+                    }
+                }
+            }
+            if (method == MCAC_VS_CAPS) {
+                veff = (veff < 0.0) ? 0.0 : veff;
+                seff = (seff < 0.0) ? 0.0 : seff;
+            }
+            d.s_veff[off + i] = veff;
+            d.s_seff[off + i] = seff;
+        }
+        double vals[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++)  // lane 0 of the xor-butterfly over lanes 0..7
+            vals[k] = ((v[k][0] + v[k][4]) + (v[k][2] + v[k][6])) + ((v[k][1] + v[k][5]) + (v[k][3] + v[k][7]));
+        double V = 0., S = 0.;
+        for (int i = 0; i < n; i++) {
+            V = V + d.s_veff[off + i];
+            S = S + d.s_seff[off + i];
+        }
+        double ovl = 0., cn = 0.;
+        const double intersections = vals[0];
+        if (intersections > 0.) {
+            ovl = vals[1] / intersections;
+            cn = intersections / static_cast<double>(n);
+            if (method == MCAC_VS_ALPHAS) {
+                const double c_s10 = vals[2] / vals[6], c_v20 = vals[3] / vals[5], c_v30 = vals[4] / vals[5];
+                const double min_cn = 2 * (1.0 - 1.0 / static_cast<double>(n));
+                const double extreme = d.a_alpha[slot];
+                V *= volume_alpha_correction(cn, c_v20, c_v30, min_cn, extreme);
+                S *= surface_alpha_correction(cn, c_s10, min_cn, extreme);
+            }
+        }
+        d.a_ovl[slot] = ovl;
+        d.a_cn[slot] = cn;
+        d.a_vol[slot] = V;
+        d.a_surf[slot] = S;
+        if (V <= 0 || S <= 0) d.sc->error = 8;  // VolSurfError, aggregat.cpp:427-429
+    }
+    // ---- update_partial
+    const double V = d.a_vol[slot];
+    double ax = 0., ay = 0., az = 0., ar = 0., av = 0.;
+    for (int i = 0; i < n; i++) {
+        const double4 rel = d.s_relv[off + i];
+        const double ve = d.s_veff[off + i];
+        ax += rel.x * ve;
+        ay += rel.y * ve;
+        az += rel.z * ve;
+        ar += d.s_posr[off + i].w;
+        av += rel.w;
+    }
+    const double cx = ax / V, cy = ay / V, cz = az / V;
+    const double dp = 2 * ar / static_cast<double>(n), vol_pp = av / static_cast<double>(n);
+    double rmax = 0., g0 = 0., g1 = 0.;
+    for (int i = 0; i < n; i++) {
+        const double4 rel = d.s_relv[off + i];
+        const double ex = rel.x - cx, ey = rel.y - cy, ez = rel.z - cz;
+        const double dc = sqrt(ex * ex + ey * ey + ez * ez);
+        d.s_dcen[off + i] = dc;
+        const double r = d.s_posr[off + i].w;
+        const double e = r + dc;
+        rmax = (rmax < e) ? e : rmax;
+        const double wgt = d.s_veff[off + i];
+        g0 = g0 + wgt * (dc * dc);
+        g1 = g1 + wgt * (r * r);
+    }
+    const double4 root = d.s_posr[off];
+    agg_store_position(d, slot, root.x + cx, root.y + cy, root.z + cz, box);
+    double4 a = d.a_posr[slot];
+    a.w = rmax;
+    d.a_posr[slot] = a;
+    d.a_rx[slot] = cx; d.a_ry[slot] = cy; d.a_rz[slot] = cz;
+    const double rg = sqrt(fabs((g0 + 3. / 5. * g1) / V));
+    d.a_rg[slot] = rg;
+    d.a_dp[slot] = dp;
+    double ch = d.a_ch[slot];
+    const Mobility mob = mobility_epilogue(d.gas, V, vol_pp, dp, &ch);
+    d.a_ch[slot] = ch;
+    d.a_bulk[slot] = mob.bulk_density;
+    d.a_fagg[slot] = mob.f_agg;
+    d.a_dm[slot] = mob.d_m;
+    d.a_ts[slot] = mob.time_step;
+    d.a_lpm[slot] = mob.lpm;
+    d.a_dgdp[slot] = 2 * rg / dp;
+    if (d.sc->maxradius < rmax) atomic_max_positive_double(&d.sc->maxradius, rmax);
 }
 
 // K4 — AggregatList::merge + Aggregate::merge + ListStorage::merge/remove (aggregat_list.cpp:367-410,
@@ -1509,15 +1658,26 @@ __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int i
     const Scalars &sc = *d.sc;
     if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
     if (individual && !sc.b_merged && slot != sc.p_slot) return;
+    if (d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], sc.box_length);
 }
-// K5-K7 over ALL aggregates (growth mode, calcul.cpp:184-206): one warp per aggregate
+// the small aggregates (n <= kSingleMax) of the same update: one aggregate per THREAD
+__global__ void __launch_bounds__(128) k_update_small(DevState d, int full, int individual, int all) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const Scalars &sc = *d.sc;
+    if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
+    if (!all && individual && !sc.b_merged && slot != sc.p_slot) return;
+    if (d.a_n[slot] > kSingleMax) return;
+    agg_update_single(d, slot, full != 0, sc.box_length);
+}
+// K5-K7 over ALL aggregates (growth mode, calcul.cpp:184-206): one warp per aggregate of more than kSingleMax spheres
 __global__ void __launch_bounds__(256) k_update_all(DevState d, int full, int only_slot) {
     __shared__ double scratch[8][kUpdateScratch / 4];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int slot = blockIdx.x * 8 + w;
     if (only_slot >= 0) { if (slot != 0) return; slot = only_slot; }
     if (slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
+    if (only_slot < 0 && d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], d.sc->box_length);
 }
 // single-aggregate entry points of the per-call C ABI
@@ -2452,6 +2612,13 @@ __global__ void __launch_bounds__(256) k_download_state(DevState d, HostLayout s
         s.per_member[ns + off + k] = d.s_seff[t];
         s.per_member[2 * ns + off + k] = d.s_dcen[t];
     }
+}
+
+// cost of the grid-wide barrier of the cooperative event kernel at its launch shape (diagnostic for K9's roofline)
+__global__ void __launch_bounds__(kEventThreads) k_barrier_probe(int n, int *sink) {
+    cgx::grid_group grid = cgx::this_grid();
+    for (int i = 0; i < n; i++) grid.sync();
+    if (sink && blockIdx.x == 0 && threadIdx.x == 0) *sink = n;
 }
 
 }  // namespace mcacb

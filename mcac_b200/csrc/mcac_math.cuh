@@ -134,19 +134,29 @@ MCAC_HD double pair_contact_distance(double p1x, double p1y, double p1z, double 
 struct CellRange {
     int lo[3], hi[3];
 };
+// floor(x / w) evaluated as the reference does (correctly rounded quotient, then floor), without the division in the common
+// case: x * inv_w differs from the rounded quotient by a few ulp, so away from an integer both floors agree.
+MCAC_HD double floor_div(double x, double w, double inv_w) {
+    const double q = x * inv_w;
+    const double fq = floor(q);
+    const double frac = q - fq;
+    if (fabs(q) < 1048576. && frac > 1e-6 && frac < 0.999999) return fq;
+    return floor(x / w);
+}
 MCAC_HD CellRange verlet_range(double sx, double sy, double sz, double vx, double vy, double vz, double reach, int n_div, double width) {
     const double src[3] = {sx, sy, sz};
     const double v[3] = {vx, vy, vz};
     CellRange r;
     const double nd = static_cast<double>(n_div);
+    const double inv_w = 1. / width;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         const double vp = (0. < v[a]) ? v[a] : 0.;  // std::max(direction, 0.)
         const double vm = (v[a] < 0.) ? v[a] : 0.;  // std::min(direction, 0.)
         const double p = src[a] + reach + vp;
         const double m = src[a] - reach + vm;
-        int b1 = static_cast<int>(floor(nd * m / width));
-        int b2 = static_cast<int>(floor(nd * p / width) + 1);
+        int b1 = static_cast<int>(floor_div(nd * m, width, inv_w));
+        int b2 = static_cast<int>(floor_div(nd * p, width, inv_w) + 1);
         if (b2 - b1 >= n_div) {
             b1 = 0;
             b2 = n_div - 1;
