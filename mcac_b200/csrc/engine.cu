@@ -46,6 +46,13 @@ struct mcac_gpu {
     mcac_params prm{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: the Verlet cell rebuild runs beside the event kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int *block_sums2 = nullptr;
+    bool cells_on_side = false;
+    int force_sort_fail = 0;    // MCAC_B200_FORCE_SORT_FAIL=k: every k-th device sort reports failure (exercises the fallback)
+    long long sort_calls = 0;
+    bool overlap = true;        // MCAC_B200_NO_OVERLAP=1 serialises the rebuild and synchronises after every event kernel  // a rebuild is in flight on stream2 (joined before the next search)
     std::string err;
     DevState d{};
     DevState alt{};  // alternate sphere buffers for pool compaction (only s_* pointers used)
@@ -193,16 +200,19 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     TRY(dev_alloc(h, &h->scan_tmp, scan_n));
     TRY(dev_alloc(h, &h->scan_out, scan_n));
     TRY(dev_alloc(h, &h->block_sums, scan_n / (kScanBlock * kScanItems) + 8));
+    TRY(dev_alloc(h, &h->block_sums2, scan_n / (kScanBlock * kScanItems) + 8));
     return E_OK;
 }
 
 // deterministic exclusive scan of n ints (in -> out[0..n], out[n] = total)
-int scan_ints(mcac_gpu *h, const int *in, int n, int *out) {
+int scan_ints(mcac_gpu *h, const int *in, int n, int *out, cudaStream_t st = nullptr, int *sums = nullptr) {
+    if (!st) st = h->stream;
+    if (!sums) sums = h->block_sums;
     const int per = kScanBlock * kScanItems;
     const int nb = std::max(1, div_up(n, per));
-    k_scan_partials<<<nb, kScanBlock, 0, h->stream>>>(in, n, h->block_sums);
-    k_scan_block_sums<<<1, 1024, 0, h->stream>>>(h->block_sums, nb);
-    k_scan_apply<<<nb, kScanBlock, 0, h->stream>>>(in, n, h->block_sums, nb, out);
+    k_scan_partials<<<nb, kScanBlock, 0, st>>>(in, n, sums);
+    k_scan_block_sums<<<1, 1024, 0, st>>>(sums, nb);
+    k_scan_apply<<<nb, kScanBlock, 0, st>>>(in, n, sums, nb, out);
     h->launches += 3;
     CK(cudaGetLastError());
     return E_OK;
@@ -233,19 +243,33 @@ int refresh_labels(mcac_gpu *h) {
 }
 
 // K2: counting sort of live aggregates into their stored Verlet cells
-int build_cells(mcac_gpu *h) {
+int build_cells(mcac_gpu *h, bool side = false) {
     if (h->cells_valid) return E_OK;
     DevState &d = h->d;
     const int n = h->sc_host.n_agg_slots;
-    CK(cudaMemsetAsync(d.cell_fill, 0, sizeof(int) * ((size_t)d.n_cells + 1), h->stream));
-    k_cell_count<<<div_up(n, 256), 256, 0, h->stream>>>(d);
+    cudaStream_t st = side ? h->stream2 : h->stream;
+    // side == true: the caller guarantees that the state the rebuild reads (positions, cells, liveness) is final, i.e. that the
+    // main stream was synchronised after the last kernel that wrote it
+    CK(cudaMemsetAsync(d.cell_fill, 0, sizeof(int) * ((size_t)d.n_cells + 1), st));
+    k_cell_count<<<div_up(n, 256), 256, 0, st>>>(d);
     h->launches++;
-    TRY(scan_ints(h, d.cell_fill, d.n_cells, d.cell_start));
-    CK(cudaMemsetAsync(d.cell_fill, 0, sizeof(int) * ((size_t)d.n_cells + 1), h->stream));
-    k_cell_scatter<<<div_up(n, 256), 256, 0, h->stream>>>(d);
+    TRY(scan_ints(h, d.cell_fill, d.n_cells, d.cell_start, st, side ? h->block_sums2 : h->block_sums));
+    CK(cudaMemsetAsync(d.cell_fill, 0, sizeof(int) * ((size_t)d.n_cells + 1), st));
+    k_cell_scatter<<<div_up(n, 256), 256, 0, st>>>(d);
     h->launches++;
     CK(cudaGetLastError());
+    if (side) {
+        CK(cudaEventRecord(h->ev_join, h->stream2));
+        h->cells_on_side = true;
+    }
     h->cells_valid = true;
+    return E_OK;
+}
+// the main stream waits for a rebuild that was forked to the side stream
+int join_cells(mcac_gpu *h) {
+    if (!h->cells_on_side) return E_OK;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    h->cells_on_side = false;
     return E_OK;
 }
 
@@ -359,7 +383,7 @@ int sort_time_steps(mcac_gpu *h, double factor) {
 // The per-event pipeline as ONE cooperative launch (k_event): labels, refresh / PhysicalModel::update, weights, replayed
 // introsort, cumulative table.  Falls back to the multi-launch form when cooperative launch is unavailable or when
 // introsort's depth limit is hit.
-int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, const double *factor = nullptr) {
+int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, const double *factor = nullptr, bool defer_sync = false) {
     if (h->coop_blocks <= 0 || h->prm.sort_order == MCAC_ORDER_HOST_STDSORT) {
         if (do_refresh || do_totals) { h->labels_valid = false; TRY(refresh_labels(h)); TRY(refresh_reduce(h)); TRY(pull_scalars(h)); }
         if (do_sort) TRY(sort_time_steps(h, factor ? *factor : h->sc_host.max_time_step));
@@ -381,13 +405,18 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
     a.local_span = h->sort_local_span;
     a.work = h->event_work;
+    a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
     const void *fn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
     CK(cudaLaunchCooperativeKernel(fn, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream));
     h->launches++;
-    TRY(pull_scalars(h));
     h->labels_valid = true;
+    if (defer_sync) {  // the caller reads the scalars after its next kernels and handles a failed sort (b_need == 99) there
+        if (do_sort) h->pick_valid = true;
+        return E_OK;
+    }
+    TRY(pull_scalars(h));
     if (do_sort) {
         if (h->sc_host.b_need == 99) {  // introsort's depth limit was hit: multi-launch path, which ends in libstdc++'s std::sort
             h->sc_host.b_need = 0;
@@ -837,6 +866,7 @@ int search_kernels(mcac_gpu *h, int nq, const int *q_slot, const double *q_dir, 
 }
 int search_launch(mcac_gpu *h, int nq) {
     TRY(build_cells(h));
+    TRY(join_cells(h));
     return search_kernels(h, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
 }
 }  // namespace
@@ -862,6 +892,9 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     CK(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaMallocHost((void **)&h->h_sc, sizeof(Scalars)));
     CK(cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)));
     fill_devstate_params(h);
@@ -869,6 +902,8 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (getenv("MCAC_B200_NO_OVERLAP")) h->overlap = false;
+        if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
@@ -903,6 +938,9 @@ int mcac_gpu_destroy(mcac_gpu *h) {
     for (void *p : {(void *)h->sweep_slot, (void *)h->sweep_dir, (void *)h->sweep_dist, (void *)h->sweep_res}) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return E_OK;
@@ -1237,7 +1275,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     CK(cudaEventRecord(ev0, h->stream));
     int64_t steps = 0, batches = 0, sorts = 0, dups = 0;
     int rc = E_OK;
-    bool fin = false, need_refresh = false;
+    bool fin = false, need_refresh = false, fallback_sorted = false;
     while (!speculative && steps < max_steps) {  // ---- general step: one MC step per iteration, calcul() order
         if (finished(h)) { fin = true; break; }
         const mcac_params &p = h->prm;
@@ -1342,15 +1380,19 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     }
     while (speculative && steps < max_steps) {
         if (finished(h)) { fin = true; break; }
-        if (h->sc_host.event || !h->pick_valid) {
+        if ((h->sc_host.event || !h->pick_valid) && !fallback_sorted) {
             // top of the loop after an event (calcul.cpp:72-101): duplication test, then sort_time_steps(max)
             if (h->sc_host.event && h->prm.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(h->prm.u_sg < 0.0)) {
                 if ((rc = duplicate(h)) != E_OK) break;
                 dups++;
             }
+            // the Verlet cell rebuild only reads positions: it runs on the side stream beside the event kernel
+            // (the last commit was synchronised by pull_scalars, so the side stream needs no fork event; the event kernel is
+            // submitted first and the rebuild's seven small launches fill in beside it)
             prof_begin(h, 2);
-            if ((rc = event_pipeline(h, need_refresh, need_refresh, true)) != E_OK) break;
+            if ((rc = event_pipeline(h, need_refresh, need_refresh, true, nullptr, h->overlap)) != E_OK) break;
             prof_end(h);
+            if (h->overlap && (rc = build_cells(h, true)) != E_OK) break;
             need_refresh = false;
             sorts++;
         }
@@ -1360,9 +1402,11 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if ((rc = ensure_rng(h, h->sc_host.rand_pos + 3LL * nq)) != E_OK) break;
         k_prepare_queries<<<div_up(nq, 128), 128, 0, h->stream>>>(h->d, nq, h->q_slot, h->q_dir, h->q_dist);
         h->launches++;
-        prof_begin(h, 3);
-        if ((rc = build_cells(h)) != E_OK) break;
-        prof_end(h);
+        if (!h->cells_valid) {
+            prof_begin(h, 3);
+            if ((rc = build_cells(h)) != E_OK) break;
+            prof_end(h);
+        }
         prof_begin(h, 0);
         if ((rc = search_launch(h, nq)) != E_OK) break;
         prof_end(h);
@@ -1382,6 +1426,16 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         h->launches++;
         if (cudaGetLastError() != cudaSuccess) { h->err = "k_commit launch failed"; rc = E_UNKNOWN; break; }
         if ((rc = pull_scalars(h)) != E_OK) break;
+        if (h->sc_host.b_need == 99) {  // the (unsynchronised) event kernel hit introsort's depth limit: k_commit did nothing;
+            h->sc_host.b_need = 0;      // redo the sort on the multi-launch path (ends in libstdc++'s std::sort), then the batch
+            if ((rc = push_scalars(h)) != E_OK) break;
+            h->sort_fallbacks++;
+            if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
+            h->pick_valid = true;
+            fallback_sorted = true;  // the event block of this step is done: go straight to the batch
+            continue;
+        }
+        fallback_sorted = false;
         batches++;
         h->cells_valid = false;
         if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
@@ -1395,6 +1449,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if (h->sc_host.b_stop_reason == STOP_FINISHED) { fin = true; break; }
         if (h->sc_host.b_committed == 0) { h->err = "batch made no progress"; rc = E_UNKNOWN; break; }
     }
+    if (join_cells(h) != E_OK && rc == E_OK) rc = E_UNKNOWN;
     if (rc == E_OK && need_refresh) {  // the call ended on a merge: refresh() / PhysicalModel::update belong to that step
         rc = event_pipeline(h, true, true, false);
         need_refresh = false;
@@ -1477,6 +1532,7 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
     }
     TRY(ensure_rng(h, h->sc_host.rand_pos + 3 * n));
     TRY(build_cells(h));
+    TRY(join_cells(h));
     k_prepare_queries<<<div_up(n, 128), 128, 0, h->stream>>>(h->d, (int)n, h->sweep_slot, h->sweep_dir, h->sweep_dist);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));

@@ -1030,6 +1030,10 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     const int n_agg_before = sc.n_agg;
     const long long steps_before = sc.steps_done, rand_before = sc.rand_pos, iter_before = sc.n_iter_without_event;
     const double dt_base = sc.max_time_step / sc.cum_total;  // AggregatList::get_time_step(max), aggregat_list.cpp:54-58
+    if (sc.b_need == 99) {  // the pick table of this batch comes from a sort that gave up (host redoes it): commit nothing
+        if (tid == 0) { sc.b_committed = 0; sc.b_stop_reason = STOP_NONE; sc.b_contact = 0; sc.b_merged = 0; }
+        return;
+    }
     if (tid == 0) { s_conf = nq; s_contact = nq; s_limit = nq; s_finished = 0; }
     for (int j = tid; j < nq; j += nth) {
         sh_slot[j] = b.q_slot[j];
@@ -1055,9 +1059,12 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     }
     for (int j = tid; j < nq; j += nth)
         if (sh_contact[j]) atomicMin(&s_contact, j);
-    // ---- conflicts with earlier movers of the batch: all (j, i<j) pairs, flattened over the block
-    for (int p = tid; p < nq * nq; p += nth) {
-        const int j = p / nq, i = p - j * nq;
+    __syncthreads();
+    // ---- conflicts with earlier movers of the batch: all (j, i<j) pairs up to the first contact (nothing behind it can be
+    // committed by this batch), flattened over the block
+    const int nj = min(min(nq, s_limit), s_contact + 1);
+    for (int p = tid; p < nj * nj; p += nth) {
+        const int j = p / nj, i = p - j * nj;
         if (i >= j || j >= s_conf) continue;  // benign race on s_conf: only ever shrinks the work
         const int sj = sh_slot[j], si = sh_slot[i];
         bool conflict = (si == sj);
@@ -2049,6 +2056,7 @@ struct EventArgs {
     int use_factor;       // sort_time_steps(factor) called with an explicit factor (per-call C ABI)
     double factor;
     int local_span;       // span (elements) below which block 0 finishes the sort alone
+    int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
     long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
 };
 namespace cgx = cooperative_groups;
@@ -2380,7 +2388,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         level++;
     }
     grid.sync();  // blocks that left the loop early wait here for block 0's local levels
-    fail = b.active[2] != 0;
+    fail = b.active[2] != 0 || a.force_fail != 0;
     if (fail) {  // the host falls back to libstdc++'s std::sort for this call
         if (gtid == 0) sc.b_need = 99;
         return;

@@ -268,6 +268,27 @@ def test_batch_width_does_not_change_the_trajectory():
     assert rb["batches"] < ra["batches"]
 
 
+@pytest.mark.parametrize("env", [{"MCAC_B200_FORCE_SORT_FAIL": "3"}, {"MCAC_B200_NO_OVERLAP": "1"}, {"MCAC_B200_SEARCH_GROUP": "0"},
+                                 {"MCAC_B200_SEARCH_GROUP": "4", "MCAC_B200_SEARCH_MB": "4"}])
+def test_execution_variants_do_not_change_the_trajectory(env, monkeypatch):
+    """Scheduling choices must be invisible in the results: a device sort that gives up (every 3rd one here) falls back to the
+    multi-launch sort and the batch is redone; serialised vs overlapped cell rebuild; wide-only vs narrow-group contact search."""
+    g = Golden("c3_small_seed42")
+    text = ini_text(merged_config(g.base, g.overrides))
+    base = Simulation(text)
+    r0, rec0 = base.run(15000, batch=256, records=15000)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    var = Simulation(text)
+    r1, rec1 = var.run(15000, batch=256, records=15000)
+    assert r0["steps"] == r1["steps"] and r0["events"] == r1["events"] and r0["events"] > 10
+    for f in INT_FIELDS + FP_FIELDS:
+        np.testing.assert_array_equal(rec0[f], rec1[f], err_msg=f)
+    s0, s1 = base.state(), var.state()
+    np.testing.assert_array_equal(s0["sphere_label"], s1["sphere_label"])
+    np.testing.assert_array_equal(s0["aggregates"]["rg"], s1["aggregates"]["rg"])
+
+
 def test_monodisperse_full_run_through_two_duplications():
     """C1 literal: 800 -> 6400 -> 51200 spheres, 1 000 452 steps, 1 688 merges — decisions via the golden digest."""
     g = Golden("monodisperse_seed42")
