@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     K, W = a.steps, max(a.warmup, 0)
@@ -201,38 +202,53 @@ def main():
     max_ms = float(t[0])
     value = float(tot[0]) / (max_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (K1 contact search), measured live with CUDA events on the handle's stream
+    # ---- rooflines, measured live with CUDA events on the handle's stream (profile mode of mcac_gpu_run)
     searches = sum(r["searches"] for r in reps)
     ps = sum(r["pair_tests_sphere"] for r in reps); pb = sum(r["pair_tests_bounding"] for r in reps)
     n_launch = max(1, sum(r["search_launches"] for r in reps))
     search_ms = sum(r["search_ms"] for r in reps)
     commit_ms = sum(r["commit_ms"] for r in reps)
-    # algorithmic bytes per search (restated for aggregate-level candidates): 36 B per bounding test
-    # (x,y,z,rmax + slot id), 32 B per sphere of the sphere-level sweep (moving + other), 48 B of result
-    alg_bytes = 36.0 * pb + 32.0 * (ps + searches) + 48.0 * searches
+    event_ms = sum(r["event_ms"] for r in reps)
+    n_event = max(1, sum(r["event_launches"] for r in reps))
     peaks = {}
     try:
         peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
-    roofline = {"kernel": "k_search (K1, speculative batch inside the MC loop)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "launches": n_launch, "avg_launch_us": 1e3 * search_ms / n_launch, "algorithmic_bytes_per_launch": alg_bytes / n_launch,
-                "share_of_step": search_ms / dev_ms if dev_ms else None, "commit_share_of_step": commit_ms / dev_ms if dev_ms else None,
-                "event_pipeline_share_of_step": sum(r["event_ms"] for r in reps) / dev_ms if dev_ms else None,
-                "cells_share_of_step": sum(r["cells_ms"] for r in reps) / dev_ms if dev_ms else None,
-                "avg_event_pipeline_us": 1e3 * sum(r["event_ms"] for r in reps) / max(1, sum(r["event_launches"] for r in reps)),
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    n_agg_now = reps[-1]["n_aggregates"]
+    # K9 (dominant kernel of the step): the per-event pipeline in one cooperative launch.  Algorithmic bytes per aggregate
+    # (one pass): liveness + label 12, refresh/totals 24, weight 8, sorted index 4, cumulative 8, pick slot 4 = 60 B.
+    k9_bytes = 60.0 * n_agg_now
+    k9_gbs = k9_bytes / (event_ms / n_event * 1e-3) / 1e9 if event_ms > 0 else 0.0
+    phases = ["reduce", "labels", "sort_init", "grid_levels", "local_levels", "leaves", "cumulative", "pick_table"]
+    sorts = max(1, sum(r["sorts"] for r in reps))
+    roofline = {"kernel": "k_event (K9: labels + refresh + totals + 1/dt weights + replayed introsort + cumulative table, one cooperative "
+                          "launch per merge)", "bound": "hbm", "achieved": k9_gbs, "peak": peak, "unit": "GB/s", "frac": k9_gbs / peak,
+                "traffic": None, "peak_source": peak_source, "launches": n_event, "avg_launch_us": 1e3 * event_ms / n_event,
+                "algorithmic_bytes_per_launch": k9_bytes, "share_of_step": event_ms / dev_ms if dev_ms else None,
+                "sort_levels_per_launch": sum(r["sort_levels"] for r in reps) / sorts,
+                "sort_span_elements_per_launch": sum(r["sort_span_elements"] for r in reps) / sorts,
+                "phase_us_per_launch": {p: sum(r["event_phase_cycles"][i] for r in reps) / 1965.0 / sorts for i, p in enumerate(phases)},
+                "note": "latency-bound, not bandwidth-bound: ~18 dependent introsort levels x 5 grid barriers per launch",
+                "commit_share_of_step": commit_ms / dev_ms if dev_ms else None, "search_share_of_step": search_ms / dev_ms if dev_ms else None,
                 "avg_commit_us": 1e3 * commit_ms / max(1, sum(r["commit_launches"] for r in reps)),
-                "avg_cells_us": 1e3 * sum(r["cells_ms"] for r in reps) / max(1, sum(r["cells_launches"] for r in reps))}
+                "avg_search_us": 1e3 * search_ms / n_launch}
+    # K1 inside the loop (speculative batches of <= 256 searches: launch-latency-bound), algorithmic bytes per search
+    # (SURVEY §8d restated for aggregate-level candidates): 36 B per bounding test (x,y,z,rmax + slot id), 32 B per sphere of the
+    # sphere-level sweep (moving + other), 48 B of result
+    alg_bytes = 36.0 * pb + 32.0 * (ps + searches) + 48.0 * searches
+    achieved = alg_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else 0.0
+    roofline_k1_inloop = {"kernel": "k_search_group<32> + k_search_wide (K1, speculative batch inside the MC loop)", "bound": "hbm",
+                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "launches": n_launch,
+                          "avg_launch_us": 1e3 * search_ms / n_launch, "algorithmic_bytes_per_launch": alg_bytes / n_launch}
     # the same kernel fed with one launch of ~3.5e5 independent searches (what an ensemble / wide speculation gives it)
     sw = sim.search_sweep(349000, repeats=3)
     sw_bytes = 36.0 * sw["pair_tests_bounding"] + 32.0 * (sw["pair_tests_sphere"] + sw["n_queries"]) + 48.0 * sw["n_queries"]
     sw_gbs = sw_bytes / (sw["kernel_ms"] * 1e-3) / 1e9
-    roofline_sweep = {"kernel": "k_search, one launch of %d searches" % sw["n_queries"], "bound": "hbm", "achieved": sw_gbs, "peak": peak,
-                      "unit": "GB/s", "frac": sw_gbs / peak, "traffic": None, "kernel_ms": sw["kernel_ms"],
+    roofline_sweep = {"kernel": "k_search_group<8> (K1), one launch of %d searches" % sw["n_queries"], "bound": "hbm", "achieved": sw_gbs,
+                      "peak": peak, "unit": "GB/s", "frac": sw_gbs / peak, "traffic": None, "kernel_ms": sw["kernel_ms"],
                       "pair_tests_per_sec": (sw["pair_tests_bounding"] + sw["pair_tests_sphere"]) / (sw["kernel_ms"] * 1e-3),
                       "searches_per_sec": sw["n_queries"] / (sw["kernel_ms"] * 1e-3)}
 
@@ -297,6 +313,18 @@ def main():
         ensemble = {"realizations": int(g.shape[0]), "n_agg": [int(x) for x in tail[:, 0]], "mean_npp": [float(x[1] / x[0]) for x in tail],
                     "mean_rg_nm": [float(1e9 * x[7] / x[0]) for x in tail]}
 
+    # ---- per-kernel table on the resident state (last: growth / update rewrite derived fields)
+    kernels = None
+    if rank == 0 and not a.no_kernel_table:
+        bytes_per_unit = {"cells": 88, "grow": 32, "update_partial": 208, "update_full": 208, "event_sort": 60, "event_nosort": 36,
+                          "grid_barriers_x100": 0, "rng_fill": 4, "morphology_stats": 28}
+        kernels = []
+        for k, bpu in bytes_per_unit.items():
+            r = sim.kernel_bench(k, reps=5)
+            gbs = r["units"] * bpu / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else None
+            kernels.append({"kernel": k, "us": 1e3 * r["ms"], "units": r["units"], "bytes_per_unit": bpu, "GBps": gbs,
+                            "frac_of_hbm_peak": gbs / peak if gbs else None})
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
@@ -315,7 +343,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "pair_tests_per_sec": float(tot[1]) / (max_ms * 1e-3), "mc_steps_timed": int(tot[0]),
                 "events_timed": sum(r["events"] for r in reps), "wall_ms_per_step": float(t[1]) / K, "init_placement_s": init_s,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[2]), "roofline": roofline, "roofline_sweep": roofline_sweep,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[2]), "roofline": roofline, "roofline_k1_inloop": roofline_k1_inloop,
+                "roofline_k1_sweep": roofline_sweep, "kernels": kernels,
                 "cpu_baseline": cpu_baseline, "ensemble_stats": ensemble}
         print(json.dumps(line))
     if world > 1:

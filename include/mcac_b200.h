@@ -84,6 +84,9 @@ typedef struct mcac_run_report {
     double event_ms, cells_ms;             /* per-event pipeline (k_event) / Verlet cell rebuild (K2) */
     int64_t event_launches, cells_launches;
     int64_t sort_span_elements, sort_levels; /* sum over sort levels of the active span (elements) / number of levels */
+    /* SM cycles of block 0 of the event kernel per phase: 0 reduce, 1 labels, 2 sort init, 3 grid-wide levels, 4 block-local levels,
+     * 5 leaf insertion sorts, 6 cumulative table, 7 pick table */
+    int64_t event_phase_cycles[8];
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction

@@ -61,10 +61,11 @@ class RunReport(C.Structure):
                                           "search_ms", "commit_ms"]] + \
                [(n, C.c_int64) for n in ["search_launches", "commit_launches"]] + \
                [(n, C.c_double) for n in ["event_ms", "cells_ms"]] + \
-               [(n, C.c_int64) for n in ["event_launches", "cells_launches", "sort_span_elements", "sort_levels"]]
+               [(n, C.c_int64) for n in ["event_launches", "cells_launches", "sort_span_elements", "sort_levels"]] + \
+               [("event_phase_cycles", C.c_int64 * 8)]
 
     def as_dict(self) -> dict:
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "event_phase_cycles" else getattr(self, n)) for n, _ in self._fields_}
 
 
 class SweepReport(C.Structure):

@@ -84,8 +84,9 @@ struct mcac_gpu {
     long long sort_levels = 0, sort_fallbacks = 0;
     int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
     int coop_bps = 1, sort_local_span = 4096;
+    int event_smem_cap = 0;   // shared-memory staging of the block-local sort levels (entries; 0 = levels stay in HBM/L2)
     long long *event_work = nullptr;
-    long long event_work_seen[2] = {0, 0};
+    long long event_work_seen[10] = {0};
     long long *part_ll = nullptr;
     double *part_d = nullptr;
     int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
@@ -405,11 +406,12 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
     a.local_span = h->sort_local_span;
     a.work = h->event_work;
+    a.smem_cap = h->event_smem_cap;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
     const void *fn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(h->coop_blocks), dim3(kEventThreads), args, 0, h->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(h->coop_blocks), dim3(kEventThreads), args, (size_t)h->event_smem_cap * kSortStageBytesPerEntry, h->stream));
     h->launches++;
     h->labels_valid = true;
     if (defer_sync) {  // the caller reads the scalars after its next kernels and handles a failed sort (b_need == 99) there
@@ -908,12 +910,26 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
-        cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, 0)
-                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, 0);
+        // block-local sort levels staged in shared memory: (local_span + 2) entries of 48 B, if the SM has room for them
+        h->event_smem_cap = 0;
+        if (!getenv("MCAC_B200_NO_SORT_SMEM")) {
+            int max_optin = 0;
+            cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+            const long long want = (long long)(h->sort_local_span + 2) * kSortStageBytesPerEntry;
+            if (want + 4096 <= max_optin / h->coop_bps) h->event_smem_cap = h->sort_local_span + 2;
+        }
+        const size_t dyn = (size_t)h->event_smem_cap * kSortStageBytesPerEntry;
+        const void *efn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
+        if (dyn > 0 && cudaFuncSetAttribute(efn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+            cudaGetLastError();
+            h->event_smem_cap = 0;
+        }
+        cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, (size_t)h->event_smem_cap * kSortStageBytesPerEntry)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, (size_t)h->event_smem_cap * kSortStageBytesPerEntry);
         if (coop && oe == cudaSuccess && occ > 0) h->coop_blocks = h->n_sm * std::min(occ, h->coop_bps);
         if (getenv("MCAC_B200_NO_COOP")) h->coop_blocks = 0;
-        TRY(dev_alloc_persistent(h, &h->event_work, 4));
-        CK(cudaMemset(h->event_work, 0, 4 * sizeof(long long)));
+        TRY(dev_alloc_persistent(h, &h->event_work, 16));
+        CK(cudaMemset(h->event_work, 0, 16 * sizeof(long long)));
         TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
         TRY(dev_alloc_persistent(h, &h->part_d, 4 * 4096));
     }
@@ -1485,11 +1501,12 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->max_time_step = sc.max_time_step;
         report->volume_fraction = sc.volume_fraction;
         report->device_ms = ms;
-        long long w[2] = {0, 0};
+        long long w[10] = {0};
         cudaMemcpy(w, h->event_work, sizeof(w), cudaMemcpyDeviceToHost);
         report->sort_span_elements = w[0] - h->event_work_seen[0];
         report->sort_levels = w[1] - h->event_work_seen[1];
-        h->event_work_seen[0] = w[0]; h->event_work_seen[1] = w[1];
+        for (int k = 0; k < 8; k++) report->event_phase_cycles[k] = w[2 + k] - h->event_work_seen[2 + k];
+        for (int k = 0; k < 10; k++) h->event_work_seen[k] = w[k];
     }
     prof_collect(h, report);
     return E_OK;

@@ -2056,10 +2056,13 @@ struct EventArgs {
     int use_factor;       // sort_time_steps(factor) called with an explicit factor (per-call C ABI)
     double factor;
     int local_span;       // span (elements) below which block 0 finishes the sort alone
+    int smem_cap;         // entries of dynamic shared memory per array available to the block-local levels (0 = none)
     int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
     long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
 };
 namespace cgx = cooperative_groups;
+extern __shared__ __align__(16) unsigned char dyn_smem[];
+constexpr int kSortStageBytesPerEntry = 48;  // wk, flags, pre (8 B each) + perm, segf, segl, tmp_a, tmp_b, cut (4 B each)
 
 __device__ __forceinline__ double block_sum_fixed(double v, double *sm /* >= 32 */) {  // fixed tree: deterministic
 #pragma unroll
@@ -2105,6 +2108,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const long long gtid = (long long)blk * nthr + tid, gsize = (long long)nblk * nthr;
     Scalars &sc = *d.sc;
     const int n_slots = sc.n_agg_slots;
+    // phase clocks of block 0 (SM cycles) accumulated into a.work[2 + k]: diagnostics for the K9 breakdown in profiles/
+    long long t_prev = clock64();
+    auto lap = [&](int k) { if (gtid == 0 && a.work) { const long long t = clock64(); a.work[2 + k] += t - t_prev; t_prev = t; } };
 
     // ---------------- phase A: live-slot count per chunk + refresh partials
     const int chunk_s = ((n_slots + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
@@ -2130,6 +2136,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         }
     }
     grid.sync();
+    lap(0);
     // ---------------- phase B: labels; every block derives n_agg / max / totals in the same fixed order
     int n_agg = 0;
     double factor = sc.max_time_step;
@@ -2184,8 +2191,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
         }
     }
-    if (!a.do_sort) return;
+    if (!a.do_sort) { lap(1); return; }
     grid.sync();
+    lap(1);
     // ---------------- phase C: weights in label order + sort state
     SortBufs b = a.sb;
     const int n = n_agg;
@@ -2234,14 +2242,51 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     int eblk = blk, enblk = nblk;
     long long etid = gtid, esize = gsize;
     auto barrier = [&]() { if (local) __syncthreads(); else grid.sync(); };
+    __shared__ int sh_act[8];
+    int *act = b.active;
+    bool staged = false;
+    int st_min = 0, st_max = 0;
+    SortBufs gb = b;
     grid.sync();  // first pivot + span in place
+    lap(2);
     while (active) {
         depth--;
-        const int amin = b.active[4 + 2 * (level & 1)], amax = b.active[5 + 2 * (level & 1)];
+        const int amin = act[4 + 2 * (level & 1)], amax = act[5 + 2 * (level & 1)];
         if (!local && amax - amin <= kSortLocal) {
             local = true;
             if (blk != 0) break;  // the other blocks wait at the barrier behind the loop
             eblk = 0; enblk = 1; etid = tid; esize = nthr;
+            if (tid < 8) sh_act[tid] = b.active[tid];
+            act = sh_act;
+            if (amax - amin + 2 <= a.smem_cap) {
+                // The remaining levels run out of shared memory: the span's sort state is staged once (element i lives at
+                // index i - amin; entry `amax` is a sentinel that reads as a finished segment), so each of the ~log2(span / 16)
+                // block-local levels costs shared-memory latency instead of five dependent rounds through L2.
+                const int cap = a.smem_cap;
+                unsigned char *p = dyn_smem;
+                double *s_wk = reinterpret_cast<double *>(p); p += sizeof(double) * cap;
+                long long *s_flags = reinterpret_cast<long long *>(p); p += sizeof(long long) * cap;
+                long long *s_pre = reinterpret_cast<long long *>(p); p += sizeof(long long) * cap;
+                int *s_perm = reinterpret_cast<int *>(p); p += sizeof(int) * cap;
+                int *s_segf = reinterpret_cast<int *>(p); p += sizeof(int) * cap;
+                int *s_segl = reinterpret_cast<int *>(p); p += sizeof(int) * cap;
+                int *s_ta = reinterpret_cast<int *>(p); p += sizeof(int) * cap;
+                int *s_tb = reinterpret_cast<int *>(p); p += sizeof(int) * cap;
+                int *s_cut = reinterpret_cast<int *>(p);
+                for (int i = amin + tid; i < amax; i += nthr) {
+                    s_perm[i - amin] = b.perm[i];
+                    s_wk[i - amin] = b.wk[i];
+                    s_segf[i - amin] = b.segf[i];
+                    s_segl[i - amin] = b.segl[i];
+                }
+                if (tid == 0) { s_segf[amax - amin] = 0x7fffffff; s_segl[amax - amin] = 0; }
+                staged = true;
+                st_min = amin; st_max = amax;
+                gb = b;
+                b.perm = s_perm - amin; b.wk = s_wk - amin; b.segf = s_segf - amin; b.segl = s_segl - amin;
+                b.flags = s_flags - amin; b.pre = s_pre - amin; b.tmp_a = s_ta - amin; b.tmp_b = s_tb - amin; b.cut = s_cut - amin;
+            }
+            __syncthreads();
         }
         const int span = amax - amin + 1;  // + 1 so that pre[amax] exists
         if (etid == 0 && a.work) { a.work[0] += span; a.work[1] += 1; }
@@ -2317,7 +2362,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                         dep--;
                     }
                 }
-                if (bad) { b.active[2] = 1; continue; }
+                if (bad) { act[2] = 1; continue; }
                 b.fin_perm[pos] = b.perm[i];
                 b.fin_wk[pos] = b.wk[i];
                 b.segf[i] = 0x7fffffff;  // done: inactive in every later phase
@@ -2358,9 +2403,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
         }
         if (etid == 0) {
-            b.active[(level + 1) & 1] = 0;
-            b.active[4 + 2 * ((level + 1) & 1)] = 0x7fffffff;
-            b.active[5 + 2 * ((level + 1) & 1)] = 0;
+            act[(level + 1) & 1] = 0;
+            act[4 + 2 * ((level + 1) & 1)] = 0x7fffffff;
+            act[5 + 2 * ((level + 1) & 1)] = 0;
         }
         barrier();
         // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
@@ -2374,20 +2419,35 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             b.segl[i] = nl;
             if (i == nf && nl - nf > kSortLeaf) {
                 if (depth > 0) {
-                    b.active[level & 1] = 1;
-                    atomicMin(&b.active[4 + 2 * ((level + 1) & 1)], nf);
-                    atomicMax(&b.active[5 + 2 * ((level + 1) & 1)], nl);
+                    act[level & 1] = 1;
+                    atomicMin(&act[4 + 2 * ((level + 1) & 1)], nf);
+                    atomicMax(&act[5 + 2 * ((level + 1) & 1)], nl);
                     pivot_of(nf, nl);
-                } else b.active[2] = 1;  // would enter introsort's heap-sort branch
+                } else act[2] = 1;  // would enter introsort's heap-sort branch
             }
         }
         barrier();
-        active = b.active[level & 1] != 0;
-        fail = b.active[2] != 0;
+        active = act[level & 1] != 0;
+        fail = act[2] != 0;
         if (fail) break;
+        lap(local ? 4 : 3);
         level++;
     }
+    if (local && blk == 0) {
+        if (staged) {  // back to HBM for the leaf pass
+            __syncthreads();
+            for (int i = st_min + tid; i < st_max; i += nthr) {
+                gb.perm[i] = b.perm[i];
+                gb.wk[i] = b.wk[i];
+                gb.segf[i] = b.segf[i];
+                gb.segl[i] = b.segl[i];
+            }
+            b = gb;
+        }
+        if (tid == 0 && sh_act[2]) b.active[2] = 1;
+    }
     grid.sync();  // blocks that left the loop early wait here for block 0's local levels
+    lap(4);
     fail = b.active[2] != 0 || a.force_fail != 0;
     if (fail) {  // the host falls back to libstdc++'s std::sort for this call
         if (gtid == 0) sc.b_need = 99;
@@ -2412,6 +2472,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         for (int x = f + 1; x < l; x++) { b.fin_perm[x] = b.perm[x]; b.fin_wk[x] = b.wk[x]; }
     }
     grid.sync();
+    lap(5);
     // ---- cumulative_time_steps
     if (n <= a.cum_sequential_max) {
         if (gtid == 0) {
@@ -2454,12 +2515,14 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         }
     }
     grid.sync();
+    lap(6);
     for (long long i = gtid; i < n; i += gsize) {
         const int lab = b.fin_perm[i];
         d.sorted_slot[i] = d.slot_of_label[lab];
         a.sorted_label[i] = lab;
     }
     if (gtid == 0) { sc.n_pick = n; sc.cum_total = d.cum[n - 1]; }
+    lap(7);
 }
 
 // ------------------------------------------------------------------------------------------------

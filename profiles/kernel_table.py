@@ -15,6 +15,8 @@ base, ov = workload_config(n, 42)
 sim = mcac_b200.Simulation(mcac_b200.ini_text(merged_config(base, ov)))
 rep, _ = sim.run(steps, batch=256)
 print(json.dumps({k: rep[k] for k in ("steps", "events", "sorts", "sort_levels", "sort_span_elements", "device_ms", "n_aggregates")}))
+ph = ["reduce", "labels", "sort_init", "grid_levels", "local_levels", "leaves", "cumulative", "pick_table"]
+print(json.dumps({"event_kernel_us_per_sort": {p: round(c / 1965.0 / max(1, rep["sorts"]), 1) for p, c in zip(ph, rep["event_phase_cycles"])}}))
 # algorithmic bytes per unit: DESIGN.md §5 / SURVEY.md §8(d)
 BYTES = {"cells": 12 + 4 + 32 + 32 + 8, "grow": 32, "update_partial": 40 + 168, "update_full": 40 + 168, "event_sort": 60, "event_nosort": 4 + 24 + 8,
          "grid_barriers_x100": 0, "rng_fill": 4, "morphology_stats": 28}
