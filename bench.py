@@ -106,6 +106,160 @@ def cpu_model() -> str:
     return "unknown"
 
 
+def classic_texts(indices: list[int], table_path: str) -> list[str]:
+    import mcac_b200
+    from mcac_b200 import ensemble as ens
+    from oracle.run_ref import merged_config  # config dict literals only
+
+    return [mcac_b200.ini_text(merged_config("classic", {"numerics": {"random_seed": s}, "inter_potential": {"interpotential_file": table_path}}))
+            for s in ens.seeds(1000, indices)]
+
+
+def ensemble_reference(a, K: int, W: int, M: int) -> dict:
+    """Reference arm of the ensemble: the unmodified reference binary, one process per realization on every host core in parallel,
+    bounded sample: `cores` realizations x (W + K) x M MC steps of examples/classic.ini (seeds 1000+k)."""
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from golden_lib import write_interpotential_file
+    from oracle.run_ref import read_summary, run_reference
+
+    cores = max(1, min(os.cpu_count() or 1, a.realizations, 32))
+    tmp = tempfile.mkdtemp(prefix="mcac_ens_ref_")
+    table = write_interpotential_file(Path(tmp) / "Interpotential_input.dat")
+
+    def one(k: int):
+        ov = {"numerics": {"random_seed": 1000 + k}, "inter_potential": {"interpotential_file": table},
+              "output": {"write_between_event_frequency": 1000000000, "write_events_frequency": 1000000000}}
+        wd, _ = run_reference("classic", ov, env={"MCAC_TAP_EXIT_STEP": M * (W + K), "MCAC_TAP_CHUNK": M})
+        s = read_summary(wd)
+        shutil.rmtree(wd, ignore_errors=True)
+        ct = [0.0] + s["chunk_times"]
+        return [b - c for c, b in zip(ct[:-1], ct[1:])]
+
+    with ThreadPoolExecutor(cores) as ex:
+        chunks = list(ex.map(one, range(cores)))
+    shutil.rmtree(tmp, ignore_errors=True)
+    # every process advances M steps per chunk, all in parallel: ensemble rate = cores * M / (slowest process' mean chunk time)
+    per_proc = [sum(c[W:W + K]) / max(1, len(c[W:W + K])) for c in chunks]
+    return {"value": cores * M / max(per_proc), "cores": cores, "ms_per_step": 1e3 * max(per_proc)}
+
+
+def ensemble_main(a, rank: int, world: int, local: int):
+    """--workload ensemble: R realizations of examples/classic.ini, realization k on rank k mod N (no communication during the run),
+    one bench step = every realization advances M MC steps; the statistic rows are all-gathered once at the end."""
+    K, W = a.steps, max(a.warmup, 0)
+    M = a.mc_steps or 300
+    R = a.realizations
+    config = {"workload": "ensemble", "ini": "examples/classic.ini (100 monomers, growth + nucleation + external potentials), random_seed=1000+k",
+              "realizations": R, "mc_steps_per_step": M, "parallelism": f"realization k -> rank k mod {world}; replicas only",
+              "l2": "per-realization state is KB-sized; every step is launch/latency-bound, no L2 flush applies"}
+    metric, unit = "ensemble_mc_steps_per_sec", "MC steps/s (sum over realizations)"
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        try:
+            r = ensemble_reference(a, K, W, M)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+            return
+        print(json.dumps({"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": a.gpus, "steps": K, "warmup": W,
+                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference",
+                                           "sample": f"{r['cores']} realizations in parallel (one process per core), {W + K} x {M} MC steps each, cpu: {cpu_model()}"},
+                          "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import tempfile
+
+    import numpy as np
+    import torch
+
+    import mcac_b200
+    from mcac_b200 import ensemble as ens
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from golden_lib import write_interpotential_file  # the committed copy of the table classic.ini points at (fixture data)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mcac_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tmp = tempfile.mkdtemp(prefix="mcac_ens_")
+    table = write_interpotential_file(Path(tmp) / "Interpotential_input.dat")
+    mine = ens.shard(R, rank, world)
+    threads = a.threads or max(1, min(32, (os.cpu_count() or 8) // max(1, world)))
+    t0 = time.perf_counter()
+    e = mcac_b200.Ensemble(classic_texts(mine, table), device=local)
+    init_s = time.perf_counter() - t0
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        e.run(M, threads=threads)
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    t_wall = time.perf_counter()
+    steps_done = launches = events = 0
+    for _ in range(K):
+        reps = e.run(M, threads=threads)
+        steps_done += sum(r["steps"] for r in reps)
+        launches += sum(r["kernel_launches"] for r in reps)
+        events += sum(r["events"] for r in reps)
+    sync_all()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    t = torch.tensor([wall_s], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(steps_done), float(launches), float(events)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    # e2e: the statistic rows of every realization cross to the host every step (the ensemble's result), states stay resident
+    t_e = time.perf_counter()
+    steps_e = 0
+    d2h = 0
+    for _ in range(max(1, min(2, K))):
+        reps = e.run(M, threads=threads)
+        rows = e.morphology_stats(ens.N_BINS, 2e-6)
+        steps_e += sum(r["steps"] for r in reps)
+        d2h = rows.nbytes
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t_e, float(steps_e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        te[0] = tmax[0]
+    # the only collective of the path
+    full = ens.gather_rows(rows, mine, R, dist=dist, device="cuda")
+    if rank == 0:
+        value = float(tot[0]) / float(t[0])
+        print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+                          "ms_per_step": 1e3 * float(t[0]) / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": dict(config, host_threads_per_rank=threads),
+                          "timing": "wall clock between device synchronisations (realizations run on independent streams), max over ranks",
+                          "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "init_s": init_s, "clocks": clocks,
+                          "e2e": {"value": float(te[1]) / float(te[0]), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+                                  "what": "mcac_ensemble_run(M steps per realization) + mcac_gpu_morphology_stats of every realization to the host, per step"},
+                          "gpu_launches": int(tot[1]),
+                          "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                                       "note": "launch/latency-bound: ~25 small launches + 3 host synchronisations per MC step and realization; "
+                                               "see DESIGN.md §6 (persistent per-realization kernel = next)"},
+                          "cpu_baseline": None, "ensemble_stats": ens.summarize(full)}))
+    shutil.rmtree(tmp, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -118,9 +272,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "ensemble"],
+                    help="c3: BASELINE's N=1e6 metric (default).  ensemble: --realizations independent runs of examples/classic.ini "
+                         "(seeds 1000+k) sharded k -> rank k mod N, all-gather of the morphology statistics at the end")
+    ap.add_argument("--realizations", type=int, default=64)
+    ap.add_argument("--threads", type=int, default=0, help="host threads driving the realizations of one rank (default: cores / ranks, <= 32)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     K, W = a.steps, max(a.warmup, 0)
+    if a.workload == "ensemble":
+        return ensemble_main(a, rank, world, local)
     config = {"workload": "c3", "ini": "validation/params_brownian.ini + number, volume_fraction=1000e-6, n_verlet_divisions=100, "
               "with_collisions=true, pick_method=random, with_domain_duplication=false", "n_monomers": a.n_monomers,
               "volume_fraction_ppm": 1000, "random_seed": "42+rank", "parallelism": f"replicas x{a.gpus} (independent realizations)",

@@ -161,6 +161,12 @@ int mcac_gpu_rand(mcac_gpu *h, int64_t n, int32_t *out);
  * may be NULL) receives one mcac_step_record per step; `batch` = speculative batch width (0 = default). */
 int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record *records, int64_t n_records, mcac_run_report *report);
 
+/* --- ensemble of independent realizations (the statistically required use: many seeds of one .ini) -------------------- */
+/* Runs mcac_gpu_run(max_steps, batch) on each of the n handles, `threads` host threads driving them concurrently (handle k on
+ * thread k mod threads; every handle has its own stream and RNG stream, nothing is shared).  reports: n entries or NULL.
+ * Returns the first non-zero error code of any realization. */
+int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t batch, int32_t threads, mcac_run_report *reports);
+
 int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_report *report);
 /* Times one kernel of the path on the resident state (CUDA events on the handle's stream, `reps` launches after one warm-up):
  * which = 0 K2 cell rebuild, 1 K8 growth (all spheres), 2 update_partial (all aggregates), 3 full update, 4 K9 event pipeline with

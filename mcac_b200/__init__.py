@@ -13,7 +13,7 @@ from . import _capi
 from ._capi import (AGG_FIELDS, CONTACT_DTYPE, SCALARS, SPHERE_FIELDS, STEP_DTYPE, Contact, McacError, Params, RunReport, SweepReport,
                     lib, ptr)
 
-__all__ = ["HostModel", "Simulation", "McacError", "ini_text", "Params"]
+__all__ = ["HostModel", "Simulation", "Ensemble", "McacError", "ini_text", "Params"]
 
 
 def ini_text(cfg: dict) -> str:
@@ -258,3 +258,28 @@ class Simulation:
         if recs is not None:
             recs = recs[:min(records, rep.steps)]
         return rep.as_dict(), recs
+
+
+class Ensemble:
+    """Independent realizations of one configuration (distinct seeds) resident on one GPU and advanced concurrently."""
+
+    def __init__(self, texts: list[str], device: int = 0):
+        self.sims = [Simulation(t, device=device) for t in texts]
+        self.L = lib()
+
+    def __len__(self):
+        return len(self.sims)
+
+    def run(self, max_steps: int, batch: int = 0, threads: int = 8) -> list[dict]:
+        n = len(self.sims)
+        hs = (C.c_void_p * n)(*[s.h for s in self.sims])
+        reps = (RunReport * n)()
+        rc = self.L.mcac_ensemble_run(hs, n, max_steps, batch, threads, reps)
+        if rc:
+            msgs = [self.L.mcac_gpu_last_error(s.h).decode() for s in self.sims]
+            raise McacError(rc, "; ".join(m for m in msgs if m)[:400])
+        return [r.as_dict() for r in reps]
+
+    def morphology_stats(self, n_bins: int = 24, rg_max: float = 1e-5) -> np.ndarray:
+        """(n_realizations, 2*n_bins + 8) statistics rows (K11), ready for the all-gather across ranks"""
+        return np.stack([s.morphology_stats(n_bins, rg_max) for s in self.sims])

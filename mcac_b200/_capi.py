@@ -89,7 +89,7 @@ EXPORTS = [
     "mcac_gpu_grow", "mcac_gpu_update", "mcac_gpu_refresh", "mcac_gpu_sort_time_steps", "mcac_gpu_get_pick_table",
     "mcac_gpu_pick_random", "mcac_gpu_pick_last", "mcac_gpu_duplicate", "mcac_gpu_rand", "mcac_gpu_run",
     "mcac_gpu_morphology_stats", "mcac_gpu_morphology_stats_device", "mcac_gpu_stream", "mcac_gpu_search_sweep",
-    "mcac_gpu_set_profile", "mcac_gpu_set_interpotential", "mcac_host_alloc_pinned", "mcac_host_free_pinned", "mcac_gpu_kernel_bench",
+    "mcac_gpu_set_profile", "mcac_gpu_set_interpotential", "mcac_host_alloc_pinned", "mcac_host_free_pinned", "mcac_gpu_kernel_bench", "mcac_ensemble_run",
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_state", "mcac_sim_create",
 ]
@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
         L.mcac_gpu_set_interpotential.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L.mcac_gpu_stream.argtypes = [vp]
         L.mcac_gpu_kernel_bench.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(dbl), C.POINTER(i64)]
+        L.mcac_ensemble_run.argtypes = [vp, C.c_int32, i64, C.c_int32, C.c_int32, vp]
         L.mcac_host_alloc_pinned.argtypes = [i64, C.POINTER(vp)]
         L.mcac_host_free_pinned.argtypes = [vp]
         L.mcac_gpu_stream.restype = vp

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -94,6 +95,8 @@ struct mcac_gpu {
     double *sweep_dir = nullptr, *sweep_dist = nullptr;
     SearchResult *sweep_res = nullptr;
     long long sweep_cap = 0;
+    BigSearch *big = nullptr;   // scratch of the three-kernel search between many-sphere aggregates
+    double big_search_npp = 24.;  // mean spheres per aggregate from which single searches take that form (MCAC_B200_BIG_NPP)
     int *wide_list = nullptr, *wide_count = nullptr;  // queries handed from the group search kernel to the wide one
     long long wide_cap = 0;
     int wide_parity = 0;
@@ -411,7 +414,11 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
     const void *fn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(h->coop_blocks), dim3(kEventThreads), args, (size_t)h->event_smem_cap * kSortStageBytesPerEntry, h->stream));
+    // grid: one CTA per 2048 aggregate slots, at most one CTA per SM — a small realization (ensembles, the early boxes of C1) gets a
+    // single CTA whose barriers are __syncthreads-cheap and which leaves the other SMs to the other realizations' streams
+    const int want_blocks = std::max(1, div_up(h->sc_host.n_agg_slots + (h->prm.with_nucleation ? 4096 : 0), 2048));
+    const int grid_blocks = std::min(h->coop_blocks, want_blocks);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kEventThreads), args, (size_t)h->event_smem_cap * kSortStageBytesPerEntry, h->stream));
     h->launches++;
     h->labels_valid = true;
     if (defer_sync) {  // the caller reads the scalars after its next kernels and handles a failed sort (b_need == 99) there
@@ -866,7 +873,20 @@ int search_kernels(mcac_gpu *h, int nq, const int *q_slot, const double *q_dir, 
     CK(cudaGetLastError());
     return E_OK;
 }
+// one search between aggregates of many spheres (general step, late stages): phase 1 / tiled sphere sweep over the grid / phase 3
+int search_big(mcac_gpu *h) {
+    TRY(build_cells(h));
+    TRY(join_cells(h));
+    if (!h->big) TRY(dev_alloc_persistent(h, &h->big, 1));
+    k_search_big_p1<<<1, kSearchThreads, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, h->q_res, h->big);
+    k_search_big_p2<<<2 * h->n_sm, 256, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, h->big);
+    k_search_big_p3<<<1, kSearchThreads, 0, h->stream>>>(h->d, h->q_slot, h->q_dir, h->q_dist, h->q_res, h->big);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return E_OK;
+}
 int search_launch(mcac_gpu *h, int nq) {
+    if (nq == 1 && h->sc_host.avg_npp >= h->big_search_npp) return search_big(h);
     TRY(build_cells(h));
     TRY(join_cells(h));
     return search_kernels(h, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
@@ -905,6 +925,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (getenv("MCAC_B200_NO_OVERLAP")) h->overlap = false;
+        if (const char *e = getenv("MCAC_B200_BIG_NPP")) h->big_search_npp = atof(e);
         if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
@@ -1366,6 +1387,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         h->launches += growth ? 3 : 2;
         if (growth) {  // calcul.cpp:184-206 — the frequency test uses the counter BEFORE this step's bookkeeping
             const int full = (h->sc_host.n_iter_without_event % p.full_aggregate_update_frequency == 0) ? 1 : 0;
+            if (p.individual_surf_reactions) { k_update_picked<<<1, kCommitThreads, 0, h->stream>>>(h->d, full); h->launches++; }
             k_update_small<<<div_up(h->sc_host.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, full, p.individual_surf_reactions, 0);
             k_update_step<<<div_up(h->sc_host.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
             h->launches += 2;
@@ -1644,6 +1666,25 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_o
     cudaEventDestroy(e1);
     h->cells_valid = false;
     h->pick_valid = false;
+    return rc;
+}
+
+// Ensemble of independent realizations (the path does not shard, replicas do): `threads` host threads drive the
+// handles concurrently, each handle on its own CUDA stream with its own RNG stream, so the small per-step kernels of different
+// realizations overlap on the device.  Handle k is driven by thread k mod threads; no data is shared between handles.
+int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t batch, int32_t threads, mcac_run_report *reports) {
+    if (!handles || n < 1) return E_INPUT;
+    const int T = std::max(1, std::min<int>(threads, n));
+    std::vector<int> rcs((size_t)n, E_OK);
+    auto work = [&](int t) {
+        for (int k = t; k < n; k += T) rcs[(size_t)k] = mcac_gpu_run(handles[k], max_steps, batch, nullptr, 0, reports ? reports + k : nullptr);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    int rc = E_OK;
+    for (int k = 0; k < n; k++) if (rcs[(size_t)k] != E_OK && rc == E_OK) rc = rcs[(size_t)k];
     return rc;
 }
 

@@ -129,9 +129,25 @@ __global__ void k_labels_to_slots(DevState d, int nq, const long long *labels, i
 //  phase 3: the suspects are ranked by (d_b, key) — the multimap order — and scanned with the reference's
 //           two early breaks, so zero-distance / stale-rmax corner cases resolve exactly as on the CPU.
 // ------------------------------------------------------------------------------------------------
+// Scratch of the three-kernel form of ONE search whose aggregates hold many spheres (late DLCA stages: 10^2..10^4 spheres per
+// aggregate): phase 1 (k_search_big_p1) leaves the eligible suspects here, the sphere-sphere sweep of all of them is cut into
+// tiles of (moving sphere, other sphere) pairs spread over the whole grid (k_search_big_p2), phase 3 (k_search_big_p3) reduces the
+// tiles in pair order and runs the reference's ordered scan.
+constexpr int kBigTiles = 8192;
+struct BigSearch {
+    int m, m_all, nb, pad;
+    long long tile_pairs, n_tiles;
+    int c_slot[kCandCap];
+    double c_db[kCandCap];
+    unsigned long long c_key[kCandCap];
+    long long tile_begin[kCandCap + 1];
+    double t_best[kBigTiles];
+    long long t_pair[kBigTiles];
+};
+template <int kPhase>  // 0: the whole search in this CTA; 1: phase 1 only -> `big`; 3: phases 2' (tile reduction) + 3 from `big`
 __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const int *__restrict__ q_slot,
                                                 const double *__restrict__ q_dir, const double *__restrict__ q_dist,
-                                                SearchResult *__restrict__ out) {
+                                                SearchResult *__restrict__ out, BigSearch *__restrict__ big = nullptr) {
     __shared__ int seg_beg[kSearchThreads];
     __shared__ int seg_pre[kSearchThreads + 1];
     __shared__ int warp_sums[32];
@@ -167,6 +183,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
     if (tid == 0) { s_count = 0; s_nb = 0; }
     __syncthreads();
 
+    if (kPhase != 3) {
     // ---- phase 1: rows (i, j) of the cell range; along k the CSR entries are contiguous (<= 2 segments with wrap)
     const int ks = wrap_cell(rg.lo[2], n_div);
     const bool wraps = ks + nk > n_div;
@@ -218,12 +235,48 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
         }
         __syncthreads();
     }
+    } else {  // the eligible suspects were left in `big` by phase 1
+        for (int t = tid; t < big->m; t += kSearchThreads) { c_slot[t] = big->c_slot[t]; c_db[t] = big->c_db[t]; c_key[t] = big->c_key[t]; }
+        if (tid == 0) { s_count = big->m_all; s_nb = big->nb; }
+        __syncthreads();
+    }
     const int m_all = s_count;
     const int m = m_all < kCandCap ? m_all : kCandCap;
     if (m_all > kCandCap) res.status = 1;  // more eligible suspects than the shared-memory list holds
 
-    // ---- phase 2: exact sphere-sphere sweep, one warp per eligible aggregate
     const int n_src = d.a_n[slot], off_src = d.a_off[slot];
+    if (kPhase == 1) {  // hand the suspects and the tile partition of their sphere pairs to the grid-wide sweep
+        __syncthreads();
+        for (int t = tid; t < m; t += kSearchThreads) { big->c_slot[t] = c_slot[t]; big->c_db[t] = c_db[t]; big->c_key[t] = c_key[t]; }
+        if (tid == 0) {
+            long long total = 0;
+            for (int t = 0; t < m; t++) total += (long long)n_src * d.a_n[c_slot[t]];
+            // sum over suspects of ceil(pairs / tile) <= total / tile + m: sized so that it never exceeds kBigTiles
+            long long tile = (total + (kBigTiles - kCandCap) - 1) / (kBigTiles - kCandCap);
+            if (tile < 2048) tile = 2048;
+            long long acc = 0;
+            for (int t = 0; t < m; t++) {
+                big->tile_begin[t] = acc;
+                acc += ((long long)n_src * d.a_n[c_slot[t]] + tile - 1) / tile;
+            }
+            big->tile_begin[m] = acc;
+            big->n_tiles = acc;
+            big->tile_pairs = tile;
+            big->m = m; big->m_all = m_all; big->nb = s_nb;
+        }
+        return;
+    }
+    // ---- phase 2: exact sphere-sphere sweep, one warp per eligible aggregate
+    if (kPhase == 3) {  // tiles of one suspect are in ascending pair order: strict `<` keeps the first minimum
+        for (int k = tid; k < m; k += kSearchThreads) {
+            double best = INFINITY;
+            long long best_p = (long long)n_src * d.a_n[c_slot[k]];
+            for (long long t = big->tile_begin[k]; t < big->tile_begin[k + 1]; t++)
+                if (big->t_best[t] < best) { best = big->t_best[t]; best_p = big->t_pair[t]; }
+            c_d[k] = best;
+            c_pair[k] = best_p;
+        }
+    } else
     for (int k = warp; k < m; k += nwarps) {
         const int o = c_slot[k];
         const int n_o = d.a_n[o], off_o = d.a_off[o];
@@ -286,9 +339,63 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_wide(DevState d, int 
                                                                 const double *__restrict__ q_dist, SearchResult *__restrict__ out) {
     const int n = list ? *count : nq;
     for (int e = blockIdx.x; e < n; e += gridDim.x) {
-        search_wide_one(d, list ? list[e] : e, q_slot, q_dir, q_dist, out);
+        search_wide_one<0>(d, list ? list[e] : e, q_slot, q_dir, q_dist, out);
         __syncthreads();
     }
+}
+
+// the three-kernel form (one query, q = 0)
+__global__ void __launch_bounds__(kSearchThreads) k_search_big_p1(DevState d, const int *__restrict__ q_slot, const double *__restrict__ q_dir,
+                                                                  const double *__restrict__ q_dist, SearchResult *__restrict__ out, BigSearch *big) {
+    if (threadIdx.x == 0) { big->m = 0; big->n_tiles = 0; }
+    __syncthreads();
+    search_wide_one<1>(d, 0, q_slot, q_dir, q_dist, out, big);
+}
+__global__ void __launch_bounds__(256) k_search_big_p2(DevState d, const int *__restrict__ q_slot, const double *__restrict__ q_dir,
+                                                       const double *__restrict__ q_dist, BigSearch *big) {
+    __shared__ double sb[8];
+    __shared__ long long sp[8];
+    const int slot = q_slot[0];
+    if (slot < 0) return;
+    const int m = big->m;
+    const long long n_tiles = big->n_tiles, tile = big->tile_pairs;
+    const double box = d.sc->box_length, dist = q_dist[0], dx = q_dir[0], dy = q_dir[1], dz = q_dir[2];
+    const int n_src = d.a_n[slot], off_src = d.a_off[slot];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int lo = 0, hi = m;  // suspect of this tile: last k with tile_begin[k] <= t
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (big->tile_begin[mid] <= t) lo = mid; else hi = mid;
+        }
+        const int o = big->c_slot[lo];
+        const int n_o = d.a_n[o], off_o = d.a_off[o];
+        const long long npairs = (long long)n_src * n_o;
+        const long long p0 = (t - big->tile_begin[lo]) * tile, p1 = (p0 + tile < npairs) ? p0 + tile : npairs;
+        double best = INFINITY;
+        long long best_p = npairs;
+        for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+            const int i = (int)(p / n_o), j = (int)(p - (long long)i * n_o);
+            const double4 a = d.s_posr[off_src + i];
+            const double4 b = d.s_posr[off_o + j];
+            const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+            if (c < best) { best = c; best_p = p; }
+        }
+        warp_argmin(best, best_p);
+        if (lane == 0) { sb[warp] = best; sp[warp] = best_p; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+                if (sb[w] < best || (sb[w] == best && sp[w] < best_p)) { best = sb[w]; best_p = sp[w]; }
+            big->t_best[t] = best;
+            big->t_pair[t] = best_p;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kSearchThreads) k_search_big_p3(DevState d, const int *__restrict__ q_slot, const double *__restrict__ q_dir,
+                                                                  const double *__restrict__ q_dist, SearchResult *__restrict__ out, BigSearch *big) {
+    search_wide_one<3>(d, 0, q_slot, q_dir, q_dist, out, big);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1664,16 +1771,26 @@ __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int i
     const int slot = blockIdx.x * 8 + w;
     const Scalars &sc = *d.sc;
     if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
-    if (individual && !sc.b_merged && slot != sc.p_slot) return;
+    if (individual && !sc.b_merged) return;  // done by k_update_picked
     if (d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], sc.box_length);
+}
+// individual surface reactions without a merge: only the picked aggregate is updated (calcul.cpp:196-203) — by a whole CTA, so
+// that a 10^3-sphere aggregate's O(n^2) contact pass is not left to one warp
+__global__ void __launch_bounds__(kCommitThreads) k_update_picked(DevState d, int full) {
+    __shared__ double scratch[kUpdateScratch];
+    const Scalars &sc = *d.sc;
+    if (sc.b_merged) return;  // every aggregate is updated by k_update_small / k_update_step
+    const int slot = sc.p_slot;
+    if (slot < 0 || slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
+    agg_update<true>(d, slot, full != 0, threadIdx.x, blockDim.x, scratch, sc.box_length);
 }
 // the small aggregates (n <= kSingleMax) of the same update: one aggregate per THREAD
 __global__ void __launch_bounds__(128) k_update_small(DevState d, int full, int individual, int all) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const Scalars &sc = *d.sc;
     if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
-    if (!all && individual && !sc.b_merged && slot != sc.p_slot) return;
+    if (!all && individual && !sc.b_merged) return;  // done by k_update_picked
     if (d.a_n[slot] > kSingleMax) return;
     agg_update_single(d, slot, full != 0, sc.box_length);
 }

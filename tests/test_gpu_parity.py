@@ -289,6 +289,25 @@ def test_execution_variants_do_not_change_the_trajectory(env, monkeypatch):
     np.testing.assert_array_equal(s0["aggregates"]["rg"], s1["aggregates"]["rg"])
 
 
+def test_big_aggregate_search_form_is_the_same_search(monkeypatch):
+    """The three-kernel search (phase 1 / sphere-pair tiles over the grid / phase 3) that single searches take once aggregates
+    hold many spheres returns exactly what the one-CTA search returns: forced on for a whole growth run (pytest config, to its
+    end) and compared with the default run, then both with the oracle."""
+    g = Golden("pytest_seed42")
+    text = ini_text(merged_config(g.base, g.overrides))
+    base = Simulation(text)
+    r0, rec0 = base.run(20000, records=20000)
+    monkeypatch.setenv("MCAC_B200_BIG_NPP", "0")
+    var = Simulation(text)
+    r1, rec1 = var.run(20000, records=20000)
+    assert r0["steps"] == r1["steps"] and r0["events"] == r1["events"] and r0["finished"] == 1
+    for f in INT_FIELDS + FP_FIELDS:
+        np.testing.assert_array_equal(rec0[f], rec1[f], err_msg=f)
+    o = Oracle(g.base, g.overrides)
+    ref = o.run(20000)
+    assert_records_match(rec1, ref, o.scalars()["box_length"])
+
+
 def test_monodisperse_full_run_through_two_duplications():
     """C1 literal: 800 -> 6400 -> 51200 spheres, 1 000 452 steps, 1 688 merges — decisions via the golden digest."""
     g = Golden("monodisperse_seed42")
