@@ -277,7 +277,8 @@ class Ensemble:
         rc = self.L.mcac_ensemble_run(hs, n, max_steps, batch, threads, reps)
         if rc:
             msgs = [self.L.mcac_gpu_last_error(s.h).decode() for s in self.sims]
-            raise McacError(rc, "; ".join(m for m in msgs if m)[:400])
+            distinct = list(dict.fromkeys(m for m in msgs if m))
+            raise McacError(rc, " | ".join(distinct)[:1500])
         return [r.as_dict() for r in reps]
 
     def morphology_stats(self, n_bins: int = 24, rg_max: float = 1e-5) -> np.ndarray:

@@ -53,6 +53,8 @@ struct mcac_gpu {
     bool cells_on_side = false;
     int force_sort_fail = 0;    // MCAC_B200_FORCE_SORT_FAIL=k: every k-th device sort reports failure (exercises the fallback)
     long long sort_calls = 0;
+    bool debug_sync = false;
+    long long nucl_headroom = 0;  // MCAC_B200_NUCL_HEADROOM: fixed (small) slot headroom, to exercise the regrow path in tests
     bool overlap = true;        // MCAC_B200_NO_OVERLAP=1 serialises the rebuild and synchronises after every event kernel  // a rebuild is in flight on stream2 (joined before the next search)
     std::string err;
     DevState d{};
@@ -122,6 +124,11 @@ struct mcac_gpu {
 
 namespace {
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+// MCAC_B200_DEBUG_SYNC=1: synchronise after every launch group of the step loops and name the group that faulted
+int dbg_sync(mcac_gpu *h, const char *tag);
+#define DBG(tag)                                                     \
+    if (h->debug_sync && (rc = dbg_sync(h, tag)) != E_OK) break
+
 
 template <class T>
 int dev_alloc(mcac_gpu *h, T **p, size_t n) {
@@ -222,6 +229,13 @@ int scan_ints(mcac_gpu *h, const int *in, int n, int *out, cudaStream_t st = nul
     return E_OK;
 }
 
+int dbg_sync(mcac_gpu *h, const char *tag) {
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) return E_OK;
+    h->err = std::string("after ") + tag + ": " + cudaGetErrorString(e) + " (realization step " + std::to_string(h->sc_host.steps_done) +
+             ", n_agg " + std::to_string(h->sc_host.n_agg) + ", n_sph " + std::to_string(h->sc_host.n_sph) + ")";
+    return E_UNKNOWN;
+}
 int pull_scalars(mcac_gpu *h) {
     CK(cudaMemcpyAsync(h->h_sc, h->d.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -674,7 +688,7 @@ int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_ste
     const long long n_agg = s.n_agg, n_sph = s.n_sph;
     if (n_agg <= 0 || n_sph <= 0) { h->err = "upload_state: empty state"; return E_INPUT; }
     if (s.offsets[0] != 0 || s.offsets[n_agg] != n_sph) { h->err = "upload_state: membership offsets do not cover the spheres"; return E_INPUT; }
-    const long long headroom = h->prm.with_nucleation ? std::max<long long>(n_agg, 4096) : 0;  // slots for nucleated monomers
+    const long long headroom = h->prm.with_nucleation ? std::max<long long>(h->nucl_headroom > 0 ? 0 : n_agg, h->nucl_headroom > 0 ? h->nucl_headroom : 4096) : 0;  // slots for nucleated monomers
     const long long need_agg = n_agg + headroom, need_sph = 3 * (n_sph + headroom) + 1024;
     if (h->owned.empty() || d.agg_cap < need_agg || d.sph_cap < need_sph) {  // otherwise the resident allocation is reused
         free_all(h);
@@ -925,6 +939,8 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (getenv("MCAC_B200_NO_OVERLAP")) h->overlap = false;
+        if (getenv("MCAC_B200_DEBUG_SYNC")) h->debug_sync = true;
+        if (const char *e = getenv("MCAC_B200_NUCL_HEADROOM")) h->nucl_headroom = std::max(80, atoi(e));
         if (const char *e = getenv("MCAC_B200_BIG_NPP")) h->big_search_npp = atof(e);
         if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
@@ -1320,15 +1336,13 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if (h->sc_host.event && p.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(p.u_sg < 0.0)) {
             if ((rc = duplicate(h)) != E_OK) break;
             dups++;
+            DBG("duplicate");
         }
-        if (!pick_last && (h->sc_host.event || growth || !h->pick_valid)) {
-            if ((rc = event_pipeline(h, false, false, true)) != E_OK) break;
-            sorts++;
-        }
-        if ((rc = refresh_labels(h)) != E_OK) break;
         if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph)
             if ((rc = compact_pool(h)) != E_OK) break;
-        // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up
+        DBG("compact_pool");
+        // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up.  This renumbers the
+        // aggregate slots (slot = label again), so it must come BEFORE the pick table of this step is built.
         if (p.with_nucleation && (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64)) {
             HostState hs;
             if ((rc = download(h, hs)) != E_OK) break;
@@ -1341,7 +1355,16 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             sc.n_agg_slots = n_slots; sc.pool_top = pool;
             if ((rc = push_scalars(h)) != E_OK) break;
         }
+        if (!pick_last && (h->sc_host.event || growth || !h->pick_valid)) {
+            if ((rc = event_pipeline(h, false, false, true)) != E_OK) break;
+            sorts++;
+            DBG("event_pipeline");
+        }
+        if ((rc = refresh_labels(h)) != E_OK) break;
+        DBG("refresh_labels");
+        DBG("nucleation regrow");
         if ((rc = ensure_rng(h, h->sc_host.rand_pos + 8192)) != E_OK) break;
+        DBG("ensure_rng");
         int draws = pick_last ? 2 : 3, n_try = 1, draws_at_search = pick_last ? 2 : 3;
         if (pick_last) {
             k_pick_last<<<1, 1024, 0, h->stream>>>(h->d, h->q_slot);
@@ -1351,10 +1374,12 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             k_prepare_queries<<<1, 128, 0, h->stream>>>(h->d, 1, h->q_slot, h->q_dir, h->q_dist);
             h->launches++;
         }
+        DBG("pick / direction");
         if (p.with_collisions) {
             prof_begin(h, 0);
             if ((rc = search_launch(h, 1)) != E_OK) break;
             prof_end(h);
+            DBG("search");
             // orientation loop of calcul.cpp:119-141: a non-sticking contact redraws the direction (n_try++)
             while (p.with_potentials) {
                 k_check_regime<<<1, 32, 0, h->stream>>>(h->d, h->q_res, h->q_dist, draws);
@@ -1381,8 +1406,11 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         sa.pick_last = pick_last; sa.with_collisions = p.with_collisions; sa.n_try = n_try; sa.draws = draws; sa.draws_at_search = draws_at_search;
         prof_begin(h, 1);
         k_step_move<<<1, kCommitThreads, 0, h->stream>>>(h->d, sa);
+        DBG("k_step_move");
         if (growth) k_grow_pending<<<div_up(p.individual_surf_reactions ? h->sc_host.n_sph : h->sc_host.pool_top, 256), 256, 0, h->stream>>>(h->d, p.individual_surf_reactions);
+        DBG("k_grow_pending");
         k_step_merge<<<1, kCommitThreads, 0, h->stream>>>(h->d, sa.rec, sa.rec_cap, sa.rec_index);
+        DBG("k_step_merge");
         prof_end(h);
         h->launches += growth ? 3 : 2;
         if (growth) {  // calcul.cpp:184-206 — the frequency test uses the counter BEFORE this step's bookkeeping
@@ -1392,12 +1420,14 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             k_update_step<<<div_up(h->sc_host.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
             h->launches += 2;
         }
+        DBG("update kernels");
         if (p.with_nucleation) {  // calcul.cpp:208-220
             k_nucleate<<<1, kCommitThreads, 0, h->stream>>>(h->d, 0., 1);
             h->launches++;
         } else {
             CK(cudaMemsetAsync(&h->d.sc->n_nucleated, 0, sizeof(int), h->stream));
         }
+        DBG("k_nucleate");
         k_step_event<<<1, 32, 0, h->stream>>>(h->d);
         h->launches++;
         {   // refresh() after an event, PhysicalModel::update after an event or in growth mode (calcul.cpp:232-234, 272-277)
@@ -1487,7 +1517,12 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if (h->sc_host.b_stop_reason == STOP_FINISHED) { fin = true; break; }
         if (h->sc_host.b_committed == 0) { h->err = "batch made no progress"; rc = E_UNKNOWN; break; }
     }
-    if (join_cells(h) != E_OK && rc == E_OK) rc = E_UNKNOWN;
+    if (rc != E_OK) {  // keep the message of the call that failed
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        return rc;
+    }
+    if (join_cells(h) != E_OK) rc = E_UNKNOWN;
     if (rc == E_OK && need_refresh) {  // the call ended on a merge: refresh() / PhysicalModel::update belong to that step
         rc = event_pipeline(h, true, true, false);
         need_refresh = false;

@@ -89,8 +89,15 @@ __global__ void k_rng_fill(GlibcRandState *st, int *out, int n) {  // n multiple
 __global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir, double *q_dist) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nq) return;
-    const Scalars &sc = *d.sc;
+    Scalars &sc = *d.sc;
     const long long p = sc.rand_pos + 3LL * j - d.rng_buf_base;
+    if (p < 0 || p + 2 >= d.rng_buf_n) {  // the host did not stage these draws: refuse instead of reading outside the buffer
+        sc.error = 21;
+        q_slot[j] = -1;
+        q_dir[3 * j] = q_dir[3 * j + 1] = q_dir[3 * j + 2] = 0.;
+        q_dist[j] = 0.;
+        return;
+    }
     const double u_pick = uniform_from_rand(d.rng_buf[p]);
     const double u_theta = uniform_from_rand(d.rng_buf[p + 1]);
     const double u_phi = uniform_from_rand(d.rng_buf[p + 2]);
@@ -101,13 +108,17 @@ __global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir
         const int mid = lo + ((hi - lo) >> 1);
         if (d.cum[mid] < val) lo = mid + 1; else hi = mid;
     }
-    const int slot = d.sorted_slot[lo];
+    int slot = d.sorted_slot[lo];
+    if (n < 1 || lo >= n || slot < 0 || slot >= sc.n_agg_slots) {  // corrupt pick table
+        sc.error = 22;
+        slot = -1;
+    }
     const Vec3 dir = direction_from_draws(u_theta, u_phi);
     q_slot[j] = slot;
     q_dir[3 * j] = dir.x;
     q_dir[3 * j + 1] = dir.y;
     q_dir[3 * j + 2] = dir.z;
-    q_dist[j] = d.a_lpm[slot];
+    q_dist[j] = slot >= 0 ? d.a_lpm[slot] : 0.;
 }
 // explicit queries given by label (the per-call C ABI)
 __global__ void k_labels_to_slots(DevState d, int nq, const long long *labels, int *q_slot) {
@@ -2650,7 +2661,11 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, double rg_max, double *out) {
     __shared__ double red[8][8];
+    __shared__ unsigned int hist[2 * 64];  // per-CTA histograms (nb <= 64 bins each): one global atomic per bin and CTA, not per aggregate
     const int n = d.sc->n_agg_slots;
+    const bool local_hist = nb <= 64;
+    for (int b = threadIdx.x; b < 2 * 64; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
     double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         if (!d.a_alive[s]) continue;
@@ -2660,8 +2675,13 @@ __global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, do
         b1 = b1 < nb ? b1 : nb - 1;
         int b2 = static_cast<int>(rg / rg_max * nb);
         b2 = b2 < 0 ? 0 : (b2 < nb ? b2 : nb - 1);
-        atomicAdd(&out[b1], 1.0);
-        atomicAdd(&out[nb + b2], 1.0);
+        if (local_hist) {
+            atomicAdd(&hist[b1], 1u);
+            atomicAdd(&hist[64 + b2], 1u);
+        } else {
+            atomicAdd(&out[b1], 1.0);
+            atomicAdd(&out[nb + b2], 1.0);
+        }
         const double lx = log(d.a_dgdp[s]), ly = log(np_);
         acc[0] += 1.; acc[1] += np_; acc[2] += lx; acc[3] += lx * lx; acc[4] += lx * ly; acc[5] += ly; acc[6] += ly * ly; acc[7] += rg;
     }
@@ -2678,6 +2698,11 @@ __global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, do
         for (int ww = 0; ww < 8; ww++) t += red[ww][threadIdx.x];
         atomicAdd(&out[2 * nb + threadIdx.x], t);
     }
+    if (local_hist)
+        for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) {
+            const unsigned int c = hist[b < nb ? b : 64 + (b - nb)];
+            if (c) atomicAdd(&out[b], static_cast<double>(c));  // counts: exact in double, order-independent
+        }
 }
 // summary of a sweep of independent searches (no commit): contacts, checksum of the finite distances, pair counters
 __global__ void __launch_bounds__(256) k_sweep_summary(const SearchResult *res, const double *q_dist, int nq, double *out /* 4 */) {

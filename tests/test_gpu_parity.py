@@ -192,10 +192,15 @@ def test_general_step_loop_growth_picklast_nocollision(name, steps):
     assert_states_match(sim.state(), o.state(), box)
 
 
-def test_classic_potentials_nucleation_individual_growth(tmp_path):
+@pytest.mark.parametrize("headroom", [None, "96"])
+def test_classic_potentials_nucleation_individual_growth(tmp_path, monkeypatch, headroom):
     """examples/classic.ini (the ensemble workload): external interaction potentials with direction redraws, nucleation,
-    individual surface reactions, normal-law diameters, three domain duplications within the first 1500 steps."""
+    individual surface reactions, normal-law diameters, three domain duplications within the first 1500 steps.
+    headroom=96: the slot headroom for nucleated monomers is made tiny, so the state is re-laid out (slots renumbered) every few
+    dozen nucleations — the pick table must be built after that, not before (regression: a stale table was read once)."""
     from golden_lib import write_interpotential_file
+    if headroom:
+        monkeypatch.setenv("MCAC_B200_NUCL_HEADROOM", headroom)
     g = Golden("classic_seed1000")
     ov = dict(g.overrides)
     ov["inter_potential"] = {"interpotential_file": write_interpotential_file(tmp_path / "Interpotential_input.dat")}
