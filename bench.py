@@ -211,34 +211,28 @@ def ensemble_main(a, rank: int, world: int, local: int):
     sampler.start()
     t_wall = time.perf_counter()
     steps_done = launches = events = 0
+    stats_s = 0.0
+    d2h = 0
+    rows = None
     for _ in range(K):
         reps = e.run(M, threads=threads)
         steps_done += sum(r["steps"] for r in reps)
         launches += sum(r["kernel_launches"] for r in reps)
         events += sum(r["events"] for r in reps)
+        # the step's result: the statistic rows of every realization cross to the host (timed apart: only e2e includes it)
+        t_s = time.perf_counter()
+        rows = e.morphology_stats(ens.N_BINS, 2e-6)
+        stats_s += time.perf_counter() - t_s
+        d2h = rows.nbytes
     sync_all()
     wall_s = time.perf_counter() - t_wall
     clocks = sampler.stop()
-    t = torch.tensor([wall_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall_s - stats_s, wall_s], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(steps_done), float(launches), float(events)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    # e2e: the statistic rows of every realization cross to the host every step (the ensemble's result), states stay resident
-    t_e = time.perf_counter()
-    steps_e = 0
-    d2h = 0
-    for _ in range(max(1, min(2, K))):
-        reps = e.run(M, threads=threads)
-        rows = e.morphology_stats(ens.N_BINS, 2e-6)
-        steps_e += sum(r["steps"] for r in reps)
-        d2h = rows.nbytes
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t_e, float(steps_e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(te, op=dist.ReduceOp.SUM)
-        te[0] = tmax[0]
+    te = torch.tensor([float(t[1]), float(tot[0])], dtype=torch.float64, device="cuda")
     # the only collective of the path
     full = ens.gather_rows(rows, mine, R, dist=dist, device="cuda")
     if rank == 0:
@@ -387,7 +381,9 @@ def main():
     sorts = max(1, sum(r["sorts"] for r in reps))
     roofline = {"kernel": "k_event (K9: labels + refresh + totals + 1/dt weights + replayed introsort + cumulative table, one cooperative "
                           "launch per merge)", "bound": "hbm", "achieved": k9_gbs, "peak": peak, "unit": "GB/s", "frac": k9_gbs / peak,
-                "traffic": None, "peak_source": peak_source, "launches": n_event, "avg_launch_us": 1e3 * event_ms / n_event,
+                "traffic": 54.6e6 if a.n_monomers == 1_000_000 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload "
+                                  "(profiles/r1b_ncu_full_summary.md), per launch", "peak_source": peak_source, "launches": n_event, "avg_launch_us": 1e3 * event_ms / n_event,
                 "algorithmic_bytes_per_launch": k9_bytes, "share_of_step": event_ms / dev_ms if dev_ms else None,
                 "sort_levels_per_launch": sum(r["sort_levels"] for r in reps) / sorts,
                 "sort_span_elements_per_launch": sum(r["sort_span_elements"] for r in reps) / sorts,
@@ -409,7 +405,8 @@ def main():
     sw_bytes = 36.0 * sw["pair_tests_bounding"] + 32.0 * (sw["pair_tests_sphere"] + sw["n_queries"]) + 48.0 * sw["n_queries"]
     sw_gbs = sw_bytes / (sw["kernel_ms"] * 1e-3) / 1e9
     roofline_sweep = {"kernel": "k_search_group<8> (K1), one launch of %d searches" % sw["n_queries"], "bound": "hbm", "achieved": sw_gbs,
-                      "peak": peak, "unit": "GB/s", "frac": sw_gbs / peak, "traffic": None, "kernel_ms": sw["kernel_ms"],
+                      "peak": peak, "unit": "GB/s", "frac": sw_gbs / peak, "traffic": 108.6e6 if a.n_monomers == 1_000_000 else None,
+                      "traffic_source": "ncu --set full capture of the same launch (profiles/r1b_ncu_full_summary.md)", "kernel_ms": sw["kernel_ms"],
                       "pair_tests_per_sec": (sw["pair_tests_bounding"] + sw["pair_tests_sphere"]) / (sw["kernel_ms"] * 1e-3),
                       "searches_per_sec": sw["n_queries"] / (sw["kernel_ms"] * 1e-3)}
 
