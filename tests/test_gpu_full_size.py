@@ -1,0 +1,113 @@
+"""Parity at BASELINE.json's full sizes (run on the B200 with -m gpu): the head of each trajectory is replayed against the oracle
+step by step (as long as the O(N)-per-event CPU restatement finishes in seconds), the rest is checked through size-independent
+properties of the domain: labels partition the spheres, sphere volume is conserved by aggregation, every committed contact is a
+contact, the speculative batch width is invisible."""
+import numpy as np
+import pytest
+
+from oracle.run_ref import merged_config
+from oracle_lib import Oracle
+from test_gpu_parity import FP_FIELDS, INT_FIELDS, assert_records_match, assert_states_match
+
+from mcac_b200 import Simulation, ini_text
+
+pytestmark = pytest.mark.gpu
+
+
+def check_structure(st):
+    """pymcac/tests/test_data.py:166-205: per time step bincount(sphere Label) == aggregate Np, labels are 0..N_agg-1."""
+    assert st["sphere_label"].min() == 0 and st["sphere_label"].max() == st["n_agg"] - 1
+    np.testing.assert_array_equal(np.bincount(st["sphere_label"], minlength=st["n_agg"]), st["agg_n_spheres"])
+    assert st["offsets"][0] == 0 and st["offsets"][-1] == st["n_sph"]
+    np.testing.assert_array_equal(np.diff(st["offsets"]), st["agg_n_spheres"])
+    assert np.array_equal(np.sort(st["members"]), np.arange(st["n_sph"]))
+    for a in np.nonzero(st["agg_n_spheres"] > 1)[0][:200]:
+        assert np.all(st["sphere_label"][st["members"][st["offsets"][a]:st["offsets"][a + 1]]] == a)
+
+
+def test_c2_polydisperse_1e5_replays_the_collision_sequence():
+    """BASELINE configs[1]: validation/params_polydisperse.ini at 1e5 spheres (lognormal Dpm, n_verlet_divisions=40),
+    single-GPU replay against the reference algorithm's collision sequence: 30 000 steps, every record and the final state."""
+    ov = {"monomers": {"number": 100000}, "numerics": {"n_verlet_divisions": 40, "with_domain_duplication": "false", "random_seed": 42}}
+    steps = 30000
+    sim = Simulation(ini_text(merged_config("polydisperse", ov)))
+    rep, recs = sim.run(steps, batch=256, records=steps)
+    o = Oracle("polydisperse", ov)
+    ref = o.run(steps)
+    box = o.scalars()["box_length"]
+    assert rep["steps"] == len(ref) == steps
+    assert_records_match(recs, ref, box, clock_rtol=1e-10)  # 1e5 aggregates: tree-summed pick total (see the 1e6 test)
+    assert rep["events"] == int(ref["merged"].sum()) and rep["events"] > 10
+    st = sim.state()
+    assert_states_match(st, o.state(), box, clock_rtol=1e-10)
+    check_structure(st)
+    assert rep["pair_tests_sphere"] == o.counters()["pair_sphere"]
+
+
+def test_c3_1e6_head_replay_and_properties():
+    """BASELINE configs[2] (the bench workload): 1e6 monodisperse spheres at FV = 1000 ppm.  First 600 steps against the oracle
+    (each of its merges costs O(N)), then 30 000 more steps checked through properties, and batch-width invisibility at full size."""
+    ov = {"monomers": {"number": 1000000}, "environment": {"volume_fraction": "1000e-6"}, "limits": {"physical_time": -1},
+          "numerics": {"with_collisions": "true", "pick_method": "random", "n_verlet_divisions": 100, "with_domain_duplication": "false",
+                       "random_seed": 42}}
+    text = ini_text(merged_config("brownian", ov))
+    sim = Simulation(text)
+    st0 = sim.state()
+    head = 600
+    rep, recs = sim.run(head, batch=256, records=head)
+    o = Oracle("brownian", ov)
+    ref = o.run(head)
+    box = o.scalars()["box_length"]
+    # every decision and every geometric quantity to the usual bar; the clocks to 1e-10: at 1e6 aggregates the reference's
+    # sequential sum of the pick weights and the device's fixed tree sum differ by ~2e-11 relative (deviation 1)
+    assert_records_match(recs, ref, box, clock_rtol=1e-10)
+    assert rep["events"] == int(ref["merged"].sum()) and rep["events"] >= 3
+    assert_states_match(sim.state(), o.state(), box, clock_rtol=1e-10)
+    del o
+    more = 30000
+    rep2, recs2 = sim.run(more, batch=256, records=more)
+    st = sim.state()
+    check_structure(st)
+    assert st["n_agg"] == st0["n_agg"] - rep["events"] - rep2["events"]
+    # aggregation moves spheres, it never changes them
+    np.testing.assert_array_equal(st["spheres"]["r"], st0["spheres"]["r"])
+    np.testing.assert_array_equal(st["spheres"]["volume"], st0["spheres"]["volume"])
+    np.testing.assert_allclose(st["aggregates"]["volume"].sum(), st0["spheres"]["volume"].sum(), rtol=1e-12)
+    # every merge was a contact within the drawn mean free path, between two different aggregates
+    m = recs2["merged"] == 1
+    assert m.sum() == rep2["events"] > 100
+    assert np.all(recs2["distance"][m] <= recs2["full_distance"][m]) and np.all(recs2["moving_label"][m] != recs2["other_label"][m])
+    # merged spheres touch: |c_i - c_j| == r_i + r_j to rounding, for the dimers of the final state
+    dim = np.nonzero(st["agg_n_spheres"] == 2)[0]
+    a, b = st["members"][st["offsets"][dim]], st["members"][st["offsets"][dim] + 1]
+    d = np.sqrt(sum((st["spheres"][k][a] - st["spheres"][k][b]) ** 2 for k in ("rx", "ry", "rz")))
+    np.testing.assert_allclose(d, st["spheres"]["r"][a] + st["spheres"]["r"][b], rtol=1e-9)
+    # time only moves forward, one RNG triple per step
+    assert np.all(np.diff(recs2["time"]) > 0) and np.all(np.diff(recs2["rand_calls"]) == 3)
+    # the batch width is invisible at full size too
+    s1, s2 = Simulation(text), Simulation(text)
+    _, r1 = s1.run(3000, batch=1, records=3000)
+    _, r2 = s2.run(3000, batch=512, records=3000)
+    for f in INT_FIELDS + FP_FIELDS:
+        np.testing.assert_array_equal(r1[f], r2[f], err_msg=f)
+
+
+def test_c4_surface_growth_1e6_first_steps():
+    """BASELINE configs[3]: validation/params_surface_growth.ini at 1e6 spheres (lognormal 10 nm, alphas method): every step grows
+    every sphere, updates every aggregate and re-sorts the pick table.  Three steps against the oracle, full state."""
+    ov = {"monomers": {"number": 1000000}, "numerics": {"n_verlet_divisions": 100, "random_seed": 42}}
+    steps = 3
+    sim = Simulation(ini_text(merged_config("surface_growth", ov)))
+    rep, recs = sim.run(steps, records=steps)
+    o = Oracle("surface_growth", ov)
+    ref = o.run(steps)
+    box = o.scalars()["box_length"]
+    assert rep["steps"] == len(ref) == steps
+    assert_records_match(recs, ref, box, clock_rtol=1e-10)
+    st = sim.state()
+    assert_states_match(st, o.state(), box, clock_rtol=1e-10)
+    check_structure(st)
+    # growth: V = 4 pi / 3 r^3 and S = 4 pi r^2 of the grown radii (sphere.cpp:113-120: plain multiplies)
+    r = st["spheres"]["r"]
+    np.testing.assert_allclose(st["spheres"]["volume"], 4 * np.pi / 3 * r * r * r, rtol=1e-15)
+    np.testing.assert_allclose(st["spheres"]["surface"], 4 * np.pi * r * r, rtol=1e-15)

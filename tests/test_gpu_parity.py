@@ -22,7 +22,7 @@ INT_FIELDS = ["step", "rand_calls", "source", "moving_sphere", "other_sphere", "
 FP_FIELDS = ["dir", "full_distance", "distance", "time", "dt", "proper_time", "pos"]
 
 
-def assert_records_match(got, ref, box):
+def assert_records_match(got, ref, box, clock_rtol=RTOL):
     n = min(len(got), len(ref))
     assert n > 0
     for f in INT_FIELDS:
@@ -36,14 +36,17 @@ def assert_records_match(got, ref, box):
     assert np.all(err <= RTOL * ref["full_distance"][:n][fin]), f"contact distance off by {err.max()}"
     np.testing.assert_allclose(got["distance"][:n][fin], ref["distance"][:n][fin], rtol=1e-9, atol=0)
     np.testing.assert_allclose(got["dir"][:n], ref["dir"][:n], rtol=0, atol=1e-15)  # unit vector: a few ulp of CUDA sincos/acos vs glibc
-    for f in ["full_distance", "time", "proper_time"]:
-        np.testing.assert_allclose(got[f][:n], ref[f][:n], rtol=RTOL, atol=0, err_msg=f)
+    np.testing.assert_allclose(got["full_distance"][:n], ref["full_distance"][:n], rtol=RTOL, atol=0, err_msg="full_distance")
+    # clocks: dt = max_dt / cumulative_time_steps.back().  Above 65 536 aggregates that total is a fixed tree sum here and a
+    # sequential sum in the reference (whose own rounding error grows like n * 2^-53): callers at such sizes pass clock_rtol
+    for f in ["time", "proper_time"]:
+        np.testing.assert_allclose(got[f][:n], ref[f][:n], rtol=clock_rtol, atol=0, err_msg=f)
     # dt of a contact step = dt * (contact distance / lpm): inherits the conditioning of the contact distance
-    np.testing.assert_allclose(got["dt"][:n], ref["dt"][:n], rtol=RTOL, atol=RTOL * ref["dt"][:n].max(), err_msg="dt")
+    np.testing.assert_allclose(got["dt"][:n], ref["dt"][:n], rtol=clock_rtol, atol=RTOL * ref["dt"][:n].max(), err_msg="dt")
     np.testing.assert_allclose(got["pos"][:n], ref["pos"][:n], rtol=0, atol=RTOL * box, err_msg="pos")
 
 
-def assert_states_match(got, ref, box):
+def assert_states_match(got, ref, box, clock_rtol=RTOL):
     assert got["n_sph"] == ref["n_sph"] and got["n_agg"] == ref["n_agg"]
     for k in ["sphere_label", "agg_n_spheres", "members", "offsets", "agg_cell"]:
         np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
@@ -53,15 +56,17 @@ def assert_states_match(got, ref, box):
         np.testing.assert_allclose(got["spheres"][k], ref["spheres"][k], rtol=RTOL, atol=0, err_msg=f"sphere {k}")
     for k in ["x", "y", "z", "rx", "ry", "rz"]:
         np.testing.assert_allclose(got["aggregates"][k], ref["aggregates"][k], rtol=0, atol=RTOL * box, err_msg=f"aggregate {k}")
-    for k in ["rg", "f_agg", "lpm", "time_step", "rmax", "volume", "surface", "proper_time", "dp", "dg_over_dp", "coordination_number", "d_m"]:
+    for k in ["rg", "f_agg", "lpm", "time_step", "rmax", "volume", "surface", "dp", "dg_over_dp", "coordination_number", "d_m"]:
         np.testing.assert_allclose(got["aggregates"][k], ref["aggregates"][k], rtol=RTOL, atol=1e-300, err_msg=f"aggregate {k}")
+    np.testing.assert_allclose(got["aggregates"]["proper_time"], ref["aggregates"]["proper_time"], rtol=clock_rtol, atol=1e-300, err_msg="aggregate proper_time")
     # mean overlap coefficient c_ij = (r_i + r_j - d) / (r_i + r_j) is a ratio in [0, 1]; for spheres that just touch it is pure
     # rounding noise (1e-16), so it is compared on the scale of the ratio
     np.testing.assert_allclose(got["aggregates"]["overlapping"], ref["aggregates"]["overlapping"], rtol=RTOL, atol=RTOL, err_msg="overlapping")
     for k in ["member_volumes", "member_surfaces"]:
         np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=0, err_msg=k)
     np.testing.assert_allclose(got["member_distances_center"], ref["member_distances_center"], rtol=0, atol=RTOL * box)
-    for k in ["time", "box_length", "maxradius", "max_time_step", "avg_npp"]:
+    np.testing.assert_allclose(got["time"], ref["time"], rtol=clock_rtol, err_msg="time")
+    for k in ["box_length", "maxradius", "max_time_step", "avg_npp"]:
         np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, err_msg=k)
 
 
