@@ -87,6 +87,8 @@ typedef struct mcac_run_report {
     /* SM cycles of block 0 of the event kernel per phase: 0 reduce, 1 labels, 2 sort init, 3 grid-wide levels, 4 block-local levels,
      * 5 leaf insertion sorts, 6 cumulative table, 7 pick table */
     int64_t event_phase_cycles[8];
+    int64_t n_iter_without_event, nucleated;   /* PhysicalModel::n_iter_without_event after the call; monomers nucleated by it */
+    double total_volume, total_surface;       /* AggregatList::get_total_volume / surface as of the last PhysicalModel::update */
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction
@@ -172,6 +174,9 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
  * which = 0 K2 cell rebuild, 1 K8 growth (all spheres), 2 update_partial (all aggregates), 3 full update, 4 K9 event pipeline with
  * sort, 5 without sort, 6 100 grid barriers at K9's launch shape, 7 K10 RNG fill, 8 K11 statistics.  units = items per launch. */
 int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_per_launch, int64_t *units);
+/* on != 0: mcac_gpu_run returns right after the step that made an event (merge or nucleation: `event` of calcul.cpp:222), so that a
+ * host loop can do what calcul() does between events (advancement.dat rows, the progress table, output files) */
+int mcac_gpu_set_stop_at_event(mcac_gpu *h, int32_t on);
 /* profile != 0: mcac_gpu_run brackets its K1 / commit launches with CUDA events (reported in mcac_run_report) */
 int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile);
 

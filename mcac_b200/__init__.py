@@ -239,6 +239,9 @@ class Simulation:
         self._ck(self.L.mcac_gpu_kernel_bench(self.h, self.KERNELS[which], reps, C.byref(ms), C.byref(units)))
         return {"kernel": which, "ms": ms.value, "units": units.value}
 
+    def set_stop_at_event(self, on: bool = True):
+        self._ck(self.L.mcac_gpu_set_stop_at_event(self.h, int(on)))
+
     def set_profile(self, on: bool = True):
         self._ck(self.L.mcac_gpu_set_profile(self.h, int(on)))
 

@@ -62,7 +62,9 @@ class RunReport(C.Structure):
                [(n, C.c_int64) for n in ["search_launches", "commit_launches"]] + \
                [(n, C.c_double) for n in ["event_ms", "cells_ms"]] + \
                [(n, C.c_int64) for n in ["event_launches", "cells_launches", "sort_span_elements", "sort_levels"]] + \
-               [("event_phase_cycles", C.c_int64 * 8)]
+               [("event_phase_cycles", C.c_int64 * 8)] + \
+               [(n, C.c_int64) for n in ["n_iter_without_event", "nucleated"]] + \
+               [(n, C.c_double) for n in ["total_volume", "total_surface"]]
 
     def as_dict(self) -> dict:
         return {n: (list(getattr(self, n)) if n == "event_phase_cycles" else getattr(self, n)) for n, _ in self._fields_}
@@ -89,7 +91,7 @@ EXPORTS = [
     "mcac_gpu_grow", "mcac_gpu_update", "mcac_gpu_refresh", "mcac_gpu_sort_time_steps", "mcac_gpu_get_pick_table",
     "mcac_gpu_pick_random", "mcac_gpu_pick_last", "mcac_gpu_duplicate", "mcac_gpu_rand", "mcac_gpu_run",
     "mcac_gpu_morphology_stats", "mcac_gpu_morphology_stats_device", "mcac_gpu_stream", "mcac_gpu_search_sweep",
-    "mcac_gpu_set_profile", "mcac_gpu_set_interpotential", "mcac_host_alloc_pinned", "mcac_host_free_pinned", "mcac_gpu_kernel_bench", "mcac_ensemble_run",
+    "mcac_gpu_set_profile", "mcac_gpu_set_interpotential", "mcac_host_alloc_pinned", "mcac_host_free_pinned", "mcac_gpu_kernel_bench", "mcac_ensemble_run", "mcac_gpu_set_stop_at_event",
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_state", "mcac_sim_create",
 ]
@@ -129,6 +131,7 @@ def lib() -> C.CDLL:
         L.mcac_gpu_morphology_stats_device.argtypes = [vp, C.c_int32, dbl, vp]
         L.mcac_gpu_search_sweep.argtypes = [vp, i64, C.c_int32, C.POINTER(SweepReport)]
         L.mcac_gpu_set_profile.argtypes = [vp, C.c_int32]
+        L.mcac_gpu_set_stop_at_event.argtypes = [vp, C.c_int32]
         L.mcac_gpu_set_interpotential.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L.mcac_gpu_stream.argtypes = [vp]
         L.mcac_gpu_kernel_bench.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(dbl), C.POINTER(i64)]

@@ -53,6 +53,7 @@ struct mcac_gpu {
     bool cells_on_side = false;
     int force_sort_fail = 0;    // MCAC_B200_FORCE_SORT_FAIL=k: every k-th device sort reports failure (exercises the fallback)
     long long sort_calls = 0;
+    bool stop_at_event = false;   // mcac_gpu_run returns after the step that made an event (merge / nucleation)
     bool debug_sync = false;
     long long nucl_headroom = 0;  // MCAC_B200_NUCL_HEADROOM: fixed (small) slot headroom, to exercise the regrow path in tests
     bool overlap = true;        // MCAC_B200_NO_OVERLAP=1 serialises the rebuild and synchronises after every event kernel  // a rebuild is in flight on stream2 (joined before the next search)
@@ -87,6 +88,7 @@ struct mcac_gpu {
     long long sort_levels = 0, sort_fallbacks = 0;
     int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
     int coop_bps = 1, sort_local_span = 4096;
+    int event_spare_sms = 8;  // MCAC_B200_EVENT_SPARE_SMS
     int event_smem_cap = 0;   // shared-memory staging of the block-local sort levels (entries; 0 = levels stay in HBM/L2)
     long long *event_work = nullptr;
     long long event_work_seen[10] = {0};
@@ -431,7 +433,8 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     // grid: one CTA per 2048 aggregate slots, at most one CTA per SM — a small realization (ensembles, the early boxes of C1) gets a
     // single CTA whose barriers are __syncthreads-cheap and which leaves the other SMs to the other realizations' streams
     const int want_blocks = std::max(1, div_up(h->sc_host.n_agg_slots + (h->prm.with_nucleation ? 4096 : 0), 2048));
-    const int grid_blocks = std::min(h->coop_blocks, want_blocks);
+    // a few SMs are left to the side stream (the overlapped Verlet cell rebuild cannot share an SM with a 512-thread, 120-register CTA)
+    const int grid_blocks = std::min(std::max(1, h->coop_blocks - (h->overlap ? h->event_spare_sms : 0)), want_blocks);
     CK(cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kEventThreads), args, (size_t)h->event_smem_cap * kSortStageBytesPerEntry, h->stream));
     h->launches++;
     h->labels_valid = true;
@@ -940,6 +943,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (getenv("MCAC_B200_NO_OVERLAP")) h->overlap = false;
         if (getenv("MCAC_B200_DEBUG_SYNC")) h->debug_sync = true;
+        if (const char *e = getenv("MCAC_B200_EVENT_SPARE_SMS")) h->event_spare_sms = std::max(0, atoi(e));
         if (const char *e = getenv("MCAC_B200_NUCL_HEADROOM")) h->nucl_headroom = std::max(80, atoi(e));
         if (const char *e = getenv("MCAC_B200_BIG_NPP")) h->big_search_npp = atof(e);
         if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
@@ -1326,7 +1330,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, h->stream));
-    int64_t steps = 0, batches = 0, sorts = 0, dups = 0;
+    int64_t steps = 0, batches = 0, sorts = 0, dups = 0, nucleated_total = 0;
     int rc = E_OK;
     bool fin = false, need_refresh = false, fallback_sorted = false;
     while (!speculative && steps < max_steps) {  // ---- general step: one MC step per iteration, calcul() order
@@ -1445,6 +1449,8 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         steps += 1;
         if (h->sc_host.b_merged) { h->pick_valid = false; h->labels_valid = false; }
         if (h->sc_host.n_nucleated > 0) h->pick_valid = false;
+        nucleated_total += h->sc_host.n_nucleated;
+        if (h->stop_at_event && (h->sc_host.b_merged || h->sc_host.n_nucleated > 0)) break;
     }
     while (speculative && steps < max_steps) {
         if (finished(h)) { fin = true; break; }
@@ -1516,6 +1522,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         }
         if (h->sc_host.b_stop_reason == STOP_FINISHED) { fin = true; break; }
         if (h->sc_host.b_committed == 0) { h->err = "batch made no progress"; rc = E_UNKNOWN; break; }
+        if (h->stop_at_event && h->sc_host.b_merged) break;
     }
     if (rc != E_OK) {  // keep the message of the call that failed
         cudaEventDestroy(ev0);
@@ -1558,6 +1565,10 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->max_time_step = sc.max_time_step;
         report->volume_fraction = sc.volume_fraction;
         report->device_ms = ms;
+        report->n_iter_without_event = sc.n_iter_without_event;
+        report->nucleated = nucleated_total;
+        report->total_volume = sc.total_volume;
+        report->total_surface = sc.total_surface;
         long long w[10] = {0};
         cudaMemcpy(w, h->event_work, sizeof(w), cudaMemcpyDeviceToHost);
         report->sort_span_elements = w[0] - h->event_work_seen[0];
@@ -1570,6 +1581,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
 }
 
 int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile) { h->profile = profile; return E_OK; }
+int mcac_gpu_set_stop_at_event(mcac_gpu *h, int32_t on) { h->stop_at_event = on != 0; return E_OK; }
 
 int mcac_gpu_morphology_stats_device(mcac_gpu *h, int32_t n_bins, double rg_max, void *device_out) {
     CK(cudaSetDevice(h->device));

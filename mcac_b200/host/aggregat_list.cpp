@@ -109,9 +109,15 @@ mcac_run_report AggregatList::run(long max_steps, int batch) {
     physicalmodel->time = rep.time;
     physicalmodel->box_length = rep.box_length;
     physicalmodel->box_volume = std::pow(rep.box_length, 3);
-    physicalmodel->volume_fraction = rep.volume_fraction;
-    physicalmodel->aggregate_concentration = static_cast<double>(rep.n_aggregates) / physicalmodel->box_volume;
-    physicalmodel->monomer_concentration = static_cast<double>(rep.n_spheres) / physicalmodel->box_volume;
+    // PhysicalModel::update runs after an event, after a duplication, and every step with surface reactions (calcul.cpp:272-277,
+    // aggregat_list.cpp:186-189): only then do the concentrations and the volume fraction change
+    if (rep.events > 0 || rep.nucleated > 0 || rep.duplications > 0 || physicalmodel->with_surface_reactions) {
+        physicalmodel->volume_fraction = rep.volume_fraction;
+        physicalmodel->aggregate_concentration = static_cast<double>(rep.n_aggregates) / physicalmodel->box_volume;
+        physicalmodel->monomer_concentration = static_cast<double>(rep.n_spheres) / physicalmodel->box_volume;
+        total_volume = rep.total_volume;
+        total_surface = rep.total_surface;
+    }
     return rep;
 }
 
@@ -121,29 +127,91 @@ static void save_advancement(const PhysicalModel &pm, const AggregatList &aggreg
     out << pm.time << " " << pm.aggregate_concentration << " " << pm.volume_fraction << " " << aggregates.get_avg_npp() << " " << pm.temperature
         << " " << pm.box_volume << " " << pm.monomer_concentration << " " << pm.u_sg << " " << pm.flux_nucleation << std::endl;
 }
+static void print_bool(bool b, int width) {  // src/calcul.cpp:44-51
+    if (b) std::cout << std::setw(width / 2 + width % 2) << "X" << std::setw(width / 2 + 3) << " | ";
+    else std::cout << std::setw(width + 3) << " | ";
+}
+// PhysicalModel::time_to_write (physical_model.cpp:338-356)
+static bool time_to_write(const PhysicalModel &pm, size_t total_events, size_t n_iter_without_event, size_t &last_timestep_written) {
+    if (pm.write_Delta_t > 0) {
+        const size_t timestep = static_cast<size_t>(std::floor(pm.time / pm.write_Delta_t));
+        if (timestep > last_timestep_written) {
+            last_timestep_written = timestep;
+            return true;
+        }
+    }
+    if (n_iter_without_event == 0 && pm.write_events_frequency > 0 && total_events % pm.write_events_frequency == 0) return true;
+    if (n_iter_without_event > 0 && pm.write_between_event_frequency > 0 && n_iter_without_event % pm.write_between_event_frequency == 0)
+        return true;
+    return false;
+}
 
-// mcac::calcul (src/calcul.cpp:55-290): the loop itself runs on the device (mcac_gpu_run); the host reports progress between
-// chunks in the layout of the reference's stdout table (:237-270) and appends advancement.dat rows.
+// mcac::calcul (src/calcul.cpp:55-290).  The MC steps run on the device (mcac_gpu_run); the host does what calcul() does around
+// them, at the same points of the loop: PhysicalModel::finished, time_to_write -> advancement.dat row (same 9 columns, same stream
+// formatting), the "Duplication" lines and the per-event progress table.  mcac_gpu_run is called in slices that end where the
+// reference's loop top could write: right after an event, or when n_iter_without_event reaches a multiple of
+// write_between_event_frequency (every step if write_Delta_t is set).
 void calcul(PhysicalModel &pm, AggregatList &aggregates) {
     pm.print();
     const std::string dir = pm.output_dir.empty() ? "." : pm.output_dir;
-    std::cout << std::setw(8) << "#" << " | " << std::setw(9) << "Npp_avg" << " | " << std::setw(8) << "NAgg" << " | " << std::setw(10) << "Time"
-              << " | " << std::setw(10) << "steps/s" << " | " << std::setw(10) << "MC steps" << std::endl;
-    long long total_events = 0, total_steps = 0;
-    save_advancement(pm, aggregates, dir);
+    mcac_gpu *gpu = aggregates.handle();
+    mcac_gpu_set_stop_at_event(gpu, 1);
+    size_t total_events = 0, n_iter = 0, last_timestep_written = 0;
+    long long total_steps = 0;
+    long long n_sph = static_cast<long long>(aggregates.n_spheres()), n_agg = static_cast<long long>(aggregates.size());
+    const clock_t cpu_start = clock();
+    bool first = true;
     while (true) {
-        const mcac_run_report rep = aggregates.run(200000);
-        total_events += rep.events;
+        // loop top of calcul(): finished() is evaluated inside mcac_gpu_run (first slice) / from the last report (later slices)
+        if (!first && pm.finished_flag) break;
+        if (time_to_write(pm, total_events, n_iter, last_timestep_written)) save_advancement(pm, aggregates, dir);
+        first = false;
+        long slice = 1;
+        if (!(pm.write_Delta_t > 0)) {
+            const size_t f = pm.write_between_event_frequency;
+            slice = f > 0 ? static_cast<long>(f - n_iter % f) : 1000000L;
+        }
+        const mcac_run_report rep = aggregates.run(slice);
+        if (rep.duplications > 0)
+            std::cout << "Duplication : " << n_sph << " spheres in " << n_agg << " aggregates duplicated into " << 8 * n_sph << " spheres in "
+                      << 8 * n_agg << " aggregates" << std::endl;
+        const bool event = rep.events > 0 || rep.nucleated > 0;
         total_steps += rep.steps;
-        save_advancement(pm, aggregates, dir);
-        std::cout.precision(3);
-        std::cout << std::scientific << std::setw(8) << total_events << " | " << std::setw(8) << rep.avg_npp << " | " << std::setw(8)
-                  << rep.n_aggregates << " | " << std::setw(8) << rep.time << "s | " << std::setw(10)
-                  << (rep.device_ms > 0 ? 1e3 * rep.steps / rep.device_ms : 0.) << " | " << std::setw(10) << total_steps << std::endl;
-        if (rep.finished || rep.steps == 0) break;
+        pm.finished_flag = rep.finished != 0;
+        if (rep.steps == 0) {
+            if (!pm.finished_flag) throw DeviceError("calcul: the device loop made no progress");
+            break;
+        }
+        if (event) {
+            total_events++;
+            if (total_events % 20 == 1)
+                std::cout << std::setw(8) << "#" << " | " << std::setw(9) << "Npp_avg" << " | " << std::setw(8) << "NAgg" << " | " << std::setw(10)
+                          << "Time" << " | " << std::setw(10) << "CPU" << " | " << std::setw(7) << "contact" << " | " << std::setw(5) << "merge"
+                          << " | " << std::setw(5) << "split" << " | " << std::setw(9) << "disappear" << " | " << std::setw(10) << "nucleation"
+                          << " | " << std::setw(8) << "after" << std::endl;
+            const double elapse = double(clock() - cpu_start) / CLOCKS_PER_SEC;
+            std::cout.precision(3);
+            std::cout << std::scientific;
+            std::cout << std::setw(8) << total_events << " | " << std::setw(8) << rep.avg_npp << " | " << std::setw(8) << rep.n_aggregates << " | "
+                      << std::setw(8) << rep.time << "s" << " | " << std::setw(8) << elapse << "s" << " | ";
+            print_bool(rep.events > 0, 7);  // contact (a contact that is kept is a merge on this path)
+            print_bool(rep.events > 0, 5);  // merge
+            print_bool(false, 5);           // split     (u_sg < 0 only: out of scope)
+            print_bool(false, 9);           // disappear (oxidation only: out of scope)
+            std::cout << std::setw(10) << rep.nucleated << " | " << std::setw(8) << (n_iter + static_cast<size_t>(rep.steps) - 1) << std::endl;
+            std::cout.unsetf(std::ios_base::floatfield);
+            std::cout.precision(6);
+        }
+        n_iter = static_cast<size_t>(rep.n_iter_without_event);
+        n_sph = rep.n_spheres;
+        n_agg = rep.n_aggregates;
     }
+    save_advancement(pm, aggregates, dir);
     std::cout << " Final residence time=" << std::setw(4) << pm.time << "s" << std::endl;
     std::cout << "Final number of aggregates : " << aggregates.size() << std::endl;
+    std::cout << "Output files saved on: \"" << dir << "\"" << std::endl;
+    std::cout << std::endl;
     std::cout << "\nThe End\n" << std::endl;
+    (void)total_steps;
 }
 }  // namespace mcac

@@ -56,6 +56,7 @@ class PhysicalModel {
     size_t n_iter_without_event = 0;
     double cpu_limit = -1, cpu_event_limit = -1, physical_time_limit = -1;
     double write_Delta_t = -1;
+    bool finished_flag = false;  // PhysicalModel::finished() as evaluated by the device loop at the last loop top
     int mean_monomere_per_aggregate_limit = -1;
     size_t number_of_aggregates_limit = 1;
     int n_iter_without_event_limit = -1;
