@@ -814,16 +814,6 @@ bool finished(const mcac_gpu *h) {
     return false;
 }
 
-// what calcul() does between a merge and the next pick: refresh(), PhysicalModel::update, duplication test, re-sort
-int after_event(mcac_gpu *h) {
-    h->labels_valid = false;
-    h->cells_valid = false;
-    TRY(refresh_labels(h));
-    TRY(refresh_reduce(h));
-    TRY(pull_scalars(h));
-    return E_OK;
-}
-
 void prof_begin(mcac_gpu *h, int kind) {
     if (!h->profile) return;
     cudaEvent_t a, b;
