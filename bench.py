@@ -396,8 +396,15 @@ def main():
                 "algorithmic_bytes_per_launch": k9_bytes, "share_of_step": event_ms / dev_ms if dev_ms else None,
                 "sort_levels_per_launch": sum(r["sort_levels"] for r in reps) / sorts,
                 "sort_span_elements_per_launch": sum(r["sort_span_elements"] for r in reps) / sorts,
-                "phase_us_per_launch": {p: sum(r["event_phase_cycles"][i] for r in reps) / 1965.0 / sorts for i, p in enumerate(phases)},
-                "note": "latency-bound, not bandwidth-bound: ~18 dependent introsort levels x 5 grid barriers per launch",
+                "phase_us_per_launch": {**{p: sum(r["event_phase_cycles"][i] for r in reps) / 1965.0 / sorts for i, p in enumerate(phases)},
+                                        **{p: sum(r["tie_phase_cycles"][i] for r in reps) / 1965.0 / sorts
+                                           for i, p in enumerate(["tie_sparse_simulation", "tie_routing_pass"])}},
+                "tie_fast_path": {"sorts": sum(r["tie_sorts"] for r in reps), "of_sorts": sorts,
+                                  "levels_per_sort": sum(r["tie_levels"] for r in reps) / max(1, sum(r["tie_sorts"] for r in reps)),
+                                  "sparse_per_sort": sum(r["tie_sparse"] for r in reps) / max(1, sum(r["tie_sorts"] for r in reps)),
+                                  "handed_per_sort": sum(r["tie_handed"] for r in reps) / max(1, sum(r["tie_sorts"] for r in reps))},
+                "note": "latency-bound, not bandwidth-bound: dependent introsort levels x grid barriers; tie-dominated tables take the "
+                        "sparse fast path (csrc/tie_sort.cuh) for the top levels",
                 "commit_share_of_step": commit_ms / dev_ms if dev_ms else None, "search_share_of_step": search_ms / dev_ms if dev_ms else None,
                 "avg_commit_us": 1e3 * commit_ms / max(1, sum(r["commit_launches"] for r in reps)),
                 "avg_search_us": 1e3 * search_ms / n_launch}

@@ -89,6 +89,10 @@ typedef struct mcac_run_report {
     int64_t event_phase_cycles[8];
     int64_t n_iter_without_event, nucleated;   /* PhysicalModel::n_iter_without_event after the call; monomers nucleated by it */
     double total_volume, total_surface;       /* AggregatList::get_total_volume / surface as of the last PhysicalModel::update */
+    /* tie-dominated pick tables (csrc/tie_sort.cuh): SM cycles of the sparse simulation (one CTA) / of the routing pass (grid),
+     * sorts that took the fast path, levels it simulated, sparse elements and elements handed to the general sort (sums) */
+    int64_t tie_phase_cycles[2];
+    int64_t tie_sorts, tie_levels, tie_sparse, tie_handed;
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction

@@ -64,10 +64,12 @@ class RunReport(C.Structure):
                [(n, C.c_int64) for n in ["event_launches", "cells_launches", "sort_span_elements", "sort_levels"]] + \
                [("event_phase_cycles", C.c_int64 * 8)] + \
                [(n, C.c_int64) for n in ["n_iter_without_event", "nucleated"]] + \
-               [(n, C.c_double) for n in ["total_volume", "total_surface"]]
+               [(n, C.c_double) for n in ["total_volume", "total_surface"]] + \
+               [("tie_phase_cycles", C.c_int64 * 2)] + \
+               [(n, C.c_int64) for n in ["tie_sorts", "tie_levels", "tie_sparse", "tie_handed"]]
 
     def as_dict(self) -> dict:
-        return {n: (list(getattr(self, n)) if n == "event_phase_cycles" else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n.endswith("_phase_cycles") else getattr(self, n)) for n, _ in self._fields_}
 
 
 class SweepReport(C.Structure):

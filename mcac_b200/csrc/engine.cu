@@ -90,8 +90,15 @@ struct mcac_gpu {
     int coop_bps = 1, sort_local_span = 4096;
     int event_spare_sms = 8;  // MCAC_B200_EVENT_SPARE_SMS
     int event_smem_cap = 0;   // shared-memory staging of the block-local sort levels (entries; 0 = levels stay in HBM/L2)
+    size_t event_dyn_bytes = 0;  // dynamic shared memory of the event kernel's launches
     long long *event_work = nullptr;
-    long long event_work_seen[10] = {0};
+    long long event_work_seen[16] = {0};
+    // tie-dominated pick tables (tie_sort.cuh): plan + per-level rank tables; allocated with the state when the table can be large
+    tiesort::Plan *ts_plan = nullptr;
+    int *ts_R = nullptr, *ts_tbl = nullptr;
+    int ts_xcap = 0;
+    int ts_min_n = 32768;     // MCAC_B200_TIE_MIN_N (0 disables the fast path)
+    int ts_max_sparse = tiesort::kMaxSparse;  // MCAC_B200_TIE_MAX_SPARSE
     long long *part_ll = nullptr;
     double *part_d = nullptr;
     int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
@@ -207,6 +214,13 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     TRY(dev_alloc(h, &sb.fin_perm, agg_cap + 1));
     TRY(dev_alloc(h, &sb.fin_wk, agg_cap + 1));
     TRY(dev_alloc(h, &sb.active, 16));
+    h->ts_plan = nullptr; h->ts_R = nullptr; h->ts_tbl = nullptr; h->ts_xcap = 0;
+    if (h->ts_min_n > 0 && agg_cap >= h->ts_min_n) {
+        h->ts_xcap = std::max(1, std::min(h->ts_max_sparse, tiesort::kMaxSparse));
+        TRY(dev_alloc(h, &h->ts_plan, 1));
+        TRY(dev_alloc(h, &h->ts_R, (size_t)(tiesort::kMaxLevels + 1) * h->ts_xcap));
+        TRY(dev_alloc(h, &h->ts_tbl, (size_t)(tiesort::kMaxLevels + 1) * tiesort::kTblStride));
+    }
     TRY(dev_alloc(h, &h->scan64_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     TRY(dev_alloc(h, &h->cum_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     const size_t scan_n = (size_t)std::max<long long>(agg_cap, d.n_cells) + 2;
@@ -426,6 +440,12 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.local_span = h->sort_local_span;
     a.work = h->event_work;
     a.smem_cap = h->event_smem_cap;
+    a.smem_bytes = (int)h->event_dyn_bytes;
+    a.ts_plan = h->ts_plan;
+    a.ts_R = h->ts_R;
+    a.ts_tbl = h->ts_tbl;
+    a.ts_xcap = h->ts_xcap;
+    a.ts_min_n = h->ts_min_n;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
@@ -435,7 +455,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     const int want_blocks = std::max(1, div_up(h->sc_host.n_agg_slots + (h->prm.with_nucleation ? 4096 : 0), 2048));
     // a few SMs are left to the side stream (the overlapped Verlet cell rebuild cannot share an SM with a 512-thread, 120-register CTA)
     const int grid_blocks = std::min(std::max(1, h->coop_blocks - (h->overlap ? h->event_spare_sms : 0)), want_blocks);
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kEventThreads), args, (size_t)h->event_smem_cap * kSortStageBytesPerEntry, h->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kEventThreads), args, h->event_dyn_bytes, h->stream));
     h->launches++;
     h->labels_valid = true;
     if (defer_sync) {  // the caller reads the scalars after its next kernels and handles a failed sort (b_need == 99) there
@@ -941,6 +961,8 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
+        if (const char *e = getenv("MCAC_B200_TIE_MIN_N")) h->ts_min_n = std::max(0, atoi(e));
+        if (const char *e = getenv("MCAC_B200_TIE_MAX_SPARSE")) h->ts_max_sparse = std::max(1, atoi(e));
         // block-local sort levels staged in shared memory: (local_span + 2) entries of 48 B, if the SM has room for them
         h->event_smem_cap = 0;
         if (!getenv("MCAC_B200_NO_SORT_SMEM")) {
@@ -949,14 +971,22 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
             const long long want = (long long)(h->sort_local_span + 2) * kSortStageBytesPerEntry;
             if (want + 4096 <= max_optin / h->coop_bps) h->event_smem_cap = h->sort_local_span + 2;
         }
-        const size_t dyn = (size_t)h->event_smem_cap * kSortStageBytesPerEntry;
+        size_t dyn = (size_t)h->event_smem_cap * kSortStageBytesPerEntry;
+        if (h->ts_min_n > 0 && !getenv("MCAC_B200_NO_SORT_SMEM")) {  // scratch of the one-CTA sparse simulation (tie_sort.cuh)
+            int max_optin = 0;
+            cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+            const size_t need = sizeof(int) * (2 * (size_t)std::min(h->ts_max_sparse, tiesort::kMaxSparse) + 2 * tiesort::kTblStride + 16 + 2 * 1024);
+            if ((long long)need + 4096 <= max_optin / h->coop_bps) dyn = std::max(dyn, need);
+        }
         const void *efn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
         if (dyn > 0 && cudaFuncSetAttribute(efn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
             cudaGetLastError();
             h->event_smem_cap = 0;
+            dyn = 0;
         }
-        cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, (size_t)h->event_smem_cap * kSortStageBytesPerEntry)
-                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, (size_t)h->event_smem_cap * kSortStageBytesPerEntry);
+        h->event_dyn_bytes = dyn;
+        cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, dyn)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, dyn);
         if (coop && oe == cudaSuccess && occ > 0) h->coop_blocks = h->n_sm * std::min(occ, h->coop_bps);
         if (getenv("MCAC_B200_NO_COOP")) h->coop_blocks = 0;
         TRY(dev_alloc_persistent(h, &h->event_work, 16));
@@ -1559,12 +1589,17 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->nucleated = nucleated_total;
         report->total_volume = sc.total_volume;
         report->total_surface = sc.total_surface;
-        long long w[10] = {0};
+        long long w[16] = {0};
         cudaMemcpy(w, h->event_work, sizeof(w), cudaMemcpyDeviceToHost);
         report->sort_span_elements = w[0] - h->event_work_seen[0];
         report->sort_levels = w[1] - h->event_work_seen[1];
         for (int k = 0; k < 8; k++) report->event_phase_cycles[k] = w[2 + k] - h->event_work_seen[2 + k];
-        for (int k = 0; k < 10; k++) h->event_work_seen[k] = w[k];
+        for (int k = 0; k < 2; k++) report->tie_phase_cycles[k] = w[10 + k] - h->event_work_seen[10 + k];
+        report->tie_sorts = w[12] - h->event_work_seen[12];
+        report->tie_levels = w[13] - h->event_work_seen[13];
+        report->tie_sparse = w[14] - h->event_work_seen[14];
+        report->tie_handed = w[15] - h->event_work_seen[15];
+        for (int k = 0; k < 16; k++) h->event_work_seen[k] = w[k];
     }
     prof_collect(h, report);
     return E_OK;

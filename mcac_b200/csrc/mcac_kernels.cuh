@@ -8,6 +8,7 @@
 
 #include "../../include/mcac_b200.h"
 #include "mcac_device.cuh"
+#include "tie_sort.cuh"
 
 namespace mcacb {
 
@@ -2187,6 +2188,20 @@ struct EventArgs {
     int smem_cap;         // entries of dynamic shared memory per array available to the block-local levels (0 = none)
     int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
     long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
+    // tie-dominated tables (tie_sort.cuh): top levels simulated on the sparse elements only
+    tiesort::Plan *ts_plan;
+    int *ts_R, *ts_tbl;   // (kMaxLevels + 1) x ts_xcap sorted positions / x kTblStride bucket tables
+    int ts_xcap;          // 0 = fast path off
+    int ts_min_n;         // smallest table the fast path is tried on
+    int smem_bytes;       // dynamic shared memory of the launch
+};
+struct BlockTeam {  // tiesort's Team for one CTA
+    int tid, nthr;
+    int *ws;  // >= 32 ints of shared memory
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_min(int *p, int v) { atomicMin(p, v); }
+    __device__ __forceinline__ int exclusive_scan(int v) { int tot; return block_exclusive_scan(v, &tot, ws); }
 };
 namespace cgx = cooperative_groups;
 extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -2211,6 +2226,17 @@ __device__ __forceinline__ double block_max_fixed(double v, double *sm) {
     __syncthreads();
     double t = 0.;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) t = (t < sm[w]) ? sm[w] : t;
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ double block_min_fixed(double v, double *sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(kFull, v, o); v = (t < v) ? t : v; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = sm[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) t = (sm[w] < t) ? sm[w] : t;
     __syncthreads();
     return t;
 }
@@ -2244,23 +2270,26 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const int chunk_s = ((n_slots + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
     {
         long long cnt = 0;
-        double mx = 0., sv = 0., ss = 0.;
+        double mx = 0., sv = 0., ss = 0., mn = __longlong_as_double(0x7ff0000000000000LL);
         const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
         for (int s = lo + tid; s < hi; s += nthr) {
             if (!d.a_alive[s]) continue;
             cnt += 1;
             const double ts = d.a_ts[s];
             mx = (mx < ts) ? ts : mx;
+            mn = (ts < mn) ? ts : mn;
             sv += d.a_vol[s];
             ss += d.a_surf[s];
         }
         const long long c = block_sum_ll(cnt, sm_ll);
         const double bmx = block_max_fixed(mx, sm_d), bsv = block_sum_fixed(sv, sm_d), bss = block_sum_fixed(ss, sm_d);
+        const double bmn = block_min_fixed(mn, sm_d);
         if (tid == 0) {
             a.part_ll[blk] = c;
             a.part_d[blk] = bmx;
             a.part_d[nblk + blk] = bsv;
             a.part_d[2 * nblk + blk] = bss;
+            a.part_d[4 * nblk + blk] = bmn;
         }
     }
     grid.sync();
@@ -2268,40 +2297,61 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     // ---------------- phase B: labels; every block derives n_agg / max / totals in the same fixed order
     int n_agg = 0;
     double factor = sc.max_time_step;
+    bool ts_try = false;
+    double ts_W = 0.;
+    __shared__ int sh_exc;
     {
         long long base = 0, total = 0;
-        double mx = 0., sv = 0., ss = 0.;
+        double mx = 0., sv = 0., ss = 0., mn = __longlong_as_double(0x7ff0000000000000LL);
         for (int b = 0; b < nblk; b++) {  // sequential, same in every thread: deterministic
             const long long c = a.part_ll[b];
             if (b < blk) base += c;
             total += c;
             const double t = a.part_d[b];
             mx = (mx < t) ? t : mx;
+            const double tm = a.part_d[4 * nblk + b];
+            mn = (tm < mn) ? tm : mn;
             sv += a.part_d[nblk + b];
             ss += a.part_d[2 * nblk + b];
         }
         n_agg = (int)total;
         if (a.do_refresh) factor = mx;
         if (a.use_factor) factor = a.factor;
-        if (a.do_labels) {
+        // tie-dominated fast path (tie_sort.cuh): W = the largest weight = factor / (smallest time step); the elements below W are
+        // staged per chunk in label order (labels in tmp_a, weights in pre) while the labels are made
+        ts_try = a.do_sort && a.ts_xcap > 0 && !a.stable && n_agg >= a.ts_min_n && n_agg > a.local_span;
+        ts_W = factor / mn;
+        if (a.do_labels || ts_try) {
             const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
-            if (tid == 0) sh_carry = base;
+            double *st_w = reinterpret_cast<double *>(a.sb.pre);
+            if (tid == 0) { sh_carry = base; sh_exc = 0; }
             __syncthreads();
             for (int t0 = lo; t0 < hi; t0 += nthr) {
                 const int s = t0 + tid;
                 const int alive = (s < hi) ? d.a_alive[s] : 0;
+                double w = 0.;
+                int exc = 0;
+                if (ts_try && alive) { w = factor / d.a_ts[s]; exc = (w != ts_W) ? 1 : 0; }
                 int tot;
                 __shared__ int ws[32];
-                const int pre = block_exclusive_scan(alive, &tot, ws);
+                const int pre2 = block_exclusive_scan(alive | (exc << 16), &tot, ws);  // <= 512 of either per round
+                const int pre = pre2 & 0xffff;
                 if (s < hi) {
                     const int lab = (int)sh_carry + pre;
-                    if (alive) { d.label_of_slot[s] = lab; d.slot_of_label[lab] = s; }
-                    else d.label_of_slot[s] = -1;
+                    if (a.do_labels) {
+                        if (alive) { d.label_of_slot[s] = lab; d.slot_of_label[lab] = s; }
+                        else d.label_of_slot[s] = -1;
+                    }
+                    if (exc) {
+                        const int k = sh_exc + (pre2 >> 16);
+                        if (k < tiesort::kMaxSparse) { a.sb.tmp_a[lo + k] = lab; st_w[lo + k] = w; }
+                    }
                 }
                 __syncthreads();
-                if (tid == 0) sh_carry += tot;
+                if (tid == 0) { sh_carry += tot & 0xffff; sh_exc += tot >> 16; }
                 __syncthreads();
             }
+            if (tid == 0) a.part_ll[2048 + blk] = sh_exc;
         }
         if (gtid == 0) {
             if (a.do_refresh) {
@@ -2327,18 +2377,107 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const int n = n_agg;
     b.n = n;
     b.stable = a.stable;
-    for (long long i = gtid; i < n; i += gsize) {
-        b.perm[i] = (int)i;
-        b.wk[i] = factor / d.a_ts[d.slot_of_label[i]];
-        b.segf[i] = 0;
-        b.segl[i] = n;
-    }
-    if (gtid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
-    grid.sync();
     int lg = 0;
     while ((1LL << (lg + 1)) <= n) lg++;
     int depth = 2 * lg;
-    bool active = n > kSortLeaf;
+    int n_sort = n, delta = 0;  // the general sort below works on [0, n_sort) and writes its result at +delta
+    // ---- tie-dominated table: the top levels on the sparse elements only (tie_sort.cuh)
+    bool ts_on = false;
+    if (ts_try) {
+        long long x = 0;
+        for (int bb = 0; bb < nblk; bb++) x += a.part_ll[2048 + bb];
+        const int need = (2 * a.ts_xcap + 2 * tiesort::kTblStride + 16 + 2 * (nblk + 1)) * (int)sizeof(int);
+        ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && need <= a.smem_bytes;
+        if (ts_on) {
+            const int xs = (int)x;
+            int *st_pos = b.tmp_b;                                 // compact staged labels / weights of the sparse elements
+            double *st_w = reinterpret_cast<double *>(b.flags);
+            if (blk == 0) {
+                int *sm = reinterpret_cast<int *>(dyn_smem);
+                int *s_pos = sm, *s_sorted = s_pos + a.ts_xcap, *s_cnt = s_sorted + a.ts_xcap, *s_tbl = s_cnt + tiesort::kTblStride,
+                    *s_misc = s_tbl + tiesort::kTblStride, *s_base = s_misc + 16;
+                if (tid == 0) {
+                    int acc = 0;
+                    for (int bb = 0; bb < nblk; bb++) { s_base[bb] = acc; acc += (int)a.part_ll[2048 + bb]; }
+                    s_base[nblk] = acc;
+                }
+                __syncthreads();
+                const double *chunk_w = reinterpret_cast<const double *>(b.pre);
+                for (int id = tid; id < xs; id += nthr) {  // gather the per-chunk stages into one ascending list
+                    int lo = 0, hi = nblk;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_base[mid] <= id) lo = mid; else hi = mid; }
+                    const int src = lo * chunk_s + (id - s_base[lo]);
+                    st_pos[id] = b.tmp_a[src];
+                    st_w[id] = chunk_w[src];
+                }
+                __syncthreads();
+                __shared__ int ts_ws[32];
+                BlockTeam tm{tid, nthr, ts_ws};
+                tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, s_pos, s_sorted,
+                                    s_cnt, s_tbl, s_misc);
+                // the sparse elements of the handed-over segment
+                const int hf = a.ts_plan->hand_f, hlen = a.ts_plan->hand_l - hf;
+                for (int id = tid; id < xs; id += nthr) {
+                    const int p = s_pos[id] - hf;
+                    b.perm[p] = st_pos[id];
+                    b.wk[p] = st_w[id];
+                    b.segf[p] = 0;
+                    b.segl[p] = hlen;
+                }
+                if (tid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
+            }
+            grid.sync();
+            lap(8);
+            __shared__ tiesort::Plan sh_plan;
+            for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
+                reinterpret_cast<int *>(&sh_plan)[k] = reinterpret_cast<const int *>(a.ts_plan)[k];
+            __syncthreads();
+            if (sh_plan.fail) {  // introsort's heap-sort branch: the host falls back to libstdc++'s std::sort for this call
+                if (gtid == 0) sc.b_need = 99;
+                return;
+            }
+            const int hf = sh_plan.hand_f, hlen = sh_plan.hand_l - hf;
+            int shift0 = 0;
+            while ((n >> shift0) > tiesort::kBuckets - 1) shift0++;
+            const int *__restrict__ R = a.ts_R;
+            const int *__restrict__ T = a.ts_tbl;
+            bool any_bad = false;
+            for (long long i = gtid; i < n; i += gsize) {  // every W element: final position, or its place in the handed-over segment
+                const int r = tiesort::rank_lt(R, T, 0, shift0, (int)i);
+                if (r < xs && R[r] == (int)i) continue;
+                bool handed, bad = false;
+                const int p = tiesort::dense_route(sh_plan, R, T, a.ts_xcap, (int)i, handed, bad);
+                if (bad) { any_bad = true; continue; }
+                if (handed) {
+                    b.perm[p - hf] = (int)i;
+                    b.wk[p - hf] = ts_W;
+                    b.segf[p - hf] = 0;
+                    b.segl[p - hf] = hlen;
+                } else {
+                    b.fin_perm[p] = (int)i;
+                    b.fin_wk[p] = ts_W;
+                }
+            }
+            if (any_bad) b.active[2] = 1;
+            n_sort = hlen;
+            delta = hf;
+            depth = sh_plan.hand_depth;
+            if (gtid == 0 && a.work) { a.work[12] += 1; a.work[13] += sh_plan.n_levels; a.work[14] += xs; a.work[15] += hlen; }
+            grid.sync();
+            lap(9);
+        }
+    }
+    if (!ts_on) {
+        for (long long i = gtid; i < n; i += gsize) {
+            b.perm[i] = (int)i;
+            b.wk[i] = factor / d.a_ts[d.slot_of_label[i]];
+            b.segf[i] = 0;
+            b.segl[i] = n;
+        }
+        if (gtid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
+        grid.sync();
+    }
+    bool active = n_sort > kSortLeaf;
     auto pivot_of = [&](int f, int l) {  // __move_median_to_first(first, first+1, mid, last-1)
         const int pa = f + 1, pb = f + (l - f) / 2, pc = l - 1;
         const double ka = b.wk[pa], kb = b.wk[pb], kc = b.wk[pc];
@@ -2358,8 +2497,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     };
     // b.active: [0],[1] ping-pong "some segment still > 16", [2] fail, [4..7] ping-pong (min, max) of the span of active segments
     if (gtid == 0) {
-        if (active) pivot_of(0, n);
-        b.active[4] = 0; b.active[5] = n; b.active[6] = 0x7fffffff; b.active[7] = 0;
+        if (active) pivot_of(0, n_sort);
+        b.active[4] = 0; b.active[5] = n_sort; b.active[6] = 0x7fffffff; b.active[7] = 0;
     }
     int level = 0;
     bool fail = false, local = false;
@@ -2425,7 +2564,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             long long acc = 0;
             for (int i = lo + tid; i < hi; i += nthr) {
                 long long fl = 0;
-                if (i < n) {
+                if (i < n_sort) {
                     const int f = b.segf[i], l = b.segl[i];
                     if (l - f > kSortLeaf && i > f) {
                         const double kp = b.wk[f], kx = b.wk[i];
@@ -2491,8 +2630,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     }
                 }
                 if (bad) { act[2] = 1; continue; }
-                b.fin_perm[pos] = b.perm[i];
-                b.fin_wk[pos] = b.wk[i];
+                b.fin_perm[pos + delta] = b.perm[i];
+                b.fin_wk[pos + delta] = b.wk[i];
                 b.segf[i] = 0x7fffffff;  // done: inactive in every later phase
                 b.segl[i] = 0;
                 continue;
@@ -2582,7 +2721,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         return;
     }
     // ---- __final_insertion_sort per leaf
-    for (long long i = gtid; i < n; i += gsize) {
+    for (long long i = gtid; i < n_sort; i += gsize) {
         if (b.segf[i] != i) continue;
         const int f = (int)i, l = b.segl[i];
         for (int x = f + 1; x < l; x++) {
@@ -2595,9 +2734,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
             b.wk[y + 1] = kv; b.perm[y + 1] = lv;
         }
-        b.fin_perm[i] = b.perm[i];  // whole leaf, written by its leader after sorting it
-        b.fin_wk[i] = b.wk[i];
-        for (int x = f + 1; x < l; x++) { b.fin_perm[x] = b.perm[x]; b.fin_wk[x] = b.wk[x]; }
+        b.fin_perm[i + delta] = b.perm[i];  // whole leaf, written by its leader after sorting it
+        b.fin_wk[i + delta] = b.wk[i];
+        for (int x = f + 1; x < l; x++) { b.fin_perm[x + delta] = b.perm[x]; b.fin_wk[x + delta] = b.wk[x]; }
     }
     grid.sync();
     lap(5);

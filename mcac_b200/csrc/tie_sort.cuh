@@ -1,0 +1,258 @@
+// mcac_b200 — K9 fast path: AggregatList::sort_time_steps (aggregat_list.cpp:109-141) for TIE-DOMINATED weight tables.
+//
+// In monodisperse runs (C1, C3, C5) almost every aggregate is a monomer, all monomers share one 1/dt weight W, and W is the
+// LARGEST weight of the table (a bigger aggregate has a longer time step).  libstdc++'s introsort on such a table is a chain:
+// at every level the median-of-3 pivot is a W element, the Hoare partition sends the few lighter ("sparse") elements to the
+// left part and leaves a right part made of W elements only, whose further fate does not depend on the data (closed form,
+// `all_equal_final`).  So the top levels of the replayed sort need no pass over the table at all:
+//   * `plan_build` (ONE CTA, shared memory): simulates the top levels on the sparse elements only — their sorted positions,
+//     the number of Hoare swaps K and the partition point of each level — and leaves per-level rank tables in global memory;
+//   * `dense_route` (every thread of the grid, one W element each): follows an element through those levels with O(1) rank
+//     queries per level until it falls into an all-W right part (final position in closed form) or reaches the segment that
+//     is handed to the general level-synchronous sort (`k_event`), which finishes the small mixed remainder.
+// The result is the same permutation std::sort produces (tests/native/tie_sort_host.cpp checks this header against
+// libstdc++'s own __introsort_loop on the host; the GPU parity tests check it against the oracle).
+// The code is host/device neutral: a `Team` supplies tid / nthr / sync / atomics (serial on the host, one CTA on the device).
+#pragma once
+#ifdef __CUDACC__
+#define TS_HD __host__ __device__ __forceinline__
+#else
+#define TS_HD inline
+#endif
+
+namespace tiesort {
+
+constexpr int kLeaf = 16;            // libstdc++ _S_threshold
+constexpr int kMaxLevels = 14;       // top levels handled on the sparse elements
+constexpr int kBuckets = 8192;       // buckets of a rank table
+constexpr int kTblStride = kBuckets + 3;
+constexpr int kMaxSparse = 8192;     // most sparse elements the one-CTA simulation takes
+constexpr int kIntMax = 0x7fffffff;
+
+struct Level {
+    int f, l;    // segment [f, l) partitioned at this level
+    int pick;    // position __move_median_to_first swaps with f (it holds a W element)
+    int K;       // Hoare swaps of __unguarded_partition
+    int cut;     // its return value: children [f, cut) (mixed: next level) and [cut, l) (W only)
+    int depth;   // depth_limit after this level's decrement
+    int shift;   // bucket shift of this level's rank table
+    int pad;
+};
+struct Plan {
+    int n_levels;                     // levels simulated sparsely
+    int hand_f, hand_l, hand_depth;   // segment handed to the general sort, before its pivot move; depth_limit it starts with
+    int fail;                         // introsort's depth limit hit (heap-sort branch): caller falls back
+    int x;                            // sparse elements
+    int pad0, pad1;
+    double W;
+    Level lv[kMaxLevels];
+};
+
+// entries of the sorted list R with position < q; tbl[b] = entries whose bucket ((pos - f) >> shift) is below b
+template <class PR, class PT>
+TS_HD int rank_lt(PR R, PT tbl, int f, int shift, int q) {
+    const int b = (q - f) >> shift;
+    int j = tbl[b];
+    const int e = tbl[b + 1];
+    while (j < e && R[j] < q) j++;
+    return j;
+}
+// k-th (0-based) position of [f+1, l) that holds no sparse element
+template <class PR, class PT>
+TS_HD int select_dense(PR R, PT tbl, int f, int shift, int k) {
+    int q = f + 1 + k;
+    for (int it = 0; it < kMaxSparse + 2; it++) {  // monotone fixed point; q grows by at least one sparse element per round
+        const int q2 = f + 1 + k + rank_lt(R, tbl, f, shift, q + 1);
+        if (q2 == q) break;
+        q = q2;
+    }
+    return q;
+}
+
+// Final position of the element at `pos` of a segment [cf, cl) whose keys are all equal; the segment was created by a level whose
+// depth_limit (after its decrement) was dep_parent.  Equal keys: median-of-3 picks `mid`, the Hoare partition mirrors
+// [cf+1, cl-1], the cut falls at cf+1+(m-1)/2, leaves do not move.
+TS_HD int all_equal_final(int cf, int cl, int pos, int dep_parent, bool &bad) {
+    int dep = dep_parent;
+    if (cl - cf > kLeaf) {
+        if (dep == 0) { bad = true; return pos; }
+        dep--;
+    }
+    while (cl - cf > kLeaf) {
+        const int m = cl - cf, mid = cf + m / 2;
+        if (pos == cf) pos = mid;
+        else if (pos == mid) pos = cf;
+        if (pos > cf) pos = cf + cl - pos;
+        const int cutp = cf + 1 + (m - 1) / 2;
+        if (pos < cutp) cl = cutp;
+        else cf = cutp;
+        if (cl - cf > kLeaf) {
+            if (dep == 0) { bad = true; return pos; }
+            dep--;
+        }
+    }
+    return pos;
+}
+
+// A W element that starts at `pos`: its final position (handed == false) or its position inside the handed-over segment.
+template <class PR, class PT>
+TS_HD int dense_route(const Plan &P, PR R, PT tbl, int xcap, int pos, bool &handed, bool &bad) {
+    handed = false;
+    for (int t = 0; t < P.n_levels; t++) {
+        const Level L = P.lv[t];
+        PR Rt = R + (size_t)(t + 1) * xcap;
+        PT Tt = tbl + (size_t)(t + 1) * kTblStride;
+        if (pos == L.f) pos = L.pick;
+        else if (pos == L.pick) pos = L.f;
+        if (pos > L.f) {
+            const int ka = pos - (L.f + 1) - rank_lt(Rt, Tt, L.f, L.shift, pos);  // rank among the left stoppers (W elements)
+            if (ka < L.K) pos = L.l - 1 - ka;                                       // every position is a right stopper
+            else {
+                const int kb = L.l - 1 - pos;
+                if (kb < L.K) pos = select_dense(Rt, Tt, L.f, L.shift, kb);
+            }
+        }
+        if (pos >= L.cut) return all_equal_final(L.cut, L.l, pos, L.depth, bad);
+    }
+    handed = true;
+    return pos;
+}
+
+// Counting sort of the sparse positions into `s_sorted` + the bucket table `s_tbl`; both are also copied to (Rg, Tg).
+template <class Team>
+TS_HD int build_table(Team &tm, int x, const int *s_pos, int f, int l, int *s_sorted, int *s_cnt, int *s_tbl, int *Rg, int *Tg) {
+    int shift = 0;
+    while (((l - f) >> shift) > kBuckets - 1) shift++;
+    const int nbk = ((l - f) >> shift) + 1;  // buckets 0 .. nbk-1, table entries 0 .. nbk
+    for (int b = tm.tid; b <= nbk; b += tm.nthr) s_cnt[b] = 0;
+    tm.sync();
+    for (int id = tm.tid; id < x; id += tm.nthr) tm.atomic_add(&s_cnt[(s_pos[id] - f) >> shift], 1);
+    tm.sync();
+    {  // exclusive scan: thread t owns the entries [t*per, (t+1)*per)
+        const int per = (nbk + 1 + tm.nthr - 1) / tm.nthr;
+        const int lo = tm.tid * per, hi = (lo + per < nbk + 1) ? lo + per : nbk + 1;
+        int s = 0;
+        for (int b = lo; b < hi; b++) s += s_cnt[b];
+        int run = tm.exclusive_scan(s);
+        for (int b = lo; b < hi; b++) {
+            const int c = s_cnt[b];
+            s_tbl[b] = run;
+            s_cnt[b] = 0;  // becomes the scatter cursor
+            run += c;
+        }
+    }
+    tm.sync();
+    for (int id = tm.tid; id < x; id += tm.nthr) {
+        const int p = s_pos[id], b = (p - f) >> shift;
+        s_sorted[s_tbl[b] + tm.atomic_add(&s_cnt[b], 1)] = p;
+    }
+    tm.sync();
+    for (int b = tm.tid; b < nbk; b += tm.nthr) {  // order inside a bucket (the scatter order is arbitrary)
+        const int lo = s_tbl[b], hi = s_tbl[b + 1];
+        for (int i = lo + 1; i < hi; i++) {
+            const int v = s_sorted[i];
+            int j = i - 1;
+            while (j >= lo && s_sorted[j] > v) { s_sorted[j + 1] = s_sorted[j]; j--; }
+            s_sorted[j + 1] = v;
+        }
+    }
+    tm.sync();
+    for (int i = tm.tid; i < x; i += tm.nthr) Rg[i] = s_sorted[i];
+    for (int b = tm.tid; b <= nbk; b += tm.nthr) Tg[b] = s_tbl[b];
+    return shift;
+}
+
+// The sparse simulation.  st_pos (ascending) / st_w: label and weight of the x elements whose weight is below W; n: table size;
+// depth0 = 2*floor(log2(n)).  s_*: scratch of the team (x, x, kTblStride, kTblStride, 16 ints).
+// On return plan, R[(t+1)*xcap ..], tbl[(t+1)*kTblStride ..] describe levels t < n_levels, table 0 the initial positions, and
+// s_pos holds the positions of the sparse elements inside the handed-over segment.
+template <class Team>
+TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *st_w, double W, int depth0, int hand_min, Plan *plan,
+                      int *R, int *tbl, int xcap, int *s_pos, int *s_sorted, int *s_cnt, int *s_tbl, int *s_misc) {
+    for (int id = tm.tid; id < x; id += tm.nthr) s_pos[id] = st_pos[id];
+    tm.sync();
+    build_table(tm, x, s_pos, 0, n, s_sorted, s_cnt, s_tbl, R, tbl);
+    int f = 0, l = n, depth = depth0, t = 0;
+    for (;;) {
+        const int len = l - f;
+        if (len <= hand_min || len <= kLeaf || t == kMaxLevels || depth == 0) break;
+        const int pa = f + 1, pb = f + len / 2, pc = l - 1;
+        for (int k = tm.tid; k < 5; k += tm.nthr) s_misc[k] = -1;
+        tm.sync();
+        for (int id = tm.tid; id < x; id += tm.nthr) {
+            const int q = s_pos[id];
+            if (q == pa) s_misc[0] = id;
+            if (q == pb) s_misc[1] = id;
+            if (q == pc) s_misc[2] = id;
+            if (q == f) s_misc[3] = id;
+        }
+        tm.sync();
+        // __move_median_to_first(first, first+1, mid, last-1) with the plain `<` of sort_indexes
+        const double ka = s_misc[0] < 0 ? W : st_w[s_misc[0]], kb = s_misc[1] < 0 ? W : st_w[s_misc[1]], kc = s_misc[2] < 0 ? W : st_w[s_misc[2]];
+        int pick;
+        double kp;
+        if (ka < kb) {
+            if (kb < kc) { pick = pb; kp = kb; }
+            else if (ka < kc) { pick = pc; kp = kc; }
+            else { pick = pa; kp = ka; }
+        } else if (ka < kc) { pick = pa; kp = ka; }
+        else if (kb < kc) { pick = pc; kp = kc; }
+        else { pick = pb; kp = kb; }
+        const int at_f = s_misc[3];
+        if (kp != W) break;  // a sparse pivot: the rest goes to the general sort
+        depth--;
+        tm.sync();
+        if (tm.tid == 0 && at_f >= 0) s_pos[at_f] = pick;
+        tm.sync();
+        const int shift = build_table(tm, x, s_pos, f, l, s_sorted, s_cnt, s_tbl, R + (size_t)(t + 1) * xcap, tbl + (size_t)(t + 1) * kTblStride);
+        // K = first k with not (k < n_a and A[k] < B[k]); A[k] = k-th W position, B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1
+        const int M = len - 1, n_a = M - x;
+        if (tm.tid == 0) s_misc[4] = n_a;
+        tm.sync();
+        for (int j = tm.tid; j <= x; j += tm.nthr) {  // the k with exactly j sparse elements before A[k]: [lo, hi)
+            const int lo = j == 0 ? 0 : s_sorted[j - 1] - (f + 1) - (j - 1);
+            const int hi = j == x ? n_a : s_sorted[j] - (f + 1) - j;
+            const int need = M - 1 - j;
+            const int kmin = need <= 0 ? 0 : (need + 1) / 2;
+            const int k = lo > kmin ? lo : kmin;
+            if (k < hi) tm.atomic_min(&s_misc[4], k);
+        }
+        tm.sync();
+        const int K = s_misc[4];
+        const int aK = K < n_a ? select_dense(s_sorted, s_tbl, f, shift, K) : kIntMax;
+        const int bK = K > 0 ? l - K : l;
+        const int cut = aK < bK ? aK : bK;
+        for (int id = tm.tid; id < x; id += tm.nthr) {  // a sparse element is a right stopper only
+            const int kb2 = l - 1 - s_pos[id];
+            if (kb2 < K) s_pos[id] = select_dense(s_sorted, s_tbl, f, shift, kb2);
+        }
+        if (tm.tid == 0) {
+            Level L;
+            L.f = f; L.l = l; L.pick = pick; L.K = K; L.cut = cut; L.depth = depth; L.shift = shift; L.pad = 0;
+            plan->lv[t] = L;
+        }
+        l = cut;
+        t++;
+        tm.sync();
+    }
+    if (tm.tid == 0) {
+        plan->n_levels = t;
+        plan->hand_f = f;
+        plan->hand_l = l;
+        plan->hand_depth = depth;
+        plan->fail = (depth == 0 && l - f > kLeaf) ? 1 : 0;
+        plan->x = x;
+        plan->W = W;
+    }
+    tm.sync();
+}
+
+struct SerialTeam {
+    int tid = 0, nthr = 1;
+    void sync() {}
+    int atomic_add(int *p, int v) { const int o = *p; *p += v; return o; }
+    void atomic_min(int *p, int v) { if (v < *p) *p = v; }
+    int exclusive_scan(int) { return 0; }
+};
+
+}  // namespace tiesort

@@ -177,6 +177,40 @@ def test_device_sort_against_std_sort_on_random_weights():
         np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))  # np.cumsum is the sequential sum
 
 
+@pytest.mark.parametrize("n,frac,classes,local", [(30000, 0.003, 3, 64), (30000, 0.05, 0, 4096), (200000, 0.0, 1, 4096),
+                                                  (200000, 0.002, 0, 4096), (200000, 0.03, 4, 512), (65537, 0.01, 2, 4096)])
+def test_tie_dominated_sort_fast_path_is_std_sort(n, frac, classes, local, monkeypatch):
+    """Tables where one weight dominates and is the largest (monodisperse runs: every monomer ties) take the sparse fast path of
+    the event kernel (csrc/tie_sort.cuh); its permutation must be libstdc++'s std::sort order, like the general replay's."""
+    from oracle_lib import introsort_order
+    monkeypatch.setenv("MCAC_B200_TIE_MIN_N", "1000")
+    monkeypatch.setenv("MCAC_B200_SORT_LOCAL", str(local))
+    text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 5, "n_verlet_divisions": 8}, "monomers": {"number": n},
+                                                   "environment": {"volume_fraction": "10e-6"}}))
+    hm = HostModel(text).state()
+    assert hm["n_agg"] == n
+    rng = np.random.default_rng(n + local)
+    ts = np.full(n, 0.5)
+    sparse = rng.random(n) < frac
+    ts[sparse] = (0.5 + rng.integers(1, classes + 1, sparse.sum())) if classes else (0.5 + rng.random(sparse.sum()))
+    st = dict(hm)
+    af = hm["agg_fields"].copy()
+    af[3] = ts  # TIME_STEP column
+    st["agg_fields"] = af
+    sim = Simulation(text)
+    sim.upload(st)
+    sim.sort_time_steps(2.0)
+    idx, cum = sim.pick_table()
+    keys = 2.0 / ts
+    ref = introsort_order(keys)
+    np.testing.assert_array_equal(idx, ref)
+    np.testing.assert_array_equal(keys[idx], np.sort(keys))
+    if n <= 65536:
+        np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))
+    rep, _ = sim.run(0)
+    assert rep["tie_sorts"] >= 1 and rep["tie_sparse"] >= int(sparse.sum())
+
+
 @pytest.mark.parametrize("name,steps", [("surface_growth_seed42", 2500), ("caps_seed7", 4000), ("pytest_seed42", 20000),
                                         ("brownian_seed42", 4000)])
 def test_general_step_loop_growth_picklast_nocollision(name, steps):
@@ -279,10 +313,13 @@ def test_batch_width_does_not_change_the_trajectory():
 
 
 @pytest.mark.parametrize("env", [{"MCAC_B200_FORCE_SORT_FAIL": "3"}, {"MCAC_B200_NO_OVERLAP": "1"}, {"MCAC_B200_SEARCH_GROUP": "0"},
-                                 {"MCAC_B200_SEARCH_GROUP": "4", "MCAC_B200_SEARCH_MB": "4"}, {"MCAC_B200_NO_SORT_SMEM": "1"}])
+                                 {"MCAC_B200_SEARCH_GROUP": "4", "MCAC_B200_SEARCH_MB": "4"}, {"MCAC_B200_NO_SORT_SMEM": "1"},
+                                 {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "64"},
+                                 {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "512", "MCAC_B200_TIE_MAX_SPARSE": "50"}])
 def test_execution_variants_do_not_change_the_trajectory(env, monkeypatch):
     """Scheduling choices must be invisible in the results: a device sort that gives up (every 3rd one here) falls back to the
-    multi-launch sort and the batch is redone; serialised vs overlapped cell rebuild; wide-only vs narrow-group contact search."""
+    multi-launch sort and the batch is redone; serialised vs overlapped cell rebuild; wide-only vs narrow-group contact search;
+    the sparse fast path of the pick-table sort (tie_sort.cuh) forced onto this small table, with and without running out of room."""
     g = Golden("c3_small_seed42")
     text = ini_text(merged_config(g.base, g.overrides))
     base = Simulation(text)
@@ -292,6 +329,11 @@ def test_execution_variants_do_not_change_the_trajectory(env, monkeypatch):
     var = Simulation(text)
     r1, rec1 = var.run(15000, batch=256, records=15000)
     assert r0["steps"] == r1["steps"] and r0["events"] == r1["events"] and r0["events"] > 10
+    assert r0["tie_sorts"] == 0
+    if "MCAC_B200_TIE_MIN_N" in env:
+        assert r1["tie_sorts"] > 10 and r1["tie_levels"] >= 2 * r1["tie_sorts"]
+        if "MCAC_B200_TIE_MAX_SPARSE" in env:
+            assert r1["tie_sorts"] < r1["sorts"]  # more than 50 non-monomers later in the run: general sort again
     for f in INT_FIELDS + FP_FIELDS:
         np.testing.assert_array_equal(rec0[f], rec1[f], err_msg=f)
     s0, s1 = base.state(), var.state()

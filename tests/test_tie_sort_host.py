@@ -1,0 +1,16 @@
+"""Host check of the K9 fast path for tie-dominated pick tables (mcac_b200/csrc/tie_sort.cuh): the header is host/device neutral,
+so its sparse simulation + routing are run here on the CPU against libstdc++'s own std::sort / __introsort_loop (the routine
+AggregatList::sort_time_steps uses, aggregat_list.cpp:109-123) on thousands of random tie-dominated tables."""
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_tie_sort_header_reproduces_std_sort(tmp_path):
+    exe = tmp_path / "tie_sort_host"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", str(exe), str(ROOT / "tests" / "native" / "tie_sort_host.cpp")])
+    for seed in (1, 2):
+        out = subprocess.run([str(exe), "400", str(seed)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.startswith("ok 400 cases"), out.stdout
