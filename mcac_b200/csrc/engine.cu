@@ -218,8 +218,8 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     if (h->ts_min_n > 0 && agg_cap >= h->ts_min_n) {
         h->ts_xcap = std::max(1, std::min(h->ts_max_sparse, tiesort::kMaxSparse));
         TRY(dev_alloc(h, &h->ts_plan, 1));
-        TRY(dev_alloc(h, &h->ts_R, (size_t)(tiesort::kMaxLevels + 1) * h->ts_xcap));
-        TRY(dev_alloc(h, &h->ts_tbl, (size_t)(tiesort::kMaxLevels + 1) * tiesort::kTblStride));
+        TRY(dev_alloc(h, &h->ts_R, (size_t)tiesort::kMaxLevels * h->ts_xcap));
+        TRY(dev_alloc(h, &h->ts_tbl, (size_t)tiesort::kMaxLevels * tiesort::kTblStride));
     }
     TRY(dev_alloc(h, &h->scan64_sums, agg_cap / (kScanBlock * kScanItems) + 8));
     TRY(dev_alloc(h, &h->cum_sums, agg_cap / (kScanBlock * kScanItems) + 8));
@@ -975,7 +975,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (h->ts_min_n > 0 && !getenv("MCAC_B200_NO_SORT_SMEM")) {  // scratch of the one-CTA sparse simulation (tie_sort.cuh)
             int max_optin = 0;
             cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-            const size_t need = sizeof(int) * (2 * (size_t)std::min(h->ts_max_sparse, tiesort::kMaxSparse) + 2 * tiesort::kTblStride + 16 + 2 * 1024);
+            const size_t need = sizeof(int) * (4 * (size_t)std::min(h->ts_max_sparse, tiesort::kMaxSparse) + tiesort::kTblStride + 16 + 2 * 1024);
             if ((long long)need + 4096 <= max_optin / h->coop_bps) dyn = std::max(dyn, need);
         }
         const void *efn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;

@@ -2272,14 +2272,27 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         long long cnt = 0;
         double mx = 0., sv = 0., ss = 0., mn = __longlong_as_double(0x7ff0000000000000LL);
         const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
-        for (int s = lo + tid; s < hi; s += nthr) {
-            if (!d.a_alive[s]) continue;
-            cnt += 1;
-            const double ts = d.a_ts[s];
-            mx = (mx < ts) ? ts : mx;
-            mn = (ts < mn) ? ts : mn;
-            sv += d.a_vol[s];
-            ss += d.a_surf[s];
+        for (int s0 = lo + tid; s0 < hi; s0 += 4 * nthr) {  // four rounds of loads in flight; same summation order as one by one
+            int al[4];
+            double ts[4], vv[4], sf[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int s = s0 + j * nthr;
+                const bool ok = s < hi;
+                al[j] = ok ? d.a_alive[s] : 0;
+                ts[j] = ok ? d.a_ts[s] : 0.;
+                vv[j] = ok ? d.a_vol[s] : 0.;
+                sf[j] = ok ? d.a_surf[s] : 0.;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!al[j]) continue;
+                cnt += 1;
+                mx = (mx < ts[j]) ? ts[j] : mx;
+                mn = (ts[j] < mn) ? ts[j] : mn;
+                sv += vv[j];
+                ss += sf[j];
+            }
         }
         const long long c = block_sum_ll(cnt, sm_ll);
         const double bmx = block_max_fixed(mx, sm_d), bsv = block_sum_fixed(sv, sm_d), bss = block_sum_fixed(ss, sm_d);
@@ -2322,30 +2335,50 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         ts_try = a.do_sort && a.ts_xcap > 0 && !a.stable && n_agg >= a.ts_min_n && n_agg > a.local_span;
         ts_W = factor / mn;
         if (a.do_labels || ts_try) {
+            // four consecutive slots per thread and round: one block scan per 4 * blockDim slots
             const int lo = blk * chunk_s, hi = min(n_slots, lo + chunk_s);
             double *st_w = reinterpret_cast<double *>(a.sb.pre);
+            unsigned char *is_sparse = reinterpret_cast<unsigned char *>(a.sb.cut);  // per label, read by the routing pass
             if (tid == 0) { sh_carry = base; sh_exc = 0; }
             __syncthreads();
-            for (int t0 = lo; t0 < hi; t0 += nthr) {
-                const int s = t0 + tid;
-                const int alive = (s < hi) ? d.a_alive[s] : 0;
-                double w = 0.;
-                int exc = 0;
-                if (ts_try && alive) { w = factor / d.a_ts[s]; exc = (w != ts_W) ? 1 : 0; }
+            for (int t0 = lo; t0 < hi; t0 += 4 * nthr) {
+                const int s0 = t0 + 4 * tid;
+                int al[4], ex[4];
+                double w[4];
+                if (s0 + 3 < hi) {
+                    const int4 v = *reinterpret_cast<const int4 *>(d.a_alive + s0);  // lo and t0 are multiples of 512
+                    al[0] = v.x; al[1] = v.y; al[2] = v.z; al[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) al[j] = (s0 + j < hi) ? d.a_alive[s0 + j] : 0;
+                }
+                int na = 0, ne = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    w[j] = 0.;
+                    ex[j] = 0;
+                    if (ts_try && al[j]) { w[j] = factor / d.a_ts[s0 + j]; ex[j] = (w[j] != ts_W) ? 1 : 0; }
+                    na += al[j];
+                    ne += ex[j];
+                }
                 int tot;
                 __shared__ int ws[32];
-                const int pre2 = block_exclusive_scan(alive | (exc << 16), &tot, ws);  // <= 512 of either per round
-                const int pre = pre2 & 0xffff;
-                if (s < hi) {
-                    const int lab = (int)sh_carry + pre;
+                const int pre2 = block_exclusive_scan(na | (ne << 16), &tot, ws);  // <= 2048 of either per round
+                int lab = (int)sh_carry + (pre2 & 0xffff), k = sh_exc + (pre2 >> 16);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int s = s0 + j;
+                    if (s >= hi) break;
                     if (a.do_labels) {
-                        if (alive) { d.label_of_slot[s] = lab; d.slot_of_label[lab] = s; }
+                        if (al[j]) { d.label_of_slot[s] = lab; d.slot_of_label[lab] = s; }
                         else d.label_of_slot[s] = -1;
                     }
-                    if (exc) {
-                        const int k = sh_exc + (pre2 >> 16);
-                        if (k < tiesort::kMaxSparse) { a.sb.tmp_a[lo + k] = lab; st_w[lo + k] = w; }
+                    if (ts_try && al[j]) is_sparse[lab] = (unsigned char)ex[j];
+                    if (ex[j]) {
+                        if (k < tiesort::kMaxSparse) { a.sb.tmp_a[lo + k] = lab; st_w[lo + k] = w[j]; }
+                        k++;
                     }
+                    lab += al[j];
                 }
                 __syncthreads();
                 if (tid == 0) { sh_carry += tot & 0xffff; sh_exc += tot >> 16; }
@@ -2386,7 +2419,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     if (ts_try) {
         long long x = 0;
         for (int bb = 0; bb < nblk; bb++) x += a.part_ll[2048 + bb];
-        const int need = (2 * a.ts_xcap + 2 * tiesort::kTblStride + 16 + 2 * (nblk + 1)) * (int)sizeof(int);
+        const int need = (4 * a.ts_xcap + tiesort::kTblStride + 16 + 2 * (nblk + 1)) * (int)sizeof(int);
         ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && need <= a.smem_bytes;
         if (ts_on) {
             const int xs = (int)x;
@@ -2394,14 +2427,19 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             double *st_w = reinterpret_cast<double *>(b.flags);
             if (blk == 0) {
                 int *sm = reinterpret_cast<int *>(dyn_smem);
-                int *s_pos = sm, *s_sorted = s_pos + a.ts_xcap, *s_cnt = s_sorted + a.ts_xcap, *s_tbl = s_cnt + tiesort::kTblStride,
+                int *a_s = sm, *a_i = a_s + a.ts_xcap, *b_s = a_i + a.ts_xcap, *b_i = b_s + a.ts_xcap, *s_tbl = b_i + a.ts_xcap,
                     *s_misc = s_tbl + tiesort::kTblStride, *s_base = s_misc + 16;
-                if (tid == 0) {
-                    int acc = 0;
-                    for (int bb = 0; bb < nblk; bb++) { s_base[bb] = acc; acc += (int)a.part_ll[2048 + bb]; }
-                    s_base[nblk] = acc;
+                __shared__ int ts_ws[32];
+                for (int b0 = 0; b0 < nblk; b0 += nthr) {  // exclusive scan of the per-chunk counts (one round: nblk <= blockDim)
+                    const int bb = b0 + tid;
+                    const int c = bb < nblk ? (int)a.part_ll[2048 + bb] : 0;
+                    int tot;
+                    const int pre = block_exclusive_scan(c, &tot, ts_ws);
+                    const int carry = b0 == 0 ? 0 : s_base[b0];
+                    if (bb < nblk) s_base[bb] = carry + pre;
+                    if (tid == 0) s_base[min(b0 + nthr, nblk)] = carry + tot;
+                    __syncthreads();
                 }
-                __syncthreads();
                 const double *chunk_w = reinterpret_cast<const double *>(b.pre);
                 for (int id = tid; id < xs; id += nthr) {  // gather the per-chunk stages into one ascending list
                     int lo = 0, hi = nblk;
@@ -2411,14 +2449,13 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     st_w[id] = chunk_w[src];
                 }
                 __syncthreads();
-                __shared__ int ts_ws[32];
                 BlockTeam tm{tid, nthr, ts_ws};
-                tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, s_pos, s_sorted,
-                                    s_cnt, s_tbl, s_misc);
+                tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, a_s, a_i, b_s, b_i,
+                                    s_tbl, s_misc);
                 // the sparse elements of the handed-over segment
                 const int hf = a.ts_plan->hand_f, hlen = a.ts_plan->hand_l - hf;
-                for (int id = tid; id < xs; id += nthr) {
-                    const int p = s_pos[id] - hf;
+                for (int j = tid; j < xs; j += nthr) {
+                    const int p = a_s[j] - hf, id = a_i[j];
                     b.perm[p] = st_pos[id];
                     b.wk[p] = st_w[id];
                     b.segf[p] = 0;
@@ -2437,25 +2474,74 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 return;
             }
             const int hf = sh_plan.hand_f, hlen = sh_plan.hand_l - hf;
-            int shift0 = 0;
-            while ((n >> shift0) > tiesort::kBuckets - 1) shift0++;
             const int *__restrict__ R = a.ts_R;
             const int *__restrict__ T = a.ts_tbl;
+            const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
             bool any_bad = false;
-            for (long long i = gtid; i < n; i += gsize) {  // every W element: final position, or its place in the handed-over segment
-                const int r = tiesort::rank_lt(R, T, 0, shift0, (int)i);
-                if (r < xs && R[r] == (int)i) continue;
-                bool handed, bad = false;
-                const int p = tiesort::dense_route(sh_plan, R, T, a.ts_xcap, (int)i, handed, bad);
-                if (bad) { any_bad = true; continue; }
-                if (handed) {
-                    b.perm[p - hf] = (int)i;
-                    b.wk[p - hf] = ts_W;
-                    b.segf[p - hf] = 0;
-                    b.segl[p - hf] = hlen;
-                } else {
-                    b.fin_perm[p] = (int)i;
-                    b.fin_wk[p] = ts_W;
+            // Every W element: final position, or its place in the handed-over segment.  kRoute elements per thread advance level
+            // by level together, so that their table look-ups (independent of each other) are in flight at the same time.
+            constexpr int kRoute = 4;
+            for (long long i0 = gtid; i0 < n; i0 += gsize * kRoute) {
+                int pos[kRoute];
+                bool live[kRoute];
+#pragma unroll
+                for (int j = 0; j < kRoute; j++) {
+                    const long long i = i0 + j * gsize;
+                    pos[j] = (int)i;
+                    live[j] = i < n && is_sparse[i < n ? i : 0] == 0;
+                }
+                for (int t = 0; t < sh_plan.n_levels; t++) {
+                    if (!(live[0] | live[1] | live[2] | live[3])) break;
+                    const tiesort::Level L = sh_plan.lv[t];
+                    const int *__restrict__ Rt = R + (size_t)t * a.ts_xcap;
+                    const int *__restrict__ Tt = T + (size_t)t * tiesort::kTblStride;
+                    int lo_[kRoute], hi_[kRoute];
+#pragma unroll
+                    for (int j = 0; j < kRoute; j++) {  // pivot move + bucket bounds (dead lanes look at a valid dummy position)
+                        int p = live[j] ? pos[j] : L.f + 1;
+                        if (p == L.f) p = L.pick;
+                        else if (p == L.pick) p = L.f;
+                        pos[j] = p;
+                        const int bkt = (p - L.f) >> L.shift;
+                        lo_[j] = Tt[bkt];
+                        hi_[j] = Tt[bkt + 1];
+                    }
+#pragma unroll
+                    for (int j = 0; j < kRoute; j++) {
+                        if (!live[j]) continue;
+                        int p = pos[j];
+                        if (p > L.f) {
+                            int r = lo_[j];
+                            while (r < hi_[j] && Rt[r] < p) r++;
+                            const int ka = p - (L.f + 1) - r;
+                            if (ka < L.K) p = L.l - 1 - ka;
+                            else {
+                                const int kb = L.l - 1 - p;
+                                if (kb < L.K) p = tiesort::select_dense(Rt, Tt, L.f, L.shift, kb);
+                            }
+                        }
+                        if (p >= L.cut) {
+                            bool bad = false;
+                            const int fp = tiesort::all_equal_final(L.cut, L.l, p, L.depth, bad);
+                            if (bad) any_bad = true;
+                            else {  // straight into the pick table; its weight (W) is implied by fp >= hand_l
+                                const int lab = (int)(i0 + j * gsize);
+                                d.sorted_slot[fp] = d.slot_of_label[lab];
+                                a.sorted_label[fp] = lab;
+                            }
+                            live[j] = false;
+                        }
+                        pos[j] = p;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kRoute; j++) {
+                    if (!live[j]) continue;
+                    const int p = pos[j] - hf;
+                    b.perm[p] = (int)(i0 + j * gsize);
+                    b.wk[p] = ts_W;
+                    b.segf[p] = 0;
+                    b.segl[p] = hlen;
                 }
             }
             if (any_bad) b.active[2] = 1;
@@ -2576,26 +2662,48 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 b.flags[i] = fl;
                 acc += fl;
             }
-            const long long t = block_sum_ll(acc, sm_ll);
-            if (tid == 0) a.part_ll[eblk] = t;
+            if (enblk > 1) {  // chunk sums feed the other blocks' scan bases
+                const long long t = block_sum_ll(acc, sm_ll);
+                if (tid == 0) a.part_ll[eblk] = t;
+            }
         }
         barrier();
         // ---- exclusive scan of the packed flags over the span
         {
-            long long base = 0;
-            for (int bb = tid; bb < eblk; bb += nthr) base += a.part_ll[bb];
-            base = block_sum_ll(base, sm_ll);
+            long long carry = 0;  // the same value in every thread
+            if (eblk > 0) {
+                for (int bb = tid; bb < eblk; bb += nthr) carry += a.part_ll[bb];
+                carry = block_sum_ll(carry, sm_ll);
+            }
             const int lo = amin + eblk * chunk, hi = min(amax + 1, lo + chunk);
-            if (tid == 0) sh_carry = base;
-            __syncthreads();
-            for (int t0 = lo; t0 < hi; t0 += nthr) {
-                const int i = t0 + tid;
-                const long long v = (i < hi) ? b.flags[i] : 0;
-                long long tot;
-                const long long pre = block_exclusive_scan_ll(v, &tot, sm_ll);
-                if (i < hi) b.pre[i] = sh_carry + pre;
+            // 16 rounds of blockDim elements at a time: warp scans of every round first, ONE block scan over the (round, warp)
+            // totals, then the warp scans again with their bases — 5 CTA barriers per 8192 elements instead of 5 per 512
+            constexpr int kRounds = 16;
+            __shared__ long long sh_wt[kRounds * (kEventThreads / 32) + 1];
+            const int lane = tid & 31, wrp = tid >> 5, nw = nthr >> 5;
+            for (int t0 = lo; t0 < hi; t0 += kRounds * nthr) {
+                const int nr = min(kRounds, (hi - t0 + nthr - 1) / nthr);
+                for (int r = 0; r < nr; r++) {
+                    const int i = t0 + r * nthr + tid;
+                    const long long inc = warp_inclusive_scan_ll((i < hi) ? b.flags[i] : 0, lane);
+                    if (lane == 31) sh_wt[r * nw + wrp] = inc;
+                }
                 __syncthreads();
-                if (tid == 0) sh_carry += tot;
+                {
+                    const int m = nr * nw;
+                    long long tot;
+                    const long long pre = block_exclusive_scan_ll(tid < m ? sh_wt[tid] : 0, &tot, sm_ll);
+                    if (tid < m) sh_wt[tid] = pre;
+                    if (tid == 0) sh_wt[kRounds * (kEventThreads / 32)] = tot;
+                    __syncthreads();
+                }
+                for (int r = 0; r < nr; r++) {
+                    const int i = t0 + r * nthr + tid;
+                    const long long v = (i < hi) ? b.flags[i] : 0;
+                    const long long inc = warp_inclusive_scan_ll(v, lane);
+                    if (i < hi) b.pre[i] = carry + sh_wt[r * nw + wrp] + inc - v;
+                }
+                carry += sh_wt[kRounds * (kEventThreads / 32)];
                 __syncthreads();
             }
         }
@@ -2740,18 +2848,19 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     }
     grid.sync();
     lap(5);
-    // ---- cumulative_time_steps
+    // ---- cumulative_time_steps (sorted weights: the general sort's output inside [delta, delta + n_sort), W everywhere else)
+    auto fw = [&](int i) { return (i >= delta && i < delta + n_sort) ? b.fin_wk[i] : ts_W; };
     if (n <= a.cum_sequential_max) {
         if (gtid == 0) {
-            double acc = b.fin_wk[0];
+            double acc = fw(0);
             d.cum[0] = acc;
-            for (int i = 1; i < n; i++) { acc = acc + b.fin_wk[i]; d.cum[i] = acc; }
+            for (int i = 1; i < n; i++) { acc = acc + fw(i); d.cum[i] = acc; }
         }
     } else {
         const int chunk_c = ((n + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
         const int lo = blk * chunk_c, hi = min(n, lo + chunk_c);
         double acc = 0.;
-        for (int i = lo + tid; i < hi; i += nthr) acc += b.fin_wk[i];
+        for (int i = lo + tid; i < hi; i += nthr) acc += fw(i);
         const double t = block_sum_fixed(acc, sm_d);
         if (tid == 0) a.part_d[3 * nblk + blk] = t;
         grid.sync();
@@ -2763,7 +2872,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         __syncthreads();
         for (int t0 = lo; t0 < hi; t0 += nthr) {
             const int i = t0 + tid;
-            const double v = (i < hi) ? b.fin_wk[i] : 0.;
+            const double v = (i < hi) ? fw(i) : 0.;
             double inc = v;
             const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -2783,7 +2892,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     }
     grid.sync();
     lap(6);
-    for (long long i = gtid; i < n; i += gsize) {
+    for (long long i = delta + gtid; i < delta + n_sort; i += gsize) {  // (the routing pass wrote the rest of a tie-dominated table)
         const int lab = b.fin_perm[i];
         d.sorted_slot[i] = d.slot_of_label[lab];
         a.sorted_label[i] = lab;

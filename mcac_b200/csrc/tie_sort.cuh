@@ -5,8 +5,9 @@
 // at every level the median-of-3 pivot is a W element, the Hoare partition sends the few lighter ("sparse") elements to the
 // left part and leaves a right part made of W elements only, whose further fate does not depend on the data (closed form,
 // `all_equal_final`).  So the top levels of the replayed sort need no pass over the table at all:
-//   * `plan_build` (ONE CTA, shared memory): simulates the top levels on the sparse elements only — their sorted positions,
-//     the number of Hoare swaps K and the partition point of each level — and leaves per-level rank tables in global memory;
+//   * `plan_build` (ONE CTA, shared memory): simulates the top levels on the sparse elements only — their sorted positions
+//     (kept sorted in closed form, nothing is re-sorted), the number of Hoare swaps K and the partition point of each level —
+//     and leaves per-level rank tables in global memory;
 //   * `dense_route` (every thread of the grid, one W element each): follows an element through those levels with O(1) rank
 //     queries per level until it falls into an all-W right part (final position in closed form) or reaches the segment that
 //     is handed to the general level-synchronous sort (`k_event`), which finishes the small mixed remainder.
@@ -43,7 +44,8 @@ struct Plan {
     int hand_f, hand_l, hand_depth;   // segment handed to the general sort, before its pivot move; depth_limit it starts with
     int fail;                         // introsort's depth limit hit (heap-sort branch): caller falls back
     int x;                            // sparse elements
-    int pad0, pad1;
+    int shift0;                       // bucket shift of table 0 (initial positions over [0, n))
+    int nb;                           // buckets of a rank table (power of two >= x, 256 .. kBuckets)
     double W;
     Level lv[kMaxLevels];
 };
@@ -100,8 +102,8 @@ TS_HD int dense_route(const Plan &P, PR R, PT tbl, int xcap, int pos, bool &hand
     handed = false;
     for (int t = 0; t < P.n_levels; t++) {
         const Level L = P.lv[t];
-        PR Rt = R + (size_t)(t + 1) * xcap;
-        PT Tt = tbl + (size_t)(t + 1) * kTblStride;
+        PR Rt = R + (size_t)t * xcap;
+        PT Tt = tbl + (size_t)t * kTblStride;
         if (pos == L.f) pos = L.pick;
         else if (pos == L.pick) pos = L.f;
         if (pos > L.f) {
@@ -118,77 +120,58 @@ TS_HD int dense_route(const Plan &P, PR R, PT tbl, int xcap, int pos, bool &hand
     return pos;
 }
 
-// Counting sort of the sparse positions into `s_sorted` + the bucket table `s_tbl`; both are also copied to (Rg, Tg).
+// Bucket table of the ascending list S (x entries, positions in [f, l]): tbl[b] = entries whose bucket ((pos - f) >> shift) is
+// below b, for b = 0 .. nbk.  Written by "boundary marking" (entry j fills the buckets between its predecessor's and its own),
+// together with the global copies (Rg, Tg) the routing pass reads.
 template <class Team>
-TS_HD int build_table(Team &tm, int x, const int *s_pos, int f, int l, int *s_sorted, int *s_cnt, int *s_tbl, int *Rg, int *Tg) {
+TS_HD int build_table(Team &tm, int x, int nb, const int *S, int f, int l, int *s_tbl, int *Rg, int *Tg) {
     int shift = 0;
-    while (((l - f) >> shift) > kBuckets - 1) shift++;
-    const int nbk = ((l - f) >> shift) + 1;  // buckets 0 .. nbk-1, table entries 0 .. nbk
-    for (int b = tm.tid; b <= nbk; b += tm.nthr) s_cnt[b] = 0;
-    tm.sync();
-    for (int id = tm.tid; id < x; id += tm.nthr) tm.atomic_add(&s_cnt[(s_pos[id] - f) >> shift], 1);
-    tm.sync();
-    {  // exclusive scan: thread t owns the entries [t*per, (t+1)*per)
-        const int per = (nbk + 1 + tm.nthr - 1) / tm.nthr;
-        const int lo = tm.tid * per, hi = (lo + per < nbk + 1) ? lo + per : nbk + 1;
-        int s = 0;
-        for (int b = lo; b < hi; b++) s += s_cnt[b];
-        int run = tm.exclusive_scan(s);
-        for (int b = lo; b < hi; b++) {
-            const int c = s_cnt[b];
-            s_tbl[b] = run;
-            s_cnt[b] = 0;  // becomes the scatter cursor
-            run += c;
-        }
+    while (((l - f) >> shift) > nb - 1) shift++;
+    const int nbk = ((l - f) >> shift) + 1;
+    for (int j = tm.tid; j <= x; j += tm.nthr) {
+        const int bprev = j == 0 ? -1 : (S[j - 1] - f) >> shift;
+        const int bcur = j == x ? nbk : (S[j] - f) >> shift;
+        for (int b = bprev + 1; b <= bcur; b++) { s_tbl[b] = j; Tg[b] = j; }
+        if (j < x) Rg[j] = S[j];
     }
-    tm.sync();
-    for (int id = tm.tid; id < x; id += tm.nthr) {
-        const int p = s_pos[id], b = (p - f) >> shift;
-        s_sorted[s_tbl[b] + tm.atomic_add(&s_cnt[b], 1)] = p;
-    }
-    tm.sync();
-    for (int b = tm.tid; b < nbk; b += tm.nthr) {  // order inside a bucket (the scatter order is arbitrary)
-        const int lo = s_tbl[b], hi = s_tbl[b + 1];
-        for (int i = lo + 1; i < hi; i++) {
-            const int v = s_sorted[i];
-            int j = i - 1;
-            while (j >= lo && s_sorted[j] > v) { s_sorted[j + 1] = s_sorted[j]; j--; }
-            s_sorted[j + 1] = v;
-        }
-    }
-    tm.sync();
-    for (int i = tm.tid; i < x; i += tm.nthr) Rg[i] = s_sorted[i];
-    for (int b = tm.tid; b <= nbk; b += tm.nthr) Tg[b] = s_tbl[b];
     return shift;
 }
 
 // The sparse simulation.  st_pos (ascending) / st_w: label and weight of the x elements whose weight is below W; n: table size;
-// depth0 = 2*floor(log2(n)).  s_*: scratch of the team (x, x, kTblStride, kTblStride, 16 ints).
-// On return plan, R[(t+1)*xcap ..], tbl[(t+1)*kTblStride ..] describe levels t < n_levels, table 0 the initial positions, and
-// s_pos holds the positions of the sparse elements inside the handed-over segment.
+// depth0 = 2*floor(log2(n)).  Scratch of the team: four lists of xcap ints (a_s, a_i, b_s, b_i), s_tbl (kTblStride), s_misc (16).
+// On return plan, R[t*xcap ..], tbl[t*kTblStride ..] describe the levels t < n_levels, and (a_s[j], a_i[j]) are the position and
+// the index into st_pos / st_w of the sparse elements inside the handed-over segment (ascending positions).
+// Per level: pivot samples -> pivot move (one list entry changes place) -> bucket table -> K (parallel minimum) -> every sparse
+// element computes its new position AND its new rank in closed form from rank queries on the current table (the right-hand
+// elements move to the K first W positions in reverse order, the left-hand ones stay), so the list stays sorted without sorting.
 template <class Team>
 TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *st_w, double W, int depth0, int hand_min, Plan *plan,
-                      int *R, int *tbl, int xcap, int *s_pos, int *s_sorted, int *s_cnt, int *s_tbl, int *s_misc) {
-    for (int id = tm.tid; id < x; id += tm.nthr) s_pos[id] = st_pos[id];
-    tm.sync();
-    build_table(tm, x, s_pos, 0, n, s_sorted, s_cnt, s_tbl, R, tbl);
+                      int *R, int *tbl, int xcap, int *a_s, int *a_i, int *b_s, int *b_i, int *s_tbl, int *s_misc) {
+    int nb = 256;
+    while (nb < x && nb < kBuckets) nb <<= 1;
     int f = 0, l = n, depth = depth0, t = 0;
+    for (int k = tm.tid; k < 5; k += tm.nthr) s_misc[k] = -1;
+    tm.sync();
+    {
+        const int pa = f + 1, pb = f + (l - f) / 2, pc = l - 1;
+        for (int j = tm.tid; j < x; j += tm.nthr) {
+            const int q = st_pos[j];
+            a_s[j] = q;
+            a_i[j] = j;
+            if (q == pa) s_misc[0] = j;
+            if (q == pb) s_misc[1] = j;
+            if (q == pc) s_misc[2] = j;
+            if (q == f) s_misc[3] = j;
+        }
+    }
+    tm.sync();
     for (;;) {
         const int len = l - f;
         if (len <= hand_min || len <= kLeaf || t == kMaxLevels || depth == 0) break;
         const int pa = f + 1, pb = f + len / 2, pc = l - 1;
-        for (int k = tm.tid; k < 5; k += tm.nthr) s_misc[k] = -1;
-        tm.sync();
-        for (int id = tm.tid; id < x; id += tm.nthr) {
-            const int q = s_pos[id];
-            if (q == pa) s_misc[0] = id;
-            if (q == pb) s_misc[1] = id;
-            if (q == pc) s_misc[2] = id;
-            if (q == f) s_misc[3] = id;
-        }
-        tm.sync();
         // __move_median_to_first(first, first+1, mid, last-1) with the plain `<` of sort_indexes
-        const double ka = s_misc[0] < 0 ? W : st_w[s_misc[0]], kb = s_misc[1] < 0 ? W : st_w[s_misc[1]], kc = s_misc[2] < 0 ? W : st_w[s_misc[2]];
+        const double ka = s_misc[0] < 0 ? W : st_w[a_i[s_misc[0]]], kb = s_misc[1] < 0 ? W : st_w[a_i[s_misc[1]]],
+                     kc = s_misc[2] < 0 ? W : st_w[a_i[s_misc[2]]];
         int pick;
         double kp;
         if (ka < kb) {
@@ -198,20 +181,30 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         } else if (ka < kc) { pick = pa; kp = ka; }
         else if (kb < kc) { pick = pc; kp = kc; }
         else { pick = pb; kp = kb; }
-        const int at_f = s_misc[3];
-        if (kp != W) break;  // a sparse pivot: the rest goes to the general sort
+        const bool at_f = s_misc[3] >= 0;  // a sparse element at f is a_s[0]
+        if (kp != W) break;                // a sparse pivot: the rest goes to the general sort
         depth--;
+        // pivot move: the element at f goes to `pick`  (list a -> list b)
+        for (int j = tm.tid; j < x; j += tm.nthr) {
+            const int q = a_s[j];
+            if (!at_f) { b_s[j] = q; b_i[j] = a_i[j]; }
+            else if (j > 0) {
+                const int r = (j - 1) + (q > pick ? 1 : 0);
+                b_s[r] = q;
+                b_i[r] = a_i[j];
+                if (q < pick && (j == x - 1 || a_s[j + 1] > pick)) { b_s[j] = pick; b_i[j] = a_i[0]; }
+            } else if (x == 1 || a_s[1] > pick) { b_s[0] = pick; b_i[0] = a_i[0]; }
+        }
         tm.sync();
-        if (tm.tid == 0 && at_f >= 0) s_pos[at_f] = pick;
-        tm.sync();
-        const int shift = build_table(tm, x, s_pos, f, l, s_sorted, s_cnt, s_tbl, R + (size_t)(t + 1) * xcap, tbl + (size_t)(t + 1) * kTblStride);
-        // K = first k with not (k < n_a and A[k] < B[k]); A[k] = k-th W position, B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1
         const int M = len - 1, n_a = M - x;
+        const int shift = build_table(tm, x, nb, b_s, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride);
+        // K = first k with not (k < n_a and A[k] < B[k]); A[k] = k-th W position, B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1
         if (tm.tid == 0) s_misc[4] = n_a;
+        for (int k = tm.tid; k < 4; k += tm.nthr) s_misc[k] = -1;
         tm.sync();
         for (int j = tm.tid; j <= x; j += tm.nthr) {  // the k with exactly j sparse elements before A[k]: [lo, hi)
-            const int lo = j == 0 ? 0 : s_sorted[j - 1] - (f + 1) - (j - 1);
-            const int hi = j == x ? n_a : s_sorted[j] - (f + 1) - j;
+            const int lo = j == 0 ? 0 : b_s[j - 1] - (f + 1) - (j - 1);
+            const int hi = j == x ? n_a : b_s[j] - (f + 1) - j;
             const int need = M - 1 - j;
             const int kmin = need <= 0 ? 0 : (need + 1) / 2;
             const int k = lo > kmin ? lo : kmin;
@@ -219,12 +212,29 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         }
         tm.sync();
         const int K = s_misc[4];
-        const int aK = K < n_a ? select_dense(s_sorted, s_tbl, f, shift, K) : kIntMax;
+        const int aK = K < n_a ? select_dense(b_s, s_tbl, f, shift, K) : kIntMax;
         const int bK = K > 0 ? l - K : l;
         const int cut = aK < bK ? aK : bK;
-        for (int id = tm.tid; id < x; id += tm.nthr) {  // a sparse element is a right stopper only
-            const int kb2 = l - 1 - s_pos[id];
-            if (kb2 < K) s_pos[id] = select_dense(s_sorted, s_tbl, f, shift, kb2);
+        // moves (list b -> list a, still ascending) + the pivot samples of the next level [f, cut)
+        const int npa = f + 1, npb = f + (cut - f) / 2, npc = cut - 1;
+        for (int j = tm.tid; j < x; j += tm.nthr) {
+            const int q = b_s[j], kb2 = l - 1 - q;
+            int np, nr;
+            if (kb2 < K) {  // right stopper of a swap: goes to the kb2-th W position; the movers end up in reverse order
+                np = select_dense(b_s, s_tbl, f, shift, kb2);
+                nr = (np - (f + 1) - kb2) + (x - 1 - j);
+            } else {        // stays; the movers that land before it: those with kb < c = W positions before q
+                const int c = q - (f + 1) - j;
+                const int first_mover = (l - c > l - K) ? l - c : l - K;
+                np = q;
+                nr = j + (x - rank_lt(b_s, s_tbl, f, shift, first_mover));
+            }
+            a_s[nr] = np;
+            a_i[nr] = b_i[j];
+            if (np == npa) s_misc[0] = nr;
+            if (np == npb) s_misc[1] = nr;
+            if (np == npc) s_misc[2] = nr;
+            if (np == f) s_misc[3] = nr;
         }
         if (tm.tid == 0) {
             Level L;
@@ -242,6 +252,8 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         plan->hand_depth = depth;
         plan->fail = (depth == 0 && l - f > kLeaf) ? 1 : 0;
         plan->x = x;
+        plan->shift0 = 0;
+        plan->nb = nb;
         plan->W = W;
     }
     tm.sync();

@@ -31,25 +31,27 @@ static int run_case(int n, const std::vector<double> &w, int hand_min, long long
     int lg = 0;
     while ((1LL << (lg + 1)) <= n) lg++;
     const int xcap = std::max(1, x);
-    std::vector<int> R((size_t)(kMaxLevels + 1) * xcap), tbl((size_t)(kMaxLevels + 1) * kTblStride);
-    std::vector<int> s_pos(xcap), s_sorted(xcap), s_cnt(kTblStride), s_tbl(kTblStride), s_misc(16);
+    std::vector<int> R((size_t)kMaxLevels * xcap), tbl((size_t)kMaxLevels * kTblStride);
+    std::vector<int> a_s(xcap), a_i(xcap), b_s(xcap), b_i(xcap), s_tbl(kTblStride), s_misc(16);
     Plan plan{};
     SerialTeam tm;
-    plan_build(tm, n, x, st_pos.data(), st_w.data(), W, 2 * lg, hand_min, &plan, R.data(), tbl.data(), xcap, s_pos.data(), s_sorted.data(),
-               s_cnt.data(), s_tbl.data(), s_misc.data());
+    plan_build(tm, n, x, st_pos.data(), st_w.data(), W, 2 * lg, hand_min, &plan, R.data(), tbl.data(), xcap, a_s.data(), a_i.data(),
+               b_s.data(), b_i.data(), s_tbl.data(), s_misc.data());
     if (plan.fail) { std::printf("plan.fail on n=%d x=%d\n", n, x); return 0; }
     *levels_out += plan.n_levels;
     std::vector<long long> out(n, -1);
     const int hf = plan.hand_f, hl = plan.hand_l;
     *handed_out += hl - hf;
-    for (int id = 0; id < x; id++) {
-        const int p = s_pos[id];
-        if (p < hf || p >= hl || out[p] != -1) { std::printf("sparse element %d at %d outside the handed segment [%d,%d)\n", id, p, hf, hl); return 1; }
-        out[p] = st_pos[id];
+    std::vector<char> is_sparse(n, 0);
+    for (int id = 0; id < x; id++) is_sparse[st_pos[id]] = 1;
+    for (int j = 0; j < x; j++) {
+        const int p = a_s[j];
+        if (j > 0 && a_s[j - 1] >= p) { std::printf("sparse list not ascending at %d\n", j); return 1; }
+        if (p < hf || p >= hl || out[p] != -1) { std::printf("sparse element %d at %d outside the handed segment [%d,%d)\n", j, p, hf, hl); return 1; }
+        out[p] = st_pos[a_i[j]];
     }
     for (int i = 0; i < n; i++) {
-        const int r = rank_lt(R.data(), tbl.data(), 0, /*shift of table 0*/ [&] { int s = 0; while ((n >> s) > kBuckets - 1) s++; return s; }(), i);
-        if (r < x && R[r] == i) continue;  // sparse
+        if (is_sparse[i]) continue;
         bool handed = false, bad = false;
         const int p = dense_route(plan, R.data(), tbl.data(), xcap, i, handed, bad);
         if (bad) { std::printf("dense_route: depth limit on n=%d\n", n); return 0; }
