@@ -2313,19 +2313,51 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     bool ts_try = false;
     double ts_W = 0.;
     __shared__ int sh_exc;
+    constexpr int kMaxCoopBlocks = 320;
+    __shared__ long long sh_pl[kMaxCoopBlocks], sh_res_ll[2];
+    __shared__ double sh_pd[4][kMaxCoopBlocks], sh_res_d[4];
     {
+        // the per-block partials are fetched once, in parallel, into shared memory; warp 0 then combines them in block order
+        // (sequential, the same in every block: deterministic) and publishes the results
         long long base = 0, total = 0;
         double mx = 0., sv = 0., ss = 0., mn = __longlong_as_double(0x7ff0000000000000LL);
-        for (int b = 0; b < nblk; b++) {  // sequential, same in every thread: deterministic
-            const long long c = a.part_ll[b];
-            if (b < blk) base += c;
-            total += c;
-            const double t = a.part_d[b];
-            mx = (mx < t) ? t : mx;
-            const double tm = a.part_d[4 * nblk + b];
-            mn = (tm < mn) ? tm : mn;
-            sv += a.part_d[nblk + b];
-            ss += a.part_d[2 * nblk + b];
+        if (nblk <= kMaxCoopBlocks) {
+            for (int b = tid; b < nblk; b += nthr) {
+                sh_pl[b] = a.part_ll[b];
+                sh_pd[0][b] = a.part_d[b];
+                sh_pd[1][b] = a.part_d[nblk + b];
+                sh_pd[2][b] = a.part_d[2 * nblk + b];
+                sh_pd[3][b] = a.part_d[4 * nblk + b];
+            }
+            __syncthreads();
+            if (tid < 32) {
+                for (int b = 0; b < nblk; b++) {
+                    const long long c = sh_pl[b];
+                    if (b < blk) base += c;
+                    total += c;
+                    const double t = sh_pd[0][b];
+                    mx = (mx < t) ? t : mx;
+                    const double tm = sh_pd[3][b];
+                    mn = (tm < mn) ? tm : mn;
+                    sv += sh_pd[1][b];
+                    ss += sh_pd[2][b];
+                }
+                if (tid == 0) { sh_res_ll[0] = base; sh_res_ll[1] = total; sh_res_d[0] = mx; sh_res_d[1] = mn; sh_res_d[2] = sv; sh_res_d[3] = ss; }
+            }
+            __syncthreads();
+            base = sh_res_ll[0]; total = sh_res_ll[1]; mx = sh_res_d[0]; mn = sh_res_d[1]; sv = sh_res_d[2]; ss = sh_res_d[3];
+        } else {
+            for (int b = 0; b < nblk; b++) {
+                const long long c = a.part_ll[b];
+                if (b < blk) base += c;
+                total += c;
+                const double t = a.part_d[b];
+                mx = (mx < t) ? t : mx;
+                const double tm = a.part_d[4 * nblk + b];
+                mn = (tm < mn) ? tm : mn;
+                sv += a.part_d[nblk + b];
+                ss += a.part_d[2 * nblk + b];
+            }
         }
         n_agg = (int)total;
         if (a.do_refresh) factor = mx;
@@ -2353,11 +2385,14 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     for (int j = 0; j < 4; j++) al[j] = (s0 + j < hi) ? d.a_alive[s0 + j] : 0;
                 }
                 int na = 0, ne = 0;
+                double tsv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) tsv[j] = (ts_try && s0 + j < hi) ? d.a_ts[s0 + j] : 1.;  // not behind the liveness load
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     w[j] = 0.;
                     ex[j] = 0;
-                    if (ts_try && al[j]) { w[j] = factor / d.a_ts[s0 + j]; ex[j] = (w[j] != ts_W) ? 1 : 0; }
+                    if (ts_try && al[j]) { w[j] = factor / tsv[j]; ex[j] = (w[j] != ts_W) ? 1 : 0; }
                     na += al[j];
                     ne += ex[j];
                 }
@@ -2418,7 +2453,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     bool ts_on = false;
     if (ts_try) {
         long long x = 0;
-        for (int bb = 0; bb < nblk; bb++) x += a.part_ll[2048 + bb];
+        for (int bb = tid; bb < nblk; bb += nthr) x += a.part_ll[2048 + bb];
+        x = block_sum_ll(x, sm_ll);
         const int need = (4 * a.ts_xcap + tiesort::kTblStride + 16 + 2 * (nblk + 1)) * (int)sizeof(int);
         ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && need <= a.smem_bytes;
         if (ts_on) {
@@ -2864,11 +2900,21 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         const double t = block_sum_fixed(acc, sm_d);
         if (tid == 0) a.part_d[3 * nblk + blk] = t;
         grid.sync();
-        double base = 0.;
-        for (int bb = 0; bb < blk; bb++) base += a.part_d[3 * nblk + bb];  // sequential: deterministic
         __shared__ double carry_d;
         __shared__ double wtot[32];
-        if (tid == 0) carry_d = base;
+        if (nblk <= kMaxCoopBlocks) {
+            for (int bb = tid; bb < blk; bb += nthr) sh_pd[0][bb] = a.part_d[3 * nblk + bb];
+            __syncthreads();
+            if (tid == 0) {
+                double base = 0.;
+                for (int bb = 0; bb < blk; bb++) base += sh_pd[0][bb];  // sequential: deterministic
+                carry_d = base;
+            }
+        } else if (tid == 0) {
+            double base = 0.;
+            for (int bb = 0; bb < blk; bb++) base += a.part_d[3 * nblk + bb];
+            carry_d = base;
+        }
         __syncthreads();
         for (int t0 = lo; t0 < hi; t0 += nthr) {
             const int i = t0 + tid;

@@ -75,11 +75,26 @@ TS_HD int select_dense(PR R, PT tbl, int f, int shift, int k) {
 // depth_limit (after its decrement) was dep_parent.  Equal keys: median-of-3 picks `mid`, the Hoare partition mirrors
 // [cf+1, cl-1], the cut falls at cf+1+(m-1)/2, leaves do not move.
 TS_HD int all_equal_final(int cf, int cl, int pos, int dep_parent, bool &bad) {
-    int dep = dep_parent;
-    if (cl - cf > kLeaf) {
-        if (dep == 0) { bad = true; return pos; }
-        dep--;
+    if (cl - cf <= kLeaf) return pos;
+    int bits = 0;  // m < 2^bits: more levels than the halving below can take
+    while (((unsigned)(cl - cf) >> bits) != 0) bits++;
+    if (dep_parent >= bits) {  // the depth limit cannot be reached: segment-relative form without the bookkeeping
+        unsigned m = (unsigned)(cl - cf), r = (unsigned)(pos - cf);
+        int base = cf;
+        while (m > (unsigned)kLeaf) {
+            const unsigned mid = m >> 1;
+            if (r == 0) r = mid;
+            else if (r == mid) r = 0;
+            if (r) r = m - r;
+            const unsigned c = 1 + ((m - 1) >> 1);
+            if (r < c) m = c;
+            else { r -= c; base += (int)c; m -= c; }
+        }
+        return base + (int)r;
     }
+    int dep = dep_parent;
+    if (dep == 0) { bad = true; return pos; }
+    dep--;
     while (cl - cf > kLeaf) {
         const int m = cl - cf, mid = cf + m / 2;
         if (pos == cf) pos = mid;

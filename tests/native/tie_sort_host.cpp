@@ -99,6 +99,15 @@ int main(int argc, char **argv) {
         if (run_case(n, w, hand_min, &levels, &handed)) return 1;
         total_n += n;
     }
+    // all_equal_final: the segment-relative fast form against the depth-tracking form
+    for (int c = 0; c < 20000; c++) {
+        const int cf = (int)(rng() % 1000), m = 1 + (int)(rng() % (c % 2 ? 3000000 : 300)), cl = cf + m, pos = cf + (int)(rng() % m);
+        int bits = 0;
+        while (((unsigned)m >> bits) != 0) bits++;
+        bool bad1 = false, bad2 = false;
+        const int p1 = all_equal_final(cf, cl, pos, 1000, bad1), p2 = all_equal_final(cf, cl, pos, bits - 1, bad2);
+        if (bad1 || (!bad2 && p1 != p2) || p1 < cf || p1 >= cl) { std::printf("all_equal_final mismatch m=%d pos=%d: %d vs %d\n", m, pos - cf, p1, p2); return 1; }
+    }
     std::printf("ok %d cases, %lld elements, %lld sparse levels, %lld elements handed over\n", cases, total_n, levels, handed);
     return 0;
 }
