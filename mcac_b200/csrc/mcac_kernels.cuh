@@ -2518,10 +2518,12 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             // by level together, so that their table look-ups (independent of each other) are in flight at the same time.
             constexpr int kRoute = 4;
             for (long long i0 = gtid; i0 < n; i0 += gsize * kRoute) {
-                int pos[kRoute];
+                int pos[kRoute], e_base[kRoute], e_dep[kRoute];
+                unsigned e_m[kRoute], e_r[kRoute];  // e_m == 0: not (yet) in an all-W segment
                 bool live[kRoute];
 #pragma unroll
                 for (int j = 0; j < kRoute; j++) {
+                    e_m[j] = 0; e_r[j] = 0; e_base[j] = 0; e_dep[j] = 0;
                     const long long i = i0 + j * gsize;
                     pos[j] = (int)i;
                     live[j] = i < n && is_sparse[i < n ? i : 0] == 0;
@@ -2556,19 +2558,57 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                                 if (kb < L.K) p = tiesort::select_dense(Rt, Tt, L.f, L.shift, kb);
                             }
                         }
-                        if (p >= L.cut) {
-                            bool bad = false;
-                            const int fp = tiesort::all_equal_final(L.cut, L.l, p, L.depth, bad);
-                            if (bad) any_bad = true;
-                            else {  // straight into the pick table; its weight (W) is implied by fp >= hand_l
-                                const int lab = (int)(i0 + j * gsize);
-                                d.sorted_slot[fp] = d.slot_of_label[lab];
-                                a.sorted_label[fp] = lab;
-                            }
+                        if (p >= L.cut) {  // into the all-W right part [cut, l): finished below, the kRoute chains interleaved
+                            e_m[j] = (unsigned)(L.l - L.cut);
+                            e_r[j] = (unsigned)(p - L.cut);
+                            e_base[j] = L.cut;
+                            e_dep[j] = L.depth;
                             live[j] = false;
                         }
                         pos[j] = p;
                     }
+                }
+                // all-equal segments (tiesort::all_equal_final, segment-relative form)
+                bool fast = true;
+#pragma unroll
+                for (int j = 0; j < kRoute; j++) {
+                    int bits = 0;
+                    while ((e_m[j] >> bits) != 0) bits++;
+                    if (e_m[j] > (unsigned)tiesort::kLeaf && e_dep[j] < bits) fast = false;
+                }
+                if (fast) {
+                    while ((e_m[0] > 16u) | (e_m[1] > 16u) | (e_m[2] > 16u) | (e_m[3] > 16u)) {
+#pragma unroll
+                        for (int j = 0; j < kRoute; j++) {
+                            unsigned m = e_m[j], r = e_r[j];
+                            const bool on = m > 16u;
+                            const unsigned mid = m >> 1;
+                            if (r == 0) r = mid;
+                            else if (r == mid) r = 0;
+                            if (r) r = m - r;
+                            const unsigned c = 1 + ((m - 1) >> 1);
+                            unsigned nm = c, nr = r;
+                            int nb = e_base[j];
+                            if (r >= c) { nr = r - c; nb += (int)c; nm = m - c; }
+                            if (on) { e_m[j] = nm; e_r[j] = nr; e_base[j] = nb; }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kRoute; j++) {
+                        if (e_m[j] == 0) continue;
+                        bool bad = false;
+                        const int fp = tiesort::all_equal_final(e_base[j], e_base[j] + (int)e_m[j], e_base[j] + (int)e_r[j], e_dep[j], bad);
+                        if (bad) { any_bad = true; e_m[j] = 0; }
+                        else { e_r[j] = (unsigned)(fp - e_base[j]); e_m[j] = 1; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kRoute; j++) {  // straight into the pick table; the weight (W) is implied by the position >= hand_l
+                    if (e_m[j] == 0) continue;
+                    const int fp = e_base[j] + (int)e_r[j], lab = (int)(i0 + j * gsize);
+                    d.sorted_slot[fp] = d.slot_of_label[lab];
+                    a.sorted_label[fp] = lab;
                 }
 #pragma unroll
                 for (int j = 0; j < kRoute; j++) {
@@ -2901,7 +2941,6 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         if (tid == 0) a.part_d[3 * nblk + blk] = t;
         grid.sync();
         __shared__ double carry_d;
-        __shared__ double wtot[32];
         if (nblk <= kMaxCoopBlocks) {
             for (int bb = tid; bb < blk; bb += nthr) sh_pd[0][bb] = a.part_d[3 * nblk + bb];
             __syncthreads();
@@ -2916,23 +2955,50 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             carry_d = base;
         }
         __syncthreads();
-        for (int t0 = lo; t0 < hi; t0 += nthr) {
-            const int i = t0 + tid;
-            const double v = (i < hi) ? fw(i) : 0.;
+        // Same arithmetic as one round of blockDim elements after the other — cum[i] = (carry + (wtot[0] + .. + wtot[w-1])) + inc,
+        // carry' = (carry + wbase of the last warp) + its total — scheduled 16 rounds at a time: warp scans of all rounds, the warp bases
+        // of every (round, warp) in parallel, the 16 carries by one thread, then the warp scans again with their bases.
+        constexpr int kCumRounds = 16, kCumWarps = kEventThreads / 32;
+        __shared__ double s_wtot[kCumRounds][kCumWarps], s_wbase[kCumRounds][kCumWarps], s_carry[kCumRounds];
+        const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+        auto warp_inc = [&](double v) {
             double inc = v;
-            const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const double tt = __shfl_up_sync(kFull, inc, o);
                 if (lane >= o) inc += tt;
             }
-            if (lane == 31) wtot[w] = inc;
+            return inc;
+        };
+        for (int t0 = lo; t0 < hi; t0 += kCumRounds * nthr) {
+            const int nr = min(kCumRounds, (hi - t0 + nthr - 1) / nthr);
+            for (int r = 0; r < nr; r++) {
+                const int i = t0 + r * nthr + tid;
+                const double inc = warp_inc((i < hi) ? fw(i) : 0.);
+                if (lane == 31) s_wtot[r][w] = inc;
+            }
             __syncthreads();
-            double wbase = 0.;
-            for (int ww = 0; ww < w; ww++) wbase += wtot[ww];
-            if (i < hi) d.cum[i] = carry_d + wbase + inc;
+            if (tid < nr * nw) {
+                const int r = tid / nw, ww_ = tid % nw;
+                double wbase = 0.;
+                for (int ww = 0; ww < ww_; ww++) wbase += s_wtot[r][ww];
+                s_wbase[r][ww_] = wbase;
+            }
             __syncthreads();
-            if (tid == nthr - 1) carry_d = carry_d + wbase + inc;
+            if (tid == 0) {
+                double c = carry_d;
+                for (int r = 0; r < nr; r++) {
+                    s_carry[r] = c;
+                    c = c + s_wbase[r][nw - 1] + s_wtot[r][nw - 1];
+                }
+                carry_d = c;
+            }
+            __syncthreads();
+            for (int r = 0; r < nr; r++) {
+                const int i = t0 + r * nthr + tid;
+                const double inc = warp_inc((i < hi) ? fw(i) : 0.);
+                if (i < hi) d.cum[i] = s_carry[r] + s_wbase[r][w] + inc;
+            }
             __syncthreads();
         }
     }
