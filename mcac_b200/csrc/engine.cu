@@ -63,6 +63,9 @@ struct mcac_gpu {
     std::vector<void *> owned;       // size-dependent allocations (re-made by upload / duplication)
     std::vector<void *> persistent;  // RNG stream, scalars, batch scratch: live as long as the handle
     Scalars *h_sc = nullptr;  // pinned mirror
+    Scalars *h_sc_ring[2] = {nullptr, nullptr};  // pinned read-back slots of the batches in flight (pipelined submission)
+    cudaEvent_t ev_cycle[2] = {nullptr, nullptr};
+    bool pipeline = true;       // MCAC_B200_NO_PIPELINE=1: read every batch back before the next one is submitted
     Scalars sc_host{};
     // scratch
     int *q_slot = nullptr;
@@ -417,7 +420,8 @@ int sort_time_steps(mcac_gpu *h, double factor) {
 // The per-event pipeline as ONE cooperative launch (k_event): labels, refresh / PhysicalModel::update, weights, replayed
 // introsort, cumulative table.  Falls back to the multi-launch form when cooperative launch is unavailable or when
 // introsort's depth limit is hit.
-int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, const double *factor = nullptr, bool defer_sync = false) {
+int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, const double *factor = nullptr, bool defer_sync = false,
+                   bool skip_if_no_event = false) {
     if (h->coop_blocks <= 0 || h->prm.sort_order == MCAC_ORDER_HOST_STDSORT) {
         if (do_refresh || do_totals) { h->labels_valid = false; TRY(refresh_labels(h)); TRY(refresh_reduce(h)); TRY(pull_scalars(h)); }
         if (do_sort) TRY(sort_time_steps(h, factor ? *factor : h->sc_host.max_time_step));
@@ -446,6 +450,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.ts_tbl = h->ts_tbl;
     a.ts_xcap = h->ts_xcap;
     a.ts_min_n = h->ts_min_n;
+    a.skip_if_no_event = skip_if_no_event ? 1 : 0;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
@@ -945,6 +950,10 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaMallocHost((void **)&h->h_sc, sizeof(Scalars)));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaMallocHost((void **)&h->h_sc_ring[k], sizeof(Scalars)));
+        CK(cudaEventCreateWithFlags(&h->ev_cycle[k], cudaEventDisableTiming));
+    }
     CK(cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)));
     fill_devstate_params(h);
     TRY(alloc_persistent(h));
@@ -952,6 +961,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         int occ = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (getenv("MCAC_B200_NO_OVERLAP")) h->overlap = false;
+        if (getenv("MCAC_B200_NO_PIPELINE")) h->pipeline = false;
         if (getenv("MCAC_B200_DEBUG_SYNC")) h->debug_sync = true;
         if (const char *e = getenv("MCAC_B200_EVENT_SPARE_SMS")) h->event_spare_sms = std::max(0, atoi(e));
         if (const char *e = getenv("MCAC_B200_NUCL_HEADROOM")) h->nucl_headroom = std::max(80, atoi(e));
@@ -1014,6 +1024,10 @@ int mcac_gpu_destroy(mcac_gpu *h) {
     if (h->wide_list) cudaFree(h->wide_list);
     for (void *p : {(void *)h->sweep_slot, (void *)h->sweep_dir, (void *)h->sweep_dist, (void *)h->sweep_res}) if (p) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
+    for (int k = 0; k < 2; k++) {
+        if (h->h_sc_ring[k]) cudaFreeHost(h->h_sc_ring[k]);
+        if (h->ev_cycle[k]) cudaEventDestroy(h->ev_cycle[k]);
+    }
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1472,8 +1486,128 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         nucleated_total += h->sc_host.n_nucleated;
         if (h->stop_at_event && (h->sc_host.b_merged || h->sc_host.n_nucleated > 0)) break;
     }
+    // Pipelined submission (speculative mode): batch i+1 — event kernel (it returns at once if batch i did not merge), cell rebuild,
+    // queries, search, commit — is submitted BEFORE the scalars of batch i are read back, so the device never waits for the host
+    // between batches.  The kernels themselves enforce what the host would have checked first (step limit, finished(), room in
+    // the pool); anything unusual drains the pipeline and is handled by the one-batch-at-a-time iteration below.
+    const long long steps_limit_abs = at_start.steps_done + max_steps;
+    const bool pipe_mode = speculative && h->pipeline && h->overlap && h->coop_blocks > 0 && h->prm.sort_order != MCAC_ORDER_HOST_STDSORT &&
+                           !(records && n_records > 0) && !h->stop_at_event && !h->prm.with_domain_duplication && !h->debug_sync;
     while (speculative && steps < max_steps) {
         if (finished(h)) { fin = true; break; }
+        if (pipe_mode && !fallback_sorted && max_steps - steps > 2LL * B) {
+            auto resources_ok = [&](int cycles) {  // from the last scalars read back: `cycles` more batches cannot run out of anything
+                const Scalars &s = h->sc_host;
+                return h->d.sph_cap - s.pool_top >= s.n_sph && s.rand_pos >= h->d.rng_buf_base &&
+                       s.rand_pos + 3LL * B * cycles + 64 <= h->rng_generated && max_steps - steps > (long long)B * cycles;
+            };
+            if ((rc = ensure_rng(h, h->sc_host.rand_pos + 3LL * B * 3 + 64)) != E_OK) break;
+            int inflight = 0, slot = 0, oldest = 0;
+            bool spec_sorted[2] = {false, false};  // the cycle was submitted ahead (its event kernel sorts iff the previous cycle merged)
+            bool anomaly = false, need_fallback_sort = false;
+            Scalars last{};
+            bool have_last = false;
+            auto enqueue = [&]() -> int {
+                const bool spec = inflight > 0;
+                if (spec) {
+                    CK(cudaEventRecord(h->ev_fork, h->stream));  // the rebuild on the side stream reads what the previous commit wrote
+                    CK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+                    h->cells_valid = false;
+                    h->labels_valid = false;  // the batch in flight may merge: labels, refresh and totals are redone with the sort
+                    prof_begin(h, 2);
+                    TRY(event_pipeline(h, true, true, true, nullptr, true, true));
+                    prof_end(h);
+                    TRY(build_cells(h, true));
+                } else if (h->sc_host.event || !h->pick_valid) {
+                    prof_begin(h, 2);
+                    TRY(event_pipeline(h, need_refresh, need_refresh, true, nullptr, true));
+                    prof_end(h);
+                    TRY(build_cells(h, true));
+                    need_refresh = false;
+                    sorts++;
+                }
+                spec_sorted[slot] = spec;
+                k_prepare_queries<<<div_up(B, 128), 128, 0, h->stream>>>(h->d, B, h->q_slot, h->q_dir, h->q_dist);
+                h->launches++;
+                if (!h->cells_valid) {
+                    prof_begin(h, 3);
+                    TRY(build_cells(h));
+                    prof_end(h);
+                }
+                prof_begin(h, 0);
+                TRY(search_launch(h, B));
+                prof_end(h);
+                BatchArgs ba;
+                ba.nq = B;
+                ba.q_slot = h->q_slot; ba.q_dir = h->q_dir; ba.q_dist = h->q_dist; ba.res = h->q_res;
+                ba.rec = nullptr; ba.rec_cap = 0; ba.rec_base = 0;
+                ba.max_steps = max_steps;
+                ba.steps_limit_abs = steps_limit_abs;
+                prof_begin(h, 1);
+                k_commit<<<1, kCommitThreads, 0, h->stream>>>(h->d, ba);
+                prof_end(h);
+                h->launches++;
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(h->h_sc_ring[slot], h->d.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaEventRecord(h->ev_cycle[slot], h->stream));
+                h->cells_valid = false;  // the commit moves aggregates
+                slot ^= 1;
+                inflight++;
+                return E_OK;
+            };
+            auto retire = [&]() -> int {
+                CK(cudaEventSynchronize(h->ev_cycle[oldest]));
+                const Scalars s = *h->h_sc_ring[oldest];
+                const bool was_spec = spec_sorted[oldest];
+                oldest ^= 1;
+                inflight--;
+                if (was_spec && have_last && last.b_merged && s.b_need != 99) sorts++;  // its event kernel re-sorted after that merge
+                last = s;
+                have_last = true;
+                h->sc_host = s;
+                if (s.b_need == 99) { anomaly = true; need_fallback_sort = true; return E_OK; }
+                batches++;
+                if (s.error) { h->err = "device-side error code " + std::to_string(s.error); return s.error; }
+                steps += s.b_committed;
+                if (s.b_merged) h->sc_host.avg_npp = static_cast<double>(s.n_sph) / static_cast<double>(s.n_agg);
+                if (s.b_stop_reason == STOP_FINISHED) { fin = true; anomaly = true; }
+                if (s.b_stop_reason == STOP_POOL || s.b_committed == 0) anomaly = true;
+                if (inflight == 0) {  // host-side validity flags as of the last batch submitted
+                    h->cells_valid = false;
+                    if (s.b_merged) { h->pick_valid = false; h->labels_valid = false; need_refresh = true; }
+                    else need_refresh = false;  // an earlier merge was refreshed and re-sorted by the event kernel that followed it
+                }
+                return E_OK;
+            };
+            if (resources_ok(1)) rc = enqueue();
+            while (rc == E_OK && inflight > 0) {
+                if (!anomaly && inflight < 2 && resources_ok(2) && !finished(h)) {
+                    if ((rc = enqueue()) != E_OK) break;
+                }
+                if ((rc = retire()) != E_OK) break;
+                if (anomaly) {  // drain: what is still in flight did nothing harmful (the kernels check the same conditions)
+                    while (inflight > 0 && (rc = retire()) == E_OK) {}
+                    break;
+                }
+                if (inflight == 0 && !(resources_ok(1) && max_steps - steps > 2LL * B)) break;
+                if (inflight == 0 && (rc = enqueue()) != E_OK) break;
+            }
+            if (rc != E_OK) break;
+            if (have_last) {  // host-side validity flags as of the last batch read back
+                h->cells_valid = false;
+                if (need_fallback_sort) {
+                    h->sc_host.b_need = 0;
+                    if ((rc = push_scalars(h)) != E_OK) break;
+                    h->sort_fallbacks++;
+                    if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
+                    h->pick_valid = true;
+                    fallback_sorted = true;
+                }
+                if (fin) break;
+                if (steps >= max_steps) break;
+                if (finished(h)) { fin = true; break; }
+            }
+        }
         if ((h->sc_host.event || !h->pick_valid) && !fallback_sorted) {
             // top of the loop after an event (calcul.cpp:72-101): duplication test, then sort_time_steps(max)
             if (h->sc_host.event && h->prm.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(h->prm.u_sg < 0.0)) {
@@ -1514,6 +1648,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         ba.rec_cap = n_records;
         ba.rec_base = steps;
         ba.max_steps = max_steps - steps;
+        ba.steps_limit_abs = 0;
         prof_begin(h, 1);
         k_commit<<<1, kCommitThreads, 0, h->stream>>>(h->d, ba);
         prof_end(h);

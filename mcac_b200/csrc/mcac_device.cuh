@@ -37,7 +37,7 @@ struct Scalars {
     int p_regime, p_regime_draws;  // check_InterPotentialRegime outcome of the last try (0 sticking) and draws it consumed
     int n_nucleated, pad_n;
 };
-enum StopReason { STOP_NONE = 0, STOP_CONTACT = 1, STOP_CONFLICT = 2, STOP_FINISHED = 3, STOP_BATCH_END = 4 };
+enum StopReason { STOP_NONE = 0, STOP_CONTACT = 1, STOP_CONFLICT = 2, STOP_FINISHED = 3, STOP_BATCH_END = 4, STOP_POOL = 5 /* no room for the merged block: host compacts */ };
 
 struct SearchResult {
     double distance;

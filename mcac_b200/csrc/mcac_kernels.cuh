@@ -1131,6 +1131,7 @@ struct BatchArgs {
     mcac_step_record *rec;  // device buffer or nullptr
     long long rec_cap, rec_base;
     long long max_steps;    // steps still allowed in this run call
+    long long steps_limit_abs;  // > 0: Scalars::steps_done may not pass this (batches submitted before the previous one was read back)
 };
 __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs b) {
     __shared__ int sh_slot[kMaxBatch];
@@ -1153,6 +1154,14 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         if (tid == 0) { sc.b_committed = 0; sc.b_stop_reason = STOP_NONE; sc.b_contact = 0; sc.b_merged = 0; }
         return;
     }
+    // PhysicalModel::finished (physical_model.cpp:288-337) at the top of the first step of the batch: the host checks the same
+    // conditions before it submits a batch, except for batches it submits ahead of reading the previous one back
+    if (sc.n_agg < 1 || sc.n_agg <= d.n_agg_limit ||
+        (d.npp_limit > 0 && static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg) >= static_cast<double>(d.npp_limit))) {
+        if (tid == 0) { sc.b_committed = 0; sc.b_stop_reason = STOP_FINISHED; sc.b_contact = 0; sc.b_merged = 0; }
+        return;
+    }
+    const long long max_steps = b.steps_limit_abs > 0 ? min(b.max_steps, b.steps_limit_abs - steps_before) : b.max_steps;
     if (tid == 0) { s_conf = nq; s_contact = nq; s_limit = nq; s_finished = 0; }
     for (int j = tid; j < nq; j += nth) {
         sh_slot[j] = b.q_slot[j];
@@ -1166,7 +1175,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     if (tid == 0) {
         double t = sc.time;
         int lim = nq;
-        if ((long long)lim > b.max_steps) lim = (int)b.max_steps;
+        if ((long long)lim > max_steps) lim = (int)(max_steps > 0 ? max_steps : 0);
         for (int j = 0; j < nq; j++) {
             sh_time[j] = t;
             const bool fin = (d.time_limit > 0 && t >= d.time_limit) || (d.n_iter_limit > 0 && iter_before + j >= d.n_iter_limit);
@@ -1210,8 +1219,12 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     int stop = s_limit;
     int reason = s_finished ? STOP_FINISHED : STOP_BATCH_END;
     if (s_conf < stop) { stop = s_conf; reason = STOP_CONFLICT; }
-    const bool do_contact = s_contact < stop;  // the contact step is valid (no conflict before it) and allowed
+    bool do_contact = s_contact < stop;  // the contact step is valid (no conflict before it) and allowed
     if (do_contact) { stop = s_contact; reason = STOP_CONTACT; }
+    if (do_contact) {  // the merged block is written at the pool top: without room for it the batch ends before the contact step
+        const int other = b.res[stop].other_agg;
+        if (other >= 0 && sc.pool_top + d.a_n[sh_slot[stop]] + d.a_n[other] > d.sph_cap) { do_contact = false; reason = STOP_POOL; }
+    }
     // ---- commit the free-flight steps [0, stop): distinct aggregates, one warp per step
     for (int j = warp; j < stop; j += nwarps) {
         const int sj = sh_slot[j];
@@ -2194,6 +2207,7 @@ struct EventArgs {
     int ts_xcap;          // 0 = fast path off
     int ts_min_n;         // smallest table the fast path is tried on
     int smem_bytes;       // dynamic shared memory of the launch
+    int skip_if_no_event; // return at once when Scalars::event == 0 (nothing changed since the last pick table)
 };
 struct BlockTeam {  // tiesort's Team for one CTA
     int tid, nthr;
@@ -2261,6 +2275,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const int tid = threadIdx.x, nthr = blockDim.x, nblk = gridDim.x, blk = blockIdx.x;
     const long long gtid = (long long)blk * nthr + tid, gsize = (long long)nblk * nthr;
     Scalars &sc = *d.sc;
+    if (a.skip_if_no_event && sc.event == 0) return;  // submitted ahead of the read-back of a batch that turned out not to merge
     const int n_slots = sc.n_agg_slots;
     // phase clocks of block 0 (SM cycles) accumulated into a.work[2 + k]: diagnostics for the K9 breakdown in profiles/
     long long t_prev = clock64();

@@ -90,6 +90,16 @@ def test_c3_1e6_head_replay_and_properties():
     _, r2 = s2.run(3000, batch=512, records=3000)
     for f in INT_FIELDS + FP_FIELDS:
         np.testing.assert_array_equal(r1[f], r2[f], err_msg=f)
+    # ... and so is the pipelined submission of the batches (no records requested: batch i+1 is submitted before batch i is read back)
+    s3 = Simulation(text)
+    r3, _ = s3.run(3000, batch=512)
+    a2, a3 = s2.state(), s3.state()
+    assert r3["steps"] == 3000 and a2["n_agg"] == a3["n_agg"] and a2["time"] == a3["time"]
+    np.testing.assert_array_equal(a2["sphere_label"], a3["sphere_label"])
+    for k in ("x", "y", "z"):
+        np.testing.assert_array_equal(a2["spheres"][k], a3["spheres"][k])
+    np.testing.assert_array_equal(a2["aggregates"]["proper_time"], a3["aggregates"]["proper_time"])
+    assert r3["tie_sorts"] > 0  # the pick table of this configuration is tie-dominated: sparse fast path of the sort
 
 
 def test_c4_surface_growth_1e6_first_steps():

@@ -341,6 +341,39 @@ def test_execution_variants_do_not_change_the_trajectory(env, monkeypatch):
     np.testing.assert_array_equal(s0["aggregates"]["rg"], s1["aggregates"]["rg"])
 
 
+@pytest.mark.parametrize("env", [{}, {"MCAC_B200_FORCE_SORT_FAIL": "3"}, {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "64"}])
+def test_pipelined_submission_is_invisible(env, monkeypatch):
+    """Without step records mcac_gpu_run submits batch i+1 (event kernel, cell rebuild, queries, search, commit) before it has read
+    batch i back; the kernels enforce the step limit / finished() / pool room themselves.  The state after any number of steps must be
+    bit-identical to the one-batch-at-a-time loop (MCAC_B200_NO_PIPELINE=1), also across calls that stop mid-way, with device sorts
+    that give up, and with the sparse fast path of the sort."""
+    g = Golden("c3_small_seed42")
+    text = ini_text(merged_config(g.base, g.overrides))
+    monkeypatch.setenv("MCAC_B200_NO_PIPELINE", "1")
+    base = Simulation(text)
+    r0, _ = base.run(15000, batch=256)
+    monkeypatch.delenv("MCAC_B200_NO_PIPELINE")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    one = Simulation(text)
+    r1, _ = one.run(15000, batch=256)
+    parts = Simulation(text)
+    done = 0
+    for chunk in (1, 700, 5000, 513, 8786):
+        rp, _ = parts.run(chunk, batch=256)
+        assert rp["steps"] == chunk
+        done += chunk
+    assert done == 15000 and r0["steps"] == r1["steps"] == 15000 and r0["events"] == r1["events"] > 10
+    s0 = base.state()
+    for other in (one.state(), parts.state()):
+        assert s0["time"] == other["time"] and s0["n_agg"] == other["n_agg"]
+        np.testing.assert_array_equal(s0["sphere_label"], other["sphere_label"])
+        for k in ("x", "y", "z"):
+            np.testing.assert_array_equal(s0["spheres"][k], other["spheres"][k])
+        for k in ("rg", "proper_time", "time_step", "volume"):
+            np.testing.assert_array_equal(s0["aggregates"][k], other["aggregates"][k])
+
+
 def test_big_aggregate_search_form_is_the_same_search(monkeypatch):
     """The three-kernel search (phase 1 / sphere-pair tiles over the grid / phase 3) that single searches take once aggregates
     hold many spheres returns exactly what the one-CTA search returns: forced on for a whole growth run (pytest config, to its
