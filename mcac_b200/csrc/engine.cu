@@ -102,6 +102,7 @@ struct mcac_gpu {
     int ts_xcap = 0;
     int ts_min_n = 32768;     // MCAC_B200_TIE_MIN_N (0 disables the fast path)
     int ts_max_sparse = tiesort::kMaxSparse;  // MCAC_B200_TIE_MAX_SPARSE
+    bool ts_no_overlap = false;               // MCAC_B200_TIE_NO_OVERLAP
     long long *part_ll = nullptr;
     double *part_d = nullptr;
     int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
@@ -451,6 +452,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.ts_xcap = h->ts_xcap;
     a.ts_min_n = h->ts_min_n;
     a.skip_if_no_event = skip_if_no_event ? 1 : 0;
+    a.ts_no_overlap = h->ts_no_overlap ? 1 : 0;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
@@ -973,6 +975,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
         if (const char *e = getenv("MCAC_B200_TIE_MIN_N")) h->ts_min_n = std::max(0, atoi(e));
         if (const char *e = getenv("MCAC_B200_TIE_MAX_SPARSE")) h->ts_max_sparse = std::max(1, atoi(e));
+        if (getenv("MCAC_B200_TIE_NO_OVERLAP")) h->ts_no_overlap = true;
         // block-local sort levels staged in shared memory: (local_span + 2) entries of 48 B, if the SM has room for them
         h->event_smem_cap = 0;
         if (!getenv("MCAC_B200_NO_SORT_SMEM")) {

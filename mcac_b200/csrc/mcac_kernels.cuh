@@ -2208,6 +2208,7 @@ struct EventArgs {
     int ts_min_n;         // smallest table the fast path is tried on
     int smem_bytes;       // dynamic shared memory of the launch
     int skip_if_no_event; // return at once when Scalars::event == 0 (nothing changed since the last pick table)
+    int ts_no_overlap;    // test / tuning hook: all CTAs route, then the general sort starts (no overlap with the block-local levels)
 };
 struct BlockTeam {  // tiesort's Team for one CTA
     int tid, nthr;
@@ -2279,7 +2280,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const int n_slots = sc.n_agg_slots;
     // phase clocks of block 0 (SM cycles) accumulated into a.work[2 + k]: diagnostics for the K9 breakdown in profiles/
     long long t_prev = clock64();
-    auto lap = [&](int k) { if (gtid == 0 && a.work) { const long long t = clock64(); a.work[2 + k] += t - t_prev; t_prev = t; } };
+    // (atomicAdd without a use of its result is a fire-and-forget reduction: no round trip to L2 on the critical path)
+    auto work_add = [&](int k, long long v) { atomicAdd(reinterpret_cast<unsigned long long *>(a.work + k), (unsigned long long)v); };
+    auto lap = [&](int k) { if (gtid == 0 && a.work) { const long long t = clock64(); work_add(2 + k, t - t_prev); t_prev = t; } };
 
     // ---------------- phase A: live-slot count per chunk + refresh partials
     const int chunk_s = ((n_slots + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
@@ -2465,21 +2468,28 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     int depth = 2 * lg;
     int n_sort = n, delta = 0;  // the general sort below works on [0, n_sort) and writes its result at +delta
     // ---- tie-dominated table: the top levels on the sparse elements only (tie_sort.cuh)
-    bool ts_on = false;
+    bool ts_on = false, ts_ovl = false;
     if (ts_try) {
         long long x = 0;
         for (int bb = tid; bb < nblk; bb += nthr) x += a.part_ll[2048 + bb];
         x = block_sum_ll(x, sm_ll);
-        const int need = (4 * a.ts_xcap + tiesort::kTblStride + 16 + 2 * (nblk + 1)) * (int)sizeof(int);
-        ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && need <= a.smem_bytes;
+        // shared memory of the simulating CTA: four lists of x entries, one bucket table, and behind them an archive of the
+        // per-level tables (as many levels as fit) for the walk back from the handed-over segment
+        int ts_nb = 256;
+        while (ts_nb < x && ts_nb < tiesort::kBuckets) ts_nb <<= 1;
+        const int xs_pad = ((int)x + 3) & ~3;
+        const int used_ints = 4 * xs_pad + (ts_nb + 3) + 16 + 2 * (nblk + 1) + 4;
+        ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && used_ints * (int)sizeof(int) <= a.smem_bytes;
         if (ts_on) {
             const int xs = (int)x;
             int *st_pos = b.tmp_b;                                 // compact staged labels / weights of the sparse elements
             double *st_w = reinterpret_cast<double *>(b.flags);
+            int *sm = reinterpret_cast<int *>(dyn_smem);
+            int *a_s = sm, *a_i = a_s + xs_pad, *b_s = a_i + xs_pad, *b_i = b_s + xs_pad, *s_tbl = b_i + xs_pad, *s_misc = s_tbl + ts_nb + 3,
+                *s_base = s_misc + 16, *arch_R = s_base + 2 * (nblk + 1) + 4;
+            const int arch_levels = min(tiesort::kMaxLevels, (a.smem_bytes / (int)sizeof(int) - used_ints) / (xs + ts_nb + 3 + 1));
+            int *arch_T = arch_R + (size_t)arch_levels * xs;
             if (blk == 0) {
-                int *sm = reinterpret_cast<int *>(dyn_smem);
-                int *a_s = sm, *a_i = a_s + a.ts_xcap, *b_s = a_i + a.ts_xcap, *b_i = b_s + a.ts_xcap, *s_tbl = b_i + a.ts_xcap,
-                    *s_misc = s_tbl + tiesort::kTblStride, *s_base = s_misc + 16;
                 __shared__ int ts_ws[32];
                 for (int b0 = 0; b0 < nblk; b0 += nthr) {  // exclusive scan of the per-chunk counts (one round: nblk <= blockDim)
                     const int bb = b0 + tid;
@@ -2502,9 +2512,13 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 __syncthreads();
                 BlockTeam tm{tid, nthr, ts_ws};
                 tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, a_s, a_i, b_s, b_i,
-                                    s_tbl, s_misc);
+                                    s_tbl, s_misc, arch_R, arch_T, arch_levels);
                 // the sparse elements of the handed-over segment
                 const int hf = a.ts_plan->hand_f, hlen = a.ts_plan->hand_l - hf;
+                // overlap: this CTA fills the W elements of a small handed-over segment itself (walk back through the archived
+                // tables) and goes straight on to the block-local sort levels, while the other CTAs route the rest of the table
+                if (tid == 0)
+                    a.ts_plan->shift0 = (a.ts_plan->n_levels <= arch_levels && hlen <= a.local_span && nblk > 1 && !a.ts_no_overlap) ? 1 : 0;
                 for (int j = tid; j < xs; j += nthr) {
                     const int p = a_s[j] - hf, id = a_i[j];
                     b.perm[p] = st_pos[id];
@@ -2529,17 +2543,31 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             const int *__restrict__ T = a.ts_tbl;
             const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
             bool any_bad = false;
+            ts_ovl = sh_plan.shift0 != 0;
+            if (ts_ovl && blk == 0) {
+                for (int p = hf + tid; p < hf + hlen; p += nthr) {
+                    int lo = 0, hi = xs;  // a_s: ascending positions of the sparse elements at hand-over
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a_s[mid] < p) lo = mid + 1; else hi = mid; }
+                    if (lo < xs && a_s[lo] == p) continue;
+                    b.perm[p - hf] = tiesort::dense_origin(sh_plan, arch_R, arch_T, xs, ts_nb + 3, p);
+                    b.wk[p - hf] = ts_W;
+                    b.segf[p - hf] = 0;
+                    b.segl[p - hf] = hlen;
+                }
+                __syncthreads();
+            }
             // Every W element: final position, or its place in the handed-over segment.  kRoute elements per thread advance level
             // by level together, so that their table look-ups (independent of each other) are in flight at the same time.
             constexpr int kRoute = 4;
-            for (long long i0 = gtid; i0 < n; i0 += gsize * kRoute) {
+            const long long rtid = ts_ovl ? gtid - nthr : gtid, rsize = ts_ovl ? gsize - nthr : gsize;
+            for (long long i0 = (ts_ovl && blk == 0) ? (long long)n : rtid; i0 < n; i0 += rsize * kRoute) {
                 int pos[kRoute], e_base[kRoute], e_dep[kRoute];
                 unsigned e_m[kRoute], e_r[kRoute];  // e_m == 0: not (yet) in an all-W segment
                 bool live[kRoute];
 #pragma unroll
                 for (int j = 0; j < kRoute; j++) {
                     e_m[j] = 0; e_r[j] = 0; e_base[j] = 0; e_dep[j] = 0;
-                    const long long i = i0 + j * gsize;
+                    const long long i = i0 + j * rsize;
                     pos[j] = (int)i;
                     live[j] = i < n && is_sparse[i < n ? i : 0] == 0;
                 }
@@ -2621,15 +2649,15 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
 #pragma unroll
                 for (int j = 0; j < kRoute; j++) {  // straight into the pick table; the weight (W) is implied by the position >= hand_l
                     if (e_m[j] == 0) continue;
-                    const int fp = e_base[j] + (int)e_r[j], lab = (int)(i0 + j * gsize);
+                    const int fp = e_base[j] + (int)e_r[j], lab = (int)(i0 + j * rsize);
                     d.sorted_slot[fp] = d.slot_of_label[lab];
                     a.sorted_label[fp] = lab;
                 }
 #pragma unroll
                 for (int j = 0; j < kRoute; j++) {
-                    if (!live[j]) continue;
+                    if (!live[j] || ts_ovl) continue;  // (overlap: the simulating CTA has filled the handed-over segment)
                     const int p = pos[j] - hf;
-                    b.perm[p] = (int)(i0 + j * gsize);
+                    b.perm[p] = (int)(i0 + j * rsize);
                     b.wk[p] = ts_W;
                     b.segf[p] = 0;
                     b.segl[p] = hlen;
@@ -2639,8 +2667,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             n_sort = hlen;
             delta = hf;
             depth = sh_plan.hand_depth;
-            if (gtid == 0 && a.work) { a.work[12] += 1; a.work[13] += sh_plan.n_levels; a.work[14] += xs; a.work[15] += hlen; }
-            grid.sync();
+            if (gtid == 0 && a.work) { work_add(12, 1); work_add(13, sh_plan.n_levels); work_add(14, xs); work_add(15, hlen); }
+            if (!ts_ovl) grid.sync();
             lap(9);
         }
     }
@@ -2691,7 +2719,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     bool staged = false;
     int st_min = 0, st_max = 0;
     SortBufs gb = b;
-    grid.sync();  // first pivot + span in place
+    if (!ts_ovl) grid.sync();  // first pivot + span in place
+    else if (blk == 0) __syncthreads();
+    else active = false;       // overlap mode: the other CTAs are done with their part (routing) and wait behind the loop
     lap(2);
     while (active) {
         depth--;
@@ -2733,7 +2763,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             __syncthreads();
         }
         const int span = amax - amin + 1;  // + 1 so that pre[amax] exists
-        if (etid == 0 && a.work) { a.work[0] += span; a.work[1] += 1; }
+        if (etid == 0 && a.work) { work_add(0, span); work_add(1, 1); }
         const int chunk = ((span + enblk - 1) / enblk + nthr - 1) / nthr * nthr;
         // ---- flags + chunk sums
         {

@@ -113,12 +113,12 @@ TS_HD int all_equal_final(int cf, int cl, int pos, int dep_parent, bool &bad) {
 
 // A W element that starts at `pos`: its final position (handed == false) or its position inside the handed-over segment.
 template <class PR, class PT>
-TS_HD int dense_route(const Plan &P, PR R, PT tbl, int xcap, int pos, bool &handed, bool &bad) {
+TS_HD int dense_route(const Plan &P, PR R, PT tbl, int r_stride, int t_stride, int pos, bool &handed, bool &bad) {
     handed = false;
     for (int t = 0; t < P.n_levels; t++) {
         const Level L = P.lv[t];
-        PR Rt = R + (size_t)t * xcap;
-        PT Tt = tbl + (size_t)t * kTblStride;
+        PR Rt = R + (size_t)t * r_stride;
+        PT Tt = tbl + (size_t)t * t_stride;
         if (pos == L.f) pos = L.pick;
         else if (pos == L.pick) pos = L.f;
         if (pos > L.f) {
@@ -135,25 +135,47 @@ TS_HD int dense_route(const Plan &P, PR R, PT tbl, int xcap, int pos, bool &hand
     return pos;
 }
 
+// The W element found at position `pos` of the handed-over segment after the simulated levels: where it started (its label).
+// Every level is an involution on positions (pivot move, Hoare swaps), and a W element of the left part was a W position before
+// the partition as well (sparse elements never leave the left part), so the same look-ups run backwards.
+template <class PR, class PT>
+TS_HD int dense_origin(const Plan &P, PR R, PT tbl, int r_stride, int t_stride, int pos) {
+    for (int t = P.n_levels - 1; t >= 0; t--) {
+        const Level L = P.lv[t];
+        if (pos == L.f) { pos = L.pick; continue; }  // the pivot came from `pick`
+        const int ka = pos - (L.f + 1) - rank_lt(R + (size_t)t * r_stride, tbl + (size_t)t * t_stride, L.f, L.shift, pos);
+        if (ka < L.K) pos = L.l - 1 - ka;            // swapped in from the right stopper B[ka]
+        if (pos == L.pick) pos = L.f;                // the element the pivot move had put there
+    }
+    return pos;
+}
+
 // Bucket table of the ascending list S (x entries, positions in [f, l]): tbl[b] = entries whose bucket ((pos - f) >> shift) is
 // below b, for b = 0 .. nbk.  Written by "boundary marking" (entry j fills the buckets between its predecessor's and its own),
 // together with the global copies (Rg, Tg) the routing pass reads.
 template <class Team>
-TS_HD int build_table(Team &tm, int x, int nb, const int *S, int f, int l, int *s_tbl, int *Rg, int *Tg) {
+TS_HD int build_table(Team &tm, int x, int nb, const int *S, int f, int l, int *s_tbl, int *Rg, int *Tg, int *Ra, int *Ta) {
     int shift = 0;
     while (((l - f) >> shift) > nb - 1) shift++;
     const int nbk = ((l - f) >> shift) + 1;
     for (int j = tm.tid; j <= x; j += tm.nthr) {
         const int bprev = j == 0 ? -1 : (S[j - 1] - f) >> shift;
         const int bcur = j == x ? nbk : (S[j] - f) >> shift;
-        for (int b = bprev + 1; b <= bcur; b++) { s_tbl[b] = j; Tg[b] = j; }
-        if (j < x) Rg[j] = S[j];
+        for (int b = bprev + 1; b <= bcur; b++) {
+            s_tbl[b] = j;
+            Tg[b] = j;
+            if (Ta) Ta[b] = j;
+        }
+        if (j < x) {
+            Rg[j] = S[j];
+            if (Ra) Ra[j] = S[j];
+        }
     }
     return shift;
 }
 
 // The sparse simulation.  st_pos (ascending) / st_w: label and weight of the x elements whose weight is below W; n: table size;
-// depth0 = 2*floor(log2(n)).  Scratch of the team: four lists of xcap ints (a_s, a_i, b_s, b_i), s_tbl (kTblStride), s_misc (16).
+// depth0 = 2*floor(log2(n)).  Scratch of the team: four lists of x ints (a_s, a_i, b_s, b_i), s_tbl (nb + 3), s_misc (16).
 // On return plan, R[t*xcap ..], tbl[t*kTblStride ..] describe the levels t < n_levels, and (a_s[j], a_i[j]) are the position and
 // the index into st_pos / st_w of the sparse elements inside the handed-over segment (ascending positions).
 // Per level: pivot samples -> pivot move (one list entry changes place) -> bucket table -> K (parallel minimum) -> every sparse
@@ -161,7 +183,8 @@ TS_HD int build_table(Team &tm, int x, int nb, const int *S, int f, int l, int *
 // elements move to the K first W positions in reverse order, the left-hand ones stay), so the list stays sorted without sorting.
 template <class Team>
 TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *st_w, double W, int depth0, int hand_min, Plan *plan,
-                      int *R, int *tbl, int xcap, int *a_s, int *a_i, int *b_s, int *b_i, int *s_tbl, int *s_misc) {
+                      int *R, int *tbl, int xcap, int *a_s, int *a_i, int *b_s, int *b_i, int *s_tbl, int *s_misc,
+                      int *arch_R = nullptr, int *arch_T = nullptr, int arch_levels = 0) {
     int nb = 256;
     while (nb < x && nb < kBuckets) nb <<= 1;
     int f = 0, l = n, depth = depth0, t = 0;
@@ -212,7 +235,10 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         }
         tm.sync();
         const int M = len - 1, n_a = M - x;
-        const int shift = build_table(tm, x, nb, b_s, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride);
+        // (arch_*: a second copy of the tables of the first arch_levels levels, strides x and nb + 3, kept by the caller)
+        const bool ar = arch_R && t < arch_levels;
+        const int shift = build_table(tm, x, nb, b_s, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride,
+                                      ar ? arch_R + (size_t)t * x : nullptr, ar ? arch_T + (size_t)t * (nb + 3) : nullptr);
         // K = first k with not (k < n_a and A[k] < B[k]); A[k] = k-th W position, B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1
         if (tm.tid == 0) s_misc[4] = n_a;
         for (int k = tm.tid; k < 4; k += tm.nthr) s_misc[k] = -1;

@@ -35,8 +35,11 @@ static int run_case(int n, const std::vector<double> &w, int hand_min, long long
     std::vector<int> a_s(xcap), a_i(xcap), b_s(xcap), b_i(xcap), s_tbl(kTblStride), s_misc(16);
     Plan plan{};
     SerialTeam tm;
+    int nb = 256;
+    while (nb < x && nb < kBuckets) nb <<= 1;
+    std::vector<int> arch_R((size_t)kMaxLevels * xcap), arch_T((size_t)kMaxLevels * (nb + 3));
     plan_build(tm, n, x, st_pos.data(), st_w.data(), W, 2 * lg, hand_min, &plan, R.data(), tbl.data(), xcap, a_s.data(), a_i.data(),
-               b_s.data(), b_i.data(), s_tbl.data(), s_misc.data());
+               b_s.data(), b_i.data(), s_tbl.data(), s_misc.data(), arch_R.data(), arch_T.data(), kMaxLevels);
     if (plan.fail) { std::printf("plan.fail on n=%d x=%d\n", n, x); return 0; }
     *levels_out += plan.n_levels;
     std::vector<long long> out(n, -1);
@@ -53,7 +56,7 @@ static int run_case(int n, const std::vector<double> &w, int hand_min, long long
     for (int i = 0; i < n; i++) {
         if (is_sparse[i]) continue;
         bool handed = false, bad = false;
-        const int p = dense_route(plan, R.data(), tbl.data(), xcap, i, handed, bad);
+        const int p = dense_route(plan, R.data(), tbl.data(), xcap, kTblStride, i, handed, bad);
         if (bad) { std::printf("dense_route: depth limit on n=%d\n", n); return 0; }
         if (p < 0 || p >= n || out[p] != -1) { std::printf("n=%d x=%d: element %d -> %d collides / out of range\n", n, x, i, p); return 1; }
         if (handed && (p < hf || p >= hl)) { std::printf("handed element outside the segment\n"); return 1; }
@@ -62,6 +65,12 @@ static int run_case(int n, const std::vector<double> &w, int hand_min, long long
     }
     for (int i = 0; i < n; i++)
         if (out[i] < 0) { std::printf("n=%d: position %d left empty\n", n, i); return 1; }
+    // the inverse walk (block 0 of the event kernel fills the handed-over segment with it), on the archived tables
+    for (int p = hf; p < hl; p++) {
+        if (is_sparse[out[p]]) continue;
+        const int o = dense_origin(plan, arch_R.data(), arch_T.data(), x, nb + 3, p);
+        if (o != (int)out[p]) { std::printf("dense_origin: n=%d x=%d position %d -> %d, expected %lld\n", n, x, p, o, out[p]); return 1; }
+    }
     std::vector<size_t> arr(out.begin(), out.end());
     if (hl - hf > 1) {
         if (hl - hf > kLeaf) std::__introsort_loop(arr.begin() + hf, arr.begin() + hl, (long)plan.hand_depth, __gnu_cxx::__ops::__iter_comp_iter(cmp));

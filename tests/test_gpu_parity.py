@@ -315,7 +315,8 @@ def test_batch_width_does_not_change_the_trajectory():
 @pytest.mark.parametrize("env", [{"MCAC_B200_FORCE_SORT_FAIL": "3"}, {"MCAC_B200_NO_OVERLAP": "1"}, {"MCAC_B200_SEARCH_GROUP": "0"},
                                  {"MCAC_B200_SEARCH_GROUP": "4", "MCAC_B200_SEARCH_MB": "4"}, {"MCAC_B200_NO_SORT_SMEM": "1"},
                                  {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "64"},
-                                 {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "512", "MCAC_B200_TIE_MAX_SPARSE": "50"}])
+                                 {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "512", "MCAC_B200_TIE_MAX_SPARSE": "50"},
+                                 {"MCAC_B200_TIE_MIN_N": "100", "MCAC_B200_SORT_LOCAL": "64", "MCAC_B200_TIE_NO_OVERLAP": "1"}])
 def test_execution_variants_do_not_change_the_trajectory(env, monkeypatch):
     """Scheduling choices must be invisible in the results: a device sort that gives up (every 3rd one here) falls back to the
     multi-launch sort and the batch is redone; serialised vs overlapped cell rebuild; wide-only vs narrow-group contact search;
