@@ -388,11 +388,12 @@ def main():
     k9_gbs = k9_bytes / (event_ms / n_event * 1e-3) / 1e9 if event_ms > 0 else 0.0
     phases = ["reduce", "labels", "sort_init", "grid_levels", "local_levels", "leaves", "cumulative", "pick_table"]
     sorts = max(1, sum(r["sorts"] for r in reps))
-    roofline = {"kernel": "k_event (K9: labels + refresh + totals + 1/dt weights + replayed introsort + cumulative table, one cooperative "
-                          "launch per merge)", "bound": "hbm", "achieved": k9_gbs, "peak": peak, "unit": "GB/s", "frac": k9_gbs / peak,
-                "traffic": 54.6e6 if a.n_monomers == 1_000_000 else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload "
-                                  "(profiles/r1b_ncu_full_summary.md), per launch", "peak_source": peak_source, "launches": n_event, "avg_launch_us": 1e3 * event_ms / n_event,
+    roofline = {"kernel": "k_event (K9: labels + refresh + totals + 1/dt weights + replayed introsort [sparse simulation + routing for "
+                          "tie-dominated tables] + cumulative table, one cooperative launch per merge)", "bound": "hbm", "achieved": k9_gbs, "peak": peak, "unit": "GB/s", "frac": k9_gbs / peak,
+                "traffic": 28.25e6 if a.n_monomers == 1_000_000 else None,
+                "traffic_source": "dram__bytes_read.sum (28.2 MB) + dram__bytes_write.sum (0.05 MB: the written tables stay in L2) of one ncu --set full "
+                                  "capture of this kernel on this workload (profiles/r1c_ncu_full_summary.md), per launch",
+                "peak_source": peak_source, "launches": n_event, "avg_launch_us": 1e3 * event_ms / n_event,
                 "algorithmic_bytes_per_launch": k9_bytes, "share_of_step": event_ms / dev_ms if dev_ms else None,
                 "sort_levels_per_launch": sum(r["sort_levels"] for r in reps) / sorts,
                 "sort_span_elements_per_launch": sum(r["sort_span_elements"] for r in reps) / sorts,

@@ -1225,9 +1225,27 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         const int other = b.res[stop].other_agg;
         if (other >= 0 && sc.pool_top + d.a_n[sh_slot[stop]] + d.a_n[other] > d.sph_cap) { do_contact = false; reason = STOP_POOL; }
     }
-    // ---- commit the free-flight steps [0, stop): distinct aggregates, one warp per step
+    // ---- commit the free-flight steps [0, stop): distinct aggregates; single-sphere aggregates one THREAD per step (all of them
+    // in flight at once: the chain of dependent loads of a move is paid once, not once per round of warps), the others one warp per step
+    for (int j = tid; j < stop; j += nth) {
+        const int sj = sh_slot[j];
+        if (d.a_n[sj] != 1) continue;
+        const double dj = b.q_dist[j];
+        const double vx = b.q_dir[3 * j] * dj, vy = b.q_dir[3 * j + 1] * dj, vz = b.q_dir[3 * j + 2] * dj;
+        const double4 a = d.a_posr[sj];  // same arithmetic as agg_translate
+        const double nx = periodic_position(a.x + vx, box), ny = periodic_position(a.y + vy, box), nz = periodic_position(a.z + vz, box);
+        const double refx = nx - d.a_rx[sj], refy = ny - d.a_ry[sj], refz = nz - d.a_rz[sj];
+        const int off = d.a_off[sj];
+        const double4 rel = d.s_relv[off];
+        double4 p = d.s_posr[off];
+        p.x = refx + rel.x; p.y = refy + rel.y; p.z = refz + rel.z;
+        d.s_posr[off] = p;
+        agg_store_position(d, sj, a.x + vx, a.y + vy, a.z + vz, box);
+        d.a_ptime[sj] += dt_base * (dj / dj + 0.0);
+    }
     for (int j = warp; j < stop; j += nwarps) {
         const int sj = sh_slot[j];
+        if (d.a_n[sj] == 1) continue;
         const double dj = b.q_dist[j];
         agg_translate<false>(d, sj, b.q_dir[3 * j] * dj, b.q_dir[3 * j + 1] * dj, b.q_dir[3 * j + 2] * dj, box, lane, 32);
         if (lane == 0) d.a_ptime[sj] += dt_base * (dj / dj + 0.0);  // calcul.cpp:147-149 with move == full, n_try == 1
