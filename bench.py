@@ -399,7 +399,9 @@ def main():
                 "sort_span_elements_per_launch": sum(r["sort_span_elements"] for r in reps) / sorts,
                 "phase_us_per_launch": {**{p: sum(r["event_phase_cycles"][i] for r in reps) / 1965.0 / sorts for i, p in enumerate(phases)},
                                         **{p: sum(r["tie_phase_cycles"][i] for r in reps) / 1965.0 / sorts
-                                           for i, p in enumerate(["tie_sparse_simulation", "tie_routing_pass"])}},
+                                           for i, p in enumerate(["tie_sparse_simulation", "tie_routing_pass"])},
+                                        **{p: sum(r["tie_sim_cycles"][i] for r in reps) / 1965.0 / sorts
+                                           for i, p in enumerate(["tie_sim_gather", "tie_sim_levels", "tie_sim_handover_barrier"])}},
                 "tie_fast_path": {"sorts": sum(r["tie_sorts"] for r in reps), "of_sorts": sorts,
                                   "levels_per_sort": sum(r["tie_levels"] for r in reps) / max(1, sum(r["tie_sorts"] for r in reps)),
                                   "sparse_per_sort": sum(r["tie_sparse"] for r in reps) / max(1, sum(r["tie_sorts"] for r in reps)),

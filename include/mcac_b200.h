@@ -93,6 +93,8 @@ typedef struct mcac_run_report {
      * sorts that took the fast path, levels it simulated, sparse elements and elements handed to the general sort (sums) */
     int64_t tie_phase_cycles[2];
     int64_t tie_sorts, tie_levels, tie_sparse, tie_handed;
+    /* SM cycles inside the sparse simulation: gathering the staged sparse elements, the simulated levels, hand-over + grid barrier */
+    int64_t tie_sim_cycles[3];
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction

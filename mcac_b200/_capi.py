@@ -66,10 +66,11 @@ class RunReport(C.Structure):
                [(n, C.c_int64) for n in ["n_iter_without_event", "nucleated"]] + \
                [(n, C.c_double) for n in ["total_volume", "total_surface"]] + \
                [("tie_phase_cycles", C.c_int64 * 2)] + \
-               [(n, C.c_int64) for n in ["tie_sorts", "tie_levels", "tie_sparse", "tie_handed"]]
+               [(n, C.c_int64) for n in ["tie_sorts", "tie_levels", "tie_sparse", "tie_handed"]] + \
+               [("tie_sim_cycles", C.c_int64 * 3)]
 
     def as_dict(self) -> dict:
-        return {n: (list(getattr(self, n)) if n.endswith("_phase_cycles") else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n.endswith("_cycles") else getattr(self, n)) for n, _ in self._fields_}
 
 
 class SweepReport(C.Structure):

@@ -91,11 +91,11 @@ struct mcac_gpu {
     long long sort_levels = 0, sort_fallbacks = 0;
     int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
     int coop_bps = 1, sort_local_span = 4096;
-    int event_spare_sms = 8;  // MCAC_B200_EVENT_SPARE_SMS
+    int event_spare_sms = 24; // MCAC_B200_EVENT_SPARE_SMS (sweep in profiles/r1_tuning.md)
     int event_smem_cap = 0;   // shared-memory staging of the block-local sort levels (entries; 0 = levels stay in HBM/L2)
     size_t event_dyn_bytes = 0;  // dynamic shared memory of the event kernel's launches
     long long *event_work = nullptr;
-    long long event_work_seen[16] = {0};
+    long long event_work_seen[32] = {0};
     // tie-dominated pick tables (tie_sort.cuh): plan + per-level rank tables; allocated with the state when the table can be large
     tiesort::Plan *ts_plan = nullptr;
     int *ts_R = nullptr, *ts_tbl = nullptr;
@@ -460,8 +460,11 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     // grid: one CTA per 2048 aggregate slots, at most one CTA per SM — a small realization (ensembles, the early boxes of C1) gets a
     // single CTA whose barriers are __syncthreads-cheap and which leaves the other SMs to the other realizations' streams
     const int want_blocks = std::max(1, div_up(h->sc_host.n_agg_slots + (h->prm.with_nucleation ? 4096 : 0), 2048));
-    // a few SMs are left to the side stream (the overlapped Verlet cell rebuild cannot share an SM with a 512-thread, 120-register CTA)
-    const int grid_blocks = std::min(std::max(1, h->coop_blocks - (h->overlap ? h->event_spare_sms : 0)), want_blocks);
+    // a few SMs are left to the side stream (the overlapped Verlet cell rebuild cannot share an SM with a 512-thread, 120-register CTA):
+    // 8 when the event kernel takes > 400 us (general sort replay: the rebuild hides behind it anyway), event_spare_sms when the last pick
+    // table came from the sparse path (~200 us: the rebuild on 8 SMs would outlast it; sweep in profiles/r1_tuning.md)
+    const int spare = !h->overlap ? 0 : (h->sc_host.last_sort_tie ? h->event_spare_sms : std::min(8, h->event_spare_sms));
+    const int grid_blocks = std::min(std::max(1, h->coop_blocks - spare), want_blocks);
     CK(cudaLaunchCooperativeKernel(fn, dim3(grid_blocks), dim3(kEventThreads), args, h->event_dyn_bytes, h->stream));
     h->launches++;
     h->labels_valid = true;
@@ -1002,8 +1005,8 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, dyn);
         if (coop && oe == cudaSuccess && occ > 0) h->coop_blocks = h->n_sm * std::min(occ, h->coop_bps);
         if (getenv("MCAC_B200_NO_COOP")) h->coop_blocks = 0;
-        TRY(dev_alloc_persistent(h, &h->event_work, 16));
-        CK(cudaMemset(h->event_work, 0, 16 * sizeof(long long)));
+        TRY(dev_alloc_persistent(h, &h->event_work, 32));
+        CK(cudaMemset(h->event_work, 0, 32 * sizeof(long long)));
         TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
         TRY(dev_alloc_persistent(h, &h->part_d, 4 * 4096));
     }
@@ -1727,7 +1730,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->nucleated = nucleated_total;
         report->total_volume = sc.total_volume;
         report->total_surface = sc.total_surface;
-        long long w[16] = {0};
+        long long w[32] = {0};
         cudaMemcpy(w, h->event_work, sizeof(w), cudaMemcpyDeviceToHost);
         report->sort_span_elements = w[0] - h->event_work_seen[0];
         report->sort_levels = w[1] - h->event_work_seen[1];
@@ -1737,7 +1740,11 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->tie_levels = w[13] - h->event_work_seen[13];
         report->tie_sparse = w[14] - h->event_work_seen[14];
         report->tie_handed = w[15] - h->event_work_seen[15];
-        for (int k = 0; k < 16; k++) h->event_work_seen[k] = w[k];
+        for (int k = 0; k < 3; k++) {
+            report->tie_sim_cycles[k] = w[16 + k] - h->event_work_seen[16 + k];
+            report->tie_phase_cycles[0] += report->tie_sim_cycles[k];
+        }
+        for (int k = 0; k < 32; k++) h->event_work_seen[k] = w[k];
     }
     prof_collect(h, report);
     return E_OK;

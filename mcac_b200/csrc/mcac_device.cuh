@@ -36,6 +36,11 @@ struct Scalars {
     double p_dt, p_dt_indiv;
     int p_regime, p_regime_draws;  // check_InterPotentialRegime outcome of the last try (0 sticking) and draws it consumed
     int n_nucleated, pad_n;
+    // pick table of a tie-dominated run: cumulative_time_steps is affine (slope pick_w) from index pick_dense_from on, up to
+    // rounding — a hint for the lower_bound of pick_random (pick_dense_from == n_pick: no such stretch)
+    double pick_w;
+    int pick_dense_from;
+    int last_sort_tie;  // 1: the last pick table was made by the sparse path of the event kernel (it is short: see event_spare_sms)
 };
 enum StopReason { STOP_NONE = 0, STOP_CONTACT = 1, STOP_CONFLICT = 2, STOP_FINISHED = 3, STOP_BATCH_END = 4, STOP_POOL = 5 /* no room for the merged block: host compacts */ };
 

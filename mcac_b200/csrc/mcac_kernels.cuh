@@ -104,7 +104,23 @@ __global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir
     const double u_phi = uniform_from_rand(d.rng_buf[p + 2]);
     const int n = sc.n_pick;
     const double val = u_pick * d.cum[n - 1];
-    int lo = 0, hi = n;  // std::lower_bound: first index with cum[i] >= val
+    int lo = 0, hi = n;  // std::lower_bound: first index with cum[i] >= val (every i < lo has cum[i] < val, every i >= hi cum[i] >= val)
+    const int df = sc.pick_dense_from;
+    if (df > 0 && df < n) {
+        // Tie-dominated table: behind the sparse head the table grows by the same weight per entry, so the answer is within a few
+        // entries of an interpolated guess.  Two probes around the guess only narrow [lo, hi) when they confirm it; the search below
+        // is the same lower_bound on whatever range is left (exact for any guess).
+        const double c0 = d.cum[df - 1];
+        if (val > c0) {
+            lo = df;
+            const double g = (val - c0) / sc.pick_w;
+            const long long p = (long long)df + (g < 2.0e9 ? (long long)g : 2000000000LL);
+            const int q1 = (int)max((long long)df - 1, min((long long)n - 1, p - 3)), q2 = (int)max((long long)df - 1, min((long long)n - 1, p + 3));
+            const double v1 = d.cum[q1], v2 = d.cum[q2];
+            if (v1 < val) lo = max(lo, q1 + 1);
+            if (v2 >= val) hi = min(hi, q2);
+        } else hi = df - 1;
+    }
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
         if (d.cum[mid] < val) lo = mid + 1; else hi = mid;
@@ -1760,7 +1776,7 @@ __global__ void k_sorted_labels_to_slots(DevState d, const int *sorted_label, in
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     d.sorted_slot[i] = d.slot_of_label[sorted_label[i]];
-    if (i == 0) { d.sc->n_pick = n; d.sc->cum_total = d.cum[n - 1]; }
+    if (i == 0) { d.sc->n_pick = n; d.sc->cum_total = d.cum[n - 1]; d.sc->pick_dense_from = n; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2195,7 +2211,7 @@ __global__ void k_sort_finish(DevState d, SortBufs b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
     d.sorted_slot[i] = d.slot_of_label[b.perm[i]];
-    if (i == 0) { d.sc->n_pick = b.n; d.sc->cum_total = d.cum[b.n - 1]; }
+    if (i == 0) { d.sc->n_pick = b.n; d.sc->cum_total = d.cum[b.n - 1]; d.sc->pick_dense_from = b.n; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2234,6 +2250,11 @@ struct BlockTeam {  // tiesort's Team for one CTA
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
     __device__ __forceinline__ void atomic_min(int *p, int v) { atomicMin(p, v); }
+    __device__ __forceinline__ void team_min(int *p, int v) {  // called by every thread of the CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(kFull, v, o); v = t < v ? t : v; }
+        if ((tid & 31) == 0 && v != 0x7fffffff) atomicMin(p, v);
+    }
     __device__ __forceinline__ int exclusive_scan(int v) { int tot; return block_exclusive_scan(v, &tot, ws); }
 };
 namespace cgx = cooperative_groups;
@@ -2528,9 +2549,11 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     st_w[id] = chunk_w[src];
                 }
                 __syncthreads();
+                lap(14);
                 BlockTeam tm{tid, nthr, ts_ws};
                 tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, a_s, a_i, b_s, b_i,
                                     s_tbl, s_misc, arch_R, arch_T, arch_levels);
+                lap(15);
                 // the sparse elements of the handed-over segment
                 const int hf = a.ts_plan->hand_f, hlen = a.ts_plan->hand_l - hf;
                 // overlap: this CTA fills the W elements of a small handed-over segment itself (walk back through the archived
@@ -2547,7 +2570,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 if (tid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
             }
             grid.sync();
-            lap(8);
+            lap(16);  // (laps 14-16 -> work[16..18]: the sparse simulation in three parts; the host adds them up for phase 8)
             __shared__ tiesort::Plan sh_plan;
             for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
                 reinterpret_cast<int *>(&sh_plan)[k] = reinterpret_cast<const int *>(a.ts_plan)[k];
@@ -2563,10 +2586,22 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             bool any_bad = false;
             ts_ovl = sh_plan.shift0 != 0;
             if (ts_ovl && blk == 0) {
+                unsigned char *s_mark = reinterpret_cast<unsigned char *>(b_s);  // list b is free after plan_build: xs_pad ints >= hlen bytes?
+                const bool marks = hlen <= 4 * xs_pad;
+                if (marks) {
+                    for (int k = tid; k < hlen; k += nthr) s_mark[k] = 0;
+                    __syncthreads();
+                    for (int j = tid; j < xs; j += nthr) s_mark[a_s[j] - hf] = 1;
+                    __syncthreads();
+                }
                 for (int p = hf + tid; p < hf + hlen; p += nthr) {
-                    int lo = 0, hi = xs;  // a_s: ascending positions of the sparse elements at hand-over
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a_s[mid] < p) lo = mid + 1; else hi = mid; }
-                    if (lo < xs && a_s[lo] == p) continue;
+                    if (marks) {
+                        if (s_mark[p - hf]) continue;
+                    } else {
+                        int lo = 0, hi = xs;  // a_s: ascending positions of the sparse elements at hand-over
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (a_s[mid] < p) lo = mid + 1; else hi = mid; }
+                        if (lo < xs && a_s[lo] == p) continue;
+                    }
                     b.perm[p - hf] = tiesort::dense_origin(sh_plan, arch_R, arch_T, xs, ts_nb + 3, p);
                     b.wk[p - hf] = ts_W;
                     b.segf[p - hf] = 0;
@@ -2923,6 +2958,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         }
         barrier();
         // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
+        int lead_min = 0x7fffffff, lead_max = 0;  // span of the new segments this thread leads
         for (long long i = amin + etid; i < amax; i += esize) {
             const int f = b.segf[i], l = b.segl[i];
             if (l - f <= kSortLeaf) continue;
@@ -2933,12 +2969,23 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             b.segl[i] = nl;
             if (i == nf && nl - nf > kSortLeaf) {
                 if (depth > 0) {
-                    act[level & 1] = 1;
-                    atomicMin(&act[4 + 2 * ((level + 1) & 1)], nf);
-                    atomicMax(&act[5 + 2 * ((level + 1) & 1)], nl);
+                    lead_min = nf < lead_min ? nf : lead_min;
+                    lead_max = nl > lead_max ? nl : lead_max;
                     pivot_of(nf, nl);
                 } else act[2] = 1;  // would enter introsort's heap-sort branch
             }
+        }
+        // one atomic pair per warp, not per new segment (hundreds of same-address atomics per level in the deep levels)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int t0 = __shfl_xor_sync(kFull, lead_min, o), t1 = __shfl_xor_sync(kFull, lead_max, o);
+            lead_min = t0 < lead_min ? t0 : lead_min;
+            lead_max = t1 > lead_max ? t1 : lead_max;
+        }
+        if ((tid & 31) == 0 && lead_max > 0) {
+            act[level & 1] = 1;
+            atomicMin(&act[4 + 2 * ((level + 1) & 1)], lead_min);
+            atomicMax(&act[5 + 2 * ((level + 1) & 1)], lead_max);
         }
         barrier();
         active = act[level & 1] != 0;
@@ -3072,7 +3119,13 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         d.sorted_slot[i] = d.slot_of_label[lab];
         a.sorted_label[i] = lab;
     }
-    if (gtid == 0) { sc.n_pick = n; sc.cum_total = d.cum[n - 1]; }
+    if (gtid == 0) {
+        sc.n_pick = n;
+        sc.cum_total = d.cum[n - 1];
+        sc.pick_dense_from = ts_on ? delta + n_sort : n;  // behind the handed-over segment every entry is a W element
+        sc.pick_w = ts_W;
+        sc.last_sort_tie = ts_on ? 1 : 0;
+    }
     lap(7);
 }
 

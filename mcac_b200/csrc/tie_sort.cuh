@@ -153,24 +153,39 @@ TS_HD int dense_origin(const Plan &P, PR R, PT tbl, int r_stride, int t_stride, 
 // Bucket table of the ascending list S (x entries, positions in [f, l]): tbl[b] = entries whose bucket ((pos - f) >> shift) is
 // below b, for b = 0 .. nbk.  Written by "boundary marking" (entry j fills the buckets between its predecessor's and its own),
 // together with the global copies (Rg, Tg) the routing pass reads.
+// Bucket table of the ascending list S (x entries, positions in [f, l]): tbl[b] = entries whose bucket ((pos - f) >> shift) is
+// below b, for b = 0 .. nbk.  Written by "boundary marking" (entry j fills the buckets between its predecessor's and its own),
+// together with the global copies (Rg, Tg) the routing pass reads and the caller's archive (Ra, Ta; may be null).  The same pass
+// finds K, the number of Hoare swaps: the first k with not (k < n_a and A[k] < B[k]), where A[k] is the k-th W position and
+// B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1; entry j owns the k with exactly j sparse elements before A[k].
 template <class Team>
-TS_HD int build_table(Team &tm, int x, int nb, const int *S, int f, int l, int *s_tbl, int *Rg, int *Tg, int *Ra, int *Ta) {
+TS_HD int build_table_and_k(Team &tm, int x, int nb, const int *S, int f, int l, int *s_tbl, int *Rg, int *Tg, int *Ra, int *Ta, int *k_min) {
     int shift = 0;
     while (((l - f) >> shift) > nb - 1) shift++;
     const int nbk = ((l - f) >> shift) + 1;
+    const int M = l - f - 1, n_a = M - x;
+    int kbest = kIntMax;
     for (int j = tm.tid; j <= x; j += tm.nthr) {
-        const int bprev = j == 0 ? -1 : (S[j - 1] - f) >> shift;
-        const int bcur = j == x ? nbk : (S[j] - f) >> shift;
+        const int sp = j == 0 ? 0 : S[j - 1], sc = j == x ? 0 : S[j];
+        const int bprev = j == 0 ? -1 : (sp - f) >> shift;
+        const int bcur = j == x ? nbk : (sc - f) >> shift;
         for (int b = bprev + 1; b <= bcur; b++) {
             s_tbl[b] = j;
             Tg[b] = j;
             if (Ta) Ta[b] = j;
         }
         if (j < x) {
-            Rg[j] = S[j];
-            if (Ra) Ra[j] = S[j];
+            Rg[j] = sc;
+            if (Ra) Ra[j] = sc;
         }
+        const int lo = j == 0 ? 0 : sp - (f + 1) - (j - 1);
+        const int hi = j == x ? n_a : sc - (f + 1) - j;
+        const int need = M - 1 - j;
+        const int kmin = need <= 0 ? 0 : (need + 1) / 2;
+        const int k = lo > kmin ? lo : kmin;
+        if (k < hi && k < kbest) kbest = k;
     }
+    tm.team_min(k_min, kbest);  // (one shared-memory atomic per warp, not one per entry: about half of the entries are candidates)
     return shift;
 }
 
@@ -178,9 +193,10 @@ TS_HD int build_table(Team &tm, int x, int nb, const int *S, int f, int l, int *
 // depth0 = 2*floor(log2(n)).  Scratch of the team: four lists of x ints (a_s, a_i, b_s, b_i), s_tbl (nb + 3), s_misc (16).
 // On return plan, R[t*xcap ..], tbl[t*kTblStride ..] describe the levels t < n_levels, and (a_s[j], a_i[j]) are the position and
 // the index into st_pos / st_w of the sparse elements inside the handed-over segment (ascending positions).
-// Per level: pivot samples -> pivot move (one list entry changes place) -> bucket table -> K (parallel minimum) -> every sparse
-// element computes its new position AND its new rank in closed form from rank queries on the current table (the right-hand
-// elements move to the K first W positions in reverse order, the left-hand ones stay), so the list stays sorted without sorting.
+// Per level: pivot samples -> pivot move (one list entry changes place; only when the element at f is sparse) -> bucket table
+// for rank queries + K (parallel minimum), one pass -> every sparse element computes its new position AND its new rank in closed
+// form from rank queries on the current table (the right-hand elements move to the K first W positions in reverse order, the
+// left-hand ones stay), so the list stays sorted without sorting.  Two team barriers per level (three with a pivot move).
 template <class Team>
 TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *st_w, double W, int depth0, int hand_min, Plan *plan,
                       int *R, int *tbl, int xcap, int *a_s, int *a_i, int *b_s, int *b_i, int *s_tbl, int *s_misc,
@@ -188,14 +204,17 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
     int nb = 256;
     while (nb < x && nb < kBuckets) nb <<= 1;
     int f = 0, l = n, depth = depth0, t = 0;
-    for (int k = tm.tid; k < 5; k += tm.nthr) s_misc[k] = -1;
+    int *cs = a_s, *ci = a_i, *os = b_s, *oi = b_i;  // current list (positions, ids) and the other buffer
+    // s_misc: two sets of {sparse element at the pivot samples pa, pb, pc and at f; running minimum for K}, used alternately by levels
+    for (int k = tm.tid; k < 4; k += tm.nthr) s_misc[k] = -1;
+    if (tm.tid == 0) s_misc[4] = kIntMax;
     tm.sync();
     {
         const int pa = f + 1, pb = f + (l - f) / 2, pc = l - 1;
         for (int j = tm.tid; j < x; j += tm.nthr) {
             const int q = st_pos[j];
-            a_s[j] = q;
-            a_i[j] = j;
+            cs[j] = q;
+            ci[j] = j;
             if (q == pa) s_misc[0] = j;
             if (q == pb) s_misc[1] = j;
             if (q == pc) s_misc[2] = j;
@@ -206,10 +225,10 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
     for (;;) {
         const int len = l - f;
         if (len <= hand_min || len <= kLeaf || t == kMaxLevels || depth == 0) break;
+        int *mc = s_misc + 8 * (t & 1), *mn = s_misc + 8 * ((t + 1) & 1);  // this level's set, the next level's set
         const int pa = f + 1, pb = f + len / 2, pc = l - 1;
         // __move_median_to_first(first, first+1, mid, last-1) with the plain `<` of sort_indexes
-        const double ka = s_misc[0] < 0 ? W : st_w[a_i[s_misc[0]]], kb = s_misc[1] < 0 ? W : st_w[a_i[s_misc[1]]],
-                     kc = s_misc[2] < 0 ? W : st_w[a_i[s_misc[2]]];
+        const double ka = mc[0] < 0 ? W : st_w[ci[mc[0]]], kb = mc[1] < 0 ? W : st_w[ci[mc[1]]], kc = mc[2] < 0 ? W : st_w[ci[mc[2]]];
         int pick;
         double kp;
         if (ka < kb) {
@@ -219,72 +238,70 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         } else if (ka < kc) { pick = pa; kp = ka; }
         else if (kb < kc) { pick = pc; kp = kc; }
         else { pick = pb; kp = kb; }
-        const bool at_f = s_misc[3] >= 0;  // a sparse element at f is a_s[0]
-        if (kp != W) break;                // a sparse pivot: the rest goes to the general sort
+        const bool at_f = mc[3] >= 0;  // a sparse element at f is cs[0]
+        if (kp != W) break;            // a sparse pivot: the rest goes to the general sort
         depth--;
-        // pivot move: the element at f goes to `pick`  (list a -> list b)
-        for (int j = tm.tid; j < x; j += tm.nthr) {
-            const int q = a_s[j];
-            if (!at_f) { b_s[j] = q; b_i[j] = a_i[j]; }
-            else if (j > 0) {
-                const int r = (j - 1) + (q > pick ? 1 : 0);
-                b_s[r] = q;
-                b_i[r] = a_i[j];
-                if (q < pick && (j == x - 1 || a_s[j + 1] > pick)) { b_s[j] = pick; b_i[j] = a_i[0]; }
-            } else if (x == 1 || a_s[1] > pick) { b_s[0] = pick; b_i[0] = a_i[0]; }
+        for (int k = tm.tid; k < 4; k += tm.nthr) mn[k] = -1;  // (last read before the barrier that ended the previous level)
+        if (tm.tid == 0) mn[4] = kIntMax;
+        if (at_f) {  // pivot move: the element at f goes to `pick`  (current list -> other buffer, which becomes the current one)
+            for (int j = tm.tid; j < x; j += tm.nthr) {
+                const int q = cs[j];
+                if (j > 0) {
+                    const int r = (j - 1) + (q > pick ? 1 : 0);
+                    os[r] = q;
+                    oi[r] = ci[j];
+                    if (q < pick && (j == x - 1 || cs[j + 1] > pick)) { os[j] = pick; oi[j] = ci[0]; }
+                } else if (x == 1 || cs[1] > pick) { os[0] = pick; oi[0] = ci[0]; }
+            }
+            int *ts_ = cs; cs = os; os = ts_;
+            int *ti_ = ci; ci = oi; oi = ti_;
+            tm.sync();
         }
-        tm.sync();
         const int M = len - 1, n_a = M - x;
         // (arch_*: a second copy of the tables of the first arch_levels levels, strides x and nb + 3, kept by the caller)
         const bool ar = arch_R && t < arch_levels;
-        const int shift = build_table(tm, x, nb, b_s, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride,
-                                      ar ? arch_R + (size_t)t * x : nullptr, ar ? arch_T + (size_t)t * (nb + 3) : nullptr);
-        // K = first k with not (k < n_a and A[k] < B[k]); A[k] = k-th W position, B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1
-        if (tm.tid == 0) s_misc[4] = n_a;
-        for (int k = tm.tid; k < 4; k += tm.nthr) s_misc[k] = -1;
+        const int shift = build_table_and_k(tm, x, nb, cs, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride,
+                                            ar ? arch_R + (size_t)t * x : nullptr, ar ? arch_T + (size_t)t * (nb + 3) : nullptr, &mc[4]);
         tm.sync();
-        for (int j = tm.tid; j <= x; j += tm.nthr) {  // the k with exactly j sparse elements before A[k]: [lo, hi)
-            const int lo = j == 0 ? 0 : b_s[j - 1] - (f + 1) - (j - 1);
-            const int hi = j == x ? n_a : b_s[j] - (f + 1) - j;
-            const int need = M - 1 - j;
-            const int kmin = need <= 0 ? 0 : (need + 1) / 2;
-            const int k = lo > kmin ? lo : kmin;
-            if (k < hi) tm.atomic_min(&s_misc[4], k);
-        }
-        tm.sync();
-        const int K = s_misc[4];
-        const int aK = K < n_a ? select_dense(b_s, s_tbl, f, shift, K) : kIntMax;
+        const int K = mc[4] < n_a ? mc[4] : n_a;
+        const int aK = K < n_a ? select_dense(cs, s_tbl, f, shift, K) : kIntMax;
         const int bK = K > 0 ? l - K : l;
         const int cut = aK < bK ? aK : bK;
-        // moves (list b -> list a, still ascending) + the pivot samples of the next level [f, cut)
+        // moves (current list -> other buffer, still ascending) + the pivot samples of the next level [f, cut)
         const int npa = f + 1, npb = f + (cut - f) / 2, npc = cut - 1;
         for (int j = tm.tid; j < x; j += tm.nthr) {
-            const int q = b_s[j], kb2 = l - 1 - q;
+            const int q = cs[j], kb2 = l - 1 - q;
             int np, nr;
             if (kb2 < K) {  // right stopper of a swap: goes to the kb2-th W position; the movers end up in reverse order
-                np = select_dense(b_s, s_tbl, f, shift, kb2);
+                np = select_dense(cs, s_tbl, f, shift, kb2);
                 nr = (np - (f + 1) - kb2) + (x - 1 - j);
             } else {        // stays; the movers that land before it: those with kb < c = W positions before q
                 const int c = q - (f + 1) - j;
                 const int first_mover = (l - c > l - K) ? l - c : l - K;
                 np = q;
-                nr = j + (x - rank_lt(b_s, s_tbl, f, shift, first_mover));
+                nr = j + (x - rank_lt(cs, s_tbl, f, shift, first_mover));
             }
-            a_s[nr] = np;
-            a_i[nr] = b_i[j];
-            if (np == npa) s_misc[0] = nr;
-            if (np == npb) s_misc[1] = nr;
-            if (np == npc) s_misc[2] = nr;
-            if (np == f) s_misc[3] = nr;
+            os[nr] = np;
+            oi[nr] = ci[j];
+            if (np == npa) mn[0] = nr;
+            if (np == npb) mn[1] = nr;
+            if (np == npc) mn[2] = nr;
+            if (np == f) mn[3] = nr;
         }
         if (tm.tid == 0) {
             Level L;
             L.f = f; L.l = l; L.pick = pick; L.K = K; L.cut = cut; L.depth = depth; L.shift = shift; L.pad = 0;
             plan->lv[t] = L;
         }
+        { int *ts_ = cs; cs = os; os = ts_; }
+        { int *ti_ = ci; ci = oi; oi = ti_; }
         l = cut;
         t++;
         tm.sync();
+    }
+    if (cs != a_s) {  // the caller reads the final list from (a_s, a_i)
+        tm.sync();
+        for (int j = tm.tid; j < x; j += tm.nthr) { a_s[j] = cs[j]; a_i[j] = ci[j]; }
     }
     if (tm.tid == 0) {
         plan->n_levels = t;
@@ -305,6 +322,7 @@ struct SerialTeam {
     void sync() {}
     int atomic_add(int *p, int v) { const int o = *p; *p += v; return o; }
     void atomic_min(int *p, int v) { if (v < *p) *p = v; }
+    void team_min(int *p, int v) { if (v < *p) *p = v; }
     int exclusive_scan(int) { return 0; }
 };
 
