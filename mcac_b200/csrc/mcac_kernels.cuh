@@ -1121,7 +1121,14 @@ __device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int 
         d.sc->n_agg -= 1;
     }
     __syncthreads();
-    agg_update<true>(d, kept, true, tid, nth, scratch, box);
+    // Aggregate::update() of the merged aggregate: a small one (the usual case: two monomers, a monomer and a dimer) by ONE thread —
+    // the CTA-cooperative form is a chain of ~20 block barriers for a handful of spheres
+    if (n_k + n_r <= kSingleMax) {
+        if (tid == 0) agg_update_single(d, kept, true, box);
+        __syncthreads();
+    } else {
+        agg_update<true>(d, kept, true, tid, nth, scratch, box);
+    }
     if (tid == 0) {
         d.a_ptime[kept] = newtime;
         d.a_charge[kept] = total_charge;
@@ -3043,32 +3050,21 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             for (int i = 1; i < n; i++) { acc = acc + fw(i); d.cum[i] = acc; }
         }
     } else {
-        const int chunk_c = ((n + nblk - 1) / nblk + nthr - 1) / nthr * nthr;
-        const int lo = blk * chunk_c, hi = min(n, lo + chunk_c);
-        double acc = 0.;
-        for (int i = lo + tid; i < hi; i += nthr) acc += fw(i);
-        const double t = block_sum_fixed(acc, sm_d);
-        if (tid == 0) a.part_d[3 * nblk + blk] = t;
+        // Fixed tree, independent of the launch shape: chunks of kCumRounds * blockDim entries (CTA b takes chunks b, b + gridDim, ...),
+        // chunk sums combined in chunk order, inside a chunk one round of blockDim entries after the other —
+        // cum[i] = (carry + (wtot[0] + .. + wtot[w-1])) + inc, carry' = (carry + wbase of the last warp) + its total.
+        constexpr int kCumRounds = 16, kCumWarps = kEventThreads / 32;
+        const int chunk_c = kCumRounds * nthr, n_chunks = (n + chunk_c - 1) / chunk_c;
+        double *chunk_sum = a.part_d + 8192;  // behind the per-block partials: room for 8192 chunks (6.7e7 entries)
+        for (int c = blk; c < n_chunks; c += nblk) {
+            const int lo = c * chunk_c, hi = min(n, lo + chunk_c);
+            double acc = 0.;
+            for (int i = lo + tid; i < hi; i += nthr) acc += fw(i);
+            const double t = block_sum_fixed(acc, sm_d);
+            if (tid == 0) chunk_sum[c] = t;
+        }
         grid.sync();
         __shared__ double carry_d;
-        if (nblk <= kMaxCoopBlocks) {
-            for (int bb = tid; bb < blk; bb += nthr) sh_pd[0][bb] = a.part_d[3 * nblk + bb];
-            __syncthreads();
-            if (tid == 0) {
-                double base = 0.;
-                for (int bb = 0; bb < blk; bb++) base += sh_pd[0][bb];  // sequential: deterministic
-                carry_d = base;
-            }
-        } else if (tid == 0) {
-            double base = 0.;
-            for (int bb = 0; bb < blk; bb++) base += a.part_d[3 * nblk + bb];
-            carry_d = base;
-        }
-        __syncthreads();
-        // Same arithmetic as one round of blockDim elements after the other — cum[i] = (carry + (wtot[0] + .. + wtot[w-1])) + inc,
-        // carry' = (carry + wbase of the last warp) + its total — scheduled 16 rounds at a time: warp scans of all rounds, the warp bases
-        // of every (round, warp) in parallel, the 16 carries by one thread, then the warp scans again with their bases.
-        constexpr int kCumRounds = 16, kCumWarps = kEventThreads / 32;
         __shared__ double s_wtot[kCumRounds][kCumWarps], s_wbase[kCumRounds][kCumWarps], s_carry[kCumRounds];
         const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
         auto warp_inc = [&](double v) {
@@ -3080,10 +3076,26 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
             return inc;
         };
-        for (int t0 = lo; t0 < hi; t0 += kCumRounds * nthr) {
-            const int nr = min(kCumRounds, (hi - t0 + nthr - 1) / nthr);
+        double base_run = 0.;  // (thread 0) sum of the chunks before the next one of this CTA, in chunk order
+        int base_upto = 0;
+        for (int c = blk; c < n_chunks; c += nblk) {
+            const int lo = c * chunk_c, hi = min(n, lo + chunk_c);
+            // the chunk sums [base_upto, c) through shared memory (at most gridDim of them per step), added by one thread in order
+            const int cnt = c - base_upto;
+            for (int k0 = 0; k0 < cnt; k0 += kMaxCoopBlocks) {
+                const int m = min(kMaxCoopBlocks, cnt - k0);
+                __syncthreads();
+                for (int k = tid; k < m; k += nthr) sh_pd[0][k] = chunk_sum[base_upto + k0 + k];
+                __syncthreads();
+                if (tid == 0)
+                    for (int k = 0; k < m; k++) base_run += sh_pd[0][k];
+            }
+            base_upto = c;
+            if (tid == 0) carry_d = base_run;
+            __syncthreads();
+            const int nr = (hi - lo + nthr - 1) / nthr;
             for (int r = 0; r < nr; r++) {
-                const int i = t0 + r * nthr + tid;
+                const int i = lo + r * nthr + tid;
                 const double inc = warp_inc((i < hi) ? fw(i) : 0.);
                 if (lane == 31) s_wtot[r][w] = inc;
             }
@@ -3096,16 +3108,15 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
             __syncthreads();
             if (tid == 0) {
-                double c = carry_d;
+                double cc = carry_d;
                 for (int r = 0; r < nr; r++) {
-                    s_carry[r] = c;
-                    c = c + s_wbase[r][nw - 1] + s_wtot[r][nw - 1];
+                    s_carry[r] = cc;
+                    cc = cc + s_wbase[r][nw - 1] + s_wtot[r][nw - 1];
                 }
-                carry_d = c;
             }
             __syncthreads();
             for (int r = 0; r < nr; r++) {
-                const int i = t0 + r * nthr + tid;
+                const int i = lo + r * nthr + tid;
                 const double inc = warp_inc((i < hi) ? fw(i) : 0.);
                 if (i < hi) d.cum[i] = s_carry[r] + s_wbase[r][w] + inc;
             }
