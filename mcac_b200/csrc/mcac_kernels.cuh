@@ -2882,26 +2882,35 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     const int i = t0 + r * nthr + tid;
                     const long long v = (i < hi) ? b.flags[i] : 0;
                     const long long inc = warp_inclusive_scan_ll(v, lane);
-                    if (i < hi) b.pre[i] = carry + sh_wt[r * nw + wrp] + inc - v;
+                    if (i < hi) {
+                        // the prefix over the whole span is also the slot of a stopper: the left stoppers of a segment [f, l) end up in
+                        // tmp_a[amin + pre[f+1].a .. amin + pre[l].a) in position order, its right stoppers likewise in tmp_b — no
+                        // per-segment reads, no separate scatter pass
+                        const long long pre_i = carry + sh_wt[r * nw + wrp] + inc - v;
+                        b.pre[i] = pre_i;
+                        if (v & 1LL) b.tmp_a[amin + (int)(pre_i & 0xffffffffLL)] = i;
+                        if (v >> 32) b.tmp_b[amin + (int)(pre_i >> 32)] = i;
+                    }
                 }
                 carry += sh_wt[kRounds * (kEventThreads / 32)];
                 __syncthreads();
             }
         }
         barrier();
-        // ---- scatter the "not < pivot" (ascending) and "not > pivot" (descending) positions.
+        // ---- pairwise swaps + where the two scans stop.
         // A segment whose elements ALL equal the pivot (whole tie classes: every monomer of a monodisperse run) needs no
         // more memory passes: introsort's moves on equal keys do not depend on the data (median-of-3 picks `mid`, the
         // Hoare partition mirrors [f+1, l-1], the cut falls at f+1+(m-1)/2, leaves do not move), so every element
         // computes its final position in registers and leaves the level loop.
-        for (long long i = amin + etid; i < amax; i += esize) {
-            const int f = b.segf[i], l = b.segl[i];
+        for (long long j = amin + etid; j < amax; j += esize) {
+            const int f = b.segf[j], l = b.segl[j];
             if (l - f <= kSortLeaf) continue;
-            const int base = f + 1;
+            const int base = f + 1, k = (int)j - base;
             const long long p0 = b.pre[base], pl = b.pre[l];
-            const int n_a = (int)((pl & 0xffffffffLL) - (p0 & 0xffffffffLL)), n_b = (int)((pl >> 32) - (p0 >> 32));
+            const int p0a = (int)(p0 & 0xffffffffLL), plb = (int)(pl >> 32);
+            const int n_a = (int)(pl & 0xffffffffLL) - p0a, n_b = plb - (int)(p0 >> 32);
             if (n_a == l - f - 1 && n_b == l - f - 1) {
-                int cf = f, cl = l, pos = (int)i, dep = depth;
+                int cf = f, cl = l, pos = (int)j, dep = depth;
                 bool first = true, bad = false;
                 while (cl - cf > kSortLeaf) {
                     const int m = cl - cf;
@@ -2919,31 +2928,20 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     }
                 }
                 if (bad) { act[2] = 1; continue; }
-                b.fin_perm[pos + delta] = b.perm[i];
-                b.fin_wk[pos + delta] = b.wk[i];
-                b.segf[i] = 0x7fffffff;  // done: inactive in every later phase
-                b.segl[i] = 0;
+                b.fin_perm[pos + delta] = b.perm[j];
+                b.fin_wk[pos + delta] = b.wk[j];
+                b.segf[j] = 0x7fffffff;  // done: inactive in every later phase
+                b.segl[j] = 0;
                 continue;
             }
-            if (i <= f) continue;
-            const long long pi_ = b.pre[i];
-            const long long fl = b.flags[i];
-            if (fl & 1LL) b.tmp_a[base + (int)((pi_ & 0xffffffffLL) - (p0 & 0xffffffffLL))] = (int)i;
-            if (fl >> 32) b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = (int)i;
-        }
-        barrier();
-        // ---- pairwise swaps + where the two scans stop
-        for (long long j = amin + etid; j < amax; j += esize) {
-            const int f = b.segf[j], l = b.segl[j];
-            if (l - f <= kSortLeaf || j <= f) continue;
-            const int base = f + 1, k = (int)j - base;
-            const long long p0 = b.pre[base], pl = b.pre[l];
-            const int n_a = (int)((pl & 0xffffffffLL) - (p0 & 0xffffffffLL)), n_b = (int)((pl >> 32) - (p0 >> 32));
+            if (j <= f) continue;
+            // k-th left stopper: tmp_a[A0 + k]; k-th right stopper counted from the right: tmp_b[B1 - k]
+            const int *A = b.tmp_a + amin + p0a, *B = b.tmp_b + amin + plb - 1;
             const int m = n_a < n_b ? n_a : n_b;
-            const bool sw = k < m && b.tmp_a[base + k] < b.tmp_b[base + k];
-            const bool next_sw = (k + 1 < m) && b.tmp_a[base + k + 1] < b.tmp_b[base + k + 1];
+            const bool sw = k < m && A[k] < B[-k];
+            const bool next_sw = (k + 1 < m) && A[k + 1] < B[-(k + 1)];
             if (sw) {
-                const int pa = b.tmp_a[base + k], pb = b.tmp_b[base + k];
+                const int pa = A[k], pb = B[-k];
                 const double ka = b.wk[pa];
                 const int la = b.perm[pa];
                 b.wk[pa] = b.wk[pb]; b.perm[pa] = b.perm[pb];
@@ -2953,8 +2951,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             if (sw && !next_sw) s_ = k + 1;
             else if (k == 0 && !sw) s_ = 0;
             if (s_ >= 0) {
-                const int a_s = s_ < n_a ? b.tmp_a[base + s_] : 0x7fffffff;
-                const int b_prev = s_ > 0 ? b.tmp_b[base + s_ - 1] : l;
+                const int a_s = s_ < n_a ? A[s_] : 0x7fffffff;
+                const int b_prev = s_ > 0 ? B[-(s_ - 1)] : l;
                 b.cut[f] = a_s < b_prev ? a_s : b_prev;
             }
         }
