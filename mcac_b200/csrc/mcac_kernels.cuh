@@ -2253,16 +2253,12 @@ struct EventArgs {
 };
 struct BlockTeam {  // tiesort's Team for one CTA
     int tid, nthr;
-    int *ws;  // >= 32 ints of shared memory
     __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
-    __device__ __forceinline__ void atomic_min(int *p, int v) { atomicMin(p, v); }
     __device__ __forceinline__ void team_min(int *p, int v) {  // called by every thread of the CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(kFull, v, o); v = t < v ? t : v; }
         if ((tid & 31) == 0 && v != 0x7fffffff) atomicMin(p, v);
     }
-    __device__ __forceinline__ int exclusive_scan(int v) { int tot; return block_exclusive_scan(v, &tot, ws); }
 };
 namespace cgx = cooperative_groups;
 extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -2557,7 +2553,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 }
                 __syncthreads();
                 lap(14);
-                BlockTeam tm{tid, nthr, ts_ws};
+                BlockTeam tm{tid, nthr};
                 tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, a_s, a_i, b_s, b_i,
                                     s_tbl, s_misc, arch_R, arch_T, arch_levels);
                 lap(15);
@@ -2566,7 +2562,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 // overlap: this CTA fills the W elements of a small handed-over segment itself (walk back through the archived
                 // tables) and goes straight on to the block-local sort levels, while the other CTAs route the rest of the table
                 if (tid == 0)
-                    a.ts_plan->shift0 = (a.ts_plan->n_levels <= arch_levels && hlen <= a.local_span && nblk > 1 && !a.ts_no_overlap) ? 1 : 0;
+                    a.ts_plan->overlap = (a.ts_plan->n_levels <= arch_levels && hlen <= a.local_span && nblk > 1 && !a.ts_no_overlap) ? 1 : 0;
                 for (int j = tid; j < xs; j += nthr) {
                     const int p = a_s[j] - hf, id = a_i[j];
                     b.perm[p] = st_pos[id];
@@ -2591,7 +2587,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             const int *__restrict__ T = a.ts_tbl;
             const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
             bool any_bad = false;
-            ts_ovl = sh_plan.shift0 != 0;
+            ts_ovl = sh_plan.overlap != 0;
             if (ts_ovl && blk == 0) {
                 unsigned char *s_mark = reinterpret_cast<unsigned char *>(b_s);  // list b is free after plan_build: xs_pad ints >= hlen bytes?
                 const bool marks = hlen <= 4 * xs_pad;

@@ -13,7 +13,7 @@
 //     is handed to the general level-synchronous sort (`k_event`), which finishes the small mixed remainder.
 // The result is the same permutation std::sort produces (tests/native/tie_sort_host.cpp checks this header against
 // libstdc++'s own __introsort_loop on the host; the GPU parity tests check it against the oracle).
-// The code is host/device neutral: a `Team` supplies tid / nthr / sync / atomics (serial on the host, one CTA on the device).
+// The code is host/device neutral: a `Team` supplies tid / nthr / sync / team_min (serial on the host, one CTA on the device).
 #pragma once
 #ifdef __CUDACC__
 #define TS_HD __host__ __device__ __forceinline__
@@ -44,7 +44,7 @@ struct Plan {
     int hand_f, hand_l, hand_depth;   // segment handed to the general sort, before its pivot move; depth_limit it starts with
     int fail;                         // introsort's depth limit hit (heap-sort branch): caller falls back
     int x;                            // sparse elements
-    int shift0;                       // bucket shift of table 0 (initial positions over [0, n))
+    int overlap;                      // set by the caller: the simulating CTA fills and sorts the handed-over segment itself
     int nb;                           // buckets of a rank table (power of two >= x, 256 .. kBuckets)
     double W;
     Level lv[kMaxLevels];
@@ -310,7 +310,7 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         plan->hand_depth = depth;
         plan->fail = (depth == 0 && l - f > kLeaf) ? 1 : 0;
         plan->x = x;
-        plan->shift0 = 0;
+        plan->overlap = 0;
         plan->nb = nb;
         plan->W = W;
     }
@@ -320,10 +320,7 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
 struct SerialTeam {
     int tid = 0, nthr = 1;
     void sync() {}
-    int atomic_add(int *p, int v) { const int o = *p; *p += v; return o; }
-    void atomic_min(int *p, int v) { if (v < *p) *p = v; }
     void team_min(int *p, int v) { if (v < *p) *p = v; }
-    int exclusive_scan(int) { return 0; }
 };
 
 }  // namespace tiesort
