@@ -2995,8 +2995,33 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         lap(local ? 4 : 3);
         level++;
     }
+    // __final_insertion_sort of one leaf [i, segl[i]) by its first element's thread
+    auto sort_leaf = [&](int i) {
+        const int f = i, l = b.segl[i];
+        for (int x = f + 1; x < l; x++) {
+            const double kv = b.wk[x];
+            const int lv = b.perm[x];
+            int y = x - 1;
+            while (y >= f && w_less(kv, lv, b.wk[y], b.perm[y], b.stable)) {
+                b.wk[y + 1] = b.wk[y]; b.perm[y + 1] = b.perm[y];
+                y--;
+            }
+            b.wk[y + 1] = kv; b.perm[y + 1] = lv;
+        }
+        for (int x = f; x < l; x++) { b.fin_perm[x + delta] = b.perm[x]; b.fin_wk[x + delta] = b.wk[x]; }
+    };
+    // overlap mode: the handed-over segment belongs to block 0 alone, which also sorts its leaves (out of shared memory when the
+    // levels were staged): the grid-wide leaf pass and its barrier are skipped
+    const bool leaves_by_block0 = ts_ovl && n_sort > kSortLeaf;
     if (local && blk == 0) {
-        if (staged) {  // back to HBM for the leaf pass
+        if (leaves_by_block0) {
+            __syncthreads();
+            if (!fail)
+                for (int i = tid; i < n_sort; i += nthr)
+                    if (b.segf[i] == i) sort_leaf(i);
+            __syncthreads();
+            if (staged) b = gb;
+        } else if (staged) {  // back to HBM for the leaf pass
             __syncthreads();
             for (int i = st_min + tid; i < st_max; i += nthr) {
                 gb.perm[i] = b.perm[i];
@@ -3016,24 +3041,11 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         return;
     }
     // ---- __final_insertion_sort per leaf
-    for (long long i = gtid; i < n_sort; i += gsize) {
-        if (b.segf[i] != i) continue;
-        const int f = (int)i, l = b.segl[i];
-        for (int x = f + 1; x < l; x++) {
-            const double kv = b.wk[x];
-            const int lv = b.perm[x];
-            int y = x - 1;
-            while (y >= f && w_less(kv, lv, b.wk[y], b.perm[y], b.stable)) {
-                b.wk[y + 1] = b.wk[y]; b.perm[y + 1] = b.perm[y];
-                y--;
-            }
-            b.wk[y + 1] = kv; b.perm[y + 1] = lv;
-        }
-        b.fin_perm[i + delta] = b.perm[i];  // whole leaf, written by its leader after sorting it
-        b.fin_wk[i + delta] = b.wk[i];
-        for (int x = f + 1; x < l; x++) { b.fin_perm[x + delta] = b.perm[x]; b.fin_wk[x + delta] = b.wk[x]; }
+    if (!leaves_by_block0) {
+        for (long long i = gtid; i < n_sort; i += gsize)
+            if (b.segf[i] == i) sort_leaf((int)i);
+        grid.sync();
     }
-    grid.sync();
     lap(5);
     // ---- cumulative_time_steps (sorted weights: the general sort's output inside [delta, delta + n_sort), W everywhere else)
     auto fw = [&](int i) { return (i >= delta && i < delta + n_sort) ? b.fin_wk[i] : ts_W; };
