@@ -2995,6 +2995,22 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         lap(local ? 4 : 3);
         level++;
     }
+    // cumulative_time_steps, first half: sums of fixed chunks of the sorted weights (the general sort's output inside
+    // [delta, delta + n_sort), W everywhere else); see the second half below
+    auto fw = [&](int i) { return (i >= delta && i < delta + n_sort) ? b.fin_wk[i] : ts_W; };
+    constexpr int kCumRounds = 16, kCumWarps = kEventThreads / 32;
+    const int chunk_c = kCumRounds * nthr, n_chunks = (n + chunk_c - 1) / chunk_c;
+    double *chunk_sum = a.part_d + 8192;  // behind the per-block partials: room for 8192 chunks (6.7e7 entries)
+    auto cum_chunk_sums = [&]() {
+        if (n <= a.cum_sequential_max) return;
+        for (int c = blk; c < n_chunks; c += nblk) {
+            const int lo = c * chunk_c, hi = min(n, lo + chunk_c);
+            double acc = 0.;
+            for (int i = lo + tid; i < hi; i += nthr) acc += fw(i);
+            const double t = block_sum_fixed(acc, sm_d);
+            if (tid == 0) chunk_sum[c] = t;
+        }
+    };
     // __final_insertion_sort of one leaf [i, segl[i]) by its first element's thread
     auto sort_leaf = [&](int i) {
         const int f = i, l = b.segl[i];
@@ -3033,6 +3049,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         }
         if (tid == 0 && sh_act[2]) b.active[2] = 1;
     }
+    // overlap mode: the chunk sums do not wait for the barrier — every chunk but the first is W only, and the first one (it holds the
+    // handed-over segment: hand_l <= 4096 < chunk) belongs to block 0, which has just finished it
+    const bool cum_early = leaves_by_block0 && delta + n_sort <= chunk_c;
+    if (cum_early) cum_chunk_sums();
     grid.sync();  // blocks that left the loop early wait here for block 0's local levels
     lap(4);
     fail = b.active[2] != 0 || a.force_fail != 0;
@@ -3047,8 +3067,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         grid.sync();
     }
     lap(5);
-    // ---- cumulative_time_steps (sorted weights: the general sort's output inside [delta, delta + n_sort), W everywhere else)
-    auto fw = [&](int i) { return (i >= delta && i < delta + n_sort) ? b.fin_wk[i] : ts_W; };
+    // ---- cumulative_time_steps, second half
     if (n <= a.cum_sequential_max) {
         if (gtid == 0) {
             double acc = fw(0);
@@ -3059,17 +3078,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         // Fixed tree, independent of the launch shape: chunks of kCumRounds * blockDim entries (CTA b takes chunks b, b + gridDim, ...),
         // chunk sums combined in chunk order, inside a chunk one round of blockDim entries after the other —
         // cum[i] = (carry + (wtot[0] + .. + wtot[w-1])) + inc, carry' = (carry + wbase of the last warp) + its total.
-        constexpr int kCumRounds = 16, kCumWarps = kEventThreads / 32;
-        const int chunk_c = kCumRounds * nthr, n_chunks = (n + chunk_c - 1) / chunk_c;
-        double *chunk_sum = a.part_d + 8192;  // behind the per-block partials: room for 8192 chunks (6.7e7 entries)
-        for (int c = blk; c < n_chunks; c += nblk) {
-            const int lo = c * chunk_c, hi = min(n, lo + chunk_c);
-            double acc = 0.;
-            for (int i = lo + tid; i < hi; i += nthr) acc += fw(i);
-            const double t = block_sum_fixed(acc, sm_d);
-            if (tid == 0) chunk_sum[c] = t;
+        if (!cum_early) {
+            cum_chunk_sums();
+            grid.sync();
         }
-        grid.sync();
         __shared__ double carry_d;
         __shared__ double s_wtot[kCumRounds][kCumWarps], s_wbase[kCumRounds][kCumWarps], s_carry[kCumRounds];
         const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
