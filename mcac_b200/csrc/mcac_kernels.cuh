@@ -2228,6 +2228,9 @@ __global__ void k_sort_finish(DevState d, SortBufs b) {
 // above; every scan is a chunk-contiguous two-phase scan (block b owns elements [b*chunk, (b+1)*chunk)).
 // ------------------------------------------------------------------------------------------------
 constexpr int kEventThreads = 512;
+// layout of the scratch arrays: part_ll (4096 entries) = [0, gridDim) per-block counts / chunk sums of the level scans, [kPartSparseCounts, +gridDim)
+// sparse elements staged per block; part_d (16384) = five per-block partials of gridDim entries each, [kPartCumChunks, +8192) chunk sums of the cumulative table
+constexpr int kPartSparseCounts = 2048, kPartCumChunks = 8192;
 struct EventArgs {
     SortBufs sb;
     long long *part_ll;   // >= gridDim + 1
@@ -2479,7 +2482,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 if (tid == 0) { sh_carry += tot & 0xffff; sh_exc += tot >> 16; }
                 __syncthreads();
             }
-            if (tid == 0) a.part_ll[2048 + blk] = sh_exc;
+            if (tid == 0) a.part_ll[kPartSparseCounts + blk] = sh_exc;
         }
         if (gtid == 0) {
             if (a.do_refresh) {
@@ -2513,7 +2516,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     bool ts_on = false, ts_ovl = false;
     if (ts_try) {
         long long x = 0;
-        for (int bb = tid; bb < nblk; bb += nthr) x += a.part_ll[2048 + bb];
+        for (int bb = tid; bb < nblk; bb += nthr) x += a.part_ll[kPartSparseCounts + bb];
         x = block_sum_ll(x, sm_ll);
         // shared memory of the simulating CTA: four lists of x entries, one bucket table, and behind them an archive of the
         // per-level tables (as many levels as fit) for the walk back from the handed-over segment
@@ -2535,7 +2538,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 __shared__ int ts_ws[32];
                 for (int b0 = 0; b0 < nblk; b0 += nthr) {  // exclusive scan of the per-chunk counts (one round: nblk <= blockDim)
                     const int bb = b0 + tid;
-                    const int c = bb < nblk ? (int)a.part_ll[2048 + bb] : 0;
+                    const int c = bb < nblk ? (int)a.part_ll[kPartSparseCounts + bb] : 0;
                     int tot;
                     const int pre = block_exclusive_scan(c, &tot, ts_ws);
                     const int carry = b0 == 0 ? 0 : s_base[b0];
@@ -3000,7 +3003,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     auto fw = [&](int i) { return (i >= delta && i < delta + n_sort) ? b.fin_wk[i] : ts_W; };
     constexpr int kCumRounds = 16, kCumWarps = kEventThreads / 32;
     const int chunk_c = kCumRounds * nthr, n_chunks = (n + chunk_c - 1) / chunk_c;
-    double *chunk_sum = a.part_d + 8192;  // behind the per-block partials: room for 8192 chunks (6.7e7 entries)
+    double *chunk_sum = a.part_d + kPartCumChunks;  // behind the per-block partials: room for 8192 chunks (6.7e7 entries)
     auto cum_chunk_sums = [&]() {
         if (n <= a.cum_sequential_max) return;
         for (int c = blk; c < n_chunks; c += nblk) {
