@@ -109,7 +109,7 @@ def cpu_model() -> str:
 def classic_texts(indices: list[int], table_path: str) -> list[str]:
     import mcac_b200
     from mcac_b200 import ensemble as ens
-    from oracle.run_ref import merged_config  # config dict literals only
+    from mcac_b200.configs import merged_config
 
     return [mcac_b200.ini_text(merged_config("classic", {"numerics": {"random_seed": s}, "inter_potential": {"interpotential_file": table_path}}))
             for s in ens.seeds(1000, indices)]
@@ -319,7 +319,7 @@ def main():
     import torch
 
     import mcac_b200
-    from oracle.run_ref import merged_config  # config dict literals only (no oracle code is executed on this arm)
+    from mcac_b200.configs import merged_config
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mcac_b200 has no CPU fallback")

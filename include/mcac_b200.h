@@ -25,7 +25,7 @@ typedef struct mcac_gpu mcac_gpu; /* opaque */
 
 enum { MCAC_PICK_RANDOM = 0, MCAC_PICK_LAST = 1 };                          /* constants.hpp:91-96  */
 enum { MCAC_VS_CAPS = 0, MCAC_VS_SBL = 1, MCAC_VS_ARVO = 2, MCAC_VS_ALPHAS = 3, MCAC_VS_NONE = 4 }; /* :103-110 */
-enum { MCAC_ORDER_LIBSTDCXX = 0, MCAC_ORDER_STABLE = 1, MCAC_ORDER_HOST_STDSORT = 2 /* debugging aid: libstdc++ std::sort on the host */ };
+enum { MCAC_ORDER_LIBSTDCXX = 0, MCAC_ORDER_STABLE = 1 };
 
 /* Physics + numerics of one realization: the PhysicalModel fields the hot path reads
  * (include/physical_model/physical_model.hpp:31-77), already derived by the host-side reader. */
@@ -95,6 +95,10 @@ typedef struct mcac_run_report {
     int64_t tie_sorts, tie_levels, tie_sparse, tie_handed;
     /* SM cycles inside the sparse simulation: gathering the staged sparse elements, the simulated levels, hand-over + grid barrier */
     int64_t tie_sim_cycles[3];
+    /* pick-table sorts of this call that the one-launch event kernel handed back to the multi-launch device path (introsort's depth
+     * limit, or the MCAC_B200_FORCE_SORT_FAIL test hook), and sorts that replayed libstdc++'s heap-sort branch.  Every sort runs on
+     * the device either way: there is no host sort in the product. */
+    int64_t sort_fallbacks, sort_heap_branches;
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction
@@ -207,6 +211,8 @@ int mcac_host_model_params(const mcac_host_model *m, mcac_params *out);
 int mcac_host_model_sizes(const mcac_host_model *m, int64_t *n_sph, int64_t *n_agg);
 int mcac_host_model_metadata(const mcac_host_model *m, char *buf, int64_t cap); /* PhysicalModel::xmf_write, io/physical_model.cpp:30-49 */
 int mcac_host_model_derived(const mcac_host_model *m, double out[12]);
+/* the echo of the parsed .ini the reference writes to <output_dir>/params.ini (inipp::Ini::generate, physical_model.cpp:271-272) */
+int mcac_host_model_ini_echo(const mcac_host_model *m, char *buf, int64_t cap);
 int mcac_host_model_state(const mcac_host_model *m, double *sphere_fields, double *agg_fields, int64_t *agg_cells, int64_t *offsets,
                           int64_t *members, double *per_member, double *scalars /*maxradius,max_time_step,avg_npp*/,
                           int64_t *rand_consumed);

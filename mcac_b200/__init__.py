@@ -52,6 +52,13 @@ class HostModel:
         self.L.mcac_host_model_metadata(self.h, buf, 4096)
         return dict(line.split("=", 1) for line in buf.value.decode().splitlines())
 
+    def ini_echo(self) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        rc = self.L.mcac_host_model_ini_echo(self.h, buf, 1 << 16)
+        if rc:
+            raise McacError(rc, "ini echo does not fit")
+        return buf.value.decode()
+
     def derived(self) -> dict:
         a = np.zeros(12)
         self.L.mcac_host_model_derived(self.h, ptr(a))

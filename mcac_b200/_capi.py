@@ -67,7 +67,8 @@ class RunReport(C.Structure):
                [(n, C.c_double) for n in ["total_volume", "total_surface"]] + \
                [("tie_phase_cycles", C.c_int64 * 2)] + \
                [(n, C.c_int64) for n in ["tie_sorts", "tie_levels", "tie_sparse", "tie_handed"]] + \
-               [("tie_sim_cycles", C.c_int64 * 3)]
+               [("tie_sim_cycles", C.c_int64 * 3)] + \
+               [(n, C.c_int64) for n in ["sort_fallbacks", "sort_heap_branches"]]
 
     def as_dict(self) -> dict:
         return {n: (list(getattr(self, n)) if n.endswith("_cycles") else getattr(self, n)) for n, _ in self._fields_}
@@ -96,7 +97,7 @@ EXPORTS = [
     "mcac_gpu_morphology_stats", "mcac_gpu_morphology_stats_device", "mcac_gpu_stream", "mcac_gpu_search_sweep",
     "mcac_gpu_set_profile", "mcac_gpu_set_interpotential", "mcac_host_alloc_pinned", "mcac_host_free_pinned", "mcac_gpu_kernel_bench", "mcac_ensemble_run", "mcac_gpu_set_stop_at_event",
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
-    "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_state", "mcac_sim_create",
+    "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_ini_echo", "mcac_host_model_state", "mcac_sim_create",
 ]
 
 
@@ -149,6 +150,7 @@ def lib() -> C.CDLL:
         L.mcac_host_model_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
         L.mcac_host_model_metadata.argtypes = [vp, C.c_char_p, i64]
         L.mcac_host_model_derived.argtypes = [vp, vp]
+        L.mcac_host_model_ini_echo.argtypes = [vp, C.c_char_p, C.c_int64]
         L.mcac_host_model_state.argtypes = [vp] + [vp] * 8
         L.mcac_sim_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
         _lib = L

@@ -23,6 +23,7 @@ using namespace mcacb;
 
 namespace {
 constexpr int kRngBuf = 31 * 33826;  // ~1.05 M draws, multiple of 31
+constexpr int kStatsMaxBlocks = 1024, kStatsHistCap = 4096;
 enum { E_OK = 0, E_UNKNOWN = 1, E_IO = 2, E_VERLET = 3, E_INPUT = 4, E_MERGE = 9 };
 
 struct Buf {  // raw device allocation
@@ -73,7 +74,8 @@ struct mcac_gpu {
     long long *q_label = nullptr;
     SearchResult *q_res = nullptr;
     int *scan_tmp = nullptr, *scan_out = nullptr, *block_sums = nullptr, *sorted_label = nullptr, *merged_flag = nullptr;
-    double *partials = nullptr, *stats_dev = nullptr;
+    double *partials = nullptr, *stats_dev = nullptr, *stats_part = nullptr;  // K11: output row, per-CTA partial sums
+    unsigned int *stats_hist = nullptr;                                       // K11: integer histogram counts + ticket
     mcac_step_record *rec_dev = nullptr;
     long long rec_cap = 0;
     long long rng_generated = 0;  // stream position after the last generated draw
@@ -88,7 +90,9 @@ struct mcac_gpu {
     long long *scan64_sums = nullptr;
     double *cum_sums = nullptr;
     int *h_flags = nullptr;  // pinned: sort `active` flags
-    long long sort_levels = 0, sort_fallbacks = 0;
+    long long sort_levels = 0, sort_fallbacks = 0, sort_heap_levels = 0;
+    long long sort_fallbacks_seen = 0, sort_heap_seen = 0;
+    int sort_depth_override = -1;  // MCAC_B200_SORT_DEPTH (test hook): introsort depth limit, to reach the heap-sort branch
     int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
     int coop_bps = 1, sort_local_span = 4096;
     int event_spare_sms = 24; // MCAC_B200_EVENT_SPARE_SMS (sweep in profiles/r1_tuning.md)
@@ -176,6 +180,8 @@ int alloc_persistent(mcac_gpu *h) {
     TRY(dev_alloc_persistent(h, &h->partials, 3 * 1024));
     TRY(dev_alloc_persistent(h, &h->merged_flag, 4));
     TRY(dev_alloc_persistent(h, &h->stats_dev, 4096));
+    TRY(dev_alloc_persistent(h, &h->stats_part, 8 * (size_t)kStatsMaxBlocks));
+    TRY(dev_alloc_persistent(h, &h->stats_hist, (size_t)kStatsHistCap));
     h->alt.sc = d.sc;
     return E_OK;
 }
@@ -256,6 +262,24 @@ int dbg_sync(mcac_gpu *h, const char *tag) {
              ", n_agg " + std::to_string(h->sc_host.n_agg) + ", n_sph " + std::to_string(h->sc_host.n_sph) + ")";
     return E_UNKNOWN;
 }
+// device-side error -> message + ErrorCodes value (Scalars::error is already one of the reference's ErrorCodes)
+int device_error(mcac_gpu *h, const Scalars &s, const char *where) {
+    const char *what = "";
+    switch (s.error_detail) {
+    case DETAIL_SUSPECT_OVERFLOW: what = ": a contact search found more eligible suspects than its list holds (the first contact is not known)"; break;
+    case DETAIL_NOT_ON_VERLET: what = ": Aggregate not on the verlet list ???"; break;
+    case DETAIL_RNG_NOT_STAGED: what = ": random draws of the step were not staged"; break;
+    case DETAIL_PICK_TABLE: what = ": corrupt pick table"; break;
+    case DETAIL_SPHERE_REMOVAL: what = ": a sphere shrank below rp_min_oxid (sphere removal / split are not built)"; break;
+    case DETAIL_POOL_FULL: what = ": sphere pool / aggregate table full"; break;
+    default: break;
+    }
+    static const char *names[] = {"NO_ERROR", "UNKNOWN_ERROR", "IO_ERROR", "VERLET_ERROR", "INPUT_ERROR", "ABANDON_ERROR", "TOO_DENSE_ERROR",
+                                  "SBL_ERROR", "VOL_SURF_ERROR", "MERGE_ERROR", "ARVO_ERROR", "INTERPOTENTIAL_ERROR"};
+    const int code = (s.error >= 1 && s.error <= 11) ? s.error : E_UNKNOWN;
+    h->err = std::string(where) + ": device-side " + names[code] + what + " (step " + std::to_string(s.steps_done) + ")";
+    return code;
+}
 int pull_scalars(mcac_gpu *h) {
     CK(cudaMemcpyAsync(h->h_sc, h->d.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -320,40 +344,10 @@ int refresh_reduce(mcac_gpu *h) {
     return E_OK;
 }
 
-// AggregatList::sort_time_steps (aggregat_list.cpp:124-141).  The 1/dt weights are computed on the device in label
-// order.  MCAC_ORDER_LIBSTDCXX reproduces the reference's std::sort (introsort) order among EQUAL weights, which
-// decides the pick in monodisperse runs: the index sort is done by libstdc++'s std::sort itself on the
-// host (the very routine the reference calls; it runs only on events), together with the sequential prefix sum.
-int sort_time_steps_host(mcac_gpu *h) {
-    DevState &d = h->d;
-    const int n = h->sc_host.n_agg;
-    std::vector<double> keys((size_t)n), cum((size_t)n);
-    CK(cudaMemcpyAsync(keys.data(), d.keys, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    std::vector<int> idx((size_t)n);
-    std::iota(idx.begin(), idx.end(), 0);
-    if (h->prm.sort_order != MCAC_ORDER_STABLE) {
-        std::vector<size_t> idx64((size_t)n);
-        std::iota(idx64.begin(), idx64.end(), 0);
-        std::sort(idx64.begin(), idx64.end(), [&keys](size_t a, size_t b) { return keys[a] < keys[b]; });
-        for (int i = 0; i < n; i++) idx[(size_t)i] = (int)idx64[(size_t)i];
-    } else {
-        std::stable_sort(idx.begin(), idx.end(), [&keys](int a, int b) { return keys[(size_t)a] < keys[(size_t)b]; });
-    }
-    cum[0] = keys[(size_t)idx[0]];
-    for (int i = 1; i < n; i++) cum[(size_t)i] = cum[(size_t)i - 1] + keys[(size_t)idx[(size_t)i]];
-    CK(cudaMemcpyAsync(h->sorted_label, idx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d.cum, cum.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-    k_sorted_labels_to_slots<<<div_up(n, 256), 256, 0, h->stream>>>(d, h->sorted_label, n);
-    h->launches++;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
-    h->sc_host.n_pick = n;
-    h->sc_host.cum_total = cum[(size_t)n - 1];
-    h->pick_valid = true;
-    return E_OK;
-}
-
+// AggregatList::sort_time_steps (aggregat_list.cpp:124-141), multi-launch form.  The 1/dt weights are computed on the device in
+// label order; MCAC_ORDER_LIBSTDCXX reproduces the reference's std::sort (introsort) order among EQUAL weights, which decides the
+// pick in monodisperse runs — partition levels, the heap-sort branch behind introsort's depth limit and the final
+// insertion sort are all replayed on the device (there is no host sort anywhere in the product).
 // Device form: weights (K9 keys) -> replayed introsort (see mcac_kernels.cuh) -> cumulative table -> slots.
 int sort_time_steps(mcac_gpu *h, double factor) {
     DevState &d = h->d;
@@ -362,7 +356,6 @@ int sort_time_steps(mcac_gpu *h, double factor) {
     const int nb = div_up(n, 256);
     k_make_keys<<<nb, 256, 0, h->stream>>>(d, factor);
     h->launches++;
-    if (h->prm.sort_order == 2) return sort_time_steps_host(h);  // MCAC_ORDER_HOST_STDSORT: debugging aid
     SortBufs sb = h->sortb;
     sb.n = n;
     sb.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
@@ -370,8 +363,9 @@ int sort_time_steps(mcac_gpu *h, double factor) {
     h->launches++;
     int lg = 0;
     while ((1LL << (lg + 1)) <= n) lg++;
-    int depth = 2 * lg;  // std::__lg(n) * 2
+    int depth = h->sort_depth_override >= 0 ? h->sort_depth_override : 2 * lg;  // std::__lg(n) * 2
     bool active = n > kSortLeaf, fail = false;
+    if (active && depth == 0) { fail = true; active = false; }  // (test hook) the very first segment already takes the heap-sort branch
     const int per = kScanBlock * kScanItems, snb = std::max(1, div_up(n + 1, per));
     while (active && !fail) {
         depth--;
@@ -393,9 +387,10 @@ int sort_time_steps(mcac_gpu *h, double factor) {
         h->sort_levels++;
     }
     CK(cudaGetLastError());
-    if (fail) {  // introsort's depth limit was hit (heap-sort branch): take libstdc++'s own std::sort for this (rare) call
-        h->sort_fallbacks++;
-        return sort_time_steps_host(h);
+    if (fail) {  // introsort's depth limit was hit: the segments still longer than 16 take the heap-sort branch
+        k_sort_heap<<<nb, 256, 0, h->stream>>>(sb);
+        h->launches++;
+        h->sort_heap_levels++;
     }
     k_sort_leaves<<<nb, 256, 0, h->stream>>>(sb);
     h->launches++;
@@ -419,11 +414,11 @@ int sort_time_steps(mcac_gpu *h, double factor) {
 }
 
 // The per-event pipeline as ONE cooperative launch (k_event): labels, refresh / PhysicalModel::update, weights, replayed
-// introsort, cumulative table.  Falls back to the multi-launch form when cooperative launch is unavailable or when
-// introsort's depth limit is hit.
+// introsort, cumulative table.  The multi-launch device form takes over when cooperative launch is unavailable or when
+// introsort's depth limit is hit (it replays the heap-sort branch).
 int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, const double *factor = nullptr, bool defer_sync = false,
                    bool skip_if_no_event = false) {
-    if (h->coop_blocks <= 0 || h->prm.sort_order == MCAC_ORDER_HOST_STDSORT) {
+    if (h->coop_blocks <= 0) {
         if (do_refresh || do_totals) { h->labels_valid = false; TRY(refresh_labels(h)); TRY(refresh_reduce(h)); TRY(pull_scalars(h)); }
         if (do_sort) TRY(sort_time_steps(h, factor ? *factor : h->sc_host.max_time_step));
         return E_OK;
@@ -453,6 +448,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.ts_min_n = h->ts_min_n;
     a.skip_if_no_event = skip_if_no_event ? 1 : 0;
     a.ts_no_overlap = h->ts_no_overlap ? 1 : 0;
+    a.depth_override = h->sort_depth_override;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
     void *args[] = {&dcopy, &a};
@@ -474,7 +470,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     }
     TRY(pull_scalars(h));
     if (do_sort) {
-        if (h->sc_host.b_need == 99) {  // introsort's depth limit was hit: multi-launch path, which ends in libstdc++'s std::sort
+        if (h->sc_host.b_need == 99) {  // introsort's depth limit was hit: multi-launch path, which replays the heap-sort branch
             h->sc_host.b_need = 0;
             TRY(push_scalars(h));
             h->sort_fallbacks++;
@@ -671,6 +667,8 @@ void fill_devstate_params(mcac_gpu *h) {
     d.nucl_dispersion_diameter = p.dispersion_diameter_nucleation;
     d.flux_nucleation = p.flux_nucleation;
     d.init_mode_normal = p.normal_initialisation;
+    d.cand_cap = kCandCap;
+    if (const char *e = getenv("MCAC_B200_CAND_CAP")) d.cand_cap = std::max(1, std::min(kCandCap, atoi(e)));
 }
 
 // carve the staging buffer into the host-layout arrays (256-byte aligned); returns the bytes needed
@@ -972,6 +970,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_NUCL_HEADROOM")) h->nucl_headroom = std::max(80, atoi(e));
         if (const char *e = getenv("MCAC_B200_BIG_NPP")) h->big_search_npp = atof(e);
         if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
+        if (const char *e = getenv("MCAC_B200_SORT_DEPTH")) h->sort_depth_override = std::max(0, atoi(e));
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
@@ -1219,7 +1218,7 @@ int mcac_gpu_merge(mcac_gpu *h, const mcac_contact *c, int *merged) {
     if (merged) *merged = m;
     if (m) { h->labels_valid = false; h->cells_valid = false; h->pick_valid = false; }
     TRY(pull_scalars(h));
-    if (h->sc_host.error) { h->err = "device error during merge"; return h->sc_host.error; }
+    if (h->sc_host.error) return device_error(h, h->sc_host, "mcac_gpu_merge");
     return E_OK;
 }
 
@@ -1228,6 +1227,7 @@ int mcac_gpu_grow(mcac_gpu *h, double dt, int64_t label) {
     TRY(pull_scalars(h));
     TRY(refresh_labels(h));
     int slot = -1, n = h->sc_host.pool_top;
+    if (label >= h->sc_host.n_agg) { h->err = "grow: bad label"; return E_INPUT; }
     if (label >= 0) {
         CK(cudaMemcpyAsync(&slot, h->d.slot_of_label + label, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1245,6 +1245,7 @@ int mcac_gpu_update(mcac_gpu *h, int64_t label, int full) {
     TRY(pull_scalars(h));
     TRY(refresh_labels(h));
     int slot = -1;
+    if (label >= h->sc_host.n_agg) { h->err = "update: bad label"; return E_INPUT; }
     if (label >= 0) {
         CK(cudaMemcpyAsync(&slot, h->d.slot_of_label + label, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1257,7 +1258,7 @@ int mcac_gpu_update(mcac_gpu *h, int64_t label, int full) {
     CK(cudaStreamSynchronize(h->stream));
     h->cells_valid = false;
     TRY(pull_scalars(h));
-    if (h->sc_host.error) { h->err = "device error during update (VolSurfError)"; return h->sc_host.error; }
+    if (h->sc_host.error) return device_error(h, h->sc_host, "mcac_gpu_update");
     return E_OK;
 }
 
@@ -1298,6 +1299,7 @@ int mcac_gpu_pick_random(mcac_gpu *h, double u, int64_t *label, double *deltatem
     TRY(pull_scalars(h));
     if (!h->pick_valid) { h->err = "pick_random before sort_time_steps"; return E_INPUT; }
     const int n = h->sc_host.n_pick;
+    if (n < 1) { h->err = "pick_random: empty pick table"; return E_INPUT; }
     std::vector<double> cum((size_t)n);
     std::vector<int> lab((size_t)n);
     CK(cudaMemcpyAsync(cum.data(), h->d.cum, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -1441,7 +1443,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                 if ((rc = search_launch(h, 1)) != E_OK) break;
             }
             if (rc != E_OK) break;
-            if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
+            if (h->sc_host.error) { rc = device_error(h, h->sc_host, "mcac_gpu_run"); break; }
         }
         StepArgs sa;
         sa.q_slot = h->q_slot; sa.q_dir = h->q_dir; sa.q_dist = h->q_dist; sa.res = h->q_res;
@@ -1485,7 +1487,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if ((rc = pull_scalars(h)) != E_OK) break;
         batches++;
         h->cells_valid = false;
-        if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
+        if (h->sc_host.error) { rc = device_error(h, h->sc_host, "mcac_gpu_run"); break; }
         steps += 1;
         if (h->sc_host.b_merged) { h->pick_valid = false; h->labels_valid = false; }
         if (h->sc_host.n_nucleated > 0) h->pick_valid = false;
@@ -1497,7 +1499,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     // between batches.  The kernels themselves enforce what the host would have checked first (step limit, finished(), room in
     // the pool); anything unusual drains the pipeline and is handled by the one-batch-at-a-time iteration below.
     const long long steps_limit_abs = at_start.steps_done + max_steps;
-    const bool pipe_mode = speculative && h->pipeline && h->overlap && h->coop_blocks > 0 && h->prm.sort_order != MCAC_ORDER_HOST_STDSORT &&
+    const bool pipe_mode = speculative && h->pipeline && h->overlap && h->coop_blocks > 0 &&
                            !(records && n_records > 0) && !h->stop_at_event && !h->prm.with_domain_duplication && !h->debug_sync;
     while (speculative && steps < max_steps) {
         if (finished(h)) { fin = true; break; }
@@ -1573,7 +1575,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                 h->sc_host = s;
                 if (s.b_need == 99) { anomaly = true; need_fallback_sort = true; return E_OK; }
                 batches++;
-                if (s.error) { h->err = "device-side error code " + std::to_string(s.error); return s.error; }
+                if (s.error) return device_error(h, s, "mcac_gpu_run");
                 steps += s.b_committed;
                 if (s.b_merged) h->sc_host.avg_npp = static_cast<double>(s.n_sph) / static_cast<double>(s.n_agg);
                 if (s.b_stop_reason == STOP_FINISHED) { fin = true; anomaly = true; }
@@ -1662,7 +1664,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         if (cudaGetLastError() != cudaSuccess) { h->err = "k_commit launch failed"; rc = E_UNKNOWN; break; }
         if ((rc = pull_scalars(h)) != E_OK) break;
         if (h->sc_host.b_need == 99) {  // the (unsynchronised) event kernel hit introsort's depth limit: k_commit did nothing;
-            h->sc_host.b_need = 0;      // redo the sort on the multi-launch path (ends in libstdc++'s std::sort), then the batch
+            h->sc_host.b_need = 0;      // redo the sort on the multi-launch path (it replays the heap-sort branch), then the batch
             if ((rc = push_scalars(h)) != E_OK) break;
             h->sort_fallbacks++;
             if ((rc = sort_time_steps(h, h->sc_host.max_time_step)) != E_OK) break;
@@ -1673,7 +1675,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         fallback_sorted = false;
         batches++;
         h->cells_valid = false;
-        if (h->sc_host.error) { h->err = "device-side error code " + std::to_string(h->sc_host.error); rc = h->sc_host.error; break; }
+        if (h->sc_host.error) { rc = device_error(h, h->sc_host, "mcac_gpu_run"); break; }
         steps += h->sc_host.b_committed;
         if (h->sc_host.b_merged) {  // refresh() + PhysicalModel::update + re-sort happen in the event pipeline at the loop top
             h->pick_valid = false;
@@ -1745,6 +1747,10 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             report->tie_phase_cycles[0] += report->tie_sim_cycles[k];
         }
         for (int k = 0; k < 32; k++) h->event_work_seen[k] = w[k];
+        report->sort_fallbacks = h->sort_fallbacks - h->sort_fallbacks_seen;
+        report->sort_heap_branches = h->sort_heap_levels - h->sort_heap_seen;
+        h->sort_fallbacks_seen = h->sort_fallbacks;
+        h->sort_heap_seen = h->sort_heap_levels;
     }
     prof_collect(h, report);
     return E_OK;
@@ -1756,10 +1762,11 @@ int mcac_gpu_set_stop_at_event(mcac_gpu *h, int32_t on) { h->stop_at_event = on 
 int mcac_gpu_morphology_stats_device(mcac_gpu *h, int32_t n_bins, double rg_max, void *device_out) {
     CK(cudaSetDevice(h->device));
     if (n_bins < 1 || !device_out) { h->err = "morphology_stats: bad arguments"; return E_INPUT; }
+    if (2 * (size_t)n_bins + 1 > kStatsHistCap) { h->err = "morphology_stats: too many bins"; return E_INPUT; }
     TRY(pull_scalars(h));
-    CK(cudaMemsetAsync(device_out, 0, sizeof(double) * (2 * (size_t)n_bins + 8), h->stream));
-    const int nb = std::min(1024, std::max(1, div_up(h->sc_host.n_agg_slots, 256)));
-    k_morphology_stats<<<nb, 256, 0, h->stream>>>(h->d, n_bins, rg_max, (double *)device_out);
+    CK(cudaMemsetAsync(h->stats_hist, 0, sizeof(unsigned int) * (2 * (size_t)n_bins + 1), h->stream));
+    const int nb = std::min(kStatsMaxBlocks, std::max(1, div_up(h->sc_host.n_agg_slots, 256)));
+    k_morphology_stats<<<nb, 256, 0, h->stream>>>(h->d, n_bins, rg_max, (double *)device_out, h->stats_part, h->stats_hist);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -1866,7 +1873,11 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_o
             units = kRngBuf;
             break;
         }
-        case 8: k_morphology_stats<<<std::min(1024, std::max(1, div_up(sc.n_agg_slots, 256))), 256, 0, h->stream>>>(h->d, 24, 2e-6, h->stats_dev); units = sc.n_agg; break;
+        case 8:
+            cudaMemsetAsync(h->stats_hist, 0, sizeof(unsigned int) * (2 * 24 + 1), h->stream);
+            k_morphology_stats<<<std::min(kStatsMaxBlocks, std::max(1, div_up(sc.n_agg_slots, 256))), 256, 0, h->stream>>>(h->d, 24, 2e-6, h->stats_dev, h->stats_part, h->stats_hist);
+            units = sc.n_agg;
+            break;
         default: h->err = "kernel_bench: unknown kernel"; rc = E_INPUT;
         }
     }

@@ -35,13 +35,17 @@ struct Scalars {
     int p_contact, p_ms, p_os, p_magg, p_oagg, p_slot;
     double p_dt, p_dt_indiv;
     int p_regime, p_regime_draws;  // check_InterPotentialRegime outcome of the last try (0 sticking) and draws it consumed
-    int n_nucleated, pad_n;
+    int n_nucleated;
+    int error_detail;  // what `error` means when the ErrorCodes value alone does not say (ErrorDetail)
     // pick table of a tie-dominated run: cumulative_time_steps is affine (slope pick_w) from index pick_dense_from on, up to
     // rounding — a hint for the lower_bound of pick_random (pick_dense_from == n_pick: no such stretch)
     double pick_w;
     int pick_dense_from;
     int last_sort_tie;  // 1: the last pick table was made by the sparse path of the event kernel (it is short: see event_spare_sms)
 };
+// finer cause of a device-side error (Scalars::error_detail); the host turns it into the message of mcac_gpu_last_error
+enum ErrorDetail { DETAIL_NONE = 0, DETAIL_SUSPECT_OVERFLOW = 12, DETAIL_NOT_ON_VERLET = 13, DETAIL_RNG_NOT_STAGED = 21, DETAIL_PICK_TABLE = 22,
+                   DETAIL_SPHERE_REMOVAL = 31, DETAIL_POOL_FULL = 32 };
 enum StopReason { STOP_NONE = 0, STOP_CONTACT = 1, STOP_CONFLICT = 2, STOP_FINISHED = 3, STOP_BATCH_END = 4, STOP_POOL = 5 /* no room for the merged block: host compacts */ };
 
 struct SearchResult {
@@ -93,7 +97,8 @@ struct DevState {
     const double *ip_dp1, *ip_dp2, *ip_ebar, *ip_ewell;
     // nucleation (physical_model.cpp:499-502, 557-578): diameter law of new monomers
     double nucl_mean_diameter, nucl_dispersion_diameter, flux_nucleation;
-    int init_mode_normal, pad_i;
+    int init_mode_normal;
+    int cand_cap;  // eligible suspects a wide search keeps (<= kCandCap; MCAC_B200_CAND_CAP shrinks it to test the overflow error)
 };
 
 }  // namespace mcacb

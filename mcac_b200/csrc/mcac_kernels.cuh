@@ -9,6 +9,7 @@
 #include "../../include/mcac_b200.h"
 #include "mcac_device.cuh"
 #include "tie_sort.cuh"
+#include "heap_sort.cuh"
 
 namespace mcacb {
 
@@ -93,7 +94,7 @@ __global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir
     Scalars &sc = *d.sc;
     const long long p = sc.rand_pos + 3LL * j - d.rng_buf_base;
     if (p < 0 || p + 2 >= d.rng_buf_n) {  // the host did not stage these draws: refuse instead of reading outside the buffer
-        sc.error = 21;
+        sc.error = 1; sc.error_detail = DETAIL_RNG_NOT_STAGED;
         q_slot[j] = -1;
         q_dir[3 * j] = q_dir[3 * j + 1] = q_dir[3 * j + 2] = 0.;
         q_dist[j] = 0.;
@@ -127,7 +128,7 @@ __global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir
     }
     int slot = d.sorted_slot[lo];
     if (n < 1 || lo >= n || slot < 0 || slot >= sc.n_agg_slots) {  // corrupt pick table
-        sc.error = 22;
+        sc.error = 1; sc.error_detail = DETAIL_PICK_TABLE;
         slot = -1;
     }
     const Vec3 dir = direction_from_draws(u_theta, u_phi);
@@ -250,7 +251,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
             atomicAdd(&s_nb, 1);
             if (db < dist) {
                 const int pos = atomicAdd(&s_count, 1);
-                if (pos < kCandCap) {
+                if (pos < d.cand_cap) {
                     const int r0 = range_rank(d.a_cx[o], rg.lo[0], rg.hi[0], n_div);
                     const int r1 = range_rank(d.a_cy[o], rg.lo[1], rg.hi[1], n_div);
                     const int r2 = range_rank(d.a_cz[o], rg.lo[2], rg.hi[2], n_div);
@@ -269,8 +270,8 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
         __syncthreads();
     }
     const int m_all = s_count;
-    const int m = m_all < kCandCap ? m_all : kCandCap;
-    if (m_all > kCandCap) res.status = 1;  // more eligible suspects than the shared-memory list holds
+    const int m = m_all < d.cand_cap ? m_all : d.cand_cap;
+    if (m_all > d.cand_cap) res.status = 1;  // more eligible suspects than the shared-memory list holds: the first contact is unknown
 
     const int n_src = d.a_n[slot], off_src = d.a_off[slot];
     if (kPhase == 1) {  // hand the suspects and the tile partition of their sphere pairs to the grid-wide sweep
@@ -1086,7 +1087,7 @@ __device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int 
     const int dst = d.sc->pool_top;
     __syncthreads();  // everybody has read pool_top / the contact spheres before anything is rewritten
     if (dst + n_k + n_r > d.sph_cap) {
-        if (tid == 0) d.sc->error = 1;
+        if (tid == 0) { d.sc->error = 1; d.sc->error_detail = DETAIL_POOL_FULL; }
         return 0;
     }
     for (int i = tid; i < n_k + n_r; i += nth) {
@@ -1162,7 +1163,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     __shared__ double sh_time[kMaxBatch + 1];
     __shared__ double scratch[kUpdateScratch];
     __shared__ double cap[8];  // contact step: dt, proper time, position right after the move
-    __shared__ int s_conf, s_contact, s_limit, s_finished;
+    __shared__ int s_conf, s_contact, s_limit, s_finished, s_bad;
     __shared__ double4 sh_posr[kMaxBatch];  // movers of the batch staged once: the O(B^2) conflict test then runs from shared memory
     __shared__ double sh_dist[kMaxBatch];
     __shared__ double sh_dir[3 * kMaxBatch];
@@ -1173,7 +1174,8 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     const int n_agg_before = sc.n_agg;
     const long long steps_before = sc.steps_done, rand_before = sc.rand_pos, iter_before = sc.n_iter_without_event;
     const double dt_base = sc.max_time_step / sc.cum_total;  // AggregatList::get_time_step(max), aggregat_list.cpp:54-58
-    if (sc.b_need == 99) {  // the pick table of this batch comes from a sort that gave up (host redoes it): commit nothing
+    if (sc.b_need == 99 || sc.error != 0) {  // the pick table of this batch comes from a sort that gave up (host redoes it), or an
+        // earlier kernel of the batch reported an error (its queries are not usable: q_slot may be -1): commit nothing
         if (tid == 0) { sc.b_committed = 0; sc.b_stop_reason = STOP_NONE; sc.b_contact = 0; sc.b_merged = 0; }
         return;
     }
@@ -1185,11 +1187,17 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         return;
     }
     const long long max_steps = b.steps_limit_abs > 0 ? min(b.max_steps, b.steps_limit_abs - steps_before) : b.max_steps;
-    if (tid == 0) { s_conf = nq; s_contact = nq; s_limit = nq; s_finished = 0; }
+    if (tid == 0) { s_conf = nq; s_contact = nq; s_limit = nq; s_finished = 0; s_bad = nq; }
+    __syncthreads();
     for (int j = tid; j < nq; j += nth) {
-        sh_slot[j] = b.q_slot[j];
+        const int qs = b.q_slot[j];
+        sh_slot[j] = qs;
+        // a search that did not complete (status 1: more eligible suspects than the list holds, 3: VerletError) or a query without
+        // an aggregate has no usable distance: the first such step bounds what this batch may commit
+        if (qs < 0 || b.res[j].status != 0) { atomicMin(&s_bad, j); sh_contact[j] = 0; sh_posr[j] = make_double4(0., 0., 0., 0.); sh_dist[j] = 0.;
+            sh_dir[3 * j] = sh_dir[3 * j + 1] = sh_dir[3 * j + 2] = 0.; continue; }
         sh_contact[j] = (b.res[j].distance <= b.q_dist[j]) ? 1 : 0;  // `next_contact <= full_distance`, calcul.cpp:128
-        sh_posr[j] = d.a_posr[b.q_slot[j]];
+        sh_posr[j] = d.a_posr[qs];
         sh_dist[j] = b.q_dist[j];
         sh_dir[3 * j] = b.q_dir[3 * j]; sh_dir[3 * j + 1] = b.q_dir[3 * j + 1]; sh_dir[3 * j + 2] = b.q_dir[3 * j + 2];
     }
@@ -1213,7 +1221,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     __syncthreads();
     // ---- conflicts with earlier movers of the batch: all (j, i<j) pairs up to the first contact (nothing behind it can be
     // committed by this batch), flattened over the block
-    const int nj = min(min(nq, s_limit), s_contact + 1);
+    const int nj = min(min(min(nq, s_limit), s_contact + 1), s_bad);
     for (int p = tid; p < nj * nj; p += nth) {
         const int j = p / nj, i = p - j * nj;
         if (i >= j || j >= s_conf) continue;  // benign race on s_conf: only ever shrinks the work
@@ -1241,6 +1249,20 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     __syncthreads();
     int stop = s_limit;
     int reason = s_finished ? STOP_FINISHED : STOP_BATCH_END;
+    if (s_bad < stop) {
+        // the reference would have thrown inside this step's distance_to_next_contact: report it instead of committing a
+        // distance that is not the first contact.  Steps before it are committed (they are what the reference did).
+        if (s_bad == 0) {
+            if (tid == 0) {
+                const bool overflow = sh_slot[0] >= 0 && b.res[0].status == 1;
+                sc.error = overflow ? 1 : 3;  // UNKNOWN_ERROR (suspect list overflow) / VerletError
+                sc.error_detail = overflow ? DETAIL_SUSPECT_OVERFLOW : DETAIL_NOT_ON_VERLET;
+                sc.b_committed = 0; sc.b_stop_reason = STOP_NONE; sc.b_contact = 0; sc.b_merged = 0;
+            }
+            return;
+        }
+        stop = s_bad; reason = STOP_BATCH_END;
+    }
     if (s_conf < stop) { stop = s_conf; reason = STOP_CONFLICT; }
     bool do_contact = s_contact < stop;  // the contact step is valid (no conflict before it) and allowed
     if (do_contact) { stop = s_contact; reason = STOP_CONTACT; }
@@ -1414,8 +1436,14 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepAr
     const int slot = a.q_slot[0];
     const double full = a.q_dist[0];
     SearchResult r;
-    r.distance = INFINITY; r.moving_slot = r.other_slot = r.other_agg = -1; r.n_bounding = 0; r.n_sphere_pairs = 0;
+    r.distance = INFINITY; r.moving_slot = r.other_slot = r.other_agg = -1; r.n_bounding = 0; r.n_sphere_pairs = 0; r.status = 0;
+    if (sc.error != 0) return;  // an earlier kernel of this step failed (the pick may be -1): nothing is moved
+    if (slot < 0) { if (tid == 0) { sc.error = 3; sc.error_detail = DETAIL_NOT_ON_VERLET; } return; }
     if (a.with_collisions) r = a.res[0];
+    if (r.status != 0) {  // incomplete search: there is no first contact to move to
+        if (tid == 0) { sc.error = r.status == 1 ? 1 : 3; sc.error_detail = r.status == 1 ? DETAIL_SUSPECT_OVERFLOW : DETAIL_NOT_ON_VERLET; }
+        return;
+    }
     const bool contact = a.with_collisions && r.distance <= full;
     const double move = contact ? r.distance : full;
     const double time_before = sc.time;
@@ -1467,6 +1495,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepAr
 // AggregatList::check_InterPotentialRegime (aggregat_list.cpp:313-366) for the contact found by the last search:
 // sticking / repulsion / bouncing decided with <= 2 draws taken at stream offset `draw_offset` of this step.
 __global__ void k_check_regime(DevState d, const SearchResult *res, const double *q_dist, long long draw_offset) {
+    if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Scalars &sc = *d.sc;
     sc.p_regime = 0;
@@ -1511,6 +1540,7 @@ __global__ void k_check_regime(DevState d, const SearchResult *res, const double
 // (bounding sphere first, then member spheres: aggregat_distance.cpp:45-58), becomes the last aggregate / last sphere and gets
 // Aggregate::update().  Single CTA; the free-space test of a try is spread over the threads.
 __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double deltatemps_unused, int use_pending_dt) {
+    if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[kUpdateScratch];
     __shared__ double cand[4];
     __shared__ int s_hit, s_stop, s_count;
@@ -1535,7 +1565,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double 
     for (int m = 0; m < n_new; m++) {
         if (tid == 0) {
             const long long p = sc.rand_pos - d.rng_buf_base;
-            if (p + 1 >= d.rng_buf_n) { sc.error = 1; s_stop = 1; }
+            if (p + 1 >= d.rng_buf_n) { sc.error = 1; sc.error_detail = DETAIL_RNG_NOT_STAGED; s_stop = 1; }
             else {
                 const double diameter = diameter_from_draw(uniform_from_rand(d.rng_buf[p]), d.nucl_mean_diameter, d.nucl_dispersion_diameter, d.init_mode_normal);
                 cand[3] = diameter * 0.5;
@@ -1549,7 +1579,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double 
         for (int attempt = 0; attempt < max_tries && !placed; attempt++) {
             if (tid == 0) {
                 const long long p = sc.rand_pos - d.rng_buf_base;
-                if (p + 3 >= d.rng_buf_n) { sc.error = 1; s_stop = 1; }
+                if (p + 3 >= d.rng_buf_n) { sc.error = 1; sc.error_detail = DETAIL_RNG_NOT_STAGED; s_stop = 1; }
                 else {
                     cand[0] = uniform_from_rand(d.rng_buf[p]) * box;
                     cand[1] = uniform_from_rand(d.rng_buf[p + 1]) * box;
@@ -1577,7 +1607,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double 
         }
         if (!placed) { if (tid == 0) sc.error = 6; return; }  // TooDenseError
         const int slot = sc.n_agg_slots, sp = sc.pool_top, id = sc.n_sph;
-        if (slot >= d.agg_cap || sp >= d.sph_cap || id >= d.sph_cap) { if (tid == 0) sc.error = 1; return; }
+        if (slot >= d.agg_cap || sp >= d.sph_cap || id >= d.sph_cap) { if (tid == 0) { sc.error = 1; sc.error_detail = DETAIL_POOL_FULL; } return; }
         if (tid == 0) {
             const double r = cand[3];
             d.s_posr[sp] = make_double4(cand[0], cand[1], cand[2], r);
@@ -1609,6 +1639,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double 
 
 // the deferred AggregatList::merge of the step (calcul.cpp:174-181) + event bookkeeping (:222-229)
 __global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
+    if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[kUpdateScratch];
     Scalars &sc = *d.sc;
     int merged = 0;
@@ -1624,6 +1655,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_
 __global__ void k_step_event(DevState d) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Scalars &sc = *d.sc;
+    if (sc.error != 0) return;
     const bool ev = sc.b_merged || sc.n_nucleated > 0;
     if (ev) { sc.n_iter_without_event = 0; sc.total_events += 1; sc.event = 1; }
     else { sc.n_iter_without_event += 1; sc.event = 0; }
@@ -1806,10 +1838,11 @@ __global__ void k_grow(DevState d, double dt, int only_slot) {
     rel.w = volume_factor() * r3;
     d.s_relv[t] = rel;
     d.s_surf[t] = surface_factor() * r2;
-    if (new_r <= d.rp_min_oxid) d.sc->error = 1;  // sphere removal by oxidation (u_sg < 0) is outside the built path
+    if (new_r <= d.rp_min_oxid) { d.sc->error = 1; d.sc->error_detail = DETAIL_SPHERE_REMOVAL; }  // sphere removal by oxidation (u_sg < 0) is outside the built path
 }
 // growth of the general step: dt and the picked aggregate are device scalars written by k_step_move
 __global__ void k_grow_pending(DevState d, int individual) {
+    if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const Scalars &sc = *d.sc;
     int lo = 0, hi = sc.pool_top;
@@ -1827,11 +1860,12 @@ __global__ void k_grow_pending(DevState d, int individual) {
     rel.w = volume_factor() * r3;
     d.s_relv[t] = rel;
     d.s_surf[t] = surface_factor() * r2;
-    if (new_r <= d.rp_min_oxid) d.sc->error = 1;
+    if (new_r <= d.rp_min_oxid) { d.sc->error = 1; d.sc->error_detail = DETAIL_SPHERE_REMOVAL; }
 }
 // update block of calcul.cpp:184-206 for the general step: mode 0 = every aggregate, mode 1 = individual reactions
 // (only the picked aggregate unless a merge happened, in which case every aggregate, as the reference does)
 __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int individual) {
+    if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[8][kUpdateScratch / 4];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 8 + w;
@@ -1844,6 +1878,7 @@ __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int i
 // individual surface reactions without a merge: only the picked aggregate is updated (calcul.cpp:196-203) — by a whole CTA, so
 // that a 10^3-sphere aggregate's O(n^2) contact pass is not left to one warp
 __global__ void __launch_bounds__(kCommitThreads) k_update_picked(DevState d, int full) {
+    if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[kUpdateScratch];
     const Scalars &sc = *d.sc;
     if (sc.b_merged) return;  // every aggregate is updated by k_update_small / k_update_step
@@ -1958,7 +1993,7 @@ __global__ void __launch_bounds__(256) k_dup_finish(DevState d, int n0, double o
 //     not > pivot, while they have not crossed", i.e. two prefix counts + one pairing pass — parallel per level;
 //   * __final_insertion_sort is a stable sort, and segments are already ordered relative to each other, so it
 //     equals a stable sort inside each leaf (<= 16 elements).
-// depth_limit exhaustion (heap-sort branch) is reported through `fail` and handled by the caller.
+// depth_limit exhaustion is reported through `fail`: the caller then runs k_sort_heap (libstdc++'s heap-sort branch).
 // `stable` != 0 orders ties by label instead (MCAC_ORDER_STABLE).
 // ------------------------------------------------------------------------------------------------
 struct SortBufs {
@@ -2091,6 +2126,18 @@ __global__ void k_sort_leaves(SortBufs b) {
         }
         b.wk[y + 1] = kv; b.perm[y + 1] = lv;
     }
+}
+// introsort's depth limit (std::__introsort_loop, bits/stl_algo.h: `if (__depth_limit == 0) { std::__partial_sort(first, last, last); return; }`):
+// every segment still longer than 16 when the limit is reached is heap-sorted — make_heap followed by sort_heap, restated here with
+// libstdc++'s __adjust_heap / __push_heap so that equal weights leave in the same order.  One thread per segment (the branch is a
+// safety net of introsort: it needs 2*log2(n) consecutive bad pivots); tests/native/heap_sort_host.cpp checks the same code against
+// std::partial_sort on the host.
+__global__ void k_sort_heap(SortBufs b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n || b.segf[i] != i) return;
+    const int l = b.segl[i];
+    if (l - i <= kSortLeaf) return;
+    heapsort::heap_sort_segment(heapsort::HeapView{b.wk, b.perm, b.stable}, i, l);
 }
 // 64-bit packed exclusive scan (same 3-phase structure as the int scan)
 __device__ __forceinline__ long long warp_inclusive_scan_ll(long long v, int lane) {
@@ -2244,6 +2291,7 @@ struct EventArgs {
     int local_span;       // span (elements) below which block 0 finishes the sort alone
     int smem_cap;         // entries of dynamic shared memory per array available to the block-local levels (0 = none)
     int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
+    int depth_override;   // test hook (MCAC_B200_SORT_DEPTH): introsort depth limit instead of 2*log2(n); < 0 = off
     long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
     // tie-dominated tables (tie_sort.cuh): top levels simulated on the sparse elements only
     tiesort::Plan *ts_plan;
@@ -2510,7 +2558,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     b.stable = a.stable;
     int lg = 0;
     while ((1LL << (lg + 1)) <= n) lg++;
-    int depth = 2 * lg;
+    int depth = a.depth_override >= 0 ? a.depth_override : 2 * lg;
     int n_sort = n, delta = 0;  // the general sort below works on [0, n_sort) and writes its result at +delta
     // ---- tie-dominated table: the top levels on the sparse elements only (tie_sort.cuh)
     bool ts_on = false, ts_ovl = false;
@@ -2581,7 +2629,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
                 reinterpret_cast<int *>(&sh_plan)[k] = reinterpret_cast<const int *>(a.ts_plan)[k];
             __syncthreads();
-            if (sh_plan.fail) {  // introsort's heap-sort branch: the host falls back to libstdc++'s std::sort for this call
+            if (sh_plan.fail) {  // introsort's heap-sort branch: the host redoes this sort on the multi-launch device path (k_sort_heap)
                 if (gtid == 0) sc.b_need = 99;
                 return;
             }
@@ -3059,7 +3107,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     grid.sync();  // blocks that left the loop early wait here for block 0's local levels
     lap(4);
     fail = b.active[2] != 0 || a.force_fail != 0;
-    if (fail) {  // the host falls back to libstdc++'s std::sort for this call
+    if (fail) {  // the host redoes this sort on the multi-launch device path, which replays the heap-sort branch (k_sort_heap)
         if (gtid == 0) sc.b_need = 99;
         return;
     }
@@ -3167,9 +3215,14 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
 // (aggregat_list_fractal_law.cpp:23-33 -> linreg, tools.cpp:126-157: x = dg_over_dp, y = Np).
 // out: [0,nb) Np histogram, [nb,2nb) Rg histogram, then n, sum_np, sumx, sumx2, sumxy, sumy, sumy2, sum_rg
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, double rg_max, double *out) {
+// Deterministic: every CTA reduces its (fixed) grid-stride share in a fixed tree and leaves 8 partial sums; the CTA that
+// finishes last (ticket counter) combines the partials in CTA order.  Histograms are integer counts (atomics on integers are
+// exact and order-independent).  No floating-point atomics: two launches on the same state give bit-identical rows.
+__global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, double rg_max, double *out, double *part /* gridDim x 8 */,
+                                                          unsigned int *ghist /* 2 * nb counts + 1 ticket, zeroed by the caller */) {
     __shared__ double red[8][8];
     __shared__ unsigned int hist[2 * 64];  // per-CTA histograms (nb <= 64 bins each): one global atomic per bin and CTA, not per aggregate
+    __shared__ int s_last;
     const int n = d.sc->n_agg_slots;
     const bool local_hist = nb <= 64;
     for (int b = threadIdx.x; b < 2 * 64; b += blockDim.x) hist[b] = 0u;
@@ -3187,8 +3240,8 @@ __global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, do
             atomicAdd(&hist[b1], 1u);
             atomicAdd(&hist[64 + b2], 1u);
         } else {
-            atomicAdd(&out[b1], 1.0);
-            atomicAdd(&out[nb + b2], 1.0);
+            atomicAdd(&ghist[b1], 1u);
+            atomicAdd(&ghist[nb + b2], 1u);
         }
         const double lx = log(d.a_dgdp[s]), ly = log(np_);
         acc[0] += 1.; acc[1] += np_; acc[2] += lx; acc[3] += lx * lx; acc[4] += lx * ly; acc[5] += ly; acc[6] += ly * ly; acc[7] += rg;
@@ -3204,13 +3257,25 @@ __global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, do
     if (threadIdx.x < 8) {
         double t = 0.;
         for (int ww = 0; ww < 8; ww++) t += red[ww][threadIdx.x];
-        atomicAdd(&out[2 * nb + threadIdx.x], t);
+        part[blockIdx.x * 8 + threadIdx.x] = t;
     }
     if (local_hist)
         for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) {
             const unsigned int c = hist[b < nb ? b : 64 + (b - nb)];
-            if (c) atomicAdd(&out[b], static_cast<double>(c));  // counts: exact in double, order-independent
+            if (c) atomicAdd(&ghist[b], c);
         }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ghist[2 * nb], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 8) {  // partial sums combined in CTA order, whichever CTA happens to be the last one
+        double t = 0.;
+        for (unsigned int bb = 0; bb < gridDim.x; bb++) t += __ldcg(&part[bb * 8 + threadIdx.x]);
+        out[2 * nb + threadIdx.x] = t;
+    }
+    for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) out[b] = static_cast<double>(__ldcg(&ghist[b]));
 }
 // summary of a sweep of independent searches (no commit): contacts, checksum of the finite distances, pair counters
 __global__ void __launch_bounds__(256) k_sweep_summary(const SearchResult *res, const double *q_dist, int nq, double *out /* 4 */) {

@@ -159,10 +159,15 @@ void calcul(PhysicalModel &pm, AggregatList &aggregates) {
     size_t total_events = 0, n_iter = 0, last_timestep_written = 0;
     long long total_steps = 0;
     long long n_sph = static_cast<long long>(aggregates.n_spheres()), n_agg = static_cast<long long>(aggregates.size());
-    const clock_t cpu_start = clock();
+    pm.cpu_last_event = pm.cpu_start = clock();  // physical_model.cpp:286
+    const clock_t cpu_start = pm.cpu_start;
     bool first = true;
     while (true) {
-        // loop top of calcul(): finished() is evaluated inside mcac_gpu_run (first slice) / from the last report (later slices)
+        // loop top of calcul(): PhysicalModel::finished.  The state-dependent rules are also enforced inside mcac_gpu_run at every
+        // step (a slice stops where the reference's loop would); STOPCODE and the cpu / cpu_event clocks are host-only and are
+        // seen here, i.e. after every event and at least every write_between_event_frequency steps.
+        pm.n_iter_without_event = n_iter;
+        if (pm.finished(static_cast<size_t>(n_agg), aggregates.get_avg_npp())) break;
         if (!first && pm.finished_flag) break;
         if (time_to_write(pm, total_events, n_iter, last_timestep_written)) save_advancement(pm, aggregates, dir);
         first = false;
@@ -184,6 +189,7 @@ void calcul(PhysicalModel &pm, AggregatList &aggregates) {
         }
         if (event) {
             total_events++;
+            pm.cpu_last_event = clock();  // calcul.cpp:238
             if (total_events % 20 == 1)
                 std::cout << std::setw(8) << "#" << " | " << std::setw(9) << "Npp_avg" << " | " << std::setw(8) << "NAgg" << " | " << std::setw(10)
                           << "Time" << " | " << std::setw(10) << "CPU" << " | " << std::setw(7) << "contact" << " | " << std::setw(5) << "merge"

@@ -1,5 +1,6 @@
 // mcac_b200 — `MCAC <params.ini>`: same command line and exit codes as the reference's src/main.cpp:26-56.
 #include <filesystem>
+#include <fstream>
 #include <iostream>
 
 #include "aggregat_list.hpp"
@@ -17,6 +18,10 @@ int main(int argc, char *argv[]) {
         const fs::path out = fs::absolute(fs::path(argv[1])).parent_path() / physicalmodel.output_dir;
         fs::create_directories(out);
         physicalmodel.output_dir = out.string();
+        {   // the echo of the parsed parameters (physical_model.cpp:271-272)
+            std::ofstream os(out / "params.ini");
+            os << physicalmodel.ini_echo;
+        }
         mcac::AggregatList aggregates(&physicalmodel);
         mcac::calcul(physicalmodel, aggregates);
     } catch (const mcac::BaseException &e) {

@@ -3,7 +3,11 @@
 // from csrc/mcac_math.cuh so the host placement and the device kernels evaluate the same expressions.
 #include "physical_model.hpp"
 
+#include <unistd.h>
+
 #include <cmath>
+#include <ctime>
+#include <filesystem>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -47,6 +51,30 @@ void take(IniMap &ini, const char *section, const char *key, T &dst) {
     if ((is >> std::boolalpha >> v) && !(is >> extra)) dst = v;
 }
 std::string take_string(IniMap &ini, const char *section, const char *key) { return ini[section][key]; }
+// inipp::Ini::generate: "[section]" / "key=value" lines in map order, a blank line after every section.  Keys that were looked up
+// but are absent from the file appear with an empty value, exactly as in the reference (extract() goes through operator[]).
+std::string generate_ini(const IniMap &ini) {
+    std::ostringstream os;
+    for (const auto &sec : ini) {
+        os << '[' << sec.first << ']' << std::endl;
+        for (const auto &kv : sec.second) os << kv.first << '=' << kv.second << std::endl;
+        os << std::endl;
+    }
+    return os.str();
+}
+// src/tools/tools.cpp:28-40 (http://www.concentric.net/~Ttwang/tech/inthash.htm): the clock / pid hash behind random_seed < 0
+unsigned long mix(unsigned long a, unsigned long b, unsigned long c) {
+    a = a - b; a = a - c; a = a ^ (c >> 13);
+    b = b - c; b = b - a; b = b ^ (a << 8);
+    c = c - a; c = c - b; c = c ^ (b >> 13);
+    a = a - b; a = a - c; a = a ^ (c >> 12);
+    b = b - c; b = b - a; b = b ^ (a << 16);
+    c = c - a; c = c - b; c = c ^ (b >> 5);
+    a = a - b; a = a - c; a = a ^ (c >> 3);
+    b = b - c; b = b - a; b = b ^ (a << 10);
+    c = c - a; c = c - b; c = c ^ (b >> 15);
+    return c;
+}
 mcacb::Gas gas_of(const PhysicalModel &p) {
     return {p.gaz_mean_free_path, p.viscosity, p.temperature, p.fractal_dimension, p.density, p.with_maturity ? 1 : 0};
 }
@@ -109,17 +137,26 @@ void PhysicalModel::parse(std::istream &in) {
     take(ini, "numerics", "enforce_volume_fraction", enforce_volume_fraction);
     take(ini, "numerics", "n_verlet_divisions", n_verlet_divisions);
     take(ini, "numerics", "random_seed", random_seed);
+    // init_random (tools.cpp:41-50): a negative seed is replaced by a hash of the CPU clock, the time and the pid; srand() then takes
+    // the int converted to unsigned.  The seed actually used is kept (print() reports it) so that the run can be replayed.
+    if (random_seed < 0) random_seed = static_cast<int>(mix(static_cast<unsigned long>(clock()), static_cast<unsigned long>(::time(nullptr)),
+                                                            static_cast<unsigned long>(getpid())));
+    random_seed_used = static_cast<uint32_t>(random_seed);
     word = take_string(ini, "numerics", "pick_method");
     if (!word.empty()) {
         pick_method = word == "random" ? PICK_RANDOM : word == "last" ? PICK_LAST : INVALID_PICK_METHOD;
         if (pick_method == INVALID_PICK_METHOD) throw InputError("Invalid pick method: " + word);
     }
-    word = take_string(ini, "numerics", "sort_order");
-    if (!word.empty()) {
-        if (word == "libstdcxx") sort_order = MCAC_ORDER_LIBSTDCXX;
-        else if (word == "stable") sort_order = MCAC_ORDER_STABLE;
-        else if (word == "host_stdsort") sort_order = MCAC_ORDER_HOST_STDSORT;
-        else throw InputError("Invalid sort_order: " + word);
+    {   // mcac_b200 extension; looked up without operator[] so that it does not show up in the params.ini echo
+        const auto sec = ini.find("numerics");
+        if (sec != ini.end()) {
+            const auto kv = sec->second.find("sort_order");
+            if (kv != sec->second.end() && !kv->second.empty()) {
+                if (kv->second == "libstdcxx") sort_order = MCAC_ORDER_LIBSTDCXX;
+                else if (kv->second == "stable") sort_order = MCAC_ORDER_STABLE;
+                else throw InputError("Invalid sort_order: " + kv->second);
+            }
+        }
     }
     take(ini, "inter_potential", "with_potentials", with_potentials);
     take(ini, "inter_potential", "with_electric_charges", with_electric_charges);
@@ -128,12 +165,24 @@ void PhysicalModel::parse(std::istream &in) {
     interpotential_file = take_string(ini, "inter_potential", "interpotential_file");
     take(ini, "inter_potential", "with_maturity", with_maturity);
     take(ini, "flame_coupling", "with_flame_coupling", with_flame_coupling);
-    if (with_flame_coupling) throw InputError("flame coupling is not part of the mcac_b200 hot path");
-    output_dir = take_string(ini, "output", "output_dir");
+    { const std::string ff = take_string(ini, "flame_coupling", "flame_file"); if (!ff.empty()) flame_file = ff; }
+    { const std::string od = take_string(ini, "output", "output_dir"); if (!od.empty()) output_dir = od; }
     take(ini, "output", "n_time_per_file", n_time_per_file);
     take(ini, "output", "write_between_event_frequency", write_between_event_frequency);
     take(ini, "output", "write_events_frequency", write_events_frequency);
     take(ini, "output", "write_Delta_t", write_Delta_t);
+    ini_echo = generate_ini(ini);  // what the reference writes to <output_dir>/params.ini (physical_model.cpp:271-272)
+    // Options of the reference that this path does not implement are refused here: a run that silently ignored them would finish
+    // with a trajectory that differs from the reference's and no diagnostic.
+    if (with_flame_coupling) throw InputError("flame coupling is not part of the mcac_b200 hot path");
+    if (with_electric_charges) throw InputError("with_electric_charges is not built in mcac_b200 (initial / merged aggregate charges)");
+    if (with_dynamic_random_charges)
+        throw InputError("with_dynamic_random_charges is not built in mcac_b200 (the reference draws a charge inside every merge)");
+    if (with_domain_reduction) throw InputError("with_domain_reduction is not built in mcac_b200 (AggregatList::reduction)");
+    if (with_surface_reactions && flux_surfgrowth < 0.)
+        throw InputError("flux_surfgrowth < 0 (oxidation: sphere removal and AggregatList::split) is not built in mcac_b200");
+    if (volsurf_method == EXACT_SBL || volsurf_method == EXACT_ARVO)
+        throw InputError("volsurf_method sbl / arvo are not built in mcac_b200 (use caps, alphas or none)");
 
     const double n = static_cast<double>(n_monomeres);
     double tot_volume_pp = 0., tot_surface_pp = 0.;
@@ -187,13 +236,36 @@ void PhysicalModel::update(size_t n_aggregates, size_t n_monomers, double total_
     monomer_concentration = static_cast<double>(n_monomers) / box_volume;
     volume_fraction = total_volume / box_volume;
 }
-// physical_model.cpp:288-337 without the STOPCODE file / CPU clocks (not reproducible, not on the device path)
+// physical_model.cpp:288-337, same order of tests and same messages.  The state-dependent rules are also evaluated by the device
+// loop at every step; the STOPCODE file and the CPU clocks can only be seen by the host, which calls this at the top of every
+// slice of calcul() (after every event and at least every write_between_event_frequency steps).
 bool PhysicalModel::finished(size_t n_agg, double avg_npp) const {
-    if (n_agg < 1) return true;
-    if (n_agg <= number_of_aggregates_limit) return true;
-    if (n_iter_without_event_limit > 0 && n_iter_without_event >= static_cast<size_t>(n_iter_without_event_limit)) return true;
-    if (physical_time_limit > 0 && time >= physical_time_limit) return true;
-    if (mean_monomere_per_aggregate_limit > 0 && avg_npp >= mean_monomere_per_aggregate_limit) return true;
+    if (!output_dir.empty() && std::filesystem::exists(std::filesystem::path(output_dir) / "STOPCODE")) {
+        std::cout << "STOPCODE" << std::endl << std::endl;
+        return true;
+    }
+    if (n_agg < 1) { std::cout << "All the aggregates disappeared" << std::endl << std::endl; return true; }
+    if (n_agg <= number_of_aggregates_limit) { std::cout << "We reach the AggMin condition" << std::endl << std::endl; return true; }
+    if (n_iter_without_event_limit > 0 && n_iter_without_event >= static_cast<size_t>(n_iter_without_event_limit)) {
+        std::cout << "We reach the WaitLimit condition" << std::endl << std::endl;
+        return true;
+    }
+    if (cpu_limit > 0) {
+        const double elapse = double(clock() - cpu_start) / CLOCKS_PER_SEC;
+        if (elapse >= cpu_limit) { std::cout << "We reach the CPULimit condition" << std::endl << std::endl; return true; }
+    }
+    if (cpu_event_limit > 0) {
+        const double elapse = double(clock() - cpu_last_event) / CLOCKS_PER_SEC;
+        if (elapse >= cpu_event_limit) { std::cout << "We reach the CPULimitEvent condition" << std::endl << std::endl; return true; }
+    }
+    if (physical_time_limit > 0 && time >= physical_time_limit) {
+        std::cout << "We reach the Maximum physical time condition " << time << "/" << physical_time_limit << std::endl;
+        return true;
+    }
+    if (mean_monomere_per_aggregate_limit > 0 && avg_npp >= mean_monomere_per_aggregate_limit) {
+        std::cout << "We reach the NPP_avg_limit condition " << avg_npp << "/" << mean_monomere_per_aggregate_limit << std::endl;
+        return true;
+    }
     return false;
 }
 void PhysicalModel::print() const {
@@ -242,7 +314,7 @@ mcac_params PhysicalModel::to_params() const {
     p.with_nucleation = with_nucleation;
     p.with_dynamic_random_charges = with_dynamic_random_charges;
     p.sort_order = sort_order;
-    p.random_seed = static_cast<uint32_t>(random_seed < 0 ? 0 : random_seed);
+    p.random_seed = random_seed_used;
     return p;
 }
 

@@ -2,7 +2,8 @@
 // (include/physical_model/physical_model.hpp:29-96, src/physical_model/physical_model.cpp:32-287,489-637).
 // Same public field names and meaning, so reference call sites (`physicalmodel.time`, `.box_length`,
 // `.finished(...)`, `.update(...)`) keep working; the .ini reader accepts the same sections/keys with the
-// same defaults.  Flame coupling, HDF5 output and wall-clock limits are out of scope.
+// same defaults.  Options whose code is not built (flame coupling, electric charges, domain reduction,
+// oxidation, sbl / arvo) are refused with InputError instead of being ignored.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -60,7 +61,10 @@ class PhysicalModel {
     int mean_monomere_per_aggregate_limit = -1;
     size_t number_of_aggregates_limit = 1;
     int n_iter_without_event_limit = -1;
-    int random_seed = -1;
+    int random_seed = -1;              // after parse(): the seed in use (a negative one was replaced, tools.cpp:41-50)
+    uint32_t random_seed_used = 0;     // srand() argument
+    long cpu_start = 0, cpu_last_event = 0;  // clock() at construction / at the last event (physical_model.cpp:286, calcul.cpp:231)
+    std::string ini_echo;              // inipp::Ini::generate of the parsed file: the content of <output_dir>/params.ini
     size_t write_events_frequency = 1, write_between_event_frequency = 100, full_aggregate_update_frequency = 1;
     std::string output_dir = "MCAC_output", flame_file = "flame_input", interpotential_file = "interpotential_file";
     bool with_domain_duplication = true, with_domain_reduction = false, with_nucleation = false, with_collisions = true;

@@ -52,11 +52,10 @@ double HostRandom::inverf(double p) { return inverse_erfc(1. - p); }
 double HostRandom::normal(double mean, double sigma) { return mean + std::sqrt(2.) * sigma * inverf(2. * uniform() - 1.0); }
 
 InitialState place_monomers(PhysicalModel &pm) {
-    if (pm.random_seed < 0) throw InputError("mcac_b200 needs [numerics] random_seed >= 0 (clock/pid seeds cannot be replayed)");
-    if (pm.with_electric_charges) throw InputError("initial electric charges are not built yet");
+    if (pm.with_electric_charges) throw InputError("with_electric_charges is not built in mcac_b200 (initial / merged aggregate charges)");
     const int64_t n = static_cast<int64_t>(pm.n_monomeres);
     const double box = pm.box_length;
-    HostRandom rng(static_cast<uint32_t>(pm.random_seed));
+    HostRandom rng(pm.random_seed_used);  // srand(seed): a negative [numerics] random_seed was replaced by parse() (tools.cpp:41-50)
     const mcacb::Gas gas{pm.gaz_mean_free_path, pm.viscosity, pm.temperature, pm.fractal_dimension, pm.density, pm.with_maturity ? 1 : 0};
     InitialState st;
     st.n_sph = st.n_agg = n;

@@ -52,6 +52,12 @@ int mcac_host_model_metadata(const mcac_host_model *m, char *buf, int64_t cap) {
     std::memcpy(buf, s.c_str(), s.size() + 1);
     return 0;
 }
+int mcac_host_model_ini_echo(const mcac_host_model *m, char *buf, int64_t cap) {
+    const std::string &s = m->pm.ini_echo;
+    if ((int64_t)s.size() + 1 > cap) return mcac::INPUT_ERROR;
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
 // derived PhysicalModel scalars for parity checks: box_length, box_volume, viscosity, gaz_mean_free_path, mean_massic_radius,
 // friction_exponnant, u_sg, aggregate_concentration, total_volume_concent, total_surface_concent, mass_nuclei, volume_fraction
 int mcac_host_model_derived(const mcac_host_model *m, double out[12]) {

@@ -1413,4 +1413,37 @@ void orc_sort_introsort(long long n, const double *keys, long long *idx) {  // t
     std::sort(v.begin(), v.end(), [keys](size_t a, size_t b) { return keys[a] < keys[b]; });
     for (long long i = 0; i < n; i++) idx[i] = (long long)v[(size_t)i];
 }
+// mcac::linreg (src/tools/tools.cpp:126-157) as AggregatList::get_instantaneous_fractal_law calls it
+// (src/aggregats/aggregat_list_fractal_law.cpp:23-33: x = dg_over_dp, y = number of spheres, in label order).
+// out = {ok, a, b, r}; `r` keeps the reference's pow(..., 2) where a square root is meant (:153-155).
+void orc_linreg(long long n_, const double *x, const double *y, double *out) {
+    double sumx = 0.0, sumx_2 = 0.0, sumxy = 0.0, sumy = 0.0, sumy_2 = 0.0;
+    const double n = static_cast<double>(n_);
+    for (long long i = 0; i < n_; i++) {
+        const double log_x = std::log(x[i]), log_y = std::log(y[i]);
+        sumx += log_x;
+        sumx_2 += std::pow(log_x, 2);
+        sumxy += log_x * log_y;
+        sumy += log_y;
+        sumy_2 += std::pow(log_y, 2);
+    }
+    const double denom = (n * sumx_2 - std::pow(sumx, 2));
+    if (n_ == 0 || std::abs(denom) < 1e-9) { out[0] = out[1] = out[2] = out[3] = 0.; return; }
+    out[0] = 1.;
+    out[1] = (n * sumxy - sumx * sumy) / denom;
+    out[2] = (sumy * sumx_2 - sumx * sumxy) / denom;
+    out[3] = (sumxy - sumx * sumy / n) / std::pow((sumx_2 - std::pow(sumx, 2) / n) * (sumy_2 - std::pow(sumy, 2) / n), 2);
+}
+// the same sort with introsort's depth limit forced to `depth` (std::sort uses 2 * floor(log2(n))): libstdc++'s own
+// __introsort_loop + __final_insertion_sort, so that the heap-sort branch behind the limit can be checked on the device
+void orc_sort_introsort_depth(long long n, const double *keys, long long depth, long long *idx) {
+    std::vector<size_t> v((size_t)n);
+    std::iota(v.begin(), v.end(), 0);
+    auto cmp = __gnu_cxx::__ops::__iter_comp_iter([keys](size_t a, size_t b) { return keys[a] < keys[b]; });
+    if (n > 1) {
+        std::__introsort_loop(v.begin(), v.end(), (long)depth, cmp);
+        std::__final_insertion_sort(v.begin(), v.end(), cmp);
+    }
+    for (long long i = 0; i < n; i++) idx[i] = (long long)v[(size_t)i];
+}
 }  // extern "C"

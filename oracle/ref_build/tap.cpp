@@ -154,6 +154,15 @@ void dump_state(const AggregatList &al, const std::string &name) {
             for (size_t k = 0; k < al[i]->myspheres.size(); k++) put_f64(f, k < v.size() ? v[k] : 0.0);
         }
     fclose(f);
+    // the reference's own morphology regression on this state (AggregatList::get_instantaneous_fractal_law ->
+    // linreg, aggregat_list_fractal_law.cpp:23-33; const, not called by calcul): pins K11 / ensemble.fractal_law
+    const auto law = al.get_instantaneous_fractal_law();
+    FILE *g = tap.open(name + ".fractal");
+    put_f64(g, std::get<0>(law) ? 1.0 : 0.0);
+    put_f64(g, std::get<1>(law));
+    put_f64(g, std::get<2>(law));
+    put_f64(g, std::get<3>(law));
+    fclose(g);
 }
 
 void Tap::summary(const char *why) {

@@ -7,7 +7,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import mcac_b200
 from golden_lib import write_interpotential_file
-from oracle.run_ref import merged_config
+from mcac_b200.configs import merged_config
 
 seed, steps = int(sys.argv[1]), int(sys.argv[2])
 tmp = tempfile.mkdtemp()

@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import mcac_b200
 from golden_lib import write_interpotential_file
-from oracle.run_ref import merged_config
+from mcac_b200.configs import merged_config
 
 R, T, M, K = (int(x) for x in sys.argv[1:5])
 FIRST = int(sys.argv[5]) if len(sys.argv) > 5 else 0

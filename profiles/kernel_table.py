@@ -7,7 +7,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import mcac_b200
 from bench import workload_config
-from oracle.run_ref import merged_config
+from mcac_b200.configs import merged_config
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60000

@@ -178,3 +178,19 @@ def introsort_order(keys: np.ndarray) -> np.ndarray:
     idx = np.zeros(len(keys), np.int64)
     lib().orc_sort_introsort(len(keys), _p(keys), _p(idx))
     return idx
+
+
+def introsort_order_depth(keys: np.ndarray, depth: int) -> np.ndarray:
+    """std::sort's loop with the depth limit forced to `depth` (the heap-sort branch is taken below it)."""
+    keys = np.ascontiguousarray(keys, np.float64)
+    idx = np.zeros(len(keys), np.int64)
+    lib().orc_sort_introsort_depth(len(keys), _p(keys), int(depth), _p(idx))
+    return idx
+
+
+def linreg(x: np.ndarray, y: np.ndarray) -> tuple:
+    """mcac::linreg restated in C (oracle/mcac_oracle.cpp:orc_linreg): (ok, a, b, r)."""
+    x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
+    out = np.zeros(4)
+    lib().orc_linreg(len(x), _p(x), _p(y), _p(out))
+    return bool(out[0]), float(out[1]), float(out[2]), float(out[3])

@@ -67,7 +67,8 @@ def test_cli_writes_the_reference_advancement_file(name, tmp_path):
     boundary: at most a handful of values per file).  pytest: growth + one duplication, 15 456 steps; monodisperse: 1 000 452
     steps, 1 688 events, two duplications (reference md5 1965853c... in SURVEY.md §8c)."""
     import numpy as np
-    from oracle.run_ref import merged_config, write_ini
+    from mcac_b200.configs import merged_config
+    from oracle.run_ref import write_ini
 
     base, ov = ADV_CASES[name]
     cfg = merged_config(base, ov)

@@ -5,7 +5,7 @@ contact, the speculative batch width is invisible."""
 import numpy as np
 import pytest
 
-from oracle.run_ref import merged_config
+from mcac_b200.configs import merged_config
 from oracle_lib import Oracle
 from test_gpu_parity import FP_FIELDS, INT_FIELDS, assert_records_match, assert_states_match
 

@@ -177,6 +177,52 @@ def test_device_sort_against_std_sort_on_random_weights():
         np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))  # np.cumsum is the sequential sum
 
 
+@pytest.mark.parametrize("depth", [0, 1, 3, 6])
+def test_device_sort_replays_the_heap_sort_branch(depth, monkeypatch):
+    """introsort's depth limit forced to a small value (MCAC_B200_SORT_DEPTH): the event kernel hands the sort back, the multi-launch
+    device path replays the partition levels down to the limit and then libstdc++'s heap-sort branch (k_sort_heap,
+    csrc/heap_sort.cuh) — the order must be that of libstdc++'s own __introsort_loop run with the same limit.  No host sort."""
+    from oracle_lib import introsort_order_depth
+    monkeypatch.setenv("MCAC_B200_SORT_DEPTH", str(depth))
+    text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 5, "n_verlet_divisions": 8}, "monomers": {"number": 3000}}))
+    hm = HostModel(text).state()
+    rng = np.random.default_rng(11 + depth)
+    n = hm["n_agg"]
+    for ts in [rng.random(n) + 0.5, rng.integers(1, 4, n).astype(float), np.ones(n)]:
+        st = dict(hm)
+        af = hm["agg_fields"].copy()
+        af[3] = ts
+        st["agg_fields"] = af
+        sim = Simulation(text)
+        sim.upload(st)
+        sim.sort_time_steps(2.0)
+        idx, cum = sim.pick_table()
+        keys = 2.0 / ts
+        ref = introsort_order_depth(keys, depth)
+        np.testing.assert_array_equal(idx, ref)
+        np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))
+        rep, _ = sim.run(0)
+        assert rep["sort_heap_branches"] >= 1 and rep["sort_fallbacks"] >= 1
+
+
+def test_suspect_list_overflow_is_an_error_not_a_wrong_contact(monkeypatch):
+    """A contact search with more eligible suspects than its list holds does not know the first contact: the run must stop
+    with an error instead of committing whichever suspects won the race.  The list is shrunk to 2 entries (MCAC_B200_CAND_CAP) in a
+    dense box searched by the wide kernel only."""
+    monkeypatch.setenv("MCAC_B200_CAND_CAP", "2")
+    monkeypatch.setenv("MCAC_B200_SEARCH_GROUP", "0")
+    text = ini_text(merged_config("monodisperse", {"numerics": {"random_seed": 3, "n_verlet_divisions": 3}, "monomers": {"number": 600},
+                                                   "environment": {"volume_fraction": "0.05"}}))
+    sim = Simulation(text)
+    with pytest.raises(mcac_b200.McacError) as e:
+        sim.run(20000, batch=64)
+    assert "more eligible suspects" in str(e.value)
+    monkeypatch.delenv("MCAC_B200_CAND_CAP")
+    ok = Simulation(text)
+    rep, _ = ok.run(2000, batch=64)
+    assert rep["steps"] == 2000
+
+
 @pytest.mark.parametrize("n,frac,classes,local", [(30000, 0.003, 3, 64), (30000, 0.05, 0, 4096), (200000, 0.0, 1, 4096),
                                                   (200000, 0.002, 0, 4096), (200000, 0.03, 4, 512), (65537, 0.01, 2, 4096)])
 def test_tie_dominated_sort_fast_path_is_std_sort(n, frac, classes, local, monkeypatch):

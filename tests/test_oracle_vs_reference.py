@@ -91,3 +91,41 @@ def test_pick_table_matches_std_sort_of_reference(name):
     idx, cum = o.pick_table()
     np.testing.assert_array_equal(idx, srt["idx"])
     np.testing.assert_array_equal(cum, srt["cum"])
+
+
+def test_fractal_law_restatements_against_the_reference():
+    """AggregatList::get_instantaneous_fractal_law -> linreg (aggregat_list_fractal_law.cpp:23-33, tools.cpp:126-157) evaluated by
+    the unmodified reference on the fixture snapshots (tests/golden/fractal_law.json, made by make_fractal_golden.py): the oracle's
+    C restatement must agree bit for bit, the numpy form used by mcac_b200/ensemble.py to summation-order rounding."""
+    import json
+    from pathlib import Path
+
+    from golden_lib import Golden
+    from mcac_b200 import ensemble as ens
+    from oracle_lib import linreg
+    gold = json.loads((Path(__file__).parent / "golden" / "fractal_law.json").read_text())
+    checked = 0
+    for name, states in gold.items():
+        g = Golden(name)
+        for key, (ok, a, b, r) in states.items():
+            if key.startswith("state_") and key[6:].isdigit() and int(key[6:]) not in g.meta["state_steps"]:
+                continue
+            try:
+                st = g.state(key)
+            except KeyError:
+                continue
+            x, y = st["aggregates"]["dg_over_dp"], st["agg_n_spheres"].astype(float)
+            got = linreg(x, y)
+            assert got[0] == bool(ok), (name, key)
+            for u, v in zip(got[1:], (a, b, r)):
+                assert (np.isnan(u) and np.isnan(v)) or u == v, (name, key, got, (ok, a, b, r))
+            if np.ptp(np.log(x)) < 1e-6:  # every aggregate still a monomer: the normal matrix is singular up to rounding noise, and
+                checked += 1              # whether |denom| < 1e-9 then depends on the summation order (sequential in the reference)
+                continue
+            nok, na, nb_, nr = ens.linreg(x, y)
+            assert nok == bool(ok)
+            if ok and np.isfinite(r):
+                np.testing.assert_allclose([na, nb_], [a, b], rtol=1e-9, atol=1e-12)
+                np.testing.assert_allclose(nr, r, rtol=1e-6)
+            checked += 1
+    assert checked >= 12

@@ -14,3 +14,13 @@ def test_tie_sort_header_reproduces_std_sort(tmp_path):
         out = subprocess.run([str(exe), "400", str(seed)], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
         assert out.stdout.startswith("ok 400 cases"), out.stdout
+
+
+def test_heap_sort_header_reproduces_libstdcxx_heap_branch(tmp_path):
+    """mcac_b200/csrc/heap_sort.cuh (the branch std::sort takes behind introsort's depth limit; k_sort_heap on the device) against
+    std::partial_sort and against libstdc++'s own __introsort_loop run with a small depth limit."""
+    exe = tmp_path / "heap_sort_host"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", str(exe), str(ROOT / "tests" / "native" / "heap_sort_host.cpp")])
+    out = subprocess.run([str(exe), "300", "7"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok 300 cases"), out.stdout
