@@ -74,7 +74,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def reference_run(n_monomers: int, seed: int, mc_steps: int, n_chunks: int) -> dict:
+def reference_run(n_monomers: int, seed: int, mc_steps: int, n_chunks: int, core: int | None = None) -> dict:
     """The reference's own CPU implementation of the path (oracle/_ref/MCAC_tap = unmodified sources + counters), one thread
     (the reference is single-threaded), bounded sample: n_chunks x mc_steps MC steps after its own initial placement."""
     from oracle.run_ref import read_summary, run_reference
@@ -86,7 +86,7 @@ def reference_run(n_monomers: int, seed: int, mc_steps: int, n_chunks: int) -> d
     if not exe.exists():
         raise FileNotFoundError("oracle/_ref/MCAC_tap is not built")
     t0 = time.perf_counter()
-    wd, _ = run_reference(base, ov, env={"MCAC_TAP_EXIT_STEP": mc_steps * n_chunks, "MCAC_TAP_CHUNK": mc_steps})
+    wd, _ = run_reference(base, ov, env={"MCAC_TAP_EXIT_STEP": mc_steps * n_chunks, "MCAC_TAP_CHUNK": mc_steps}, taskset_core=core)
     total_wall = time.perf_counter() - t0
     s = read_summary(wd)
     shutil.rmtree(wd, ignore_errors=True)
@@ -293,7 +293,7 @@ def main():
             from concurrent.futures import ThreadPoolExecutor
 
             with ThreadPoolExecutor(n_proc) as ex:
-                runs = list(ex.map(lambda k: reference_run(a.n_monomers, 42 + k, M, W + K), range(n_proc)))
+                runs = list(ex.map(lambda k: reference_run(a.n_monomers, 42 + k, M, W + K, core=k), range(n_proc)))
         except Exception as e:  # noqa: BLE001
             print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
             return
@@ -303,6 +303,10 @@ def main():
         value = n_proc * M * K / max(per_proc)
         r = dict(r, pair_tests=sum(x["pair_tests"] for x in runs))
         config["mc_steps_per_step"] = M
+        # the CPU arm cannot reach the GPU arm's window within minutes (100 000 MC steps take ~3.5 min at ~480 steps/s): it times the
+        # head of the same trajectory; its per-step cost is flat over the run (profiles/r2_tuning.md)
+        config["window_mc_steps"] = [W * M, (W + K) * M]
+        config["pinning"] = f"taskset -c k for process k (k < {n_proc})"
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * sum(timed) / len(timed), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
@@ -330,6 +334,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     M = a.mc_steps or 20000
     config["mc_steps_per_step"] = M
+    config["window_mc_steps"] = [W * M, (W + K) * M]
     config["batch"] = a.batch
     base, ov = workload_config(a.n_monomers, 42 + rank)
     text = mcac_b200.ini_text(merged_config(base, ov))
@@ -381,6 +386,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    k9_traffic = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from an ncu --set full capture of THIS build and window
+        k9_traffic = json.load(open(ROOT / "profiles" / "r2_k9_traffic.json"))
+    except (OSError, ValueError):
+        pass
     n_agg_now = reps[-1]["n_aggregates"]
     # K9 (dominant kernel of the step): the per-event pipeline in one cooperative launch.  Algorithmic bytes per aggregate
     # (one pass): liveness + label 12, refresh/totals 24, weight 8, sorted index 4, cumulative 8, pick slot 4 = 60 B.
@@ -390,9 +400,8 @@ def main():
     sorts = max(1, sum(r["sorts"] for r in reps))
     roofline = {"kernel": "k_event (K9: labels + refresh + totals + 1/dt weights + replayed introsort [sparse simulation + routing for "
                           "tie-dominated tables] + cumulative table, one cooperative launch per merge)", "bound": "hbm", "achieved": k9_gbs, "peak": peak, "unit": "GB/s", "frac": k9_gbs / peak,
-                "traffic": 28.25e6 if a.n_monomers == 1_000_000 else None,
-                "traffic_source": "dram__bytes_read.sum (28.2 MB) + dram__bytes_write.sum (0.05 MB: the written tables stay in L2) of one ncu --set full "
-                                  "capture of this kernel on this workload (profiles/r1c_ncu_full_summary.md), per launch",
+                "traffic": k9_traffic.get("dram_bytes_per_launch") if a.n_monomers == 1_000_000 else None,
+                "traffic_source": k9_traffic.get("source", "no ncu capture of this build committed (profiles/r2_k9_traffic.json)"),
                 "peak_source": peak_source, "launches": n_event, "avg_launch_us": 1e3 * event_ms / n_event,
                 "algorithmic_bytes_per_launch": k9_bytes, "share_of_step": event_ms / dev_ms if dev_ms else None,
                 "sort_levels_per_launch": sum(r["sort_levels"] for r in reps) / sorts,
@@ -424,8 +433,7 @@ def main():
     sw_bytes = 36.0 * sw["pair_tests_bounding"] + 32.0 * (sw["pair_tests_sphere"] + sw["n_queries"]) + 48.0 * sw["n_queries"]
     sw_gbs = sw_bytes / (sw["kernel_ms"] * 1e-3) / 1e9
     roofline_sweep = {"kernel": "k_search_group<8> (K1), one launch of %d searches" % sw["n_queries"], "bound": "hbm", "achieved": sw_gbs,
-                      "peak": peak, "unit": "GB/s", "frac": sw_gbs / peak, "traffic": 108.6e6 if a.n_monomers == 1_000_000 else None,
-                      "traffic_source": "ncu --set full capture of the same launch (profiles/r1b_ncu_full_summary.md)", "kernel_ms": sw["kernel_ms"],
+                      "peak": peak, "unit": "GB/s", "frac": sw_gbs / peak, "traffic": None, "kernel_ms": sw["kernel_ms"],
                       "pair_tests_per_sec": (sw["pair_tests_bounding"] + sw["pair_tests_sphere"]) / (sw["kernel_ms"] * 1e-3),
                       "searches_per_sec": sw["n_queries"] / (sw["kernel_ms"] * 1e-3)}
 
@@ -506,10 +514,10 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             Mr = 400
-            r = reference_run(a.n_monomers, 42, Mr, 8)
+            r = reference_run(a.n_monomers, 42, Mr, 8, core=0)
             timed = r["chunk_s"][2:]
             cpu_baseline = {"value": Mr * len(timed) / sum(timed), "unit": UNIT, "cores": 1, "kind": r["kind"],
-                            "sample": f"{len(timed)} x {Mr} MC steps of the same N={a.n_monomers} workload (seed 42) after 2 warm-up chunks, one thread "
+                            "sample": f"{len(timed)} x {Mr} MC steps of the same N={a.n_monomers} workload (seed 42) after 2 warm-up chunks, one thread pinned with taskset "
                                       f"(the reference is single-threaded), placement ({r['init_s']:.1f} s) excluded, cpu: {cpu_model()}",
                             "pair_tests_per_sec": r["pair_tests"] / r["calcul_wall_s"]}
         except Exception as e:  # noqa: BLE001

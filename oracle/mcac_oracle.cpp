@@ -1365,6 +1365,76 @@ void orc_get_pick_table(void *h, long long *idx, double *cum) {
 }
 long long orc_pick_table_size(void *h) { return (long long)((System *)h)->index_sorted_time_steps.size(); }
 
+// Re-synchronise the restatement with a state downloaded from the device (same layouts as orc_get_spheres / orc_get_aggregates):
+// everything a step reads is replaced — sphere and aggregate fields, ordered membership, Verlet cells (recomputed from the stored
+// cell of every aggregate), clocks and counters of calcul() — and the RNG stream is positioned `rand_consumed` draws after
+// srand(seed).  `event` is forced so that the next step re-sorts the pick table (valid whenever no aggregate changed since the
+// last event, i.e. at any point of a run without surface growth).  The box must be the one of the .ini (no duplication yet).
+// scalars = {time, maxradius, max_time_step, avg_npp, n_iter_without_event}.
+int orc_set_state(void *h, long long n_sph, long long n_agg, const double *sph_fields, const long long *sph_label, const double *agg_fields,
+                  const long long *cells, const long long *offsets, const long long *members, const double *per_member,
+                  const double *scalars, long long rand_consumed) {
+    ORC_TRY
+    System &s = *(System *)h;
+    orc::Spheres &sp = s.spheres;
+    std::vector<double> *f[9] = {&sp.x, &sp.y, &sp.z, &sp.r, &sp.volume, &sp.surface, &sp.rx, &sp.ry, &sp.rz};
+    for (int k = 0; k < 9; k++) f[k]->assign(sph_fields + k * n_sph, sph_fields + (k + 1) * n_sph);
+    sp.label.assign((size_t)n_sph, 0);
+    sp.charge.assign((size_t)n_sph, 0);
+    for (long long i = 0; i < n_sph; i++) sp.label[(size_t)i] = (long)sph_label[i];
+    s.list.clear();
+    s.verlet_reset(s.pm.n_verlet_divisions, s.pm.box_length);
+    for (long long i = 0; i < n_agg; i++) {
+        auto a = std::make_unique<orc::Aggregate>();
+        double *v[21] = {&a->rg, &a->f_agg, &a->lpm, &a->time_step, &a->rmax, &a->volume, &a->surface, &a->x, &a->y, &a->z, &a->rx, &a->ry,
+                         &a->rz, &a->proper_time, &a->dp, &a->dg_over_dp, &a->overlapping, &a->coordination_number,
+                         &a->electric_charge_field, &a->d_m, &a->CH_ratio};
+        for (int k = 0; k < 21; k++) *v[k] = agg_fields[k * n_agg + i];
+        const long long lo = offsets[i], hi = offsets[i + 1];
+        a->n_spheres = (size_t)(hi - lo);
+        a->alpha_vs_extreme = 1.0 / static_cast<double>(a->n_spheres);
+        for (long long k = lo; k < hi; k++) {
+            a->myspheres.push_back((size_t)members[k]);
+            a->volumes.push_back(per_member[k]);
+            a->surfaces.push_back(per_member[n_sph + k]);
+            a->distances_center.push_back(per_member[2 * n_sph + k]);
+        }
+        a->index_verlet = {(size_t)cells[i], (size_t)cells[n_agg + i], (size_t)cells[2 * n_agg + i]};
+        a->in_verlet = true;
+        {   // contact graph (Aggregate::distances) rebuilt from the relative positions and the CURRENT radii; the stored overlap
+            // statistics are kept.  With surface growth this equals the reference's graph only right after a full-update step
+            // (calcul.cpp:184-206): re-synchronise there.
+            const double ovl = a->overlapping, cn = a->coordination_number;
+            const std::vector<double> dc = a->distances_center;
+            s.update_distances_and_overlapping(*a);
+            a->overlapping = ovl;
+            a->coordination_number = cn;
+            a->distances_center = dc;
+        }
+        s.list.push_back(std::move(a));
+        s.cell(s.list.back()->index_verlet).insert((size_t)i);
+    }
+    s.pm.time = scalars[0];
+    s.maxradius = scalars[1];
+    s.max_time_step = scalars[2];
+    s.avg_npp = scalars[3];
+    s.pm.n_iter_without_event = (size_t)scalars[4];
+    s.event = true;
+    s.pm.rng.seed((unsigned)s.pm.random_seed);
+    for (long long i = 0; i < rand_consumed; i++) s.pm.rng.next();
+    return 0;
+    ORC_CATCH(-1)
+}
+// Aggregate::update() (aggregat.cpp:284-288) of every aggregate from its spheres' radii and relative positions: the per-aggregate
+// morphology (V, S, Rg, rmax, f_agg, d_m, lpm, time_step ...) a downloaded device state is checked against
+int orc_update_all(void *h) {
+    ORC_TRY
+    System &s = *(System *)h;
+    for (size_t i = 0; i < s.size(); i++) s.update(i);
+    return 0;
+    ORC_CATCH(-1)
+}
+
 // ---- unit-level entry points
 double orc_pair_distance(const double p1[3], double r1, const double p2[3], double r2, const double dir[3], double dist, double L) {
     return orc::pair_distance_to_contact({p1[0], p1[1], p1[2]}, r1, {p2[0], p2[1], p2[2]}, r2, {dir[0], dir[1], dir[2]}, dist, L);

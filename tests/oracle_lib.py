@@ -136,6 +136,25 @@ class Oracle:
         out.update(self.scalars())
         return out
 
+    def set_state(self, st: dict, rand_consumed: int) -> None:
+        """Re-synchronise with a state in the layout Simulation.state() / Oracle.state() return (see orc_set_state)."""
+        ns, na = int(st["n_sph"]), int(st["n_agg"])
+        sf = np.ascontiguousarray(np.stack([st["spheres"][k] for k in SPHERE_FIELDS]), np.float64)
+        af = np.ascontiguousarray(np.stack([st["aggregates"][k] for k in AGG_FIELDS]), np.float64)
+        lab = np.ascontiguousarray(st["sphere_label"], np.int64)
+        cells = np.ascontiguousarray(st["agg_cell"], np.int64)
+        offs = np.ascontiguousarray(st["offsets"], np.int64); mem = np.ascontiguousarray(st["members"], np.int64)
+        pm = np.ascontiguousarray(np.stack([st["member_volumes"], st["member_surfaces"], st["member_distances_center"]]), np.float64)
+        sc = np.array([st["time"], st["maxradius"], st["max_time_step"], st["avg_npp"], st["n_iter_without_event"]], np.float64)
+        self.L.orc_set_state.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong] + [C.c_void_p] * 8 + [C.c_longlong]
+        if self.L.orc_set_state(self.h, ns, na, _p(sf), _p(lab), _p(af), _p(cells), _p(offs), _p(mem), _p(pm), _p(sc), int(rand_consumed)):
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
+
+    def update_all(self) -> None:
+        self.L.orc_update_all.argtypes = [C.c_void_p]
+        if self.L.orc_update_all(self.h):
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
+
     def pick_table(self):
         n = int(self.L.orc_pick_table_size(self.h))
         idx = np.zeros(n, np.int64); cum = np.zeros(n)

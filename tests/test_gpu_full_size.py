@@ -9,7 +9,7 @@ from mcac_b200.configs import merged_config
 from oracle_lib import Oracle
 from test_gpu_parity import FP_FIELDS, INT_FIELDS, assert_records_match, assert_states_match
 
-from mcac_b200 import Simulation, ini_text
+from mcac_b200 import HostModel, Simulation, ini_text
 
 pytestmark = pytest.mark.gpu
 
@@ -100,6 +100,141 @@ def test_c3_1e6_head_replay_and_properties():
         np.testing.assert_array_equal(a2["spheres"][k], a3["spheres"][k])
     np.testing.assert_array_equal(a2["aggregates"]["proper_time"], a3["aggregates"]["proper_time"])
     assert r3["tie_sorts"] > 0  # the pick table of this configuration is tie-dominated: sparse fast path of the sort
+
+
+def as_upload(st):
+    """Simulation.state() -> the dict Simulation.upload() takes (field-major stacks in the reference's field order)."""
+    import ref_trace as rt
+    out = dict(st)
+    out["sphere_fields"] = np.stack([st["spheres"][k] for k in rt.SPHERE_FIELDS])
+    out["agg_fields"] = np.stack([st["aggregates"][k] for k in rt.AGG_FIELDS])
+    out["per_member"] = np.stack([st["member_volumes"], st["member_surfaces"], st["member_distances_center"]])
+    return out
+
+
+def relative_steps(recs):
+    out = recs.copy()
+    out["step"] -= out["step"][0]
+    return out
+
+
+C3_OV = {"monomers": {"number": 1000000}, "environment": {"volume_fraction": "1000e-6"}, "limits": {"physical_time": -1},
+         "numerics": {"with_collisions": "true", "pick_method": "random", "n_verlet_divisions": 100, "with_domain_duplication": "false",
+                      "random_seed": 42}}
+
+
+def test_c3_1e6_parity_over_the_window_the_bench_times(monkeypatch):
+    """VERDICT r1 item 1.  `bench.py --steps 20 --warmup 5` times MC steps 100 000 - 500 000 of this workload; the regimes of the
+    pick-table sort change along the way (sparse elements of the tie-dominated table: ~100, ~2 000 — overlap on —, ~3 000 — handed-over
+    segment > 4096, overlap lost —, ~7 000, and > 8 192 — general replay back).  The run is taken to 700 000 steps and at six
+    checkpoints the device state is downloaded and checked:
+      (a) the pick table the event kernel builds == libstdc++'s std::sort order of max_dt / time_step on that state (index order
+          bit-exact; cumulative table to the documented 1e-10 of the tree sum), and at one checkpoint also with the sparse path
+          switched off (forced general replay on the same state);
+      (b) the structure invariants (labels partition the spheres, CSR membership);
+      (c) every multi-sphere aggregate's V / S / Rg / rmax / f_agg / d_m / lpm / time_step == Aggregate::update() of the oracle on the
+          same members (the monomers' stored fields predate the initial radius rescale, aggregat_list_storage.cpp:75-87);
+      (d) the oracle is re-synchronised from the downloaded state and the next 200 steps are replayed step by step.
+    aggregat_list.cpp:109-141 (sort), aggregat.cpp:247-483 (update)."""
+    from oracle_lib import introsort_order
+    text = ini_text(merged_config("brownian", C3_OV))
+    consumed0 = HostModel(text).state()["rand_consumed"]
+    sim = Simulation(text)
+    st0 = sim.state()
+    o = Oracle("brownian", C3_OV, construct=False)
+    box = st0["box_length"]
+    done, events, seen_paths = 0, 0, set()
+    for cp in [7500, 150000, 225000, 520000, 650000, 700000]:
+        rep, _ = sim.run(cp - done, batch=256)  # no records: the pipelined submission the bench uses
+        assert rep["steps"] == cp - done and rep["sort_fallbacks"] == 0
+        done, events = cp, events + rep["events"]
+        st = sim.state()
+        check_structure(st)
+        assert st["n_agg"] == st0["n_agg"] - events
+        # ---- (a) the pick table of this state
+        ts = st["aggregates"]["time_step"]
+        keys = st["max_time_step"] / ts
+        assert st["max_time_step"] == ts.max()
+        ref = introsort_order(keys)
+        sim.sort_time_steps(st["max_time_step"])
+        idx, cum = sim.pick_table()
+        np.testing.assert_array_equal(idx, ref, err_msg=f"pick table order at step {cp}")
+        np.testing.assert_allclose(cum, np.cumsum(keys[ref]), rtol=1e-10, atol=0)
+        n_sparse = int((keys != keys.max()).sum())
+        r0, _ = sim.run(0)
+        path = "tie" if r0["tie_sorts"] > 0 else "general"
+        assert path == ("tie" if n_sparse <= 8192 else "general"), (cp, n_sparse, r0["tie_sorts"])
+        seen_paths.add((path, n_sparse > 2500))
+        if cp == 150000:  # the same state through the general replay only
+            monkeypatch.setenv("MCAC_B200_TIE_MIN_N", "0")
+            gen = Simulation(text)
+            monkeypatch.delenv("MCAC_B200_TIE_MIN_N")
+            gen.upload(as_upload(st))
+            gen.sort_time_steps(st["max_time_step"])
+            gidx, gcum = gen.pick_table()
+            assert gen.run(0)[0]["tie_sorts"] == 0
+            np.testing.assert_array_equal(gidx, ref, err_msg="general replay on the same state")
+            np.testing.assert_array_equal(gcum, cum)
+            del gen
+        # ---- (c) morphology of every aggregate that was ever updated
+        consumed = consumed0 + 3 * done
+        o.set_state(st, consumed)
+        o.update_all()
+        so = o.state()
+        multi = st["agg_n_spheres"] > 1
+        assert multi.sum() == n_sparse
+        for k in ("volume", "surface", "rg", "rmax", "f_agg", "d_m", "lpm", "time_step", "dp", "dg_over_dp"):
+            np.testing.assert_allclose(st["aggregates"][k][multi], so["aggregates"][k][multi], rtol=1e-12, atol=0, err_msg=f"{k} at step {cp}")
+        # ---- (d) 200 steps in lock-step from here
+        o.set_state(st, consumed)
+        ref_recs = o.run(200)
+        rep2, recs = sim.run(200, batch=256, records=200)
+        assert rep2["steps"] == 200 and recs["rand_calls"][0] == consumed + 3
+        assert_records_match(relative_steps(recs), ref_recs, box, clock_rtol=1e-10)
+        assert rep2["events"] == int(ref_recs["merged"].sum()) and rep2["events"] >= 1
+        assert_states_match(sim.state(), o.state(), box, clock_rtol=1e-10)
+        done, events = done + 200, events + rep2["events"]
+    assert seen_paths == {("tie", False), ("tie", True), ("general", True)}, seen_paths
+
+
+def test_c4_surface_growth_1e6_through_its_first_merge():
+    """BASELINE configs[3] at size, with the overlap volume / surface update stressed: the window around the FIRST MERGE of
+    the 1e6-sphere surface-growth run — located by a scout run on the device — is replayed step by step against the oracle, which is
+    re-synchronised from the device state right after a full-update step (every aggregate's contact graph is fresh there: calcul.cpp:
+    184-206 with full_aggregate_update_frequency = 100), at least 50 steps including the merge and the alphas volume / surface of the
+    merged aggregate (aggregat.cpp:321-430)."""
+    ov = {"monomers": {"number": 1000000}, "numerics": {"n_verlet_divisions": 100, "random_seed": 42}}
+    text = ini_text(merged_config("surface_growth", ov))
+    scout = Simulation(text)
+    scout.set_stop_at_event(True)
+    rep, _ = scout.run(4000)
+    assert rep["events"] == 1, "no merge within 4000 steps"
+    merge_step = rep["steps"] - 1
+    del scout
+    # the last full update before the merge window: n_iter_without_event % 100 == 0 at steps 0, 100, 200, ... (no event yet)
+    start = ((merge_step - 40) // 100 * 100 + 1) if merge_step >= 141 else 0
+    n_replay = max(50, merge_step - start + 11)
+    sim = Simulation(text)
+    consumed0 = HostModel(text).state()["rand_consumed"]
+    o = Oracle("surface_growth", ov, construct=start == 0)
+    if start > 0:
+        r, _ = sim.run(start)
+        assert r["steps"] == start and r["events"] == 0
+        st = sim.state()
+        o.set_state(st, consumed0 + 3 * start)
+    rep2, recs = sim.run(n_replay, records=n_replay)
+    ref = o.run(n_replay)
+    box = o.scalars()["box_length"]
+    assert rep2["steps"] == len(ref) == n_replay
+    assert_records_match(relative_steps(recs), relative_steps(ref), box, clock_rtol=1e-10)
+    assert rep2["events"] == int(ref["merged"].sum()) >= 1
+    got, want = sim.state(), o.state()
+    assert_states_match(got, want, box, clock_rtol=1e-10)
+    check_structure(got)
+    merged = np.nonzero(got["agg_n_spheres"] > 1)[0]
+    assert len(merged) >= 1
+    for k in ("volume", "surface", "overlapping", "coordination_number"):
+        np.testing.assert_allclose(got["aggregates"][k][merged], want["aggregates"][k][merged], rtol=1e-12, atol=1e-300, err_msg=k)
 
 
 def test_c4_surface_growth_1e6_first_steps():

@@ -129,3 +129,54 @@ def test_fractal_law_restatements_against_the_reference():
                 np.testing.assert_allclose(nr, r, rtol=1e-6)
             checked += 1
     assert checked >= 12
+
+
+def test_oracle_resynchronised_from_a_state_continues_the_same_trajectory():
+    """orc_set_state (used by the full-size GPU tests to check late windows of a 1e6 run without replaying it from step 0 on the
+    CPU): an oracle re-created from the state of another one, RNG repositioned, must produce the very same records."""
+    from golden_lib import Golden
+    g = Golden("c3_small_seed42")
+    a = Oracle(g.base, g.overrides)
+    a.run(5000, record=False)
+    st = a.state()
+    b = Oracle(g.base, g.overrides)
+    b.set_state(st, a.counters()["rand_calls"])
+    ra, rb = a.run(3000), b.run(3000)
+    assert ra["merged"].sum() > 3
+    for f in ra.dtype.names:
+        if f == "step":
+            continue
+        np.testing.assert_array_equal(ra[f], rb[f], err_msg=f)
+    sa, sb = a.state(), b.state()
+    np.testing.assert_array_equal(sa["sphere_label"], sb["sphere_label"])
+    np.testing.assert_array_equal(sa["aggregates"]["rg"], sb["aggregates"]["rg"])
+    # Aggregate::update() of every aggregate reproduces the stored morphology from radii + relative positions alone
+    # (of every aggregate that was updated since the initial radius rescale: aggregat_list_storage.cpp:75-87 re-runs only
+    # compute_volume_surface on the monomers, so their stored Rg / time step still belong to the radii before the rescale)
+    b.update_all()
+    sc = b.state()
+    multi = sb["agg_n_spheres"] > 1
+    assert multi.sum() > 10
+    for k in ("rg", "volume", "surface", "rmax", "lpm", "time_step", "f_agg", "d_m"):
+        np.testing.assert_array_equal(sb["aggregates"][k][multi], sc["aggregates"][k][multi], err_msg=k)
+
+
+def test_oracle_resynchronised_in_growth_mode_right_after_a_full_update():
+    """Same, with surface growth (alphas volumes depend on when the contact graph was last refreshed): exact when the state is taken
+    right after a step that fully updated every aggregate (n_iter_without_event % full_aggregate_update_frequency == 0 before it)."""
+    from golden_lib import Golden
+    g = Golden("pytest_seed42")
+    a = Oracle(g.base, g.overrides)
+    a.run(448, record=False)   # step 446 merged; step 447 (n_iter_without_event == 0) fully updated every aggregate
+    st = a.state()
+    b = Oracle(g.base, g.overrides, construct=False)
+    b.set_state(st, a.counters()["rand_calls"])
+    ra, rb = a.run(1500), b.run(1500)
+    assert ra["merged"].sum() >= 3
+    for f in ra.dtype.names:
+        if f == "step":
+            continue
+        np.testing.assert_array_equal(ra[f], rb[f], err_msg=f)
+    sa, sb = a.state(), b.state()
+    for k in ("rg", "volume", "surface", "time_step", "overlapping", "coordination_number"):
+        np.testing.assert_array_equal(sa["aggregates"][k], sb["aggregates"][k], err_msg=k)
