@@ -132,7 +132,7 @@ def ensemble_reference(a, K: int, W: int, M: int) -> dict:
     def one(k: int):
         ov = {"numerics": {"random_seed": 1000 + k}, "inter_potential": {"interpotential_file": table},
               "output": {"write_between_event_frequency": 1000000000, "write_events_frequency": 1000000000}}
-        wd, _ = run_reference("classic", ov, env={"MCAC_TAP_EXIT_STEP": M * (W + K), "MCAC_TAP_CHUNK": M})
+        wd, _ = run_reference("classic", ov, env={"MCAC_TAP_EXIT_STEP": M * (W + K), "MCAC_TAP_CHUNK": M}, taskset_core=k)
         s = read_summary(wd)
         shutil.rmtree(wd, ignore_errors=True)
         ct = [0.0] + s["chunk_times"]
@@ -146,15 +146,24 @@ def ensemble_reference(a, K: int, W: int, M: int) -> dict:
     return {"value": cores * M / max(per_proc), "cores": cores, "ms_per_step": 1e3 * max(per_proc)}
 
 
+ENSEMBLE_TOTAL_STEPS = 3200  # per realization: what the unmodified reference reaches in classic.ini's own `cpu = 60` budget (3220 steps, this image)
+
+
 def ensemble_main(a, rank: int, world: int, local: int):
-    """--workload ensemble: R realizations of examples/classic.ini, realization k on rank k mod N (no communication during the run),
-    one bench step = every realization advances M MC steps; the statistic rows are all-gathered once at the end."""
+    """--workload ensemble (the default for --gpus N > 1): R realizations of examples/classic.ini (seeds 1000+k), realization k on rank
+    k mod N, no communication during the run.  Deterministic stop: an MC-step count — every realization advances exactly
+    (W + K) * M steps with M = ceil(3200 / (W + K)) unless --mc-steps is given (classic.ini's only practical stop is the wall-clock
+    `cpu = 60`, which the reference turns into ~3 220 steps on this image; physical time reached varies with the seed).  One bench
+    step = every realization advances M steps (one launch of k_ensemble_loop per round of host services); the statistic rows (K11)
+    are all-gathered over NCCL once at the end."""
     K, W = a.steps, max(a.warmup, 0)
-    M = a.mc_steps or 300
+    M = a.mc_steps or -(-ENSEMBLE_TOTAL_STEPS // max(1, W + K))
     R = a.realizations
     config = {"workload": "ensemble", "ini": "examples/classic.ini (100 monomers, growth + nucleation + external potentials), random_seed=1000+k",
-              "realizations": R, "mc_steps_per_step": M, "parallelism": f"realization k -> rank k mod {world}; replicas only",
-              "l2": "per-realization state is KB-sized; every step is launch/latency-bound, no L2 flush applies"}
+              "realizations": R, "mc_steps_per_step": M, "stop": f"MC-step count: {(W + K) * M} steps per realization",
+              "window_mc_steps": [W * M, (W + K) * M],
+              "parallelism": f"realization k -> rank k mod {world}; replicas only, one all-gather of the K11 rows at the end",
+              "l2": "per-realization state (<= 35 MB, 1024 realizations) exceeds L2 in total; the sphere sweep of a step re-reads one aggregate pair from L1/L2"}
     metric, unit = "ensemble_mc_steps_per_sec", "MC steps/s (sum over realizations)"
     if a.impl == "reference":
         if rank != 0:
@@ -168,7 +177,7 @@ def ensemble_main(a, rank: int, world: int, local: int):
                           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference",
-                                           "sample": f"{r['cores']} realizations in parallel (one process per core), {W + K} x {M} MC steps each, cpu: {cpu_model()}"},
+                                           "sample": f"{r['cores']} realizations in parallel (one pinned process per core), {W + K} x {M} MC steps each, cpu: {cpu_model()}"},
                           "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     import tempfile
@@ -209,8 +218,9 @@ def ensemble_main(a, rank: int, world: int, local: int):
     sampler = ClockSampler(local)
     sync_all()
     sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
-    steps_done = launches = events = 0
+    steps_done = launches = events = pair_tests = 0
     stats_s = 0.0
     d2h = 0
     rows = None
@@ -219,6 +229,7 @@ def ensemble_main(a, rank: int, world: int, local: int):
         steps_done += sum(r["steps"] for r in reps)
         launches += sum(r["kernel_launches"] for r in reps)
         events += sum(r["events"] for r in reps)
+        pair_tests += sum(r["pair_tests_sphere"] + r["pair_tests_bounding"] for r in reps)
         # the step's result: the statistic rows of every realization cross to the host (timed apart: only e2e includes it)
         t_s = time.perf_counter()
         rows = e.morphology_stats(ens.N_BINS, 2e-6)
@@ -227,8 +238,9 @@ def ensemble_main(a, rank: int, world: int, local: int):
     sync_all()
     wall_s = time.perf_counter() - t_wall
     clocks = sampler.stop()
+    del ev0, ev1
     t = torch.tensor([wall_s - stats_s, wall_s], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(steps_done), float(launches), float(events)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(steps_done), float(launches), float(events), float(pair_tests)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -237,18 +249,49 @@ def ensemble_main(a, rank: int, world: int, local: int):
     full = ens.gather_rows(rows, mine, R, dist=dist, device="cuda")
     if rank == 0:
         value = float(tot[0]) / float(t[0])
+        # the dominant kernel is k_ensemble_loop; its time is the sphere-pair sweep of the contact search (FP64-pipe-bound: both
+        # aggregates of a pair are re-read from L1/L2, 104 FP64 ops per pair test).  Peaks measured here.
+        sim0 = e.sims[0]
+        dfma = sim0.kernel_bench("fp64_dfma", reps=3)
+        dmad = sim0.kernel_bench("fp64_dmul_dadd", reps=3)
+        peak_dfma = dfma["units"] / (dfma["ms"] * 1e-3) / 1e12
+        peak_nofma = dmad["units"] / (dmad["ms"] * 1e-3) / 1e12
+        pair_rate = float(tot[3]) / float(t[0])
+        fp64_tflops = pair_rate * 104.0 / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_gbs = pair_rate * 32.0 / 1e9  # 32 B (x, y, z, r) of the candidate sphere per pair test
+        cpu_baseline = None
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                r = ensemble_reference(a, K, W, M)
+                cpu_baseline = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference",
+                                "sample": f"{r['cores']} realizations in parallel (one pinned process per core), {W + K} x {M} MC steps each "
+                                          f"(timed: the last {K} x {M}), cpu: {cpu_model()}"}
+            except Exception as ex:  # noqa: BLE001
+                cpu_baseline = {"value": None, "unit": unit, "cores": None, "kind": "reference", "sample": f"unavailable: {str(ex)[:160]}"}
         print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
                           "ms_per_step": 1e3 * float(t[0]) / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f64", "data": "synthetic", "config": dict(config, host_threads_per_rank=threads),
-                          "timing": "wall clock between device synchronisations (realizations run on independent streams), max over ranks",
-                          "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "init_s": init_s, "clocks": clocks,
+                          "timing": "wall clock between device synchronisations around the K steps (every step = rounds of one k_ensemble_loop launch + "
+                                    "host services), max over ranks",
+                          "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "pair_tests_per_sec": pair_rate, "init_s": init_s, "clocks": clocks,
                           "e2e": {"value": float(te[1]) / float(te[0]), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
-                                  "what": "mcac_ensemble_run(M steps per realization) + mcac_gpu_morphology_stats of every realization to the host, per step"},
+                                  "what": "mcac_ensemble_run(M steps per realization) + mcac_gpu_morphology_stats of every realization to the host, per step; "
+                                          "the realizations are created on the host (placement) and live in HBM from then on"},
                           "gpu_launches": int(tot[1]),
-                          "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                                       "note": "launch/latency-bound: ~25 small launches + 3 host synchronisations per MC step and realization; "
-                                               "see DESIGN.md §6 (persistent per-realization kernel = next)"},
-                          "cpu_baseline": None, "ensemble_stats": ens.summarize(full)}))
+                          "roofline": {"kernel": "k_ensemble_loop (per-realization step loop; time = ordered sphere-pair sweep of the contact search)",
+                                       "bound": "hbm", "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak, "traffic": None,
+                                       "binding": "fp64", "fp64_achieved_tflops": fp64_tflops, "fp64_peak_dfma_tflops": peak_dfma,
+                                       "fp64_peak_dmul_dadd_tflops": peak_nofma, "fp64_frac_of_dmul_dadd_peak": fp64_tflops / peak_nofma if peak_nofma else None,
+                                       "note": "algorithmic bytes = 32 B per sphere-pair test; the sweep re-reads two aggregates from L1/L2, so the binding "
+                                               "roofline is the FP64 pipe: 104 FP64 ops per pair test against the DMUL+DADD peak measured by "
+                                               "k_fp64_peak<1> (the library is built --fmad=false)"},
+                          "cpu_baseline": cpu_baseline, "ensemble_stats": ens.summarize(full)}))
     shutil.rmtree(tmp, ignore_errors=True)
     if world > 1:
         dist.destroy_process_group()
@@ -266,14 +309,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "ensemble"],
+    ap.add_argument("--workload", default=None, choices=["c3", "ensemble"],
                     help="c3: BASELINE's N=1e6 metric (default).  ensemble: --realizations independent runs of examples/classic.ini "
                          "(seeds 1000+k) sharded k -> rank k mod N, all-gather of the morphology statistics at the end")
-    ap.add_argument("--realizations", type=int, default=64)
+    ap.add_argument("--realizations", type=int, default=1024)
     ap.add_argument("--threads", type=int, default=0, help="host threads driving the realizations of one rank (default: cores / ranks, <= 32)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     K, W = a.steps, max(a.warmup, 0)
+    if a.workload is None:
+        # one GPU: BASELINE's N = 1e6 metric (the path does not shard); several GPUs: the multi-GPU workload BASELINE names, the
+        # 1024-realization ensemble of examples/classic.ini sharded over the ranks (replicas of the N = 1e6 run cannot fail to scale)
+        a.workload = "c3" if a.gpus <= 1 and world <= 1 else "ensemble"
     if a.workload == "ensemble":
         return ensemble_main(a, rank, world, local)
     config = {"workload": "c3", "ini": "validation/params_brownian.ini + number, volume_fraction=1000e-6, n_verlet_divisions=100, "

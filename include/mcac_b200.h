@@ -182,7 +182,8 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
 int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_report *report);
 /* Times one kernel of the path on the resident state (CUDA events on the handle's stream, `reps` launches after one warm-up):
  * which = 0 K2 cell rebuild, 1 K8 growth (all spheres), 2 update_partial (all aggregates), 3 full update, 4 K9 event pipeline with
- * sort, 5 without sort, 6 100 grid barriers at K9's launch shape, 7 K10 RNG fill, 8 K11 statistics.  units = items per launch. */
+ * sort, 5 without sort, 6 100 grid barriers at K9's launch shape, 7 K10 RNG fill, 8 K11 statistics, 9 / 10 FP64 pipe peak with DFMA /
+ * with DMUL + DADD (the library is built --fmad=false): units = flops per launch.  units = items per launch otherwise. */
 int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_per_launch, int64_t *units);
 /* on != 0: mcac_gpu_run returns right after the step that made an event (merge or nucleation: `event` of calcul.cpp:222), so that a
  * host loop can do what calcul() does between events (advancement.dat rows, the progress table, output files) */
@@ -216,6 +217,23 @@ int mcac_host_model_ini_echo(const mcac_host_model *m, char *buf, int64_t cap);
 int mcac_host_model_state(const mcac_host_model *m, double *sphere_fields, double *agg_fields, int64_t *agg_cells, int64_t *offsets,
                           int64_t *members, double *per_member, double *scalars /*maxradius,max_time_step,avg_npp*/,
                           int64_t *rand_consumed);
+/* --- output files of the reference (src/io/*): <prefix>_<k>.h5 (HDF5 heavy data) + <prefix>_<k>.xmf (XDMF light data) ----------- */
+/* One series = the reference's ThreadedIO for "Spheres" or "Aggregats" (threaded_io.cpp, writer.cpp:72-142): n_time_per_file grids per
+ * file pair, k zero-padded to ceil(log10(n_for_width)) + 4 digits (format.cpp:60-65).  Written by a libhdf5-free HDF5 writer
+ * (superblock v0, contiguous datasets Data0, Data1, ...: what XdmfHDF5Writer emits with deflate off).  physics = "name=value\n" lines
+ * of PhysicalModel::xmf_write (io/physical_model.cpp:30-49).  type: 0 = float64, 1 = int32, 2 = int64. */
+typedef struct mcac_io_writer mcac_io_writer;
+int mcac_io_writer_create(const char *prefix, const char *grid_name, int64_t n_time_per_file, int64_t n_for_width, const char *physics,
+                          mcac_io_writer **out);
+int mcac_io_begin_step(mcac_io_writer *w, double time);                                    /* XdmfUnstructuredGrid + XdmfTime      */
+int mcac_io_positions(mcac_io_writer *w, const double *xyz_interleaved, int64_t n_points); /* the_positions(), writer.cpp:37-43   */
+int mcac_io_attribute(mcac_io_writer *w, const char *name, int32_t type, const void *data, int64_t count, int32_t scalar_on_nodes);
+int mcac_io_end_step(mcac_io_writer *w);                                                   /* ThreadedIO::write                     */
+int mcac_io_writer_destroy(mcac_io_writer *w);                                             /* ~ThreadedIO: flushes the open file    */
+/* SphereList::save() + AggregatList::save() (io/sphere_list.cpp:36-57, io/aggregat_list.cpp:36-67) of the state resident in HBM:
+ * one grid appended to each of the two series */
+int mcac_gpu_save(mcac_gpu *h, mcac_io_writer *spheres, mcac_io_writer *aggregates);
+
 /* main(): PhysicalModel(ini) -> AggregatList(&physicalmodel) with the state resident in HBM of `device` */
 int mcac_sim_create(const char *ini_text, int device, mcac_gpu **out);
 

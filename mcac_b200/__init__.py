@@ -239,7 +239,7 @@ class Simulation:
         return rep.as_dict()
 
     KERNELS = {"cells": 0, "grow": 1, "update_partial": 2, "update_full": 3, "event_sort": 4, "event_nosort": 5, "grid_barriers_x100": 6,
-               "rng_fill": 7, "morphology_stats": 8}
+               "rng_fill": 7, "morphology_stats": 8, "fp64_dfma": 9, "fp64_dmul_dadd": 10}
 
     def kernel_bench(self, which: str, reps: int = 5) -> dict:
         ms, units = C.c_double(), C.c_int64()
@@ -273,8 +273,14 @@ class Simulation:
 class Ensemble:
     """Independent realizations of one configuration (distinct seeds) resident on one GPU and advanced concurrently."""
 
-    def __init__(self, texts: list[str], device: int = 0):
-        self.sims = [Simulation(t, device=device) for t in texts]
+    def __init__(self, texts: list[str], device: int = 0, threads: int = 16):
+        # creation = host placement + (classic.ini) parsing the interaction-potential table: the C calls release the GIL
+        from concurrent.futures import ThreadPoolExecutor
+        if len(texts) > 8 and threads > 1:
+            with ThreadPoolExecutor(threads) as ex:
+                self.sims = list(ex.map(lambda t: Simulation(t, device=device), texts))
+        else:
+            self.sims = [Simulation(t, device=device) for t in texts]
         self.L = lib()
 
     def __len__(self):

@@ -98,6 +98,8 @@ EXPORTS = [
     "mcac_gpu_set_profile", "mcac_gpu_set_interpotential", "mcac_host_alloc_pinned", "mcac_host_free_pinned", "mcac_gpu_kernel_bench", "mcac_ensemble_run", "mcac_gpu_set_stop_at_event",
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_ini_echo", "mcac_host_model_state", "mcac_sim_create",
+    "mcac_io_writer_create", "mcac_io_begin_step", "mcac_io_positions", "mcac_io_attribute", "mcac_io_end_step", "mcac_io_writer_destroy",
+    "mcac_gpu_save",
 ]
 
 
@@ -153,6 +155,13 @@ def lib() -> C.CDLL:
         L.mcac_host_model_ini_echo.argtypes = [vp, C.c_char_p, C.c_int64]
         L.mcac_host_model_state.argtypes = [vp] + [vp] * 8
         L.mcac_sim_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.mcac_io_writer_create.argtypes = [C.c_char_p, C.c_char_p, i64, i64, C.c_char_p, C.POINTER(vp)]
+        L.mcac_io_begin_step.argtypes = [vp, C.c_double]
+        L.mcac_io_positions.argtypes = [vp, vp, i64]
+        L.mcac_io_attribute.argtypes = [vp, C.c_char_p, C.c_int32, vp, i64, C.c_int32]
+        L.mcac_io_end_step.argtypes = [vp]
+        L.mcac_io_writer_destroy.argtypes = [vp]
+        L.mcac_gpu_save.argtypes = [vp, vp, vp]
         _lib = L
     return _lib
 

@@ -18,6 +18,7 @@
 
 #include "../../include/mcac_b200.h"
 #include "mcac_kernels.cuh"
+#include "mcac_steploop.cuh"
 
 using namespace mcacb;
 
@@ -121,6 +122,11 @@ struct mcac_gpu {
     int wide_parity = 0;
     int search_group = -1;    // lanes per query of K1 (4, 8, 16, 32; 0 = wide kernel only; -1 = by launch size)
     int search_min_blocks = 8;  // occupancy target (__launch_bounds__ min blocks) of the narrow-group kernels
+    // per-realization step loop (mcac_steploop.cuh): the general step of calcul() as one persistent CTA
+    bool fused = true;            // MCAC_B200_NO_LOOP=1: every general step goes through the multi-launch sequence
+    int fused_max_slots = 16384;  // MCAC_B200_LOOP_MAX_SLOTS: larger aggregate tables leave the loop to the multi-launch path
+    LoopState *loop_dev = nullptr, *loop_host = nullptr;
+    long long loop_launches = 0, loop_steps = 0;
     void *stage = nullptr;  // device staging of the host-layout arrays at the upload / download boundary
     size_t stage_bytes = 0;
 };
@@ -180,6 +186,7 @@ int alloc_persistent(mcac_gpu *h) {
     TRY(dev_alloc_persistent(h, &h->partials, 3 * 1024));
     TRY(dev_alloc_persistent(h, &h->merged_flag, 4));
     TRY(dev_alloc_persistent(h, &h->stats_dev, 4096));
+    TRY(dev_alloc_persistent(h, &h->loop_dev, 1));
     TRY(dev_alloc_persistent(h, &h->stats_part, 8 * (size_t)kStatsMaxBlocks));
     TRY(dev_alloc_persistent(h, &h->stats_hist, (size_t)kStatsHistCap));
     h->alt.sc = d.sc;
@@ -926,6 +933,68 @@ int search_launch(mcac_gpu *h, int nq) {
     TRY(join_cells(h));
     return search_kernels(h, nq, h->q_slot, h->q_dir, h->q_dist, h->q_res);
 }
+
+// ---- per-realization step loop (mcac_steploop.cuh) --------------------------------------------------------------------------
+bool is_speculative(const mcac_gpu *h) {
+    return h->prm.pick_method == MCAC_PICK_RANDOM && h->prm.with_collisions && !h->prm.with_surface_reactions && !h->prm.with_potentials &&
+           !h->prm.with_nucleation;
+}
+bool loop_usable(const mcac_gpu *h) {
+    return h->fused && !h->debug_sync && !h->profile && h->sc_host.n_agg_slots <= h->fused_max_slots &&
+           h->sc_host.n_agg <= h->cum_sequential_max;
+}
+void loop_fill_args(mcac_gpu *h, LoopArgs &a, long long max_steps, mcac_step_record *rec, long long rec_cap, long long rec_base) {
+    const mcac_params &p = h->prm;
+    a.q_slot = h->q_slot; a.q_dir = h->q_dir; a.q_dist = h->q_dist; a.q_res = h->q_res;
+    a.sb = h->sortb;
+    a.sorted_label = h->sorted_label;
+    a.scan_tmp = h->scan_tmp;
+    a.alt_posr = h->alt.s_posr; a.alt_relv = h->alt.s_relv; a.alt_surf = h->alt.s_surf; a.alt_veff = h->alt.s_veff;
+    a.alt_seff = h->alt.s_seff; a.alt_dcen = h->alt.s_dcen; a.alt_id = h->alt.s_id; a.alt_charge = h->alt.s_charge;
+    a.rec = rec; a.rec_cap = rec_cap; a.rec_base = rec_base;
+    a.max_steps = max_steps;
+    a.dup_threshold = h->dup_threshold;
+    a.full_freq = std::max<long long>(1, p.full_aggregate_update_frequency);
+    a.with_nucleation = p.with_nucleation; a.with_potentials = p.with_potentials; a.growth = p.with_surface_reactions;
+    a.individual = p.individual_surf_reactions; a.pick_last = p.pick_method == MCAC_PICK_LAST ? 1 : 0;
+    a.with_collisions = p.with_collisions; a.with_domain_duplication = p.with_domain_duplication;
+    a.cum_sequential_max = h->cum_sequential_max;
+    a.stable = p.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
+    a.depth_override = h->sort_depth_override;
+    a.pick_valid = h->pick_valid ? 1 : 0; a.labels_valid = h->labels_valid ? 1 : 0;
+    a.stop_at_event = h->stop_at_event ? 1 : 0;
+    a.max_slots = h->fused_max_slots;
+    a.out = h->loop_dev;
+}
+// host-side bookkeeping after a loop launch: the pool may have been compacted (buffers swapped), validity flags
+void loop_apply(mcac_gpu *h, const LoopState &ls) {
+    if (ls.flipped) {
+        DevState &d = h->d;
+        std::swap(d.s_posr, h->alt.s_posr); std::swap(d.s_relv, h->alt.s_relv); std::swap(d.s_surf, h->alt.s_surf);
+        std::swap(d.s_veff, h->alt.s_veff); std::swap(d.s_seff, h->alt.s_seff); std::swap(d.s_dcen, h->alt.s_dcen);
+        std::swap(d.s_id, h->alt.s_id); std::swap(d.s_charge, h->alt.s_charge);
+    }
+    h->pick_valid = ls.pick_valid != 0;
+    h->labels_valid = ls.labels_valid != 0;
+    h->cells_valid = false;
+    h->loop_launches++;
+    h->loop_steps += ls.steps;
+}
+// slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up.  This renumbers the
+// aggregate slots (slot = label again), so it must come BEFORE the pick table of the step is built.
+int regrow_tables(mcac_gpu *h) {
+    HostState hs;
+    TRY(download(h, hs));
+    const Scalars keep = h->sc_host;
+    h->uploaded = false;
+    TRY(upload(h, hs, keep.maxradius, keep.max_time_step, false));
+    Scalars &sc = h->sc_host;
+    const int n_slots = sc.n_agg_slots, pool = sc.pool_top;
+    sc = keep;
+    sc.n_agg_slots = n_slots; sc.pool_top = pool;
+    TRY(push_scalars(h));
+    return E_OK;
+}
 }  // namespace
 
 // =================================================================================================
@@ -958,6 +1027,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         CK(cudaEventCreateWithFlags(&h->ev_cycle[k], cudaEventDisableTiming));
     }
     CK(cudaMallocHost((void **)&h->h_flags, 4 * sizeof(int)));
+    CK(cudaMallocHost((void **)&h->loop_host, sizeof(LoopState)));
     fill_devstate_params(h);
     TRY(alloc_persistent(h));
     {
@@ -971,6 +1041,8 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_BIG_NPP")) h->big_search_npp = atof(e);
         if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
         if (const char *e = getenv("MCAC_B200_SORT_DEPTH")) h->sort_depth_override = std::max(0, atoi(e));
+        if (getenv("MCAC_B200_NO_LOOP")) h->fused = false;
+        if (const char *e = getenv("MCAC_B200_LOOP_MAX_SLOTS")) h->fused_max_slots = std::max(1, atoi(e));
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
@@ -1034,6 +1106,7 @@ int mcac_gpu_destroy(mcac_gpu *h) {
         if (h->ev_cycle[k]) cudaEventDestroy(h->ev_cycle[k]);
     }
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->loop_host) cudaFreeHost(h->loop_host);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1355,8 +1428,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         return E_INPUT;
     }
     // speculative batches need a pick sequence that is fixed between events: random pick, no per-step growth / redraws / nucleation
-    const bool speculative = h->prm.pick_method == MCAC_PICK_RANDOM && h->prm.with_collisions && !h->prm.with_surface_reactions &&
-                             !h->prm.with_potentials && !h->prm.with_nucleation;
+    const bool speculative = is_speculative(h);
     const int B = !speculative ? 1 : (batch > 0 ? std::min<int>(batch, kMaxBatch) : 256);
     TRY(pull_scalars(h));
     const Scalars at_start = h->sc_host;
@@ -1374,7 +1446,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
     CK(cudaEventRecord(ev0, h->stream));
     int64_t steps = 0, batches = 0, sorts = 0, dups = 0, nucleated_total = 0;
     int rc = E_OK;
-    bool fin = false, need_refresh = false, fallback_sorted = false;
+    bool fin = false, need_refresh = false, fallback_sorted = false, loop_too_big = false;
     while (!speculative && steps < max_steps) {  // ---- general step: one MC step per iteration, calcul() order
         if (finished(h)) { fin = true; break; }
         const mcac_params &p = h->prm;
@@ -1384,23 +1456,36 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             dups++;
             DBG("duplicate");
         }
+        if (!loop_too_big && loop_usable(h)) {
+            // the per-realization step loop: one persistent CTA walks the steps until the call is served or the realization needs
+            // the host (duplication, table regrow, more staged draws) — mcac_steploop.cuh
+            if ((rc = ensure_rng(h, h->sc_host.rand_pos + 8192 + 64 + 31)) != E_OK) break;
+            LoopArgs la;
+            loop_fill_args(h, la, max_steps - steps, (records && n_records > 0) ? h->rec_dev : nullptr, n_records, steps);
+            k_step_loop<<<1, kLoopThreads, 0, h->stream>>>(h->d, la);
+            h->launches++;
+            if (cudaGetLastError() != cudaSuccess) { h->err = "step loop launch failed"; rc = E_UNKNOWN; break; }
+            if (cudaMemcpyAsync(h->loop_host, h->loop_dev, sizeof(LoopState), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = E_UNKNOWN; break; }
+            if ((rc = pull_scalars(h)) != E_OK) break;
+            const LoopState ls = *h->loop_host;
+            loop_apply(h, ls);
+            steps += ls.steps;
+            batches += ls.steps;
+            sorts += ls.sorts;
+            nucleated_total += ls.nucleated;
+            if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rc = device_error(h, h->sc_host, "mcac_gpu_run"); break; }
+            if (ls.exit_reason == LOOP_FINISHED) { fin = true; break; }
+            if (ls.exit_reason == LOOP_EVENT_STOP) break;
+            if (ls.exit_reason == LOOP_NEED_REGROW) { if ((rc = regrow_tables(h)) != E_OK) break; }
+            if (ls.exit_reason == LOOP_TOO_BIG) loop_too_big = true;
+            // LOOP_NEED_DUP / LOOP_NEED_RNG / LOOP_STEPS_DONE: served at the top of the next iteration
+            continue;
+        }
         if (h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph)
             if ((rc = compact_pool(h)) != E_OK) break;
         DBG("compact_pool");
-        // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up.  This renumbers the
-        // aggregate slots (slot = label again), so it must come BEFORE the pick table of this step is built.
-        if (p.with_nucleation && (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64)) {
-            HostState hs;
-            if ((rc = download(h, hs)) != E_OK) break;
-            const Scalars keep = h->sc_host;
-            h->uploaded = false;
-            if ((rc = upload(h, hs, keep.maxradius, keep.max_time_step, false)) != E_OK) break;
-            Scalars &sc = h->sc_host;
-            const int n_slots = sc.n_agg_slots, pool = sc.pool_top;
-            sc = keep;
-            sc.n_agg_slots = n_slots; sc.pool_top = pool;
-            if ((rc = push_scalars(h)) != E_OK) break;
-        }
+        if (p.with_nucleation && (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64))
+            if ((rc = regrow_tables(h)) != E_OK) break;
         if (!pick_last && (h->sc_host.event || growth || !h->pick_valid)) {
             if ((rc = event_pipeline(h, false, false, true)) != E_OK) break;
             sorts++;
@@ -1830,7 +1915,7 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
 // Per-kernel timings on the resident state (bench.py's per-kernel roofline table; profiles/).  `which`:
 //  0 K2 cell list rebuild, 1 K8 growth of every sphere (dt = 0), 2 K6/K7 update_partial of every aggregate, 3 K5-K7 full update,
 //  4 K9 event pipeline with sort, 5 event pipeline without sort (labels + refresh + totals), 6 100 grid barriers at K9's launch shape,
-//  7 K10 RNG fill (kRngBuf draws), 8 K11 morphology statistics.
+//  7 K10 RNG fill (kRngBuf draws), 8 K11 morphology statistics, 9 / 10 FP64 pipe peak (DFMA / DMUL+DADD; units = flops).
 // Growth / update rewrite derived fields from the resident radii (a replayed trajectory should not continue from this state).
 int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_out, int64_t *units_out) {
     CK(cudaSetDevice(h->device));
@@ -1878,6 +1963,14 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_o
             k_morphology_stats<<<std::min(kStatsMaxBlocks, std::max(1, div_up(sc.n_agg_slots, 256))), 256, 0, h->stream>>>(h->d, 24, 2e-6, h->stats_dev, h->stats_part, h->stats_hist);
             units = sc.n_agg;
             break;
+        case 9:
+        case 10: {  // FP64 pipe peaks: 9 = DFMA, 10 = DMUL + DADD (this library is built --fmad=false); units = flops per launch
+            const int iters = 4096, blocks = h->n_sm * 8;
+            if (which == 9) k_fp64_peak<0><<<blocks, 256, 0, h->stream>>>(h->stats_dev, iters, 1.0);
+            else k_fp64_peak<1><<<blocks, 256, 0, h->stream>>>(h->stats_dev, iters, 1.0);
+            units = (int64_t)blocks * 256 * 8 * 2 * iters;
+            break;
+        }
         default: h->err = "kernel_bench: unknown kernel"; rc = E_INPUT;
         }
     }
@@ -1897,20 +1990,178 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_o
     return rc;
 }
 
-// Ensemble of independent realizations (the path does not shard, replicas do): `threads` host threads drive the
-// handles concurrently, each handle on its own CUDA stream with its own RNG stream, so the small per-step kernels of different
-// realizations overlap on the device.  Handle k is driven by thread k mod threads; no data is shared between handles.
+// Ensemble of independent realizations (the path does not shard, replicas do).
+//
+// Realizations whose steps run in the per-realization step loop (general step: growth / potentials / nucleation / pick_last; the
+// ensemble of examples/classic.ini) are advanced by ONE launch of k_ensemble_loop per round: the CTAs of the grid take realizations
+// from a queue and walk their MC steps without the host, so the device holds as many realizations in flight as it has CTA slots.  A
+// round ends when every realization has either done its steps or needs the host (domain duplication, table regrow, more staged
+// draws); `threads` host threads serve those in parallel (each handle has its own stream), then the next round starts.
+// Other realizations (speculative batches of the collision-only configurations, or MCAC_B200_NO_LOOP) are driven by the host threads,
+// handle k on thread k mod threads.  No data is shared between handles; the first non-zero error code of any realization is returned.
+static void fill_report_basic(mcac_gpu *h, const Scalars &at_start, long long launches0, mcac_run_report *report, int64_t steps, int64_t dups,
+                              int64_t sorts, int64_t nucleated, bool fin) {
+    const Scalars &sc = h->sc_host;
+    std::memset(report, 0, sizeof(*report));
+    report->steps = steps;
+    report->events = sc.total_events - at_start.total_events;
+    report->searches = sc.searches - at_start.searches;
+    report->pair_tests_sphere = sc.pair_sphere - at_start.pair_sphere;
+    report->pair_tests_bounding = sc.pair_bounding - at_start.pair_bounding;
+    report->batches = steps;
+    report->duplications = dups;
+    report->sorts = sorts;
+    report->kernel_launches = h->launches - launches0;
+    report->n_aggregates = sc.n_agg;
+    report->n_spheres = sc.n_sph;
+    report->finished = (fin || finished(h)) ? 1 : 0;
+    report->time = sc.time;
+    report->box_length = sc.box_length;
+    report->avg_npp = sc.avg_npp;
+    report->max_time_step = sc.max_time_step;
+    report->volume_fraction = sc.volume_fraction;
+    report->n_iter_without_event = sc.n_iter_without_event;
+    report->nucleated = nucleated;
+    report->total_volume = sc.total_volume;
+    report->total_surface = sc.total_surface;
+}
+
 int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t batch, int32_t threads, mcac_run_report *reports) {
     if (!handles || n < 1) return E_INPUT;
     const int T = std::max(1, std::min<int>(threads, n));
     std::vector<int> rcs((size_t)n, E_OK);
-    auto work = [&](int t) {
-        for (int k = t; k < n; k += T) rcs[(size_t)k] = mcac_gpu_run(handles[k], max_steps, batch, nullptr, 0, reports ? reports + k : nullptr);
+    auto parallel_for = [&](const std::vector<int> &items, auto &&fn) {
+        const int W = std::max(1, std::min<int>(T, (int)items.size()));
+        auto work = [&](int t) { for (size_t i = (size_t)t; i < items.size(); i += (size_t)W) fn(items[i]); };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < W; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
     };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < T; t++) pool.emplace_back(work, t);
-    work(0);
-    for (auto &th : pool) th.join();
+    // ---- realizations that take the step loop, all on one device
+    std::vector<int> loop_set, host_set;
+    for (int k = 0; k < n; k++) {
+        mcac_gpu *h = handles[k];
+        const bool ok = h && h->uploaded && !is_speculative(h) && h->fused && !h->debug_sync && !h->profile && !h->stop_at_event &&
+                        h->device == handles[0]->device &&
+                        !(h->prm.with_external_potentials && h->prm.with_potentials && !h->d.ip_ebar);
+        (ok ? loop_set : host_set).push_back(k);
+    }
+    if (!host_set.empty())
+        parallel_for(host_set, [&](int k) { rcs[(size_t)k] = mcac_gpu_run(handles[k], max_steps, batch, nullptr, 0, reports ? reports + k : nullptr); });
+    if (!loop_set.empty()) {
+        const int m = (int)loop_set.size();
+        cudaSetDevice(handles[loop_set[0]]->device);
+        struct Track { Scalars at_start; long long launches0; int64_t steps = 0, dups = 0, sorts = 0, nucleated = 0; bool fin = false, host_only = false; };
+        std::vector<Track> tr((size_t)m);
+        parallel_for(loop_set, [&](int k) { cudaSetDevice(handles[k]->device); rcs[(size_t)k] = pull_scalars(handles[k]); });
+        for (int i = 0; i < m; i++) { tr[(size_t)i].at_start = handles[loop_set[(size_t)i]]->sc_host; tr[(size_t)i].launches0 = handles[loop_set[(size_t)i]]->launches; }
+        cudaStream_t es = nullptr;
+        DevState *ds_dev = nullptr;
+        LoopArgs *as_dev = nullptr;
+        int *next_dev = nullptr;
+        std::vector<DevState> ds_host((size_t)m);
+        std::vector<LoopArgs> as_host((size_t)m);
+        int rc_all = E_OK;
+        if (cudaStreamCreateWithFlags(&es, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void **)&ds_dev, sizeof(DevState) * (size_t)m) != cudaSuccess ||
+            cudaMalloc((void **)&as_dev, sizeof(LoopArgs) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&next_dev, sizeof(int)) != cudaSuccess)
+            rc_all = E_UNKNOWN;
+        int occ = 1, n_sm = handles[loop_set[0]]->n_sm;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_loop, kLoopThreads, 0);
+        while (rc_all == E_OK) {
+            // ---- host services of the round (in parallel): what the loop asked for, or what calcul() does at the loop top
+            std::vector<int> active;  // indices into loop_set
+            for (int i = 0; i < m; i++) {
+                const int k = loop_set[(size_t)i];
+                if (rcs[(size_t)k] == E_OK && !tr[(size_t)i].fin && tr[(size_t)i].steps < max_steps) active.push_back(i);
+            }
+            if (active.empty()) break;
+            parallel_for(active, [&](int i) {
+                const int k = loop_set[(size_t)i];
+                mcac_gpu *h = handles[k];
+                Track &t = tr[(size_t)i];
+                cudaSetDevice(h->device);
+                int rc = E_OK;
+                if (finished(h)) { t.fin = true; return; }
+                const mcac_params &p = h->prm;
+                if (h->sc_host.event && p.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(p.u_sg < 0.0)) {
+                    rc = duplicate(h);
+                    t.dups++;
+                }
+                if (rc == E_OK && p.with_nucleation &&
+                    (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64))
+                    rc = regrow_tables(h);
+                if (rc == E_OK) rc = ensure_rng(h, h->sc_host.rand_pos + 8192 + 64 + 31);
+                if (rc == E_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = E_UNKNOWN;
+                t.host_only = !loop_usable(h);
+                rcs[(size_t)k] = rc;
+            });
+            // realizations that outgrew the loop finish on the host-driven path
+            std::vector<int> big, run;
+            for (int i : active) {
+                const int k = loop_set[(size_t)i];
+                if (rcs[(size_t)k] != E_OK || tr[(size_t)i].fin) continue;
+                (tr[(size_t)i].host_only ? big : run).push_back(i);
+            }
+            if (!big.empty())
+                parallel_for(big, [&](int i) {
+                    const int k = loop_set[(size_t)i];
+                    mcac_run_report rep{};
+                    rcs[(size_t)k] = mcac_gpu_run(handles[k], max_steps - tr[(size_t)i].steps, batch, nullptr, 0, &rep);
+                    tr[(size_t)i].steps += rep.steps; tr[(size_t)i].dups += rep.duplications; tr[(size_t)i].sorts += rep.sorts;
+                    tr[(size_t)i].nucleated += rep.nucleated;
+                    if (rep.finished || rep.steps == 0) tr[(size_t)i].fin = true;
+                });
+            if (run.empty()) continue;
+            // ---- one launch for the whole round
+            const int nr = (int)run.size();
+            for (int j = 0; j < nr; j++) {
+                mcac_gpu *h = handles[loop_set[(size_t)run[(size_t)j]]];
+                ds_host[(size_t)j] = h->d;
+                loop_fill_args(h, as_host[(size_t)j], max_steps - tr[(size_t)run[(size_t)j]].steps, nullptr, 0, 0);
+            }
+            const int grid = std::max(1, std::min(nr, n_sm * std::max(1, occ)));
+            if (cudaMemcpyAsync(ds_dev, ds_host.data(), sizeof(DevState) * (size_t)nr, cudaMemcpyHostToDevice, es) != cudaSuccess ||
+                cudaMemcpyAsync(as_dev, as_host.data(), sizeof(LoopArgs) * (size_t)nr, cudaMemcpyHostToDevice, es) != cudaSuccess ||
+                cudaMemsetAsync(next_dev, 0, sizeof(int), es) != cudaSuccess) { rc_all = E_UNKNOWN; break; }
+            k_ensemble_loop<<<grid, kLoopThreads, 0, es>>>(ds_dev, as_dev, nr, next_dev);
+            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(es) != cudaSuccess) {
+                for (int j = 0; j < nr; j++) {
+                    mcac_gpu *h = handles[loop_set[(size_t)run[(size_t)j]]];
+                    h->err = std::string("ensemble step loop: ") + cudaGetErrorString(cudaGetLastError());
+                }
+                rc_all = E_UNKNOWN;
+                break;
+            }
+            // ---- read every realization back (its own stream; the launch above is complete)
+            parallel_for(run, [&](int i) {
+                const int k = loop_set[(size_t)i];
+                mcac_gpu *h = handles[k];
+                Track &t = tr[(size_t)i];
+                cudaSetDevice(h->device);
+                h->launches++;
+                if (cudaMemcpyAsync(h->loop_host, h->loop_dev, sizeof(LoopState), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rcs[(size_t)k] = E_UNKNOWN; return; }
+                if ((rcs[(size_t)k] = pull_scalars(h)) != E_OK) return;
+                const LoopState ls = *h->loop_host;
+                loop_apply(h, ls);
+                t.steps += ls.steps; t.sorts += ls.sorts; t.nucleated += ls.nucleated;
+                if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rcs[(size_t)k] = device_error(h, h->sc_host, "mcac_ensemble_run"); return; }
+                if (ls.exit_reason == LOOP_FINISHED) t.fin = true;
+                if (ls.exit_reason == LOOP_STEPS_DONE && ls.steps == 0 && t.steps < max_steps) { h->err = "step loop made no progress"; rcs[(size_t)k] = E_UNKNOWN; }
+            });
+        }
+        if (es) cudaStreamDestroy(es);
+        if (ds_dev) cudaFree(ds_dev);
+        if (as_dev) cudaFree(as_dev);
+        if (next_dev) cudaFree(next_dev);
+        for (int i = 0; i < m; i++) {
+            const int k = loop_set[(size_t)i];
+            if (rc_all != E_OK && rcs[(size_t)k] == E_OK) rcs[(size_t)k] = rc_all;
+            if (reports && rcs[(size_t)k] == E_OK)
+                fill_report_basic(handles[k], tr[(size_t)i].at_start, tr[(size_t)i].launches0, reports + k, tr[(size_t)i].steps, tr[(size_t)i].dups,
+                                  tr[(size_t)i].sorts, tr[(size_t)i].nucleated, tr[(size_t)i].fin);
+        }
+    }
     int rc = E_OK;
     for (int k = 0; k < n; k++) if (rcs[(size_t)k] != E_OK && rc == E_OK) rc = rcs[(size_t)k];
     return rc;

@@ -88,9 +88,7 @@ __global__ void k_rng_fill(GlibcRandState *st, int *out, int n) {  // n multiple
 // K9 — pick: one thread per speculative step j reads its three draws (pick, theta, phi), does
 // pick_random (lower_bound on the cumulative table, aggregat_list.cpp:59-66) and random_direction.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir, double *q_dist) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nq) return;
+__device__ __forceinline__ void dev_prepare_query(const DevState &d, int j, int *q_slot, double *q_dir, double *q_dist) {
     Scalars &sc = *d.sc;
     const long long p = sc.rand_pos + 3LL * j - d.rng_buf_base;
     if (p < 0 || p + 2 >= d.rng_buf_n) {  // the host did not stage these draws: refuse instead of reading outside the buffer
@@ -138,6 +136,11 @@ __global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir
     q_dir[3 * j + 2] = dir.z;
     q_dist[j] = slot >= 0 ? d.a_lpm[slot] : 0.;
 }
+__global__ void k_prepare_queries(DevState d, int nq, int *q_slot, double *q_dir, double *q_dist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    dev_prepare_query(d, j, q_slot, q_dir, q_dist);
+}
 // explicit queries given by label (the per-call C ABI)
 __global__ void k_labels_to_slots(DevState d, int nq, const long long *labels, int *q_slot) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,12 +176,16 @@ struct BigSearch {
     double t_best[kBigTiles];
     long long t_pair[kBigTiles];
 };
-template <int kPhase>  // 0: the whole search in this CTA; 1: phase 1 only -> `big`; 3: phases 2' (tile reduction) + 3 from `big`
+// kPhase 0: the whole search in this CTA; 1: phase 1 only -> `big`; 3: phases 2' (tile reduction) + 3 from `big`.  NT = threads of the
+// CTA.  kOrdered (with kPhase 0): the eligible suspects are ranked in the multimap order FIRST and swept in that order by the whole CTA
+// with the reference's two breaks (aggregat_list.cpp:459-482), so suspects the reference never examines are never swept — the form the
+// per-realization step loop uses, where a search between 10^2..10^3-sphere aggregates is most of a step.
+template <int kPhase, int NT = kSearchThreads, bool kOrdered = false>
 __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const int *__restrict__ q_slot,
                                                 const double *__restrict__ q_dir, const double *__restrict__ q_dist,
                                                 SearchResult *__restrict__ out, BigSearch *__restrict__ big = nullptr) {
-    __shared__ int seg_beg[kSearchThreads];
-    __shared__ int seg_pre[kSearchThreads + 1];
+    __shared__ int seg_beg[NT];
+    __shared__ int seg_pre[NT + 1];
     __shared__ int warp_sums[32];
     __shared__ int c_slot[kCandCap];
     __shared__ double c_db[kCandCap];
@@ -188,7 +195,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
     __shared__ int c_order[kCandCap];
     __shared__ int s_count, s_nb;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSearchThreads >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const int slot = q_slot[q];
     SearchResult res;
     res.distance = INFINITY;
@@ -217,7 +224,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
     const int ks = wrap_cell(rg.lo[2], n_div);
     const bool wraps = ks + nk > n_div;
     const int nseg = ni * nj * (wraps ? 2 : 1);
-    for (int seg0 = 0; seg0 < nseg; seg0 += kSearchThreads) {
+    for (int seg0 = 0; seg0 < nseg; seg0 += NT) {
         int len = 0, beg = 0;
         const int s = seg0 + tid;
         if (s < nseg) {
@@ -236,10 +243,10 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
         const int pre = block_exclusive_scan(len, &total, warp_sums);
         seg_beg[tid] = beg;
         seg_pre[tid] = pre;
-        if (tid == 0) seg_pre[kSearchThreads] = total;
+        if (tid == 0) seg_pre[NT] = total;
         __syncthreads();
-        for (int f = tid; f < total; f += kSearchThreads) {
-            int lo = 0, hi = kSearchThreads;  // last segment whose prefix <= f
+        for (int f = tid; f < total; f += NT) {
+            int lo = 0, hi = NT;  // last segment whose prefix <= f
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (seg_pre[mid] <= f) lo = mid; else hi = mid;
@@ -265,7 +272,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
         __syncthreads();
     }
     } else {  // the eligible suspects were left in `big` by phase 1
-        for (int t = tid; t < big->m; t += kSearchThreads) { c_slot[t] = big->c_slot[t]; c_db[t] = big->c_db[t]; c_key[t] = big->c_key[t]; }
+        for (int t = tid; t < big->m; t += NT) { c_slot[t] = big->c_slot[t]; c_db[t] = big->c_db[t]; c_key[t] = big->c_key[t]; }
         if (tid == 0) { s_count = big->m_all; s_nb = big->nb; }
         __syncthreads();
     }
@@ -274,9 +281,71 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
     if (m_all > d.cand_cap) res.status = 1;  // more eligible suspects than the shared-memory list holds: the first contact is unknown
 
     const int n_src = d.a_n[slot], off_src = d.a_off[slot];
+    if (kPhase == 0 && kOrdered) {
+        __shared__ double o_best[32];
+        __shared__ long long o_pair[32];
+        for (int t = tid; t < m; t += NT) {
+            const double db = c_db[t];
+            const unsigned long long key = c_key[t];
+            int rank = 0;
+            for (int u = 0; u < m; u++) {
+                const double du = c_db[u];
+                rank += (du < db || (du == db && c_key[u] < key)) ? 1 : 0;
+            }
+            c_order[rank] = t;
+        }
+        __syncthreads();
+        double closest = INFINITY;  // the scan state is kept identically by every thread
+        int who = -1;
+        long long who_pair = 0, examined = 0;
+        for (int r = 0; r < m; r++) {
+            const int t = c_order[r];
+            if (closest <= 0.) break;
+            if (closest < c_db[t]) break;
+            const int o = c_slot[t];
+            const int n_o = d.a_n[o], off_o = d.a_off[o];
+            const long long npairs = (long long)n_src * n_o;
+            double best = INFINITY;
+            long long best_p = npairs;
+            // pair p = i * n_o + j (moving sphere i outer, other sphere j inner: the reference's visiting order), NT pairs at a time
+            const int qs = NT / n_o, rs = NT % n_o;
+            int i = tid / n_o, j = tid % n_o;
+            for (long long p = tid; p < npairs; p += NT) {
+                const double4 a = d.s_posr[off_src + i];
+                const double4 b = d.s_posr[off_o + j];
+                const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+                if (c < best) { best = c; best_p = p; }
+                j += rs; i += qs;
+                if (j >= n_o) { j -= n_o; i++; }
+            }
+            warp_argmin(best, best_p);
+            if (lane == 0) { o_best[warp] = best; o_pair[warp] = best_p; }
+            __syncthreads();
+            best = o_best[0]; best_p = o_pair[0];
+            for (int w = 1; w < nwarps; w++)
+                if (o_best[w] < best || (o_best[w] == best && o_pair[w] < best_p)) { best = o_best[w]; best_p = o_pair[w]; }
+            __syncthreads();
+            examined += npairs;
+            if (best < closest) { closest = best; who = t; who_pair = best_p; }
+        }
+        if (tid == 0) {
+            res.n_bounding = s_nb;
+            res.n_sphere_pairs = examined;
+            if (who >= 0) {
+                const int o = c_slot[who];
+                const int n_o = d.a_n[o];
+                res.distance = closest;
+                res.moving_slot = off_src + (int)(who_pair / n_o);
+                res.other_slot = d.a_off[o] + (int)(who_pair % n_o);
+                res.other_agg = o;
+            }
+            out[q] = res;
+        }
+        return;
+    }
     if (kPhase == 1) {  // hand the suspects and the tile partition of their sphere pairs to the grid-wide sweep
         __syncthreads();
-        for (int t = tid; t < m; t += kSearchThreads) { big->c_slot[t] = c_slot[t]; big->c_db[t] = c_db[t]; big->c_key[t] = c_key[t]; }
+        for (int t = tid; t < m; t += NT) { big->c_slot[t] = c_slot[t]; big->c_db[t] = c_db[t]; big->c_key[t] = c_key[t]; }
         if (tid == 0) {
             long long total = 0;
             for (int t = 0; t < m; t++) total += (long long)n_src * d.a_n[c_slot[t]];
@@ -297,7 +366,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
     }
     // ---- phase 2: exact sphere-sphere sweep, one warp per eligible aggregate
     if (kPhase == 3) {  // tiles of one suspect are in ascending pair order: strict `<` keeps the first minimum
-        for (int k = tid; k < m; k += kSearchThreads) {
+        for (int k = tid; k < m; k += NT) {
             double best = INFINITY;
             long long best_p = (long long)n_src * d.a_n[c_slot[k]];
             for (long long t = big->tile_begin[k]; t < big->tile_begin[k + 1]; t++)
@@ -325,7 +394,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
     __syncthreads();
 
     // ---- phase 3: multimap order + the reference's scan with its two breaks (aggregat_list.cpp:459-482)
-    for (int t = tid; t < m; t += kSearchThreads) {
+    for (int t = tid; t < m; t += NT) {
         const double db = c_db[t];
         const unsigned long long key = c_key[t];
         int rank = 0;
@@ -1386,7 +1455,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
 // order of calcul() (src/calcul.cpp:93-234): move + clocks here, then K8 growth, then the deferred merge, then updates.
 // ------------------------------------------------------------------------------------------------
 // AggregatList::pick_last (aggregat_list.cpp:67-81): first minimum of proper_time in label (= slot) order
-__global__ void __launch_bounds__(1024) k_pick_last(DevState d, int *q_slot) {
+__device__ __forceinline__ void dev_pick_last(const DevState &d, int *q_slot) {
     __shared__ double sv[32];
     __shared__ int si[32];
     const int n = d.sc->n_agg_slots;
@@ -1411,13 +1480,18 @@ __global__ void __launch_bounds__(1024) k_pick_last(DevState d, int *q_slot) {
         q_slot[0] = who;
     }
 }
-// direction (2 draws) + lpm for an already picked aggregate (PICK_LAST, or a re-drawn orientation)
-__global__ void k_prepare_direction(DevState d, int *q_slot, double *q_dir, double *q_dist, long long draw_offset) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(1024) k_pick_last(DevState d, int *q_slot) { dev_pick_last(d, q_slot); }
+// direction (2 draws) + lpm for an already picked aggregate (PICK_LAST, or a re-drawn orientation); thread 0 of the CTA
+__device__ __forceinline__ void dev_prepare_direction(const DevState &d, int *q_slot, double *q_dir, double *q_dist, long long draw_offset) {
+    if (threadIdx.x != 0) return;
     const long long p = d.sc->rand_pos + draw_offset - d.rng_buf_base;
     const Vec3 dir = direction_from_draws(uniform_from_rand(d.rng_buf[p]), uniform_from_rand(d.rng_buf[p + 1]));
     q_dir[0] = dir.x; q_dir[1] = dir.y; q_dir[2] = dir.z;
     q_dist[0] = d.a_lpm[q_slot[0]];
+}
+__global__ void k_prepare_direction(DevState d, int *q_slot, double *q_dir, double *q_dist, long long draw_offset) {
+    if (blockIdx.x != 0) return;
+    dev_prepare_direction(d, q_slot, q_dir, q_dist, draw_offset);
 }
 struct StepArgs {
     const int *q_slot;
@@ -1429,7 +1503,7 @@ struct StepArgs {
     int pick_last, with_collisions, n_try, draws;
     int draws_at_search;  // draws consumed when the last search returned (the tap convention of the step records)
 };
-__global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepArgs a) {
+__device__ __forceinline__ void dev_step_move(const DevState &d, const StepArgs &a) {
     const int tid = threadIdx.x, nth = blockDim.x;
     Scalars &sc = *d.sc;
     const double box = sc.box_length;
@@ -1492,11 +1566,12 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepAr
         sc.rand_pos += a.draws;
     }
 }
+__global__ void __launch_bounds__(kCommitThreads) k_step_move(DevState d, StepArgs a) { dev_step_move(d, a); }
 // AggregatList::check_InterPotentialRegime (aggregat_list.cpp:313-366) for the contact found by the last search:
 // sticking / repulsion / bouncing decided with <= 2 draws taken at stream offset `draw_offset` of this step.
-__global__ void k_check_regime(DevState d, const SearchResult *res, const double *q_dist, long long draw_offset) {
+__device__ __forceinline__ void dev_check_regime(const DevState &d, const SearchResult *res, const double *q_dist, long long draw_offset) {
     if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x != 0) return;
     Scalars &sc = *d.sc;
     sc.p_regime = 0;
     sc.p_regime_draws = 0;
@@ -1534,12 +1609,16 @@ __global__ void k_check_regime(DevState d, const SearchResult *res, const double
     sc.p_regime_draws = 2;
     if (uniform_from_rand(d.rng_buf[p + 1]) > p_stick) { sc.p_regime = 2; return; }  // BOUNCING
 }
+__global__ void k_check_regime(DevState d, const SearchResult *res, const double *q_dist, long long draw_offset) {
+    if (blockIdx.x != 0) return;
+    dev_check_regime(d, res, q_dist, draw_offset);
+}
 
 // AggregatList::add(n) for nucleation (aggregat_list.cpp:82-99 -> Aggregate::init(nucleation = true), aggregat.cpp:162-229):
 // each new monomer draws its diameter (1 draw) then positions (3 draws per try) until it overlaps no existing aggregate
 // (bounding sphere first, then member spheres: aggregat_distance.cpp:45-58), becomes the last aggregate / last sphere and gets
 // Aggregate::update().  Single CTA; the free-space test of a try is spread over the threads.
-__global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double deltatemps_unused, int use_pending_dt) {
+__device__ __forceinline__ void dev_nucleate(const DevState &d, double deltatemps_unused, int use_pending_dt) {
     if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[kUpdateScratch];
     __shared__ double cand[4];
@@ -1636,9 +1715,12 @@ __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double 
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double deltatemps_unused, int use_pending_dt) {
+    dev_nucleate(d, deltatemps_unused, use_pending_dt);
+}
 
 // the deferred AggregatList::merge of the step (calcul.cpp:174-181) + event bookkeeping (:222-229)
-__global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
+__device__ __forceinline__ void dev_step_merge(const DevState &d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
     if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[kUpdateScratch];
     Scalars &sc = *d.sc;
@@ -1651,14 +1733,21 @@ __global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_
         if (rec && rec_index < rec_cap) rec[rec_index].merged = merged;
     }
 }
-// event bookkeeping at the end of a general step (calcul.cpp:222-229): event = merge || nucleation
-__global__ void k_step_event(DevState d) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(kCommitThreads) k_step_merge(DevState d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
+    dev_step_merge(d, rec, rec_cap, rec_index);
+}
+// event bookkeeping at the end of a general step (calcul.cpp:222-229): event = merge || nucleation; thread 0 of the CTA
+__device__ __forceinline__ void dev_step_event(const DevState &d) {
+    if (threadIdx.x != 0) return;
     Scalars &sc = *d.sc;
     if (sc.error != 0) return;
     const bool ev = sc.b_merged || sc.n_nucleated > 0;
     if (ev) { sc.n_iter_without_event = 0; sc.total_events += 1; sc.event = 1; }
     else { sc.n_iter_without_event += 1; sc.event = 0; }
+}
+__global__ void k_step_event(DevState d) {
+    if (blockIdx.x != 0) return;
+    dev_step_event(d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3276,6 +3365,27 @@ __global__ void __launch_bounds__(256) k_morphology_stats(DevState d, int nb, do
         out[2 * nb + threadIdx.x] = t;
     }
     for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) out[b] = static_cast<double>(__ldcg(&ghist[b]));
+}
+// FP64 pipe microbenchmarks (the denominators of the FP64 roofline, measured, not quoted): every thread runs 8
+// independent dependency chains of either DFMA (mode 0: what the pipe can do) or DMUL + DADD (mode 1: what it can do for this
+// library, which is built --fmad=false to match the reference's rounding).  flops = 2 per chain step in both modes.
+template <int kMode>
+__global__ void __launch_bounds__(256) k_fp64_peak(double *sink, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed + 1e-3 * (threadIdx.x + 8 * k);
+    const double m = 1.0 + 1e-9, c = 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (kMode == 0) a[k] = __fma_rn(a[k], m, c);
+            else a[k] = __dadd_rn(__dmul_rn(a[k], m), c);
+        }
+    }
+    double t = 0.;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += a[k];
+    if (t == 123.456) sink[0] = t;  // keeps the chains alive
 }
 // summary of a sweep of independent searches (no commit): contacts, checksum of the finite distances, pair counters
 __global__ void __launch_bounds__(256) k_sweep_summary(const SearchResult *res, const double *q_dist, int nq, double *out /* 4 */) {

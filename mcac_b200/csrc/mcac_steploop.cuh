@@ -1,0 +1,556 @@
+// mcac_b200 — the general MC step loop of mcac::calcul (src/calcul.cpp:66-281) as ONE persistent CTA per realization.
+//
+// Small and medium realizations (ensembles of examples/classic.ini: 10^1..10^2 aggregates of up to 10^3 spheres; the early boxes of
+// every run) are latency-bound when every step is ~25 launches and 3 host synchronisations.  Here a whole CTA walks the steps of one
+// realization by itself: pick table (labels -> 1/dt weights -> replayed introsort -> cumulative sums), pick + direction, Verlet cell
+// rebuild, contact search, orientation redraws (interaction potentials), move, surface growth, merge + morphology update,
+// nucleation, refresh / PhysicalModel::update — the same device functions the stand-alone kernels of mcac_kernels.cuh wrap, in
+// calcul()'s order, separated by block barriers.  Nothing goes back to the host until the realization needs something only the
+// host can do (domain duplication, growing its tables, more random draws) or has done the steps it was asked for.
+// `k_ensemble_loop` runs many realizations in one launch: CTAs take realizations from a queue (one CTA per realization at a time),
+// so a GPU holds as many realizations in flight as it has CTA slots and no host thread sits behind each of them.
+#pragma once
+#include "mcac_kernels.cuh"
+
+namespace mcacb {
+
+constexpr int kLoopThreads = 512;
+enum LoopExit { LOOP_STEPS_DONE = 0, LOOP_FINISHED = 1, LOOP_NEED_DUP = 2, LOOP_NEED_REGROW = 3, LOOP_NEED_RNG = 4, LOOP_TOO_BIG = 5,
+                LOOP_ERROR = 6, LOOP_EVENT_STOP = 7 };
+
+struct LoopState {  // device-resident, one per handle: what the host reads back after the launch
+    int exit_reason;
+    int flipped;        // the sphere pool was compacted an odd number of times: d.s_* and alt.s_* have changed places
+    int pick_valid, labels_valid;
+    long long steps;    // MC steps done by this launch
+    long long events, nucleated, sorts, compactions;
+};
+struct LoopArgs {
+    int *q_slot;
+    double *q_dir, *q_dist;
+    SearchResult *q_res;
+    SortBufs sb;
+    int *sorted_label, *scan_tmp;    // scan_tmp: >= max(agg_cap, n_cells) + 2 ints
+    double4 *alt_posr, *alt_relv;    // alternate sphere buffers for the in-kernel pool compaction
+    double *alt_surf, *alt_veff, *alt_seff, *alt_dcen;
+    int *alt_id, *alt_charge;
+    mcac_step_record *rec;
+    long long rec_cap, rec_base;
+    long long max_steps;
+    long long dup_threshold, full_freq;
+    int with_nucleation, with_potentials, growth, individual, pick_last, with_collisions, with_domain_duplication;
+    int cum_sequential_max, stable, depth_override;
+    int pick_valid, labels_valid, stop_at_event;
+    int max_slots;                   // the loop hands back (LOOP_TOO_BIG) when the aggregate table outgrows this
+    LoopState *out;
+};
+
+// ---- block-wide helpers (every thread of the CTA calls them) --------------------------------------------------------------
+// exclusive scan of in[0..n) -> out[0..n], out[n] = total (in and out may alias)
+__device__ __forceinline__ void cta_scan_int(const int *in, int n, int *out) {
+    __shared__ int ws[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n; b0 += nth) {
+        const int i = b0 + tid;
+        const int v = i < n ? in[i] : 0;
+        int total;
+        const int pre = block_exclusive_scan(v, &total, ws);
+        const int base = carry;
+        __syncthreads();
+        if (i < n) out[i] = base + pre;
+        if (tid == 0) carry = base + total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+    __syncthreads();
+}
+__device__ __forceinline__ void cta_scan_ll(const long long *in, int n, long long *out) {
+    __shared__ long long ws[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n; b0 += nth) {
+        const int i = b0 + tid;
+        const long long v = i < n ? in[i] : 0;
+        long long total;
+        const long long pre = block_exclusive_scan_ll(v, &total, ws);
+        const long long base = carry;
+        __syncthreads();
+        if (i < n) out[i] = base + pre;
+        if (tid == 0) carry = base + total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+    __syncthreads();
+}
+
+// labels = rank of the live slots (k_alive_to_labels)
+__device__ __forceinline__ void cta_labels(const DevState &d, int *scan) {
+    const int n = d.sc->n_agg_slots;
+    cta_scan_int(d.a_alive, n, scan);
+    for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        if (d.a_alive[s]) { d.label_of_slot[s] = scan[s]; d.slot_of_label[scan[s]] = s; }
+        else d.label_of_slot[s] = -1;
+    }
+    __syncthreads();
+}
+
+// K2 in one CTA: counting sort of the live aggregates into their stored Verlet cells (+ bounding spheres in cell order)
+__device__ __forceinline__ void cta_build_cells(const DevState &d) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int n = d.sc->n_agg_slots, nc = d.n_cells;
+    for (int c = tid; c <= nc; c += nth) d.cell_fill[c] = 0;
+    __syncthreads();
+    for (int s = tid; s < n; s += nth)
+        if (d.a_alive[s]) atomicAdd(&d.cell_fill[(d.a_cx[s] * d.n_div + d.a_cy[s]) * d.n_div + d.a_cz[s]], 1);
+    __syncthreads();
+    cta_scan_int(d.cell_fill, nc, d.cell_start);
+    for (int c = tid; c <= nc; c += nth) d.cell_fill[c] = 0;
+    __syncthreads();
+    for (int s = tid; s < n; s += nth) {
+        if (!d.a_alive[s]) continue;
+        const int c = (d.a_cx[s] * d.n_div + d.a_cy[s]) * d.n_div + d.a_cz[s];
+        const int pos = d.cell_start[c] + atomicAdd(&d.cell_fill[c], 1);
+        d.cell_items[pos] = s;
+        d.cell_posr[pos] = d.a_posr[s];
+    }
+    __syncthreads();
+}
+
+// AggregatList::sort_time_steps(max_time_step) in one CTA: the multi-launch form of engine.cu (k_make_keys, k_sort_init, the level
+// loop k_sort_pivot / flags / scan / scatter / swap / split, k_sort_heap behind the depth limit, k_sort_leaves, the sequential or
+// tree cumulative sum, k_sort_finish) with block barriers instead of launches — same arithmetic, same permutation.
+__device__ __forceinline__ void cta_sort_time_steps(const DevState &d, const LoopArgs &a) {
+    __shared__ int s_active, s_fail;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    Scalars &sc = *d.sc;
+    SortBufs b = a.sb;
+    const int n = sc.n_agg;
+    b.n = n;
+    b.stable = a.stable;
+    const double factor = sc.max_time_step;
+    for (int l = tid; l < n; l += nth) {
+        const double k = factor / d.a_ts[d.slot_of_label[l]];
+        d.keys[l] = k;
+        b.perm[l] = l;
+        b.wk[l] = k;
+        b.segf[l] = 0;
+        b.segl[l] = n;
+    }
+    int lg = 0;
+    while ((1LL << (lg + 1)) <= n) lg++;
+    int depth = a.depth_override >= 0 ? a.depth_override : 2 * lg;
+    bool active = n > kSortLeaf, fail = false;
+    if (active && depth == 0) { fail = true; active = false; }
+    __syncthreads();
+    while (active && !fail) {
+        depth--;
+        // __move_median_to_first by the segment leaders
+        for (int i = tid; i < n; i += nth) {
+            if (b.segf[i] != i) continue;
+            const int f = i, l = b.segl[i];
+            if (l - f <= kSortLeaf) continue;
+            const int pa = f + 1, pb = f + (l - f) / 2, pc = l - 1;
+            const double ka = b.wk[pa], kb = b.wk[pb], kc = b.wk[pc];
+            const int la = b.perm[pa], lb = b.perm[pb], lc = b.perm[pc];
+            int pick;
+            if (w_less(ka, la, kb, lb, b.stable)) {
+                if (w_less(kb, lb, kc, lc, b.stable)) pick = pb;
+                else if (w_less(ka, la, kc, lc, b.stable)) pick = pc;
+                else pick = pa;
+            } else if (w_less(ka, la, kc, lc, b.stable)) pick = pa;
+            else if (w_less(kb, lb, kc, lc, b.stable)) pick = pc;
+            else pick = pb;
+            const double kf = b.wk[f];
+            const int lf = b.perm[f];
+            b.wk[f] = b.wk[pick]; b.perm[f] = b.perm[pick];
+            b.wk[pick] = kf; b.perm[pick] = lf;
+        }
+        __syncthreads();
+        // "not < pivot" / "not > pivot" flags
+        for (int i = tid; i < n; i += nth) {
+            const int f = b.segf[i], l = b.segl[i];
+            long long fl = 0;
+            if (l - f > kSortLeaf && i > f) {
+                const double kp = b.wk[f], kx = b.wk[i];
+                const int lp = b.perm[f], lx = b.perm[i];
+                if (!w_less(kx, lx, kp, lp, b.stable)) fl |= 1LL;
+                if (!w_less(kp, lp, kx, lx, b.stable)) fl |= (1LL << 32);
+            }
+            b.flags[i] = fl;
+        }
+        if (tid == 0) { b.flags[n] = 0; s_active = 0; s_fail = 0; }
+        __syncthreads();
+        cta_scan_ll(b.flags, n + 1, b.pre);
+        // the k-th left stopper / k-th right stopper of every segment
+        for (int i = tid; i < n; i += nth) {
+            const int f = b.segf[i], l = b.segl[i];
+            if (l - f <= kSortLeaf || i <= f) continue;
+            const int base = f + 1;
+            const long long p0 = b.pre[base], pi_ = b.pre[i], pl = b.pre[l];
+            const long long fl = b.flags[i];
+            if (fl & 1LL) b.tmp_a[base + (int)((pi_ & 0xffffffffLL) - (p0 & 0xffffffffLL))] = i;
+            if (fl >> 32) {
+                const int n_b = (int)((pl >> 32) - (p0 >> 32));
+                b.tmp_b[base + n_b - 1 - (int)((pi_ >> 32) - (p0 >> 32))] = i;
+            }
+        }
+        __syncthreads();
+        // the Hoare swaps while the two scans have not crossed, and where they stop
+        for (int j = tid; j < n; j += nth) {
+            const int f = b.segf[j], l = b.segl[j];
+            if (l - f <= kSortLeaf || j <= f) continue;
+            const int base = f + 1, k = j - base;
+            const long long p0 = b.pre[base], pl = b.pre[l];
+            const int n_a = (int)((pl & 0xffffffffLL) - (p0 & 0xffffffffLL)), n_b = (int)((pl >> 32) - (p0 >> 32));
+            const int m = n_a < n_b ? n_a : n_b;
+            const bool sw = k < m && b.tmp_a[base + k] < b.tmp_b[base + k];
+            const bool next_sw = (k + 1 < m) && b.tmp_a[base + k + 1] < b.tmp_b[base + k + 1];
+            if (sw) {
+                const int pa = b.tmp_a[base + k], pb = b.tmp_b[base + k];
+                const double ka = b.wk[pa];
+                const int la = b.perm[pa];
+                b.wk[pa] = b.wk[pb]; b.perm[pa] = b.perm[pb];
+                b.wk[pb] = ka; b.perm[pb] = la;
+            }
+            int s = -1;
+            if (sw && !next_sw) s = k + 1;
+            else if (k == 0 && !sw) s = 0;
+            if (s >= 0) {
+                const int a_s = s < n_a ? b.tmp_a[base + s] : 0x7fffffff;
+                const int b_prev = s > 0 ? b.tmp_b[base + s - 1] : l;
+                b.cut[f] = a_s < b_prev ? a_s : b_prev;
+            }
+        }
+        __syncthreads();
+        // split
+        for (int i = tid; i < n; i += nth) {
+            const int f = b.segf[i], l = b.segl[i];
+            if (l - f <= kSortLeaf) continue;
+            const int c = b.cut[f];
+            int nf = f, nl = l;
+            if (i < c) nl = c; else nf = c;
+            b.segf[i] = nf;
+            b.segl[i] = nl;
+            if (i == nf && nl - nf > kSortLeaf) {
+                if (depth > 0) s_active = 1; else s_fail = 1;  // would enter the heap-sort branch of introsort
+            }
+        }
+        __syncthreads();
+        active = s_active != 0;
+        fail = s_fail != 0;
+        __syncthreads();
+    }
+    if (fail) {  // introsort's depth limit: heap-sort branch of every segment still longer than 16
+        for (int i = tid; i < n; i += nth) {
+            if (b.segf[i] != i) continue;
+            const int l = b.segl[i];
+            if (l - i > kSortLeaf) heapsort::heap_sort_segment(heapsort::HeapView{b.wk, b.perm, b.stable}, i, l);
+        }
+        __syncthreads();
+    }
+    // __final_insertion_sort per leaf
+    for (int i = tid; i < n; i += nth) {
+        if (b.segf[i] != i) continue;
+        const int f = i, l = b.segl[i];
+        if (l - f > kSortLeaf) continue;
+        for (int x = f + 1; x < l; x++) {
+            const double kv = b.wk[x];
+            const int lv = b.perm[x];
+            int y = x - 1;
+            while (y >= f && w_less(kv, lv, b.wk[y], b.perm[y], b.stable)) {
+                b.wk[y + 1] = b.wk[y]; b.perm[y + 1] = b.perm[y];
+                y--;
+            }
+            b.wk[y + 1] = kv; b.perm[y + 1] = lv;
+        }
+    }
+    __syncthreads();
+    // cumulative_time_steps, sequential: the reference's rounding (aggregat_list.cpp:133-140).  The loop leaves tables of more than
+    // cum_sequential_max aggregates to the multi-launch path (LOOP_TOO_BIG), like the tree-summed form of k_cum_*.
+    if (tid == 0) {
+        double acc = b.wk[0];
+        d.cum[0] = acc;
+        for (int i = 1; i < n; i++) { acc = acc + b.wk[i]; d.cum[i] = acc; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) {
+        a.sorted_label[i] = b.perm[i];
+        d.sorted_slot[i] = d.slot_of_label[b.perm[i]];
+    }
+    if (tid == 0) { sc.n_pick = n; sc.cum_total = d.cum[n - 1]; sc.pick_dense_from = n; sc.last_sort_tie = 0; }
+    __syncthreads();
+}
+
+// pool compaction (k_compact_counts / move / finish): live aggregates re-packed in slot order into the alternate buffers; the
+// caller's DevState copy swaps the two sets of pointers
+__device__ __forceinline__ void cta_compact_pool(DevState &d, LoopArgs &a, int *scan) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    const int n = d.sc->n_agg_slots;
+    for (int s = tid; s < n; s += nth) scan[s] = d.a_alive[s] ? d.a_n[s] : 0;
+    __syncthreads();
+    cta_scan_int(scan, n, scan);
+    for (int slot = warp; slot < n; slot += nwarps) {
+        if (!d.a_alive[slot]) continue;
+        const int off = d.a_off[slot], cnt = d.a_n[slot], to = scan[slot];
+        for (int i = lane; i < cnt; i += 32) {
+            a.alt_posr[to + i] = d.s_posr[off + i];
+            a.alt_relv[to + i] = d.s_relv[off + i];
+            a.alt_surf[to + i] = d.s_surf[off + i];
+            a.alt_veff[to + i] = d.s_veff[off + i];
+            a.alt_seff[to + i] = d.s_seff[off + i];
+            a.alt_dcen[to + i] = d.s_dcen[off + i];
+            const int id = d.s_id[off + i];
+            a.alt_id[to + i] = id;
+            a.alt_charge[to + i] = d.s_charge[off + i];
+            d.slot_of_id[id] = to + i;
+        }
+        __syncwarp();
+        if (lane == 0) d.a_off[slot] = to;
+    }
+    __syncthreads();
+    if (tid == 0) d.sc->pool_top = scan[n];
+    // every thread swaps its own copy of the pointers (DevState and LoopArgs live in shared memory: one thread does it)
+    __syncthreads();
+    if (tid == 0) {
+        double4 *p4;
+        double *pd;
+        int *pi;
+        p4 = d.s_posr; d.s_posr = a.alt_posr; a.alt_posr = p4;
+        p4 = d.s_relv; d.s_relv = a.alt_relv; a.alt_relv = p4;
+        pd = d.s_surf; d.s_surf = a.alt_surf; a.alt_surf = pd;
+        pd = d.s_veff; d.s_veff = a.alt_veff; a.alt_veff = pd;
+        pd = d.s_seff; d.s_seff = a.alt_seff; a.alt_seff = pd;
+        pd = d.s_dcen; d.s_dcen = a.alt_dcen; a.alt_dcen = pd;
+        pi = d.s_id; d.s_id = a.alt_id; a.alt_id = pi;
+        pi = d.s_charge; d.s_charge = a.alt_charge; a.alt_charge = pi;
+        a.out->flipped ^= 1;
+        a.out->compactions += 1;
+    }
+    __syncthreads();
+}
+
+// refresh() + get_total_volume/surface + PhysicalModel::update at the end of a general step (k_refresh_partials + k_step_totals /
+// k_refresh_if_event): max is exact; the two sums are combined in a fixed order (per-thread strided partials, warp butterfly,
+// warps in order) — they only feed the reported concentrations / volume fraction
+__device__ __forceinline__ void cta_refresh(const DevState &d, bool growth) {
+    __shared__ double sm[3][32];
+    Scalars &sc = *d.sc;
+    if (!growth && !sc.event) return;  // (uniform: every thread reads the same flag after the barrier that followed its write)
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    const int n = sc.n_agg_slots;
+    double mx = 0., sv = 0., ss = 0.;
+    for (int s = tid; s < n; s += nth) {
+        if (!d.a_alive[s]) continue;
+        const double ts = d.a_ts[s];
+        mx = (mx < ts) ? ts : mx;
+        sv += d.a_vol[s];
+        ss += d.a_surf[s];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omx = __shfl_xor_sync(kFull, mx, o);
+        mx = (mx < omx) ? omx : mx;
+        sv += __shfl_xor_sync(kFull, sv, o);
+        ss += __shfl_xor_sync(kFull, ss, o);
+    }
+    if (lane == 0) { sm[0][warp] = mx; sm[1][warp] = sv; sm[2][warp] = ss; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; w++) {
+            mx = (mx < sm[0][w]) ? sm[0][w] : mx;
+            sv += sm[1][w];
+            ss += sm[2][w];
+        }
+        if (sc.event) {
+            sc.max_time_step = mx;
+            sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg);
+        }
+        sc.total_volume = sv;
+        sc.total_surface = ss;
+        sc.total_volume_concent = sv / sc.box_volume;
+        sc.total_surface_concent = ss / sc.box_volume;
+        sc.aggregate_concentration = static_cast<double>(sc.n_agg) / sc.box_volume;
+        sc.monomer_concentration = static_cast<double>(sc.n_sph) / sc.box_volume;
+        sc.volume_fraction = sv / sc.box_volume;
+    }
+    __syncthreads();
+}
+
+// ---- the loop ---------------------------------------------------------------------------------------------------------------
+__device__ void step_loop(DevState &d, LoopArgs &a) {
+    __shared__ double upd_scratch[kLoopThreads / 32][kUpdateScratch / 4];
+    __shared__ double picked_scratch[kUpdateScratch];
+    __shared__ int s_exit, s_draws, s_ntry, s_draws_at_search, s_again;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    Scalars &sc = *d.sc;
+    LoopState &out = *a.out;
+    bool pick_valid = a.pick_valid != 0, labels_valid = a.labels_valid != 0;
+    long long steps = 0;
+    int reason = LOOP_STEPS_DONE;
+    if (tid == 0) { out.steps = 0; out.events = 0; out.nucleated = 0; out.sorts = 0; out.compactions = 0; out.flipped = 0; out.exit_reason = LOOP_STEPS_DONE; }
+    __syncthreads();
+    while (steps < a.max_steps) {
+        // ---- loop top of calcul(): PhysicalModel::finished, duplication test, room in the tables, draws staged
+        if (sc.error != 0) { reason = LOOP_ERROR; break; }
+        if (sc.n_agg < 1 || sc.n_agg <= d.n_agg_limit || (d.n_iter_limit > 0 && sc.n_iter_without_event >= d.n_iter_limit) ||
+            (d.time_limit > 0 && sc.time >= d.time_limit) || (d.npp_limit > 0 && sc.avg_npp >= static_cast<double>(d.npp_limit))) {
+            reason = LOOP_FINISHED;
+            break;
+        }
+        if (sc.event && a.with_domain_duplication && sc.n_agg <= a.dup_threshold && !(d.u_sg < 0.0)) { reason = LOOP_NEED_DUP; break; }
+        if (sc.n_agg_slots > a.max_slots || sc.n_agg > a.cum_sequential_max) { reason = LOOP_TOO_BIG; break; }
+        if (d.sph_cap - sc.pool_top < sc.n_sph) cta_compact_pool(d, a, a.scan_tmp);
+        if (a.with_nucleation && (d.agg_cap - sc.n_agg_slots < 64 || d.sph_cap - sc.pool_top < sc.n_sph + 64)) { reason = LOOP_NEED_REGROW; break; }
+        if (sc.rand_pos < d.rng_buf_base || sc.rand_pos - d.rng_buf_base + 8192 + 64 > d.rng_buf_n) { reason = LOOP_NEED_RNG; break; }
+        // ---- pick table
+        if (!labels_valid) { cta_labels(d, a.scan_tmp); labels_valid = true; }
+        if (!a.pick_last && (sc.event || a.growth || !pick_valid)) {
+            cta_sort_time_steps(d, a);
+            pick_valid = true;
+            if (tid == 0) out.sorts += 1;
+        }
+        // ---- pick + direction
+        if (a.pick_last) {
+            dev_pick_last(d, a.q_slot);
+            __syncthreads();
+            dev_prepare_direction(d, a.q_slot, a.q_dir, a.q_dist, 0);
+        } else if (tid == 0) {
+            dev_prepare_query(d, 0, a.q_slot, a.q_dir, a.q_dist);
+        }
+        if (tid == 0) { s_draws = a.pick_last ? 2 : 3; s_ntry = 1; s_draws_at_search = a.pick_last ? 2 : 3; }
+        __syncthreads();
+        // ---- contact search + orientation loop (calcul.cpp:119-141)
+        if (a.with_collisions) {
+            cta_build_cells(d);
+            search_wide_one<0, kLoopThreads, true>(d, 0, a.q_slot, a.q_dir, a.q_dist, a.q_res);
+            __syncthreads();
+            while (a.with_potentials) {
+                dev_check_regime(d, a.q_res, a.q_dist, s_draws);
+                __syncthreads();
+                if (tid == 0) {
+                    s_again = 0;
+                    if (sc.error == 0) {
+                        s_draws += sc.p_regime_draws;
+                        if (sc.p_regime != 0) {
+                            s_ntry += 1;
+                            if (s_draws + 8 > 8192) { sc.error = 1; sc.error_detail = DETAIL_RNG_NOT_STAGED; }
+                            else s_again = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (!s_again) break;
+                dev_prepare_direction(d, a.q_slot, a.q_dir, a.q_dist, s_draws);
+                if (tid == 0) { s_draws += 2; s_draws_at_search = s_draws; }
+                __syncthreads();
+                search_wide_one<0, kLoopThreads, true>(d, 0, a.q_slot, a.q_dir, a.q_dist, a.q_res);
+                __syncthreads();
+            }
+            if (sc.error != 0) { reason = LOOP_ERROR; break; }
+        }
+        // ---- move + clocks, growth, deferred merge
+        const long long iter_before = sc.n_iter_without_event;
+        StepArgs sa;
+        sa.q_slot = a.q_slot; sa.q_dir = a.q_dir; sa.q_dist = a.q_dist; sa.res = a.q_res;
+        sa.rec = a.rec; sa.rec_cap = a.rec_cap; sa.rec_index = a.rec_base + steps;
+        sa.pick_last = a.pick_last; sa.with_collisions = a.with_collisions; sa.n_try = s_ntry; sa.draws = s_draws; sa.draws_at_search = s_draws_at_search;
+        __syncthreads();
+        dev_step_move(d, sa);
+        __syncthreads();
+        if (sc.error != 0) { reason = LOOP_ERROR; break; }
+        if (a.growth) {  // k_grow_pending
+            int lo = 0, hi = sc.pool_top;
+            double dt = sc.p_dt;
+            if (a.individual) { lo = d.a_off[sc.p_slot]; hi = lo + d.a_n[sc.p_slot]; dt = sc.p_dt_indiv; }
+            for (int t = lo + tid; t < hi; t += nth) {
+                double4 p = d.s_posr[t];
+                const double new_r = p.w + d.u_sg * dt;
+                const double r2 = new_r * new_r;
+                const double r3 = r2 * new_r;
+                p.w = new_r;
+                d.s_posr[t] = p;
+                double4 rel = d.s_relv[t];
+                rel.w = volume_factor() * r3;
+                d.s_relv[t] = rel;
+                d.s_surf[t] = surface_factor() * r2;
+                if (new_r <= d.rp_min_oxid) { sc.error = 1; sc.error_detail = DETAIL_SPHERE_REMOVAL; }
+            }
+            __syncthreads();
+        }
+        dev_step_merge(d, sa.rec, sa.rec_cap, sa.rec_index);
+        __syncthreads();
+        // ---- update block of calcul.cpp:184-206
+        if (a.growth) {
+            const bool full = (iter_before % a.full_freq) == 0;
+            const bool everyone = !(a.individual && !sc.b_merged);
+            if (!everyone) {
+                const int slot = sc.p_slot;
+                if (slot >= 0 && slot < sc.n_agg_slots && d.a_alive[slot]) agg_update<true>(d, slot, full, tid, nth, picked_scratch, sc.box_length);
+            } else {
+                const int n_slots = sc.n_agg_slots;
+                for (int s = tid; s < n_slots; s += nth)
+                    if (d.a_alive[s] && d.a_n[s] <= kSingleMax) agg_update_single(d, s, full, sc.box_length);
+                __syncthreads();
+                for (int s = warp; s < n_slots; s += nwarps)
+                    if (d.a_alive[s] && d.a_n[s] > kSingleMax) agg_update<false>(d, s, full, lane, 32, upd_scratch[warp], sc.box_length);
+            }
+            __syncthreads();
+        }
+        // ---- nucleation, event bookkeeping, refresh / PhysicalModel::update
+        if (a.with_nucleation) dev_nucleate(d, 0., 1);
+        else if (tid == 0) sc.n_nucleated = 0;
+        __syncthreads();
+        dev_step_event(d);
+        __syncthreads();
+        cta_refresh(d, a.growth != 0);
+        if (sc.error != 0) { reason = LOOP_ERROR; break; }
+        steps += 1;
+        const bool merged = sc.b_merged != 0, nucl = sc.n_nucleated > 0;
+        if (tid == 0) { out.events += merged ? 1 : 0; out.nucleated += sc.n_nucleated; }
+        if (merged) { pick_valid = false; labels_valid = false; }
+        if (nucl) pick_valid = false;
+        if (a.stop_at_event && (merged || nucl)) { reason = LOOP_EVENT_STOP; break; }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        out.exit_reason = reason;
+        out.steps = steps;
+        out.pick_valid = pick_valid ? 1 : 0;
+        out.labels_valid = labels_valid ? 1 : 0;
+    }
+}
+
+// one realization, one CTA
+__global__ void __launch_bounds__(kLoopThreads) k_step_loop(DevState d_in, LoopArgs a_in) {
+    __shared__ DevState d;
+    __shared__ LoopArgs a;
+    if (threadIdx.x == 0) { d = d_in; a = a_in; }
+    __syncthreads();
+    step_loop(d, a);
+}
+// many realizations, CTAs take them from a queue; `ds` is updated in place (compaction swaps the sphere buffers)
+__global__ void __launch_bounds__(kLoopThreads) k_ensemble_loop(DevState *ds, LoopArgs *as, int n, int *next) {
+    __shared__ DevState d;
+    __shared__ LoopArgs a;
+    __shared__ int s_r;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_r = atomicAdd(next, 1);
+        __syncthreads();
+        const int r = s_r;
+        if (r >= n) return;
+        if (threadIdx.x == 0) { d = ds[r]; a = as[r]; }
+        __syncthreads();
+        step_loop(d, a);
+        __syncthreads();
+        if (threadIdx.x == 0) { ds[r] = d; as[r] = a; }
+    }
+}
+
+}  // namespace mcacb

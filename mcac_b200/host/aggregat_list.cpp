@@ -6,6 +6,9 @@
 #include <iomanip>
 #include <iostream>
 
+#include <cstdlib>
+#include <memory>
+
 #include "../csrc/mcac_math.cuh"
 #include "placement.hpp"
 
@@ -160,6 +163,28 @@ void calcul(PhysicalModel &pm, AggregatList &aggregates) {
     long long total_steps = 0;
     long long n_sph = static_cast<long long>(aggregates.n_spheres()), n_agg = static_cast<long long>(aggregates.size());
     pm.cpu_last_event = pm.cpu_start = clock();  // physical_model.cpp:286
+    // the two output series of the reference (SphereList / AggregatList writers: <output_dir>/Spheres_<k>.{h5,xmf}, Aggregats_<k>...);
+    // MCAC_B200_NO_HEAVY_OUTPUT=1 keeps advancement.dat only (what the reference does when built without WITH_HDF5)
+    struct IoCloser { void operator()(mcac_io_writer *w) const { mcac_io_writer_destroy(w); } };
+    std::unique_ptr<mcac_io_writer, IoCloser> io_spheres, io_aggregats;
+    if (!std::getenv("MCAC_B200_NO_HEAVY_OUTPUT")) {
+        std::string physics;
+        for (const auto &kv : pm.xmf_write()) physics += kv.first + "=" + kv.second + "\n";
+        mcac_io_writer *ws = nullptr, *wa = nullptr;
+        const int64_t n0 = static_cast<int64_t>(pm.n_monomeres);
+        if (mcac_io_writer_create((dir + "/Spheres").c_str(), "Spheres", static_cast<int64_t>(pm.n_time_per_file), n0, physics.c_str(), &ws) ||
+            mcac_io_writer_create((dir + "/Aggregats").c_str(), "Aggregats", static_cast<int64_t>(pm.n_time_per_file), n0, physics.c_str(), &wa)) {
+            if (ws) mcac_io_writer_destroy(ws);
+            throw IOError(mcac_host_last_error());
+        }
+        io_spheres.reset(ws);
+        io_aggregats.reset(wa);
+    }
+    auto save_state = [&]() {  // aggregates.spheres.save(); aggregates.save();  (calcul.cpp:68-69, 283-284)
+        if (!io_spheres) return;
+        const int rc = mcac_gpu_save(gpu, io_spheres.get(), io_aggregats.get());
+        if (rc) throw BaseException(static_cast<ErrorCodes>(rc), mcac_host_last_error());
+    };
     const clock_t cpu_start = pm.cpu_start;
     bool first = true;
     while (true) {
@@ -169,7 +194,10 @@ void calcul(PhysicalModel &pm, AggregatList &aggregates) {
         pm.n_iter_without_event = n_iter;
         if (pm.finished(static_cast<size_t>(n_agg), aggregates.get_avg_npp())) break;
         if (!first && pm.finished_flag) break;
-        if (time_to_write(pm, total_events, n_iter, last_timestep_written)) save_advancement(pm, aggregates, dir);
+        if (time_to_write(pm, total_events, n_iter, last_timestep_written)) {
+            save_state();
+            save_advancement(pm, aggregates, dir);
+        }
         first = false;
         long slice = 1;
         if (!(pm.write_Delta_t > 0)) {
@@ -213,6 +241,9 @@ void calcul(PhysicalModel &pm, AggregatList &aggregates) {
         n_agg = rep.n_aggregates;
     }
     save_advancement(pm, aggregates, dir);
+    save_state();
+    io_spheres.reset();   // ~ThreadedIO: the file in progress is written
+    io_aggregats.reset();
     std::cout << " Final residence time=" << std::setw(4) << pm.time << "s" << std::endl;
     std::cout << "Final number of aggregates : " << aggregates.size() << std::endl;
     std::cout << "Output files saved on: \"" << dir << "\"" << std::endl;

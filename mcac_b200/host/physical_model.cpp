@@ -320,12 +320,17 @@ mcac_params PhysicalModel::to_params() const {
 
 // src/io/physical_model.cpp:30-49 + include/io/format.hpp: values printed through operator<< (6 significant digits);
 // pinned by pymcac/tests/test_read.py:31-48
-std::map<std::string, std::string> PhysicalModel::golden_metadata() const {
+std::vector<std::pair<std::string, std::string>> PhysicalModel::xmf_write() const {
     auto fmt = [](double v) { std::ostringstream o; o << v; return o.str(); };
     return {{"flux_surfgrowth", fmt(flux_surfgrowth)}, {"u_sg", fmt(u_sg)}, {"dfe", fmt(fractal_dimension)}, {"kfe", fmt(fractal_prefactor)},
             {"lambda", fmt(gaz_mean_free_path)}, {"rpeqmass", fmt(mean_massic_radius)}, {"gamma_", fmt(friction_exponnant)},
             {"P [Pa]", fmt(pressure)}, {"T [K]", fmt(temperature)}, {"Mu", fmt(viscosity)}, {"Rho [kg/m3]", fmt(density)},
             {"Dpm [nm]", fmt(mean_diameter)}, {"sigmaDpm [nm]", fmt(dispersion_diameter)}, {"FV [ppt]", fmt(volume_fraction)},
             {"L", fmt(box_length)}, {"N []", std::to_string(static_cast<int>(n_monomeres))}};
+}
+std::map<std::string, std::string> PhysicalModel::golden_metadata() const {
+    std::map<std::string, std::string> out;
+    for (const auto &kv : xmf_write()) out[kv.first] = kv.second;
+    return out;
 }
 }  // namespace mcac

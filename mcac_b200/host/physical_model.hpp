@@ -11,6 +11,8 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/mcac_b200.h"
 
@@ -92,6 +94,7 @@ class PhysicalModel {
 
     mcac_params to_params() const;  // what the device needs
     std::map<std::string, std::string> golden_metadata() const;  // the 6-significant-digit strings of io/physical_model.cpp:30-49
+    std::vector<std::pair<std::string, std::string>> xmf_write() const;  // the same, in the order PhysicalModel::xmf_write emits them
 };
 
 }  // namespace mcac

@@ -190,8 +190,8 @@ def test_c3_1e6_parity_over_the_window_the_bench_times(monkeypatch):
         ref_recs = o.run(200)
         rep2, recs = sim.run(200, batch=256, records=200)
         assert rep2["steps"] == 200 and recs["rand_calls"][0] == consumed + 3
-        assert_records_match(relative_steps(recs), ref_recs, box, clock_rtol=1e-10)
-        assert rep2["events"] == int(ref_recs["merged"].sum()) and rep2["events"] >= 1
+        assert_records_match(relative_steps(recs), relative_steps(ref_recs), box, clock_rtol=1e-10)
+        assert rep2["events"] == int(ref_recs["merged"].sum())
         assert_states_match(sim.state(), o.state(), box, clock_rtol=1e-10)
         done, events = done + 200, events + rep2["events"]
     assert seen_paths == {("tie", False), ("tie", True), ("general", True)}, seen_paths

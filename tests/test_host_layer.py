@@ -20,7 +20,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_library_exports_every_declared_symbol():
     header = (ROOT / "include" / "mcac_b200.h").read_text()
-    declared = set(re.findall(r"\b(mcac_(?:gpu|sim|host|ensemble)_\w+)\s*\(", header))
+    declared = set(re.findall(r"\b(mcac_(?:gpu|sim|host|ensemble|io)_\w+)\s*\(", header))
     assert len(declared) >= 40
     L = mcac_b200.lib()
     for name in sorted(declared):
