@@ -220,7 +220,8 @@ def ensemble_main(a, rank: int, world: int, local: int):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
-    steps_done = launches = events = pair_tests = 0
+    steps_done = launches = events = pair_tests = pair_exec = 0
+    phase_cycles = [0] * 5
     stats_s = 0.0
     d2h = 0
     rows = None
@@ -230,6 +231,9 @@ def ensemble_main(a, rank: int, world: int, local: int):
         launches += sum(r["kernel_launches"] for r in reps)
         events += sum(r["events"] for r in reps)
         pair_tests += sum(r["pair_tests_sphere"] + r["pair_tests_bounding"] for r in reps)
+        pair_exec += sum(r["pair_tests_executed"] for r in reps)
+        for k in range(5):
+            phase_cycles[k] += sum(r["loop_phase_cycles"][k] for r in reps)
         # the step's result: the statistic rows of every realization cross to the host (timed apart: only e2e includes it)
         t_s = time.perf_counter()
         rows = e.morphology_stats(ens.N_BINS, 2e-6)
@@ -240,7 +244,8 @@ def ensemble_main(a, rank: int, world: int, local: int):
     clocks = sampler.stop()
     del ev0, ev1
     t = torch.tensor([wall_s - stats_s, wall_s], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(steps_done), float(launches), float(events), float(pair_tests)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(steps_done), float(launches), float(events), float(pair_tests), float(pair_exec)] + [float(c) for c in phase_cycles],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -257,14 +262,18 @@ def ensemble_main(a, rank: int, world: int, local: int):
         peak_dfma = dfma["units"] / (dfma["ms"] * 1e-3) / 1e12
         peak_nofma = dmad["units"] / (dmad["ms"] * 1e-3) / 1e12
         pair_rate = float(tot[3]) / float(t[0])
-        fp64_tflops = pair_rate * 104.0 / 1e12
+        exec_rate = float(tot[4]) / float(t[0])  # sphere-pair tests the pruned sweeps actually executed
+        fp64_tflops = exec_rate * 104.0 / 1e12
+        cyc = [float(x) for x in tot[5:10]]
+        phase_share = {n: (c / sum(cyc) if sum(cyc) else None) for n, c in
+                       zip(["pick_table", "cells_and_search", "move_growth_merge_update", "nucleation_refresh", "loop_top"], cyc)}
         peaks = {}
         try:
             peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_gbs = pair_rate * 32.0 / 1e9  # 32 B (x, y, z, r) of the candidate sphere per pair test
+        alg_gbs = exec_rate * 32.0 / 1e9  # 32 B (x, y, z, r) of the candidate sphere per executed pair test
         cpu_baseline = None
         if world == 1 and not a.no_cpu_baseline:
             try:
@@ -279,7 +288,8 @@ def ensemble_main(a, rank: int, world: int, local: int):
                           "dtype": "f64", "data": "synthetic", "config": dict(config, host_threads_per_rank=threads),
                           "timing": "wall clock between device synchronisations around the K steps (every step = rounds of one k_ensemble_loop launch + "
                                     "host services), max over ranks",
-                          "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "pair_tests_per_sec": pair_rate, "init_s": init_s, "clocks": clocks,
+                          "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "pair_tests_per_sec": pair_rate,
+                          "pair_tests_executed_per_sec": exec_rate, "loop_phase_share": phase_share, "init_s": init_s, "clocks": clocks,
                           "e2e": {"value": float(te[1]) / float(te[0]), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
                                   "what": "mcac_ensemble_run(M steps per realization) + mcac_gpu_morphology_stats of every realization to the host, per step; "
                                           "the realizations are created on the host (placement) and live in HBM from then on"},

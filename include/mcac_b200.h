@@ -99,6 +99,13 @@ typedef struct mcac_run_report {
      * limit, or the MCAC_B200_FORCE_SORT_FAIL test hook), and sorts that replayed libstdc++'s heap-sort branch.  Every sort runs on
      * the device either way: there is no host sort in the product. */
     int64_t sort_fallbacks, sort_heap_branches;
+    /* sphere-pair tests the per-realization step loop actually executed: its ordered sweep prunes pairs that cannot touch with
+     * enclosing balls (same result); pair_tests_sphere stays the number of tests the reference runs.  0 on the other paths
+     * (they execute what they count). */
+    int64_t pair_tests_executed;
+    /* SM cycles of the step loop's CTA per part of the step: 0 pick table (labels + sort), 1 cell rebuild + contact search (+ redraws),
+     * 2 move + growth + merge + updates, 3 nucleation + bookkeeping + refresh, 4 loop top (checks, pool compaction) */
+    int64_t loop_phase_cycles[5];
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction
@@ -188,6 +195,10 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_p
 /* on != 0: mcac_gpu_run returns right after the step that made an event (merge or nucleation: `event` of calcul.cpp:222), so that a
  * host loop can do what calcul() does between events (advancement.dat rows, the progress table, output files) */
 int mcac_gpu_set_stop_at_event(mcac_gpu *h, int32_t on);
+/* on != 0: strict replay mode.  random_direction() (src/tools/tools.cpp:82-89) is evaluated on the host with glibc's sin / cos / acos for
+ * every staged pair of draws and read from a table by the kernels, so directions — and with them contact distances, positions and
+ * clocks — are the reference's bit for bit instead of within 2 ulp of CUDA's sincos / acos (costs one host pass per ~10^6 draws). */
+int mcac_gpu_set_strict_direction(mcac_gpu *h, int32_t on);
 /* profile != 0: mcac_gpu_run brackets its K1 / commit launches with CUDA events (reported in mcac_run_report) */
 int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile);
 

@@ -249,6 +249,10 @@ class Simulation:
     def set_stop_at_event(self, on: bool = True):
         self._ck(self.L.mcac_gpu_set_stop_at_event(self.h, int(on)))
 
+    def set_strict_direction(self, on: bool = True):
+        """Directions from the host's glibc (bit-exact replay of the reference) instead of CUDA's sincos / acos."""
+        self._ck(self.L.mcac_gpu_set_strict_direction(self.h, int(on)))
+
     def set_profile(self, on: bool = True):
         self._ck(self.L.mcac_gpu_set_profile(self.h, int(on)))
 

@@ -68,7 +68,8 @@ class RunReport(C.Structure):
                [("tie_phase_cycles", C.c_int64 * 2)] + \
                [(n, C.c_int64) for n in ["tie_sorts", "tie_levels", "tie_sparse", "tie_handed"]] + \
                [("tie_sim_cycles", C.c_int64 * 3)] + \
-               [(n, C.c_int64) for n in ["sort_fallbacks", "sort_heap_branches"]]
+               [(n, C.c_int64) for n in ["sort_fallbacks", "sort_heap_branches", "pair_tests_executed"]] + \
+               [("loop_phase_cycles", C.c_int64 * 5)]
 
     def as_dict(self) -> dict:
         return {n: (list(getattr(self, n)) if n.endswith("_cycles") else getattr(self, n)) for n, _ in self._fields_}
@@ -99,7 +100,7 @@ EXPORTS = [
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_ini_echo", "mcac_host_model_state", "mcac_sim_create",
     "mcac_io_writer_create", "mcac_io_begin_step", "mcac_io_positions", "mcac_io_attribute", "mcac_io_end_step", "mcac_io_writer_destroy",
-    "mcac_gpu_save",
+    "mcac_gpu_save", "mcac_gpu_set_strict_direction",
 ]
 
 
@@ -162,6 +163,7 @@ def lib() -> C.CDLL:
         L.mcac_io_end_step.argtypes = [vp]
         L.mcac_io_writer_destroy.argtypes = [vp]
         L.mcac_gpu_save.argtypes = [vp, vp, vp]
+        L.mcac_gpu_set_strict_direction.argtypes = [vp, C.c_int32]
         _lib = L
     return _lib
 

@@ -96,6 +96,8 @@ struct mcac_gpu {
     int sort_depth_override = -1;  // MCAC_B200_SORT_DEPTH (test hook): introsort depth limit, to reach the heap-sort branch
     int coop_blocks = 0;      // grid of the cooperative event kernel (0 = not available / disabled)
     int coop_bps = 1, sort_local_span = 4096;
+    int sort_switch_span = 0;      // MCAC_B200_SORT_SWITCH: span below which block 0 of the event kernel sorts alone, still out of L2
+                                   // (0 = local_span: measured slower at 16384, profiles/r2_tuning.md)
     int event_spare_sms = 24; // MCAC_B200_EVENT_SPARE_SMS (sweep in profiles/r1_tuning.md)
     int event_smem_cap = 0;   // shared-memory staging of the block-local sort levels (entries; 0 = levels stay in HBM/L2)
     size_t event_dyn_bytes = 0;  // dynamic shared memory of the event kernel's launches
@@ -126,7 +128,12 @@ struct mcac_gpu {
     bool fused = true;            // MCAC_B200_NO_LOOP=1: every general step goes through the multi-launch sequence
     int fused_max_slots = 16384;  // MCAC_B200_LOOP_MAX_SLOTS: larger aggregate tables leave the loop to the multi-launch path
     LoopState *loop_dev = nullptr, *loop_host = nullptr;
+    bool strict_dir = false;      // MCAC_B200_STRICT_DIRECTION / mcac_gpu_set_strict_direction: directions evaluated by the host's glibc
+    bool dir_tab_valid = false;
+    double *dir_tab = nullptr;
+    bool loop_prune = true;       // MCAC_B200_NO_PRUNE=1: the ordered sweep tests every sphere pair of an examined suspect
     long long loop_launches = 0, loop_steps = 0;
+    long long loop_cycles[5] = {0, 0, 0, 0, 0}, loop_cycles_seen[5] = {0, 0, 0, 0, 0};
     void *stage = nullptr;  // device staging of the host-layout arrays at the upload / download boundary
     size_t stage_bytes = 0;
 };
@@ -445,6 +452,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.cum_sequential_max = h->cum_sequential_max;
     a.stable = h->prm.sort_order == MCAC_ORDER_STABLE ? 1 : 0;
     a.local_span = h->sort_local_span;
+    a.switch_span = std::max(h->sort_switch_span, h->sort_local_span);
     a.work = h->event_work;
     a.smem_cap = h->event_smem_cap;
     a.smem_bytes = (int)h->event_dyn_bytes;
@@ -488,10 +496,35 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     return E_OK;
 }
 
+// strict replay mode: random_direction() (src/tools/tools.cpp:82-89) of every pair of consecutive staged draws, evaluated HERE with the
+// host's glibc sin / cos / acos — the very functions the reference calls — and handed to the device as a table
+int build_direction_table(mcac_gpu *h) {
+    DevState &d = h->d;
+    const int n = d.rng_buf_n;
+    if (!h->dir_tab) TRY(dev_alloc_persistent(h, &h->dir_tab, 3 * (size_t)(kRngBuf + 64)));
+    std::vector<int> draws((size_t)std::max(n, 1));
+    std::vector<double> tab(3 * (size_t)std::max(n, 1), 0.);
+    if (n > 0) {
+        CK(cudaMemcpyAsync(draws.data(), d.rng_buf, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int p = 0; p + 1 < n; p++) {
+            const Vec3 v = direction_from_draws(uniform_from_rand(draws[(size_t)p]), uniform_from_rand(draws[(size_t)p + 1]));
+            tab[3 * (size_t)p] = v.x; tab[3 * (size_t)p + 1] = v.y; tab[3 * (size_t)p + 2] = v.z;
+        }
+        CK(cudaMemcpyAsync(h->dir_tab, tab.data(), sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    d.dir_tab = h->dir_tab;
+    h->dir_tab_valid = true;
+    return E_OK;
+}
 int ensure_rng(mcac_gpu *h, long long need_until) {  // draws [rand_pos, need_until) must be in rng_buf
     DevState &d = h->d;
     const long long pos = h->sc_host.rand_pos;
-    if (need_until <= h->rng_generated && pos >= d.rng_buf_base) return E_OK;
+    if (need_until <= h->rng_generated && pos >= d.rng_buf_base) {
+        if (h->strict_dir && !h->dir_tab_valid) TRY(build_direction_table(h));
+        return E_OK;
+    }
     const long long keep = std::max<long long>(0, h->rng_generated - pos);  // generated but unconsumed
     if (keep > 0 && pos > d.rng_buf_base) {
         std::vector<int> tmp((size_t)keep);
@@ -508,6 +541,8 @@ int ensure_rng(mcac_gpu *h, long long need_until) {  // draws [rand_pos, need_un
     CK(cudaGetLastError());
     h->rng_generated = pos + keep + room;
     d.rng_buf_n = (int)(keep + room);
+    h->dir_tab_valid = false;
+    if (h->strict_dir) TRY(build_direction_table(h));
     return E_OK;
 }
 
@@ -627,6 +662,7 @@ int duplicate(mcac_gpu *h) {
     h->sc_host.rand_pos = keep.rand_pos;
     h->sc_host.pair_sphere = keep.pair_sphere;
     h->sc_host.pair_bounding = keep.pair_bounding;
+    h->sc_host.pair_exec = keep.pair_exec;
     h->sc_host.searches = keep.searches;
     h->sc_host.conflicts = keep.conflicts;
     h->sc_host.event = keep.event;
@@ -765,6 +801,7 @@ int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_ste
     sc.n_sph = sc.pool_top = (int)n_sph;
     sc.event = 1;
     sc.rand_pos = old.rand_pos;
+    sc.pair_exec = old.pair_exec;
     sc.aggregate_concentration = static_cast<double>(n_agg) / sc.box_volume;
     sc.monomer_concentration = static_cast<double>(n_sph) / sc.box_volume;
     TRY(push_scalars(h));  // synchronizes the stream: the host arrays may be reused on return
@@ -964,6 +1001,7 @@ void loop_fill_args(mcac_gpu *h, LoopArgs &a, long long max_steps, mcac_step_rec
     a.pick_valid = h->pick_valid ? 1 : 0; a.labels_valid = h->labels_valid ? 1 : 0;
     a.stop_at_event = h->stop_at_event ? 1 : 0;
     a.max_slots = h->fused_max_slots;
+    a.prune = h->loop_prune ? 1 : 0;
     a.out = h->loop_dev;
 }
 // host-side bookkeeping after a loop launch: the pool may have been compacted (buffers swapped), validity flags
@@ -979,6 +1017,7 @@ void loop_apply(mcac_gpu *h, const LoopState &ls) {
     h->cells_valid = false;
     h->loop_launches++;
     h->loop_steps += ls.steps;
+    for (int k = 0; k < 5; k++) h->loop_cycles[k] += ls.phase_cycles[k];
 }
 // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up.  This renumbers the
 // aggregate slots (slot = label again), so it must come BEFORE the pick table of the step is built.
@@ -1042,11 +1081,14 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_FORCE_SORT_FAIL")) h->force_sort_fail = atoi(e);
         if (const char *e = getenv("MCAC_B200_SORT_DEPTH")) h->sort_depth_override = std::max(0, atoi(e));
         if (getenv("MCAC_B200_NO_LOOP")) h->fused = false;
+        if (getenv("MCAC_B200_NO_PRUNE")) h->loop_prune = false;
+        if (getenv("MCAC_B200_STRICT_DIRECTION")) h->strict_dir = true;
         if (const char *e = getenv("MCAC_B200_LOOP_MAX_SLOTS")) h->fused_max_slots = std::max(1, atoi(e));
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
         if (const char *e = getenv("MCAC_B200_SEARCH_MB")) h->search_min_blocks = atoi(e);
         if (const char *e = getenv("MCAC_B200_COOP_BPS")) h->coop_bps = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("MCAC_B200_SORT_LOCAL")) h->sort_local_span = std::max(64, atoi(e));
+        if (const char *e = getenv("MCAC_B200_SORT_SWITCH")) h->sort_switch_span = std::max(64, atoi(e));
         if (const char *e = getenv("MCAC_B200_TIE_MIN_N")) h->ts_min_n = std::max(0, atoi(e));
         if (const char *e = getenv("MCAC_B200_TIE_MAX_SPARSE")) h->ts_max_sparse = std::max(1, atoi(e));
         if (getenv("MCAC_B200_TIE_NO_OVERLAP")) h->ts_no_overlap = true;
@@ -1139,6 +1181,7 @@ int mcac_gpu_set_rng(mcac_gpu *h, uint32_t seed, int64_t consumed) {
     h->d.rng_buf_base = consumed;
     h->d.rng_buf_n = 0;
     h->rng_generated = consumed;
+    h->dir_tab_valid = false;
     if (h->uploaded) TRY(push_scalars(h));
     return E_OK;
 }
@@ -1182,7 +1225,7 @@ int mcac_gpu_upload_state(mcac_gpu *h, int64_t n_sph, int64_t n_agg, const doubl
         Scalars &sc = h->sc_host;
         sc.time = live.time; sc.n_iter_without_event = live.n_iter_without_event; sc.total_events = live.total_events;
         sc.steps_done = live.steps_done; sc.rand_pos = live.rand_pos; sc.pair_sphere = live.pair_sphere;
-        sc.pair_bounding = live.pair_bounding; sc.searches = live.searches; sc.conflicts = live.conflicts;
+        sc.pair_bounding = live.pair_bounding; sc.searches = live.searches; sc.conflicts = live.conflicts; sc.pair_exec = live.pair_exec;
         sc.nucleation_accum = live.nucleation_accum; sc.event = 1;
         sc.total_volume = live.total_volume; sc.total_surface = live.total_surface; sc.volume_fraction = live.volume_fraction;
         TRY(push_scalars(h));
@@ -1799,6 +1842,8 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->searches = sc.searches - at_start.searches;
         report->pair_tests_sphere = sc.pair_sphere - at_start.pair_sphere;
         report->pair_tests_bounding = sc.pair_bounding - at_start.pair_bounding;
+        report->pair_tests_executed = sc.pair_exec - at_start.pair_exec;
+        for (int k = 0; k < 5; k++) { report->loop_phase_cycles[k] = h->loop_cycles[k] - h->loop_cycles_seen[k]; h->loop_cycles_seen[k] = h->loop_cycles[k]; }
         report->batches = batches;
         report->conflicts = sc.conflicts - at_start.conflicts;
         report->duplications = dups;
@@ -1842,6 +1887,12 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
 }
 
 int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile) { h->profile = profile; return E_OK; }
+int mcac_gpu_set_strict_direction(mcac_gpu *h, int32_t on) {
+    h->strict_dir = on != 0;
+    h->dir_tab_valid = false;
+    if (!h->strict_dir) h->d.dir_tab = nullptr;
+    return E_OK;
+}
 int mcac_gpu_set_stop_at_event(mcac_gpu *h, int32_t on) { h->stop_at_event = on != 0; return E_OK; }
 
 int mcac_gpu_morphology_stats_device(mcac_gpu *h, int32_t n_bins, double rg_max, void *device_out) {
@@ -2008,6 +2059,8 @@ static void fill_report_basic(mcac_gpu *h, const Scalars &at_start, long long la
     report->searches = sc.searches - at_start.searches;
     report->pair_tests_sphere = sc.pair_sphere - at_start.pair_sphere;
     report->pair_tests_bounding = sc.pair_bounding - at_start.pair_bounding;
+    report->pair_tests_executed = sc.pair_exec - at_start.pair_exec;
+    for (int k = 0; k < 5; k++) { report->loop_phase_cycles[k] = h->loop_cycles[k] - h->loop_cycles_seen[k]; h->loop_cycles_seen[k] = h->loop_cycles[k]; }
     report->batches = steps;
     report->duplications = dups;
     report->sorts = sorts;

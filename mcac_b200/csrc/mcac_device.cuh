@@ -42,6 +42,8 @@ struct Scalars {
     double pick_w;
     int pick_dense_from;
     int last_sort_tie;  // 1: the last pick table was made by the sparse path of the event kernel (it is short: see event_spare_sms)
+    // sphere-pair tests actually EXECUTED by the step loop's pruned sweeps (pair_sphere counts the tests the reference runs)
+    long long pair_exec;
 };
 // finer cause of a device-side error (Scalars::error_detail); the host turns it into the message of mcac_gpu_last_error
 enum ErrorDetail { DETAIL_NONE = 0, DETAIL_SUSPECT_OVERFLOW = 12, DETAIL_NOT_ON_VERLET = 13, DETAIL_RNG_NOT_STAGED = 21, DETAIL_PICK_TABLE = 22,
@@ -83,6 +85,9 @@ struct DevState {
     int *rng_buf;
     long long rng_buf_base;  // stream position of rng_buf[0]
     int rng_buf_n;
+    // strict replay mode: random_direction() of the draws (rng_buf[p], rng_buf[p+1]) evaluated on the HOST with glibc's sin / cos / acos
+    // (3 doubles per buffer position), so that directions are the reference's bit for bit; nullptr = CUDA's sincos / acos (<= 2 ulp)
+    const double *dir_tab;
     // ---- misc
     Scalars *sc;
     int agg_cap, sph_cap, n_div, n_cells;

@@ -88,6 +88,11 @@ __global__ void k_rng_fill(GlibcRandState *st, int *out, int n) {  // n multiple
 // K9 — pick: one thread per speculative step j reads its three draws (pick, theta, phi), does
 // pick_random (lower_bound on the cumulative table, aggregat_list.cpp:59-66) and random_direction.
 // ------------------------------------------------------------------------------------------------
+// random_direction() for the draws at buffer positions (p, p + 1): from the host-evaluated table in strict replay mode
+__device__ __forceinline__ Vec3 dev_direction(const DevState &d, long long p) {
+    if (d.dir_tab) return Vec3{d.dir_tab[3 * p], d.dir_tab[3 * p + 1], d.dir_tab[3 * p + 2]};
+    return direction_from_draws(uniform_from_rand(d.rng_buf[p]), uniform_from_rand(d.rng_buf[p + 1]));
+}
 __device__ __forceinline__ void dev_prepare_query(const DevState &d, int j, int *q_slot, double *q_dir, double *q_dist) {
     Scalars &sc = *d.sc;
     const long long p = sc.rand_pos + 3LL * j - d.rng_buf_base;
@@ -99,8 +104,6 @@ __device__ __forceinline__ void dev_prepare_query(const DevState &d, int j, int 
         return;
     }
     const double u_pick = uniform_from_rand(d.rng_buf[p]);
-    const double u_theta = uniform_from_rand(d.rng_buf[p + 1]);
-    const double u_phi = uniform_from_rand(d.rng_buf[p + 2]);
     const int n = sc.n_pick;
     const double val = u_pick * d.cum[n - 1];
     int lo = 0, hi = n;  // std::lower_bound: first index with cum[i] >= val (every i < lo has cum[i] < val, every i >= hi cum[i] >= val)
@@ -129,7 +132,7 @@ __device__ __forceinline__ void dev_prepare_query(const DevState &d, int j, int 
         sc.error = 1; sc.error_detail = DETAIL_PICK_TABLE;
         slot = -1;
     }
-    const Vec3 dir = direction_from_draws(u_theta, u_phi);
+    const Vec3 dir = dev_direction(d, p + 1);
     q_slot[j] = slot;
     q_dir[3 * j] = dir.x;
     q_dir[3 * j + 1] = dir.y;
@@ -165,6 +168,7 @@ __global__ void k_labels_to_slots(DevState d, int nq, const long long *labels, i
 // aggregate): phase 1 (k_search_big_p1) leaves the eligible suspects here, the sphere-sphere sweep of all of them is cut into
 // tiles of (moving sphere, other sphere) pairs spread over the whole grid (k_search_big_p2), phase 3 (k_search_big_p3) reduces the
 // tiles in pair order and runs the reference's ordered scan.
+constexpr long long kPruneMinPairs = 4096;  // sphere pairs of two aggregates from which the ordered sweep prunes with enclosing balls
 constexpr int kBigTiles = 8192;
 struct BigSearch {
     int m, m_all, nb, pad;
@@ -183,7 +187,8 @@ struct BigSearch {
 template <int kPhase, int NT = kSearchThreads, bool kOrdered = false>
 __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const int *__restrict__ q_slot,
                                                 const double *__restrict__ q_dir, const double *__restrict__ q_dist,
-                                                SearchResult *__restrict__ out, BigSearch *__restrict__ big = nullptr) {
+                                                SearchResult *__restrict__ out, BigSearch *__restrict__ big = nullptr,
+                                                int *list_i = nullptr, int *list_j = nullptr /* kOrdered: >= spheres of an aggregate each */) {
     __shared__ int seg_beg[NT];
     __shared__ int seg_pre[NT + 1];
     __shared__ int warp_sums[32];
@@ -297,7 +302,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
         __syncthreads();
         double closest = INFINITY;  // the scan state is kept identically by every thread
         int who = -1;
-        long long who_pair = 0, examined = 0;
+        long long who_pair = 0, examined = 0, executed = 0;
         for (int r = 0; r < m; r++) {
             const int t = c_order[r];
             if (closest <= 0.) break;
@@ -307,6 +312,68 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
             const long long npairs = (long long)n_src * n_o;
             double best = INFINITY;
             long long best_p = npairs;
+            if (list_i && npairs >= kPruneMinPairs) {
+                // Pruned sweep (same result): only moving spheres that can reach the other aggregate's enclosing ball and other spheres
+                // the moving aggregate's enclosing ball can reach are paired (sweep_may_touch, mcac_math.cuh: a conservative
+                // necessary condition for a finite pair distance).  The balls are taken about the aggregate centres with radii
+                // recomputed from the relative positions (not the stored rmax, which growth can leave stale).
+                __shared__ double o_rad[2][32];
+                __shared__ int s_ni, s_nj;
+                const double mrx = d.a_rx[slot], mry = d.a_ry[slot], mrz = d.a_rz[slot];
+                const double orx = d.a_rx[o], ory = d.a_ry[o], orz = d.a_rz[o];
+                double rm = 0., ro = 0.;
+                for (int i2 = tid; i2 < n_src; i2 += NT) {
+                    const double4 rel = d.s_relv[off_src + i2];
+                    const double ex = rel.x - mrx, ey = rel.y - mry, ez = rel.z - mrz;
+                    const double t = sqrt(ex * ex + ey * ey + ez * ez) + d.s_posr[off_src + i2].w;
+                    rm = t > rm ? t : rm;
+                }
+                for (int j2 = tid; j2 < n_o; j2 += NT) {
+                    const double4 rel = d.s_relv[off_o + j2];
+                    const double ex = rel.x - orx, ey = rel.y - ory, ez = rel.z - orz;
+                    const double t = sqrt(ex * ex + ey * ey + ez * ez) + d.s_posr[off_o + j2].w;
+                    ro = t > ro ? t : ro;
+                }
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const double t0 = __shfl_xor_sync(kFull, rm, sft), t1 = __shfl_xor_sync(kFull, ro, sft);
+                    rm = t0 > rm ? t0 : rm;
+                    ro = t1 > ro ? t1 : ro;
+                }
+                if (lane == 0) { o_rad[0][warp] = rm; o_rad[1][warp] = ro; }
+                if (tid == 0) { s_ni = 0; s_nj = 0; }
+                __syncthreads();
+                rm = o_rad[0][0]; ro = o_rad[1][0];
+                for (int w = 1; w < nwarps; w++) { rm = o_rad[0][w] > rm ? o_rad[0][w] : rm; ro = o_rad[1][w] > ro ? o_rad[1][w] : ro; }
+                const double4 oc = d.a_posr[o];
+                for (int i2 = tid; i2 < n_src; i2 += NT) {
+                    const double4 p = d.s_posr[off_src + i2];
+                    if (sweep_may_touch(p.x, p.y, p.z, p.w, oc.x, oc.y, oc.z, ro, dx, dy, dz, dist, box)) list_i[atomicAdd(&s_ni, 1)] = i2;
+                }
+                for (int j2 = tid; j2 < n_o; j2 += NT) {
+                    const double4 p = d.s_posr[off_o + j2];
+                    if (sweep_may_touch(me.x, me.y, me.z, rm, p.x, p.y, p.z, p.w, dx, dy, dz, dist, box)) list_j[atomicAdd(&s_nj, 1)] = j2;
+                }
+                __syncthreads();
+                const int ni = s_ni, nj = s_nj;
+                const long long nsel = (long long)ni * nj;
+                if (nj > 0) {
+                    const int qs = NT / nj, rs = NT % nj;
+                    int ii = tid / nj, jj = tid % nj;
+                    for (long long p = tid; p < nsel; p += NT) {
+                        const int i2 = list_i[ii], j2 = list_j[jj];
+                        const double4 a = d.s_posr[off_src + i2];
+                        const double4 b = d.s_posr[off_o + j2];
+                        const double c = pair_contact_distance(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, dx, dy, dz, dist, box);
+                        const long long pp = (long long)i2 * n_o + j2;
+                        if (c < best || (c == best && pp < best_p)) { best = c; best_p = pp; }  // the lists are unordered
+                        jj += rs; ii += qs;
+                        if (jj >= nj) { jj -= nj; ii++; }
+                    }
+                }
+                executed += nsel + n_src + n_o;
+                __syncthreads();  // the lists are reused by the next suspect
+            } else {
             // pair p = i * n_o + j (moving sphere i outer, other sphere j inner: the reference's visiting order), NT pairs at a time
             const int qs = NT / n_o, rs = NT % n_o;
             int i = tid / n_o, j = tid % n_o;
@@ -317,6 +384,8 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
                 if (c < best) { best = c; best_p = p; }
                 j += rs; i += qs;
                 if (j >= n_o) { j -= n_o; i++; }
+            }
+            executed += npairs;
             }
             warp_argmin(best, best_p);
             if (lane == 0) { o_best[warp] = best; o_pair[warp] = best_p; }
@@ -340,6 +409,7 @@ __device__ __forceinline__ void search_wide_one(const DevState &d, int q, const 
                 res.other_agg = o;
             }
             out[q] = res;
+            d.sc->pair_exec += executed;
         }
         return;
     }
@@ -1485,7 +1555,7 @@ __global__ void __launch_bounds__(1024) k_pick_last(DevState d, int *q_slot) { d
 __device__ __forceinline__ void dev_prepare_direction(const DevState &d, int *q_slot, double *q_dir, double *q_dist, long long draw_offset) {
     if (threadIdx.x != 0) return;
     const long long p = d.sc->rand_pos + draw_offset - d.rng_buf_base;
-    const Vec3 dir = direction_from_draws(uniform_from_rand(d.rng_buf[p]), uniform_from_rand(d.rng_buf[p + 1]));
+    const Vec3 dir = dev_direction(d, p);
     q_dir[0] = dir.x; q_dir[1] = dir.y; q_dir[2] = dir.z;
     q_dist[0] = d.a_lpm[q_slot[0]];
 }
@@ -2377,7 +2447,8 @@ struct EventArgs {
     int cum_sequential_max, stable;
     int use_factor;       // sort_time_steps(factor) called with an explicit factor (per-call C ABI)
     double factor;
-    int local_span;       // span (elements) below which block 0 finishes the sort alone
+    int local_span;       // span (elements) that fits the shared-memory staging of the block-local levels
+    int switch_span;      // span (elements) below which block 0 finishes the sort alone (>= local_span)
     int smem_cap;         // entries of dynamic shared memory per array available to the block-local levels (0 = none)
     int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
     int depth_override;   // test hook (MCAC_B200_SORT_DEPTH): introsort depth limit instead of 2*log2(n); < 0 = off
@@ -2906,7 +2977,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     // Work is restricted to the span [amin, amax) of the still-active segments (all-equal segments leave the loop
     // analytically, so in tie-dominated tables the span halves every level).  Once the span fits kSortLocal elements,
     // block 0 finishes the remaining levels alone with __syncthreads() instead of grid barriers.
-    const int kSortLocal = a.local_span;
+    // Two thresholds: below `switch_span` elements block 0 works alone (block barriers instead of grid barriers; the state still in
+    // HBM / L2: a span of ~10^4 elements gains nothing from more CTAs and each grid barrier costs ~3 us), and once the span also fits
+    // the shared-memory staging area (smem_cap, sized by local_span) the remaining levels run out of shared memory.
+    const int kSortSwitch = a.switch_span > a.local_span ? a.switch_span : a.local_span;
     int eblk = blk, enblk = nblk;
     long long etid = gtid, esize = gsize;
     auto barrier = [&]() { if (local) __syncthreads(); else grid.sync(); };
@@ -2922,12 +2996,15 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     while (active) {
         depth--;
         const int amin = act[4 + 2 * (level & 1)], amax = act[5 + 2 * (level & 1)];
-        if (!local && amax - amin <= kSortLocal) {
+        if (!local && amax - amin <= kSortSwitch) {
             local = true;
             if (blk != 0) break;  // the other blocks wait at the barrier behind the loop
             eblk = 0; enblk = 1; etid = tid; esize = nthr;
             if (tid < 8) sh_act[tid] = b.active[tid];
             act = sh_act;
+            __syncthreads();
+        }
+        if (local && !staged) {  // (block 0 only from here on)
             if (amax - amin + 2 <= a.smem_cap) {
                 // The remaining levels run out of shared memory: the span's sort state is staged once (element i lives at
                 // index i - amin; entry `amax` is a sentinel that reads as a finished segment), so each of the ~log2(span / 16)
@@ -3100,7 +3177,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         barrier();
         // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
         int lead_min = 0x7fffffff, lead_max = 0;  // span of the new segments this thread leads
-        for (long long i = amin + etid; i < amax; i += esize) {
+        // (the swap pass may already have hit the depth limit inside an all-equal segment: some of its elements are finished, the others
+        // are not, and the segment has no cut — nothing below may touch it; the loop ends on `fail` right after this pass)
+        const bool failed_in_swap = act[2] != 0;
+        for (long long i = amin + etid; i < amax && !failed_in_swap; i += esize) {
             const int f = b.segf[i], l = b.segl[i];
             if (l - f <= kSortLeaf) continue;
             const int c = b.cut[f];

@@ -127,6 +127,43 @@ MCAC_HD double pair_contact_distance(double p1x, double p1y, double p1z, double 
     return res;
 }
 
+// Conservative companion of the pair test, for pruning sphere-pair sweeps between big aggregates without changing their result:
+// can ANY sphere lying inside the ball (c2, r2) — or the ball itself — give a finite pair_contact_distance against a moving sphere
+// that lies inside the ball (p1, r1)?  A finite pair result needs a periodic image q of the static sphere with 0 <= proj <= dist
+// (or the end-of-move overlap: proj <= dist + r1' + r2') and an axis distance <= r1' + r2', or an overlap at the start: in every
+// case q is within r1' + r2' of the segment [p1', p1' + (dist + r1' + r2') dir].  Moving both spheres to the centres of their
+// enclosing balls changes that distance by at most (r1 - r1') + (r2 - r2') and lengthens the segment, hence the test below:
+// some image of c2 within r1 + r2 of the segment [p1, p1 + (dist + r1 + r2) dir].  False => every enclosed pair returns +inf.
+MCAC_HD bool sweep_may_touch(double p1x, double p1y, double p1z, double r1, double c2x, double c2y, double c2z, double r2,
+                             double dx, double dy, double dz, double dist, double box) {
+    const double rsum = (r1 + r2) * (1. + 1e-9) + 1e-12 * box;  // slack for the rounding of positions / radii of the enclosed spheres
+    const double rsum2 = rsum * rsum;
+    const double len = dist + rsum;
+    const double p1[3] = {p1x, p1y, p1z}, dir[3] = {dx, dy, dz};
+    double c[3] = {c2x, c2y, c2z};
+    int nper[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const double moved = p1[l] + dir[l] * len;
+        const double lo = ((moved < p1[l]) ? moved : p1[l]) - rsum;
+        const double hi = ((p1[l] < moved) ? moved : p1[l]) + rsum;
+        double w = fmod(c[l] - lo, box);
+        if (w < 0) w += box;
+        c[l] = w + lo;  // the image in [lo, lo + box); further images at + k box while they are <= hi
+        nper[l] = static_cast<int>(floor((hi - lo) / box));
+    }
+    for (int i = 0; i <= nper[0]; i++)
+        for (int j = 0; j <= nper[1]; j++)
+            for (int k = 0; k <= nper[2]; k++) {
+                const double fx = c[0] + i * box - p1[0], fy = c[1] + j * box - p1[1], fz = c[2] + k * box - p1[2];
+                double t = fx * dir[0] + fy * dir[1] + fz * dir[2];
+                t = t < 0. ? 0. : (t > len ? len : t);
+                const double ex = fx - t * dir[0], ey = fy - t * dir[1], ez = fz - t * dir[2];
+                if (ex * ex + ey * ey + ez * ez <= rsum2) return true;
+            }
+    return false;
+}
+
 // --------------------------------------------------------------------------------------------------
 // Verlet cell range swept by a move (src/verlet/verlet.cpp:52-79): inclusive, un-wrapped cell indices.
 // `reach` = rmax(source) + maxradius; (vx,vy,vz) = distance * direction.

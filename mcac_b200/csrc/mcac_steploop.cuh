@@ -24,6 +24,9 @@ struct LoopState {  // device-resident, one per handle: what the host reads back
     int pick_valid, labels_valid;
     long long steps;    // MC steps done by this launch
     long long events, nucleated, sorts, compactions;
+    // SM cycles of the CTA per part of the step: 0 pick table (labels + sort), 1 cells + contact search (+ redraws), 2 move + growth +
+    // merge + updates, 3 nucleation + bookkeeping + refresh, 4 loop top (checks, compaction)
+    long long phase_cycles[5];
 };
 struct LoopArgs {
     int *q_slot;
@@ -42,6 +45,7 @@ struct LoopArgs {
     int cum_sequential_max, stable, depth_override;
     int pick_valid, labels_valid, stop_at_event;
     int max_slots;                   // the loop hands back (LOOP_TOO_BIG) when the aggregate table outgrows this
+    int prune;                       // 0: every sphere pair of an examined suspect is tested (MCAC_B200_NO_PRUNE)
     LoopState *out;
 };
 
@@ -392,7 +396,12 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
     bool pick_valid = a.pick_valid != 0, labels_valid = a.labels_valid != 0;
     long long steps = 0;
     int reason = LOOP_STEPS_DONE;
-    if (tid == 0) { out.steps = 0; out.events = 0; out.nucleated = 0; out.sorts = 0; out.compactions = 0; out.flipped = 0; out.exit_reason = LOOP_STEPS_DONE; }
+    if (tid == 0) {
+        out.steps = 0; out.events = 0; out.nucleated = 0; out.sorts = 0; out.compactions = 0; out.flipped = 0; out.exit_reason = LOOP_STEPS_DONE;
+        for (int k = 0; k < 5; k++) out.phase_cycles[k] = 0;
+    }
+    long long t_prev = clock64();
+    auto lap = [&](int k) { if (tid == 0) { const long long t = clock64(); out.phase_cycles[k] += t - t_prev; t_prev = t; } };
     __syncthreads();
     while (steps < a.max_steps) {
         // ---- loop top of calcul(): PhysicalModel::finished, duplication test, room in the tables, draws staged
@@ -407,6 +416,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
         if (d.sph_cap - sc.pool_top < sc.n_sph) cta_compact_pool(d, a, a.scan_tmp);
         if (a.with_nucleation && (d.agg_cap - sc.n_agg_slots < 64 || d.sph_cap - sc.pool_top < sc.n_sph + 64)) { reason = LOOP_NEED_REGROW; break; }
         if (sc.rand_pos < d.rng_buf_base || sc.rand_pos - d.rng_buf_base + 8192 + 64 > d.rng_buf_n) { reason = LOOP_NEED_RNG; break; }
+        lap(4);
         // ---- pick table
         if (!labels_valid) { cta_labels(d, a.scan_tmp); labels_valid = true; }
         if (!a.pick_last && (sc.event || a.growth || !pick_valid)) {
@@ -414,6 +424,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             pick_valid = true;
             if (tid == 0) out.sorts += 1;
         }
+        lap(0);
         // ---- pick + direction
         if (a.pick_last) {
             dev_pick_last(d, a.q_slot);
@@ -427,7 +438,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
         // ---- contact search + orientation loop (calcul.cpp:119-141)
         if (a.with_collisions) {
             cta_build_cells(d);
-            search_wide_one<0, kLoopThreads, true>(d, 0, a.q_slot, a.q_dir, a.q_dist, a.q_res);
+            search_wide_one<0, kLoopThreads, true>(d, 0, a.q_slot, a.q_dir, a.q_dist, a.q_res, nullptr, a.prune ? a.alt_id : nullptr, a.alt_charge);
             __syncthreads();
             while (a.with_potentials) {
                 dev_check_regime(d, a.q_res, a.q_dist, s_draws);
@@ -448,11 +459,12 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
                 dev_prepare_direction(d, a.q_slot, a.q_dir, a.q_dist, s_draws);
                 if (tid == 0) { s_draws += 2; s_draws_at_search = s_draws; }
                 __syncthreads();
-                search_wide_one<0, kLoopThreads, true>(d, 0, a.q_slot, a.q_dir, a.q_dist, a.q_res);
+                search_wide_one<0, kLoopThreads, true>(d, 0, a.q_slot, a.q_dir, a.q_dist, a.q_res, nullptr, a.prune ? a.alt_id : nullptr, a.alt_charge);
                 __syncthreads();
             }
             if (sc.error != 0) { reason = LOOP_ERROR; break; }
         }
+        lap(1);
         // ---- move + clocks, growth, deferred merge
         const long long iter_before = sc.n_iter_without_event;
         StepArgs sa;
@@ -501,6 +513,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             }
             __syncthreads();
         }
+        lap(2);
         // ---- nucleation, event bookkeeping, refresh / PhysicalModel::update
         if (a.with_nucleation) dev_nucleate(d, 0., 1);
         else if (tid == 0) sc.n_nucleated = 0;
@@ -508,6 +521,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
         dev_step_event(d);
         __syncthreads();
         cta_refresh(d, a.growth != 0);
+        lap(3);
         if (sc.error != 0) { reason = LOOP_ERROR; break; }
         steps += 1;
         const bool merged = sc.b_merged != 0, nucl = sc.n_nucleated > 0;

@@ -17,8 +17,12 @@
 #pragma once
 #ifdef __CUDACC__
 #define TS_HD __host__ __device__ __forceinline__
+// (rank queries out of line — __noinline__ — were tried to shrink the level loop of the sparse simulation: 104 us instead of 92 us
+// per sort at ~3900 sparse elements, profiles/r2_tuning.md; they stay inlined)
+#define TS_HD_CALL __host__ __device__ __forceinline__
 #else
 #define TS_HD inline
+#define TS_HD_CALL inline
 #endif
 
 namespace tiesort {
@@ -52,7 +56,7 @@ struct Plan {
 
 // entries of the sorted list R with position < q; tbl[b] = entries whose bucket ((pos - f) >> shift) is below b
 template <class PR, class PT>
-TS_HD int rank_lt(PR R, PT tbl, int f, int shift, int q) {
+TS_HD_CALL int rank_lt(PR R, PT tbl, int f, int shift, int q) {
     const int b = (q - f) >> shift;
     int j = tbl[b];
     const int e = tbl[b + 1];
@@ -61,7 +65,7 @@ TS_HD int rank_lt(PR R, PT tbl, int f, int shift, int q) {
 }
 // k-th (0-based) position of [f+1, l) that holds no sparse element
 template <class PR, class PT>
-TS_HD int select_dense(PR R, PT tbl, int f, int shift, int k) {
+TS_HD_CALL int select_dense(PR R, PT tbl, int f, int shift, int k) {
     int q = f + 1 + k;
     for (int it = 0; it < kMaxSparse + 2; it++) {  // monotone fixed point; q grows by at least one sparse element per round
         const int q2 = f + 1 + k + rank_lt(R, tbl, f, shift, q + 1);

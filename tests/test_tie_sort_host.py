@@ -24,3 +24,14 @@ def test_heap_sort_header_reproduces_libstdcxx_heap_branch(tmp_path):
     out = subprocess.run([str(exe), "300", "7"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("ok 300 cases"), out.stdout
+
+
+def test_enclosing_ball_pruning_never_drops_a_finite_pair(tmp_path):
+    """sweep_may_touch (csrc/mcac_math.cuh), the pruning of the step loop's sphere-pair sweeps, against the exact pair test on
+    random aggregate pairs with un-wrapped positions, several periodic images, grazing contacts and overlapping starts."""
+    exe = tmp_path / "prune_host"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", str(exe), str(ROOT / "tests" / "native" / "prune_host.cpp")])
+    for seed in (3, 11):
+        out = subprocess.run([str(exe), "20000", str(seed)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.startswith("ok 20000 cases"), out.stdout
