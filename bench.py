@@ -180,16 +180,7 @@ def ensemble_main(a, rank: int, world: int, local: int):
                                            "sample": f"{r['cores']} realizations in parallel (one pinned process per core), {W + K} x {M} MC steps each, cpu: {cpu_model()}"},
                           "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    import tempfile
-
-    import numpy as np
     import torch
-
-    import mcac_b200
-    from mcac_b200 import ensemble as ens
-
-    sys.path.insert(0, str(ROOT / "tests"))
-    from golden_lib import write_interpotential_file  # the committed copy of the table classic.ini points at (fixture data)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mcac_b200 has no CPU fallback")
@@ -199,8 +190,32 @@ def ensemble_main(a, rank: int, world: int, local: int):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = ensemble_measure(a, rank, world, local, dist, config, metric, unit, K, W, M, R)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ensemble_measure(a, rank, world, local, dist, config, metric, unit, K, W, M, R):
+    """The ensemble workload on the ranks of `dist` (None: this process alone); returns the JSON line on rank 0."""
+    import tempfile
+
+    import numpy as np  # noqa: F401
+    import torch
+
+    import mcac_b200
+    from mcac_b200 import ensemble as ens
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from golden_lib import write_interpotential_file  # the committed copy of the table classic.ini points at (fixture data)
+
     tmp = tempfile.mkdtemp(prefix="mcac_ens_")
     table = write_interpotential_file(Path(tmp) / "Interpotential_input.dat")
+    # room for the three domain duplications of the run (100 -> 51 200 spheres + nucleated monomers) from the start, so that the device
+    # loop duplicates by itself (mcac_gpu_reserve; ~40 MB per realization)
+    os.environ.setdefault("MCAC_B200_RESERVE_SPHERES", "60000")
+    os.environ.setdefault("MCAC_B200_RESERVE_AGGREGATES", "4096")
     mine = ens.shard(R, rank, world)
     threads = a.threads or max(1, min(32, (os.cpu_count() or 8) // max(1, world)))
     t0 = time.perf_counter()
@@ -220,8 +235,9 @@ def ensemble_main(a, rank: int, world: int, local: int):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
-    steps_done = launches = events = pair_tests = pair_exec = 0
-    phase_cycles = [0] * 5
+    steps_done = launches = events = pair_tests = pair_exec = rounds = 0
+    kernel_ms = 0.0
+    phase_cycles = [0] * 8
     stats_s = 0.0
     d2h = 0
     rows = None
@@ -232,7 +248,9 @@ def ensemble_main(a, rank: int, world: int, local: int):
         events += sum(r["events"] for r in reps)
         pair_tests += sum(r["pair_tests_sphere"] + r["pair_tests_bounding"] for r in reps)
         pair_exec += sum(r["pair_tests_executed"] for r in reps)
-        for k in range(5):
+        kernel_ms += reps[0]["device_ms"] if reps else 0.0
+        rounds += reps[0]["conflicts"] if reps else 0
+        for k in range(8):
             phase_cycles[k] += sum(r["loop_phase_cycles"][k] for r in reps)
         # the step's result: the statistic rows of every realization cross to the host (timed apart: only e2e includes it)
         t_s = time.perf_counter()
@@ -252,6 +270,7 @@ def ensemble_main(a, rank: int, world: int, local: int):
     te = torch.tensor([float(t[1]), float(tot[0])], dtype=torch.float64, device="cuda")
     # the only collective of the path
     full = ens.gather_rows(rows, mine, R, dist=dist, device="cuda")
+    line = None
     if rank == 0:
         value = float(tot[0]) / float(t[0])
         # the dominant kernel is k_ensemble_loop; its time is the sphere-pair sweep of the contact search (FP64-pipe-bound: both
@@ -264,9 +283,9 @@ def ensemble_main(a, rank: int, world: int, local: int):
         pair_rate = float(tot[3]) / float(t[0])
         exec_rate = float(tot[4]) / float(t[0])  # sphere-pair tests the pruned sweeps actually executed
         fp64_tflops = exec_rate * 104.0 / 1e12
-        cyc = [float(x) for x in tot[5:10]]
+        cyc = [float(x) for x in tot[5:13]]
         phase_share = {n: (c / sum(cyc) if sum(cyc) else None) for n, c in
-                       zip(["pick_table", "cells_and_search", "move_growth_merge_update", "nucleation_refresh", "loop_top"], cyc)}
+                       zip(["pick_table", "cells_and_search", "update_block", "nucleation_refresh", "loop_top", "move", "growth", "merge"], cyc)}
         peaks = {}
         try:
             peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
@@ -283,13 +302,15 @@ def ensemble_main(a, rank: int, world: int, local: int):
                                           f"(timed: the last {K} x {M}), cpu: {cpu_model()}"}
             except Exception as ex:  # noqa: BLE001
                 cpu_baseline = {"value": None, "unit": unit, "cores": None, "kind": "reference", "sample": f"unavailable: {str(ex)[:160]}"}
-        print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+        line = ({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
                           "ms_per_step": 1e3 * float(t[0]) / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f64", "data": "synthetic", "config": dict(config, host_threads_per_rank=threads),
                           "timing": "wall clock between device synchronisations around the K steps (every step = rounds of one k_ensemble_loop launch + "
                                     "host services), max over ranks",
                           "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "pair_tests_per_sec": pair_rate,
                           "pair_tests_executed_per_sec": exec_rate, "loop_phase_share": phase_share, "init_s": init_s, "clocks": clocks,
+                          "rank0_kernel_ms_per_step": kernel_ms / K, "rank0_rounds_per_step": rounds / K,
+                          "rank0_kernel_share_of_wall": kernel_ms * 1e-3 / (wall_s - stats_s) if wall_s > stats_s else None,
                           "e2e": {"value": float(te[1]) / float(te[0]), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
                                   "what": "mcac_ensemble_run(M steps per realization) + mcac_gpu_morphology_stats of every realization to the host, per step; "
                                           "the realizations are created on the host (placement) and live in HBM from then on"},
@@ -301,10 +322,10 @@ def ensemble_main(a, rank: int, world: int, local: int):
                                        "note": "algorithmic bytes = 32 B per sphere-pair test; the sweep re-reads two aggregates from L1/L2, so the binding "
                                                "roofline is the FP64 pipe: 104 FP64 ops per pair test against the DMUL+DADD peak measured by "
                                                "k_fp64_peak<1> (the library is built --fmad=false)"},
-                          "cpu_baseline": cpu_baseline, "ensemble_stats": ens.summarize(full)}))
+                          "cpu_baseline": cpu_baseline, "ensemble_stats": ens.summarize(full)})
     shutil.rmtree(tmp, ignore_errors=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del e
+    return line
 
 
 def main():
@@ -319,6 +340,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--no-ensemble", action="store_true", help="c3 workload at one GPU: do not append the 1-GPU point of the ensemble workload")
     ap.add_argument("--workload", default=None, choices=["c3", "ensemble"],
                     help="c3: BASELINE's N=1e6 metric (default).  ensemble: --realizations independent runs of examples/classic.ini "
                          "(seeds 1000+k) sharded k -> rank k mod N, all-gather of the morphology statistics at the end")
@@ -580,6 +602,20 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {str(e)[:160]}"}
 
+    ensemble_point = None
+    if world == 1 and not a.no_ensemble:
+        # the multi-GPU workload of BASELINE.json (what `--gpus N` runs for N > 1) at ONE GPU, so that its scaling can be read against
+        # this run: value(N) / (N * ensemble.value)
+        del sim
+        Me = -(-ENSEMBLE_TOTAL_STEPS // max(1, W + K))
+        econf = {"workload": "ensemble", "realizations": a.realizations, "mc_steps_per_step": Me, "stop": f"MC-step count: {(W + K) * Me} steps per realization"}
+        a_e = argparse.Namespace(**{**vars(a), "no_cpu_baseline": True})
+        try:
+            e_line = ensemble_measure(a_e, 0, 1, local, None, econf, "ensemble_mc_steps_per_sec", "MC steps/s (sum over realizations)", K, W, Me, a.realizations)
+            ensemble_point = {k: e_line[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "pair_tests_per_sec", "pair_tests_executed_per_sec",
+                                                     "loop_phase_share", "e2e", "gpu_launches", "roofline")}
+        except Exception as ex:  # noqa: BLE001
+            ensemble_point = {"unavailable": str(ex)[:200]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -587,7 +623,7 @@ def main():
                 "events_timed": sum(r["events"] for r in reps), "wall_ms_per_step": float(t[1]) / K, "init_placement_s": init_s,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[2]), "roofline": roofline, "roofline_k1_inloop": roofline_k1_inloop,
                 "roofline_k1_sweep": roofline_sweep, "kernels": kernels,
-                "cpu_baseline": cpu_baseline, "ensemble_stats": ensemble}
+                "cpu_baseline": cpu_baseline, "ensemble_stats": ensemble, "ensemble": ensemble_point}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

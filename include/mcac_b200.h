@@ -104,8 +104,9 @@ typedef struct mcac_run_report {
      * (they execute what they count). */
     int64_t pair_tests_executed;
     /* SM cycles of the step loop's CTA per part of the step: 0 pick table (labels + sort), 1 cell rebuild + contact search (+ redraws),
-     * 2 move + growth + merge + updates, 3 nucleation + bookkeeping + refresh, 4 loop top (checks, pool compaction) */
-    int64_t loop_phase_cycles[5];
+     * 2 update block (calcul.cpp:184-206), 3 nucleation + bookkeeping + refresh, 4 loop top (checks, pool compaction), 5 move + clocks,
+     * 6 surface growth, 7 merge (incl. Aggregate::update of the merged aggregate) */
+    int64_t loop_phase_cycles[8];
 } mcac_run_report;
 
 /* One launch of K1 over `n` independent speculative searches drawn from the handle's RNG stream (pick + direction
@@ -195,6 +196,9 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_p
 /* on != 0: mcac_gpu_run returns right after the step that made an event (merge or nucleation: `event` of calcul.cpp:222), so that a
  * host loop can do what calcul() does between events (advancement.dat rows, the progress table, output files) */
 int mcac_gpu_set_stop_at_event(mcac_gpu *h, int32_t on);
+/* Table sizes to allocate at least at the next mcac_gpu_upload_state / regrow (std::vector::reserve of the reference's ListStorage
+ * vectors, include/list_storage/list_storage.hpp:32-34): with room for the next domain duplications the device loop does them itself. */
+int mcac_gpu_reserve(mcac_gpu *h, int64_t n_spheres, int64_t n_aggregates);
 /* on != 0: strict replay mode.  random_direction() (src/tools/tools.cpp:82-89) is evaluated on the host with glibc's sin / cos / acos for
  * every staged pair of draws and read from a table by the kernels, so directions — and with them contact distances, positions and
  * clocks — are the reference's bit for bit instead of within 2 ulp of CUDA's sincos / acos (costs one host pass per ~10^6 draws). */

@@ -69,7 +69,7 @@ class RunReport(C.Structure):
                [(n, C.c_int64) for n in ["tie_sorts", "tie_levels", "tie_sparse", "tie_handed"]] + \
                [("tie_sim_cycles", C.c_int64 * 3)] + \
                [(n, C.c_int64) for n in ["sort_fallbacks", "sort_heap_branches", "pair_tests_executed"]] + \
-               [("loop_phase_cycles", C.c_int64 * 5)]
+               [("loop_phase_cycles", C.c_int64 * 8)]
 
     def as_dict(self) -> dict:
         return {n: (list(getattr(self, n)) if n.endswith("_cycles") else getattr(self, n)) for n, _ in self._fields_}
@@ -100,7 +100,7 @@ EXPORTS = [
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_ini_echo", "mcac_host_model_state", "mcac_sim_create",
     "mcac_io_writer_create", "mcac_io_begin_step", "mcac_io_positions", "mcac_io_attribute", "mcac_io_end_step", "mcac_io_writer_destroy",
-    "mcac_gpu_save", "mcac_gpu_set_strict_direction",
+    "mcac_gpu_save", "mcac_gpu_set_strict_direction", "mcac_gpu_reserve",
 ]
 
 
@@ -164,6 +164,7 @@ def lib() -> C.CDLL:
         L.mcac_io_writer_destroy.argtypes = [vp]
         L.mcac_gpu_save.argtypes = [vp, vp, vp]
         L.mcac_gpu_set_strict_direction.argtypes = [vp, C.c_int32]
+        L.mcac_gpu_reserve.argtypes = [vp, i64, i64]
         _lib = L
     return _lib
 

@@ -131,9 +131,11 @@ struct mcac_gpu {
     bool strict_dir = false;      // MCAC_B200_STRICT_DIRECTION / mcac_gpu_set_strict_direction: directions evaluated by the host's glibc
     bool dir_tab_valid = false;
     double *dir_tab = nullptr;
+    bool loop_dups = true;        // MCAC_B200_NO_LOOP_DUP=1: the loop hands every domain duplication to the host
+    long long reserve_sph = 0, reserve_agg = 0;  // mcac_gpu_reserve / MCAC_B200_RESERVE_SPHERES, _AGGREGATES: table sizes to allocate at least
     bool loop_prune = true;       // MCAC_B200_NO_PRUNE=1: the ordered sweep tests every sphere pair of an examined suspect
     long long loop_launches = 0, loop_steps = 0;
-    long long loop_cycles[5] = {0, 0, 0, 0, 0}, loop_cycles_seen[5] = {0, 0, 0, 0, 0};
+    long long loop_cycles[8] = {0}, loop_cycles_seen[8] = {0};
     void *stage = nullptr;  // device staging of the host-layout arrays at the upload / download boundary
     size_t stage_bytes = 0;
 };
@@ -584,6 +586,7 @@ struct HostOut {
     double *per_member, *scalars;
 };
 int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_step);
+bool is_speculative(const mcac_gpu *h);
 int upload(mcac_gpu *h, const HostState &s, double maxradius, double max_time_step, bool keep_scalars);
 int download(mcac_gpu *h, HostState &s);
 int download_to(mcac_gpu *h, const HostOut &o);
@@ -763,7 +766,11 @@ int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_ste
     if (n_agg <= 0 || n_sph <= 0) { h->err = "upload_state: empty state"; return E_INPUT; }
     if (s.offsets[0] != 0 || s.offsets[n_agg] != n_sph) { h->err = "upload_state: membership offsets do not cover the spheres"; return E_INPUT; }
     const long long headroom = h->prm.with_nucleation ? std::max<long long>(h->nucl_headroom > 0 ? 0 : n_agg, h->nucl_headroom > 0 ? h->nucl_headroom : 4096) : 0;  // slots for nucleated monomers
-    const long long need_agg = n_agg + headroom, need_sph = 3 * (n_sph + headroom) + 1024;
+    // tables: what the state needs now, or more when the caller reserved room (mcac_gpu_reserve) or — small realizations that duplicate
+    // their domain — for the next duplication (x8), so that the step loop can do it without the host
+    long long want_sph = std::max(n_sph, h->reserve_sph), want_agg = std::max(n_agg, h->reserve_agg);
+    if (h->prm.with_domain_duplication && !is_speculative(h) && n_sph <= 100000) { want_sph = std::max(want_sph, 8 * n_sph); want_agg = std::max(want_agg, 8 * n_agg); }
+    const long long need_agg = want_agg + headroom, need_sph = 3 * (want_sph + headroom) + 1024;
     if (h->owned.empty() || d.agg_cap < need_agg || d.sph_cap < need_sph) {  // otherwise the resident allocation is reused
         free_all(h);
         TRY(alloc_state(h, need_agg, need_sph));
@@ -1002,6 +1009,8 @@ void loop_fill_args(mcac_gpu *h, LoopArgs &a, long long max_steps, mcac_step_rec
     a.stop_at_event = h->stop_at_event ? 1 : 0;
     a.max_slots = h->fused_max_slots;
     a.prune = h->loop_prune ? 1 : 0;
+    a.dups_allowed = h->loop_dups ? 4 : 0;
+    for (int k = 0; k < 4; k++) a.dup_box_volume[k] = std::pow(h->prm.box_length * (double)(2 << k), 3);  // duplicate(): box x2, std::pow(box, 3)
     a.out = h->loop_dev;
 }
 // host-side bookkeeping after a loop launch: the pool may have been compacted (buffers swapped), validity flags
@@ -1012,12 +1021,17 @@ void loop_apply(mcac_gpu *h, const LoopState &ls) {
         std::swap(d.s_veff, h->alt.s_veff); std::swap(d.s_seff, h->alt.s_seff); std::swap(d.s_dcen, h->alt.s_dcen);
         std::swap(d.s_id, h->alt.s_id); std::swap(d.s_charge, h->alt.s_charge);
     }
+    for (long long k = 0; k < ls.dups; k++) {  // the host's mirror of the box (duplicate(): aggregat_list.cpp:145-148)
+        h->prm.box_length = h->prm.box_length * 2;
+        h->prm.n_monomeres *= 8;
+        h->prm.box_volume = std::pow(h->prm.box_length, 3);
+    }
     h->pick_valid = ls.pick_valid != 0;
     h->labels_valid = ls.labels_valid != 0;
     h->cells_valid = false;
     h->loop_launches++;
     h->loop_steps += ls.steps;
-    for (int k = 0; k < 5; k++) h->loop_cycles[k] += ls.phase_cycles[k];
+    for (int k = 0; k < 8; k++) h->loop_cycles[k] += ls.phase_cycles[k];
 }
 // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up.  This renumbers the
 // aggregate slots (slot = label again), so it must come BEFORE the pick table of the step is built.
@@ -1082,6 +1096,9 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_SORT_DEPTH")) h->sort_depth_override = std::max(0, atoi(e));
         if (getenv("MCAC_B200_NO_LOOP")) h->fused = false;
         if (getenv("MCAC_B200_NO_PRUNE")) h->loop_prune = false;
+        if (getenv("MCAC_B200_NO_LOOP_DUP")) h->loop_dups = false;
+        if (const char *e = getenv("MCAC_B200_RESERVE_SPHERES")) h->reserve_sph = std::max(0LL, atoll(e));
+        if (const char *e = getenv("MCAC_B200_RESERVE_AGGREGATES")) h->reserve_agg = std::max(0LL, atoll(e));
         if (getenv("MCAC_B200_STRICT_DIRECTION")) h->strict_dir = true;
         if (const char *e = getenv("MCAC_B200_LOOP_MAX_SLOTS")) h->fused_max_slots = std::max(1, atoi(e));
         if (const char *e = getenv("MCAC_B200_SEARCH_GROUP")) h->search_group = atoi(e);
@@ -1118,6 +1135,10 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<1>, kEventThreads, dyn);
         if (coop && oe == cudaSuccess && occ > 0) h->coop_blocks = h->n_sm * std::min(occ, h->coop_bps);
         if (getenv("MCAC_B200_NO_COOP")) h->coop_blocks = 0;
+        // the step-loop kernels use 31 KB of static + 20 KB of dynamic shared memory: opt in above 48 KB
+        cudaFuncSetAttribute(k_step_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoopDynSmem);
+        cudaFuncSetAttribute(k_ensemble_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoopDynSmem);
+        cudaGetLastError();
         TRY(dev_alloc_persistent(h, &h->event_work, 32));
         CK(cudaMemset(h->event_work, 0, 32 * sizeof(long long)));
         TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
@@ -1505,7 +1526,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             if ((rc = ensure_rng(h, h->sc_host.rand_pos + 8192 + 64 + 31)) != E_OK) break;
             LoopArgs la;
             loop_fill_args(h, la, max_steps - steps, (records && n_records > 0) ? h->rec_dev : nullptr, n_records, steps);
-            k_step_loop<<<1, kLoopThreads, 0, h->stream>>>(h->d, la);
+            k_step_loop<<<1, kLoopThreads, kLoopDynSmem, h->stream>>>(h->d, la);
             h->launches++;
             if (cudaGetLastError() != cudaSuccess) { h->err = "step loop launch failed"; rc = E_UNKNOWN; break; }
             if (cudaMemcpyAsync(h->loop_host, h->loop_dev, sizeof(LoopState), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = E_UNKNOWN; break; }
@@ -1514,6 +1535,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             loop_apply(h, ls);
             steps += ls.steps;
             batches += ls.steps;
+            dups += ls.dups;
             sorts += ls.sorts;
             nucleated_total += ls.nucleated;
             if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rc = device_error(h, h->sc_host, "mcac_gpu_run"); break; }
@@ -1843,7 +1865,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->pair_tests_sphere = sc.pair_sphere - at_start.pair_sphere;
         report->pair_tests_bounding = sc.pair_bounding - at_start.pair_bounding;
         report->pair_tests_executed = sc.pair_exec - at_start.pair_exec;
-        for (int k = 0; k < 5; k++) { report->loop_phase_cycles[k] = h->loop_cycles[k] - h->loop_cycles_seen[k]; h->loop_cycles_seen[k] = h->loop_cycles[k]; }
+        for (int k = 0; k < 8; k++) { report->loop_phase_cycles[k] = h->loop_cycles[k] - h->loop_cycles_seen[k]; h->loop_cycles_seen[k] = h->loop_cycles[k]; }
         report->batches = batches;
         report->conflicts = sc.conflicts - at_start.conflicts;
         report->duplications = dups;
@@ -1887,6 +1909,12 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
 }
 
 int mcac_gpu_set_profile(mcac_gpu *h, int32_t profile) { h->profile = profile; return E_OK; }
+int mcac_gpu_reserve(mcac_gpu *h, int64_t n_spheres, int64_t n_aggregates) {
+    if (n_spheres < 0 || n_aggregates < 0) { h->err = "reserve: negative size"; return E_INPUT; }
+    h->reserve_sph = n_spheres;
+    h->reserve_agg = n_aggregates;
+    return E_OK;
+}
 int mcac_gpu_set_strict_direction(mcac_gpu *h, int32_t on) {
     h->strict_dir = on != 0;
     h->dir_tab_valid = false;
@@ -2060,7 +2088,7 @@ static void fill_report_basic(mcac_gpu *h, const Scalars &at_start, long long la
     report->pair_tests_sphere = sc.pair_sphere - at_start.pair_sphere;
     report->pair_tests_bounding = sc.pair_bounding - at_start.pair_bounding;
     report->pair_tests_executed = sc.pair_exec - at_start.pair_exec;
-    for (int k = 0; k < 5; k++) { report->loop_phase_cycles[k] = h->loop_cycles[k] - h->loop_cycles_seen[k]; h->loop_cycles_seen[k] = h->loop_cycles[k]; }
+    for (int k = 0; k < 8; k++) { report->loop_phase_cycles[k] = h->loop_cycles[k] - h->loop_cycles_seen[k]; h->loop_cycles_seen[k] = h->loop_cycles[k]; }
     report->batches = steps;
     report->duplications = dups;
     report->sorts = sorts;
@@ -2120,7 +2148,12 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
             cudaMalloc((void **)&as_dev, sizeof(LoopArgs) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&next_dev, sizeof(int)) != cudaSuccess)
             rc_all = E_UNKNOWN;
         int occ = 1, n_sm = handles[loop_set[0]]->n_sm;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_loop, kLoopThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_loop, kLoopThreads, kLoopDynSmem);
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+        cudaEventCreate(&ev_a);
+        cudaEventCreate(&ev_b);
+        double kernel_ms = 0.;
+        long long rounds = 0;
         while (rc_all == E_OK) {
             // ---- host services of the round (in parallel): what the loop asked for, or what calcul() does at the loop top
             std::vector<int> active;  // indices into loop_set
@@ -2177,7 +2210,10 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
             if (cudaMemcpyAsync(ds_dev, ds_host.data(), sizeof(DevState) * (size_t)nr, cudaMemcpyHostToDevice, es) != cudaSuccess ||
                 cudaMemcpyAsync(as_dev, as_host.data(), sizeof(LoopArgs) * (size_t)nr, cudaMemcpyHostToDevice, es) != cudaSuccess ||
                 cudaMemsetAsync(next_dev, 0, sizeof(int), es) != cudaSuccess) { rc_all = E_UNKNOWN; break; }
-            k_ensemble_loop<<<grid, kLoopThreads, 0, es>>>(ds_dev, as_dev, nr, next_dev);
+            cudaEventRecord(ev_a, es);
+            k_ensemble_loop<<<grid, kLoopThreads, kLoopDynSmem, es>>>(ds_dev, as_dev, nr, next_dev);
+            cudaEventRecord(ev_b, es);
+            rounds++;
             if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(es) != cudaSuccess) {
                 for (int j = 0; j < nr; j++) {
                     mcac_gpu *h = handles[loop_set[(size_t)run[(size_t)j]]];
@@ -2185,6 +2221,10 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 }
                 rc_all = E_UNKNOWN;
                 break;
+            }
+            {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, ev_a, ev_b) == cudaSuccess) kernel_ms += ms;
             }
             // ---- read every realization back (its own stream; the launch above is complete)
             parallel_for(run, [&](int i) {
@@ -2197,12 +2237,14 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 if ((rcs[(size_t)k] = pull_scalars(h)) != E_OK) return;
                 const LoopState ls = *h->loop_host;
                 loop_apply(h, ls);
-                t.steps += ls.steps; t.sorts += ls.sorts; t.nucleated += ls.nucleated;
+                t.steps += ls.steps; t.sorts += ls.sorts; t.nucleated += ls.nucleated; t.dups += ls.dups;
                 if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rcs[(size_t)k] = device_error(h, h->sc_host, "mcac_ensemble_run"); return; }
                 if (ls.exit_reason == LOOP_FINISHED) t.fin = true;
                 if (ls.exit_reason == LOOP_STEPS_DONE && ls.steps == 0 && t.steps < max_steps) { h->err = "step loop made no progress"; rcs[(size_t)k] = E_UNKNOWN; }
             });
         }
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
         if (es) cudaStreamDestroy(es);
         if (ds_dev) cudaFree(ds_dev);
         if (as_dev) cudaFree(as_dev);
@@ -2211,8 +2253,12 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
             const int k = loop_set[(size_t)i];
             if (rc_all != E_OK && rcs[(size_t)k] == E_OK) rcs[(size_t)k] = rc_all;
             if (reports && rcs[(size_t)k] == E_OK)
+            {
                 fill_report_basic(handles[k], tr[(size_t)i].at_start, tr[(size_t)i].launches0, reports + k, tr[(size_t)i].steps, tr[(size_t)i].dups,
                                   tr[(size_t)i].sorts, tr[(size_t)i].nucleated, tr[(size_t)i].fin);
+                reports[k].device_ms = kernel_ms;  // CUDA-event time of the k_ensemble_loop launches of this call (shared by its realizations)
+                reports[k].conflicts = rounds;     // rounds (= launches) of this call
+            }
         }
     }
     int rc = E_OK;

@@ -898,8 +898,12 @@ __device__ __forceinline__ void agg_translate(const DevState &d, int slot, doubl
 // tree (deterministic, <= 1e-15 relative from the reference's hash-map order).
 // scratch: kUpdateScratch doubles of shared memory private to the group.
 constexpr int kUpdateScratch = 192;  // [0,8) results, [8,40) per-warp maxima, [40,40+7*16) per-warp partial sums
+// stage (optional): 5 * nth doubles of shared memory private to the group.  The ordered sums are sequential by definition (one add
+// after the other in `myspheres` order); with `stage` the group computes the TERMS of a chunk of nth spheres in parallel, and the
+// accumulating lanes only run the add chains over shared memory — same operations in the same order, without one global-memory
+// round trip per sphere on the critical path (a 10^2..10^3-sphere aggregate of the classic.ini ensemble: ~100 us -> a few us).
 template <bool kBlock>
-__device__ void agg_update(const DevState &d, int slot, bool full, int tid, int nth, double *scratch, double box) {
+__device__ void agg_update(const DevState &d, int slot, bool full, int tid, int nth, double *scratch, double box, double *stage = nullptr) {
     const int off = d.a_off[slot], n = d.a_n[slot];
     const int method = d.volsurf_method;
     const int w = tid >> 5, nw = (nth + 31) >> 5;
@@ -916,9 +920,14 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
                 const double4 rj = d.s_relv[off + j];
                 const double r_j = d.s_posr[off + j].w;
                 const double ex = ri.x - rj.x, ey = ri.y - rj.y, ez = ri.z - rj.z;
-                const double dist = sqrt(ex * ex + ey * ey + ez * ez);
+                const double d2 = ex * ex + ey * ey + ez * ez;
                 const double rs = r_i + r_j;
-                if (dist <= (1. + kCoordinationEpsilon) * rs) {
+                const double lim = (1. + kCoordinationEpsilon) * rs;
+                // far apart (with a margin of 1e-12 that dwarfs the rounding of sqrt and of the products): no square root needed —
+                // almost every pair of a 10^2..10^3-sphere aggregate; the reference's own test decides the others
+                if (d2 > (lim * lim) * (1. + 1e-12)) continue;
+                const double dist = sqrt(d2);
+                if (dist <= lim) {
                     const double c_ij = (rs - dist) / rs;
                     vals[0] += 1.;
                     vals[1] += c_ij;
@@ -967,8 +976,26 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
             }
         }
         group_sync<kBlock>();  // s_veff / s_seff visible
+        if (stage) {  // V and S: two add chains (lanes 0, 1) over staged chunks
+            double acc = 0.;
+            for (int base = 0; base < n; base += nth) {
+                const int i = base + tid;
+                if (i < n) { stage[tid] = d.s_veff[off + i]; stage[nth + tid] = d.s_seff[off + i]; }
+                group_sync<kBlock>();
+                if (tid < 2) {
+                    const double *src = stage + tid * nth;
+                    const int m = (n - base < nth) ? n - base : nth;
+                    for (int k = 0; k < m; k++) acc = acc + src[k];
+                }
+                group_sync<kBlock>();
+            }
+            if (tid < 2) scratch[tid] = acc;
+            group_sync<kBlock>();
+        }
         if (tid == 0) {
             double V = 0., S = 0.;
+            if (stage) { V = scratch[0]; S = scratch[1]; }
+            else
             for (int i = 0; i < n; i++) {
                 V = V + d.s_veff[off + i];
                 S = S + d.s_seff[off + i];
@@ -996,7 +1023,31 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
     }
     // ---- update_partial: centre of mass (lanes 0..2), mean diameter / mean sphere volume (lanes 3, 4)
     const double V = d.a_vol[slot];
-    if (tid < 3) {
+    if (stage) {
+        double acc = 0.;
+        for (int base = 0; base < n; base += nth) {
+            const int i = base + tid;
+            if (i < n) {
+                const double4 rel = d.s_relv[off + i];
+                const double ve = d.s_veff[off + i];
+                stage[tid] = rel.x * ve;
+                stage[nth + tid] = rel.y * ve;
+                stage[2 * nth + tid] = rel.z * ve;
+                stage[3 * nth + tid] = d.s_posr[off + i].w;
+                stage[4 * nth + tid] = rel.w;
+            }
+            group_sync<kBlock>();
+            if (tid < 5) {
+                const double *src = stage + tid * nth;
+                const int m = (n - base < nth) ? n - base : nth;
+                for (int k = 0; k < m; k++) acc += src[k];
+            }
+            group_sync<kBlock>();
+        }
+        if (tid < 3) scratch[tid] = acc / V;
+        else if (tid == 3) scratch[3] = 2 * acc / static_cast<double>(n);  // dp
+        else if (tid == 4) scratch[4] = acc / static_cast<double>(n);      // vol_pp
+    } else if (tid < 3) {
         double acc = 0.;
         for (int i = 0; i < n; i++) {
             const double4 rel = d.s_relv[off + i];
@@ -1016,6 +1067,31 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
     group_sync<kBlock>();
     const double cx = scratch[0], cy = scratch[1], cz = scratch[2];
     double rmax = 0.;
+    double gacc = 0.;  // gyration sums (lanes 0, 1), aggregat.cpp:465-483
+    if (stage) {
+        for (int base = 0; base < n; base += nth) {
+            const int i = base + tid;
+            if (i < n) {
+                const double4 rel = d.s_relv[off + i];
+                const double ex = rel.x - cx, ey = rel.y - cy, ez = rel.z - cz;
+                const double dc = sqrt(ex * ex + ey * ey + ez * ez);
+                d.s_dcen[off + i] = dc;
+                const double r_i = d.s_posr[off + i].w;
+                const double e = r_i + dc;
+                rmax = (rmax < e) ? e : rmax;
+                const double wgt = d.s_veff[off + i];
+                stage[tid] = wgt * (dc * dc);
+                stage[nth + tid] = wgt * (r_i * r_i);
+            }
+            group_sync<kBlock>();
+            if (tid < 2) {
+                const double *src = stage + tid * nth;
+                const int m = (n - base < nth) ? n - base : nth;
+                for (int k = 0; k < m; k++) gacc = gacc + src[k];
+            }
+            group_sync<kBlock>();
+        }
+    } else
     for (int i = tid; i < n; i += nth) {
         const double4 rel = d.s_relv[off + i];
         const double ex = rel.x - cx, ey = rel.y - cy, ez = rel.z - cz;
@@ -1035,7 +1111,9 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
         for (int ww = 0; ww < nw; ww++) rmax = (rmax < scratch[8 + ww]) ? scratch[8 + ww] : rmax;
     }
     group_sync<kBlock>();  // s_dcen visible
-    if (tid < 2) {  // gyration sums, aggregat.cpp:465-483
+    if (stage) {
+        if (tid < 2) scratch[5 + tid] = gacc;
+    } else if (tid < 2) {  // gyration sums, aggregat.cpp:465-483
         double acc = 0.;
         for (int i = 0; i < n; i++) {
             const double wgt = d.s_veff[off + i];
@@ -1207,7 +1285,7 @@ __device__ void agg_update_single(const DevState &d, int slot, bool full, double
 
 // K4 — AggregatList::merge + Aggregate::merge + ListStorage::merge/remove (aggregat_list.cpp:367-410,
 // aggregat.cpp:486-544): CTA-cooperative.  Returns (to every thread, uniformly) 1 when the aggregates were united.
-__device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int other_agg, double *scratch, double box) {
+__device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int other_agg, double *scratch, double box, double *stage = nullptr) {
     const int tid = threadIdx.x, nth = blockDim.x;
     const double4 pm = d.s_posr[ms], po = d.s_posr[os];
     if (!spheres_in_contact(pm.x, pm.y, pm.z, pm.w, po.x, po.y, po.z, po.w, box)) return 0;  // aggregat_list.cpp:375
@@ -1267,7 +1345,7 @@ __device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int 
         if (tid == 0) agg_update_single(d, kept, true, box);
         __syncthreads();
     } else {
-        agg_update<true>(d, kept, true, tid, nth, scratch, box);
+        agg_update<true>(d, kept, true, tid, nth, scratch, box, stage);
     }
     if (tid == 0) {
         d.a_ptime[kept] = newtime;
@@ -1790,12 +1868,12 @@ __global__ void __launch_bounds__(kCommitThreads) k_nucleate(DevState d, double 
 }
 
 // the deferred AggregatList::merge of the step (calcul.cpp:174-181) + event bookkeeping (:222-229)
-__device__ __forceinline__ void dev_step_merge(const DevState &d, mcac_step_record *rec, long long rec_cap, long long rec_index) {
+__device__ __forceinline__ void dev_step_merge(const DevState &d, mcac_step_record *rec, long long rec_cap, long long rec_index, double *stage = nullptr) {
     if (d.sc->error != 0) return;  // an earlier kernel of this step failed: leave the state as it is
     __shared__ double scratch[kUpdateScratch];
     Scalars &sc = *d.sc;
     int merged = 0;
-    if (sc.p_contact) merged = agg_merge(d, sc.p_ms, sc.p_os, sc.p_magg, sc.p_oagg, scratch, sc.box_length);
+    if (sc.p_contact) merged = agg_merge(d, sc.p_ms, sc.p_os, sc.p_magg, sc.p_oagg, scratch, sc.box_length, stage);
     __syncthreads();
     if (threadIdx.x == 0) {
         sc.b_merged = merged;

@@ -15,6 +15,8 @@
 namespace mcacb {
 
 constexpr int kLoopThreads = 512;
+constexpr int kLoopWarpMax = 96;  // spheres of an aggregate up to which one warp updates it when every aggregate is updated
+constexpr int kLoopDynSmem = 5 * kLoopThreads * (int)sizeof(double);
 enum LoopExit { LOOP_STEPS_DONE = 0, LOOP_FINISHED = 1, LOOP_NEED_DUP = 2, LOOP_NEED_REGROW = 3, LOOP_NEED_RNG = 4, LOOP_TOO_BIG = 5,
                 LOOP_ERROR = 6, LOOP_EVENT_STOP = 7 };
 
@@ -23,10 +25,10 @@ struct LoopState {  // device-resident, one per handle: what the host reads back
     int flipped;        // the sphere pool was compacted an odd number of times: d.s_* and alt.s_* have changed places
     int pick_valid, labels_valid;
     long long steps;    // MC steps done by this launch
-    long long events, nucleated, sorts, compactions;
-    // SM cycles of the CTA per part of the step: 0 pick table (labels + sort), 1 cells + contact search (+ redraws), 2 move + growth +
-    // merge + updates, 3 nucleation + bookkeeping + refresh, 4 loop top (checks, compaction)
-    long long phase_cycles[5];
+    long long events, nucleated, sorts, compactions, dups;
+    // SM cycles of the CTA per part of the step: 0 pick table (labels + sort), 1 cells + contact search (+ redraws), 2 update block of
+    // calcul.cpp:184-206, 3 nucleation + bookkeeping + refresh, 4 loop top (checks, compaction), 5 move + clocks, 6 growth, 7 merge
+    long long phase_cycles[8];
 };
 struct LoopArgs {
     int *q_slot;
@@ -46,6 +48,9 @@ struct LoopArgs {
     int pick_valid, labels_valid, stop_at_event;
     int max_slots;                   // the loop hands back (LOOP_TOO_BIG) when the aggregate table outgrows this
     int prune;                       // 0: every sphere pair of an examined suspect is tested (MCAC_B200_NO_PRUNE)
+    int dups_allowed;                // domain duplications this launch may do by itself (<= 4; 0: always hand them to the host)
+    double dup_box_volume[4];        // PhysicalModel::box_volume after the 1st .. 4th duplication from now: std::pow(box_length, 3) is
+                                     // evaluated by the HOST (the reference's libm), like every other box quantity
     LoopState *out;
 };
 
@@ -341,10 +346,10 @@ __device__ __forceinline__ void cta_compact_pool(DevState &d, LoopArgs &a, int *
 // refresh() + get_total_volume/surface + PhysicalModel::update at the end of a general step (k_refresh_partials + k_step_totals /
 // k_refresh_if_event): max is exact; the two sums are combined in a fixed order (per-thread strided partials, warp butterfly,
 // warps in order) — they only feed the reported concentrations / volume fraction
-__device__ __forceinline__ void cta_refresh(const DevState &d, bool growth) {
+__device__ __forceinline__ void cta_refresh(const DevState &d, bool growth, bool totals_only = false) {
     __shared__ double sm[3][32];
     Scalars &sc = *d.sc;
-    if (!growth && !sc.event) return;  // (uniform: every thread reads the same flag after the barrier that followed its write)
+    if (!totals_only && !growth && !sc.event) return;  // (uniform: every thread reads the same flag after the barrier that followed its write)
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
     const int n = sc.n_agg_slots;
     double mx = 0., sv = 0., ss = 0.;
@@ -370,7 +375,7 @@ __device__ __forceinline__ void cta_refresh(const DevState &d, bool growth) {
             sv += sm[1][w];
             ss += sm[2][w];
         }
-        if (sc.event) {
+        if (sc.event && !totals_only) {
             sc.max_time_step = mx;
             sc.avg_npp = static_cast<double>(sc.n_sph) / static_cast<double>(sc.n_agg);
         }
@@ -385,20 +390,112 @@ __device__ __forceinline__ void cta_refresh(const DevState &d, bool growth) {
     __syncthreads();
 }
 
+// AggregatList::duplication (aggregat_list.cpp:142-190) inside the loop, when the tables have room for it: the box doubles, every
+// aggregate gets 7 translated copies appended in (aggregate, shift) order — labels n0 + 7a + c - 1 and fresh sphere indices in member
+// order, exactly as the copy constructor chain of the reference numbers them (aggregat_storage.cpp:117-159) — then the copies are moved
+// by (i,j,k) * old box with the NEW box's periodicity, every Verlet cell is recomputed and PhysicalModel::update refreshes the
+// concentrations (:186-189).  Slots are stable: the live slots of the originals come first, the copies are appended behind them, so
+// the rank of a slot among the live slots is the reference's label.  Returns false (nothing touched) when the tables are too small:
+// the host then does the same through the upload boundary, with bigger tables.
+__device__ __forceinline__ bool cta_duplicate(DevState &d, LoopArgs &a, bool &labels_valid, int dup_index) {
+    __shared__ int s_ok;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    Scalars &sc = *d.sc;
+    const int n0 = sc.n_agg, m0 = sc.n_sph;
+    if (d.sph_cap - sc.pool_top < 7 * m0 && sc.pool_top > m0) cta_compact_pool(d, a, a.scan_tmp);
+    if (tid == 0)
+        s_ok = (sc.n_agg_slots + 7LL * n0 + 64 <= d.agg_cap && sc.pool_top + 7LL * m0 + (a.with_nucleation ? m0 + 64 : 0) <= d.sph_cap &&
+                8LL * m0 + 64 <= d.sph_cap) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) return false;
+    if (!labels_valid) { cta_labels(d, a.scan_tmp); labels_valid = true; }
+    int *scan = a.scan_tmp;
+    for (int l = tid; l < n0; l += nth) scan[l] = d.a_n[d.slot_of_label[l]];
+    __syncthreads();
+    cta_scan_int(scan, n0, scan);  // spheres of the aggregates with a smaller label
+    const int base_slot = sc.n_agg_slots, base_pool = sc.pool_top;
+    const double old_l = sc.box_length;
+    __syncthreads();
+    for (int t = warp; t < 7 * n0; t += nwarps) {
+        const int al = t / 7, c = t % 7 + 1;
+        const int src = d.slot_of_label[al], dst = base_slot + t;
+        const int n = d.a_n[src], off_src = d.a_off[src];
+        const int off_dst = base_pool + 7 * scan[al] + (c - 1) * n;
+        const int id0 = m0 + 7 * scan[al] + (c - 1) * n;
+        if (lane == 0) {
+            d.a_posr[dst] = d.a_posr[src];
+            d.a_rg[dst] = d.a_rg[src]; d.a_fagg[dst] = d.a_fagg[src]; d.a_lpm[dst] = d.a_lpm[src]; d.a_ts[dst] = d.a_ts[src];
+            d.a_vol[dst] = d.a_vol[src]; d.a_surf[dst] = d.a_surf[src];
+            d.a_rx[dst] = d.a_rx[src]; d.a_ry[dst] = d.a_ry[src]; d.a_rz[dst] = d.a_rz[src]; d.a_ptime[dst] = d.a_ptime[src];
+            d.a_dp[dst] = d.a_dp[src]; d.a_dgdp[dst] = d.a_dgdp[src]; d.a_ovl[dst] = d.a_ovl[src]; d.a_cn[dst] = d.a_cn[src];
+            d.a_dm[dst] = d.a_dm[src]; d.a_ch[dst] = d.a_ch[src]; d.a_bulk[dst] = d.a_bulk[src]; d.a_alpha[dst] = d.a_alpha[src];
+            d.a_n[dst] = n; d.a_off[dst] = off_dst;
+            d.a_cx[dst] = d.a_cx[src]; d.a_cy[dst] = d.a_cy[src]; d.a_cz[dst] = d.a_cz[src];
+            d.a_charge[dst] = 0;  // the copy constructor resets the charge (aggregat_storage.cpp:138)
+            d.a_alive[dst] = 1;
+            d.label_of_slot[dst] = n0 + t;
+            d.slot_of_label[n0 + t] = dst;
+        }
+        for (int k = lane; k < n; k += 32) {
+            d.s_posr[off_dst + k] = d.s_posr[off_src + k];
+            d.s_relv[off_dst + k] = d.s_relv[off_src + k];
+            d.s_surf[off_dst + k] = d.s_surf[off_src + k];
+            d.s_veff[off_dst + k] = d.s_veff[off_src + k];
+            d.s_seff[off_dst + k] = d.s_seff[off_src + k];
+            d.s_dcen[off_dst + k] = d.s_dcen[off_src + k];
+            d.s_id[off_dst + k] = id0 + k;
+            d.s_charge[off_dst + k] = 0;
+            d.slot_of_id[id0 + k] = off_dst + k;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sc.box_length = old_l * 2;
+        sc.n_monomeres *= 8;
+        sc.box_volume = a.dup_box_volume[dup_index];
+        sc.n_agg = 8 * n0;
+        sc.n_agg_slots = base_slot + 7 * n0;
+        sc.n_sph = 8 * m0;
+        sc.pool_top = base_pool + 7 * m0;
+        a.out->dups += 1;
+    }
+    __syncthreads();
+    const double box = sc.box_length;
+    const int n_slots = sc.n_agg_slots;
+    for (int s = warp; s < n_slots; s += nwarps) {  // k_dup_finish
+        if (!d.a_alive[s]) continue;
+        if (s >= base_slot) {
+            const int c = (s - base_slot) % 7 + 1;
+            agg_translate<false>(d, s, ((c >> 2) & 1) * old_l, ((c >> 1) & 1) * old_l, (c & 1) * old_l, box, lane, 32);
+        } else if (lane == 0) {
+            const double4 p = d.a_posr[s];
+            d.a_cx[s] = cell_of(p.x, d.n_div, box);
+            d.a_cy[s] = cell_of(p.y, d.n_div, box);
+            d.a_cz[s] = cell_of(p.z, d.n_div, box);
+        }
+    }
+    __syncthreads();
+    cta_refresh(d, true, true);  // PhysicalModel::update: totals and concentrations for the new box; max_time_step / avg_npp are kept
+    return true;
+}
+
 // ---- the loop ---------------------------------------------------------------------------------------------------------------
 __device__ void step_loop(DevState &d, LoopArgs &a) {
     __shared__ double upd_scratch[kLoopThreads / 32][kUpdateScratch / 4];
     __shared__ double picked_scratch[kUpdateScratch];
+    // terms of the ordered sums (agg_update's `stage`): 5 x 512 doubles for the CTA-wide update, 5 x 32 per warp otherwise — dynamic
+    // shared memory (kLoopDynSmem bytes), the static part of this kernel is already at 31 KB
+    double *upd_stage = reinterpret_cast<double *>(dyn_smem);
     __shared__ int s_exit, s_draws, s_ntry, s_draws_at_search, s_again;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
     Scalars &sc = *d.sc;
     LoopState &out = *a.out;
     bool pick_valid = a.pick_valid != 0, labels_valid = a.labels_valid != 0;
     long long steps = 0;
-    int reason = LOOP_STEPS_DONE;
+    int reason = LOOP_STEPS_DONE, dups_done = 0;
     if (tid == 0) {
-        out.steps = 0; out.events = 0; out.nucleated = 0; out.sorts = 0; out.compactions = 0; out.flipped = 0; out.exit_reason = LOOP_STEPS_DONE;
-        for (int k = 0; k < 5; k++) out.phase_cycles[k] = 0;
+        out.steps = 0; out.events = 0; out.nucleated = 0; out.sorts = 0; out.compactions = 0; out.dups = 0; out.flipped = 0; out.exit_reason = LOOP_STEPS_DONE;
+        for (int k = 0; k < 8; k++) out.phase_cycles[k] = 0;
     }
     long long t_prev = clock64();
     auto lap = [&](int k) { if (tid == 0) { const long long t = clock64(); out.phase_cycles[k] += t - t_prev; t_prev = t; } };
@@ -411,7 +508,11 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             reason = LOOP_FINISHED;
             break;
         }
-        if (sc.event && a.with_domain_duplication && sc.n_agg <= a.dup_threshold && !(d.u_sg < 0.0)) { reason = LOOP_NEED_DUP; break; }
+        if (sc.event && a.with_domain_duplication && sc.n_agg <= a.dup_threshold && !(d.u_sg < 0.0)) {
+            if (dups_done >= a.dups_allowed || !cta_duplicate(d, a, labels_valid, dups_done)) { reason = LOOP_NEED_DUP; break; }
+            dups_done++;
+            pick_valid = false;
+        }
         if (sc.n_agg_slots > a.max_slots || sc.n_agg > a.cum_sequential_max) { reason = LOOP_TOO_BIG; break; }
         if (d.sph_cap - sc.pool_top < sc.n_sph) cta_compact_pool(d, a, a.scan_tmp);
         if (a.with_nucleation && (d.agg_cap - sc.n_agg_slots < 64 || d.sph_cap - sc.pool_top < sc.n_sph + 64)) { reason = LOOP_NEED_REGROW; break; }
@@ -474,6 +575,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
         __syncthreads();
         dev_step_move(d, sa);
         __syncthreads();
+        lap(5);
         if (sc.error != 0) { reason = LOOP_ERROR; break; }
         if (a.growth) {  // k_grow_pending
             int lo = 0, hi = sc.pool_top;
@@ -494,22 +596,30 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             }
             __syncthreads();
         }
-        dev_step_merge(d, sa.rec, sa.rec_cap, sa.rec_index);
+        lap(6);
+        dev_step_merge(d, sa.rec, sa.rec_cap, sa.rec_index, upd_stage);
         __syncthreads();
+        lap(7);
         // ---- update block of calcul.cpp:184-206
         if (a.growth) {
             const bool full = (iter_before % a.full_freq) == 0;
             const bool everyone = !(a.individual && !sc.b_merged);
             if (!everyone) {
                 const int slot = sc.p_slot;
-                if (slot >= 0 && slot < sc.n_agg_slots && d.a_alive[slot]) agg_update<true>(d, slot, full, tid, nth, picked_scratch, sc.box_length);
+                if (slot >= 0 && slot < sc.n_agg_slots && d.a_alive[slot]) agg_update<true>(d, slot, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
             } else {
+                // small aggregates one per thread, medium ones one per warp, big ones by the whole CTA one after the other (a full
+                // update is O(n^2): a 10^3-sphere aggregate left to one warp would keep the other 15 waiting for milliseconds)
                 const int n_slots = sc.n_agg_slots;
                 for (int s = tid; s < n_slots; s += nth)
                     if (d.a_alive[s] && d.a_n[s] <= kSingleMax) agg_update_single(d, s, full, sc.box_length);
                 __syncthreads();
                 for (int s = warp; s < n_slots; s += nwarps)
-                    if (d.a_alive[s] && d.a_n[s] > kSingleMax) agg_update<false>(d, s, full, lane, 32, upd_scratch[warp], sc.box_length);
+                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && d.a_n[s] <= kLoopWarpMax)
+                        agg_update<false>(d, s, full, lane, 32, upd_scratch[warp], sc.box_length, upd_stage + warp * (5 * 32));
+                __syncthreads();
+                for (int s = 0; s < n_slots; s++)
+                    if (d.a_alive[s] && d.a_n[s] > kLoopWarpMax) agg_update<true>(d, s, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
             }
             __syncthreads();
         }
