@@ -237,6 +237,8 @@ def ensemble_measure(a, rank, world, local, dist, config, metric, unit, K, W, M,
     t_wall = time.perf_counter()
     steps_done = launches = events = pair_tests = pair_exec = rounds = 0
     kernel_ms = 0.0
+    host_ms = [0.0] * 4
+    host_services = [0] * 3
     phase_cycles = [0] * 8
     stats_s = 0.0
     d2h = 0
@@ -249,6 +251,10 @@ def ensemble_measure(a, rank, world, local, dist, config, metric, unit, K, W, M,
         pair_tests += sum(r["pair_tests_sphere"] + r["pair_tests_bounding"] for r in reps)
         pair_exec += sum(r["pair_tests_executed"] for r in reps)
         kernel_ms += reps[0]["device_ms"] if reps else 0.0
+        for k, name in enumerate(("search_ms", "commit_ms", "event_ms", "cells_ms")):
+            host_ms[k] += reps[0][name] if reps else 0.0
+        for k, name in enumerate(("search_launches", "commit_launches", "event_launches")):
+            host_services[k] += reps[0][name] if reps else 0
         rounds += reps[0]["conflicts"] if reps else 0
         for k in range(8):
             phase_cycles[k] += sum(r["loop_phase_cycles"][k] for r in reps)
@@ -309,6 +315,8 @@ def ensemble_measure(a, rank, world, local, dist, config, metric, unit, K, W, M,
                                     "host services), max over ranks",
                           "mc_steps_timed": int(tot[0]), "events_timed": int(tot[2]), "pair_tests_per_sec": pair_rate,
                           "pair_tests_executed_per_sec": exec_rate, "loop_phase_share": phase_share, "init_s": init_s, "clocks": clocks,
+                          "rank0_host_ms_per_step": dict(zip(["services", "launch_wait_readback", "bookkeeping", "whole_call"], [x / K for x in host_ms])),
+                          "rank0_host_services_timed": dict(zip(["duplications", "table_regrows", "rng_refills"], host_services)),
                           "rank0_kernel_ms_per_step": kernel_ms / K, "rank0_rounds_per_step": rounds / K,
                           "rank0_kernel_share_of_wall": kernel_ms * 1e-3 / (wall_s - stats_s) if wall_s > stats_s else None,
                           "e2e": {"value": float(te[1]) / float(te[0]), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -594,7 +596,13 @@ int download_to(mcac_gpu *h, const HostOut &o);
 // AggregatList::duplication (aggregat_list.cpp:142-190): box x2, 7 translated copies of every aggregate appended in
 // (i,j,k) order, Verlet rebuilt.  Rare (once per 8x drop of N_agg) and purely a re-layout, so it is orchestrated
 // through the download/upload boundary; the copies' positions are produced by the same K3 translate kernel.
+int duplicate_on_device(mcac_gpu *h, bool *done);
 int duplicate(mcac_gpu *h) {
+    {   // in place on the device when the tables have room for 8x the state (k_duplicate, mcac_steploop.cuh)
+        bool done = false;
+        TRY(duplicate_on_device(h, &done));
+        if (done) return E_OK;
+    }
     HostState s;
     TRY(download(h, s));
     const long long n0 = s.n_agg, m0 = s.n_sph;
@@ -769,7 +777,7 @@ int upload(mcac_gpu *h, const HostView &s, double maxradius, double max_time_ste
     // tables: what the state needs now, or more when the caller reserved room (mcac_gpu_reserve) or — small realizations that duplicate
     // their domain — for the next duplication (x8), so that the step loop can do it without the host
     long long want_sph = std::max(n_sph, h->reserve_sph), want_agg = std::max(n_agg, h->reserve_agg);
-    if (h->prm.with_domain_duplication && !is_speculative(h) && n_sph <= 100000) { want_sph = std::max(want_sph, 8 * n_sph); want_agg = std::max(want_agg, 8 * n_agg); }
+    if (h->prm.with_domain_duplication && h->reserve_sph == 0 && n_sph <= 100000) { want_sph = std::max(want_sph, 8 * n_sph); want_agg = std::max(want_agg, 8 * n_agg); }
     const long long need_agg = want_agg + headroom, need_sph = 3 * (want_sph + headroom) + 1024;
     if (h->owned.empty() || d.agg_cap < need_agg || d.sph_cap < need_sph) {  // otherwise the resident allocation is reused
         free_all(h);
@@ -1032,6 +1040,26 @@ void loop_apply(mcac_gpu *h, const LoopState &ls) {
     h->loop_launches++;
     h->loop_steps += ls.steps;
     for (int k = 0; k < 8; k++) h->loop_cycles[k] += ls.phase_cycles[k];
+}
+int duplicate_on_device(mcac_gpu *h, bool *done) {
+    *done = false;
+    if (!h->loop_dups || h->debug_sync) return E_OK;
+    const Scalars &sc = h->sc_host;
+    if (sc.n_agg_slots + 7LL * sc.n_agg + 64 > h->d.agg_cap || 8LL * sc.n_sph + 64 > h->d.sph_cap || 9LL * sc.n_sph + 64 > h->d.sph_cap) return E_OK;
+    LoopArgs la;
+    loop_fill_args(h, la, 0, nullptr, 0, 0);
+    k_duplicate<<<1, kLoopThreads, kLoopDynSmem, h->stream>>>(h->d, la);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->loop_host, h->loop_dev, sizeof(LoopState), cudaMemcpyDeviceToHost, h->stream));
+    TRY(pull_scalars(h));
+    const LoopState ls = *h->loop_host;
+    if (ls.dups != 1) return E_OK;  // the kernel found the tables too small after all: nothing was touched
+    loop_apply(h, ls);
+    h->loop_launches--;  // (not a step-loop launch)
+    h->pick_valid = false;
+    *done = true;
+    return E_OK;
 }
 // slots for nucleated monomers: regrow through the upload boundary when the headroom is nearly used up.  This renumbers the
 // aggregate slots (slot = label again), so it must come BEFORE the pick table of the step is built.
@@ -1389,8 +1417,14 @@ int mcac_gpu_update(mcac_gpu *h, int64_t label, int full) {
     }
     const int nblk = label >= 0 ? 1 : div_up(h->sc_host.n_agg_slots, 8);
     if (label < 0) { k_update_small<<<div_up(h->sc_host.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, full, 0, 1); h->launches++; }
-    k_update_all<<<nblk, 256, 0, h->stream>>>(h->d, full, slot);
-    h->launches++;
+    if (label >= 0) {
+        k_update_one<<<1, kCommitThreads, 0, h->stream>>>(h->d, full, slot);
+        h->launches++;
+    } else {
+        k_update_all<<<nblk, 256, 0, h->stream>>>(h->d, full, slot);
+        k_update_big<<<std::min(h->sc_host.n_agg_slots, 4 * h->n_sm), kCommitThreads, 0, h->stream>>>(h->d, full, 0);
+        h->launches += 2;
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     h->cells_valid = false;
@@ -1614,7 +1648,8 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             if (p.individual_surf_reactions) { k_update_picked<<<1, kCommitThreads, 0, h->stream>>>(h->d, full); h->launches++; }
             k_update_small<<<div_up(h->sc_host.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, full, p.individual_surf_reactions, 0);
             k_update_step<<<div_up(h->sc_host.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
-            h->launches += 2;
+            k_update_big<<<std::min(h->sc_host.n_agg_slots, 4 * h->n_sm), kCommitThreads, 0, h->stream>>>(h->d, full, p.individual_surf_reactions);
+            h->launches += 3;
         }
         DBG("update kernels");
         if (p.with_nucleation) {  // calcul.cpp:208-220
@@ -2016,6 +2051,7 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_o
         case 3:
             k_update_small<<<div_up(sc.n_agg_slots, 128), 128, 0, h->stream>>>(h->d, which == 3, 0, 1);
             k_update_all<<<div_up(sc.n_agg_slots, 8), 256, 0, h->stream>>>(h->d, which == 3, -1);
+            k_update_big<<<std::min(sc.n_agg_slots, 4 * h->n_sm), kCommitThreads, 0, h->stream>>>(h->d, which == 3, 0);
             units = sc.n_agg;
             break;
         case 4: h->labels_valid = false; rc = event_pipeline(h, true, true, true); units = sc.n_agg; break;
@@ -2109,6 +2145,10 @@ static void fill_report_basic(mcac_gpu *h, const Scalars &at_start, long long la
 
 int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t batch, int32_t threads, mcac_run_report *reports) {
     if (!handles || n < 1) return E_INPUT;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    double service_ms = 0., launch_ms = 0., apply_ms = 0.;
+    std::atomic<long long> n_dup_services{0}, n_regrow_services{0}, n_rng_services{0};
     const int T = std::max(1, std::min<int>(threads, n));
     std::vector<int> rcs((size_t)n, E_OK);
     auto parallel_for = [&](const std::vector<int> &items, auto &&fn) {
@@ -2135,17 +2175,22 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
         cudaSetDevice(handles[loop_set[0]]->device);
         struct Track { Scalars at_start; long long launches0; int64_t steps = 0, dups = 0, sorts = 0, nucleated = 0; bool fin = false, host_only = false; };
         std::vector<Track> tr((size_t)m);
-        parallel_for(loop_set, [&](int k) { cudaSetDevice(handles[k]->device); rcs[(size_t)k] = pull_scalars(handles[k]); });
+        parallel_for(loop_set, [&](int k) { cudaSetDevice(handles[k]->device); rcs[(size_t)k] = pull_scalars(handles[k]); handles[k]->loop_host->exit_reason = LOOP_STEPS_DONE; });
         for (int i = 0; i < m; i++) { tr[(size_t)i].at_start = handles[loop_set[(size_t)i]]->sc_host; tr[(size_t)i].launches0 = handles[loop_set[(size_t)i]]->launches; }
         cudaStream_t es = nullptr;
         DevState *ds_dev = nullptr;
         LoopArgs *as_dev = nullptr;
         int *next_dev = nullptr;
+        Scalars *sc_all_dev = nullptr;
+        LoopState *ls_all_dev = nullptr;
         std::vector<DevState> ds_host((size_t)m);
         std::vector<LoopArgs> as_host((size_t)m);
+        std::vector<Scalars> sc_all_host((size_t)m);
+        std::vector<LoopState> ls_all_host((size_t)m);
         int rc_all = E_OK;
         if (cudaStreamCreateWithFlags(&es, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void **)&ds_dev, sizeof(DevState) * (size_t)m) != cudaSuccess ||
-            cudaMalloc((void **)&as_dev, sizeof(LoopArgs) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&next_dev, sizeof(int)) != cudaSuccess)
+            cudaMalloc((void **)&as_dev, sizeof(LoopArgs) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&next_dev, sizeof(int)) != cudaSuccess ||
+            cudaMalloc((void **)&sc_all_dev, sizeof(Scalars) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&ls_all_dev, sizeof(LoopState) * (size_t)m) != cudaSuccess)
             rc_all = E_UNKNOWN;
         int occ = 1, n_sm = handles[loop_set[0]]->n_sm;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_loop, kLoopThreads, kLoopDynSmem);
@@ -2155,33 +2200,57 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
         double kernel_ms = 0.;
         long long rounds = 0;
         while (rc_all == E_OK) {
-            // ---- host services of the round (in parallel): what the loop asked for, or what calcul() does at the loop top
-            std::vector<int> active;  // indices into loop_set
+            // ---- host services of the round: what the loop asked for, or what calcul() does at the loop top.  Most rounds need none
+            // (the loop duplicates, compacts and re-sorts by itself): the handles are scanned here, and only those that need the host
+            // are served, in parallel
+            const auto t_service = std::chrono::steady_clock::now();
+            std::vector<int> active, need;  // indices into loop_set
             for (int i = 0; i < m; i++) {
                 const int k = loop_set[(size_t)i];
-                if (rcs[(size_t)k] == E_OK && !tr[(size_t)i].fin && tr[(size_t)i].steps < max_steps) active.push_back(i);
+                if (rcs[(size_t)k] != E_OK || tr[(size_t)i].fin || tr[(size_t)i].steps >= max_steps) continue;
+                mcac_gpu *h = handles[k];
+                if (finished(h)) { tr[(size_t)i].fin = true; continue; }
+                active.push_back(i);
+                const mcac_params &p = h->prm;
+                const bool dup = h->sc_host.event && p.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(p.u_sg < 0.0) &&
+                                 h->loop_host->exit_reason == LOOP_NEED_DUP;  // (otherwise the loop does it, if its tables have room)
+                const bool regrow = p.with_nucleation &&
+                                    (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64);
+                const bool rng = !(h->sc_host.rand_pos + 8192 + 64 + 31 <= h->rng_generated && h->sc_host.rand_pos >= h->d.rng_buf_base) ||
+                                 (h->strict_dir && !h->dir_tab_valid);
+                tr[(size_t)i].host_only = !loop_usable(h);
+                if (dup || regrow || rng) need.push_back(i);
             }
             if (active.empty()) break;
-            parallel_for(active, [&](int i) {
-                const int k = loop_set[(size_t)i];
-                mcac_gpu *h = handles[k];
-                Track &t = tr[(size_t)i];
-                cudaSetDevice(h->device);
-                int rc = E_OK;
-                if (finished(h)) { t.fin = true; return; }
-                const mcac_params &p = h->prm;
-                if (h->sc_host.event && p.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(p.u_sg < 0.0)) {
-                    rc = duplicate(h);
-                    t.dups++;
-                }
-                if (rc == E_OK && p.with_nucleation &&
-                    (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64))
-                    rc = regrow_tables(h);
-                if (rc == E_OK) rc = ensure_rng(h, h->sc_host.rand_pos + 8192 + 64 + 31);
-                if (rc == E_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = E_UNKNOWN;
-                t.host_only = !loop_usable(h);
-                rcs[(size_t)k] = rc;
-            });
+            if (!need.empty())
+                parallel_for(need, [&](int i) {
+                    const int k = loop_set[(size_t)i];
+                    mcac_gpu *h = handles[k];
+                    Track &t = tr[(size_t)i];
+                    cudaSetDevice(h->device);
+                    int rc = E_OK;
+                    const mcac_params &p = h->prm;
+                    if (h->sc_host.event && p.with_domain_duplication && h->sc_host.n_agg <= h->dup_threshold && !(p.u_sg < 0.0) &&
+                        h->loop_host->exit_reason == LOOP_NEED_DUP) {
+                        rc = duplicate(h);
+                        t.dups++;
+                        n_dup_services++;
+                        h->loop_host->exit_reason = LOOP_STEPS_DONE;
+                    }
+                    if (rc == E_OK && p.with_nucleation &&
+                        (h->d.agg_cap - h->sc_host.n_agg_slots < 64 || h->d.sph_cap - h->sc_host.pool_top < h->sc_host.n_sph + 64)) {
+                        rc = regrow_tables(h);
+                        n_regrow_services++;
+                    }
+                    if (rc == E_OK) {
+                        const long long before = h->rng_generated;
+                        rc = ensure_rng(h, h->sc_host.rand_pos + 8192 + 64 + 31);
+                        if (h->rng_generated != before) n_rng_services++;
+                    }
+                    if (rc == E_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = E_UNKNOWN;
+                    t.host_only = !loop_usable(h);
+                    rcs[(size_t)k] = rc;
+                });
             // realizations that outgrew the loop finish on the host-driven path
             std::vector<int> big, run;
             for (int i : active) {
@@ -2198,7 +2267,9 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                     tr[(size_t)i].nucleated += rep.nucleated;
                     if (rep.finished || rep.steps == 0) tr[(size_t)i].fin = true;
                 });
+            service_ms += since(t_service);
             if (run.empty()) continue;
+            const auto t_launch = std::chrono::steady_clock::now();
             // ---- one launch for the whole round
             const int nr = (int)run.size();
             for (int j = 0; j < nr; j++) {
@@ -2211,10 +2282,15 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 cudaMemcpyAsync(as_dev, as_host.data(), sizeof(LoopArgs) * (size_t)nr, cudaMemcpyHostToDevice, es) != cudaSuccess ||
                 cudaMemsetAsync(next_dev, 0, sizeof(int), es) != cudaSuccess) { rc_all = E_UNKNOWN; break; }
             cudaEventRecord(ev_a, es);
-            k_ensemble_loop<<<grid, kLoopThreads, kLoopDynSmem, es>>>(ds_dev, as_dev, nr, next_dev);
+            k_ensemble_loop<<<grid, kLoopThreads, kLoopDynSmem, es>>>(ds_dev, as_dev, nr, next_dev, sc_all_dev, ls_all_dev);
             cudaEventRecord(ev_b, es);
             rounds++;
-            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(es) != cudaSuccess) {
+            // the whole round comes back with two copies (every realization left its Scalars / LoopState in the contiguous arrays)
+            bool ok = cudaGetLastError() == cudaSuccess &&
+                      cudaMemcpyAsync(sc_all_host.data(), sc_all_dev, sizeof(Scalars) * (size_t)nr, cudaMemcpyDeviceToHost, es) == cudaSuccess &&
+                      cudaMemcpyAsync(ls_all_host.data(), ls_all_dev, sizeof(LoopState) * (size_t)nr, cudaMemcpyDeviceToHost, es) == cudaSuccess &&
+                      cudaStreamSynchronize(es) == cudaSuccess;
+            if (!ok) {
                 for (int j = 0; j < nr; j++) {
                     mcac_gpu *h = handles[loop_set[(size_t)run[(size_t)j]]];
                     h->err = std::string("ensemble step loop: ") + cudaGetErrorString(cudaGetLastError());
@@ -2226,22 +2302,23 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 float ms = 0.f;
                 if (cudaEventElapsedTime(&ms, ev_a, ev_b) == cudaSuccess) kernel_ms += ms;
             }
-            // ---- read every realization back (its own stream; the launch above is complete)
-            parallel_for(run, [&](int i) {
-                const int k = loop_set[(size_t)i];
+            launch_ms += since(t_launch);
+            const auto t_apply = std::chrono::steady_clock::now();
+            for (int j = 0; j < nr; j++) {
+                const int i = run[(size_t)j], k = loop_set[(size_t)i];
                 mcac_gpu *h = handles[k];
                 Track &t = tr[(size_t)i];
-                cudaSetDevice(h->device);
                 h->launches++;
-                if (cudaMemcpyAsync(h->loop_host, h->loop_dev, sizeof(LoopState), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rcs[(size_t)k] = E_UNKNOWN; return; }
-                if ((rcs[(size_t)k] = pull_scalars(h)) != E_OK) return;
-                const LoopState ls = *h->loop_host;
+                h->sc_host = sc_all_host[(size_t)j];
+                const LoopState ls = ls_all_host[(size_t)j];
+                *h->loop_host = ls;
                 loop_apply(h, ls);
                 t.steps += ls.steps; t.sorts += ls.sorts; t.nucleated += ls.nucleated; t.dups += ls.dups;
-                if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rcs[(size_t)k] = device_error(h, h->sc_host, "mcac_ensemble_run"); return; }
+                if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rcs[(size_t)k] = device_error(h, h->sc_host, "mcac_ensemble_run"); continue; }
                 if (ls.exit_reason == LOOP_FINISHED) t.fin = true;
                 if (ls.exit_reason == LOOP_STEPS_DONE && ls.steps == 0 && t.steps < max_steps) { h->err = "step loop made no progress"; rcs[(size_t)k] = E_UNKNOWN; }
-            });
+            }
+            apply_ms += since(t_apply);
         }
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
@@ -2249,6 +2326,8 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
         if (ds_dev) cudaFree(ds_dev);
         if (as_dev) cudaFree(as_dev);
         if (next_dev) cudaFree(next_dev);
+        if (sc_all_dev) cudaFree(sc_all_dev);
+        if (ls_all_dev) cudaFree(ls_all_dev);
         for (int i = 0; i < m; i++) {
             const int k = loop_set[(size_t)i];
             if (rc_all != E_OK && rcs[(size_t)k] == E_OK) rcs[(size_t)k] = rc_all;
@@ -2258,6 +2337,10 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                                   tr[(size_t)i].sorts, tr[(size_t)i].nucleated, tr[(size_t)i].fin);
                 reports[k].device_ms = kernel_ms;  // CUDA-event time of the k_ensemble_loop launches of this call (shared by its realizations)
                 reports[k].conflicts = rounds;     // rounds (= launches) of this call
+                // host side of the call (ms, shared by its realizations): services, launch + wait + read-back, bookkeeping, whole call so far
+                reports[k].search_ms = service_ms; reports[k].commit_ms = launch_ms; reports[k].event_ms = apply_ms; reports[k].cells_ms = since(t_call);
+                // host services of the call: duplications / table regrows through the upload boundary, RNG refills
+                reports[k].search_launches = n_dup_services; reports[k].commit_launches = n_regrow_services; reports[k].event_launches = n_rng_services;
             }
         }
     }

@@ -1153,6 +1153,7 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
 // in the same order as agg_update (sequential `myspheres` order; the overlap statistics in the butterfly order of its warp
 // reduction), so both forms give bit-identical results.
 constexpr int kSingleMax = 8;
+constexpr int kUpdateWarpMax = 96;  // spheres of an aggregate up to which ONE WARP updates it when every aggregate is updated
 __device__ void agg_update_single(const DevState &d, int slot, bool full, double box) {
     const int off = d.a_off[slot], n = d.a_n[slot];
     const int method = d.volsurf_method;
@@ -2110,7 +2111,21 @@ __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int i
     if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
     if (individual && !sc.b_merged) return;  // done by k_update_picked
     if (d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
+    if (d.a_n[slot] > kUpdateWarpMax) return;  // done by k_update_big
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], sc.box_length);
+}
+// ... and the big ones (n > kUpdateWarpMax) by a whole CTA each: a full update is O(n^2), a 10^3-sphere aggregate left to one warp would
+// take milliseconds.  (The overlap statistics are combined in the tree of the group that computes them: every path — this kernel and
+// the per-realization step loop — gives an aggregate of a given size to the same kind of group, so all paths agree bit for bit.)
+__global__ void __launch_bounds__(kCommitThreads) k_update_big(DevState d, int full, int individual) {
+    __shared__ double scratch[kUpdateScratch];
+    const Scalars &sc = *d.sc;
+    if (d.sc->error != 0) return;
+    if (individual && !sc.b_merged) return;
+    for (int slot = blockIdx.x; slot < sc.n_agg_slots; slot += gridDim.x) {
+        if (!d.a_alive[slot] || d.a_n[slot] <= kUpdateWarpMax) continue;
+        agg_update<true>(d, slot, full != 0, threadIdx.x, blockDim.x, scratch, sc.box_length);
+    }
 }
 // individual surface reactions without a merge: only the picked aggregate is updated (calcul.cpp:196-203) — by a whole CTA, so
 // that a 10^3-sphere aggregate's O(n^2) contact pass is not left to one warp
@@ -2140,7 +2155,17 @@ __global__ void __launch_bounds__(256) k_update_all(DevState d, int full, int on
     if (only_slot >= 0) { if (slot != 0) return; slot = only_slot; }
     if (slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
     if (only_slot < 0 && d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
+    if (only_slot < 0 && d.a_n[slot] > kUpdateWarpMax) return;  // done by k_update_big
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], d.sc->box_length);
+}
+// Aggregate::update() / update_partial() of ONE aggregate (per-call C ABI), by the group every other path gives an aggregate of its size
+__global__ void __launch_bounds__(kCommitThreads) k_update_one(DevState d, int full, int slot) {
+    __shared__ double scratch[kUpdateScratch];
+    if (slot < 0 || slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
+    const int n = d.a_n[slot];
+    if (n <= kSingleMax) { if (threadIdx.x == 0) agg_update_single(d, slot, full != 0, d.sc->box_length); }
+    else if (n <= kUpdateWarpMax) { if (threadIdx.x < 32) agg_update<false>(d, slot, full != 0, threadIdx.x, 32, scratch, d.sc->box_length); }
+    else agg_update<true>(d, slot, full != 0, threadIdx.x, blockDim.x, scratch, d.sc->box_length);
 }
 // single-aggregate entry points of the per-call C ABI
 __global__ void __launch_bounds__(kCommitThreads) k_translate_one(DevState d, int slot, double vx, double vy, double vz) {

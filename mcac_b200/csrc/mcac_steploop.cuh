@@ -15,7 +15,6 @@
 namespace mcacb {
 
 constexpr int kLoopThreads = 512;
-constexpr int kLoopWarpMax = 96;  // spheres of an aggregate up to which one warp updates it when every aggregate is updated
 constexpr int kLoopDynSmem = 5 * kLoopThreads * (int)sizeof(double);
 enum LoopExit { LOOP_STEPS_DONE = 0, LOOP_FINISHED = 1, LOOP_NEED_DUP = 2, LOOP_NEED_REGROW = 3, LOOP_NEED_RNG = 4, LOOP_TOO_BIG = 5,
                 LOOP_ERROR = 6, LOOP_EVENT_STOP = 7 };
@@ -514,7 +513,9 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             pick_valid = false;
         }
         if (sc.n_agg_slots > a.max_slots || sc.n_agg > a.cum_sequential_max) { reason = LOOP_TOO_BIG; break; }
-        if (d.sph_cap - sc.pool_top < sc.n_sph) cta_compact_pool(d, a, a.scan_tmp);
+        // (with nucleation the regrow test below wants 64 more free slots than the plain compaction test: compact for those as well,
+        // a regrow goes through the host)
+        if (d.sph_cap - sc.pool_top < sc.n_sph + (a.with_nucleation ? 64 : 0) && sc.pool_top > sc.n_sph) cta_compact_pool(d, a, a.scan_tmp);
         if (a.with_nucleation && (d.agg_cap - sc.n_agg_slots < 64 || d.sph_cap - sc.pool_top < sc.n_sph + 64)) { reason = LOOP_NEED_REGROW; break; }
         if (sc.rand_pos < d.rng_buf_base || sc.rand_pos - d.rng_buf_base + 8192 + 64 > d.rng_buf_n) { reason = LOOP_NEED_RNG; break; }
         lap(4);
@@ -615,11 +616,11 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
                     if (d.a_alive[s] && d.a_n[s] <= kSingleMax) agg_update_single(d, s, full, sc.box_length);
                 __syncthreads();
                 for (int s = warp; s < n_slots; s += nwarps)
-                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && d.a_n[s] <= kLoopWarpMax)
+                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && d.a_n[s] <= kUpdateWarpMax)
                         agg_update<false>(d, s, full, lane, 32, upd_scratch[warp], sc.box_length, upd_stage + warp * (5 * 32));
                 __syncthreads();
                 for (int s = 0; s < n_slots; s++)
-                    if (d.a_alive[s] && d.a_n[s] > kLoopWarpMax) agg_update<true>(d, s, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
+                    if (d.a_alive[s] && d.a_n[s] > kUpdateWarpMax) agg_update<true>(d, s, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
             }
             __syncthreads();
         }
@@ -650,6 +651,27 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
     }
 }
 
+// AggregatList::duplication alone (the speculative-batch path and the per-call C ABI): one CTA, in place when the tables have room
+// (LoopState::dups == 1 afterwards; 0: nothing was touched, the host re-allocates and does it through the upload boundary)
+__global__ void __launch_bounds__(kLoopThreads) k_duplicate(DevState d_in, LoopArgs a_in) {
+    __shared__ DevState d;
+    __shared__ LoopArgs a;
+    if (threadIdx.x == 0) {
+        d = d_in; a = a_in;
+        LoopState &out = *a_in.out;
+        out.steps = 0; out.events = 0; out.nucleated = 0; out.sorts = 0; out.compactions = 0; out.dups = 0; out.flipped = 0;
+        for (int k = 0; k < 8; k++) out.phase_cycles[k] = 0;
+    }
+    __syncthreads();
+    bool labels_valid = a.labels_valid != 0;
+    const bool ok = cta_duplicate(d, a, labels_valid, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.out->exit_reason = ok ? LOOP_STEPS_DONE : LOOP_NEED_DUP;
+        a.out->labels_valid = labels_valid ? 1 : 0;
+        a.out->pick_valid = 0;
+    }
+}
 // one realization, one CTA
 __global__ void __launch_bounds__(kLoopThreads) k_step_loop(DevState d_in, LoopArgs a_in) {
     __shared__ DevState d;
@@ -659,7 +681,9 @@ __global__ void __launch_bounds__(kLoopThreads) k_step_loop(DevState d_in, LoopA
     step_loop(d, a);
 }
 // many realizations, CTAs take them from a queue; `ds` is updated in place (compaction swaps the sphere buffers)
-__global__ void __launch_bounds__(kLoopThreads) k_ensemble_loop(DevState *ds, LoopArgs *as, int n, int *next) {
+// sc_all / ls_all (optional): every realization's Scalars and LoopState are also left in these contiguous arrays when it leaves the
+// loop, so that the host reads the whole round back with two copies instead of two per realization
+__global__ void __launch_bounds__(kLoopThreads) k_ensemble_loop(DevState *ds, LoopArgs *as, int n, int *next, Scalars *sc_all, LoopState *ls_all) {
     __shared__ DevState d;
     __shared__ LoopArgs a;
     __shared__ int s_r;
@@ -674,6 +698,14 @@ __global__ void __launch_bounds__(kLoopThreads) k_ensemble_loop(DevState *ds, Lo
         step_loop(d, a);
         __syncthreads();
         if (threadIdx.x == 0) { ds[r] = d; as[r] = a; }
+        if (sc_all) {
+            const int *src = reinterpret_cast<const int *>(d.sc);
+            int *dst = reinterpret_cast<int *>(sc_all + r);
+            for (int k = threadIdx.x; k < (int)(sizeof(Scalars) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+            const int *ls = reinterpret_cast<const int *>(a.out);
+            int *ld = reinterpret_cast<int *>(ls_all + r);
+            for (int k = threadIdx.x; k < (int)(sizeof(LoopState) / sizeof(int)); k += blockDim.x) ld[k] = ls[k];
+        }
     }
 }
 
