@@ -223,7 +223,7 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     for (double **p : {&d.a_rg, &d.a_fagg, &d.a_lpm, &d.a_ts, &d.a_vol, &d.a_surf, &d.a_rx, &d.a_ry, &d.a_rz, &d.a_ptime, &d.a_dp,
                        &d.a_dgdp, &d.a_ovl, &d.a_cn, &d.a_dm, &d.a_ch, &d.a_bulk, &d.a_alpha, &d.cum, &d.keys})
         TRY(dev_alloc(h, p, agg_cap));
-    for (int **p : {&d.a_n, &d.a_off, &d.a_cx, &d.a_cy, &d.a_cz, &d.a_charge, &d.a_alive, &d.label_of_slot, &d.slot_of_label,
+    for (int **p : {&d.a_n, &d.a_off, &d.a_cx, &d.a_cy, &d.a_cz, &d.a_charge, &d.a_alive, &d.a_dirty, &d.label_of_slot, &d.slot_of_label,
                     &d.sorted_slot, &d.cell_items, &h->sorted_label})
         TRY(dev_alloc(h, p, agg_cap));
     TRY(dev_alloc(h, &d.cell_posr, agg_cap));

@@ -73,6 +73,9 @@ struct DevState {
     double *a_rg, *a_fagg, *a_lpm, *a_ts, *a_vol, *a_surf, *a_rx, *a_ry, *a_rz, *a_ptime, *a_dp, *a_dgdp, *a_ovl, *a_cn, *a_dm, *a_ch,
         *a_bulk, *a_alpha;
     int *a_n, *a_off, *a_cx, *a_cy, *a_cz, *a_charge, *a_alive;
+    // 1: radii or membership changed since the aggregate's last FULL update (its contact graph, overlap statistics and effective
+    // volumes / surfaces must be recomputed); 0: a full update would recompute exactly what is stored, so it runs as a partial one
+    int *a_dirty;
     int *label_of_slot, *slot_of_label;
     // ---- Verlet cells
     int *cell_start, *cell_fill, *cell_items;

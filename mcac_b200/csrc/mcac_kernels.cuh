@@ -907,6 +907,11 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
     const int off = d.a_off[slot], n = d.a_n[slot];
     const int method = d.volsurf_method;
     const int w = tid >> 5, nw = (nth + 31) >> 5;
+    // Aggregate::update() of an aggregate whose spheres did not change since its last full update recomputes, from the same relative
+    // positions and radii, exactly the contact graph, overlap statistics, effective volumes / surfaces and V, S that are stored: the
+    // O(n^2) pass is skipped (individual surface reactions grow one aggregate per step; the reference's loop updates all of them)
+    if (full && d.a_dirty[slot] == 0) full = false;
+    group_sync<kBlock>();  // everybody has read the flag before the full pass clears it
     if (full) {
         // ---- contact pass (update_distances_and_overlapping + the contact-graph loops of compute_volume_surface)
         double vals[7] = {0., 0., 0., 0., 0., 0., 0.};  // intersections, sum c_ij, c_s10, c_v20, c_v30, vp_sum, sp_sum
@@ -1017,6 +1022,7 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
             d.a_cn[slot] = cn;
             d.a_vol[slot] = V;
             d.a_surf[slot] = S;
+            d.a_dirty[slot] = 0;
             if (V <= 0 || S <= 0) d.sc->error = 8;  // VolSurfError, aggregat.cpp:427-429
         }
         group_sync<kBlock>();
@@ -1234,6 +1240,7 @@ __device__ void agg_update_single(const DevState &d, int slot, bool full, double
         d.a_cn[slot] = cn;
         d.a_vol[slot] = V;
         d.a_surf[slot] = S;
+        d.a_dirty[slot] = 0;
         if (V <= 0 || S <= 0) d.sc->error = 8;  // VolSurfError, aggregat.cpp:427-429
     }
     // ---- update_partial
@@ -1337,6 +1344,7 @@ __device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int 
         d.a_alpha[kept] = 1.0 / static_cast<double>(n_k + n_r);
         d.a_alive[removed] = 0;
         d.a_n[removed] = 0;
+        d.a_dirty[kept] = 1;
         d.sc->n_agg -= 1;
     }
     __syncthreads();
@@ -1848,6 +1856,7 @@ __device__ __forceinline__ void dev_nucleate(const DevState &d, double deltatemp
             d.a_off[slot] = sp;
             d.a_alpha[slot] = 1.0;
             d.a_alive[slot] = 1;
+            d.a_dirty[slot] = 1;
             d.a_charge[slot] = 0;
             d.a_ptime[slot] = sc.time;
             d.a_ch[slot] = 0.;
@@ -2065,6 +2074,9 @@ __global__ void k_grow(DevState d, double dt, int only_slot) {
     int lo = 0, hi = d.sc->pool_top;
     if (only_slot >= 0) { lo = d.a_off[only_slot]; hi = lo + d.a_n[only_slot]; }
     const int t = lo + s;
+    // radii change: the aggregates concerned need their next full update in full (there are never more aggregate slots than spheres)
+    if (only_slot >= 0) { if (s == 0) d.a_dirty[only_slot] = 1; }
+    else if (s < d.sc->n_agg_slots) d.a_dirty[s] = 1;
     if (t >= hi) return;
     double4 p = d.s_posr[t];
     const double new_r = p.w + d.u_sg * dt;  // PhysicalModel::grow, physical_model.cpp:587-590
@@ -2087,6 +2099,8 @@ __global__ void k_grow_pending(DevState d, int individual) {
     double dt = sc.p_dt;
     if (individual) { lo = d.a_off[sc.p_slot]; hi = lo + d.a_n[sc.p_slot]; dt = sc.p_dt_indiv; }
     const int t = lo + s;
+    if (individual) { if (s == 0) d.a_dirty[sc.p_slot] = 1; }
+    else if (s < sc.n_agg_slots) d.a_dirty[s] = 1;
     if (t >= hi) return;
     double4 p = d.s_posr[t];
     const double new_r = p.w + d.u_sg * dt;
@@ -3645,6 +3659,7 @@ __global__ void __launch_bounds__(256) k_upload_aggregates(DevState d, HostLayou
     d.a_cx[a] = (int)s.agg_cells[a]; d.a_cy[a] = (int)s.agg_cells[m + a]; d.a_cz[a] = (int)s.agg_cells[2 * m + a];
     d.a_charge[a] = (int)s.agg_charge[a];
     d.a_alive[a] = 1;
+    d.a_dirty[a] = 1;
     d.label_of_slot[a] = (int)a;
     d.slot_of_label[a] = (int)a;
 }

@@ -432,6 +432,7 @@ __device__ __forceinline__ bool cta_duplicate(DevState &d, LoopArgs &a, bool &la
             d.a_cx[dst] = d.a_cx[src]; d.a_cy[dst] = d.a_cy[src]; d.a_cz[dst] = d.a_cz[src];
             d.a_charge[dst] = 0;  // the copy constructor resets the charge (aggregat_storage.cpp:138)
             d.a_alive[dst] = 1;
+            d.a_dirty[dst] = d.a_dirty[src];
             d.label_of_slot[dst] = n0 + t;
             d.slot_of_label[n0 + t] = dst;
         }
@@ -582,6 +583,8 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             int lo = 0, hi = sc.pool_top;
             double dt = sc.p_dt;
             if (a.individual) { lo = d.a_off[sc.p_slot]; hi = lo + d.a_n[sc.p_slot]; dt = sc.p_dt_indiv; }
+            if (a.individual) { if (tid == 0) d.a_dirty[sc.p_slot] = 1; }
+            else for (int s2 = tid; s2 < sc.n_agg_slots; s2 += nth) d.a_dirty[s2] = 1;
             for (int t = lo + tid; t < hi; t += nth) {
                 double4 p = d.s_posr[t];
                 const double new_r = p.w + d.u_sg * dt;
