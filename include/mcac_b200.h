@@ -163,6 +163,10 @@ int mcac_gpu_merge(mcac_gpu *h, const mcac_contact *contact, int *merged);
 int mcac_gpu_grow(mcac_gpu *h, double dt, int64_t label);
 /* Aggregate::update() (full != 0) / update_partial() for one label or all (label < 0)  aggregat.cpp:247-288 */
 int mcac_gpu_update(mcac_gpu *h, int64_t label, int full);
+/* Aggregate::get_lpm / get_time_step / ... (include/aggregats/aggregat.hpp:83-133): the 21 AggregatesFields of one aggregate (constants.hpp:
+ * 46-69 order: RG, F_AGG, LPM, TIME_STEP, RMAX, VOLUME, SURFACE, X, Y, Z, RX, RY, RZ, TIME, DP, DG_OVER_DP, OVERLAPPING, COORDINATION_NUMBER,
+ * ELECTRIC_CHARGE, D_M, CH_RATIO) and its number of spheres */
+int mcac_gpu_aggregate_fields(mcac_gpu *h, int64_t label, double fields[21], int64_t *n_spheres);
 /* AggregatList::refresh() + get_total_volume/surface() + PhysicalModel::update  aggregat_list.cpp:100-108,28-45 */
 int mcac_gpu_refresh(mcac_gpu *h, double *max_time_step, double *avg_npp, double *total_volume, double *total_surface);
 /* AggregatList::sort_time_steps(factor)                                 aggregat_list.cpp:124-141 */

@@ -206,6 +206,12 @@ class Simulation:
     def update(self, label: int = -1, full: bool = True):
         self._ck(self.L.mcac_gpu_update(self.h, label, int(full)))
 
+    def aggregate_fields(self, label: int):
+        """(the 21 AggregatesFields of one aggregate as a dict, n_spheres) — Aggregate::get_lpm / get_time_step / ..."""
+        f = np.zeros(21); n = C.c_int64()
+        self._ck(self.L.mcac_gpu_aggregate_fields(self.h, label, ptr(f), C.byref(n)))
+        return dict(zip(AGG_FIELDS, (float(v) for v in f))), n.value
+
     def refresh(self):
         a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         self._ck(self.L.mcac_gpu_refresh(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

@@ -100,7 +100,7 @@ EXPORTS = [
     "mcac_host_last_error", "mcac_host_model_create", "mcac_host_model_destroy", "mcac_host_model_params", "mcac_host_model_sizes",
     "mcac_host_model_metadata", "mcac_host_model_derived", "mcac_host_model_ini_echo", "mcac_host_model_state", "mcac_sim_create",
     "mcac_io_writer_create", "mcac_io_begin_step", "mcac_io_positions", "mcac_io_attribute", "mcac_io_end_step", "mcac_io_writer_destroy",
-    "mcac_gpu_save", "mcac_gpu_set_strict_direction", "mcac_gpu_reserve",
+    "mcac_gpu_save", "mcac_gpu_set_strict_direction", "mcac_gpu_reserve", "mcac_gpu_aggregate_fields",
 ]
 
 
@@ -165,6 +165,7 @@ def lib() -> C.CDLL:
         L.mcac_gpu_save.argtypes = [vp, vp, vp]
         L.mcac_gpu_set_strict_direction.argtypes = [vp, C.c_int32]
         L.mcac_gpu_reserve.argtypes = [vp, i64, i64]
+        L.mcac_gpu_aggregate_fields.argtypes = [vp, i64, vp, C.POINTER(i64)]
         _lib = L
     return _lib
 

@@ -1433,6 +1433,24 @@ int mcac_gpu_update(mcac_gpu *h, int64_t label, int full) {
     return E_OK;
 }
 
+int mcac_gpu_aggregate_fields(mcac_gpu *h, int64_t label, double fields[21], int64_t *n_spheres) {
+    CK(cudaSetDevice(h->device));
+    TRY(pull_scalars(h));
+    TRY(refresh_labels(h));
+    if (label < 0 || label >= h->sc_host.n_agg) { h->err = "aggregate_fields: bad label"; return E_INPUT; }
+    int slot;
+    CK(cudaMemcpyAsync(&slot, h->d.slot_of_label + label, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    k_aggregate_fields<<<1, 32, 0, h->stream>>>(h->d, slot, h->stats_dev);
+    h->launches++;
+    double v[22];
+    CK(cudaMemcpyAsync(v, h->stats_dev, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (fields) std::memcpy(fields, v, 21 * sizeof(double));
+    if (n_spheres) *n_spheres = (int64_t)v[21];
+    return E_OK;
+}
+
 int mcac_gpu_refresh(mcac_gpu *h, double *max_time_step, double *avg_npp, double *total_volume, double *total_surface) {
     CK(cudaSetDevice(h->device));
     TRY(pull_scalars(h));
@@ -2175,8 +2193,7 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
         cudaSetDevice(handles[loop_set[0]]->device);
         struct Track { Scalars at_start; long long launches0; int64_t steps = 0, dups = 0, sorts = 0, nucleated = 0; bool fin = false, host_only = false; };
         std::vector<Track> tr((size_t)m);
-        parallel_for(loop_set, [&](int k) { cudaSetDevice(handles[k]->device); rcs[(size_t)k] = pull_scalars(handles[k]); handles[k]->loop_host->exit_reason = LOOP_STEPS_DONE; });
-        for (int i = 0; i < m; i++) { tr[(size_t)i].at_start = handles[loop_set[(size_t)i]]->sc_host; tr[(size_t)i].launches0 = handles[loop_set[(size_t)i]]->launches; }
+        // (the Scalars of all realizations are fetched below with one gather kernel + one copy, once the scratch arrays exist)
         cudaStream_t es = nullptr;
         DevState *ds_dev = nullptr;
         LoopArgs *as_dev = nullptr;
@@ -2192,6 +2209,27 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
             cudaMalloc((void **)&as_dev, sizeof(LoopArgs) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&next_dev, sizeof(int)) != cudaSuccess ||
             cudaMalloc((void **)&sc_all_dev, sizeof(Scalars) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&ls_all_dev, sizeof(LoopState) * (size_t)m) != cudaSuccess)
             rc_all = E_UNKNOWN;
+        if (rc_all == E_OK) {  // current Scalars of every realization: one gather + one copy (every handle's stream is idle between calls)
+            std::vector<Scalars *> ptrs((size_t)m);
+            for (int i = 0; i < m; i++) ptrs[(size_t)i] = handles[loop_set[(size_t)i]]->d.sc;
+            Scalars **ptrs_dev = reinterpret_cast<Scalars **>(as_dev);  // (scratch: LoopArgs is larger than a pointer)
+            bool ok = cudaDeviceSynchronize() == cudaSuccess &&
+                      cudaMemcpyAsync(ptrs_dev, ptrs.data(), sizeof(Scalars *) * (size_t)m, cudaMemcpyHostToDevice, es) == cudaSuccess;
+            if (ok) {
+                k_gather_scalars<<<std::max(1, std::min(m, 296)), 256, 0, es>>>(ptrs_dev, m, sc_all_dev);
+                ok = cudaGetLastError() == cudaSuccess &&
+                     cudaMemcpyAsync(sc_all_host.data(), sc_all_dev, sizeof(Scalars) * (size_t)m, cudaMemcpyDeviceToHost, es) == cudaSuccess &&
+                     cudaStreamSynchronize(es) == cudaSuccess;
+            }
+            if (!ok) rc_all = E_UNKNOWN;
+            for (int i = 0; i < m && ok; i++) {
+                mcac_gpu *h = handles[loop_set[(size_t)i]];
+                h->sc_host = sc_all_host[(size_t)i];
+                h->loop_host->exit_reason = LOOP_STEPS_DONE;
+                tr[(size_t)i].at_start = h->sc_host;
+                tr[(size_t)i].launches0 = h->launches;
+            }
+        }
         int occ = 1, n_sm = handles[loop_set[0]]->n_sm;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_loop, kLoopThreads, kLoopDynSmem);
         cudaEvent_t ev_a = nullptr, ev_b = nullptr;

@@ -2125,7 +2125,7 @@ __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int i
     if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
     if (individual && !sc.b_merged) return;  // done by k_update_picked
     if (d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
-    if (d.a_n[slot] > kUpdateWarpMax) return;  // done by k_update_big
+    if (full && d.a_n[slot] > kUpdateWarpMax && d.a_dirty[slot]) return;  // an O(n^2) pass of a big aggregate: done by k_update_big
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], sc.box_length);
 }
 // ... and the big ones (n > kUpdateWarpMax) by a whole CTA each: a full update is O(n^2), a 10^3-sphere aggregate left to one warp would
@@ -2136,9 +2136,10 @@ __global__ void __launch_bounds__(kCommitThreads) k_update_big(DevState d, int f
     const Scalars &sc = *d.sc;
     if (d.sc->error != 0) return;
     if (individual && !sc.b_merged) return;
+    if (!full) return;  // partial updates are chains of ordered adds: one warp each (k_update_step / k_update_all)
     for (int slot = blockIdx.x; slot < sc.n_agg_slots; slot += gridDim.x) {
-        if (!d.a_alive[slot] || d.a_n[slot] <= kUpdateWarpMax) continue;
-        agg_update<true>(d, slot, full != 0, threadIdx.x, blockDim.x, scratch, sc.box_length);
+        if (!d.a_alive[slot] || d.a_n[slot] <= kUpdateWarpMax || !d.a_dirty[slot]) continue;
+        agg_update<true>(d, slot, true, threadIdx.x, blockDim.x, scratch, sc.box_length);
     }
 }
 // individual surface reactions without a merge: only the picked aggregate is updated (calcul.cpp:196-203) — by a whole CTA, so
@@ -2169,7 +2170,7 @@ __global__ void __launch_bounds__(256) k_update_all(DevState d, int full, int on
     if (only_slot >= 0) { if (slot != 0) return; slot = only_slot; }
     if (slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
     if (only_slot < 0 && d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
-    if (only_slot < 0 && d.a_n[slot] > kUpdateWarpMax) return;  // done by k_update_big
+    if (only_slot < 0 && full && d.a_n[slot] > kUpdateWarpMax && d.a_dirty[slot]) return;  // done by k_update_big
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], d.sc->box_length);
 }
 // Aggregate::update() / update_partial() of ONE aggregate (per-call C ABI), by the group every other path gives an aggregate of its size
@@ -2178,8 +2179,17 @@ __global__ void __launch_bounds__(kCommitThreads) k_update_one(DevState d, int f
     if (slot < 0 || slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
     const int n = d.a_n[slot];
     if (n <= kSingleMax) { if (threadIdx.x == 0) agg_update_single(d, slot, full != 0, d.sc->box_length); }
-    else if (n <= kUpdateWarpMax) { if (threadIdx.x < 32) agg_update<false>(d, slot, full != 0, threadIdx.x, 32, scratch, d.sc->box_length); }
+    else if (n <= kUpdateWarpMax || !full || !d.a_dirty[slot]) { if (threadIdx.x < 32) agg_update<false>(d, slot, full != 0, threadIdx.x, 32, scratch, d.sc->box_length); }
     else agg_update<true>(d, slot, full != 0, threadIdx.x, blockDim.x, scratch, d.sc->box_length);
+}
+// the 21 AggregatesFields of one aggregate slot (per-call C ABI)
+__global__ void k_aggregate_fields(DevState d, int slot, double *out /* 22 */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double4 p = d.a_posr[slot];
+    const double v[22] = {d.a_rg[slot], d.a_fagg[slot], d.a_lpm[slot], d.a_ts[slot], p.w, d.a_vol[slot], d.a_surf[slot], p.x, p.y, p.z, d.a_rx[slot],
+                          d.a_ry[slot], d.a_rz[slot], d.a_ptime[slot], d.a_dp[slot], d.a_dgdp[slot], d.a_ovl[slot], d.a_cn[slot],
+                          static_cast<double>(d.a_charge[slot]), d.a_dm[slot], d.a_ch[slot], static_cast<double>(d.a_n[slot])};
+    for (int k = 0; k < 22; k++) out[k] = v[k];
 }
 // single-aggregate entry points of the per-call C ABI
 __global__ void __launch_bounds__(kCommitThreads) k_translate_one(DevState d, int slot, double vx, double vy, double vz) {

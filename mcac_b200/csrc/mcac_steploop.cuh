@@ -618,12 +618,16 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
                 for (int s = tid; s < n_slots; s += nth)
                     if (d.a_alive[s] && d.a_n[s] <= kSingleMax) agg_update_single(d, s, full, sc.box_length);
                 __syncthreads();
+                // (only an O(n^2) pass needs the whole CTA: a big aggregate that is clean, or a partial update, is a chain of ordered adds —
+                // sixteen of those run side by side on sixteen warps)
                 for (int s = warp; s < n_slots; s += nwarps)
-                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && d.a_n[s] <= kUpdateWarpMax)
+                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && !(full && d.a_n[s] > kUpdateWarpMax && d.a_dirty[s]))
                         agg_update<false>(d, s, full, lane, 32, upd_scratch[warp], sc.box_length, upd_stage + warp * (5 * 32));
                 __syncthreads();
-                for (int s = 0; s < n_slots; s++)
-                    if (d.a_alive[s] && d.a_n[s] > kUpdateWarpMax) agg_update<true>(d, s, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
+                if (full)
+                    for (int s = 0; s < n_slots; s++)
+                        if (d.a_alive[s] && d.a_n[s] > kUpdateWarpMax && d.a_dirty[s])
+                            agg_update<true>(d, s, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
             }
             __syncthreads();
         }
@@ -682,6 +686,14 @@ __global__ void __launch_bounds__(kLoopThreads) k_step_loop(DevState d_in, LoopA
     if (threadIdx.x == 0) { d = d_in; a = a_in; }
     __syncthreads();
     step_loop(d, a);
+}
+// Scalars of many realizations into one contiguous array (one copy to the host instead of one per handle)
+__global__ void k_gather_scalars(Scalars *const *ptrs, int n, Scalars *out) {
+    const int per = (int)(sizeof(Scalars) / sizeof(int));
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (long long)n * per; k += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(k / per), w = (int)(k % per);
+        reinterpret_cast<int *>(out + r)[w] = reinterpret_cast<const int *>(ptrs[r])[w];
+    }
 }
 // many realizations, CTAs take them from a queue; `ds` is updated in place (compaction swaps the sphere buffers)
 // sc_all / ls_all (optional): every realization's Scalars and LoopState are also left in these contiguous arrays when it leaves the

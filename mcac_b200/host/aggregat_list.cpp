@@ -104,6 +104,21 @@ bool AggregatList::croissance_surface(double dt, size_t index) { check(mcac_gpu_
 void AggregatList::translate(size_t label, const std::array<double, 3> &v) { check(mcac_gpu_translate(gpu, static_cast<int64_t>(label), v.data())); }
 void AggregatList::update(long label) { check(mcac_gpu_update(gpu, label, 1)); }
 void AggregatList::update_partial(long label) { check(mcac_gpu_update(gpu, label, 0)); }
+std::array<double, 21> AggregatList::fields(size_t label, size_t *n_spheres) const {
+    std::array<double, 21> f{};
+    int64_t n = 0;
+    check(mcac_gpu_aggregate_fields(gpu, static_cast<int64_t>(label), f.data(), &n));
+    if (n_spheres) *n_spheres = static_cast<size_t>(n);
+    return f;
+}
+void Aggregate::translate(const std::array<double, 3> &vector) { list->translate(label, vector); }
+void Aggregate::update() { list->update(static_cast<long>(label)); }
+void Aggregate::update_partial() { list->update_partial(static_cast<long>(label)); }
+double Aggregate::get_lpm() const { return list->fields(label)[2]; }
+double Aggregate::get_time_step() const { return list->fields(label)[3]; }
+double Aggregate::get_rg() const { return list->fields(label)[0]; }
+size_t Aggregate::size() const { size_t n = 0; list->fields(label, &n); return n; }
+size_t SphereList::size() const { return list->n_spheres(); }
 mcac_run_report AggregatList::run(long max_steps, int batch) {
     mcac_run_report rep{};
     check(mcac_gpu_run(gpu, max_steps, batch, nullptr, 0, &rep));

@@ -20,6 +20,38 @@ struct AggregateContactInfo {
     bool operator<(const AggregateContactInfo &o) const { return distance < o.distance; }
 };
 
+class AggregatList;
+
+// One aggregate of the list, resident in HBM and addressed by its label: the methods mcac::calcul calls on `aggregates[i]`
+// (include/aggregats/aggregat.hpp:83-133).  `aggregates[num_agg]->translate(v)` reads as in src/calcul.cpp:144.
+class Aggregate {
+  public:
+    Aggregate(AggregatList *owner, size_t label) : list(owner), label(label) {}
+    Aggregate *operator->() { return this; }
+    void translate(const std::array<double, 3> &vector);
+    void update();
+    void update_partial();
+    double get_lpm() const;         // *lpm
+    double get_time_step() const;   // *time_step
+    double get_rg() const;
+    size_t size() const;            // n_spheres
+    size_t get_label() const { return label; }
+
+  private:
+    AggregatList *list;
+    size_t label;
+};
+
+// The sphere list of the AggregatList (include/spheres/sphere_list.hpp): size and output
+class SphereList {
+  public:
+    explicit SphereList(AggregatList *owner) : list(owner) {}
+    size_t size() const;
+
+  private:
+    AggregatList *list;
+};
+
 class AggregatList {
   public:
     explicit AggregatList(PhysicalModel *physicalmodel, int device = 0);  // placement (host) + upload + RNG continuation
@@ -50,6 +82,9 @@ class AggregatList {
     void update_partial(long label = -1);                               // Aggregate::update_partial()
     mcac_run_report run(long max_steps, int batch = 0);                 // the whole calcul() loop on the device
     mcac_gpu *handle() const { return gpu; }
+    Aggregate operator[](size_t label) { return Aggregate(this, label); }  // aggregates[i]->...
+    SphereList spheres{this};
+    std::array<double, 21> fields(size_t label, size_t *n_spheres = nullptr) const;  // the AggregatesFields of one aggregate
 
   private:
     void check(int rc) const;

@@ -1,6 +1,6 @@
 """Short ensemble driver for ncu (run on the B200): N realizations of examples/classic.ini advanced to a late stage outside the
 captured launch, then ONE k_ensemble_loop launch of a few steps each (ncu replays a kernel ~40 times: keep it short).
-    python profiles/ens_profile.py [realizations=148] [warm steps=2600] [captured steps=8]"""
+    ncu --profile-from-start off ... python profiles/ens_profile.py [realizations=148] [warm steps=2600] [captured steps=8]"""
 import os
 import sys
 import tempfile
@@ -23,6 +23,10 @@ table = write_interpotential_file(Path(tmp) / "Interpotential_input.dat")
 e = mcac_b200.Ensemble(classic_texts(list(range(n)), table))
 reps = e.run(warm, threads=16)
 print("warm:", sum(r["steps"] for r in reps), "steps,", sum(r["n_spheres"] for r in reps) // n, "spheres per realization")
+import torch  # noqa: E402  (only for cudaProfilerStart / Stop: ncu --profile-from-start off captures the launch below)
+
+torch.cuda.profiler.start()
 reps = e.run(cap, threads=16)
+torch.cuda.profiler.stop()
 print("captured:", sum(r["steps"] for r in reps), "steps,", sum(r["pair_tests_sphere"] for r in reps), "pair tests (reference count),",
       sum(r["pair_tests_executed"] for r in reps), "executed, kernel ms", reps[0]["device_ms"], "rounds", reps[0]["conflicts"])

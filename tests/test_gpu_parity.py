@@ -461,12 +461,13 @@ LOOP_CASES = [("classic_seed1000", 2200), ("pytest_seed42", 4000), ("brownian_se
 
 
 @pytest.mark.parametrize("name,steps", LOOP_CASES)
-@pytest.mark.parametrize("env", [{"MCAC_B200_NO_LOOP": "1"}, {"MCAC_B200_LOOP_MAX_SLOTS": "150"}, {"MCAC_B200_NO_PRUNE": "1"}])
+@pytest.mark.parametrize("env", [{"MCAC_B200_NO_LOOP": "1"}, {"MCAC_B200_LOOP_MAX_SLOTS": "150"}, {"MCAC_B200_NO_PRUNE": "1"},
+                                 {"MCAC_B200_NO_LOOP_DUP": "1"}])
 def test_step_loop_is_the_multi_launch_general_step(name, steps, env, monkeypatch, tmp_path):
     """The per-realization step loop (csrc/mcac_steploop.cuh: the whole general step of calcul() in one persistent CTA, in-kernel pool
     compaction, ordered CTA-wide sphere sweep) against the multi-launch sequence of the same device functions — bit-identical records
-    and states, across duplications / nucleation regrows / the hand-over when the aggregate table outgrows the loop
-    (MCAC_B200_LOOP_MAX_SLOTS).  Both are checked against the oracle elsewhere in this file; here: same trajectory, far fewer launches."""
+    and states, across duplications (in place on the device vs the host re-layout through the upload boundary, MCAC_B200_NO_LOOP_DUP) /
+    nucleation regrows / the hand-over when the aggregate table outgrows the loop (MCAC_B200_LOOP_MAX_SLOTS).  Both are checked against the oracle elsewhere in this file; here: same trajectory, far fewer launches."""
     from golden_lib import write_interpotential_file
     g = Golden(name)
     ov = {k: dict(v) for k, v in g.overrides.items()}
@@ -527,3 +528,21 @@ def test_strict_direction_mode_meets_the_1e12_bar_on_contact_distances(name, ste
     assert fin.sum() >= 3
     np.testing.assert_allclose(recs["distance"][fin], ref["distance"][fin], rtol=1e-12, atol=0)
     np.testing.assert_allclose(recs["full_distance"], ref["full_distance"], rtol=1e-12, atol=0)
+
+
+def test_single_aggregate_getters_read_the_device_state():
+    """Aggregate::get_lpm / get_time_step / size (include/aggregats/aggregat.hpp:83-133) through mcac_gpu_aggregate_fields: the 21
+    AggregatesFields of one label equal the downloaded state's row."""
+    g = Golden("c3_small_seed42")
+    sim = Simulation(ini_text(merged_config(g.base, g.overrides)))
+    sim.run(6000, batch=128)
+    st = sim.state()
+    for label in (0, 17, st["n_agg"] - 1, int(np.argmax(st["agg_n_spheres"]))):
+        f, n = sim.aggregate_fields(label)
+        assert n == st["agg_n_spheres"][label]
+        for k, v in f.items():
+            if k == "electric_charge_field":
+                continue
+            assert v == st["aggregates"][k][label], (label, k)
+    with pytest.raises(mcac_b200.McacError):
+        sim.aggregate_fields(st["n_agg"])
