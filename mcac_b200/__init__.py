@@ -245,7 +245,7 @@ class Simulation:
         return rep.as_dict()
 
     KERNELS = {"cells": 0, "grow": 1, "update_partial": 2, "update_full": 3, "event_sort": 4, "event_nosort": 5, "grid_barriers_x100": 6,
-               "rng_fill": 7, "morphology_stats": 8, "fp64_dfma": 9, "fp64_dmul_dadd": 10}
+               "rng_fill": 7, "morphology_stats": 8, "fp64_dfma": 9, "fp64_dmul_dadd": 10, "plan_probe": 11}
 
     def kernel_bench(self, which: str, reps: int = 5) -> dict:
         ms, units = C.c_double(), C.c_int64()

@@ -241,7 +241,7 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     TRY(dev_alloc(h, &sb.cut, agg_cap + 1));
     TRY(dev_alloc(h, &sb.fin_perm, agg_cap + 1));
     TRY(dev_alloc(h, &sb.fin_wk, agg_cap + 1));
-    TRY(dev_alloc(h, &sb.active, 16));
+    TRY(dev_alloc(h, &sb.active, kWinBase + 4 * kMaxWin));
     h->ts_plan = nullptr; h->ts_R = nullptr; h->ts_tbl = nullptr; h->ts_xcap = 0;
     if (h->ts_min_n > 0 && agg_cap >= h->ts_min_n) {
         h->ts_xcap = std::max(1, std::min(h->ts_max_sparse, tiesort::kMaxSparse));
@@ -459,6 +459,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.switch_span = std::max(h->sort_switch_span, h->sort_local_span);
     a.work = h->event_work;
     a.smem_cap = h->event_smem_cap;
+    a.no_windows = getenv("MCAC_B200_NO_SORT_WINDOWS") ? 1 : 0;
     a.smem_bytes = (int)h->event_dyn_bytes;
     a.ts_plan = h->ts_plan;
     a.ts_R = h->ts_R;
@@ -2102,6 +2103,47 @@ int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_o
             if (which == 9) k_fp64_peak<0><<<blocks, 256, 0, h->stream>>>(h->stats_dev, iters, 1.0);
             else k_fp64_peak<1><<<blocks, 256, 0, h->stream>>>(h->stats_dev, iters, 1.0);
             units = (int64_t)blocks * 256 * 8 * 2 * iters;
+            break;
+        }
+        case 11: {  // tuning probe: the sparse simulation alone (MCAC_B200_PROBE_X sparse elements among n_agg, synthetic positions)
+            if (!h->ts_plan || h->event_dyn_bytes == 0) { h->err = "kernel_bench: tie-sort path off"; rc = E_INPUT; break; }
+            int x = 3915;
+            if (const char *e = getenv("MCAC_B200_PROBE_X")) x = std::max(1, std::min(atoi(e), h->ts_xcap));
+            const int n = (int)sc.n_agg;
+            if (r == -1) {
+                std::vector<int> pos(x);
+                std::vector<double> w(x);
+                unsigned long long lcg = 88172645463325252ULL;
+                auto rnd = [&]() { lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(lcg >> 11) / 9007199254740992.0; };
+                const double stride = (double)n / x;
+                for (int j = 0; j < x; j++) {
+                    pos[j] = std::min(n - 1, (int)(j * stride + rnd() * std::max(1.0, stride - 1.0)));
+                    if (j > 0 && pos[j] <= pos[j - 1]) pos[j] = pos[j - 1] + 1;
+                    w[j] = 0.2 + 0.7 * rnd();
+                }
+                if ((rc = ensure_stage(h, (sizeof(int) + sizeof(double)) * (size_t)x + 64)) != E_OK) break;
+                CK(cudaMemcpyAsync(h->stage, w.data(), sizeof(double) * x, cudaMemcpyHostToDevice, h->stream));
+                CK(cudaMemcpyAsync((char *)h->stage + sizeof(double) * x, pos.data(), sizeof(int) * x, cudaMemcpyHostToDevice, h->stream));
+                CK(cudaMemsetAsync(h->event_work, 0, 32 * sizeof(long long), h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                cudaFuncSetAttribute(k_plan_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->event_dyn_bytes);
+            }
+            int lg = 0;
+            while ((1LL << (lg + 1)) <= n) lg++;
+            k_plan_probe<<<1, kEventThreads, h->event_dyn_bytes, h->stream>>>(n, x, (const int *)((char *)h->stage + sizeof(double) * x), (const double *)h->stage, 1.0,
+                                                                             2 * lg, h->sort_local_span, h->ts_plan, h->ts_R, h->ts_tbl, h->ts_xcap,
+                                                                             (int)h->event_dyn_bytes, h->event_work);
+            units = x;
+            if (r == reps - 1) {
+                long long cyc[12];
+                CK(cudaMemcpyAsync(cyc, h->event_work, sizeof(cyc), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                fprintf(stderr, "plan_probe: n %d x %d cycles/launch %.0f levels %.2f handed %.0f | per launch: pivot %.0f pivot-move %.0f table %.0f barrier %.0f aK %.0f moves %.0f end %.0f\n",
+                        n, x, (double)cyc[0] / (reps + 1), (double)cyc[1] / (reps + 1), (double)cyc[2] / (reps + 1), (double)cyc[4] / (reps + 1),
+                        (double)cyc[5] / (reps + 1), (double)cyc[6] / (reps + 1), (double)cyc[7] / (reps + 1), (double)cyc[8] / (reps + 1),
+                        (double)cyc[9] / (reps + 1), (double)cyc[10] / (reps + 1));
+                CK(cudaMemsetAsync(h->event_work, 0, 32 * sizeof(long long), h->stream));
+            }
             break;
         }
         default: h->err = "kernel_bench: unknown kernel"; rc = E_INPUT;

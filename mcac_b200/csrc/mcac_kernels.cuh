@@ -2564,6 +2564,7 @@ constexpr int kEventThreads = 512;
 // layout of the scratch arrays: part_ll (4096 entries) = [0, gridDim) per-block counts / chunk sums of the level scans, [kPartSparseCounts, +gridDim)
 // sparse elements staged per block; part_d (16384) = five per-block partials of gridDim entries each, [kPartCumChunks, +8192) chunk sums of the cumulative table
 constexpr int kPartSparseCounts = 2048, kPartCumChunks = 8192;
+constexpr int kMaxWin = 512, kWinMin = 256, kWinBase = 16;  // SortBufs::active holds kWinBase + 4 * kMaxWin entries
 struct EventArgs {
     SortBufs sb;
     long long *part_ll;   // >= gridDim + 1
@@ -2579,6 +2580,7 @@ struct EventArgs {
     int smem_cap;         // entries of dynamic shared memory per array available to the block-local levels (0 = none)
     int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
     int depth_override;   // test hook (MCAC_B200_SORT_DEPTH): introsort depth limit instead of 2*log2(n); < 0 = off
+    int no_windows;       // tuning hook (MCAC_B200_NO_SORT_WINDOWS): the local levels by block 0 alone, as before
     long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
     // tie-dominated tables (tie_sort.cuh): top levels simulated on the sparse elements only
     tiesort::Plan *ts_plan;
@@ -2596,6 +2598,27 @@ struct BlockTeam {  // tiesort's Team for one CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(kFull, v, o); v = t < v ? t : v; }
         if ((tid & 31) == 0 && v != 0x7fffffff) atomicMin(p, v);
+    }
+    __device__ __forceinline__ void lap(int) {}
+    // called after a CTA barrier: what the team wrote before it becomes visible device-wide, then the progress word
+    __device__ __forceinline__ void publish(int *p, int v) {
+        if (tid == 0) { __threadfence(); *reinterpret_cast<volatile int *>(p) = v; }
+    }
+};
+struct ProbeTeam {  // BlockTeam + phase clocks of thread 0 (k_plan_probe)
+    int tid, nthr;
+    long long *acc, prev;
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void team_min(int *p, int v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(kFull, v, o); v = t < v ? t : v; }
+        if ((tid & 31) == 0 && v != 0x7fffffff) atomicMin(p, v);
+    }
+    __device__ __forceinline__ void lap(int k) {
+        if (tid == 0) { const long long t = clock64(); atomicAdd(reinterpret_cast<unsigned long long *>(acc + k), (unsigned long long)(t - prev)); prev = t; }
+    }
+    __device__ __forceinline__ void publish(int *p, int v) {
+        if (tid == 0) { __threadfence(); *reinterpret_cast<volatile int *>(p) = v; }
     }
 };
 namespace cgx = cooperative_groups;
@@ -2657,6 +2680,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const long long gtid = (long long)blk * nthr + tid, gsize = (long long)nblk * nthr;
     Scalars &sc = *d.sc;
     if (a.skip_if_no_event && sc.event == 0) return;  // submitted ahead of the read-back of a batch that turned out not to merge
+    if (gtid == 0 && a.ts_plan) { a.ts_plan->ready = 0; a.ts_plan->done = 0; }  // (two grid barriers before anybody looks at them)
     const int n_slots = sc.n_agg_slots;
     // phase clocks of block 0 (SM cycles) accumulated into a.work[2 + k]: diagnostics for the K9 breakdown in profiles/
     long long t_prev = clock64();
@@ -2859,7 +2883,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         while (ts_nb < x && ts_nb < tiesort::kBuckets) ts_nb <<= 1;
         const int xs_pad = ((int)x + 3) & ~3;
         const int used_ints = 4 * xs_pad + (ts_nb + 3) + 16 + 2 * (nblk + 1) + 4;
-        ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && used_ints * (int)sizeof(int) <= a.smem_bytes;
+        ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && used_ints * (int)sizeof(int) <= a.smem_bytes &&
+                a.smem_bytes >= 4 * nthr * (int)sizeof(int);  // (the routing pass parks >= 4 positions per thread in shared memory)
         if (ts_on) {
             const int xs = (int)x;
             int *st_pos = b.tmp_b;                                 // compact staged labels / weights of the sparse elements
@@ -2889,6 +2914,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     st_pos[id] = b.tmp_a[src];
                     st_w[id] = chunk_w[src];
                 }
+                if (tid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }  // (before the first level is published)
                 __syncthreads();
                 lap(14);
                 BlockTeam tm{tid, nthr};
@@ -2901,6 +2927,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 // tables) and goes straight on to the block-local sort levels, while the other CTAs route the rest of the table
                 if (tid == 0)
                     a.ts_plan->overlap = (a.ts_plan->n_levels <= arch_levels && hlen <= a.local_span && nblk > 1 && !a.ts_no_overlap) ? 1 : 0;
+                __syncthreads();
+                tm.publish(&a.ts_plan->done, 1);  // the plan is final: the routing CTAs leave their level loop
                 for (int j = tid; j < xs; j += nthr) {
                     const int p = a_s[j] - hf, id = a_i[j];
                     b.perm[p] = st_pos[id];
@@ -2908,23 +2936,129 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     b.segf[p] = 0;
                     b.segl[p] = hlen;
                 }
-                if (tid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }
             }
-            grid.sync();
-            lap(16);  // (laps 14-16 -> work[16..18]: the sparse simulation in three parts; the host adds them up for phase 8)
+            // Routing pass of the other CTAs: every W element follows the simulated levels to its final position or to its place in
+            // the handed-over segment.  It runs BESIDE the simulation: a CTA waits for level t to be published (Plan::ready), moves
+            // all its elements through it (positions parked in shared memory between levels, kRoute elements advanced together so
+            // that their independent table look-ups are in flight at the same time), and is one level behind when the simulation ends.
             __shared__ tiesort::Plan sh_plan;
-            for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
-                reinterpret_cast<int *>(&sh_plan)[k] = reinterpret_cast<const int *>(a.ts_plan)[k];
-            __syncthreads();
+            __shared__ int sh_ready, sh_done;
+            const int *__restrict__ R = a.ts_R;
+            const int *__restrict__ T = a.ts_tbl;
+            const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
+            bool any_bad = false;
+            constexpr int kRoute = 4;
+            const bool router = nblk > 1 ? blk != 0 : true;  // (a one-CTA launch routes after its own simulation)
+            const long long rtid = nblk > 1 ? gtid - nthr : gtid, rsize = nblk > 1 ? gsize - nthr : gsize;
+            int *s_pos = reinterpret_cast<int *>(dyn_smem);  // [e][tid]; free in the routing CTAs (and in a lone CTA after plan_build)
+            const int e_cap = min(64, max(kRoute, (a.smem_bytes / (int)sizeof(int) / nthr) & ~(kRoute - 1)));  // (64: the `live` mask)
+            const int e_all = (int)((n + rsize - 1) / rsize);
+            // all-equal right part [cut, l) entered at `p`: final position by the closed form, straight into the pick table
+            auto finish_dense = [&](const tiesort::Level &L, int p, int lab) {
+                bool bad = false;
+                const int fp = tiesort::all_equal_final(L.cut, L.l, p, L.depth, bad);
+                if (bad) { any_bad = true; return; }
+                d.sorted_slot[fp] = d.slot_of_label[lab];
+                a.sorted_label[fp] = lab;
+            };
+            int known_ready = 0, known_done = 0;
+            for (int e0 = 0; router && e0 < e_all; e0 += e_cap) {
+                const int E = min(e_cap, e_all - e0);
+                unsigned long long live = 0;
+                for (int e = 0; e < E; e++) {
+                    const long long i = rtid + (long long)(e0 + e) * rsize;
+                    s_pos[e * nthr + tid] = (int)i;
+                    if (i < n && is_sparse[i] == 0) live |= 1ULL << e;
+                }
+                for (int t = 0;; t++) {
+                    if (t >= known_ready && !known_done) {  // wait for level t (or for the end of the simulation)
+                        __syncthreads();
+                        if (tid == 0) {
+                            const volatile int *vr = &a.ts_plan->ready, *vd = &a.ts_plan->done;
+                            int r = *vr, dn = 0;
+                            while (r <= t) {
+                                dn = *vd;
+                                if (dn) { r = *vr; break; }
+                                __nanosleep(100);
+                                r = *vr;
+                            }
+                            __threadfence();
+                            sh_ready = r;
+                            sh_done = dn;
+                        }
+                        __syncthreads();
+                        known_ready = sh_ready;
+                        known_done = sh_done;
+                    }
+                    if (t >= known_ready) break;  // (done, and every published level taken)
+                    const tiesort::Level L = a.ts_plan->lv[t];
+                    const int *__restrict__ Rt = R + (size_t)t * a.ts_xcap;
+                    const int *__restrict__ Tt = T + (size_t)t * tiesort::kTblStride;
+                    for (int g = 0; g < E; g += kRoute) {
+                        const unsigned lv4 = (unsigned)(live >> g) & ((1u << kRoute) - 1);
+                        if (!lv4) continue;
+                        int pos[kRoute], lo_[kRoute], hi_[kRoute];
+#pragma unroll
+                        for (int j = 0; j < kRoute; j++) {  // pivot move + bucket bounds (dead lanes look at a valid dummy position)
+                            int p = (lv4 >> j & 1) ? s_pos[(g + j) * nthr + tid] : L.f + 1;
+                            if (p == L.f) p = L.pick;
+                            else if (p == L.pick) p = L.f;
+                            pos[j] = p;
+                            const int bkt = (p - L.f) >> L.shift;
+                            lo_[j] = Tt[bkt];
+                            hi_[j] = Tt[bkt + 1];
+                        }
+#pragma unroll
+                        for (int j = 0; j < kRoute; j++) {
+                            if (!(lv4 >> j & 1)) continue;
+                            int p = pos[j];
+                            if (p > L.f) {
+                                int r = lo_[j];
+                                while (r < hi_[j] && Rt[r] < p) r++;
+                                const int ka = p - (L.f + 1) - r;
+                                if (ka < L.K) p = L.l - 1 - ka;
+                                else {
+                                    const int kb = L.l - 1 - p;
+                                    if (kb < L.K) p = tiesort::select_dense(Rt, Tt, L.f, L.shift, kb);
+                                }
+                            }
+                            if (p >= L.cut) {  // into the all-W right part [cut, l)
+                                finish_dense(L, p, (int)(rtid + (long long)(e0 + g + j) * rsize));
+                                live &= ~(1ULL << (g + j));
+                            } else s_pos[(g + j) * nthr + tid] = p;
+                        }
+                    }
+                }
+                if (e0 == 0) {  // the plan is final here
+                    for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
+                        reinterpret_cast<int *>(&sh_plan)[k] = reinterpret_cast<const volatile int *>(a.ts_plan)[k];
+                    __syncthreads();
+                }
+                if (!sh_plan.overlap && !sh_plan.fail) {  // (overlap: the simulating CTA has filled the handed-over segment)
+                    const int hf = sh_plan.hand_f, hlen = sh_plan.hand_l - hf;
+                    for (int e = 0; e < E; e++) {
+                        if (!(live >> e & 1)) continue;
+                        const int p = s_pos[e * nthr + tid] - hf;
+                        b.perm[p] = (int)(rtid + (long long)(e0 + e) * rsize);
+                        b.wk[p] = ts_W;
+                        b.segf[p] = 0;
+                        b.segl[p] = hlen;
+                    }
+                }
+                __syncthreads();  // s_pos is reused by the next round
+            }
+            if (!router || e_all == 0) {  // the simulating CTA (and routers without elements): the final plan
+                __syncthreads();
+                for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
+                    reinterpret_cast<int *>(&sh_plan)[k] = reinterpret_cast<const volatile int *>(a.ts_plan)[k];
+                __syncthreads();
+            }
+            lap(16);  // (laps 14-16 -> work[16..18]: the sparse simulation in three parts; the host adds them up for phase 8)
             if (sh_plan.fail) {  // introsort's heap-sort branch: the host redoes this sort on the multi-launch device path (k_sort_heap)
                 if (gtid == 0) sc.b_need = 99;
                 return;
             }
             const int hf = sh_plan.hand_f, hlen = sh_plan.hand_l - hf;
-            const int *__restrict__ R = a.ts_R;
-            const int *__restrict__ T = a.ts_tbl;
-            const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
-            bool any_bad = false;
             ts_ovl = sh_plan.overlap != 0;
             if (ts_ovl && blk == 0) {
                 unsigned char *s_mark = reinterpret_cast<unsigned char *>(b_s);  // list b is free after plan_build: xs_pad ints >= hlen bytes?
@@ -2949,113 +3083,6 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     b.segl[p - hf] = hlen;
                 }
                 __syncthreads();
-            }
-            // Every W element: final position, or its place in the handed-over segment.  kRoute elements per thread advance level
-            // by level together, so that their table look-ups (independent of each other) are in flight at the same time.
-            constexpr int kRoute = 4;
-            const long long rtid = ts_ovl ? gtid - nthr : gtid, rsize = ts_ovl ? gsize - nthr : gsize;
-            for (long long i0 = (ts_ovl && blk == 0) ? (long long)n : rtid; i0 < n; i0 += rsize * kRoute) {
-                int pos[kRoute], e_base[kRoute], e_dep[kRoute];
-                unsigned e_m[kRoute], e_r[kRoute];  // e_m == 0: not (yet) in an all-W segment
-                bool live[kRoute];
-#pragma unroll
-                for (int j = 0; j < kRoute; j++) {
-                    e_m[j] = 0; e_r[j] = 0; e_base[j] = 0; e_dep[j] = 0;
-                    const long long i = i0 + j * rsize;
-                    pos[j] = (int)i;
-                    live[j] = i < n && is_sparse[i < n ? i : 0] == 0;
-                }
-                for (int t = 0; t < sh_plan.n_levels; t++) {
-                    if (!(live[0] | live[1] | live[2] | live[3])) break;
-                    const tiesort::Level L = sh_plan.lv[t];
-                    const int *__restrict__ Rt = R + (size_t)t * a.ts_xcap;
-                    const int *__restrict__ Tt = T + (size_t)t * tiesort::kTblStride;
-                    int lo_[kRoute], hi_[kRoute];
-#pragma unroll
-                    for (int j = 0; j < kRoute; j++) {  // pivot move + bucket bounds (dead lanes look at a valid dummy position)
-                        int p = live[j] ? pos[j] : L.f + 1;
-                        if (p == L.f) p = L.pick;
-                        else if (p == L.pick) p = L.f;
-                        pos[j] = p;
-                        const int bkt = (p - L.f) >> L.shift;
-                        lo_[j] = Tt[bkt];
-                        hi_[j] = Tt[bkt + 1];
-                    }
-#pragma unroll
-                    for (int j = 0; j < kRoute; j++) {
-                        if (!live[j]) continue;
-                        int p = pos[j];
-                        if (p > L.f) {
-                            int r = lo_[j];
-                            while (r < hi_[j] && Rt[r] < p) r++;
-                            const int ka = p - (L.f + 1) - r;
-                            if (ka < L.K) p = L.l - 1 - ka;
-                            else {
-                                const int kb = L.l - 1 - p;
-                                if (kb < L.K) p = tiesort::select_dense(Rt, Tt, L.f, L.shift, kb);
-                            }
-                        }
-                        if (p >= L.cut) {  // into the all-W right part [cut, l): finished below, the kRoute chains interleaved
-                            e_m[j] = (unsigned)(L.l - L.cut);
-                            e_r[j] = (unsigned)(p - L.cut);
-                            e_base[j] = L.cut;
-                            e_dep[j] = L.depth;
-                            live[j] = false;
-                        }
-                        pos[j] = p;
-                    }
-                }
-                // all-equal segments (tiesort::all_equal_final, segment-relative form)
-                bool fast = true;
-#pragma unroll
-                for (int j = 0; j < kRoute; j++) {
-                    int bits = 0;
-                    while ((e_m[j] >> bits) != 0) bits++;
-                    if (e_m[j] > (unsigned)tiesort::kLeaf && e_dep[j] < bits) fast = false;
-                }
-                if (fast) {
-                    while ((e_m[0] > 16u) | (e_m[1] > 16u) | (e_m[2] > 16u) | (e_m[3] > 16u)) {
-#pragma unroll
-                        for (int j = 0; j < kRoute; j++) {
-                            unsigned m = e_m[j], r = e_r[j];
-                            const bool on = m > 16u;
-                            const unsigned mid = m >> 1;
-                            if (r == 0) r = mid;
-                            else if (r == mid) r = 0;
-                            if (r) r = m - r;
-                            const unsigned c = 1 + ((m - 1) >> 1);
-                            unsigned nm = c, nr = r;
-                            int nb = e_base[j];
-                            if (r >= c) { nr = r - c; nb += (int)c; nm = m - c; }
-                            if (on) { e_m[j] = nm; e_r[j] = nr; e_base[j] = nb; }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kRoute; j++) {
-                        if (e_m[j] == 0) continue;
-                        bool bad = false;
-                        const int fp = tiesort::all_equal_final(e_base[j], e_base[j] + (int)e_m[j], e_base[j] + (int)e_r[j], e_dep[j], bad);
-                        if (bad) { any_bad = true; e_m[j] = 0; }
-                        else { e_r[j] = (unsigned)(fp - e_base[j]); e_m[j] = 1; }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kRoute; j++) {  // straight into the pick table; the weight (W) is implied by the position >= hand_l
-                    if (e_m[j] == 0) continue;
-                    const int fp = e_base[j] + (int)e_r[j], lab = (int)(i0 + j * rsize);
-                    d.sorted_slot[fp] = d.slot_of_label[lab];
-                    a.sorted_label[fp] = lab;
-                }
-#pragma unroll
-                for (int j = 0; j < kRoute; j++) {
-                    if (!live[j] || ts_ovl) continue;  // (overlap: the simulating CTA has filled the handed-over segment)
-                    const int p = pos[j] - hf;
-                    b.perm[p] = (int)(i0 + j * rsize);
-                    b.wk[p] = ts_W;
-                    b.segf[p] = 0;
-                    b.segl[p] = hlen;
-                }
             }
             if (any_bad) b.active[2] = 1;
             n_sort = hlen;
@@ -3094,7 +3121,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         b.wk[f] = b.wk[pick]; b.perm[f] = b.perm[pick];
         b.wk[pick] = kf; b.perm[pick] = lf;
     };
-    // b.active: [0],[1] ping-pong "some segment still > 16", [2] fail, [4..7] ping-pong (min, max) of the span of active segments
+    // b.active: [0],[1] ping-pong "some segment still > 16", [2] fail, [4..7] ping-pong (min, max) of the span of active segments,
+    // [kWinBase + parity * 2 * kMaxWin + 2 * k, + 1]: (min, max) of the active segments that START in window k of the span (below)
     if (gtid == 0) {
         if (active) pivot_of(0, n_sort);
         b.active[4] = 0; b.active[5] = n_sort; b.active[6] = 0x7fffffff; b.active[7] = 0;
@@ -3107,7 +3135,14 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     // Two thresholds: below `switch_span` elements block 0 works alone (block barriers instead of grid barriers; the state still in
     // HBM / L2: a span of ~10^4 elements gains nothing from more CTAs and each grid barrier costs ~3 us), and once the span also fits
     // the shared-memory staging area (smem_cap, sized by local_span) the remaining levels run out of shared memory.
+    // Windows: the segments of a level are independent of each other, so as soon as every group of active segments that start in
+    // the same window of the span (width >= kWinMin, at most one window per CTA) fits the shared-memory staging area, each CTA
+    // takes its window's segments through ALL the remaining levels alone — block barriers and shared memory instead of four grid
+    // barriers per level, and the windows run in parallel.  The new segment leaders record the windows of the next level.
     const int kSortSwitch = a.switch_span > a.local_span ? a.switch_span : a.local_span;
+    const int n_win = min(nblk, kMaxWin);
+    const bool win_allowed = a.smem_cap > 0 && !ts_ovl && nblk > 1 && !a.no_windows;
+    bool win_rec = false, windowed = false;  // win_rec: the previous level recorded the windows of this one
     int eblk = blk, enblk = nblk;
     long long etid = gtid, esize = gsize;
     auto barrier = [&]() { if (local) __syncthreads(); else grid.sync(); };
@@ -3122,7 +3157,29 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     lap(2);
     while (active) {
         depth--;
-        const int amin = act[4 + 2 * (level & 1)], amax = act[5 + 2 * (level & 1)];
+        int amin = act[4 + 2 * (level & 1)], amax = act[5 + 2 * (level & 1)];
+        if (!local && win_rec) {
+            const int *win = b.active + kWinBase + (level & 1) * 2 * kMaxWin;
+            int fits = 1;
+            for (int k = tid; k < n_win; k += nthr) {
+                const int lo = win[2 * k], hi = win[2 * k + 1];
+                if (hi > lo && hi - lo + 2 > a.smem_cap) fits = 0;
+            }
+            if (__syncthreads_and(fits)) {
+                local = true;
+                windowed = true;
+                const int lo = blk < n_win ? win[2 * blk] : 0x7fffffff, hi = blk < n_win ? win[2 * blk + 1] : 0;
+                if (hi <= lo) break;  // no segment starts in this CTA's window: wait at the barrier behind the loop
+                eblk = 0; enblk = 1; etid = tid; esize = nthr;
+                if (tid < 8) sh_act[tid] = b.active[tid];
+                __syncthreads();
+                if (tid == 0) { sh_act[4 + 2 * (level & 1)] = lo; sh_act[5 + 2 * (level & 1)] = hi; }
+                act = sh_act;
+                __syncthreads();
+                amin = lo;
+                amax = hi;
+            }
+        }
         if (!local && amax - amin <= kSortSwitch) {
             local = true;
             if (blk != 0) break;  // the other blocks wait at the barrier behind the loop
@@ -3131,6 +3188,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             act = sh_act;
             __syncthreads();
         }
+        // (uniform over the grid) this level's new leaders record the windows of the next level
+        const int win_w = max(kWinMin, (amax - amin + n_win - 1) / n_win);
+        const bool win_now = !local && win_allowed && (long long)(amax - amin) <= (long long)n_win * a.smem_cap;
+        int *win_next = b.active + kWinBase + ((level + 1) & 1) * 2 * kMaxWin;
         if (local && !staged) {  // (block 0 only from here on)
             if (amax - amin + 2 <= a.smem_cap) {
                 // The remaining levels run out of shared memory: the span's sort state is staged once (element i lives at
@@ -3163,7 +3224,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             __syncthreads();
         }
         const int span = amax - amin + 1;  // + 1 so that pre[amax] exists
-        if (etid == 0 && a.work) { work_add(0, span); work_add(1, 1); }
+        if (gtid == 0 && a.work) { work_add(0, span); work_add(1, 1); }
         const int chunk = ((span + enblk - 1) / enblk + nthr - 1) / nthr * nthr;
         // ---- flags + chunk sums
         {
@@ -3301,6 +3362,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             act[4 + 2 * ((level + 1) & 1)] = 0x7fffffff;
             act[5 + 2 * ((level + 1) & 1)] = 0;
         }
+        if (win_now && etid < 2 * n_win) win_next[etid] = (etid & 1) ? 0 : 0x7fffffff;
         barrier();
         // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
         int lead_min = 0x7fffffff, lead_max = 0;  // span of the new segments this thread leads
@@ -3320,6 +3382,11 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     lead_min = nf < lead_min ? nf : lead_min;
                     lead_max = nl > lead_max ? nl : lead_max;
                     pivot_of(nf, nl);
+                    if (win_now) {
+                        const int k = (nf - amin) / win_w;
+                        atomicMin(&win_next[2 * k], nf);
+                        atomicMax(&win_next[2 * k + 1], nl);
+                    }
                 } else act[2] = 1;  // would enter introsort's heap-sort branch
             }
         }
@@ -3340,6 +3407,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         fail = act[2] != 0;
         if (fail) break;
         lap(local ? 4 : 3);
+        win_rec = win_now;
         level++;
     }
     // cumulative_time_steps, first half: sums of fixed chunks of the sorted weights (the general sort's output inside
@@ -3376,7 +3444,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     // overlap mode: the handed-over segment belongs to block 0 alone, which also sorts its leaves (out of shared memory when the
     // levels were staged): the grid-wide leaf pass and its barrier are skipped
     const bool leaves_by_block0 = ts_ovl && n_sort > kSortLeaf;
-    if (local && blk == 0) {
+    if (local && (blk == 0 || windowed) && act == sh_act) {  // (a CTA without a window of its own has nothing staged)
         if (leaves_by_block0) {
             __syncthreads();
             if (!fail)
@@ -3503,6 +3571,31 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         sc.last_sort_tie = ts_on ? 1 : 0;
     }
     lap(7);
+}
+
+// Tuning probe (mcac_gpu_kernel_bench 11): the sparse simulation of tie_sort.cuh alone, one CTA with k_event's shared-memory layout,
+// on a synthetic tie-dominated table (x sparse elements among n).  cycles[0] += SM cycles of plan_build, cycles[1] += its levels.
+__global__ void __launch_bounds__(kEventThreads) k_plan_probe(int n, int xs, const int *st_pos, const double *st_w, double W, int depth0, int hand_min,
+                                                              tiesort::Plan *plan, int *R, int *tbl, int xcap, int smem_bytes, long long *cycles) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int ts_nb = 256;
+    while (ts_nb < xs && ts_nb < tiesort::kBuckets) ts_nb <<= 1;
+    const int xs_pad = (xs + 3) & ~3;
+    const int used_ints = 4 * xs_pad + (ts_nb + 3) + 16;
+    int *sm = reinterpret_cast<int *>(dyn_smem);
+    int *a_s = sm, *a_i = a_s + xs_pad, *b_s = a_i + xs_pad, *b_i = b_s + xs_pad, *s_tbl = b_i + xs_pad, *s_misc = s_tbl + ts_nb + 3, *arch_R = s_misc + 16;
+    const int arch_levels = min(tiesort::kMaxLevels, (smem_bytes / (int)sizeof(int) - used_ints) / (xs + ts_nb + 3 + 1));
+    int *arch_T = arch_R + (size_t)arch_levels * xs;
+    ProbeTeam tm{tid, nthr, cycles + 4, 0};
+    __syncthreads();
+    const long long t0 = clock64();
+    tm.prev = t0;
+    tiesort::plan_build(tm, n, xs, st_pos, st_w, W, depth0, hand_min, plan, R, tbl, xcap, a_s, a_i, b_s, b_i, s_tbl, s_misc, arch_R, arch_T, arch_levels);
+    if (tid == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(cycles), (unsigned long long)(clock64() - t0));
+        atomicAdd(reinterpret_cast<unsigned long long *>(cycles + 1), (unsigned long long)plan->n_levels);
+        atomicAdd(reinterpret_cast<unsigned long long *>(cycles + 2), (unsigned long long)(plan->hand_l - plan->hand_f));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -50,6 +50,8 @@ struct Plan {
     int x;                            // sparse elements
     int overlap;                      // set by the caller: the simulating CTA fills and sorts the handed-over segment itself
     int nb;                           // buckets of a rank table (power of two >= x, 256 .. kBuckets)
+    int ready;                        // levels published so far (tables + lv[] visible device-wide): the routing pass follows it level by level
+    int done;                         // set by the caller after the last level and the fields above are final
     double W;
     Level lv[kMaxLevels];
 };
@@ -244,6 +246,7 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         else { pick = pb; kp = kb; }
         const bool at_f = mc[3] >= 0;  // a sparse element at f is cs[0]
         if (kp != W) break;            // a sparse pivot: the rest goes to the general sort
+        tm.lap(0);
         depth--;
         for (int k = tm.tid; k < 4; k += tm.nthr) mn[k] = -1;  // (last read before the barrier that ended the previous level)
         if (tm.tid == 0) mn[4] = kIntMax;
@@ -261,18 +264,22 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
             int *ti_ = ci; ci = oi; oi = ti_;
             tm.sync();
         }
+        tm.lap(1);
         const int M = len - 1, n_a = M - x;
         // (arch_*: a second copy of the tables of the first arch_levels levels, strides x and nb + 3, kept by the caller)
         const bool ar = arch_R && t < arch_levels;
         const int shift = build_table_and_k(tm, x, nb, cs, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride,
                                             ar ? arch_R + (size_t)t * x : nullptr, ar ? arch_T + (size_t)t * (nb + 3) : nullptr, &mc[4]);
+        tm.lap(2);
         tm.sync();
+        tm.lap(3);
         const int K = mc[4] < n_a ? mc[4] : n_a;
         const int aK = K < n_a ? select_dense(cs, s_tbl, f, shift, K) : kIntMax;
         const int bK = K > 0 ? l - K : l;
         const int cut = aK < bK ? aK : bK;
         // moves (current list -> other buffer, still ascending) + the pivot samples of the next level [f, cut)
         const int npa = f + 1, npb = f + (cut - f) / 2, npc = cut - 1;
+        tm.lap(4);
         for (int j = tm.tid; j < x; j += tm.nthr) {
             const int q = cs[j], kb2 = l - 1 - q;
             int np, nr;
@@ -292,6 +299,7 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
             if (np == npc) mn[2] = nr;
             if (np == f) mn[3] = nr;
         }
+        tm.lap(5);
         if (tm.tid == 0) {
             Level L;
             L.f = f; L.l = l; L.pick = pick; L.K = K; L.cut = cut; L.depth = depth; L.shift = shift; L.pad = 0;
@@ -302,6 +310,8 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         l = cut;
         t++;
         tm.sync();
+        tm.publish(&plan->ready, t);  // level t - 1 (its tables, its Level record) can be used by other teams
+        tm.lap(6);
     }
     if (cs != a_s) {  // the caller reads the final list from (a_s, a_i)
         tm.sync();
@@ -325,6 +335,8 @@ struct SerialTeam {
     int tid = 0, nthr = 1;
     void sync() {}
     void team_min(int *p, int v) { if (v < *p) *p = v; }
+    void lap(int) {}
+    void publish(int *p, int v) { *p = v; }
 };
 
 }  // namespace tiesort
