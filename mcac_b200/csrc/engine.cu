@@ -16,6 +16,7 @@
 #include <string>
 #include <thread>
 #include <type_traits>
+#include <mutex>
 #include <vector>
 
 #include "../../include/mcac_b200.h"
@@ -246,7 +247,7 @@ int alloc_state(mcac_gpu *h, long long agg_cap, long long sph_cap) {
     if (h->ts_min_n > 0 && agg_cap >= h->ts_min_n) {
         h->ts_xcap = std::max(1, std::min(h->ts_max_sparse, tiesort::kMaxSparse));
         TRY(dev_alloc(h, &h->ts_plan, 1));
-        TRY(dev_alloc(h, &h->ts_R, (size_t)tiesort::kMaxLevels * h->ts_xcap));
+        TRY(dev_alloc(h, &h->ts_R, (size_t)tiesort::kMaxLevels * h->ts_xcap + 8));  // (+8: rank look-ups read two entries past a row)
         TRY(dev_alloc(h, &h->ts_tbl, (size_t)tiesort::kMaxLevels * tiesort::kTblStride));
     }
     TRY(dev_alloc(h, &h->scan64_sums, agg_cap / (kScanBlock * kScanItems) + 8));
@@ -460,6 +461,8 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.work = h->event_work;
     a.smem_cap = h->event_smem_cap;
     a.no_windows = getenv("MCAC_B200_NO_SORT_WINDOWS") ? 1 : 0;
+    a.win_cap = 2048 + 2;  // (profiles/r2_tuning.md: 4096 -> 94 us, 2048 -> 84 us, 1024 -> 88 us of sort levels per event at N = 1e6)
+    if (const char *e = getenv("MCAC_B200_SORT_WINDOW")) a.win_cap = std::max(64, atoi(e)) + 2;
     a.smem_bytes = (int)h->event_dyn_bytes;
     a.ts_plan = h->ts_plan;
     a.ts_R = h->ts_R;
@@ -1150,14 +1153,24 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (h->ts_min_n > 0 && !getenv("MCAC_B200_NO_SORT_SMEM")) {  // scratch of the one-CTA sparse simulation (tie_sort.cuh)
             int max_optin = 0;
             cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-            const size_t need = sizeof(int) * (4 * (size_t)std::min(h->ts_max_sparse, tiesort::kMaxSparse) + tiesort::kTblStride + 16 + 2 * 1024);
+            const size_t need = sizeof(int) * (4 * ((size_t)std::min(h->ts_max_sparse, tiesort::kMaxSparse) + 4) + tiesort::kTblStride + tiesort::kMiscInts + 2 * 1024);
             if ((long long)need + 4096 <= max_optin / h->coop_bps) dyn = std::max(dyn, need);
         }
         const void *efn = h->coop_bps == 2 ? (const void *)k_event<2> : (const void *)k_event<1>;
-        if (dyn > 0 && cudaFuncSetAttribute(efn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
-            cudaGetLastError();
-            h->event_smem_cap = 0;
-            dyn = 0;
+        // (the attribute belongs to the function, not to the handle: it is only ever raised, or a handle created later with a smaller
+        // need — the sparse path switched off, say — would take the launches of the earlier ones below their dynamic size)
+        static size_t attr_set[64][2] = {};
+        static std::mutex attr_mu;
+        {
+            std::lock_guard<std::mutex> lk(attr_mu);
+            size_t &cur = attr_set[device & 63][h->coop_bps == 2 ? 1 : 0];
+            if (dyn > cur) {
+                if (cudaFuncSetAttribute(efn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->event_smem_cap = 0;
+                    dyn = 0;
+                } else cur = dyn;
+            }
         }
         h->event_dyn_bytes = dyn;
         cudaError_t oe = h->coop_bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_event<2>, kEventThreads, dyn)

@@ -2581,6 +2581,7 @@ struct EventArgs {
     int force_fail;       // test hook: report introsort's depth-limit failure although the sort succeeded
     int depth_override;   // test hook (MCAC_B200_SORT_DEPTH): introsort depth limit instead of 2*log2(n); < 0 = off
     int no_windows;       // tuning hook (MCAC_B200_NO_SORT_WINDOWS): the local levels by block 0 alone, as before
+    int win_cap;          // a window is taken by its CTA once every window spans at most this many elements (<= smem_cap)
     long long *work;      // [0] += sum over levels of the active span (elements touched by the level passes), [1] += levels
     // tie-dominated tables (tie_sort.cuh): top levels simulated on the sparse elements only
     tiesort::Plan *ts_plan;
@@ -2604,6 +2605,21 @@ struct BlockTeam {  // tiesort's Team for one CTA
     __device__ __forceinline__ void publish(int *p, int v) {
         if (tid == 0) { __threadfence(); *reinterpret_cast<volatile int *>(p) = v; }
     }
+    __device__ __forceinline__ void add(int *p, int v) { atomicAdd(p, v); }  // (shared memory; result unused: a reduction)
+    // exclusive scan over the CTA's threads; scratch: >= 32 ints of shared memory, free again after the next CTA barrier
+    __device__ __forceinline__ int excl_scan(int v, int *scratch) {
+        const int lane = tid & 31, w = tid >> 5;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) scratch[w] = inc;
+        __syncthreads();
+        int ws = lane < (nthr >> 5) ? scratch[lane] : 0;  // every warp scans the (<= 32) warp totals itself
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, ws, o); if (lane >= o) ws += t; }
+        const int base = __shfl_sync(kFull, ws, w > 0 ? w - 1 : 0);
+        return (w > 0 ? base : 0) + inc - v;
+    }
 };
 struct ProbeTeam {  // BlockTeam + phase clocks of thread 0 (k_plan_probe)
     int tid, nthr;
@@ -2619,6 +2635,21 @@ struct ProbeTeam {  // BlockTeam + phase clocks of thread 0 (k_plan_probe)
     }
     __device__ __forceinline__ void publish(int *p, int v) {
         if (tid == 0) { __threadfence(); *reinterpret_cast<volatile int *>(p) = v; }
+    }
+    __device__ __forceinline__ void add(int *p, int v) { atomicAdd(p, v); }  // (shared memory; result unused: a reduction)
+    // exclusive scan over the CTA's threads; scratch: >= 32 ints of shared memory, free again after the next CTA barrier
+    __device__ __forceinline__ int excl_scan(int v, int *scratch) {
+        const int lane = tid & 31, w = tid >> 5;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) scratch[w] = inc;
+        __syncthreads();
+        int ws = lane < (nthr >> 5) ? scratch[lane] : 0;  // every warp scans the (<= 32) warp totals itself
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, ws, o); if (lane >= o) ws += t; }
+        const int base = __shfl_sync(kFull, ws, w > 0 ? w - 1 : 0);
+        return (w > 0 ? base : 0) + inc - v;
     }
 };
 namespace cgx = cooperative_groups;
@@ -2881,18 +2912,21 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         // per-level tables (as many levels as fit) for the walk back from the handed-over segment
         int ts_nb = 256;
         while (ts_nb < x && ts_nb < tiesort::kBuckets) ts_nb <<= 1;
-        const int xs_pad = ((int)x + 3) & ~3;
-        const int used_ints = 4 * xs_pad + (ts_nb + 3) + 16 + 2 * (nblk + 1) + 4;
+        const int xs_pad = ((int)x + 2 + 3) & ~3;  // (the lists are read up to two entries past their end)
+        const int used_ints = 4 * xs_pad + (ts_nb + 4) + tiesort::kMiscInts + 2 * (nblk + 1) + 4;
         ts_on = x <= a.ts_xcap && x <= tiesort::kMaxSparse && used_ints * (int)sizeof(int) <= a.smem_bytes &&
                 a.smem_bytes >= 4 * nthr * (int)sizeof(int);  // (the routing pass parks >= 4 positions per thread in shared memory)
         if (ts_on) {
             const int xs = (int)x;
             int *st_pos = b.tmp_b;                                 // compact staged labels / weights of the sparse elements
             double *st_w = reinterpret_cast<double *>(b.flags);
-            int *sm = reinterpret_cast<int *>(dyn_smem);
-            int *a_s = sm, *a_i = a_s + xs_pad, *b_s = a_i + xs_pad, *b_i = b_s + xs_pad, *s_tbl = b_i + xs_pad, *s_misc = s_tbl + ts_nb + 3,
-                *s_base = s_misc + 16, *arch_R = s_base + 2 * (nblk + 1) + 4;
-            const int arch_levels = min(tiesort::kMaxLevels, (a.smem_bytes / (int)sizeof(int) - used_ints) / (xs + ts_nb + 3 + 1));
+            // (the sparse elements' weights first, when there is room: the pivot samples of every level read them)
+            const bool w_smem = (used_ints + 2 * xs_pad) * (int)sizeof(int) <= a.smem_bytes;
+            double *s_w = reinterpret_cast<double *>(dyn_smem);
+            int *sm = reinterpret_cast<int *>(dyn_smem) + (w_smem ? 2 * xs_pad : 0);
+            int *a_s = sm, *a_i = a_s + xs_pad, *b_s = a_i + xs_pad, *b_i = b_s + xs_pad, *s_tbl = b_i + xs_pad, *s_misc = s_tbl + ts_nb + 4,
+                *s_base = s_misc + tiesort::kMiscInts, *arch_R = s_base + 2 * (nblk + 1) + 4;
+            const int arch_levels = min(tiesort::kMaxLevels, (a.smem_bytes / (int)sizeof(int) - used_ints - (w_smem ? 2 * xs_pad : 0)) / (xs + ts_nb + 3 + 1));
             int *arch_T = arch_R + (size_t)arch_levels * xs;
             if (blk == 0) {
                 __shared__ int ts_ws[32];
@@ -2912,14 +2946,16 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_base[mid] <= id) lo = mid; else hi = mid; }
                     const int src = lo * chunk_s + (id - s_base[lo]);
                     st_pos[id] = b.tmp_a[src];
-                    st_w[id] = chunk_w[src];
+                    const double wv = chunk_w[src];
+                    st_w[id] = wv;
+                    if (w_smem) s_w[id] = wv;
                 }
                 if (tid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }  // (before the first level is published)
                 __syncthreads();
                 lap(14);
                 BlockTeam tm{tid, nthr};
-                tiesort::plan_build(tm, n, xs, st_pos, st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, a_s, a_i, b_s, b_i,
-                                    s_tbl, s_misc, arch_R, arch_T, arch_levels);
+                tiesort::plan_build(tm, n, xs, st_pos, w_smem ? s_w : st_w, ts_W, depth, a.local_span, a.ts_plan, a.ts_R, a.ts_tbl, a.ts_xcap, a_s, a_i,
+                                    b_s, b_i, s_tbl, s_misc, arch_R, arch_T, arch_levels);
                 lap(15);
                 // the sparse elements of the handed-over segment
                 const int hf = a.ts_plan->hand_f, hlen = a.ts_plan->hand_l - hf;
@@ -3141,7 +3177,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     // barriers per level, and the windows run in parallel.  The new segment leaders record the windows of the next level.
     const int kSortSwitch = a.switch_span > a.local_span ? a.switch_span : a.local_span;
     const int n_win = min(nblk, kMaxWin);
-    const bool win_allowed = a.smem_cap > 0 && !ts_ovl && nblk > 1 && !a.no_windows;
+    const int win_cap = min(a.smem_cap, a.win_cap);
+    const bool win_allowed = win_cap > kSortLeaf + 2 && !ts_ovl && nblk > 1 && !a.no_windows;
     bool win_rec = false, windowed = false;  // win_rec: the previous level recorded the windows of this one
     int eblk = blk, enblk = nblk;
     long long etid = gtid, esize = gsize;
@@ -3163,7 +3200,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             int fits = 1;
             for (int k = tid; k < n_win; k += nthr) {
                 const int lo = win[2 * k], hi = win[2 * k + 1];
-                if (hi > lo && hi - lo + 2 > a.smem_cap) fits = 0;
+                if (hi > lo && hi - lo + 2 > win_cap) fits = 0;
             }
             if (__syncthreads_and(fits)) {
                 local = true;
@@ -3190,7 +3227,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         }
         // (uniform over the grid) this level's new leaders record the windows of the next level
         const int win_w = max(kWinMin, (amax - amin + n_win - 1) / n_win);
-        const bool win_now = !local && win_allowed && (long long)(amax - amin) <= (long long)n_win * a.smem_cap;
+        const bool win_now = !local && win_allowed && (long long)(amax - amin) <= (long long)n_win * win_cap;
         int *win_next = b.active + kWinBase + ((level + 1) & 1) * 2 * kMaxWin;
         if (local && !staged) {  // (block 0 only from here on)
             if (amax - amin + 2 <= a.smem_cap) {
@@ -3580,10 +3617,11 @@ __global__ void __launch_bounds__(kEventThreads) k_plan_probe(int n, int xs, con
     const int tid = threadIdx.x, nthr = blockDim.x;
     int ts_nb = 256;
     while (ts_nb < xs && ts_nb < tiesort::kBuckets) ts_nb <<= 1;
-    const int xs_pad = (xs + 3) & ~3;
-    const int used_ints = 4 * xs_pad + (ts_nb + 3) + 16;
+    const int xs_pad = (xs + 2 + 3) & ~3;
+    const int used_ints = 4 * xs_pad + (ts_nb + 4) + tiesort::kMiscInts;
     int *sm = reinterpret_cast<int *>(dyn_smem);
-    int *a_s = sm, *a_i = a_s + xs_pad, *b_s = a_i + xs_pad, *b_i = b_s + xs_pad, *s_tbl = b_i + xs_pad, *s_misc = s_tbl + ts_nb + 3, *arch_R = s_misc + 16;
+    int *a_s = sm, *a_i = a_s + xs_pad, *b_s = a_i + xs_pad, *b_i = b_s + xs_pad, *s_tbl = b_i + xs_pad, *s_misc = s_tbl + ts_nb + 4,
+        *arch_R = s_misc + tiesort::kMiscInts;
     const int arch_levels = min(tiesort::kMaxLevels, (smem_bytes / (int)sizeof(int) - used_ints) / (xs + ts_nb + 3 + 1));
     int *arch_T = arch_R + (size_t)arch_levels * xs;
     ProbeTeam tm{tid, nthr, cycles + 4, 0};

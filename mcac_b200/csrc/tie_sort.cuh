@@ -30,9 +30,10 @@ namespace tiesort {
 constexpr int kLeaf = 16;            // libstdc++ _S_threshold
 constexpr int kMaxLevels = 14;       // top levels handled on the sparse elements
 constexpr int kBuckets = 8192;       // buckets of a rank table
-constexpr int kTblStride = kBuckets + 3;
+constexpr int kTblStride = kBuckets + 4;   // (rows stay 16-byte aligned)
 constexpr int kMaxSparse = 8192;     // most sparse elements the one-CTA simulation takes
 constexpr int kIntMax = 0x7fffffff;
+constexpr int kMiscInts = 64;        // plan_build's s_misc: 16 entries of level state + 48 of scan scratch
 
 struct Level {
     int f, l;    // segment [f, l) partitioned at this level
@@ -57,13 +58,61 @@ struct Plan {
 };
 
 // entries of the sorted list R with position < q; tbl[b] = entries whose bucket ((pos - f) >> shift) is below b
+// (a bucket holds about one entry: the first two are fetched together instead of one after the other — the lists are readable two
+// entries past their end)
 template <class PR, class PT>
 TS_HD_CALL int rank_lt(PR R, PT tbl, int f, int shift, int q) {
     const int b = (q - f) >> shift;
     int j = tbl[b];
     const int e = tbl[b + 1];
-    while (j < e && R[j] < q) j++;
+    const int r0 = R[j], r1 = R[j + 1];
+    if (j < e && r0 < q) {
+        j++;
+        if (j < e && r1 < q) {
+            j++;
+            while (j < e && R[j] < q) j++;
+        }
+    }
     return j;
+}
+// The simulating team keeps ONE packed table: low 16 bits = the position table above, high 16 bits = the same kind of table over
+// d_i = R[i] - (f + 1) - i (the W positions of [f+1, l) before entry i; non-decreasing), bucket d_i >> shiftD.
+template <class PR, class PT>
+TS_HD_CALL int rank_lt_pk(PR R, PT pk, int f, int shift, int q) {
+    const int b = (q - f) >> shift;
+    int j = pk[b] & 0xffff;
+    const int e = pk[b + 1] & 0xffff;
+    const int r0 = R[j], r1 = R[j + 1];
+    if (j < e && r0 < q) {
+        j++;
+        if (j < e && r1 < q) {
+            j++;
+            while (j < e && R[j] < q) j++;
+        }
+    }
+    return j;
+}
+// entries with d_i < v
+template <class PR, class PT>
+TS_HD_CALL int rank_dense_lt_pk(PR R, PT pk, int f, int shiftD, int v) {
+    const int b = v >> shiftD;
+    int j = pk[b] >> 16;
+    const int e = pk[b + 1] >> 16;
+    const int r0 = R[j], r1 = R[j + 1];
+    const int t = v + f + 1;  // d_i < v  <=>  R[i] - i < v + f + 1
+    if (j < e && r0 - j < t) {
+        j++;
+        if (j < e && r1 - j < t) {
+            j++;
+            while (j < e && R[j] - j < t) j++;
+        }
+    }
+    return j;
+}
+// k-th (0-based) position of [f+1, l) that holds no sparse element, in one look-up: the sparse entries before it are those with d_i <= k
+template <class PR, class PT>
+TS_HD_CALL int select_dense_direct(PR R, PT pk, int f, int shiftD, int k) {
+    return f + 1 + k + rank_dense_lt_pk(R, pk, f, shiftD, k + 1);
 }
 // k-th (0-based) position of [f+1, l) that holds no sparse element
 template <class PR, class PT>
@@ -156,43 +205,100 @@ TS_HD int dense_origin(const Plan &P, PR R, PT tbl, int r_stride, int t_stride, 
     return pos;
 }
 
-// Bucket table of the ascending list S (x entries, positions in [f, l]): tbl[b] = entries whose bucket ((pos - f) >> shift) is
-// below b, for b = 0 .. nbk.  Written by "boundary marking" (entry j fills the buckets between its predecessor's and its own),
-// together with the global copies (Rg, Tg) the routing pass reads.
-// Bucket table of the ascending list S (x entries, positions in [f, l]): tbl[b] = entries whose bucket ((pos - f) >> shift) is
-// below b, for b = 0 .. nbk.  Written by "boundary marking" (entry j fills the buckets between its predecessor's and its own),
-// together with the global copies (Rg, Tg) the routing pass reads and the caller's archive (Ra, Ta; may be null).  The same pass
-// finds K, the number of Hoare swaps: the first k with not (k < n_a and A[k] < B[k]), where A[k] is the k-th W position and
-// B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1; entry j owns the k with exactly j sparse elements before A[k].
+// Bucket tables of the ascending list S (x entries, positions in [f, l]), packed (see rank_lt_pk): a histogram of the entries'
+// buckets (shared-memory adds, one entry apart: about one entry per bucket) followed by one scan over the <= nb + 1 buckets,
+// each thread a contiguous chunk.  The scan also writes the position table to the global copy Tg the routing pass reads and to the
+// caller's archive Ta (may be null); the entry pass copies the list to Rg / Ra and finds K, the number of Hoare swaps: the first k
+// with not (k < n_a and A[k] < B[k]), where A[k] is the k-th W position and B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1;
+// entry j owns the k with exactly j sparse elements before A[k].  Three team barriers, the last one at the end.
+TS_HD int bits_of(unsigned v) {  // number of significant bits (0 for 0)
+#ifdef __CUDA_ARCH__
+    return 32 - __clz((int)v);
+#else
+    return v ? 32 - __builtin_clz(v) : 0;
+#endif
+}
 template <class Team>
-TS_HD int build_table_and_k(Team &tm, int x, int nb, const int *S, int f, int l, int *s_tbl, int *Rg, int *Tg, int *Ra, int *Ta, int *k_min) {
-    int shift = 0;
-    while (((l - f) >> shift) > nb - 1) shift++;
-    const int nbk = ((l - f) >> shift) + 1;
+TS_HD void build_table_and_k(Team &tm, int x, int nb, const int *__restrict__ S, int f, int l, int *__restrict__ s_pk, int *__restrict__ Rg,
+                             int *__restrict__ Tg, int *__restrict__ Ra, int *__restrict__ Ta, int *k_min, int *scratch, int &shift_out, int &shiftD_out) {
+    // smallest shifts with ((l - f) >> shift) <= nb - 1 and (n_a >> shiftD) <= nb - 1 (nb is a power of two)
     const int M = l - f - 1, n_a = M - x;
+    const int nb_bits = bits_of((unsigned)nb) - 1;
+    const int shift = bits_of((unsigned)(l - f)) > nb_bits ? bits_of((unsigned)(l - f)) - nb_bits : 0;
+    const int shiftD = bits_of((unsigned)n_a) > nb_bits ? bits_of((unsigned)n_a) - nb_bits : 0;
+    const int nbk = ((l - f) >> shift) + 1, nbkD = (n_a >> shiftD) + 1;
+    const int ntab = (nbk > nbkD ? nbk : nbkD) + 1;  // entries 0 .. ntab-1 of the packed table are used (written in groups of four)
+    const int ngrp = (ntab + 3) >> 2;
+    shift_out = shift;
+    shiftD_out = shiftD;
+#ifdef __CUDA_ARCH__
+    for (int g = tm.tid; g < ngrp; g += tm.nthr) reinterpret_cast<int4 *>(s_pk)[g] = make_int4(0, 0, 0, 0);
+#else
+    for (int b = tm.tid; b < 4 * ngrp; b += tm.nthr) s_pk[b] = 0;
+#endif
+    tm.sync();
     int kbest = kIntMax;
-    for (int j = tm.tid; j <= x; j += tm.nthr) {
-        const int sp = j == 0 ? 0 : S[j - 1], sc = j == x ? 0 : S[j];
-        const int bprev = j == 0 ? -1 : (sp - f) >> shift;
-        const int bcur = j == x ? nbk : (sc - f) >> shift;
-        for (int b = bprev + 1; b <= bcur; b++) {
-            s_tbl[b] = j;
-            Tg[b] = j;
-            if (Ta) Ta[b] = j;
-        }
-        if (j < x) {
-            Rg[j] = sc;
-            if (Ra) Ra[j] = sc;
-        }
-        const int lo = j == 0 ? 0 : sp - (f + 1) - (j - 1);
-        const int hi = j == x ? n_a : sc - (f + 1) - j;
-        const int need = M - 1 - j;
-        const int kmin = need <= 0 ? 0 : (need + 1) / 2;
-        const int k = lo > kmin ? lo : kmin;
-        if (k < hi && k < kbest) kbest = k;
+    const int need0 = M - 1;
+#pragma unroll 4
+    for (int j = tm.tid; j < x; j += tm.nthr) {
+        const int sp = j ? S[j - 1] : f, sc = S[j];  // (sp = f makes lo = 0 for the first entry)
+        const int dj = sc - (f + 1) - j;
+        tm.add(&s_pk[((sc - f) >> shift) + 1], 1);
+        tm.add(&s_pk[(dj >> shiftD) + 1], 1 << 16);
+        Rg[j] = sc;
+        if (Ra) Ra[j] = sc;
+        const int lo = sp - f - j;  // = sp - (f + 1) - (j - 1)
+        const int kmin = (need0 - j + 1) >> 1;
+        int k = lo > kmin ? lo : kmin;
+        k = k > 0 ? k : 0;
+        if (k < dj && k < kbest) kbest = k;
+    }
+    if (tm.tid == 0) {  // the k behind the last sparse entry
+        const int lo = x ? S[x - 1] - f - x : 0;
+        const int kmin = (need0 - x + 1) >> 1;
+        int k = lo > kmin ? lo : kmin;
+        k = k > 0 ? k : 0;
+        if (k < n_a && k < kbest) kbest = k;
     }
     tm.team_min(k_min, kbest);  // (one shared-memory atomic per warp, not one per entry: about half of the entries are candidates)
-    return shift;
+    tm.sync();
+    // scan: each thread a contiguous chunk of groups; an odd number of groups per chunk keeps the 16-byte accesses of neighbouring
+    // threads in different banks
+    const int gchunk = ((ngrp + tm.nthr - 1) / tm.nthr) | 1;
+    const int g0 = tm.tid * gchunk < ngrp ? tm.tid * gchunk : ngrp, g1 = g0 + gchunk < ngrp ? g0 + gchunk : ngrp;
+    int sum = 0;
+#ifdef __CUDA_ARCH__
+    for (int g = g0; g < g1; g++) {
+        const int4 v = reinterpret_cast<const int4 *>(s_pk)[g];
+        sum += (v.x + v.y) + (v.z + v.w);
+    }
+#else
+    for (int b = 4 * g0; b < 4 * g1; b++) sum += s_pk[b];
+#endif
+    int run = tm.excl_scan(sum, scratch);
+    for (int g = g0; g < g1; g++) {
+#ifdef __CUDA_ARCH__
+        int4 v = reinterpret_cast<const int4 *>(s_pk)[g];
+        v.x += run; v.y += v.x; v.z += v.y; v.w += v.z;
+        run = v.w;
+        reinterpret_cast<int4 *>(s_pk)[g] = v;
+        if (4 * g <= nbk) {
+            const int4 lo4 = make_int4(v.x & 0xffff, v.y & 0xffff, v.z & 0xffff, v.w & 0xffff);
+            reinterpret_cast<int4 *>(Tg)[g] = lo4;
+            if (Ta) { Ta[4 * g] = lo4.x; Ta[4 * g + 1] = lo4.y; Ta[4 * g + 2] = lo4.z; Ta[4 * g + 3] = lo4.w; }
+        }
+#else
+        for (int b = 4 * g; b < 4 * g + 4; b++) {
+            run += s_pk[b];
+            s_pk[b] = run;
+            if (4 * g <= nbk) {
+                Tg[b] = run & 0xffff;
+                if (Ta) Ta[b] = run & 0xffff;
+            }
+        }
+#endif
+    }
+    tm.sync();
 }
 
 // The sparse simulation.  st_pos (ascending) / st_w: label and weight of the x elements whose weight is below W; n: table size;
@@ -203,6 +309,7 @@ TS_HD int build_table_and_k(Team &tm, int x, int nb, const int *S, int f, int l,
 // for rank queries + K (parallel minimum), one pass -> every sparse element computes its new position AND its new rank in closed
 // form from rank queries on the current table (the right-hand elements move to the K first W positions in reverse order, the
 // left-hand ones stay), so the list stays sorted without sorting.  Two team barriers per level (three with a pivot move).
+// (s_tbl: the packed bucket table, nb + 4 entries, 16-byte aligned; s_misc: kMiscInts entries; the four lists must be readable two entries past x)
 template <class Team>
 TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *st_w, double W, int depth0, int hand_min, Plan *plan,
                       int *R, int *tbl, int xcap, int *a_s, int *a_i, int *b_s, int *b_i, int *s_tbl, int *s_misc,
@@ -268,13 +375,13 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         const int M = len - 1, n_a = M - x;
         // (arch_*: a second copy of the tables of the first arch_levels levels, strides x and nb + 3, kept by the caller)
         const bool ar = arch_R && t < arch_levels;
-        const int shift = build_table_and_k(tm, x, nb, cs, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride,
-                                            ar ? arch_R + (size_t)t * x : nullptr, ar ? arch_T + (size_t)t * (nb + 3) : nullptr, &mc[4]);
+        int shift, shiftD;
+        build_table_and_k(tm, x, nb, cs, f, l, s_tbl, R + (size_t)t * xcap, tbl + (size_t)t * kTblStride, ar ? arch_R + (size_t)t * x : nullptr,
+                          ar ? arch_T + (size_t)t * (nb + 3) : nullptr, &mc[4], s_misc + 16, shift, shiftD);
         tm.lap(2);
-        tm.sync();
         tm.lap(3);
         const int K = mc[4] < n_a ? mc[4] : n_a;
-        const int aK = K < n_a ? select_dense(cs, s_tbl, f, shift, K) : kIntMax;
+        const int aK = K < n_a ? select_dense_direct(cs, s_tbl, f, shiftD, K) : kIntMax;
         const int bK = K > 0 ? l - K : l;
         const int cut = aK < bK ? aK : bK;
         // moves (current list -> other buffer, still ascending) + the pivot samples of the next level [f, cut)
@@ -284,13 +391,14 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
             const int q = cs[j], kb2 = l - 1 - q;
             int np, nr;
             if (kb2 < K) {  // right stopper of a swap: goes to the kb2-th W position; the movers end up in reverse order
-                np = select_dense(cs, s_tbl, f, shift, kb2);
-                nr = (np - (f + 1) - kb2) + (x - 1 - j);
+                const int before = rank_dense_lt_pk(cs, s_tbl, f, shiftD, kb2 + 1);  // sparse entries before that position
+                np = f + 1 + kb2 + before;
+                nr = before + (x - 1 - j);
             } else {        // stays; the movers that land before it: those with kb < c = W positions before q
                 const int c = q - (f + 1) - j;
                 const int first_mover = (l - c > l - K) ? l - c : l - K;
                 np = q;
-                nr = j + (x - rank_lt(cs, s_tbl, f, shift, first_mover));
+                nr = j + (x - rank_lt_pk(cs, s_tbl, f, shift, first_mover));
             }
             os[nr] = np;
             oi[nr] = ci[j];
@@ -337,6 +445,8 @@ struct SerialTeam {
     void team_min(int *p, int v) { if (v < *p) *p = v; }
     void lap(int) {}
     void publish(int *p, int v) { *p = v; }
+    void add(int *p, int v) { *p += v; }
+    int excl_scan(int, int *) { return 0; }
 };
 
 }  // namespace tiesort

@@ -12,7 +12,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 base, ov = workload_config(n, 42)
 sim = mcac_b200.Simulation(mcac_b200.ini_text(merged_config(base, ov)))
 sim.run(256, batch=256)
-for x in (250, 500, 1000, 2000, 3915, 8000):
+xs = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [250, 500, 1000, 2000, 3915, 8000]
+for x in xs:
     os.environ["MCAC_B200_PROBE_X"] = str(x)
     r = sim.kernel_bench("plan_probe", reps=20)
     print(x, r, flush=True)

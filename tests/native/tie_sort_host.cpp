@@ -31,13 +31,13 @@ static int run_case(int n, const std::vector<double> &w, int hand_min, long long
     int lg = 0;
     while ((1LL << (lg + 1)) <= n) lg++;
     const int xcap = std::max(1, x);
-    std::vector<int> R((size_t)kMaxLevels * xcap), tbl((size_t)kMaxLevels * kTblStride);
-    std::vector<int> a_s(xcap), a_i(xcap), b_s(xcap), b_i(xcap), s_tbl(kTblStride), s_misc(16);
+    std::vector<int> R((size_t)kMaxLevels * xcap + 2), tbl((size_t)kMaxLevels * kTblStride);
+    std::vector<int> a_s(xcap + 2), a_i(xcap + 2), b_s(xcap + 2), b_i(xcap + 2), s_tbl(kTblStride), s_misc(kMiscInts);
     Plan plan{};
     SerialTeam tm;
     int nb = 256;
     while (nb < x && nb < kBuckets) nb <<= 1;
-    std::vector<int> arch_R((size_t)kMaxLevels * xcap), arch_T((size_t)kMaxLevels * (nb + 3));
+    std::vector<int> arch_R((size_t)kMaxLevels * xcap + 2), arch_T((size_t)kMaxLevels * (nb + 3));
     plan_build(tm, n, x, st_pos.data(), st_w.data(), W, 2 * lg, hand_min, &plan, R.data(), tbl.data(), xcap, a_s.data(), a_i.data(),
                b_s.data(), b_i.data(), s_tbl.data(), s_misc.data(), arch_R.data(), arch_T.data(), kMaxLevels);
     if (plan.fail) { std::printf("plan.fail on n=%d x=%d\n", n, x); return 0; }
