@@ -461,7 +461,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.work = h->event_work;
     a.smem_cap = h->event_smem_cap;
     a.no_windows = getenv("MCAC_B200_NO_SORT_WINDOWS") ? 1 : 0;
-    a.win_cap = 2048 + 2;  // (profiles/r2_tuning.md: 4096 -> 94 us, 2048 -> 84 us, 1024 -> 88 us of sort levels per event at N = 1e6)
+    a.win_cap = 2048;  // (span + 1 <= 4 * blockDim: the register form of the flag scan) (profiles/r2_tuning.md: 4096 -> 94 us, 2048 -> 84 us, 1024 -> 88 us of sort levels per event at N = 1e6)
     if (const char *e = getenv("MCAC_B200_SORT_WINDOW")) a.win_cap = std::max(64, atoi(e)) + 2;
     a.smem_bytes = (int)h->event_dyn_bytes;
     a.ts_plan = h->ts_plan;
@@ -1964,6 +1964,14 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         for (int k = 0; k < 3; k++) {
             report->tie_sim_cycles[k] = w[16 + k] - h->event_work_seen[16 + k];
             report->tie_phase_cycles[0] += report->tie_sim_cycles[k];
+        }
+        if (getenv("MCAC_B200_K9_DEBUG") && w[21] > h->event_work_seen[21]) {
+            const double nw = (double)(w[21] - h->event_work_seen[21]), ns = std::max(1.0, (double)(w[12] - h->event_work_seen[12]));
+            fprintf(stderr, "k9 windows: %.1f per sort, mean %.0f cycles and %.2f levels per window; block 0 waits %.0f cycles per sort behind its own levels\n",
+                    nw / ns, (w[19] - h->event_work_seen[19]) / nw, (w[20] - h->event_work_seen[20]) / nw, (w[22] - h->event_work_seen[22]) / ns);
+            fprintf(stderr, "k9 window cycles per window: top+staging %.0f, flags+scan %.0f, scan tail %.0f, swaps %.0f, split %.0f\n",
+                    (w[23] - h->event_work_seen[23]) / nw, (w[24] - h->event_work_seen[24]) / nw, (w[25] - h->event_work_seen[25]) / nw,
+                    (w[26] - h->event_work_seen[26]) / nw, (w[27] - h->event_work_seen[27]) / nw);
         }
         for (int k = 0; k < 32; k++) h->event_work_seen[k] = w[k];
         report->sort_fallbacks = h->sort_fallbacks - h->sort_fallbacks_seen;

@@ -2941,14 +2941,26 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     __syncthreads();
                 }
                 const double *chunk_w = reinterpret_cast<const double *>(b.pre);
-                for (int id = tid; id < xs; id += nthr) {  // gather the per-chunk stages into one ascending list
-                    int lo = 0, hi = nblk;
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_base[mid] <= id) lo = mid; else hi = mid; }
-                    const int src = lo * chunk_s + (id - s_base[lo]);
-                    st_pos[id] = b.tmp_a[src];
-                    const double wv = chunk_w[src];
-                    st_w[id] = wv;
-                    if (w_smem) s_w[id] = wv;
+                for (int id0 = tid; id0 < xs; id0 += 4 * nthr) {  // gather the per-chunk stages into one ascending list (four loads in flight)
+                    int pv[4];
+                    double wv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int id = id0 + u * nthr;
+                        int lo = 0, hi = nblk;
+                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_base[mid] <= id) lo = mid; else hi = mid; }
+                        const int src = id < xs ? lo * chunk_s + (id - s_base[lo]) : 0;
+                        pv[u] = b.tmp_a[src];
+                        wv[u] = chunk_w[src];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int id = id0 + u * nthr;
+                        if (id >= xs) break;
+                        st_pos[id] = pv[u];
+                        st_w[id] = wv[u];
+                        if (w_smem) s_w[id] = wv[u];
+                    }
                 }
                 if (tid == 0) { b.active[0] = 0; b.active[1] = 0; b.active[2] = 0; b.active[3] = 0; }  // (before the first level is published)
                 __syncthreads();
@@ -2965,12 +2977,25 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     a.ts_plan->overlap = (a.ts_plan->n_levels <= arch_levels && hlen <= a.local_span && nblk > 1 && !a.ts_no_overlap) ? 1 : 0;
                 __syncthreads();
                 tm.publish(&a.ts_plan->done, 1);  // the plan is final: the routing CTAs leave their level loop
-                for (int j = tid; j < xs; j += nthr) {
-                    const int p = a_s[j] - hf, id = a_i[j];
-                    b.perm[p] = st_pos[id];
-                    b.wk[p] = st_w[id];
-                    b.segf[p] = 0;
-                    b.segl[p] = hlen;
+                for (int j0 = tid; j0 < xs; j0 += 4 * nthr) {  // (four loads in flight)
+                    int pp[4], lab[4];
+                    double wv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = j0 + u * nthr < xs ? j0 + u * nthr : tid;
+                        const int id = a_i[j];
+                        pp[u] = a_s[j] - hf;
+                        lab[u] = st_pos[id];
+                        wv[u] = w_smem ? s_w[id] : st_w[id];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (j0 + u * nthr >= xs) break;
+                        b.perm[pp[u]] = lab[u];
+                        b.wk[pp[u]] = wv[u];
+                        b.segf[pp[u]] = 0;
+                        b.segl[pp[u]] = hlen;
+                    }
                 }
             }
             // Routing pass of the other CTAs: every W element follows the simulated levels to its final position or to its place in
@@ -3041,8 +3066,8 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                             else if (p == L.pick) p = L.f;
                             pos[j] = p;
                             const int bkt = (p - L.f) >> L.shift;
-                            lo_[j] = Tt[bkt];
-                            hi_[j] = Tt[bkt + 1];
+                            lo_[j] = Tt[bkt] & 0xffff;  // (packed table: position half)
+                            hi_[j] = Tt[bkt + 1] & 0xffff;
                         }
 #pragma unroll
                         for (int j = 0; j < kRoute; j++) {
@@ -3055,7 +3080,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                                 if (ka < L.K) p = L.l - 1 - ka;
                                 else {
                                     const int kb = L.l - 1 - p;
-                                    if (kb < L.K) p = tiesort::select_dense(Rt, Tt, L.f, L.shift, kb);
+                                    if (kb < L.K) p = tiesort::select_dense_direct(Rt, Tt, L.f, L.shiftD, kb);
                                 }
                             }
                             if (p >= L.cut) {  // into the all-W right part [cut, l)
@@ -3180,6 +3205,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const int win_cap = min(a.smem_cap, a.win_cap);
     const bool win_allowed = win_cap > kSortLeaf + 2 && !ts_ovl && nblk > 1 && !a.no_windows;
     bool win_rec = false, windowed = false;  // win_rec: the previous level recorded the windows of this one
+    long long t_win = 0;                     // diagnostics: work[19..21] += cycles / levels / 1 per window, work[22] += block 0's wait for the others
+    int level_win = 0;
+    long long t_wl = 0;                      // work[23..27] += window cycles in: level top + staging, flags + scan, (rest of scan), swaps, split
+    auto wlap = [&](int k) { if (a.work && windowed && tid == 0) { const long long t = clock64(); work_add(23 + k, t - t_wl); t_wl = t; } };
     int eblk = blk, enblk = nblk;
     long long etid = gtid, esize = gsize;
     auto barrier = [&]() { if (local) __syncthreads(); else grid.sync(); };
@@ -3205,6 +3234,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             if (__syncthreads_and(fits)) {
                 local = true;
                 windowed = true;
+                t_win = clock64();
+                t_wl = t_win;
+                level_win = level;
                 const int lo = blk < n_win ? win[2 * blk] : 0x7fffffff, hi = blk < n_win ? win[2 * blk + 1] : 0;
                 if (hi <= lo) break;  // no segment starts in this CTA's window: wait at the barrier behind the loop
                 eblk = 0; enblk = 1; etid = tid; esize = nthr;
@@ -3260,9 +3292,73 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
             __syncthreads();
         }
+        wlap(0);
         const int span = amax - amin + 1;  // + 1 so that pre[amax] exists
         if (gtid == 0 && a.work) { work_add(0, span); work_add(1, 1); }
         const int chunk = ((span + enblk - 1) / enblk + nthr - 1) / nthr * nthr;
+        // Staged window of at most kLean * blockDim entries: flags and their scan stay in registers — both counters packed in one
+        // int (a window holds < 65536 entries), the warp scans of the kLean rounds independent of each other (in flight together),
+        // one pass over the (round, warp) totals by warp 0.  Two CTA barriers instead of eight, no 64-bit shuffles.
+        constexpr int kLean = 4;
+        const bool lean = local && staged && span <= kLean * nthr;
+        if (lean) {
+            __shared__ int sh_lean[kLean * (kEventThreads / 32)];
+            // (one instantiation per number of rounds: the time of this block follows the size of its unrolled code)
+            auto lean_pass = [&](auto nr_c) {
+                constexpr int NR = decltype(nr_c)::value;
+                const int lane = tid & 31, wrp = tid >> 5, nw = nthr >> 5;
+                int v[NR], inc[NR];
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    const int i = amin + r * nthr + tid;
+                    int fl = 0;
+                    if (i < amax && i < n_sort) {
+                        const int f = b.segf[i], l = b.segl[i];
+                        if (l - f > kSortLeaf && i > f) {
+                            const double kp = b.wk[f], kx = b.wk[i];
+                            const int lp = b.perm[f], lx = b.perm[i];
+                            if (!w_less(kx, lx, kp, lp, b.stable)) fl |= 1;
+                            if (!w_less(kp, lp, kx, lx, b.stable)) fl |= 1 << 16;
+                        }
+                    }
+                    v[r] = fl;
+                }
+#pragma unroll
+                for (int r = 0; r < NR; r++) inc[r] = warp_inclusive_scan(v[r], lane);
+                if (lane == 31) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) sh_lean[r * nw + wrp] = inc[r];
+                }
+                __syncthreads();
+                if (tid < 32) {  // exclusive scan of the NR * nw <= 128 totals, four per lane
+                    const int m = NR * nw;
+                    int t4[4], sum = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { t4[k] = 4 * lane + k < m ? sh_lean[4 * lane + k] : 0; sum += t4[k]; }
+                    int ex = warp_inclusive_scan(sum, lane) - sum;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (4 * lane + k < m) sh_lean[4 * lane + k] = ex;
+                        ex += t4[k];
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    const int i = amin + r * nthr + tid;
+                    if (i <= amax) {
+                        const int pre_i = sh_lean[r * nw + wrp] + inc[r] - v[r];
+                        const int pa_ = pre_i & 0xffff, pb_ = pre_i >> 16;
+                        b.pre[i] = (long long)pa_ | ((long long)pb_ << 32);
+                        if (v[r] & 1) b.tmp_a[amin + pa_] = i;
+                        if (v[r] >> 16) b.tmp_b[amin + pb_] = i;
+                    }
+                }
+            };
+            if (span <= nthr) lean_pass(std::integral_constant<int, 1>{});
+            else if (span <= 2 * nthr) lean_pass(std::integral_constant<int, 2>{});
+            else lean_pass(std::integral_constant<int, kLean>{});
+        } else {
         // ---- flags + chunk sums
         {
             const int lo = amin + eblk * chunk, hi = min(amax + 1, lo + chunk);
@@ -3287,6 +3383,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
         }
         barrier();
+        wlap(1);
         // ---- exclusive scan of the packed flags over the span
         {
             long long carry = 0;  // the same value in every thread
@@ -3334,7 +3431,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 __syncthreads();
             }
         }
+        }  // (not lean)
         barrier();
+        wlap(2);
         // ---- pairwise swaps + where the two scans stop.
         // A segment whose elements ALL equal the pivot (whole tie classes: every monomer of a monodisperse run) needs no
         // more memory passes: introsort's moves on equal keys do not depend on the data (median-of-3 picks `mid`, the
@@ -3401,6 +3500,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         }
         if (win_now && etid < 2 * n_win) win_next[etid] = (etid & 1) ? 0 : 0x7fffffff;
         barrier();
+        wlap(3);
         // ---- split + (fused) median-of-3 pivots of the next level by the new leaders
         int lead_min = 0x7fffffff, lead_max = 0;  // span of the new segments this thread leads
         // (the swap pass may already have hit the depth limit inside an all-equal segment: some of its elements are finished, the others
@@ -3440,6 +3540,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             atomicMax(&act[5 + 2 * ((level + 1) & 1)], lead_max);
         }
         barrier();
+        wlap(4);
         active = act[level & 1] != 0;
         fail = act[2] != 0;
         if (fail) break;
@@ -3505,7 +3606,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     // handed-over segment: hand_l <= 4096 < chunk) belongs to block 0, which has just finished it
     const bool cum_early = leaves_by_block0 && delta + n_sort <= chunk_c;
     if (cum_early) cum_chunk_sums();
+    if (a.work && tid == 0 && windowed && act == sh_act) { work_add(19, clock64() - t_win); work_add(20, level - level_win); work_add(21, 1); }
+    const long long t_wait = clock64();
     grid.sync();  // blocks that left the loop early wait here for block 0's local levels
+    if (a.work && gtid == 0) work_add(22, clock64() - t_wait);
     lap(4);
     fail = b.active[2] != 0 || a.force_fail != 0;
     if (fail) {  // the host redoes this sort on the multi-launch device path, which replays the heap-sort branch (k_sort_heap)

@@ -41,8 +41,8 @@ struct Level {
     int K;       // Hoare swaps of __unguarded_partition
     int cut;     // its return value: children [f, cut) (mixed: next level) and [cut, l) (W only)
     int depth;   // depth_limit after this level's decrement
-    int shift;   // bucket shift of this level's rank table
-    int pad;
+    int shift;   // bucket shift of this level's rank table (position half)
+    int shiftD;  // bucket shift of its dense-coordinate half
 };
 struct Plan {
     int n_levels;                     // levels simulated sparsely
@@ -177,11 +177,11 @@ TS_HD int dense_route(const Plan &P, PR R, PT tbl, int r_stride, int t_stride, i
         if (pos == L.f) pos = L.pick;
         else if (pos == L.pick) pos = L.f;
         if (pos > L.f) {
-            const int ka = pos - (L.f + 1) - rank_lt(Rt, Tt, L.f, L.shift, pos);  // rank among the left stoppers (W elements)
-            if (ka < L.K) pos = L.l - 1 - ka;                                       // every position is a right stopper
+            const int ka = pos - (L.f + 1) - rank_lt_pk(Rt, Tt, L.f, L.shift, pos);  // rank among the left stoppers (W elements)
+            if (ka < L.K) pos = L.l - 1 - ka;                                          // every position is a right stopper
             else {
                 const int kb = L.l - 1 - pos;
-                if (kb < L.K) pos = select_dense(Rt, Tt, L.f, L.shift, kb);
+                if (kb < L.K) pos = select_dense_direct(Rt, Tt, L.f, L.shiftD, kb);
             }
         }
         if (pos >= L.cut) return all_equal_final(L.cut, L.l, pos, L.depth, bad);
@@ -207,8 +207,8 @@ TS_HD int dense_origin(const Plan &P, PR R, PT tbl, int r_stride, int t_stride, 
 
 // Bucket tables of the ascending list S (x entries, positions in [f, l]), packed (see rank_lt_pk): a histogram of the entries'
 // buckets (shared-memory adds, one entry apart: about one entry per bucket) followed by one scan over the <= nb + 1 buckets,
-// each thread a contiguous chunk.  The scan also writes the position table to the global copy Tg the routing pass reads and to the
-// caller's archive Ta (may be null); the entry pass copies the list to Rg / Ra and finds K, the number of Hoare swaps: the first k
+// each thread a contiguous chunk.  The scan also writes the packed table to the global copy Tg the routing pass reads and its
+// position half to the caller's archive Ta (may be null); the entry pass copies the list to Rg / Ra and finds K, the number of Hoare swaps: the first k
 // with not (k < n_a and A[k] < B[k]), where A[k] is the k-th W position and B[k] = l-1-k  <=>  2k + #{sparse before A[k]} >= M-1;
 // entry j owns the k with exactly j sparse elements before A[k].  Three team barriers, the last one at the end.
 TS_HD int bits_of(unsigned v) {  // number of significant bits (0 for 0)
@@ -282,19 +282,14 @@ TS_HD void build_table_and_k(Team &tm, int x, int nb, const int *__restrict__ S,
         v.x += run; v.y += v.x; v.z += v.y; v.w += v.z;
         run = v.w;
         reinterpret_cast<int4 *>(s_pk)[g] = v;
-        if (4 * g <= nbk) {
-            const int4 lo4 = make_int4(v.x & 0xffff, v.y & 0xffff, v.z & 0xffff, v.w & 0xffff);
-            reinterpret_cast<int4 *>(Tg)[g] = lo4;
-            if (Ta) { Ta[4 * g] = lo4.x; Ta[4 * g + 1] = lo4.y; Ta[4 * g + 2] = lo4.z; Ta[4 * g + 3] = lo4.w; }
-        }
+        reinterpret_cast<int4 *>(Tg)[g] = v;
+        if (Ta && 4 * g <= nbk) { Ta[4 * g] = v.x & 0xffff; Ta[4 * g + 1] = v.y & 0xffff; Ta[4 * g + 2] = v.z & 0xffff; Ta[4 * g + 3] = v.w & 0xffff; }
 #else
         for (int b = 4 * g; b < 4 * g + 4; b++) {
             run += s_pk[b];
             s_pk[b] = run;
-            if (4 * g <= nbk) {
-                Tg[b] = run & 0xffff;
-                if (Ta) Ta[b] = run & 0xffff;
-            }
+            Tg[b] = run;
+            if (Ta && 4 * g <= nbk) Ta[b] = run & 0xffff;
         }
 #endif
     }
@@ -410,7 +405,7 @@ TS_HD void plan_build(Team &tm, int n, int x, const int *st_pos, const double *s
         tm.lap(5);
         if (tm.tid == 0) {
             Level L;
-            L.f = f; L.l = l; L.pick = pick; L.K = K; L.cut = cut; L.depth = depth; L.shift = shift; L.pad = 0;
+            L.f = f; L.l = l; L.pick = pick; L.K = K; L.cut = cut; L.depth = depth; L.shift = shift; L.shiftD = shiftD;
             plan->lv[t] = L;
         }
         { int *ts_ = cs; cs = os; os = ts_; }
