@@ -3299,65 +3299,59 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         // Staged window of at most kLean * blockDim entries: flags and their scan stay in registers — both counters packed in one
         // int (a window holds < 65536 entries), the warp scans of the kLean rounds independent of each other (in flight together),
         // one pass over the (round, warp) totals by warp 0.  Two CTA barriers instead of eight, no 64-bit shuffles.
-        constexpr int kLean = 4;
+        constexpr int kLean = 8;
         const bool lean = local && staged && span <= kLean * nthr;
         if (lean) {
+            // (rolled loops on purpose: this kernel's phases are paced by instruction fetch — the time of a block of code follows the
+            // size of what it executes, profiles/r2_tuning.md — so the per-round values are parked in the unused `flags` staging
+            // array instead of an unrolled register array)
             __shared__ int sh_lean[kLean * (kEventThreads / 32)];
-            // (one instantiation per number of rounds: the time of this block follows the size of its unrolled code)
-            auto lean_pass = [&](auto nr_c) {
-                constexpr int NR = decltype(nr_c)::value;
-                const int lane = tid & 31, wrp = tid >> 5, nw = nthr >> 5;
-                int v[NR], inc[NR];
-#pragma unroll
-                for (int r = 0; r < NR; r++) {
-                    const int i = amin + r * nthr + tid;
-                    int fl = 0;
-                    if (i < amax && i < n_sort) {
-                        const int f = b.segf[i], l = b.segl[i];
-                        if (l - f > kSortLeaf && i > f) {
-                            const double kp = b.wk[f], kx = b.wk[i];
-                            const int lp = b.perm[f], lx = b.perm[i];
-                            if (!w_less(kx, lx, kp, lp, b.stable)) fl |= 1;
-                            if (!w_less(kp, lp, kx, lx, b.stable)) fl |= 1 << 16;
-                        }
-                    }
-                    v[r] = fl;
-                }
-#pragma unroll
-                for (int r = 0; r < NR; r++) inc[r] = warp_inclusive_scan(v[r], lane);
-                if (lane == 31) {
-#pragma unroll
-                    for (int r = 0; r < NR; r++) sh_lean[r * nw + wrp] = inc[r];
-                }
-                __syncthreads();
-                if (tid < 32) {  // exclusive scan of the NR * nw <= 128 totals, four per lane
-                    const int m = NR * nw;
-                    int t4[4], sum = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { t4[k] = 4 * lane + k < m ? sh_lean[4 * lane + k] : 0; sum += t4[k]; }
-                    int ex = warp_inclusive_scan(sum, lane) - sum;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (4 * lane + k < m) sh_lean[4 * lane + k] = ex;
-                        ex += t4[k];
+            const int lane = tid & 31, wrp = tid >> 5, nw = nthr >> 5;
+            const int nr = (span + nthr - 1) / nthr;
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                const int i = amin + r * nthr + tid;
+                int fl = 0;
+                if (i < amax && i < n_sort) {
+                    const int f = b.segf[i], l = b.segl[i];
+                    if (l - f > kSortLeaf && i > f) {
+                        const double kp = b.wk[f], kx = b.wk[i];
+                        const int lp = b.perm[f], lx = b.perm[i];
+                        if (!w_less(kx, lx, kp, lp, b.stable)) fl |= 1;
+                        if (!w_less(kp, lp, kx, lx, b.stable)) fl |= 1 << 16;
                     }
                 }
-                __syncthreads();
+                const int inc = warp_inclusive_scan(fl, lane);
+                if (i <= amax) b.flags[i] = (long long)(unsigned)(inc - fl) | ((long long)fl << 32);  // exclusive prefix inside the warp, own flags
+                if (lane == 31) sh_lean[r * nw + wrp] = inc;
+            }
+            __syncthreads();
+            if (tid < 32) {  // exclusive scan of the nr * nw <= 128 totals, four per lane
+                const int m = nr * nw;
+                int t4[4], sum = 0;
 #pragma unroll
-                for (int r = 0; r < NR; r++) {
-                    const int i = amin + r * nthr + tid;
-                    if (i <= amax) {
-                        const int pre_i = sh_lean[r * nw + wrp] + inc[r] - v[r];
-                        const int pa_ = pre_i & 0xffff, pb_ = pre_i >> 16;
-                        b.pre[i] = (long long)pa_ | ((long long)pb_ << 32);
-                        if (v[r] & 1) b.tmp_a[amin + pa_] = i;
-                        if (v[r] >> 16) b.tmp_b[amin + pb_] = i;
-                    }
+                for (int k = 0; k < 4; k++) { t4[k] = 4 * lane + k < m ? sh_lean[4 * lane + k] : 0; sum += t4[k]; }
+                int ex = warp_inclusive_scan(sum, lane) - sum;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (4 * lane + k < m) sh_lean[4 * lane + k] = ex;
+                    ex += t4[k];
                 }
-            };
-            if (span <= nthr) lean_pass(std::integral_constant<int, 1>{});
-            else if (span <= 2 * nthr) lean_pass(std::integral_constant<int, 2>{});
-            else lean_pass(std::integral_constant<int, kLean>{});
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int r = 0; r < nr; r++) {
+                const int i = amin + r * nthr + tid;
+                if (i <= amax) {
+                    const long long pk = b.flags[i];
+                    const int fl = (int)(pk >> 32);
+                    const int pre_i = sh_lean[r * nw + wrp] + (int)(pk & 0xffffffffLL);
+                    const int pa_ = pre_i & 0xffff, pb_ = pre_i >> 16;
+                    b.pre[i] = (long long)pa_ | ((long long)pb_ << 32);
+                    if (fl & 1) b.tmp_a[amin + pa_] = i;
+                    if (fl >> 16) b.tmp_b[amin + pb_] = i;
+                }
+            }
         } else {
         // ---- flags + chunk sums
         {
