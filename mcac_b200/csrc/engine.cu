@@ -105,6 +105,7 @@ struct mcac_gpu {
     int event_smem_cap = 0;   // shared-memory staging of the block-local sort levels (entries; 0 = levels stay in HBM/L2)
     size_t event_dyn_bytes = 0;  // dynamic shared memory of the event kernel's launches
     long long *event_work = nullptr;
+    long long *commit_prof = nullptr;  // MCAC_B200_K9_DEBUG: phase clocks of k_commit
     long long event_work_seen[32] = {0};
     // tie-dominated pick tables (tie_sort.cuh): plan + per-level rank tables; allocated with the state when the table can be large
     tiesort::Plan *ts_plan = nullptr;
@@ -1181,6 +1182,10 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         cudaFuncSetAttribute(k_step_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoopDynSmem);
         cudaFuncSetAttribute(k_ensemble_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoopDynSmem);
         cudaGetLastError();
+        if (getenv("MCAC_B200_K9_DEBUG")) {
+            TRY(dev_alloc_persistent(h, &h->commit_prof, 16));
+            CK(cudaMemset(h->commit_prof, 0, 16 * sizeof(long long)));
+        }
         TRY(dev_alloc_persistent(h, &h->event_work, 32));
         CK(cudaMemset(h->event_work, 0, 32 * sizeof(long long)));
         TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
@@ -1768,6 +1773,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                 ba.rec = nullptr; ba.rec_cap = 0; ba.rec_base = 0;
                 ba.max_steps = max_steps;
                 ba.steps_limit_abs = steps_limit_abs;
+                ba.prof = h->commit_prof;
                 prof_begin(h, 1);
                 k_commit<<<1, kCommitThreads, 0, h->stream>>>(h->d, ba);
                 prof_end(h);
@@ -1874,6 +1880,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         ba.rec_base = steps;
         ba.max_steps = max_steps - steps;
         ba.steps_limit_abs = 0;
+        ba.prof = h->commit_prof;
         prof_begin(h, 1);
         k_commit<<<1, kCommitThreads, 0, h->stream>>>(h->d, ba);
         prof_end(h);
@@ -1964,6 +1971,14 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         for (int k = 0; k < 3; k++) {
             report->tie_sim_cycles[k] = w[16 + k] - h->event_work_seen[16 + k];
             report->tie_phase_cycles[0] += report->tie_sim_cycles[k];
+        }
+        if (h->commit_prof) {
+            long long c[16];
+            cudaMemcpy(c, h->commit_prof, sizeof(c), cudaMemcpyDeviceToHost);
+            cudaMemset(h->commit_prof, 0, sizeof(c));
+            const double nl = std::max(1.0, (double)c[15]);
+            fprintf(stderr, "k_commit cycles per launch (%lld launches): stage %.0f, stop conditions %.0f, conflicts %.0f, free-flight moves %.0f, contact move %.0f, merge + update %.0f, tail %.0f\n",
+                    c[15], c[0] / nl, c[1] / nl, c[2] / nl, c[3] / nl, c[4] / nl, c[5] / nl, c[6] / nl);
         }
         if (getenv("MCAC_B200_K9_DEBUG") && w[21] > h->event_work_seen[21]) {
             const double nw = (double)(w[21] - h->event_work_seen[21]), ns = std::max(1.0, (double)(w[12] - h->event_work_seen[12]));

@@ -1382,6 +1382,7 @@ struct BatchArgs {
     long long rec_cap, rec_base;
     long long max_steps;    // steps still allowed in this run call
     long long steps_limit_abs;  // > 0: Scalars::steps_done may not pass this (batches submitted before the previous one was read back)
+    long long *prof;            // diagnostics (may be null): [k] += SM cycles of thread 0 in phase k of k_commit, [15] += launches
 };
 __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs b) {
     __shared__ int sh_slot[kMaxBatch];
@@ -1400,6 +1401,8 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
     const int n_agg_before = sc.n_agg;
     const long long steps_before = sc.steps_done, rand_before = sc.rand_pos, iter_before = sc.n_iter_without_event;
     const double dt_base = sc.max_time_step / sc.cum_total;  // AggregatList::get_time_step(max), aggregat_list.cpp:54-58
+    long long t_prev = clock64();
+    auto plap = [&](int k) { if (b.prof && tid == 0) { const long long t = clock64(); atomicAdd(reinterpret_cast<unsigned long long *>(b.prof + k), (unsigned long long)(t - t_prev)); t_prev = t; } };
     if (sc.b_need == 99 || sc.error != 0) {  // the pick table of this batch comes from a sort that gave up (host redoes it), or an
         // earlier kernel of the batch reported an error (its queries are not usable: q_slot may be -1): commit nothing
         if (tid == 0) { sc.b_committed = 0; sc.b_stop_reason = STOP_NONE; sc.b_contact = 0; sc.b_merged = 0; }
@@ -1428,23 +1431,30 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         sh_dir[3 * j] = b.q_dir[3 * j]; sh_dir[3 * j + 1] = b.q_dir[3 * j + 1]; sh_dir[3 * j + 2] = b.q_dir[3 * j + 2];
     }
     __syncthreads();
+    plap(0);
     // ---- stop conditions evaluated at the top of every step (PhysicalModel::finished, physical_model.cpp:288-337)
-    if (tid == 0) {
-        double t = sc.time;
-        int lim = nq;
-        if ((long long)lim > max_steps) lim = (int)(max_steps > 0 ? max_steps : 0);
-        for (int j = 0; j < nq; j++) {
-            sh_time[j] = t;
-            const bool fin = (d.time_limit > 0 && t >= d.time_limit) || (d.n_iter_limit > 0 && iter_before + j >= d.n_iter_limit);
-            if (fin && j < lim) { lim = j; s_finished = 1; }
-            t = t + dt_base;  // free flight: dt * (lpm/lpm + 0) == dt
-        }
-        sh_time[nq] = t;
-        s_limit = lim;
-    }
     for (int j = tid; j < nq; j += nth)
         if (sh_contact[j]) atomicMin(&s_contact, j);
     __syncthreads();
+    if (tid == 0) {  // (a chain of dependent additions: only as far as the first contact, behind which nothing is committed)
+        double t = sc.time;
+        int lim = nq;
+        if ((long long)lim > max_steps) lim = (int)(max_steps > 0 ? max_steps : 0);
+        const int upto = min(nq, s_contact + 1);
+        const bool limits = d.time_limit > 0 || d.n_iter_limit > 0;
+        for (int j = 0; j < upto; j++) {
+            sh_time[j] = t;
+            if (limits) {
+                const bool fin = (d.time_limit > 0 && t >= d.time_limit) || (d.n_iter_limit > 0 && iter_before + j >= d.n_iter_limit);
+                if (fin && j < lim) { lim = j; s_finished = 1; }
+            }
+            t = t + dt_base;  // free flight: dt * (lpm/lpm + 0) == dt
+        }
+        sh_time[upto] = t;
+        s_limit = lim;
+    }
+    __syncthreads();
+    plap(1);
     // ---- conflicts with earlier movers of the batch: all (j, i<j) pairs up to the first contact (nothing behind it can be
     // committed by this batch), flattened over the block
     const int nj = min(min(min(nq, s_limit), s_contact + 1), s_bad);
@@ -1473,6 +1483,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         if (conflict) atomicMin(&s_conf, j);
     }
     __syncthreads();
+    plap(2);
     int stop = s_limit;
     int reason = s_finished ? STOP_FINISHED : STOP_BATCH_END;
     if (s_bad < stop) {
@@ -1522,6 +1533,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         if (lane == 0) d.a_ptime[sj] += dt_base * (dj / dj + 0.0);  // calcul.cpp:147-149 with move == full, n_try == 1
     }
     __syncthreads();
+    plap(3);
     int merged = 0;
     if (do_contact) {
         const int j = stop;
@@ -1537,7 +1549,9 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
             cap[0] = dt; cap[1] = d.a_ptime[sj]; cap[2] = a.x; cap[3] = a.y; cap[4] = a.z;
         }
         __syncthreads();
+        plap(4);
         merged = agg_merge(d, r.moving_slot, r.other_slot, sj, r.other_agg, scratch, box);
+        plap(5);
     } else if (tid == 0) {
         sc.time = sh_time[stop];
     }
@@ -1605,6 +1619,8 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         sc.b_contact = do_contact ? 1 : 0;
         sc.b_merged = merged;
     }
+    plap(6);
+    if (b.prof && tid == 0) atomicAdd(reinterpret_cast<unsigned long long *>(b.prof + 15), 1ULL);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3644,6 +3660,11 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             }
             return inc;
         };
+        // tie-dominated table: behind the handed-over segment every entry is W, and the warp scan of 32 equal values is the same
+        // vector in every such warp — computed once, not 2 x 16 times per chunk (the scans are shuffle-throughput-bound)
+        const double inc_w = warp_inc(ts_W);
+        const int dense_from = ts_on ? delta + n_sort : n;
+        auto all_w = [&](int i) { const int w0 = i - lane; return w0 >= dense_from && w0 + 31 < n; };  // (warp-uniform)
         double base_run = 0.;  // (thread 0) sum of the chunks before the next one of this CTA, in chunk order
         int base_upto = 0;
         for (int c = blk; c < n_chunks; c += nblk) {
@@ -3664,7 +3685,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             const int nr = (hi - lo + nthr - 1) / nthr;
             for (int r = 0; r < nr; r++) {
                 const int i = lo + r * nthr + tid;
-                const double inc = warp_inc((i < hi) ? fw(i) : 0.);
+                const double inc = all_w(i) ? inc_w : warp_inc((i < hi) ? fw(i) : 0.);
                 if (lane == 31) s_wtot[r][w] = inc;
             }
             __syncthreads();
@@ -3685,7 +3706,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             __syncthreads();
             for (int r = 0; r < nr; r++) {
                 const int i = lo + r * nthr + tid;
-                const double inc = warp_inc((i < hi) ? fw(i) : 0.);
+                const double inc = all_w(i) ? inc_w : warp_inc((i < hi) ? fw(i) : 0.);
                 if (i < hi) d.cum[i] = s_carry[r] + s_wbase[r][w] + inc;
             }
             __syncthreads();
