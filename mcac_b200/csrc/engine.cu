@@ -106,6 +106,7 @@ struct mcac_gpu {
     size_t event_dyn_bytes = 0;  // dynamic shared memory of the event kernel's launches
     long long *event_work = nullptr;
     long long *commit_prof = nullptr;  // MCAC_B200_K9_DEBUG: phase clocks of k_commit
+    double loop_cost_per_step = 0.;    // SM cycles per MC step of this realization's last step-loop launch (ensemble queue order)
     long long event_work_seen[32] = {0};
     // tie-dominated pick tables (tie_sort.cuh): plan + per-level rank tables; allocated with the state when the table can be large
     tiesort::Plan *ts_plan = nullptr;
@@ -2388,6 +2389,16 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
             const auto t_launch = std::chrono::steady_clock::now();
             // ---- one launch for the whole round
             const int nr = (int)run.size();
+            // queue order: longest expected first (cycles per MC step of the realization's last launch x the steps it still has to
+            // do), so that the CTAs that finish early are not left waiting for a long realization taken last
+            {
+                auto cost = [&](int i) {
+                    const mcac_gpu *h = handles[loop_set[(size_t)i]];
+                    const double per_step = h->loop_cost_per_step > 0. ? h->loop_cost_per_step : (double)h->sc_host.n_sph;
+                    return per_step * (double)(max_steps - tr[(size_t)i].steps);
+                };
+                std::stable_sort(run.begin(), run.end(), [&](int x, int y) { return cost(x) > cost(y); });
+            }
             for (int j = 0; j < nr; j++) {
                 mcac_gpu *h = handles[loop_set[(size_t)run[(size_t)j]]];
                 ds_host[(size_t)j] = h->d;
@@ -2428,6 +2439,11 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 h->sc_host = sc_all_host[(size_t)j];
                 const LoopState ls = ls_all_host[(size_t)j];
                 *h->loop_host = ls;
+                if (ls.steps > 0) {
+                    long long cyc = 0;
+                    for (int q = 0; q < 8; q++) cyc += ls.phase_cycles[q];
+                    h->loop_cost_per_step = (double)cyc / (double)ls.steps;
+                }
                 loop_apply(h, ls);
                 t.steps += ls.steps; t.sorts += ls.sorts; t.nucleated += ls.nucleated; t.dups += ls.dups;
                 if (ls.exit_reason == LOOP_ERROR || h->sc_host.error) { rcs[(size_t)k] = device_error(h, h->sc_host, "mcac_ensemble_run"); continue; }
