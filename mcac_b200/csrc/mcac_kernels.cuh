@@ -867,6 +867,7 @@ __device__ __forceinline__ void agg_store_position(const DevState &d, int slot, 
     d.a_cy[slot] = cell_of(ny, d.n_div, box);
     d.a_cz[slot] = cell_of(nz, d.n_div, box);
 }
+constexpr int kDirtyFull = 1, kDirtyPartial = 2, kDirtyAll = 3;  // DevState::a_dirty (see agg_update)
 template <bool kBlock>
 __device__ __forceinline__ void group_sync() {
     if (kBlock) __syncthreads(); else __syncwarp();
@@ -886,7 +887,10 @@ __device__ __forceinline__ void agg_translate(const DevState &d, int slot, doubl
         d.s_posr[off + i] = p;
     }
     group_sync<kBlock>();
-    if (tid == 0) agg_store_position(d, slot, a.x + vx, a.y + vy, a.z + vz, box);
+    if (tid == 0) {
+        agg_store_position(d, slot, a.x + vx, a.y + vy, a.z + vz, box);
+        atomicOr(&d.a_dirty[slot], kDirtyPartial);  // (result unused: no round trip)
+    }
     group_sync<kBlock>();
 }
 
@@ -910,8 +914,15 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
     // Aggregate::update() of an aggregate whose spheres did not change since its last full update recomputes, from the same relative
     // positions and radii, exactly the contact graph, overlap statistics, effective volumes / surfaces and V, S that are stored: the
     // O(n^2) pass is skipped (individual surface reactions grow one aggregate per step; the reference's loop updates all of them)
-    if (full && d.a_dirty[slot] == 0) full = false;
-    group_sync<kBlock>();  // everybody has read the flag before the full pass clears it
+    // The same holds for update_partial(): an aggregate that has neither changed nor MOVED since its last update gets, from the same
+    // inputs, exactly the centre, radii, friction and time step it already has (the first update after a move is kept: it re-derives
+    // the aggregate position from the root sphere, which can differ from the translated one in the last bit).  With individual
+    // surface reactions one aggregate per step changes, and the loop over all of them costs one flag read each.
+    // a_dirty: kDirtyFull = spheres changed (contact pass due), kDirtyPartial = update_partial due.
+    const int flags = d.a_dirty[slot];
+    group_sync<kBlock>();  // everybody has read the flags before they are rewritten
+    if (full && !(flags & kDirtyFull)) full = false;
+    if (!full && !(flags & kDirtyPartial)) return;
     if (full) {
         // ---- contact pass (update_distances_and_overlapping + the contact-graph loops of compute_volume_surface)
         double vals[7] = {0., 0., 0., 0., 0., 0., 0.};  // intersections, sum c_ij, c_s10, c_v20, c_v30, vp_sum, sp_sum
@@ -1022,7 +1033,6 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
             d.a_cn[slot] = cn;
             d.a_vol[slot] = V;
             d.a_surf[slot] = S;
-            d.a_dirty[slot] = 0;
             if (V <= 0 || S <= 0) d.sc->error = 8;  // VolSurfError, aggregat.cpp:427-429
         }
         group_sync<kBlock>();
@@ -1150,6 +1160,7 @@ __device__ void agg_update(const DevState &d, int slot, bool full, int tid, int 
         d.a_lpm[slot] = mob.lpm;
         d.a_dgdp[slot] = 2 * rg / dp;
         if (d.sc->maxradius < rmax) atomic_max_positive_double(&d.sc->maxradius, rmax);  // only ever grows: the plain read filters almost all
+        d.a_dirty[slot] = full ? 0 : (flags & kDirtyFull);  // (a partial update leaves a due contact pass due)
     }
     group_sync<kBlock>();
 }
@@ -1163,6 +1174,9 @@ constexpr int kUpdateWarpMax = 96;  // spheres of an aggregate up to which ONE W
 __device__ void agg_update_single(const DevState &d, int slot, bool full, double box) {
     const int off = d.a_off[slot], n = d.a_n[slot];
     const int method = d.volsurf_method;
+    const int flags = d.a_dirty[slot];  // (see agg_update)
+    if (full && !(flags & kDirtyFull)) full = false;
+    if (!full && !(flags & kDirtyPartial)) return;
     if (full) {
         double v[7][kSingleMax];
 #pragma unroll
@@ -1240,7 +1254,6 @@ __device__ void agg_update_single(const DevState &d, int slot, bool full, double
         d.a_cn[slot] = cn;
         d.a_vol[slot] = V;
         d.a_surf[slot] = S;
-        d.a_dirty[slot] = 0;
         if (V <= 0 || S <= 0) d.sc->error = 8;  // VolSurfError, aggregat.cpp:427-429
     }
     // ---- update_partial
@@ -1289,6 +1302,7 @@ __device__ void agg_update_single(const DevState &d, int slot, bool full, double
     d.a_lpm[slot] = mob.lpm;
     d.a_dgdp[slot] = 2 * rg / dp;
     if (d.sc->maxradius < rmax) atomic_max_positive_double(&d.sc->maxradius, rmax);
+    d.a_dirty[slot] = full ? 0 : (flags & kDirtyFull);
 }
 
 // K4 — AggregatList::merge + Aggregate::merge + ListStorage::merge/remove (aggregat_list.cpp:367-410,
@@ -1344,7 +1358,7 @@ __device__ int agg_merge(const DevState &d, int ms, int os, int moving_agg, int 
         d.a_alpha[kept] = 1.0 / static_cast<double>(n_k + n_r);
         d.a_alive[removed] = 0;
         d.a_n[removed] = 0;
-        d.a_dirty[kept] = 1;
+        d.a_dirty[kept] = kDirtyAll;
         d.sc->n_agg -= 1;
     }
     __syncthreads();
@@ -1523,6 +1537,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit(DevState d, BatchArgs
         p.x = refx + rel.x; p.y = refy + rel.y; p.z = refz + rel.z;
         d.s_posr[off] = p;
         agg_store_position(d, sj, a.x + vx, a.y + vy, a.z + vz, box);
+        atomicOr(&d.a_dirty[sj], kDirtyPartial);
         d.a_ptime[sj] += dt_base * (dj / dj + 0.0);
     }
     for (int j = warp; j < stop; j += nwarps) {
@@ -1872,7 +1887,7 @@ __device__ __forceinline__ void dev_nucleate(const DevState &d, double deltatemp
             d.a_off[slot] = sp;
             d.a_alpha[slot] = 1.0;
             d.a_alive[slot] = 1;
-            d.a_dirty[slot] = 1;
+            d.a_dirty[slot] = kDirtyAll;
             d.a_charge[slot] = 0;
             d.a_ptime[slot] = sc.time;
             d.a_ch[slot] = 0.;
@@ -2091,8 +2106,8 @@ __global__ void k_grow(DevState d, double dt, int only_slot) {
     if (only_slot >= 0) { lo = d.a_off[only_slot]; hi = lo + d.a_n[only_slot]; }
     const int t = lo + s;
     // radii change: the aggregates concerned need their next full update in full (there are never more aggregate slots than spheres)
-    if (only_slot >= 0) { if (s == 0) d.a_dirty[only_slot] = 1; }
-    else if (s < d.sc->n_agg_slots) d.a_dirty[s] = 1;
+    if (only_slot >= 0) { if (s == 0) d.a_dirty[only_slot] = kDirtyAll; }
+    else if (s < d.sc->n_agg_slots) d.a_dirty[s] = kDirtyAll;
     if (t >= hi) return;
     double4 p = d.s_posr[t];
     const double new_r = p.w + d.u_sg * dt;  // PhysicalModel::grow, physical_model.cpp:587-590
@@ -2115,8 +2130,8 @@ __global__ void k_grow_pending(DevState d, int individual) {
     double dt = sc.p_dt;
     if (individual) { lo = d.a_off[sc.p_slot]; hi = lo + d.a_n[sc.p_slot]; dt = sc.p_dt_indiv; }
     const int t = lo + s;
-    if (individual) { if (s == 0) d.a_dirty[sc.p_slot] = 1; }
-    else if (s < sc.n_agg_slots) d.a_dirty[s] = 1;
+    if (individual) { if (s == 0) d.a_dirty[sc.p_slot] = kDirtyAll; }
+    else if (s < sc.n_agg_slots) d.a_dirty[s] = kDirtyAll;
     if (t >= hi) return;
     double4 p = d.s_posr[t];
     const double new_r = p.w + d.u_sg * dt;
@@ -2141,7 +2156,7 @@ __global__ void __launch_bounds__(256) k_update_step(DevState d, int full, int i
     if (slot >= sc.n_agg_slots || !d.a_alive[slot]) return;
     if (individual && !sc.b_merged) return;  // done by k_update_picked
     if (d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
-    if (full && d.a_n[slot] > kUpdateWarpMax && d.a_dirty[slot]) return;  // an O(n^2) pass of a big aggregate: done by k_update_big
+    if (full && d.a_n[slot] > kUpdateWarpMax && (d.a_dirty[slot] & kDirtyFull)) return;  // an O(n^2) pass of a big aggregate: done by k_update_big
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], sc.box_length);
 }
 // ... and the big ones (n > kUpdateWarpMax) by a whole CTA each: a full update is O(n^2), a 10^3-sphere aggregate left to one warp would
@@ -2154,7 +2169,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_update_big(DevState d, int f
     if (individual && !sc.b_merged) return;
     if (!full) return;  // partial updates are chains of ordered adds: one warp each (k_update_step / k_update_all)
     for (int slot = blockIdx.x; slot < sc.n_agg_slots; slot += gridDim.x) {
-        if (!d.a_alive[slot] || d.a_n[slot] <= kUpdateWarpMax || !d.a_dirty[slot]) continue;
+        if (!d.a_alive[slot] || d.a_n[slot] <= kUpdateWarpMax || !(d.a_dirty[slot] & kDirtyFull)) continue;
         agg_update<true>(d, slot, true, threadIdx.x, blockDim.x, scratch, sc.box_length);
     }
 }
@@ -2186,7 +2201,7 @@ __global__ void __launch_bounds__(256) k_update_all(DevState d, int full, int on
     if (only_slot >= 0) { if (slot != 0) return; slot = only_slot; }
     if (slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
     if (only_slot < 0 && d.a_n[slot] <= kSingleMax) return;  // done by k_update_small
-    if (only_slot < 0 && full && d.a_n[slot] > kUpdateWarpMax && d.a_dirty[slot]) return;  // done by k_update_big
+    if (only_slot < 0 && full && d.a_n[slot] > kUpdateWarpMax && (d.a_dirty[slot] & kDirtyFull)) return;  // done by k_update_big
     agg_update<false>(d, slot, full != 0, lane, 32, scratch[w], d.sc->box_length);
 }
 // Aggregate::update() / update_partial() of ONE aggregate (per-call C ABI), by the group every other path gives an aggregate of its size
@@ -2195,7 +2210,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_update_one(DevState d, int f
     if (slot < 0 || slot >= d.sc->n_agg_slots || !d.a_alive[slot]) return;
     const int n = d.a_n[slot];
     if (n <= kSingleMax) { if (threadIdx.x == 0) agg_update_single(d, slot, full != 0, d.sc->box_length); }
-    else if (n <= kUpdateWarpMax || !full || !d.a_dirty[slot]) { if (threadIdx.x < 32) agg_update<false>(d, slot, full != 0, threadIdx.x, 32, scratch, d.sc->box_length); }
+    else if (n <= kUpdateWarpMax || !full || !(d.a_dirty[slot] & kDirtyFull)) { if (threadIdx.x < 32) agg_update<false>(d, slot, full != 0, threadIdx.x, 32, scratch, d.sc->box_length); }
     else agg_update<true>(d, slot, full != 0, threadIdx.x, blockDim.x, scratch, d.sc->box_length);
 }
 // the 21 AggregatesFields of one aggregate slot (per-call C ABI)
@@ -3919,7 +3934,7 @@ __global__ void __launch_bounds__(256) k_upload_aggregates(DevState d, HostLayou
     d.a_cx[a] = (int)s.agg_cells[a]; d.a_cy[a] = (int)s.agg_cells[m + a]; d.a_cz[a] = (int)s.agg_cells[2 * m + a];
     d.a_charge[a] = (int)s.agg_charge[a];
     d.a_alive[a] = 1;
-    d.a_dirty[a] = 1;
+    d.a_dirty[a] = kDirtyAll;
     d.label_of_slot[a] = (int)a;
     d.slot_of_label[a] = (int)a;
 }

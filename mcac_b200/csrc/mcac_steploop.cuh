@@ -583,8 +583,8 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
             int lo = 0, hi = sc.pool_top;
             double dt = sc.p_dt;
             if (a.individual) { lo = d.a_off[sc.p_slot]; hi = lo + d.a_n[sc.p_slot]; dt = sc.p_dt_indiv; }
-            if (a.individual) { if (tid == 0) d.a_dirty[sc.p_slot] = 1; }
-            else for (int s2 = tid; s2 < sc.n_agg_slots; s2 += nth) d.a_dirty[s2] = 1;
+            if (a.individual) { if (tid == 0) d.a_dirty[sc.p_slot] = kDirtyAll; }
+            else for (int s2 = tid; s2 < sc.n_agg_slots; s2 += nth) d.a_dirty[s2] = kDirtyAll;
             for (int t = lo + tid; t < hi; t += nth) {
                 double4 p = d.s_posr[t];
                 const double new_r = p.w + d.u_sg * dt;
@@ -621,12 +621,12 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
                 // (only an O(n^2) pass needs the whole CTA: a big aggregate that is clean, or a partial update, is a chain of ordered adds —
                 // sixteen of those run side by side on sixteen warps)
                 for (int s = warp; s < n_slots; s += nwarps)
-                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && !(full && d.a_n[s] > kUpdateWarpMax && d.a_dirty[s]))
+                    if (d.a_alive[s] && d.a_n[s] > kSingleMax && !(full && d.a_n[s] > kUpdateWarpMax && (d.a_dirty[s] & kDirtyFull)))
                         agg_update<false>(d, s, full, lane, 32, upd_scratch[warp], sc.box_length, upd_stage + warp * (5 * 32));
                 __syncthreads();
                 if (full)
                     for (int s = 0; s < n_slots; s++)
-                        if (d.a_alive[s] && d.a_n[s] > kUpdateWarpMax && d.a_dirty[s])
+                        if (d.a_alive[s] && d.a_n[s] > kUpdateWarpMax && (d.a_dirty[s] & kDirtyFull))
                             agg_update<true>(d, s, full, tid, nth, picked_scratch, sc.box_length, upd_stage);
             }
             __syncthreads();
