@@ -195,7 +195,9 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
 /* Times one kernel of the path on the resident state (CUDA events on the handle's stream, `reps` launches after one warm-up):
  * which = 0 K2 cell rebuild, 1 K8 growth (all spheres), 2 update_partial (all aggregates), 3 full update, 4 K9 event pipeline with
  * sort, 5 without sort, 6 100 grid barriers at K9's launch shape, 7 K10 RNG fill, 8 K11 statistics, 9 / 10 FP64 pipe peak with DFMA /
- * with DMUL + DADD (the library is built --fmad=false): units = flops per launch.  units = items per launch otherwise. */
+ * with DMUL + DADD (the library is built --fmad=false): units = flops per launch; 11 tuning probe: the one-CTA sparse simulation of K9's
+ * tie-dominated sort alone, on a synthetic table of the resident size (MCAC_B200_PROBE_X sparse elements).  units = items per launch
+ * otherwise. */
 int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_per_launch, int64_t *units);
 /* on != 0: mcac_gpu_run returns right after the step that made an event (merge or nucleation: `event` of calcul.cpp:222), so that a
  * host loop can do what calcul() does between events (advancement.dat rows, the progress table, output files) */

@@ -2085,7 +2085,8 @@ int mcac_gpu_search_sweep(mcac_gpu *h, int64_t n, int32_t repeats, mcac_sweep_re
 // Per-kernel timings on the resident state (bench.py's per-kernel roofline table; profiles/).  `which`:
 //  0 K2 cell list rebuild, 1 K8 growth of every sphere (dt = 0), 2 K6/K7 update_partial of every aggregate, 3 K5-K7 full update,
 //  4 K9 event pipeline with sort, 5 event pipeline without sort (labels + refresh + totals), 6 100 grid barriers at K9's launch shape,
-//  7 K10 RNG fill (kRngBuf draws), 8 K11 morphology statistics, 9 / 10 FP64 pipe peak (DFMA / DMUL+DADD; units = flops).
+//  7 K10 RNG fill (kRngBuf draws), 8 K11 morphology statistics, 9 / 10 FP64 pipe peak (DFMA / DMUL+DADD; units = flops),
+//  11 the sparse simulation of the tie-dominated sort alone (tuning probe).
 // Growth / update rewrite derived fields from the resident radii (a replayed trajectory should not continue from this state).
 int mcac_gpu_kernel_bench(mcac_gpu *h, int32_t which, int32_t reps, double *ms_out, int64_t *units_out) {
     CK(cudaSetDevice(h->device));
