@@ -486,7 +486,7 @@ __device__ void step_loop(DevState &d, LoopArgs &a) {
     // terms of the ordered sums (agg_update's `stage`): 5 x 512 doubles for the CTA-wide update, 5 x 32 per warp otherwise — dynamic
     // shared memory (kLoopDynSmem bytes), the static part of this kernel is already at 31 KB
     double *upd_stage = reinterpret_cast<double *>(dyn_smem);
-    __shared__ int s_exit, s_draws, s_ntry, s_draws_at_search, s_again;
+    __shared__ int s_draws, s_ntry, s_draws_at_search, s_again;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
     Scalars &sc = *d.sc;
     LoopState &out = *a.out;

@@ -260,6 +260,9 @@ def test_tie_dominated_sort_fast_path_is_std_sort(n, frac, classes, local, monke
     np.testing.assert_array_equal(keys[idx], np.sort(keys))
     if n <= 65536:
         np.testing.assert_array_equal(cum, np.cumsum(keys[ref]))
+    else:  # the library's own fixed summation tree (relative chunks + the head's total): the sequential sum to rounding
+        np.testing.assert_allclose(cum, np.cumsum(keys[ref]), rtol=1e-11, atol=0)
+        assert np.all(np.diff(cum) > 0)
     rep, _ = sim.run(0)
     assert rep["tie_sorts"] >= 1 and rep["tie_sparse"] >= int(sparse.sum())
 
