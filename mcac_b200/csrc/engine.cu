@@ -2452,6 +2452,27 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 if (ls.exit_reason == LOOP_STEPS_DONE && ls.steps == 0 && t.steps < max_steps) { h->err = "step loop made no progress"; rcs[(size_t)k] = E_UNKNOWN; }
             }
             apply_ms += since(t_apply);
+            if (getenv("MCAC_B200_K9_DEBUG")) {  // the round's three most expensive realizations (the queue takes them first)
+                std::vector<std::pair<long long, int>> cost;
+                for (int j = 0; j < nr; j++) {
+                    long long cyc = 0;
+                    for (int q = 0; q < 8; q++) cyc += ls_all_host[(size_t)j].phase_cycles[q];
+                    cost.push_back({cyc, j});
+                }
+                std::sort(cost.begin(), cost.end());
+                long long total = 0;
+                for (auto &c : cost) total += c.first;
+                fprintf(stderr, "ensemble round: %d realizations, mean %.0f cycles, median %lld, max %lld\n", nr, (double)total / nr, cost[(size_t)nr / 2].first,
+                        cost.back().first);
+                for (int t = 0; t < std::min(3, nr); t++) {
+                    const int j = cost[(size_t)(nr - 1 - t)].second;
+                    const LoopState &ls = ls_all_host[(size_t)j];
+                    const Scalars &sc = sc_all_host[(size_t)j];
+                    fprintf(stderr, "  #%d: handle %d steps %lld n_sph %d n_agg %d events %lld | cycles: pick %lld search %lld update %lld nucl+refresh %lld top %lld move %lld growth %lld merge %lld\n",
+                            t, loop_set[(size_t)run[(size_t)j]], ls.steps, (int)sc.n_sph, (int)sc.n_agg, ls.events, ls.phase_cycles[0], ls.phase_cycles[1], ls.phase_cycles[2],
+                            ls.phase_cycles[3], ls.phase_cycles[4], ls.phase_cycles[5], ls.phase_cycles[6], ls.phase_cycles[7]);
+                }
+            }
         }
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
