@@ -2285,10 +2285,26 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
         std::vector<Scalars> sc_all_host((size_t)m);
         std::vector<LoopState> ls_all_host((size_t)m);
         int rc_all = E_OK;
-        if (cudaStreamCreateWithFlags(&es, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void **)&ds_dev, sizeof(DevState) * (size_t)m) != cudaSuccess ||
-            cudaMalloc((void **)&as_dev, sizeof(LoopArgs) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&next_dev, sizeof(int)) != cudaSuccess ||
-            cudaMalloc((void **)&sc_all_dev, sizeof(Scalars) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&ls_all_dev, sizeof(LoopState) * (size_t)m) != cudaSuccess)
+        // scratch of the call (argument arrays, queue counter, read-back arrays, stream, events): kept per device between calls and only
+        // ever grown — cudaMalloc / cudaFree / stream creation per call are device-wide synchronising driver calls whose cost was seen
+        // to reach 200 ms per call on some boxes with 1024 realizations resident
+        struct EnsScratch { int cap = 0; cudaStream_t es = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr; DevState *ds = nullptr; LoopArgs *as = nullptr;
+                            int *next = nullptr; Scalars *sc = nullptr; LoopState *ls = nullptr; };
+        static EnsScratch scratch_of[64];
+        static std::mutex scratch_mu;
+        std::unique_lock<std::mutex> scratch_lock(scratch_mu);  // (one ensemble call at a time per process: they share the scratch)
+        EnsScratch &S = scratch_of[handles[loop_set[0]]->device & 63];
+        if (!S.es && (cudaStreamCreateWithFlags(&S.es, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&S.ev_a) != cudaSuccess ||
+                      cudaEventCreate(&S.ev_b) != cudaSuccess || cudaMalloc((void **)&S.next, sizeof(int)) != cudaSuccess))
             rc_all = E_UNKNOWN;
+        if (rc_all == E_OK && S.cap < m) {
+            if (S.ds) { cudaFree(S.ds); cudaFree(S.as); cudaFree(S.sc); cudaFree(S.ls); S.ds = nullptr; S.as = nullptr; S.sc = nullptr; S.ls = nullptr; S.cap = 0; }
+            if (cudaMalloc((void **)&S.ds, sizeof(DevState) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&S.as, sizeof(LoopArgs) * (size_t)m) != cudaSuccess ||
+                cudaMalloc((void **)&S.sc, sizeof(Scalars) * (size_t)m) != cudaSuccess || cudaMalloc((void **)&S.ls, sizeof(LoopState) * (size_t)m) != cudaSuccess)
+                rc_all = E_UNKNOWN;
+            else S.cap = m;
+        }
+        es = S.es; ds_dev = S.ds; as_dev = S.as; next_dev = S.next; sc_all_dev = S.sc; ls_all_dev = S.ls;
         if (rc_all == E_OK) {  // current Scalars of every realization: one gather + one copy (every handle's stream is idle between calls)
             std::vector<Scalars *> ptrs((size_t)m);
             for (int i = 0; i < m; i++) ptrs[(size_t)i] = handles[loop_set[(size_t)i]]->d.sc;
@@ -2310,11 +2326,10 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 tr[(size_t)i].launches0 = h->launches;
             }
         }
+        const double prologue_ms = since(t_call);
         int occ = 1, n_sm = handles[loop_set[0]]->n_sm;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_loop, kLoopThreads, kLoopDynSmem);
-        cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-        cudaEventCreate(&ev_a);
-        cudaEventCreate(&ev_b);
+        cudaEvent_t ev_a = S.ev_a, ev_b = S.ev_b;
         double kernel_ms = 0.;
         long long rounds = 0;
         while (rc_all == E_OK) {
@@ -2474,14 +2489,10 @@ int mcac_ensemble_run(mcac_gpu **handles, int32_t n, int64_t max_steps, int32_t 
                 }
             }
         }
-        if (ev_a) cudaEventDestroy(ev_a);
-        if (ev_b) cudaEventDestroy(ev_b);
-        if (es) cudaStreamDestroy(es);
-        if (ds_dev) cudaFree(ds_dev);
-        if (as_dev) cudaFree(as_dev);
-        if (next_dev) cudaFree(next_dev);
-        if (sc_all_dev) cudaFree(sc_all_dev);
-        if (ls_all_dev) cudaFree(ls_all_dev);
+        if (getenv("MCAC_B200_K9_DEBUG"))
+            fprintf(stderr, "ensemble call: prologue %.2f ms, services %.2f, launch+wait %.2f, bookkeeping %.2f, so far %.2f ms, %lld rounds\n", prologue_ms, service_ms,
+                    launch_ms, apply_ms, since(t_call), rounds);
+        scratch_lock.unlock();
         for (int i = 0; i < m; i++) {
             const int k = loop_set[(size_t)i];
             if (rc_all != E_OK && rcs[(size_t)k] == E_OK) rcs[(size_t)k] = rc_all;
