@@ -115,6 +115,7 @@ struct mcac_gpu {
     int ts_min_n = 32768;     // MCAC_B200_TIE_MIN_N (0 disables the fast path)
     int ts_max_sparse = tiesort::kMaxSparse;  // MCAC_B200_TIE_MAX_SPARSE
     bool ts_no_overlap = false;               // MCAC_B200_TIE_NO_OVERLAP
+    bool no_exact_cum = false;                // MCAC_B200_NO_EXACT_CUM: big tie-dominated tables summed by the fixed tree (tuning: the cost of the exact table)
     long long *part_ll = nullptr;
     double *part_d = nullptr;
     int cum_sequential_max = 65536;  // below this size cumulative_time_steps is summed sequentially (the reference's rounding)
@@ -473,6 +474,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.ts_min_n = h->ts_min_n;
     a.skip_if_no_event = skip_if_no_event ? 1 : 0;
     a.ts_no_overlap = h->ts_no_overlap ? 1 : 0;
+    a.no_exact_cum = h->no_exact_cum ? 1 : 0;
     a.depth_override = h->sort_depth_override;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
@@ -1143,6 +1145,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_TIE_MIN_N")) h->ts_min_n = std::max(0, atoi(e));
         if (const char *e = getenv("MCAC_B200_TIE_MAX_SPARSE")) h->ts_max_sparse = std::max(1, atoi(e));
         if (getenv("MCAC_B200_TIE_NO_OVERLAP")) h->ts_no_overlap = true;
+        if (getenv("MCAC_B200_NO_EXACT_CUM")) h->no_exact_cum = true;
         // block-local sort levels staged in shared memory: (local_span + 2) entries of 48 B, if the SM has room for them
         h->event_smem_cap = 0;
         if (!getenv("MCAC_B200_NO_SORT_SMEM")) {
@@ -1980,6 +1983,11 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
             const double nl = std::max(1.0, (double)c[15]);
             fprintf(stderr, "k_commit cycles per launch (%lld launches): stage %.0f, stop conditions %.0f, conflicts %.0f, free-flight moves %.0f, contact move %.0f, merge + update %.0f, tail %.0f\n",
                     c[15], c[0] / nl, c[1] / nl, c[2] / nl, c[3] / nl, c[4] / nl, c[5] / nl, c[6] / nl);
+        }
+        if (getenv("MCAC_B200_K9_DEBUG") && w[29] > h->event_work_seen[29]) {
+            const double nc = (double)(w[29] - h->event_work_seen[29]);
+            fprintf(stderr, "k9 exact cumulative tables: %.0f, %.0f cycles of the building CTA and %.1f segments of the W run per table\n", nc,
+                    (w[28] - h->event_work_seen[28]) / nc, (w[30] - h->event_work_seen[30]) / nc);
         }
         if (getenv("MCAC_B200_K9_DEBUG") && w[21] > h->event_work_seen[21]) {
             const double nw = (double)(w[21] - h->event_work_seen[21]), ns = std::max(1.0, (double)(w[12] - h->event_work_seen[12]));

@@ -10,6 +10,7 @@
 #include "mcac_device.cuh"
 #include "tie_sort.cuh"
 #include "heap_sort.cuh"
+#include "seq_cumsum.cuh"
 
 namespace mcacb {
 
@@ -2595,6 +2596,9 @@ constexpr int kEventThreads = 512;
 // layout of the scratch arrays: part_ll (4096 entries) = [0, gridDim) per-block counts / chunk sums of the level scans, [kPartSparseCounts, +gridDim)
 // sparse elements staged per block; part_d (16384) = five per-block partials of gridDim entries each, [kPartCumChunks, +8192) chunk sums of the cumulative table
 constexpr int kPartSparseCounts = 2048, kPartCumChunks = 8192;
+// exact cumulative table of a tie-dominated pick table (seq_cumsum.cuh): part_ll[kPartCumSegN] = segments of the W run (-1: none, the
+// summation tree is used), part_d[kPartCumSegs, + 3 * kMaxSegs) = the segments
+constexpr int kPartCumSegN = 4000, kPartCumSegs = 6144;
 constexpr int kMaxWin = 512, kWinMin = 256, kWinBase = 16;  // SortBufs::active holds kWinBase + 4 * kMaxWin entries
 struct EventArgs {
     SortBufs sb;
@@ -2622,6 +2626,7 @@ struct EventArgs {
     int smem_bytes;       // dynamic shared memory of the launch
     int skip_if_no_event; // return at once when Scalars::event == 0 (nothing changed since the last pick table)
     int ts_no_overlap;    // test / tuning hook: all CTAs route, then the general sort starts (no overlap with the block-local levels)
+    int no_exact_cum;     // tuning hook (MCAC_B200_NO_EXACT_CUM): cumulative table of a big tie-dominated table by the summation tree, as before
 };
 struct BlockTeam {  // tiesort's Team for one CTA
     int tid, nthr;
@@ -2742,7 +2747,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     const long long gtid = (long long)blk * nthr + tid, gsize = (long long)nblk * nthr;
     Scalars &sc = *d.sc;
     if (a.skip_if_no_event && sc.event == 0) return;  // submitted ahead of the read-back of a batch that turned out not to merge
-    if (gtid == 0 && a.ts_plan) { a.ts_plan->ready = 0; a.ts_plan->done = 0; }  // (two grid barriers before anybody looks at them)
+    if (gtid == 0 && a.ts_plan) { a.ts_plan->ready = 0; a.ts_plan->done = 0; a.ts_plan->cum_gathered = 0; }  // (two grid barriers before anybody looks at them)
     const int n_slots = sc.n_agg_slots;
     // phase clocks of block 0 (SM cycles) accumulated into a.work[2 + k]: diagnostics for the K9 breakdown in profiles/
     long long t_prev = clock64();
@@ -2935,6 +2940,13 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     int n_sort = n, delta = 0;  // the general sort below works on [0, n_sort) and writes its result at +delta
     // ---- tie-dominated table: the top levels on the sparse elements only (tie_sort.cuh)
     bool ts_on = false, ts_ovl = false;
+    // exact_cum: the cumulative table of a big tie-dominated table is the reference's sequential sum, bit for bit (seq_cumsum.cuh).  Only
+    // the sorted VALUES matter for it, and those are known without the introsort replay: the sparse (lighter) weights in ascending
+    // order, then W over and over.  The LAST CTA sorts the sparse weights on its own (bitonic, shared memory), adds them up one after
+    // the other, and walks the binades of the W run — beside the sparse simulation and the sort levels, off the critical path; behind
+    // the sort every thread of the grid evaluates its entries of the W run in closed form.
+    bool exact_cum = false;
+    int cum_xs = 0, cum_P = 1;
     if (ts_try) {
         long long x = 0;
         for (int bb = tid; bb < nblk; bb += nthr) x += a.part_ll[kPartSparseCounts + bb];
@@ -2949,6 +2961,10 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 a.smem_bytes >= 4 * nthr * (int)sizeof(int);  // (the routing pass parks >= 4 positions per thread in shared memory)
         if (ts_on) {
             const int xs = (int)x;
+            cum_xs = xs;
+            while (cum_P < xs) cum_P <<= 1;
+            exact_cum = n > a.cum_sequential_max && !a.no_exact_cum && nblk > 1 &&
+                        cum_P * (int)sizeof(double) + seqsum::kMaxSegs * (int)sizeof(seqsum::Seg) + (nblk + 2) * (int)sizeof(int) + 64 <= a.smem_bytes;
             int *st_pos = b.tmp_b;                                 // compact staged labels / weights of the sparse elements
             double *st_w = reinterpret_cast<double *>(b.flags);
             // (the sparse elements' weights first, when there is room: the pivot samples of every level read them)
@@ -3040,8 +3056,171 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
             bool any_bad = false;
             constexpr int kRoute = 4;
-            const bool router = nblk > 1 ? blk != 0 : true;  // (a one-CTA launch routes after its own simulation)
-            const long long rtid = nblk > 1 ? gtid - nthr : gtid, rsize = nblk > 1 ? gsize - nthr : gsize;
+            // (the CTA that builds the exact cumulative table does not route when there are CTAs enough; in a grid of two or three it
+            // routes first)
+            const bool cum_builder = exact_cum && blk == nblk - 1, cum_dedicated = exact_cum && nblk >= 4;
+            const bool router = nblk > 1 ? (blk != 0 && !(cum_builder && cum_dedicated)) : true;  // (a one-CTA launch routes after its own simulation)
+            const long long rtid = nblk > 1 ? gtid - nthr : gtid, rsize = nblk > 1 ? gsize - (cum_dedicated ? 2 : 1) * nthr : gsize;
+            auto cum_exact_build = [&]() {
+                const long long t_cb = clock64();
+                // dynamic shared memory: [cum_P] sparse weights, then their running sums | segments of the W run | first sparse element of
+                // every chunk | and, when there is room, the scratch of the parallel head (seq_cumsum.cuh): K, exact sums at the irregular
+                // steps, approximate sums behind the threads' chunks, the irregular steps' indexes / binades, the elements' stretch
+                double *s_v = reinterpret_cast<double *>(dyn_smem);
+                seqsum::Seg *s_seg = reinterpret_cast<seqsum::Seg *>(s_v + cum_P);
+                int *s_cb = reinterpret_cast<int *>(s_seg + seqsum::kMaxSegs);
+                long long *s_K = reinterpret_cast<long long *>(s_cb + ((nblk + 2 + 1) & ~1));
+                double *s_base = reinterpret_cast<double *>(s_K + cum_P);
+                double *s_endp = s_base + seqsum::kMaxIrr;
+                int *s_iidx = reinterpret_cast<int *>(s_endp + nthr);
+                int *s_ie = s_iidx + seqsum::kMaxIrr;
+                unsigned short *s_c = reinterpret_cast<unsigned short *>(s_ie + seqsum::kMaxIrr);
+                const bool head_parallel = reinterpret_cast<unsigned char *>(s_c + cum_P) - dyn_smem <= a.smem_bytes && xs >= 64;
+                __shared__ int cb_ws[32];
+                __shared__ int cb_ns;
+                __syncthreads();
+                for (int b0 = 0; b0 < nblk; b0 += nthr) {  // exclusive scan of the per-chunk counts
+                    const int bb = b0 + tid;
+                    const int c = bb < nblk ? (int)a.part_ll[kPartSparseCounts + bb] : 0;
+                    int tot;
+                    const int pre = block_exclusive_scan(c, &tot, cb_ws);
+                    const int carry = b0 == 0 ? 0 : s_cb[b0];
+                    if (bb < nblk) s_cb[bb] = carry + pre;
+                    if (tid == 0) s_cb[min(b0 + nthr, nblk)] = carry + tot;
+                    __syncthreads();
+                }
+                const double *chunk_w = reinterpret_cast<const double *>(b.pre);
+                for (int id0 = tid; id0 < cum_P; id0 += 4 * nthr) {  // the per-chunk stages into one list (four loads in flight), +inf behind it
+                    double wv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int id = id0 + u * nthr;
+                        int lo = 0, hi = nblk;
+                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_cb[mid] <= id) lo = mid; else hi = mid; }
+                        wv[u] = id < xs ? chunk_w[lo * chunk_s + (id - s_cb[lo])] : __longlong_as_double(0x7ff0000000000000LL);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int id = id0 + u * nthr;
+                        if (id < cum_P) s_v[id] = wv[u];
+                    }
+                }
+                __syncthreads();
+                // (the stages lie in scratch of the sort levels: the simulating CTA waits for this word before it starts its own levels)
+                if (tid == 0) *reinterpret_cast<volatile int *>(&a.ts_plan->cum_gathered) = 1;
+                // bitonic sort, ascending (any correct sort gives the reference's sequence of values).  The steps whose partner is less
+                // than a tile (512 entries) away stay inside one warp's tile: warp barriers only
+                auto cmp_swap = [&](int t, int j, int k) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const double va = s_v[i], vb = s_v[l];
+                    if ((va > vb) == ((i & k) == 0)) { s_v[i] = vb; s_v[l] = va; }
+                };
+                const int tile = min(cum_P, 512), lane_ = tid & 31, warp_ = tid >> 5, nwarp_ = nthr >> 5;
+                auto tile_steps = [&](int k, int j_from) {  // steps j_from, j_from / 2, .., 1 of stage k, every tile by one warp
+                    for (int tl = warp_; tl < cum_P / tile; tl += nwarp_)
+                        for (int j = j_from; j > 0; j >>= 1) {
+                            for (int t = tl * (tile >> 1) + lane_; t < (tl + 1) * (tile >> 1); t += 32) cmp_swap(t, j, k);
+                            __syncwarp();
+                        }
+                };
+                for (int k = 2; k <= tile; k <<= 1) tile_steps(k, k >> 1);
+                __syncthreads();
+                for (int k = 2 * tile; k <= cum_P; k <<= 1) {
+                    for (int j = k >> 1; j >= tile; j >>= 1) {
+                        for (int t = tid; t < (cum_P >> 1); t += nthr) cmp_swap(t, j, k);
+                        __syncthreads();
+                    }
+                    tile_steps(k, tile >> 1);
+                    __syncthreads();
+                }
+                __shared__ int cb_head_ok;
+                if (head_parallel) {
+                    // the head's sequential sums as integer prefix sums between the irregular steps (seq_cumsum.cuh): a thread owns E
+                    // consecutive elements
+                    const int E = max(1, cum_P / nthr), lo = min(xs, tid * E), hi = min(xs, lo + E);
+                    __shared__ double cb_wd[32];
+                    __shared__ long long cb_wt[32];
+                    __shared__ int cb_wf[32], cb_wn[32];
+                    const double ls = seqsum::head_chunk_sum(s_v, lo, hi, 0.);
+                    double inc = ls;  // approximate sum before the chunk: warp scan + the warps before this one
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(kFull, inc, o); if (lane_ >= o) inc += t; }
+                    if (lane_ == 31) cb_wd[warp_] = inc;
+                    __syncthreads();
+                    double pex = inc - ls;
+                    for (int w = 0; w < warp_; w++) pex += cb_wd[w];
+                    s_endp[tid] = seqsum::head_chunk_sum(s_v, lo, hi, pex);
+                    __syncthreads();
+                    const seqsum::ChunkAgg g = seqsum::head_chunk_classify(s_v, lo, hi, pex, tid > 0 ? s_endp[tid - 1] : 0., s_K, s_c);
+                    // exclusive scan of the chunk aggregates (agg_combine) over the threads
+                    int f = g.has_irr, ni = g.n_irr;
+                    long long tl = g.tail;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int f2 = __shfl_up_sync(kFull, f, o), n2 = __shfl_up_sync(kFull, ni, o);
+                        const long long t2 = __shfl_up_sync(kFull, tl, o);
+                        if (lane_ >= o) { if (!f) tl += t2; f |= f2; ni += n2; }
+                    }
+                    if (lane_ == 31) { cb_wf[warp_] = f; cb_wt[warp_] = tl; cb_wn[warp_] = ni; }
+                    __syncthreads();
+                    int pf = 0, pn = 0;  // everything before this warp
+                    long long pt = 0;
+                    for (int w = 0; w < warp_; w++) { pt = cb_wf[w] ? cb_wt[w] : pt + cb_wt[w]; pf |= cb_wf[w]; pn += cb_wn[w]; }
+                    // ... followed by the lanes before this one (inclusive value of lane - 1)
+                    const int f1 = __shfl_up_sync(kFull, f, 1), n1 = __shfl_up_sync(kFull, ni, 1);
+                    const long long t1 = __shfl_up_sync(kFull, tl, 1);
+                    long long carry_in = pt;
+                    int irr_before = pn;
+                    if (lane_ > 0) { carry_in = f1 ? t1 : pt + t1; irr_before = pn + n1; }
+                    int M = 0;
+                    for (int w = 0; w < nwarp_; w++) M += cb_wn[w];
+                    seqsum::head_chunk_finish(s_v, lo, hi, pex, carry_in, irr_before, s_K, s_c, s_iidx, s_ie);
+                    __syncthreads();
+                    if (tid == 0) cb_head_ok = seqsum::head_stitch(s_v, s_K, s_iidx, s_ie, M, xs, s_base) ? 1 : 0;
+                    __syncthreads();
+                    if (cb_head_ok)  // (nothing reads the weights any more: the sums go in their place)
+                        for (int i = lo; i < hi; i++) s_v[i] = seqsum::head_value(i, s_K, s_c, s_iidx, s_ie, s_base);
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    double acc = 0.;  // (0 + w == w: the reference starts with cum[0] = w[0])
+                    if (head_parallel && cb_head_ok) acc = xs > 0 ? s_v[xs - 1] : 0.;
+                    else {  // one addition after the other
+                        int i = 0;
+                        for (; i + 8 <= xs; i += 8) {  // (the loads do not wait for the chain of additions)
+                            double w8[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) w8[u] = s_v[i + u];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { acc = acc + w8[u]; s_v[i + u] = acc; }
+                        }
+                        for (; i < xs; i++) { acc = acc + s_v[i]; s_v[i] = acc; }
+                    }
+                    int ns = 0;
+                    seqsum::run_segments(acc, xs, n - xs, ts_W, s_seg, ns, seqsum::kMaxSegs);
+                    cb_ns = ns <= seqsum::kMaxSegs ? ns : -1;
+                    if (a.work && head_parallel) work_add(31, cb_head_ok ? 1 : 0);
+                }
+                __syncthreads();
+                const int ns = cb_ns;
+                for (int i = tid; i < xs; i += nthr) d.cum[i] = s_v[i];
+                long long *seg_g = reinterpret_cast<long long *>(a.part_d + kPartCumSegs);
+                for (int k = tid; k < 3 * max(ns, 0); k += nthr) seg_g[k] = reinterpret_cast<const long long *>(s_seg)[k];
+                if (tid == 0) {
+                    a.part_ll[kPartCumSegN] = ns;
+                    if (a.work) { work_add(28, clock64() - t_cb); work_add(29, 1); work_add(30, max(ns, 0)); }
+                }
+                __syncthreads();
+            };
+            if (cum_builder && cum_dedicated) {
+                cum_exact_build();
+                if (tid == 0) {  // the plan this CTA goes on with must be the final one
+                    const volatile int *vd = &a.ts_plan->done;
+                    while (*vd == 0) __nanosleep(200);
+                    __threadfence();
+                }
+                __syncthreads();
+            }
             int *s_pos = reinterpret_cast<int *>(dyn_smem);  // [e][tid]; free in the routing CTAs (and in a lone CTA after plan_build)
             const int e_cap = min(64, max(kRoute, (a.smem_bytes / (int)sizeof(int) / nthr) & ~(kRoute - 1)));  // (64: the `live` mask)
             const int e_all = (int)((n + rsize - 1) / rsize);
@@ -3139,6 +3318,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 }
                 __syncthreads();  // s_pos is reused by the next round
             }
+            if (cum_builder && !cum_dedicated) cum_exact_build();
             if (!router || e_all == 0) {  // the simulating CTA (and routers without elements): the final plan
                 __syncthreads();
                 for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)
@@ -3249,8 +3429,13 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     int st_min = 0, st_max = 0;
     SortBufs gb = b;
     if (!ts_ovl) grid.sync();  // first pivot + span in place
-    else if (blk == 0) __syncthreads();
-    else active = false;       // overlap mode: the other CTAs are done with their part (routing) and wait behind the loop
+    else if (blk == 0) {
+        if (exact_cum && tid == 0) {  // the staged sparse weights share the level passes' scratch: not before their last reader is done
+            const volatile int *vg = &a.ts_plan->cum_gathered;
+            while (*vg == 0) __nanosleep(100);
+        }
+        __syncthreads();
+    } else active = false;       // overlap mode: the other CTAs are done with their part (routing) and wait behind the loop
     lap(2);
     while (active) {
         depth--;
@@ -3629,7 +3814,7 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
     }
     // overlap mode: the chunk sums do not wait for the barrier — every chunk but the first is W only, and the first one (it holds the
     // handed-over segment: hand_l <= 4096 < chunk) belongs to block 0, which has just finished it
-    const bool cum_early = leaves_by_block0 && delta + n_sort <= chunk_c;
+    const bool cum_early = !exact_cum && leaves_by_block0 && delta + n_sort <= chunk_c;
     if (cum_early) cum_chunk_sums();
     if (a.work && tid == 0 && windowed && act == sh_act) { work_add(19, clock64() - t_win); work_add(20, level - level_win); work_add(21, 1); }
     const long long t_wait = clock64();
@@ -3654,6 +3839,20 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             double acc = fw(0);
             d.cum[0] = acc;
             for (int i = 1; i < n; i++) { acc = acc + fw(i); d.cum[i] = acc; }
+        }
+    } else if (exact_cum && (int)__ldcg(a.part_ll + kPartCumSegN) >= 0) {
+        // the sparse head is in place (written by the last CTA, which also left the segments of the W run): every entry of the run in
+        // closed form, the reference's sequential sum bit for bit (seq_cumsum.cuh)
+        const int ns = (int)__ldcg(a.part_ll + kPartCumSegN);
+        long long *s_seg = reinterpret_cast<long long *>(dyn_smem);
+        const long long *seg_g = reinterpret_cast<const long long *>(a.part_d + kPartCumSegs);
+        __syncthreads();
+        for (int k = tid; k < 3 * ns; k += nthr) s_seg[k] = __ldcg(seg_g + k);
+        __syncthreads();
+        const seqsum::Seg *segs = reinterpret_cast<const seqsum::Seg *>(dyn_smem);
+        for (long long i = cum_xs + gtid; i < n; i += gsize) {
+            const int sg = seqsum::find_segment(segs, ns, (int)i);
+            d.cum[i] = seqsum::segment_value(segs[sg], (int)i);
         }
     } else {
         // Fixed tree, independent of the launch shape: chunks of kCumRounds * blockDim entries (CTA b takes chunks b, b + gridDim, ...),

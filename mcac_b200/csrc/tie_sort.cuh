@@ -53,6 +53,7 @@ struct Plan {
     int nb;                           // buckets of a rank table (power of two >= x, 256 .. kBuckets)
     int ready;                        // levels published so far (tables + lv[] visible device-wide): the routing pass follows it level by level
     int done;                         // set by the caller after the last level and the fields above are final
+    int cum_gathered;                 // caller's: the CTA that builds the exact cumulative table has read the staged sparse weights
     double W;
     Level lv[kMaxLevels];
 };

@@ -35,3 +35,14 @@ def test_enclosing_ball_pruning_never_drops_a_finite_pair(tmp_path):
         out = subprocess.run([str(exe), "20000", str(seed)], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
         assert out.stdout.startswith("ok 20000 cases"), out.stdout
+
+
+def test_seq_cumsum_header_is_the_sequential_sum(tmp_path):
+    """mcac_b200/csrc/seq_cumsum.cuh (cumulative_time_steps over a run of equal weights in closed form, aggregat_list.cpp:131-140)
+    against the plain loop cum[i] = cum[i-1] + w, every entry bit for bit, incl. round-to-even ties and binade crossings."""
+    exe = tmp_path / "seq_cumsum_host"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", str(exe), str(ROOT / "tests" / "native" / "seq_cumsum_host.cpp")])
+    for seed in (1, 9):
+        out = subprocess.run([str(exe), "600", str(seed)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.startswith("ok 600 cases"), out.stdout
