@@ -107,7 +107,7 @@ struct mcac_gpu {
     long long *event_work = nullptr;
     long long *commit_prof = nullptr;  // MCAC_B200_K9_DEBUG: phase clocks of k_commit
     double loop_cost_per_step = 0.;    // SM cycles per MC step of this realization's last step-loop launch (ensemble queue order)
-    long long event_work_seen[32] = {0};
+    long long event_work_seen[40] = {0};
     // tie-dominated pick tables (tie_sort.cuh): plan + per-level rank tables; allocated with the state when the table can be large
     tiesort::Plan *ts_plan = nullptr;
     int *ts_R = nullptr, *ts_tbl = nullptr;
@@ -115,6 +115,7 @@ struct mcac_gpu {
     int ts_min_n = 32768;     // MCAC_B200_TIE_MIN_N (0 disables the fast path)
     int ts_max_sparse = tiesort::kMaxSparse;  // MCAC_B200_TIE_MAX_SPARSE
     bool ts_no_overlap = false;               // MCAC_B200_TIE_NO_OVERLAP
+    int exact_cum_max_sparse = 8192;          // MCAC_B200_EXACT_CUM_MAX_SPARSE: most lighter aggregates the exact cumulative table is built for
     bool no_exact_cum = false;                // MCAC_B200_NO_EXACT_CUM: big tie-dominated tables summed by the fixed tree (tuning: the cost of the exact table)
     long long *part_ll = nullptr;
     double *part_d = nullptr;
@@ -475,6 +476,7 @@ int event_pipeline(mcac_gpu *h, bool do_refresh, bool do_totals, bool do_sort, c
     a.skip_if_no_event = skip_if_no_event ? 1 : 0;
     a.ts_no_overlap = h->ts_no_overlap ? 1 : 0;
     a.no_exact_cum = h->no_exact_cum ? 1 : 0;
+    a.exact_cum_max_sparse = h->exact_cum_max_sparse;
     a.depth_override = h->sort_depth_override;
     a.force_fail = (do_sort && h->force_sort_fail > 0 && (++h->sort_calls % h->force_sort_fail) == 0) ? 1 : 0;
     DevState dcopy = h->d;
@@ -1146,6 +1148,7 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
         if (const char *e = getenv("MCAC_B200_TIE_MAX_SPARSE")) h->ts_max_sparse = std::max(1, atoi(e));
         if (getenv("MCAC_B200_TIE_NO_OVERLAP")) h->ts_no_overlap = true;
         if (getenv("MCAC_B200_NO_EXACT_CUM")) h->no_exact_cum = true;
+        if (const char *e = getenv("MCAC_B200_EXACT_CUM_MAX_SPARSE")) h->exact_cum_max_sparse = std::max(0, atoi(e));
         // block-local sort levels staged in shared memory: (local_span + 2) entries of 48 B, if the SM has room for them
         h->event_smem_cap = 0;
         if (!getenv("MCAC_B200_NO_SORT_SMEM")) {
@@ -1190,8 +1193,8 @@ int mcac_gpu_create(const mcac_params *params, int device, mcac_gpu **out) {
             TRY(dev_alloc_persistent(h, &h->commit_prof, 16));
             CK(cudaMemset(h->commit_prof, 0, 16 * sizeof(long long)));
         }
-        TRY(dev_alloc_persistent(h, &h->event_work, 32));
-        CK(cudaMemset(h->event_work, 0, 32 * sizeof(long long)));
+        TRY(dev_alloc_persistent(h, &h->event_work, 40));
+        CK(cudaMemset(h->event_work, 0, 40 * sizeof(long long)));
         TRY(dev_alloc_persistent(h, &h->part_ll, 4096));
         TRY(dev_alloc_persistent(h, &h->part_d, 4 * 4096));
     }
@@ -1962,7 +1965,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         report->nucleated = nucleated_total;
         report->total_volume = sc.total_volume;
         report->total_surface = sc.total_surface;
-        long long w[32] = {0};
+        long long w[40] = {0};
         cudaMemcpy(w, h->event_work, sizeof(w), cudaMemcpyDeviceToHost);
         report->sort_span_elements = w[0] - h->event_work_seen[0];
         report->sort_levels = w[1] - h->event_work_seen[1];
@@ -1986,8 +1989,11 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
         }
         if (getenv("MCAC_B200_K9_DEBUG") && w[29] > h->event_work_seen[29]) {
             const double nc = (double)(w[29] - h->event_work_seen[29]);
-            fprintf(stderr, "k9 exact cumulative tables: %.0f, %.0f cycles of the building CTA and %.1f segments of the W run per table\n", nc,
-                    (w[28] - h->event_work_seen[28]) / nc, (w[30] - h->event_work_seen[30]) / nc);
+            fprintf(stderr, "k9 exact cumulative tables: %.0f, %.0f cycles of the building CTA and %.1f segments of the W run per table; head by integer prefix sums in %.0f\n", nc,
+                    (w[28] - h->event_work_seen[28]) / nc, (w[30] - h->event_work_seen[30]) / nc, (double)(w[31] - h->event_work_seen[31]));
+            fprintf(stderr, "k9 building CTA cycles per table: gather %.0f, sort %.0f (redone by the one-step network: %.0f tables), head %.0f, W run + write-out %.0f\n",
+                    (w[32] - h->event_work_seen[32]) / nc, (w[33] - h->event_work_seen[33]) / nc, (double)(w[36] - h->event_work_seen[36]),
+                    (w[34] - h->event_work_seen[34]) / nc, (w[35] - h->event_work_seen[35]) / nc);
         }
         if (getenv("MCAC_B200_K9_DEBUG") && w[21] > h->event_work_seen[21]) {
             const double nw = (double)(w[21] - h->event_work_seen[21]), ns = std::max(1.0, (double)(w[12] - h->event_work_seen[12]));
@@ -1997,7 +2003,7 @@ int mcac_gpu_run(mcac_gpu *h, int64_t max_steps, int32_t batch, mcac_step_record
                     (w[23] - h->event_work_seen[23]) / nw, (w[24] - h->event_work_seen[24]) / nw, (w[25] - h->event_work_seen[25]) / nw,
                     (w[26] - h->event_work_seen[26]) / nw, (w[27] - h->event_work_seen[27]) / nw);
         }
-        for (int k = 0; k < 32; k++) h->event_work_seen[k] = w[k];
+        for (int k = 0; k < 40; k++) h->event_work_seen[k] = w[k];
         report->sort_fallbacks = h->sort_fallbacks - h->sort_fallbacks_seen;
         report->sort_heap_branches = h->sort_heap_levels - h->sort_heap_seen;
         h->sort_fallbacks_seen = h->sort_fallbacks;

@@ -2626,6 +2626,7 @@ struct EventArgs {
     int smem_bytes;       // dynamic shared memory of the launch
     int skip_if_no_event; // return at once when Scalars::event == 0 (nothing changed since the last pick table)
     int ts_no_overlap;    // test / tuning hook: all CTAs route, then the general sort starts (no overlap with the block-local levels)
+    int exact_cum_max_sparse;  // most sparse elements the exact cumulative table is built for (above: the summation tree)
     int no_exact_cum;     // tuning hook (MCAC_B200_NO_EXACT_CUM): cumulative table of a big tie-dominated table by the summation tree, as before
 };
 struct BlockTeam {  // tiesort's Team for one CTA
@@ -2735,6 +2736,35 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long *sm) {
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sm[w];
     __syncthreads();
     return t;
+}
+
+// One pass of a bitonic sorting network over v[0, P) (P a power of two), stage k: the G steps whose partners are 2^(b+G-1) .. 2^b apart.
+// The 2^G entries base | (m << b) are closed under those steps: a thread takes them through all G steps in registers — one load and
+// one store per entry and pass instead of one per step (the network is bound by shared-memory bandwidth).  Barrier between passes.
+template <int G>
+__device__ __forceinline__ void bitonic_pass(const seqsum::Padded<double> &v, int P, int k, int b, int tid, int nthr) {
+    constexpr int NG = 1 << G;
+    for (int q = tid; q < (P >> G); q += nthr) {
+        const int base = ((q >> b) << (b + G)) | (q & ((1 << b) - 1));
+        const bool asc = (base & k) == 0;  // (k lies above every bit the group varies)
+        double r[NG];
+#pragma unroll
+        for (int m = 0; m < NG; m++) r[m] = v[base | (m << b)];
+#pragma unroll
+        for (int st = G - 1; st >= 0; st--) {
+#pragma unroll
+            for (int m = 0; m < NG; m++) {
+                if ((m & (1 << st)) == 0) {
+                    const double x = r[m], y = r[m | (1 << st)];
+                    const bool sw = (x > y) == asc;
+                    r[m] = sw ? y : x;
+                    r[m | (1 << st)] = sw ? x : y;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NG; m++) v[base | (m << b)] = r[m];
+    }
 }
 
 template <int kMinBlocks>
@@ -2962,9 +2992,14 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
         if (ts_on) {
             const int xs = (int)x;
             cum_xs = xs;
+            cum_P = 64;
             while (cum_P < xs) cum_P <<= 1;
-            exact_cum = n > a.cum_sequential_max && !a.no_exact_cum && nblk > 1 &&
-                        cum_P * (int)sizeof(double) + seqsum::kMaxSegs * (int)sizeof(seqsum::Seg) + (nblk + 2) * (int)sizeof(int) + 64 <= a.smem_bytes;
+            {   // shared memory of the building CTA (laid out in cum_exact_build)
+                const int pp = seqsum::padded_size(cum_P);
+                const int need = pp * (int)(sizeof(double) + sizeof(long long) + sizeof(unsigned short)) + seqsum::kMaxSegs * (int)sizeof(seqsum::Seg) +
+                                 (nblk + 4) * (int)sizeof(int) + seqsum::kMaxIrr * (int)(sizeof(double) + 2 * sizeof(int)) + nthr * (int)sizeof(double) + 64;
+                exact_cum = n > a.cum_sequential_max && !a.no_exact_cum && nblk >= 4 && xs <= a.exact_cum_max_sparse && need <= a.smem_bytes;
+            }
             int *st_pos = b.tmp_b;                                 // compact staged labels / weights of the sparse elements
             double *st_w = reinterpret_cast<double *>(b.flags);
             // (the sparse elements' weights first, when there is room: the pivot samples of every level read them)
@@ -3056,26 +3091,30 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
             const unsigned char *__restrict__ is_sparse = reinterpret_cast<const unsigned char *>(b.cut);
             bool any_bad = false;
             constexpr int kRoute = 4;
-            // (the CTA that builds the exact cumulative table does not route when there are CTAs enough; in a grid of two or three it
-            // routes first)
-            const bool cum_builder = exact_cum && blk == nblk - 1, cum_dedicated = exact_cum && nblk >= 4;
+            // (the CTA that builds the exact cumulative table does not route: exact_cum asks for a grid of four CTAs at least)
+            const bool cum_builder = exact_cum && blk == nblk - 1, cum_dedicated = exact_cum;
             const bool router = nblk > 1 ? (blk != 0 && !(cum_builder && cum_dedicated)) : true;  // (a one-CTA launch routes after its own simulation)
             const long long rtid = nblk > 1 ? gtid - nthr : gtid, rsize = nblk > 1 ? gsize - (cum_dedicated ? 2 : 1) * nthr : gsize;
             auto cum_exact_build = [&]() {
                 const long long t_cb = clock64();
-                // dynamic shared memory: [cum_P] sparse weights, then their running sums | segments of the W run | first sparse element of
-                // every chunk | and, when there is room, the scratch of the parallel head (seq_cumsum.cuh): K, exact sums at the irregular
-                // steps, approximate sums behind the threads' chunks, the irregular steps' indexes / binades, the elements' stretch
+                // dynamic shared memory: sparse weights in ascending order, then their running sums (padded view: the threads of a warp walk
+                // chunks of consecutive entries) | segments of the W run | first sparse element of every chunk | K of the parallel head
+                // (seq_cumsum.cuh; first the plain array the weights are sorted in) | exact sums at the irregular steps | approximate sums
+                // behind the threads' chunks | the irregular steps' indexes / binades | the entries' stretch
+                const int pp = seqsum::padded_size(cum_P);
                 double *s_v = reinterpret_cast<double *>(dyn_smem);
-                seqsum::Seg *s_seg = reinterpret_cast<seqsum::Seg *>(s_v + cum_P);
+                seqsum::Seg *s_seg = reinterpret_cast<seqsum::Seg *>(s_v + pp);
                 int *s_cb = reinterpret_cast<int *>(s_seg + seqsum::kMaxSegs);
                 long long *s_K = reinterpret_cast<long long *>(s_cb + ((nblk + 2 + 1) & ~1));
-                double *s_base = reinterpret_cast<double *>(s_K + cum_P);
+                double *s_base = reinterpret_cast<double *>(s_K + pp);
                 double *s_endp = s_base + seqsum::kMaxIrr;
                 int *s_iidx = reinterpret_cast<int *>(s_endp + nthr);
                 int *s_ie = s_iidx + seqsum::kMaxIrr;
                 unsigned short *s_c = reinterpret_cast<unsigned short *>(s_ie + seqsum::kMaxIrr);
-                const bool head_parallel = reinterpret_cast<unsigned char *>(s_c + cum_P) - dyn_smem <= a.smem_bytes && xs >= 64;
+                double *s_sort = reinterpret_cast<double *>(s_K);  // (K is not needed before the sort is over)
+                const seqsum::Padded<double> v_p{s_v};
+                const seqsum::Padded<long long> K_p{s_K};
+                const seqsum::Padded<unsigned short> c_p{s_c};
                 __shared__ int cb_ws[32];
                 __shared__ int cb_ns;
                 __syncthreads();
@@ -3102,46 +3141,98 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int id = id0 + u * nthr;
-                        if (id < cum_P) s_v[id] = wv[u];
+                        if (id < cum_P) s_sort[id] = wv[u];
                     }
                 }
                 __syncthreads();
+                const int lane_ = tid & 31, warp_ = tid >> 5, nwarp_ = nthr >> 5;
+                long long t_cl = t_cb;
+                auto cb_lap = [&](int k) { if (a.work && tid == 0) { const long long t = clock64(); work_add(k, t - t_cl); t_cl = t; } };
+                cb_lap(32);
                 // (the stages lie in scratch of the sort levels: the simulating CTA waits for this word before it starts its own levels)
                 if (tid == 0) *reinterpret_cast<volatile int *>(&a.ts_plan->cum_gathered) = 1;
-                // bitonic sort, ascending (any correct sort gives the reference's sequence of values).  The steps whose partner is less
-                // than a tile (512 entries) away stay inside one warp's tile: warp barriers only
-                auto cmp_swap = [&](int t, int j, int k) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                    const double va = s_v[i], vb = s_v[l];
-                    if ((va > vb) == ((i & k) == 0)) { s_v[i] = vb; s_v[l] = va; }
+                // Ascending sort (any correct sort gives the reference's sequence of values): a bitonic network in the padded array, three
+                // steps per pass in registers (bitonic_pass).  Its result is checked — sorted, and the same multiset (two sums over the bit
+                // patterns) — and a result that fails is redone from the plain copy by the one-step-at-a-time network below.
+                auto pattern_sums = [&](auto &&at, long long &hi_sum, long long &lo_sum, long long &unsorted) {
+                    long long h_ = 0, l_ = 0, u_ = 0;
+                    for (int i = tid; i < cum_P; i += nthr) {
+                        const double x = at(i);
+                        const long long bits = __double_as_longlong(x);
+                        h_ += bits >> 20;
+                        l_ += bits & 0xfffff;
+                        if (i + 1 < cum_P && x > at(i + 1)) u_++;
+                    }
+                    hi_sum = block_sum_ll(h_, sm_ll);
+                    lo_sum = block_sum_ll(l_, sm_ll);
+                    unsorted = block_sum_ll(u_, sm_ll);
                 };
-                const int tile = min(cum_P, 512), lane_ = tid & 31, warp_ = tid >> 5, nwarp_ = nthr >> 5;
-                auto tile_steps = [&](int k, int j_from) {  // steps j_from, j_from / 2, .., 1 of stage k, every tile by one warp
-                    for (int tl = warp_; tl < cum_P / tile; tl += nwarp_)
-                        for (int j = j_from; j > 0; j >>= 1) {
-                            for (int t = tl * (tile >> 1) + lane_; t < (tl + 1) * (tile >> 1); t += 32) cmp_swap(t, j, k);
-                            __syncwarp();
-                        }
-                };
-                for (int k = 2; k <= tile; k <<= 1) tile_steps(k, k >> 1);
+                long long in_hi, in_lo, in_uns;
+                pattern_sums([&](int i) { return s_sort[i]; }, in_hi, in_lo, in_uns);
+                for (int i = tid; i < cum_P; i += nthr) v_p[i] = s_sort[i];
                 __syncthreads();
-                for (int k = 2 * tile; k <= cum_P; k <<= 1) {
-                    for (int j = k >> 1; j >= tile; j >>= 1) {
-                        for (int t = tid; t < (cum_P >> 1); t += nthr) cmp_swap(t, j, k);
+                for (int k = 2, lg = 1; k <= cum_P; k <<= 1, lg++)
+                    for (int top = lg - 1; top >= 0;) {
+                        const int g = min(3, top + 1), bb = top - g + 1;
+                        if (g == 3) bitonic_pass<3>(v_p, cum_P, k, bb, tid, nthr);
+                        else if (g == 2) bitonic_pass<2>(v_p, cum_P, k, bb, tid, nthr);
+                        else bitonic_pass<1>(v_p, cum_P, k, bb, tid, nthr);
+                        __syncthreads();
+                        top -= g;
+                    }
+                long long out_hi, out_lo, out_uns;
+                pattern_sums([&](int i) { return v_p[i]; }, out_hi, out_lo, out_uns);
+                if (out_hi != in_hi || out_lo != in_lo || out_uns != 0) {  // (block-uniform)
+                    // the steps whose partner is less than a tile away stay inside one warp's tile (warp barriers only); the pairs of
+                    // a step are disjoint: a thread loads up to four of them before it stores any
+                    auto cmp_swap4 = [&](int t0, int stride, int cnt, int j, int k) {  // pairs t0, t0 + stride, .. (cnt <= 4 of them)
+                        int ii[4];
+                        double va[4], vb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (u < cnt) {
+                                const int t = t0 + u * stride;
+                                ii[u] = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                                va[u] = s_sort[ii[u]];
+                                vb[u] = s_sort[ii[u] | j];
+                            }
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (u < cnt && (va[u] > vb[u]) == ((ii[u] & k) == 0)) { s_sort[ii[u]] = vb[u]; s_sort[ii[u] | j] = va[u]; }
+                    };
+                    const int tile = max(64, cum_P / nwarp_), half = tile >> 1;  // (cum_P >= 64; at most one tile per warp)
+                    auto tile_steps = [&](int k, int j_from) {  // steps j_from, j_from / 2, .., 1 of stage k, every tile by one warp
+                        for (int tl = warp_; tl < cum_P / tile; tl += nwarp_)
+                            for (int j = j_from; j > 0; j >>= 1) {
+                                for (int t0 = tl * half + lane_; t0 < (tl + 1) * half; t0 += 4 * 32)
+                                    cmp_swap4(t0, 32, min(4, ((tl + 1) * half - t0 + 31) / 32), j, k);
+                                __syncwarp();
+                            }
+                    };
+                    for (int k = 2; k <= tile; k <<= 1) tile_steps(k, k >> 1);
+                    __syncthreads();
+                    for (int k = 2 * tile; k <= cum_P; k <<= 1) {
+                        for (int j = k >> 1; j >= tile; j >>= 1) {
+                            for (int t0 = tid; t0 < (cum_P >> 1); t0 += 4 * nthr) cmp_swap4(t0, nthr, min(4, ((cum_P >> 1) - t0 + nthr - 1) / nthr), j, k);
+                            __syncthreads();
+                        }
+                        tile_steps(k, half);
                         __syncthreads();
                     }
-                    tile_steps(k, tile >> 1);
+                    for (int i = tid; i < cum_P; i += nthr) v_p[i] = s_sort[i];
+                    if (a.work && tid == 0) work_add(36, 1);
                     __syncthreads();
                 }
+                cb_lap(33);
                 __shared__ int cb_head_ok;
-                if (head_parallel) {
+                {
                     // the head's sequential sums as integer prefix sums between the irregular steps (seq_cumsum.cuh): a thread owns E
                     // consecutive elements
                     const int E = max(1, cum_P / nthr), lo = min(xs, tid * E), hi = min(xs, lo + E);
                     __shared__ double cb_wd[32];
                     __shared__ long long cb_wt[32];
                     __shared__ int cb_wf[32], cb_wn[32];
-                    const double ls = seqsum::head_chunk_sum(s_v, lo, hi, 0.);
+                    const double ls = seqsum::head_chunk_sum(v_p, lo, hi, 0.);
                     double inc = ls;  // approximate sum before the chunk: warp scan + the warps before this one
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(kFull, inc, o); if (lane_ >= o) inc += t; }
@@ -3149,9 +3240,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     __syncthreads();
                     double pex = inc - ls;
                     for (int w = 0; w < warp_; w++) pex += cb_wd[w];
-                    s_endp[tid] = seqsum::head_chunk_sum(s_v, lo, hi, pex);
+                    s_endp[tid] = seqsum::head_chunk_sum(v_p, lo, hi, pex);
                     __syncthreads();
-                    const seqsum::ChunkAgg g = seqsum::head_chunk_classify(s_v, lo, hi, pex, tid > 0 ? s_endp[tid - 1] : 0., s_K, s_c);
+                    const seqsum::ChunkAgg g = seqsum::head_chunk_classify(v_p, lo, hi, pex, tid > 0 ? s_endp[tid - 1] : 0., K_p, c_p);
                     // exclusive scan of the chunk aggregates (agg_combine) over the threads
                     int f = g.has_irr, ni = g.n_irr;
                     long long tl = g.tail;
@@ -3174,41 +3265,35 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                     if (lane_ > 0) { carry_in = f1 ? t1 : pt + t1; irr_before = pn + n1; }
                     int M = 0;
                     for (int w = 0; w < nwarp_; w++) M += cb_wn[w];
-                    seqsum::head_chunk_finish(s_v, lo, hi, pex, carry_in, irr_before, s_K, s_c, s_iidx, s_ie);
+                    seqsum::head_chunk_finish(v_p, lo, hi, pex, carry_in, irr_before, K_p, c_p, s_iidx, s_ie);
                     __syncthreads();
-                    if (tid == 0) cb_head_ok = seqsum::head_stitch(s_v, s_K, s_iidx, s_ie, M, xs, s_base) ? 1 : 0;
+                    if (tid == 0) cb_head_ok = seqsum::head_stitch(v_p, K_p, s_iidx, s_ie, M, xs, s_base) ? 1 : 0;
                     __syncthreads();
                     if (cb_head_ok)  // (nothing reads the weights any more: the sums go in their place)
-                        for (int i = lo; i < hi; i++) s_v[i] = seqsum::head_value(i, s_K, s_c, s_iidx, s_ie, s_base);
+                        for (int i = lo; i < hi; i++) v_p[i] = seqsum::head_value(i, K_p, c_p, s_iidx, s_ie, s_base);
                     __syncthreads();
                 }
                 if (tid == 0) {
                     double acc = 0.;  // (0 + w == w: the reference starts with cum[0] = w[0])
-                    if (head_parallel && cb_head_ok) acc = xs > 0 ? s_v[xs - 1] : 0.;
-                    else {  // one addition after the other
-                        int i = 0;
-                        for (; i + 8 <= xs; i += 8) {  // (the loads do not wait for the chain of additions)
-                            double w8[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) w8[u] = s_v[i + u];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) { acc = acc + w8[u]; s_v[i + u] = acc; }
-                        }
-                        for (; i < xs; i++) { acc = acc + s_v[i]; s_v[i] = acc; }
+                    if (cb_head_ok) {
+                        cb_lap(34);
+                        acc = xs > 0 ? v_p[xs - 1] : 0.;
+                    } else {  // a stretch was refused: one addition after the other
+                        for (int i = 0; i < xs; i++) { acc = acc + v_p[i]; v_p[i] = acc; }
                     }
                     int ns = 0;
                     seqsum::run_segments(acc, xs, n - xs, ts_W, s_seg, ns, seqsum::kMaxSegs);
                     cb_ns = ns <= seqsum::kMaxSegs ? ns : -1;
-                    if (a.work && head_parallel) work_add(31, cb_head_ok ? 1 : 0);
+                    if (a.work) work_add(31, cb_head_ok ? 1 : 0);
                 }
                 __syncthreads();
                 const int ns = cb_ns;
-                for (int i = tid; i < xs; i += nthr) d.cum[i] = s_v[i];
+                for (int i = tid; i < xs; i += nthr) d.cum[i] = v_p[i];
                 long long *seg_g = reinterpret_cast<long long *>(a.part_d + kPartCumSegs);
                 for (int k = tid; k < 3 * max(ns, 0); k += nthr) seg_g[k] = reinterpret_cast<const long long *>(s_seg)[k];
                 if (tid == 0) {
                     a.part_ll[kPartCumSegN] = ns;
-                    if (a.work) { work_add(28, clock64() - t_cb); work_add(29, 1); work_add(30, max(ns, 0)); }
+                    if (a.work) { cb_lap(35); work_add(28, clock64() - t_cb); work_add(29, 1); work_add(30, max(ns, 0)); }
                 }
                 __syncthreads();
             };
@@ -3318,7 +3403,6 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 }
                 __syncthreads();  // s_pos is reused by the next round
             }
-            if (cum_builder && !cum_dedicated) cum_exact_build();
             if (!router || e_all == 0) {  // the simulating CTA (and routers without elements): the final plan
                 __syncthreads();
                 for (int k = tid; k < (int)(sizeof(tiesort::Plan) / sizeof(int)); k += nthr)

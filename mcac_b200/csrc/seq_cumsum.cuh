@@ -94,6 +94,14 @@ SC_HD double run_segments(double x, int i0, int cnt, double v, Seg *segs, int &n
 // Which binade a step lands in is taken from APPROXIMATE prefix sums P_i (any summation order) and verified on the exact values: every
 // stretch must start and end in the binade its elements were classified for, otherwise `head_stitch` reports failure (the caller then
 // adds the head up one by one).  A thread owns a chunk [lo, hi) of consecutive elements; `pex` = approximate sum before the chunk.
+// (the arrays are any indexable views: plain pointers, or `Padded` ones whose stride between the chunks of neighbouring threads is odd,
+// so that the threads of a warp walking their own chunks do not meet in one shared-memory bank)
+template <class T>
+struct Padded {
+    T *p;
+    SC_HD T &operator[](int i) const { return p[i + (i >> 4)]; }
+};
+SC_HD int padded_size(int n) { return n + (n >> 4) + 1; }
 constexpr int kMaxIrr = 512;                 // irregular steps a head may have (about one per binade crossed + the rare ties)
 constexpr unsigned short kIrrMark = 0xffff;
 
@@ -110,14 +118,16 @@ SC_HD ChunkAgg agg_combine(const ChunkAgg &a, const ChunkAgg &b) {
     r.n_irr = a.n_irr + b.n_irr;
     return r;
 }
-SC_HD double head_chunk_sum(const double *w, int lo, int hi, double pex) {
+template <class WA>
+SC_HD double head_chunk_sum(WA w, int lo, int hi, double pex) {
     double p = pex;
     for (int i = lo; i < hi; i++) p = p + w[i];
     return p;
 }
 // classification of a chunk; p_before = P of element lo - 1 as ITS chunk computed it (head_chunk_sum of the previous chunk).
 // K[i] = sum of k since the last irregular step inside the chunk, c[i] = kIrrMark on irregular steps.
-SC_HD ChunkAgg head_chunk_classify(const double *w, int lo, int hi, double pex, double p_before, long long *K, unsigned short *c) {
+template <class WA, class KA, class CA>
+SC_HD ChunkAgg head_chunk_classify(WA w, int lo, int hi, double pex, double p_before, KA K, CA c) {
     ChunkAgg g;
     g.has_irr = 0; g.tail = 0; g.n_irr = 0;
     double p = pex;
@@ -145,8 +155,8 @@ SC_HD ChunkAgg head_chunk_classify(const double *w, int lo, int hi, double pex, 
 }
 // carry_in / irr_before: tail and number of irregular steps of everything before the chunk.  Leaves K[i] = sum of k since the last
 // irregular step, c[i] = index of that step in the list (irr_idx, irr_e = binade its stretch was classified for).
-SC_HD void head_chunk_finish(const double *w, int lo, int hi, double pex, long long carry_in, int irr_before, long long *K, unsigned short *c,
-                             int *irr_idx, int *irr_e) {
+template <class WA, class KA, class CA>
+SC_HD void head_chunk_finish(WA w, int lo, int hi, double pex, long long carry_in, int irr_before, KA K, CA c, int *irr_idx, int *irr_e) {
     int m = irr_before - 1;
     bool seen = false;
     double p = pex;
@@ -161,7 +171,8 @@ SC_HD void head_chunk_finish(const double *w, int lo, int hi, double pex, long l
     }
 }
 // one thread: the exact sums at the M irregular steps; false = a stretch is not where the approximate sums put it
-SC_HD bool head_stitch(const double *w, const long long *K, const int *irr_idx, const int *irr_e, int M, int xs, double *base) {
+template <class WA, class KA>
+SC_HD bool head_stitch(WA w, KA K, const int *irr_idx, const int *irr_e, int M, int xs, double *base) {
     if (M > kMaxIrr) return false;
     double s = 0.;
     for (int m = 0; m < M; m++) {
@@ -177,7 +188,8 @@ SC_HD bool head_stitch(const double *w, const long long *K, const int *irr_idx, 
     }
     return true;
 }
-SC_HD double head_value(int i, const long long *K, const unsigned short *c, const int *irr_idx, const int *irr_e, const double *base) {
+template <class KA, class CA>
+SC_HD double head_value(int i, KA K, CA c, const int *irr_idx, const int *irr_e, const double *base) {
     const int m = c[i];
     if (irr_idx[m] == i) return base[m];
     return fma((double)K[i], ldexp(1.0, irr_e[m] - 52), base[m]);

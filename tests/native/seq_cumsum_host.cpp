@@ -57,13 +57,31 @@ static long long check_run(double x0, int i0, int cnt, double v, long long &segs
 // The head of the table (seqsum::head_*): the chunked integer-prefix form, run the way a CTA of `T` threads runs it (the scans across
 // chunks are serial here), against the plain loop.  `jitter`: relative perturbation of the approximate sums before the chunks (another
 // summation order); whatever they are, a head that `head_stitch` accepts must be the sequential sum bit for bit.
+template <class WA, class KA, class CA>
+static int check_head_on(const std::vector<double> &w0, WA w, KA K, CA c, int T, double jitter, long long &fails, long long &irr_max);
 static int check_head(const std::vector<double> &w, int T, double jitter, long long &fails, long long &irr_max) {
     const int xs = (int)w.size();
+    if (T == 512) {  // the device's layout: padded views
+        const int pn = seqsum::padded_size(xs + 1);
+        std::vector<double> wp(pn);
+        std::vector<long long> Kp(pn);
+        std::vector<unsigned short> cp(pn);
+        seqsum::Padded<double> wv{wp.data()};
+        for (int i = 0; i < xs; i++) wv[i] = w[i];
+        return check_head_on(w, wv, seqsum::Padded<long long>{Kp.data()}, seqsum::Padded<unsigned short>{cp.data()}, T, jitter, fails, irr_max);
+    }
+    std::vector<double> wc(w);
+    wc.push_back(0.);
+    std::vector<long long> K(xs + 1);
+    std::vector<unsigned short> c(xs + 1);
+    return check_head_on(w, wc.data(), K.data(), c.data(), T, jitter, fails, irr_max);
+}
+template <class WA, class KA, class CA>
+static int check_head_on(const std::vector<double> &w0, WA w, KA K, CA c, int T, double jitter, long long &fails, long long &irr_max) {
+    const int xs = (int)w0.size();
     int P = 1;
     while (P < xs) P <<= 1;
     const int E = std::max(1, P / T);
-    std::vector<long long> K(xs + 1);
-    std::vector<unsigned short> c(xs + 1);
     std::vector<int> irr_idx(seqsum::kMaxIrr), irr_e(seqsum::kMaxIrr);
     std::vector<double> base(seqsum::kMaxIrr), pex(T + 1), endP(T + 1);
     std::vector<seqsum::ChunkAgg> agg(T);
@@ -71,27 +89,27 @@ static int check_head(const std::vector<double> &w, int T, double jitter, long l
     for (int t = 0; t < T; t++) {
         const int lo = std::min(xs, t * E), hi = std::min(xs, lo + E);
         pex[t] = run * (1.0 + jitter * ((double)(rng() % 2001) - 1000.0) / 1000.0);
-        run = run + seqsum::head_chunk_sum(w.data(), lo, hi, 0.);
-        endP[t] = seqsum::head_chunk_sum(w.data(), lo, hi, pex[t]);
+        run = run + seqsum::head_chunk_sum(w, lo, hi, 0.);
+        endP[t] = seqsum::head_chunk_sum(w, lo, hi, pex[t]);
     }
     for (int t = 0; t < T; t++) {
         const int lo = std::min(xs, t * E), hi = std::min(xs, lo + E);
-        agg[t] = seqsum::head_chunk_classify(w.data(), lo, hi, pex[t], t > 0 ? endP[t - 1] : 0., K.data(), c.data());
+        agg[t] = seqsum::head_chunk_classify(w, lo, hi, pex[t], t > 0 ? endP[t - 1] : 0., K, c);
     }
     seqsum::ChunkAgg acc;
     acc.has_irr = 0; acc.tail = 0; acc.n_irr = 0;
     for (int t = 0; t < T; t++) {
         const int lo = std::min(xs, t * E), hi = std::min(xs, lo + E);
-        seqsum::head_chunk_finish(w.data(), lo, hi, pex[t], acc.tail, acc.n_irr, K.data(), c.data(), irr_idx.data(), irr_e.data());
+        seqsum::head_chunk_finish(w, lo, hi, pex[t], acc.tail, acc.n_irr, K, c, irr_idx.data(), irr_e.data());
         acc = seqsum::agg_combine(acc, agg[t]);
     }
     const int M = acc.n_irr;
     if (M > irr_max) irr_max = M;
-    if (!seqsum::head_stitch(w.data(), K.data(), irr_idx.data(), irr_e.data(), M, xs, base.data())) { fails++; return 0; }
+    if (!seqsum::head_stitch(w, K, irr_idx.data(), irr_e.data(), M, xs, base.data())) { fails++; return 0; }
     double s = 0.;
     for (int i = 0; i < xs; i++) {
-        s = s + w[i];
-        const double got = seqsum::head_value(i, K.data(), c.data(), irr_idx.data(), irr_e.data(), base.data());
+        s = s + w0[i];
+        const double got = seqsum::head_value(i, K, c, irr_idx.data(), irr_e.data(), base.data());
         if (bits(got) != bits(s)) {
             std::printf("FAIL: head entry %d of %d: %a, sequential %a (T=%d jitter=%g M=%d)\n", i, xs, got, s, T, jitter, M);
             return -1;
