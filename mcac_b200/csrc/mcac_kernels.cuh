@@ -2738,35 +2738,6 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long *sm) {
     return t;
 }
 
-// One pass of a bitonic sorting network over v[0, P) (P a power of two), stage k: the G steps whose partners are 2^(b+G-1) .. 2^b apart.
-// The 2^G entries base | (m << b) are closed under those steps: a thread takes them through all G steps in registers — one load and
-// one store per entry and pass instead of one per step (the network is bound by shared-memory bandwidth).  Barrier between passes.
-template <int G>
-__device__ __forceinline__ void bitonic_pass(const seqsum::Padded<double> &v, int P, int k, int b, int tid, int nthr) {
-    constexpr int NG = 1 << G;
-    for (int q = tid; q < (P >> G); q += nthr) {
-        const int base = ((q >> b) << (b + G)) | (q & ((1 << b) - 1));
-        const bool asc = (base & k) == 0;  // (k lies above every bit the group varies)
-        double r[NG];
-#pragma unroll
-        for (int m = 0; m < NG; m++) r[m] = v[base | (m << b)];
-#pragma unroll
-        for (int st = G - 1; st >= 0; st--) {
-#pragma unroll
-            for (int m = 0; m < NG; m++) {
-                if ((m & (1 << st)) == 0) {
-                    const double x = r[m], y = r[m | (1 << st)];
-                    const bool sw = (x > y) == asc;
-                    r[m] = sw ? y : x;
-                    r[m | (1 << st)] = sw ? x : y;
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < NG; m++) v[base | (m << b)] = r[m];
-    }
-}
-
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d, EventArgs a) {
     cgx::grid_group grid = cgx::this_grid();
@@ -3174,9 +3145,9 @@ __global__ void __launch_bounds__(kEventThreads, kMinBlocks) k_event(DevState d,
                 for (int k = 2, lg = 1; k <= cum_P; k <<= 1, lg++)
                     for (int top = lg - 1; top >= 0;) {
                         const int g = min(3, top + 1), bb = top - g + 1;
-                        if (g == 3) bitonic_pass<3>(v_p, cum_P, k, bb, tid, nthr);
-                        else if (g == 2) bitonic_pass<2>(v_p, cum_P, k, bb, tid, nthr);
-                        else bitonic_pass<1>(v_p, cum_P, k, bb, tid, nthr);
+                        if (g == 3) seqsum::bitonic_pass<3>(v_p, cum_P, k, bb, tid, nthr);
+                        else if (g == 2) seqsum::bitonic_pass<2>(v_p, cum_P, k, bb, tid, nthr);
+                        else seqsum::bitonic_pass<1>(v_p, cum_P, k, bb, tid, nthr);
                         __syncthreads();
                         top -= g;
                     }

@@ -195,4 +195,34 @@ SC_HD double head_value(int i, KA K, CA c, const int *irr_idx, const int *irr_e,
     return fma((double)K[i], ldexp(1.0, irr_e[m] - 52), base[m]);
 }
 
+// ---- sorting the head's weights ------------------------------------------------------------------------------------------
+// One pass of a bitonic sorting network over v[0, P) (P a power of two), stage k: the G steps whose partners are 2^(b+G-1) .. 2^b apart.
+// The 2^G entries base | (m << b) are closed under those steps: a thread takes them through all G steps in registers — one load and
+// one store per entry and pass instead of one per step (the network is bound by shared-memory bandwidth).  Barrier between passes.
+template <int G, class VA>
+SC_HD void bitonic_pass(const VA &v, int P, int k, int b, int tid, int nthr) {
+    constexpr int NG = 1 << G;
+    for (int q = tid; q < (P >> G); q += nthr) {
+        const int base = ((q >> b) << (b + G)) | (q & ((1 << b) - 1));
+        const bool asc = (base & k) == 0;  // (k lies above every bit the group varies)
+        double r[NG];
+#pragma unroll
+        for (int m = 0; m < NG; m++) r[m] = v[base | (m << b)];
+#pragma unroll
+        for (int st = G - 1; st >= 0; st--) {
+#pragma unroll
+            for (int m = 0; m < NG; m++) {
+                if ((m & (1 << st)) == 0) {
+                    const double x = r[m], y = r[m | (1 << st)];
+                    const bool sw = (x > y) == asc;
+                    r[m] = sw ? y : x;
+                    r[m | (1 << st)] = sw ? x : y;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NG; m++) v[base | (m << b)] = r[m];
+    }
+}
+
 }  // namespace seqsum

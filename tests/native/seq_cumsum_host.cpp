@@ -148,6 +148,34 @@ static int head_cases(int cases, long long &entries) {
     return 0;
 }
 
+// seqsum::bitonic_pass (the building CTA's sort): the passes in the order k_event issues them, every thread of a 512-thread CTA one
+// after the other between two barriers, on the padded view; must leave the array sorted with its +inf padding behind.
+static int sort_cases(int cases) {
+    for (int cidx = 0; cidx < cases; cidx++) {
+        int P = 64 << (cidx % 8);  // 64 .. 8192
+        const int xs = (int)(rng() % (P + 1)), nthr = 512;
+        std::vector<double> plain(P, INFINITY), pad(seqsum::padded_size(P));
+        for (int i = 0; i < xs; i++) plain[i] = (cidx % 3 == 0) ? (double)(rng() % 50) : random_weight();
+        seqsum::Padded<double> v{pad.data()};
+        for (int i = 0; i < P; i++) v[i] = plain[i];
+        for (int k = 2, lg = 1; k <= P; k <<= 1, lg++)
+            for (int top = lg - 1; top >= 0;) {
+                const int g = std::min(3, top + 1), bb = top - g + 1;
+                for (int tid = 0; tid < nthr; tid++) {
+                    if (g == 3) seqsum::bitonic_pass<3>(v, P, k, bb, tid, nthr);
+                    else if (g == 2) seqsum::bitonic_pass<2>(v, P, k, bb, tid, nthr);
+                    else seqsum::bitonic_pass<1>(v, P, k, bb, tid, nthr);
+                }
+                top -= g;
+            }
+        std::sort(plain.begin(), plain.end());
+        for (int i = 0; i < P; i++)
+            if (bits(v[i]) != bits(plain[i])) { std::printf("FAIL: bitonic passes, P = %d, entry %d\n", P, i); return 1; }
+    }
+    std::printf("sort: %d tables of 64 .. 8192 entries\n", cases);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     const int cases = argc > 1 ? std::atoi(argv[1]) : 200;
     rng.seed(argc > 2 ? std::strtoull(argv[2], nullptr, 10) : 1);
@@ -179,5 +207,6 @@ int main(int argc, char **argv) {
     }
     std::printf("ok %d cases, %lld entries, at most %lld segments per run\n", cases, entries, segs_max);
     if (head_cases(cases, entries)) return 1;
+    if (sort_cases(std::min(cases, 160))) return 1;
     return 0;
 }

@@ -39,10 +39,13 @@ def test_enclosing_ball_pruning_never_drops_a_finite_pair(tmp_path):
 
 def test_seq_cumsum_header_is_the_sequential_sum(tmp_path):
     """mcac_b200/csrc/seq_cumsum.cuh (cumulative_time_steps over a run of equal weights in closed form, aggregat_list.cpp:131-140)
-    against the plain loop cum[i] = cum[i-1] + w, every entry bit for bit, incl. round-to-even ties and binade crossings."""
+    against the plain loop cum[i] = cum[i-1] + w, every entry bit for bit, incl. round-to-even ties and binade crossings; the head of
+    lighter weights as integer prefix sums between irregular steps (chunked the way a 512-thread CTA runs it, on the padded views, with
+    perturbed approximate sums: accepted heads must be exact); and the building CTA's sort passes (bitonic_pass) in k_event's order."""
     exe = tmp_path / "seq_cumsum_host"
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", str(exe), str(ROOT / "tests" / "native" / "seq_cumsum_host.cpp")])
     for seed in (1, 9):
         out = subprocess.run([str(exe), "600", str(seed)], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
         assert out.stdout.startswith("ok 600 cases"), out.stdout
+        assert "head: 600 cases" in out.stdout and "sort: 160 tables" in out.stdout, out.stdout
