@@ -11,21 +11,11 @@
 
 #include <cmath>
 
+#include "../csrc/mcac_math.cuh"
+
 namespace mcac {
 namespace {
-// inverfc / inverf, src/tools/tools.cpp:56-77 (Numerical-Recipes style: rational start + 2 Halley steps)
-double inverse_erfc(double p) {
-    if (p >= 2.) return -100.;
-    if (p <= 0.0) return 100.;
-    const double pp = (p < 1.0) ? p : 2. - p;
-    const double t = std::sqrt(-2. * std::log(pp / 2.));
-    double x = -0.70711 * ((2.30753 + t * 0.27061) / (1. + t * (0.99229 + t * 0.04481)) - t);
-    for (int it = 0; it < 2; it++) {
-        const double err = std::erfc(x) - pp;
-        x += err / (1.12837916709551257 * std::exp(-(x * x)) - x * err);
-    }
-    return (p < 1.0 ? x : -x);
-}
+using mcacb::inverse_erfc;  // inverfc / inverf of src/tools/tools.cpp:56-77: the one restatement, shared with the device (csrc/mcac_math.cuh)
 
 struct Grid {  // periodic hash grid of placed monomers
     int n = 1;
