@@ -195,6 +195,15 @@ int main(int argc, char **argv) {
         if (r < 0) return 1;
         entries += r;
     }
+    // every short-mantissa weight against every short-mantissa start: all the round-to-even situations of the first binades, and
+    // (scaled starts) of binades far above the weight, where most steps are ties or stagnate
+    for (int m = 1; m <= 96; m++)
+        for (int j = 0; j <= 96; j++)
+            for (int sh = 0; sh <= 54; sh += 6) {
+                const long long r = check_run(std::ldexp((double)j, sh - 5), 7, 700, std::ldexp((double)m, -5), segs_max);
+                if (r < 0) return 1;
+                entries += r;
+            }
     // the shape the pick table has: a head of lighter weights summed one by one, then ~10^6 copies of the largest weight
     for (int c = 0; c < 8; c++) {
         const double W = random_weight();
